@@ -1,0 +1,95 @@
+"""ctypes binding of libcontextgs_b200.so (the C ABI in include/contextgs_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcontextgs_b200.so")
+
+c_void_p, c_int, c_int64, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+
+
+class RasterSettings(ctypes.Structure):
+    """struct cgs_raster_settings"""
+    _fields_ = [
+        ("image_height", ctypes.c_int32),
+        ("image_width", ctypes.c_int32),
+        ("tanfovx", ctypes.c_float),
+        ("tanfovy", ctypes.c_float),
+        ("bg", ctypes.c_float * 3),
+        ("scale_modifier", ctypes.c_float),
+        ("viewmatrix", ctypes.c_float * 16),
+        ("projmatrix", ctypes.c_float * 16),
+        ("sh_degree", ctypes.c_int32),
+        ("campos", ctypes.c_float * 3),
+        ("prefiltered", ctypes.c_int32),
+        ("debug", ctypes.c_int32),
+    ]
+
+
+STATUS_NUM_RENDERED, STATUS_OVERFLOW, STATUS_NUM_SORTED, STATUS_WORDS = 0, 1, 2, 8
+GEOM_STRIDE = 12
+
+# name -> (restype, argtypes); every symbol declared in include/contextgs_b200.h
+_PTR = c_void_p
+SIGNATURES = {
+    "cgs_abi_version": (c_int, []),
+    "cgs_last_error": (ctypes.c_char_p, []),
+    "cgs_visible_filter": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR]),
+    "cgs_mark_visible": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR]),
+    "cgs_raster_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int]),
+    "cgs_rasterize_forward": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, c_int64, _PTR, _PTR, _PTR, _PTR, _PTR,
+                                      _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
+    "cgs_raster_backward_workspace_bytes": (c_size_t, [c_int]),
+    "cgs_rasterize_backward": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
+                                       _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
+    "cgs_sort_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "cgs_sort_pairs_u32": (c_int, [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, c_int64, c_int, c_int, _PTR, c_size_t,
+                                   _PTR]),
+}
+
+_lib = None
+
+
+class CgsError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CgsError(
+                f"{LIB_PATH} is missing: build it with `python -m contextgs_b200.build` "
+                "(there is no CPU or PyTorch fallback for the contextgs_b200 hot path)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the ABI and this table disagree
+            fn.restype = res
+            fn.argtypes = args
+        if L.cgs_abi_version() != 1:
+            raise CgsError("libcontextgs_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(code, what=""):
+    if code != 0:
+        msg = lib().cgs_last_error()
+        raise CgsError(f"{what} failed with code {code}: {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL).  The tensor must be contiguous."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "contextgs_b200 kernels need contiguous tensors"
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

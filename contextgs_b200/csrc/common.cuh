@@ -1,0 +1,95 @@
+// Shared helpers for the contextgs_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/contextgs_b200.h"
+
+namespace cgs {
+
+constexpr int kTile = CGS_TILE;
+constexpr int kTilePixels = kTile * kTile;
+constexpr int kGeomStride = CGS_GEOM_STRIDE;
+constexpr int kNumSMs = 148;  // B200
+
+// geom record slots
+enum { G_X = 0, G_Y, G_CA, G_CB, G_CC, G_OP, G_R, G_G, G_B, G_DEPTH, G_RADIUS, G_TILES };
+
+void set_error(const char *fmt, ...);
+int check_launch(const char *what);
+
+#define CGS_CHECK_PTR(p)                                   \
+    do {                                                   \
+        if ((p) == nullptr) {                              \
+            cgs::set_error("%s: null pointer " #p, __func__); \
+            return -1;                                     \
+        }                                                  \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Camera constants passed by value to kernels (lives in the constant bank).
+struct CamParams {
+    float view[16];
+    float proj[16];
+    float tanfovx, tanfovy;
+    float focal_x, focal_y;
+    float scale_modifier;
+    int W, H, grid_x, grid_y;
+    float bg[3];
+};
+
+static inline CamParams make_cam(const cgs_raster_settings *s)
+{
+    CamParams c;
+    for (int i = 0; i < 16; ++i) {
+        c.view[i] = s->viewmatrix[i];
+        c.proj[i] = s->projmatrix[i];
+    }
+    c.tanfovx = s->tanfovx;
+    c.tanfovy = s->tanfovy;
+    c.W = s->image_width;
+    c.H = s->image_height;
+    c.focal_x = (float)c.W / (2.0f * c.tanfovx);
+    c.focal_y = (float)c.H / (2.0f * c.tanfovy);
+    c.scale_modifier = s->scale_modifier;
+    c.grid_x = (c.W + kTile - 1) / kTile;
+    c.grid_y = (c.H + kTile - 1) / kTile;
+    for (int i = 0; i < 3; ++i) c.bg[i] = s->bg[i];
+    return c;
+}
+
+__device__ __forceinline__ void get_rect(float px, float py, int radius, int gx, int gy, int &x0, int &y0, int &x1,
+                                         int &y1)
+{
+    float r = (float)radius;
+    x0 = min(gx, max(0, (int)((px - r) / (float)kTile)));
+    y0 = min(gy, max(0, (int)((py - r) / (float)kTile)));
+    x1 = min(gx, max(0, (int)((px + r + (float)(kTile - 1)) / (float)kTile)));
+    y1 = min(gy, max(0, (int)((py + r + (float)(kTile - 1)) / (float)kTile)));
+}
+
+// ---- sort / scan primitives (radix_sort.cu) -------------------------------------------
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per CTA
+
+struct SortPlan {
+    int npass;
+    int64_t tiles_cap;
+    size_t hist_off, lookback_off, ticket_off, zero_bytes, total_bytes;
+};
+SortPlan make_sort_plan(int64_t n_cap, int begin_bit, int end_bit);
+
+// Enqueue a stable LSD sort.  `ws` must hold plan.total_bytes; its first plan.zero_bytes are
+// expected to be ZERO on entry (sort_pairs zeroes them itself when zero_ws is true).
+// The final pass writes to (keys_out, vals_out); passes ping-pong through (keys_tmp, vals_tmp).
+int sort_pairs(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
+               uint32_t *keys_tmp, uint32_t *vals_tmp, const uint32_t *n_dev, int64_t n_cap, int begin_bit,
+               int end_bit, void *ws, bool zero_ws, cudaStream_t stream);
+
+}  // namespace cgs

@@ -1,0 +1,273 @@
+// C-ABI entry points of the rasterizer (include/contextgs_b200.h) and the error plumbing.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cgs {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char *what)
+{
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+        return -100 - (int)e;
+    }
+    return 0;
+}
+
+// launchers defined in the kernel translation units
+void launch_preprocess(const CamParams &, int, const float *, const float *, const float *, const float *,
+                       const float *, int32_t *, float *, uint32_t *, cudaStream_t);
+void launch_filter(const CamParams &, int, const float *, const float *, const float *, int32_t *, cudaStream_t);
+void launch_mark_visible(const CamParams &, int, const float *, uint8_t *, cudaStream_t);
+void launch_preprocess_backward(const CamParams &, int, const float *, const float *, const float *, const int32_t *,
+                                const float *, float *, float *, float *, float *, float *, float *, cudaStream_t);
+void launch_scan_tiles(const uint32_t *, const float *, int, int64_t, uint32_t *, unsigned long long *, uint32_t *,
+                       int32_t *, cudaStream_t);
+void launch_emit_instances(const uint32_t *, const float *, const uint32_t *, int, int, int, int64_t, uint32_t *,
+                           uint32_t *, cudaStream_t);
+void launch_tile_ranges(const uint32_t *, const int32_t *, int64_t, uint32_t *, cudaStream_t);
+int scan_tiles_count(int P);
+void launch_render_forward(const CamParams &, const uint32_t *, const uint32_t *, const float *, float *, float *,
+                           uint32_t *, cudaStream_t);
+void launch_render_backward(const CamParams &, const uint32_t *, const uint32_t *, const float *, const float *,
+                            const uint32_t *, const float *, float *, cudaStream_t);
+
+__global__ void set_u32_kernel(uint32_t *p, uint32_t v) { *p = v; }
+
+static int tile_bits(int tiles)
+{
+    int b = 1;
+    while ((1 << b) < tiles) ++b;
+    return b;
+}
+
+// Workspace layout of the forward pass.  Everything that must start at zero is grouped at the
+// front so that one memset covers it.
+struct RasterPlan {
+    SortPlan depth_sort, tile_sort;
+    size_t depth_ws_off, tile_ws_off, scan_state_off, scan_ticket_off, zero_bytes;
+    size_t depth_keys_off[3], depth_vals_off[2], offsets_off;  // keys: in / tmp / out ; vals: tmp / out
+    size_t tile_keys_off[3], tile_vals_off[2];                 // keys: in / tmp / out ; vals: in / tmp
+    size_t total;
+    int tbits;
+};
+
+static RasterPlan make_plan(int P, int64_t R_cap, int W, int H)
+{
+    RasterPlan p;
+    const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
+    p.tbits = tile_bits(gx * gy);
+    const int64_t Pc = P > 0 ? P : 1, Rc = R_cap > 0 ? R_cap : 1;
+    p.depth_sort = make_sort_plan(Pc, 0, 32);
+    p.tile_sort = make_sort_plan(Rc, 0, p.tbits);
+    size_t off = 0;
+    p.depth_ws_off = off;
+    off += p.depth_sort.total_bytes;
+    p.tile_ws_off = off;
+    off += p.tile_sort.total_bytes;
+    p.scan_state_off = off;
+    off += align_up((size_t)scan_tiles_count((int)Pc) * sizeof(unsigned long long));
+    p.scan_ticket_off = off;
+    off += align_up(4 * sizeof(uint32_t));
+    p.zero_bytes = off;
+    for (int i = 0; i < 3; ++i) {
+        p.depth_keys_off[i] = off;
+        off += align_up((size_t)Pc * 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+        p.depth_vals_off[i] = off;
+        off += align_up((size_t)Pc * 4);
+    }
+    p.offsets_off = off;
+    off += align_up((size_t)Pc * 4);
+    for (int i = 0; i < 3; ++i) {
+        p.tile_keys_off[i] = off;
+        off += align_up((size_t)Rc * 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+        p.tile_vals_off[i] = off;
+        off += align_up((size_t)Rc * 4);
+    }
+    p.total = off;
+    return p;
+}
+
+}  // namespace cgs
+
+using namespace cgs;
+
+extern "C" int cgs_abi_version(void) { return CGS_ABI_VERSION; }
+extern "C" const char *cgs_last_error(void) { return g_error; }
+
+static int validate_settings(const cgs_raster_settings *s, const char *fn)
+{
+    if (!s) {
+        set_error("%s: null settings", fn);
+        return -1;
+    }
+    if (s->image_width <= 0 || s->image_height <= 0) {
+        set_error("%s: invalid image size %dx%d", fn, s->image_width, s->image_height);
+        return -2;
+    }
+    if ((int64_t)((s->image_width + kTile - 1) / kTile) * ((s->image_height + kTile - 1) / kTile) > (1 << 30)) {
+        set_error("%s: too many tiles", fn);
+        return -2;
+    }
+    return 0;
+}
+
+extern "C" int cgs_visible_filter(const cgs_raster_settings *s, int N, const float *means3D, const float *scales,
+                                  const float *rotations, int32_t *radii, void *stream)
+{
+    if (int e = validate_settings(s, __func__)) return e;
+    if (N <= 0) return 0;
+    CGS_CHECK_PTR(means3D);
+    CGS_CHECK_PTR(scales);
+    CGS_CHECK_PTR(rotations);
+    CGS_CHECK_PTR(radii);
+    launch_filter(make_cam(s), N, means3D, scales, rotations, radii, static_cast<cudaStream_t>(stream));
+    return check_launch(__func__);
+}
+
+extern "C" int cgs_mark_visible(const cgs_raster_settings *s, int N, const float *means3D, uint8_t *visible,
+                                void *stream)
+{
+    if (int e = validate_settings(s, __func__)) return e;
+    if (N <= 0) return 0;
+    CGS_CHECK_PTR(means3D);
+    CGS_CHECK_PTR(visible);
+    launch_mark_visible(make_cam(s), N, means3D, visible, static_cast<cudaStream_t>(stream));
+    return check_launch(__func__);
+}
+
+extern "C" size_t cgs_raster_workspace_bytes(int P, int64_t R_cap, int W, int H)
+{
+    return make_plan(P, R_cap, W, H).total;
+}
+
+extern "C" int cgs_rasterize_forward(const cgs_raster_settings *s, int P, const float *means3D, const float *colors,
+                                     const float *opacities, const float *scales, const float *rotations,
+                                     int64_t R_cap, float *out_color, int32_t *radii, float *geom,
+                                     uint32_t *point_list, uint32_t *ranges, float *final_T, uint32_t *n_contrib,
+                                     int32_t *status, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (int e = validate_settings(s, __func__)) return e;
+    CGS_CHECK_PTR(out_color);
+    CGS_CHECK_PTR(ranges);
+    CGS_CHECK_PTR(final_T);
+    CGS_CHECK_PTR(n_contrib);
+    CGS_CHECK_PTR(status);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const CamParams cam = make_cam(s);
+    const int tiles = cam.grid_x * cam.grid_y;
+    if (P < 0 || R_cap < 0) {
+        set_error("%s: negative size", __func__);
+        return -2;
+    }
+    cudaMemsetAsync(status, 0, CGS_STATUS_WORDS * sizeof(int32_t), st);
+    cudaMemsetAsync(ranges, 0, (size_t)tiles * 2 * sizeof(uint32_t), st);
+    if (P > 0) {
+        CGS_CHECK_PTR(means3D);
+        CGS_CHECK_PTR(colors);
+        CGS_CHECK_PTR(opacities);
+        CGS_CHECK_PTR(scales);
+        CGS_CHECK_PTR(rotations);
+        CGS_CHECK_PTR(radii);
+        CGS_CHECK_PTR(geom);
+        CGS_CHECK_PTR(workspace);
+        if (R_cap > 0) CGS_CHECK_PTR(point_list);
+        const RasterPlan plan = make_plan(P, R_cap, cam.W, cam.H);
+        if (workspace_bytes < plan.total) {
+            set_error("%s: workspace %zu < %zu bytes", __func__, workspace_bytes, plan.total);
+            return -3;
+        }
+        char *ws = static_cast<char *>(workspace);
+        cudaMemsetAsync(ws, 0, plan.zero_bytes, st);
+        auto u32 = [&](size_t off) { return reinterpret_cast<uint32_t *>(ws + off); };
+        uint32_t *dkeys_in = u32(plan.depth_keys_off[0]), *dkeys_tmp = u32(plan.depth_keys_off[1]);
+        uint32_t *dkeys_out = u32(plan.depth_keys_off[2]);
+        uint32_t *dvals_tmp = u32(plan.depth_vals_off[0]), *order = u32(plan.depth_vals_off[1]);
+        uint32_t *offsets = u32(plan.offsets_off);
+        uint32_t *tkeys_in = u32(plan.tile_keys_off[0]), *tkeys_tmp = u32(plan.tile_keys_off[1]);
+        uint32_t *tkeys_out = u32(plan.tile_keys_off[2]);
+        uint32_t *tvals_in = u32(plan.tile_vals_off[0]), *tvals_tmp = u32(plan.tile_vals_off[1]);
+        unsigned long long *scan_state = reinterpret_cast<unsigned long long *>(ws + plan.scan_state_off);
+        uint32_t *scan_ticket = reinterpret_cast<uint32_t *>(ws + plan.scan_ticket_off);
+        // the element count of the depth sort is P (host-known); park it in the zeroed ticket block
+        uint32_t *p_dev = scan_ticket + 1;
+        set_u32_kernel<<<1, 1, 0, st>>>(p_dev, (uint32_t)P);
+
+        launch_preprocess(cam, P, means3D, colors, opacities, scales, rotations, radii, geom, dkeys_in, st);
+        // 1. Gaussians by depth (value = Gaussian id, implicit iota on the first pass)
+        if (int e = sort_pairs(dkeys_in, nullptr, dkeys_out, order, dkeys_tmp, dvals_tmp, p_dev, P, 0, 32,
+                               ws + plan.depth_ws_off, false, st))
+            return e;
+        // 2. instance offsets in depth order, R stays on the device
+        launch_scan_tiles(order, geom, P, R_cap, offsets, scan_state, scan_ticket, status, st);
+        if (R_cap > 0) {
+            // 3. emit (tile, id)
+            launch_emit_instances(order, geom, offsets, P, cam.grid_x, cam.grid_y, R_cap, tkeys_in, tvals_in, st);
+            // 4. stable sort by tile id; last pass writes the ids straight into point_list
+            const uint32_t *n_sorted = reinterpret_cast<const uint32_t *>(status + CGS_STATUS_NUM_SORTED);
+            if (int e = sort_pairs(tkeys_in, tvals_in, tkeys_out, point_list, tkeys_tmp, tvals_tmp, n_sorted, R_cap, 0,
+                                   plan.tbits, ws + plan.tile_ws_off, false, st))
+                return e;
+            launch_tile_ranges(tkeys_out, status, R_cap, ranges, st);
+        }
+    }
+    launch_render_forward(cam, ranges, point_list, geom, out_color, final_T, n_contrib, st);
+    return check_launch(__func__);
+}
+
+extern "C" size_t cgs_raster_backward_workspace_bytes(int P) { return align_up((size_t)(P > 0 ? P : 1) * 9 * 4); }
+
+extern "C" int cgs_rasterize_backward(const cgs_raster_settings *s, int P, const float *means3D, const float *scales,
+                                      const float *rotations, const int32_t *radii, const float *geom,
+                                      const uint32_t *point_list, const uint32_t *ranges, const float *final_T,
+                                      const uint32_t *n_contrib, const float *dL_dpix, float *dL_dmeans3D,
+                                      float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity, float *dL_dscales,
+                                      float *dL_drots, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (int e = validate_settings(s, __func__)) return e;
+    if (P <= 0) return 0;
+    CGS_CHECK_PTR(means3D);
+    CGS_CHECK_PTR(scales);
+    CGS_CHECK_PTR(rotations);
+    CGS_CHECK_PTR(radii);
+    CGS_CHECK_PTR(geom);
+    CGS_CHECK_PTR(ranges);
+    CGS_CHECK_PTR(final_T);
+    CGS_CHECK_PTR(n_contrib);
+    CGS_CHECK_PTR(dL_dpix);
+    CGS_CHECK_PTR(dL_dmeans3D);
+    CGS_CHECK_PTR(dL_dmeans2D);
+    CGS_CHECK_PTR(dL_dcolors);
+    CGS_CHECK_PTR(dL_dopacity);
+    CGS_CHECK_PTR(dL_dscales);
+    CGS_CHECK_PTR(dL_drots);
+    CGS_CHECK_PTR(workspace);
+    if (workspace_bytes < cgs_raster_backward_workspace_bytes(P)) {
+        set_error("%s: workspace too small", __func__);
+        return -3;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const CamParams cam = make_cam(s);
+    float *acc = static_cast<float *>(workspace);
+    cudaMemsetAsync(acc, 0, (size_t)P * 9 * sizeof(float), st);
+    launch_render_backward(cam, ranges, point_list, geom, final_T, n_contrib, dL_dpix, acc, st);
+    launch_preprocess_backward(cam, P, means3D, scales, rotations, radii, acc, dL_dmeans3D, dL_dmeans2D, dL_dcolors,
+                               dL_dopacity, dL_dscales, dL_drots, st);
+    return check_launch(__func__);
+}

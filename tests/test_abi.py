@@ -1,0 +1,45 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/*.h declares."""
+import ctypes
+import glob
+import os
+import re
+
+from contextgs_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        src = open(h).read()
+        names |= set(re.findall(r"CGS_API[^;(]*?\b(cgs_\w+)\s*\(", src))
+    return names
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    build.build_library()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    decl = declared_symbols()
+    assert len(decl) >= 10
+    for name in decl:
+        assert hasattr(L, name), f"{name} declared in include/ but not exported"
+    # the ctypes signature table covers exactly the declared ABI
+    assert set(_lib.SIGNATURES) == decl
+    assert _lib.lib().cgs_abi_version() == 1
+
+
+def test_settings_struct_layout_matches_header():
+    # 2 ints + 2 floats + 3 + 1 + 16 + 16 floats + int + 3 floats + 2 ints = 46 words
+    assert ctypes.sizeof(_lib.RasterSettings) == 46 * 4
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libcontextgs_b200.so")
+    try:
+        _lib.lib()
+    except _lib.CgsError as e:
+        assert "no CPU or PyTorch fallback" in str(e)
+    else:
+        raise AssertionError("expected CgsError")
