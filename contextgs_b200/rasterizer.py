@@ -7,6 +7,7 @@ gaussian_renderer/__init__.py:20 and drives at :179-205 (render) and :250-285 (p
 the C ABI (include/contextgs_b200.h); torch only provides memory, the stream and autograd glue.
 """
 import os
+import weakref
 from typing import NamedTuple
 
 import torch
@@ -32,22 +33,27 @@ class GaussianRasterizationSettings(NamedTuple):
 
 # ------------------------------------------------------------------ host-side caches
 
-_host_cache = {}  # (data_ptr, version, numel) -> tuple of floats (camera matrices live on the GPU)
+_host_cache = {}  # id(tensor) -> (weakref, version, floats); camera matrices live on the GPU
 
 
 def _host_floats(t, n):
+    """Host copy of a small device tensor, cached per tensor OBJECT (weakref + version checked, so a
+    recycled address or an in-place update can never return stale values)."""
     if not torch.is_tensor(t):
         vals = tuple(float(v) for v in t)
         assert len(vals) == n
         return vals
-    key = (t.data_ptr(), t._version, t.numel(), str(t.device))
-    v = _host_cache.get(key)
-    if v is None:
+    ent = _host_cache.get(id(t))
+    if ent is not None and ent[0]() is t and ent[1] == t._version:
+        return ent[2]
+    if len(_host_cache) > 4096:
+        for k in [k for k, e in _host_cache.items() if e[0]() is None]:
+            del _host_cache[k]
         if len(_host_cache) > 4096:
             _host_cache.clear()
-        v = tuple(t.detach().reshape(-1).to("cpu", torch.float32).tolist())
-        assert len(v) == n, f"expected {n} values, got {len(v)}"
-        _host_cache[key] = v
+    v = tuple(t.detach().reshape(-1).to("cpu", torch.float32).tolist())
+    assert len(v) == n, f"expected {n} values, got {len(v)}"
+    _host_cache[id(t)] = (weakref.ref(t), t._version, v)
     return v
 
 
