@@ -45,6 +45,23 @@ SIGNATURES = {
     "cgs_raster_backward_workspace_bytes": (c_size_t, [c_int]),
     "cgs_rasterize_backward": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
                                        _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
+    "cgs_neural_gaussians_packed_floats": (c_int, []),
+    "cgs_neural_gaussians_workspace_bytes": (c_size_t, [c_int]),
+    "cgs_neural_gaussians_forward": (c_int, [_PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
+                                             _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
+    "cgs_compact_workspace_bytes": (c_size_t, [c_int]),
+    "cgs_compact_indices": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, c_size_t, _PTR]),
+    "cgs_eb_param_floats": (c_int, []),
+    "cgs_eb_forward": (c_int, [_PTR, c_int, _PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR]),
+    "cgs_context_level_packed_floats": (c_int, [c_int]),
+    "cgs_context_level_forward": (c_int, [c_int, _PTR, _PTR, _PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
+                                          _PTR, _PTR, ctypes.c_float, ctypes.c_float, ctypes.c_float, _PTR, _PTR,
+                                          _PTR, _PTR, _PTR, _PTR]),
+    "cgs_gaussian_bits_forward": (c_int, [_PTR, _PTR, _PTR, _PTR, c_int, ctypes.c_float, c_int64, c_int, _PTR, _PTR]),
+    "cgs_gaussian_bits_backward": (c_int, [_PTR, _PTR, _PTR, _PTR, c_int, ctypes.c_float, c_int64, c_int, _PTR, _PTR,
+                                           _PTR, _PTR, _PTR, _PTR]),
+    "cgs_ste_multistep": (c_int, [_PTR, _PTR, c_int64, c_int, _PTR, _PTR]),
+    "cgs_quantize_anchor": (c_int, [_PTR, _PTR, _PTR, c_int64, _PTR, _PTR, _PTR]),
     "cgs_sort_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "cgs_sort_pairs_u32": (c_int, [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, c_int64, c_int, c_int, _PTR, c_size_t,
                                    _PTR]),

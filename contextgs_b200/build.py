@@ -28,6 +28,11 @@ SOURCES = {
     "radix_sort.cu": [],
     "raster_binning.cu": [],
     "raster_render.cu": [],
+    # -fmad=false: the elementwise value-defining code (x + noise*Q, anchor + offset*scale, interval
+    # arithmetic ...) rounds once per operation like the PyTorch expressions it replaces; the GEMM
+    # inner loops use explicit fmaf() and are unaffected.
+    "neural_gaussians.cu": ["-fmad=false"],
+    "context_model.cu": ["-fmad=false"],
 }
 
 

@@ -1,0 +1,227 @@
+"""Anchor-level autoregressive context / entropy model: drop-in for `multi_scale_generating`,
+`find_divide_scale`, `divide_levels` (scene/gaussian_model.py:1541-1793) on top of the fused CUDA
+kernels in contextgs_b200/csrc/context_model.cu.
+
+Per call: 1 EntropyBottleneck kernel + 3 fused level kernels (coarse -> fine).  The level index
+bookkeeping (which rows each level codes, where each row's context comes from -- including the
+reference's mid-level row misalignment) is flattened once into int32 index
+arrays (`LevelPlan`) and cached while anchors and masks are unchanged.
+"""
+from types import SimpleNamespace
+
+import torch
+
+from . import _lib
+from .encodings import get_binary_vxl_size
+
+N_CODED = 86  # 50 feat + 6 scaling + 30 offsets
+
+_grid_pack_cache = {}
+
+
+def pack_grid_weights(pc, level):
+    """W1[in][100] | b1[100] | W2[100][176] | b2[176] (k-major) for `pc.get_grid_mlp[level]`."""
+    m = pc.get_grid_mlp[level]
+    params = (m[0].weight, m[0].bias, m[2].weight, m[2].bias)
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    ent = _grid_pack_cache.get((id(pc), level))
+    if ent is not None and ent[0] == key:
+        return ent[1], ent[2]
+    with torch.no_grad():
+        dev = params[0].device
+        in_dim = m[0].weight.shape[1]
+        W2 = torch.zeros(100, 176, device=dev)
+        W2[:, :175] = m[2].weight.t()
+        b2 = torch.zeros(176, device=dev)
+        b2[:175] = m[2].bias
+        packed = torch.cat([m[0].weight.t().reshape(-1), m[0].bias, W2.reshape(-1), b2]).float().contiguous()
+    assert packed.numel() == _lib.lib().cgs_context_level_packed_floats(in_dim)
+    _grid_pack_cache[(id(pc), level)] = (key, packed, in_dim)
+    return packed, in_dim
+
+
+# ----------------------------------------------------------------------------- level division (E1-E3)
+
+def _unique_rows_first_index(rows):
+    """utils/multi_level.py:3-31 semantics on the device: sorted unique rows, inverse, min source index."""
+    uniq, inverse = torch.unique(rows, return_inverse=True, dim=0)
+    first = torch.full((uniq.shape[0],), rows.shape[0], dtype=torch.long, device=rows.device)
+    first.scatter_reduce_(0, inverse, torch.arange(rows.shape[0], device=rows.device), reduce="amin")
+    return uniq, inverse, first
+
+
+def find_divide_scale(pc, anchor, target_ratio, level_num):
+    """scene/gaussian_model.py:1726-1749."""
+    upper0 = float(((pc.x_bound_max - pc.x_bound_min) / pc.voxel_size).max())
+    cur, lower, scales = anchor, 1.0, []
+    for _ in range(level_num - 1):
+        hi, lo = upper0, lower
+        while True:
+            scale = (hi + lo) / 2
+            uniq = torch.unique(torch.round(cur / pc.voxel_size / scale), dim=0) * pc.voxel_size * scale
+            ratio = uniq.shape[0] / cur.shape[0]
+            if abs(ratio - target_ratio) < 0.01 or abs(hi - lo) < 1:
+                break
+            if ratio < target_ratio:
+                hi = scale
+            else:
+                lo = scale
+        cur, lower = uniq, scale
+        scales.append(float(scale))
+    return scales
+
+
+def divide_levels(pc, anchor, mask_anchor_bool=None):
+    """scene/gaussian_model.py:1751-1765 -> (hybrid_anchor_list, inverse_indices_list, mapping_list, last)."""
+    level_anchor, inverse, first = [anchor], [], []
+    cur = anchor
+    for i in range(1, pc.level_num):
+        if i == 1 and mask_anchor_bool is not None:
+            cur = cur * mask_anchor_bool.unsqueeze(1)
+        _, inv, fst = _unique_rows_first_index(torch.round(cur / pc.voxel_size / pc.level_scale[i - 1]))
+        cur = cur[fst]
+        level_anchor.append(cur)
+        inverse.append(inv)
+        first.append(fst)
+    return level_anchor, inverse, first, cur
+
+
+def build_level_plan(pc, anchor, mask_anchor_bool=None):
+    """Flatten the 3-level coding order into int32 index arrays (see oracle/entropy_ref.level_plan
+    for the derivation from scene/gaussian_model.py:1562-1652,1711-1793)."""
+    N, dev = anchor.shape[0], anchor.device
+    level_anchor, inverse, first, _ = divide_levels(pc, anchor, mask_anchor_bool)
+    map1, map2 = first
+    inv1, inv2 = inverse
+    o1, o2 = map1, map1[map2]
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    levels = [SimpleNamespace(level=2, orig=i32(o2), ctx_src=None, level_anchor=level_anchor[2].contiguous(),
+                              n=int(o2.shape[0]))]
+    to_code1 = torch.ones(map1.shape[0], dtype=torch.bool, device=dev)
+    to_code1[map2] = False
+    coded = torch.zeros(N, dtype=torch.bool, device=dev)
+    coded[o2] = True
+    member1 = torch.zeros(N, dtype=torch.bool, device=dev)
+    member1[o1] = True
+    gather1 = torch.nonzero(member1 & ~coded)[:, 0]          # ascending ORIGINAL index (quirk Q1)
+    levels.append(SimpleNamespace(level=1, orig=i32(o1[to_code1]), ctx_src=i32(o2[inv2[inv1[gather1]]]),
+                                  level_anchor=None, n=int(gather1.shape[0])))
+    coded[o1] = True
+    gather0 = torch.nonzero(~coded)[:, 0]
+    levels.append(SimpleNamespace(level=0, orig=i32(gather0), ctx_src=i32(o1[inv1[gather0]]), level_anchor=None,
+                                  n=int(gather0.shape[0])))
+    return SimpleNamespace(N=N, levels=levels, inverse=inverse, first=first, level_anchor=level_anchor)
+
+
+def get_level_plan(pc, anchor, mask_anchor_bool):
+    """Plan cache: valid while the anchor positions / offset masks it was derived from are unchanged
+    (position lr is 0 in the reference, arguments/__init__.py:86-87; masks flip rarely)."""
+    src_a, src_m = getattr(pc, "_anchor", anchor), getattr(pc, "_mask", None)
+    key = (anchor.shape[0], anchor.data_ptr() if anchor is src_a else None, src_a.data_ptr(), src_a._version,
+           None if src_m is None else (src_m.data_ptr(), src_m._version), mask_anchor_bool is None,
+           tuple(pc.level_scale))
+    ent = getattr(pc, "_cgs_level_plan", None)
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    plan = build_level_plan(pc, anchor, mask_anchor_bool)
+    try:
+        pc._cgs_level_plan = (key, plan)
+    except Exception:
+        pass
+    return plan
+
+
+# ----------------------------------------------------------------------------- the fused forward
+
+@torch.no_grad()
+def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, binary_grid_masks,
+                           mask_anchor_bool=None, training=False, predict_bpp=False, return_sum_bits=False,
+                           noise=None, return_details=False):
+    """Same signature and the same three return arities as scene/gaussian_model.py:1541-1707.
+    `noise` (optional, for reproducible parity runs): dict(eb=[N,12], levels=[[n_i,86] x3 coarse->fine],
+    choose=bool[N]); otherwise drawn with the CUDA generator."""
+    L = _lib.lib()
+    dev = anchor.device
+    N, K = anchor.shape[0], pc.n_offsets
+    anchor = anchor.contiguous()
+    feat = feat.contiguous()
+    scaling = grid_scaling.contiguous()
+    offsets = grid_offsets.reshape(N, 3 * K).contiguous()
+    masks = binary_grid_masks.reshape(N, K).contiguous()
+    hyper = hyper.contiguous()
+    if pc.level_scale is None:
+        pc.level_scale = find_divide_scale(pc, anchor[mask_anchor_bool], pc.target_ratio, pc.level_num)
+    plan = get_level_plan(pc, anchor, mask_anchor_bool)
+
+    if predict_bpp:
+        if noise is not None and "choose" in noise:
+            choose = noise["choose"].to(dev)
+        else:
+            thresh = 1 if return_sum_bits else 0.15
+            choose = torch.rand(N, device=dev) <= thresh
+        if mask_anchor_bool is not None:
+            choose = choose & mask_anchor_bool
+    else:
+        choose = torch.zeros(N, dtype=torch.bool, device=dev)
+    choose_u8 = choose.contiguous().view(torch.uint8)
+
+    sums = torch.zeros(16, dtype=torch.float64, device=dev)  # [4*i..4*i+3] level i (coarse->fine); [12] hyper
+    hyper_q, lik = pc.latent_codec(hyper, training=training, noise=None if noise is None else noise["eb"],
+                                   choose=choose_u8, bit_sum=sums[12:13])
+    if getattr(pc, "disable_hyper", False):
+        hyper_q = hyper_q * 0
+    feat_q = torch.zeros_like(feat)
+    scaling_q = torch.zeros_like(scaling)
+    offsets_q = torch.zeros_like(offsets)
+    bits_out = torch.zeros((N, N_CODED), dtype=torch.float32, device=dev) if return_details else None
+    f_mean = float(pc._anchor_feat.mean())
+    s_mean = float(pc.get_scaling.mean())
+    o_mean = float(pc._offset.mean())
+    stream = _lib.stream_ptr()
+    for li, lv in enumerate(plan.levels):
+        if lv.n == 0:
+            continue
+        packed, in_dim = pack_grid_weights(pc, lv.level)
+        nz = None
+        if training:
+            nz = noise["levels"][li].to(dev).contiguous() if noise is not None else \
+                torch.empty((lv.n, N_CODED), device=dev).uniform_(-0.5, 0.5)
+        _lib.check(L.cgs_context_level_forward(
+            in_dim, _lib.ptr(packed), _lib.ptr(lv.orig), _lib.ptr(lv.ctx_src), _lib.ptr(lv.level_anchor), lv.n,
+            _lib.ptr(anchor), _lib.ptr(hyper_q), _lib.ptr(feat), _lib.ptr(scaling), _lib.ptr(offsets), _lib.ptr(masks),
+            _lib.ptr(choose_u8), _lib.ptr(nz), f_mean, s_mean, o_mean, _lib.ptr(feat_q), _lib.ptr(scaling_q),
+            _lib.ptr(offsets_q), _lib.ptr(bits_out), _lib.ptr(sums[4 * li:4 * li + 4]), stream),
+            "cgs_context_level_forward")
+    offsets_q3 = offsets_q.view(N, K, 3)
+    if not predict_bpp:
+        return feat_q, scaling_q, offsets_q3
+
+    s = sums.tolist()  # one host read-back (the reference has several .item() calls here)
+    bit_feat, bit_scaling, bit_offsets = (sum(s[4 * i + c] for i in range(3)) for c in range(3))
+    n_chosen = sum(s[4 * i + 3] for i in range(3))
+    bit_hyper = s[12]
+    details = dict(feat_q=feat_q, scaling_q=scaling_q, offsets_q=offsets_q3, bits=bits_out, hyper_q=hyper_q,
+                   lik_hyper=lik, choose=choose, sums=s, plan=plan)
+    if return_sum_bits:
+        bit_anchor = int(n_chosen) * 3 * 16
+        bit_masks = get_binary_vxl_size(binary_grid_masks)[1].item()
+        res = (bit_anchor, bit_hyper, bit_feat, bit_scaling, bit_offsets, bit_masks)
+        return (res, details) if return_details else res
+    if mask_anchor_bool is not None:
+        rate = float(mask_anchor_bool.sum()) / mask_anchor_bool.numel()
+    else:
+        rate = 1.0
+    nc = max(n_chosen, 1e-30)
+    t = lambda v: torch.tensor(v, dtype=torch.float32, device=dev)
+    per_hyper = bit_hyper / (nc * 12) * rate
+    per_feat = t(bit_feat / (nc * 50) * rate)
+    per_scaling = t(bit_scaling / (nc * 6) * rate)
+    per_offsets = t(bit_offsets / (nc * 30) * rate)
+    per_param = t((bit_feat + bit_scaling + bit_offsets + bit_hyper) / (nc * N_CODED) * rate)
+    level_bpp = [1 - rate, per_hyper]
+    for li, lv in enumerate(plan.levels):
+        cnt = s[4 * li + 3]
+        bpp = (s[4 * li] + s[4 * li + 1] + s[4 * li + 2]) / cnt / N_CODED if cnt > 0 else float("nan")
+        level_bpp.append([lv.n / N, bpp])
+    res = (feat_q, scaling_q, offsets_q3, per_param, per_feat, per_scaling, per_offsets, level_bpp)
+    return (res, details) if return_details else res

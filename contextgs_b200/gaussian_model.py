@@ -1,0 +1,231 @@
+"""Host-side mirror of the hot-path surface of the reference's `GaussianModel`
+(scene/gaussian_model.py:46-190, getters :288-345): the per-anchor parameters, the three decoder
+MLPs, the three context ("grid") MLPs and the hyper-prior entropy bottleneck, with the same
+attribute names the reference's glue reads (gaussian_renderer/__init__.py:31-142).
+
+Optimizer set-up, densification, ply / checkpoint / bitstream IO are OUT OF SCOPE (SURVEY.md 2.1
+row 2d) and stay with the reference; this class only has to hold `nn.Parameter`s of the same names
+and shapes so that those routines keep working against it.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .encodings import Quantize_anchor
+
+
+class EntropyBottleneck(nn.Module):
+    """Parameter container + CUDA forward of compressai's EntropyBottleneck (channels = feat_dim //
+    hyper_divisor; reference: scene/gaussian_model.py:135,1556).  Same parameter names/shapes as
+    CompressAI (matrices / biases / factors / quantiles) so that checkpoints map one-to-one."""
+
+    def __init__(self, channels, filters=(3, 3, 3, 3), init_scale=10.0, tail_mass=1e-9):
+        super().__init__()
+        self.channels, self.filters = int(channels), tuple(int(f) for f in filters)
+        f = (1,) + self.filters + (1,)
+        scale = init_scale ** (1 / (len(self.filters) + 1))
+        self.matrices, self.biases, self.factors = nn.ParameterList(), nn.ParameterList(), nn.ParameterList()
+        for i in range(len(self.filters) + 1):
+            init = math.log(math.expm1(1 / scale / f[i + 1]))
+            self.matrices.append(nn.Parameter(torch.full((channels, f[i + 1], f[i]), init)))
+            self.biases.append(nn.Parameter(torch.rand(channels, f[i + 1], 1) - 0.5))
+            if i < len(self.filters):
+                self.factors.append(nn.Parameter(torch.zeros(channels, f[i + 1], 1)))
+        self.quantiles = nn.Parameter(torch.tensor([-init_scale, 0.0, init_scale]).repeat(channels, 1, 1))
+        self._packed = None
+        self._packed_key = None
+
+    def packed(self):
+        """[C, 59] parameter block of the CUDA kernel (softplus / tanh pre-applied), cached per
+        parameter version."""
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed is None or self._packed_key != key:
+            with torch.no_grad():
+                cols = []
+                for i in range(len(self.filters) + 1):
+                    cols.append(torch.nn.functional.softplus(self.matrices[i]).reshape(self.channels, -1))
+                    cols.append(self.biases[i].reshape(self.channels, -1))
+                    if i < len(self.filters):
+                        cols.append(torch.tanh(self.factors[i]).reshape(self.channels, -1))
+                cols.append(self.quantiles[:, 0, 1:2])
+                self._packed = torch.cat(cols, dim=1).float().contiguous()
+            assert self._packed.shape[1] == _lib.lib().cgs_eb_param_floats()
+            self._packed_key = key
+        return self._packed
+
+    @torch.no_grad()
+    def forward(self, x, training=None, noise=None, choose=None, bit_sum=None):
+        """x [N,C] -> (x_hat, likelihood).  training=True adds U(-.5,.5) (pass `noise` [N,C] for
+        reproducibility), otherwise rounds about the median.  No autograd: the differentiable
+        training path lives in contextgs_b200.context_model."""
+        if training is None:
+            training = self.training
+        x = x.contiguous()
+        N, C = x.shape
+        if training and noise is None:
+            noise = torch.empty_like(x).uniform_(-0.5, 0.5)
+        out, lik = torch.empty_like(x), torch.empty_like(x)
+        _lib.check(_lib.lib().cgs_eb_forward(
+            _lib.ptr(self.packed()), C, _lib.ptr(x), _lib.ptr(noise.contiguous()) if training else None, N,
+            _lib.ptr(out), _lib.ptr(lik), _lib.ptr(choose), _lib.ptr(bit_sum), _lib.stream_ptr()), "cgs_eb_forward")
+        return out, lik
+
+
+def _mlp(i, h, o, act=None):
+    layers = [nn.Linear(i, h), nn.ReLU(True), nn.Linear(h, o)]
+    if act is not None:
+        layers.append(act)
+    return nn.Sequential(*layers)
+
+
+class GaussianModel(nn.Module):
+    def __init__(self, feat_dim=50, n_offsets=10, voxel_size=0.001, level_num=3, hyper_divisor=4, target_ratio=0.2,
+                 decoded_version=False, device="cuda"):
+        super().__init__()
+        if (feat_dim, n_offsets, hyper_divisor, level_num) != (50, 10, 4, 3):
+            raise NotImplementedError("the CUDA kernels are specialised for the ContextGS defaults "
+                                      "feat_dim=50, n_offsets=10, hyper_divisor=4, level_num=3 "
+                                      "(arguments/__init__.py:50-52,67-68; train.py:595)")
+        self.feat_dim, self.n_offsets, self.voxel_size = feat_dim, n_offsets, voxel_size
+        self.level_num, self.hyper_divisor, self.target_ratio = level_num, hyper_divisor, target_ratio
+        self.decoded_version = decoded_version
+        self.level_scale = None
+        self.disable_hyper = False
+        self.adaptQ_per_channel = False
+        self.x_bound_min = torch.zeros(1, 3, device=device)
+        self.x_bound_max = torch.ones(1, 3, device=device)
+        e = torch.empty(0, device=device)
+        self._anchor = self._offset = self._mask = self._anchor_feat = self._hyper_latent = e
+        self._scaling = self._rotation = self._opacity = e
+        self.rotation_activation = torch.nn.functional.normalize
+        self.latent_codec = EntropyBottleneck(feat_dim // hyper_divisor).to(device)
+        d = feat_dim + 3 + 1
+        self.mlp_opacity = _mlp(d, feat_dim, n_offsets, nn.Tanh()).to(device)
+        self.mlp_cov = _mlp(d, feat_dim, 7 * n_offsets).to(device)
+        self.mlp_color = _mlp(d, feat_dim, 3 * n_offsets, nn.Sigmoid()).to(device)
+        self.mlp_grid = nn.ModuleList()
+        out = (feat_dim + 6 + 3 * n_offsets) * 2 + 3
+        H = feat_dim // hyper_divisor
+        for i in range(level_num):
+            fin = H + 3 if i == level_num - 1 else feat_dim + 6 + 3 + H
+            self.mlp_grid.append(_mlp(fin, feat_dim * 2, out).to(device))
+
+    # ---- construction from synthetic tensors (tests, bench) ---------------------------------
+    @classmethod
+    def from_tensors(cls, scene, mlps=None, eb=None, device="cuda", **kw):
+        """scene: dict(anchor, feat, hyper, offset, scaling, mask, voxel_size) as produced by
+        contextgs_b200.synthetic.make_scene; mlps/eb: optional weights in the oracle's layout
+        (lists [W1,b1,W2,b2]; EntropyBottleneckRef) so that both sides share identical parameters."""
+        m = cls(voxel_size=scene["voxel_size"], device=device, **kw)
+        P = lambda t, g=True: nn.Parameter(t.detach().clone().float().to(device).contiguous(), requires_grad=g)
+        m._anchor, m._anchor_feat, m._hyper_latent = P(scene["anchor"]), P(scene["feat"]), P(scene["hyper"])
+        m._offset, m._mask, m._scaling = P(scene["offset"]), P(scene["mask"]), P(scene["scaling"])
+        N = m._anchor.shape[0]
+        rot = torch.zeros(N, 4)
+        rot[:, 0] = 1
+        m._rotation = P(rot, False)
+        m._opacity = P(torch.zeros(N, 1), False)
+        if mlps is not None:
+            with torch.no_grad():
+                for name in ("opacity", "cov", "color"):
+                    seq = getattr(m, "mlp_" + name)
+                    W1, b1, W2, b2 = mlps[name]
+                    seq[0].weight.copy_(W1); seq[0].bias.copy_(b1); seq[2].weight.copy_(W2); seq[2].bias.copy_(b2)
+                for i, (W1, b1, W2, b2) in enumerate(mlps["grid"]):
+                    seq = m.mlp_grid[i]
+                    seq[0].weight.copy_(W1); seq[0].bias.copy_(b1); seq[2].weight.copy_(W2); seq[2].bias.copy_(b2)
+        if eb is not None:
+            with torch.no_grad():
+                for i, t in enumerate(eb.matrices):
+                    m.latent_codec.matrices[i].copy_(t)
+                for i, t in enumerate(eb.biases):
+                    m.latent_codec.biases[i].copy_(t)
+                for i, t in enumerate(eb.factors):
+                    m.latent_codec.factors[i].copy_(t)
+                m.latent_codec.quantiles.copy_(eb.quantiles)
+        m.update_anchor_bound()
+        return m
+
+    # ---- getters (scene/gaussian_model.py:288-345) -------------------------------------------
+    @property
+    def get_scaling(self):
+        if self.decoded_version:
+            return self._scaling
+        return 1.0 * torch.exp(self._scaling)
+
+    @property
+    def get_mask(self):
+        if self.decoded_version:
+            return self._mask
+        mask_sig = torch.sigmoid(self._mask)
+        return ((mask_sig > 0.01).float() - mask_sig).detach() + mask_sig
+
+    @property
+    def get_mask_anchor(self):
+        with torch.no_grad():
+            if self.decoded_version:
+                return (torch.sum(self._mask, dim=1)[:, 0]) > 0
+            mask_sig = torch.sigmoid(self._mask)
+            mask = ((mask_sig > 0.01).float() - mask_sig).detach() + mask_sig
+            return (torch.sum(mask, dim=1)[:, 0]) > 0
+
+    @property
+    def get_opacity_mlp(self):
+        return self.mlp_opacity
+
+    @property
+    def get_cov_mlp(self):
+        return self.mlp_cov
+
+    @property
+    def get_color_mlp(self):
+        return self.mlp_color
+
+    @property
+    def get_grid_mlp(self):
+        return self.mlp_grid
+
+    @property
+    def get_rotation(self):
+        return self.rotation_activation(self._rotation)
+
+    @property
+    def get_anchor(self):
+        if self.decoded_version:
+            return self._anchor
+        anchor, _ = Quantize_anchor.apply(self._anchor, self.x_bound_min, self.x_bound_max)
+        return anchor
+
+    @torch.no_grad()
+    def update_anchor_bound(self):
+        """scene/gaussian_model.py:352-360."""
+        mn = torch.min(self._anchor, dim=0, keepdim=True)[0].detach()
+        mx = torch.max(self._anchor, dim=0, keepdim=True)[0].detach()
+        self.x_bound_min = torch.where(mn < 0, mn * 1.2, mn * 0.8)
+        self.x_bound_max = torch.where(mx > 0, mx * 1.2, mx * 0.8)
+
+    def eval(self):
+        for m in (self.mlp_opacity, self.mlp_cov, self.mlp_color, self.latent_codec, self.mlp_grid):
+            m.eval()
+        return self
+
+    def train(self, mode=True):
+        for m in (self.mlp_opacity, self.mlp_cov, self.mlp_color, self.latent_codec, self.mlp_grid):
+            m.train(mode)
+        return self
+
+    @torch.no_grad()
+    def estimate_final_bits(self, return_values=False):
+        """scene/gaussian_model.py:981-1004 (without the side-effect files at :1681-1682)."""
+        from .context_model import multi_scale_generating
+        sel = self.get_mask_anchor
+        sums = multi_scale_generating(self, self.get_anchor[sel], self._hyper_latent[sel], self._anchor_feat[sel],
+                                      self._offset[sel], self.get_scaling[sel], binary_grid_masks=self.get_mask[sel],
+                                      predict_bpp=True, return_sum_bits=True)
+        if return_values:
+            return sums
+        names = ["anchor", "hyper", "feat", "scaling", "offsets", "masks"]
+        mb = 8 * 1024 * 1024
+        return "\nEstimated sizes in MB: " + ", ".join(f"{n} {round(v / mb, 4)}" for n, v in zip(names, sums))

@@ -1,0 +1,133 @@
+"""Anchor -> neural Gaussian generation: drop-in for `generate_neural_gaussians`
+(gaussian_renderer/__init__.py:25-150) on top of the fused CUDA kernel
+`cgs_neural_gaussians_forward` (contextgs_b200/csrc/neural_gaussians.cu)."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+Q_FEAT, Q_SCALING, Q_OFFSETS = 1, 0.001, 0.2  # gaussian_renderer/__init__.py:40-42
+
+_pack_cache = {}
+
+
+def pack_decoder_weights(pc):
+    """Packed weight block of the three decoder MLPs (layout: include/contextgs_b200.h), cached per
+    parameter version so that inference frames do not repack."""
+    mods = (pc.get_opacity_mlp, pc.get_color_mlp, pc.get_cov_mlp)
+    params = [p for m in mods for p in (m[0].weight, m[0].bias, m[2].weight, m[2].bias)]
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    ent = _pack_cache.get(id(pc))
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    with torch.no_grad():
+        dev = params[0].device
+        W1 = torch.zeros(54, 152, device=dev)
+        b1 = torch.zeros(152, device=dev)
+        for i, m in enumerate(mods):
+            W1[:, 50 * i:50 * i + 50] = m[0].weight.t()
+            b1[50 * i:50 * i + 50] = m[0].bias
+        parts = [W1.reshape(-1), b1]
+        for m, ld in zip(mods, (12, 32, 72)):
+            n = m[2].weight.shape[0]
+            W2 = torch.zeros(50, ld, device=dev)
+            W2[:, :n] = m[2].weight.t()
+            b2 = torch.zeros(ld, device=dev)
+            b2[:n] = m[2].bias
+            parts += [W2.reshape(-1), b2]
+        packed = torch.cat(parts).float().contiguous()
+    assert packed.numel() == _lib.lib().cgs_neural_gaussians_packed_floats()
+    _pack_cache[id(pc)] = (key, packed)
+    return packed
+
+
+def compact_indices(mask):
+    """Order-preserving device-side `nonzero` of a bool/uint8 mask -> (idx[int32, capacity N], count_dev)."""
+    L = _lib.lib()
+    m = mask.contiguous().view(torch.uint8)
+    N = m.numel()
+    idx = torch.empty((max(N, 1),), dtype=torch.int32, device=m.device)
+    cnt = torch.empty((1,), dtype=torch.int32, device=m.device)
+    ws = torch.empty((L.cgs_compact_workspace_bytes(N),), dtype=torch.uint8, device=m.device)
+    _lib.check(L.cgs_compact_indices(_lib.ptr(m), N, _lib.ptr(idx), _lib.ptr(cnt), _lib.ptr(ws), ws.numel(),
+                                     _lib.stream_ptr()), "cgs_compact_indices")
+    return idx, cnt
+
+
+def generate_raw(pc, camera_center, anchor, feat, grid_offsets, grid_scaling, binary_grid_masks, vis_idx=None,
+                 n_vis=None):
+    """Launch the fused kernel.  Inputs are the FULL per-anchor arrays plus an optional visible-index
+    list; returns capacity-sized outputs and the device-side Gaussian count."""
+    L = _lib.lib()
+    dev = anchor.device
+    Nv = int(anchor.shape[0] if vis_idx is None else (n_vis if n_vis is not None else vis_idx.shape[0]))
+    cap = max(Nv * pc.n_offsets, 1)
+    f32 = torch.float32
+    out = dict(
+        xyz=torch.empty((cap, 3), dtype=f32, device=dev), color=torch.empty((cap, 3), dtype=f32, device=dev),
+        opacity=torch.empty((cap, 1), dtype=f32, device=dev), scaling=torch.empty((cap, 3), dtype=f32, device=dev),
+        rot=torch.empty((cap, 4), dtype=f32, device=dev), neural_opacity=torch.empty((cap, 1), dtype=f32, device=dev),
+        mask=torch.empty((cap,), dtype=torch.uint8, device=dev), count=torch.empty((1,), dtype=torch.int32, device=dev))
+    ws = torch.empty((L.cgs_neural_gaussians_workspace_bytes(Nv),), dtype=torch.uint8, device=dev)
+    from .rasterizer import _host_floats
+    campos = (ctypes.c_float * 3)(*_host_floats(camera_center, 3))
+    _lib.check(L.cgs_neural_gaussians_forward(
+        _lib.ptr(pack_decoder_weights(pc)), _lib.ptr(vis_idx), Nv, _lib.ptr(anchor.contiguous()),
+        _lib.ptr(feat.contiguous()), _lib.ptr(grid_offsets.contiguous()), _lib.ptr(grid_scaling.contiguous()),
+        _lib.ptr(binary_grid_masks.contiguous()), campos, _lib.ptr(out["xyz"]), _lib.ptr(out["color"]),
+        _lib.ptr(out["opacity"]), _lib.ptr(out["scaling"]), _lib.ptr(out["rot"]), _lib.ptr(out["neural_opacity"]),
+        _lib.ptr(out["mask"]), _lib.ptr(out["count"]), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+        "cgs_neural_gaussians_forward")
+    out["n_vis"] = Nv
+    return out
+
+
+@torch.no_grad()
+def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False, step=0):
+    """Same signature and return tuples as gaussian_renderer/__init__.py:25-150.
+
+    NOTE (round 1): forward only -- outputs carry no autograd graph.  The differentiable G1 backward
+    kernel is the next row of the build plan; training-mode calls work for
+    evaluation of the forward values (bit_per_param etc.)."""
+    from .context_model import multi_scale_generating
+    anchor_all = pc.get_anchor
+    N = anchor_all.shape[0]
+    if visible_mask is None:
+        visible_mask = torch.ones(N, dtype=torch.bool, device=anchor_all.device)
+    bit_per_param = bit_per_feat_param = bit_per_scaling_param = bit_per_offsets_param = bpp_per_level = None
+    feat, grid_offsets, grid_scaling = pc._anchor_feat, pc._offset, pc.get_scaling
+    binary_grid_masks = pc.get_mask
+    if is_training:
+        if 3000 < step <= 10000:
+            feat = feat + torch.empty_like(feat).uniform_(-0.5, 0.5) * Q_FEAT
+            grid_scaling = grid_scaling + torch.empty_like(grid_scaling).uniform_(-0.5, 0.5) * Q_SCALING
+            grid_offsets = grid_offsets + torch.empty_like(grid_offsets).uniform_(-0.5, 0.5) * Q_OFFSETS
+        if step == 10000:
+            pc.update_anchor_bound()
+        if step > 10000:
+            mask_anchor_bool = pc.get_mask_anchor.to(torch.bool)
+            (feat, grid_scaling, grid_offsets, bit_per_param, bit_per_feat_param, bit_per_scaling_param,
+             bit_per_offsets_param, bpp_per_level) = multi_scale_generating(
+                pc, anchor_all, pc._hyper_latent, feat, grid_offsets, grid_scaling, binary_grid_masks,
+                mask_anchor_bool, predict_bpp=True, training=True)
+    elif not pc.decoded_version:
+        mask_anchor_bool = pc.get_mask_anchor.to(torch.bool)
+        feat, grid_scaling, grid_offsets = multi_scale_generating(
+            pc, anchor_all, pc._hyper_latent, feat, grid_offsets, grid_scaling, binary_grid_masks, mask_anchor_bool,
+            predict_bpp=False, training=False)
+
+    vis_idx, cnt = compact_indices(visible_mask)
+    n_vis = int(cnt.item())  # the reference synchronises here too (boolean indexing, :44-50)
+    raw = generate_raw(pc, viewpoint_camera.camera_center, anchor_all, feat, grid_offsets.reshape(N, -1),
+                       grid_scaling, binary_grid_masks.reshape(N, -1), vis_idx=vis_idx, n_vis=n_vis)
+    P = int(raw["count"].item())
+    K = pc.n_offsets
+    xyz, color, opacity = raw["xyz"][:P], raw["color"][:P], raw["opacity"][:P]
+    scaling, rot = raw["scaling"][:P], raw["rot"][:P]
+    if is_training:
+        neural_opacity = raw["neural_opacity"][:n_vis * K]
+        mask = raw["mask"][:n_vis * K].bool()
+        return (xyz, color, opacity, scaling, rot, neural_opacity, mask, bit_per_param, 16, bit_per_feat_param,
+                bit_per_scaling_param, bit_per_offsets_param, bpp_per_level)
+    return xyz, color, opacity, scaling, rot, 0

@@ -111,6 +111,88 @@ CGS_API int cgs_rasterize_backward(const cgs_raster_settings *s, int P, const fl
                            float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity, float *dL_dscales,
                            float *dL_drots, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------ anchor -> Gaussians (G1) */
+
+/* Number of floats of the packed decoder-MLP weight block consumed by cgs_neural_gaussians_forward:
+ *   W1[54][152] (k-major; columns 0-49 opacity / 50-99 color / 100-149 cov hidden units, 2 zero pads),
+ *   b1[152], W2_opacity[50][12] b[12], W2_color[50][32] b[32], W2_cov[50][72] b[72] (h-major, zero padded).
+ * Source layers: scene/gaussian_model.py:153-174. */
+CGS_API int cgs_neural_gaussians_packed_floats(void);
+CGS_API size_t cgs_neural_gaussians_workspace_bytes(int Nv);
+
+/* Replaces gaussian_renderer/__init__.py:106-145 (everything `generate_neural_gaussians` does after
+ * the per-anchor attributes have been chosen): view dir/dist, 3 decoder MLPs, `opacity*mask > 0`
+ * selection, order-preserving compaction, scale/rotation/position post-processing.
+ *   vis_idx[Nv] : indices of the visible anchors (NULL = all Nv anchors in order)
+ *   anchor[N,3] feat[N,50] offsets[N,10,3] scaling[N,6] mask[N,10]   (fp32, N = full anchor count)
+ *   campos_host : 3 HOST floats (camera centre)
+ *   outputs have CAPACITY Nv*10 rows; *count_dev (device int32) receives P, the number emitted:
+ *     o_xyz[P,3] o_color[P,3] o_opacity[P] o_scaling[P,3] o_rot[P,4]
+ *     o_neural_opacity[Nv*10], o_mask[Nv*10] (uint8) -- the reference's `neural_opacity`, `mask` */
+CGS_API int cgs_neural_gaussians_forward(const float *packed_weights, const int32_t *vis_idx, int Nv,
+                                         const float *anchor, const float *feat, const float *offsets,
+                                         const float *scaling, const float *mask, const float *campos_host,
+                                         float *o_xyz, float *o_color, float *o_opacity, float *o_scaling,
+                                         float *o_rot, float *o_neural_opacity, uint8_t *o_mask, int32_t *count_dev,
+                                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* Order-preserving compaction of a byte mask into an index list (the device-side replacement of
+ * the reference's `tensor[bool_mask]` / torch.nonzero host-synchronising idiom, e.g.
+ * gaussian_renderer/__init__.py:44-50).  mask must be 8-byte aligned. *count_dev = popcount. */
+CGS_API size_t cgs_compact_workspace_bytes(int N);
+CGS_API int cgs_compact_indices(const uint8_t *mask, int N, int32_t *out_idx, int32_t *count_dev, void *workspace,
+                                size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------ context / entropy model (E4-E7, G2) */
+
+/* Floats per channel of the packed EntropyBottleneck parameters (softplus(matrices), biases,
+ * tanh(factors), median) -- see oracle/entropy_ref.py EntropyBottleneckRef.packed(). */
+CGS_API int cgs_eb_param_floats(void);
+
+/* Replaces `pc.latent_codec(hyper, training=...)` = compressai EntropyBottleneck.forward
+ * (reference call: scene/gaussian_model.py:1556).  hyper[N,C]; noise[N,C] (training) or NULL (eval:
+ * round about the median); outputs hyper_q[N,C], likelihood[N,C] (floored at 1e-9).  If bit_sum is
+ * given, sum(-log2 likelihood) over the anchors selected by choose[N] (NULL = all) is ADDED to it. */
+CGS_API int cgs_eb_forward(const float *packed_params, int C, const float *hyper, const float *noise, int N,
+                           float *hyper_q, float *likelihood, const uint8_t *choose, double *bit_sum, void *stream);
+
+/* Packed context-MLP weights for one level: W1[in_dim][100] | b1[100] | W2[100][176] | b2[176]
+ * (k-major; scene/gaussian_model.py:177-188).  in_dim is 71 (context 59 + hyper 12) or 15 (xyz + hyper). */
+CGS_API int cgs_context_level_packed_floats(int in_dim);
+
+/* One level of the coarse-to-fine autoregression, fused (replaces the loop body
+ * scene/gaussian_model.py:1562-1652 plus the Entropy_gaussian calls at :1667-1670 and the sums at
+ * :1685-1693 for the rows of this level):
+ *   rows r < n_rows: orig_idx[r] = anchor coded by the row; ctx_src[r] = anchor whose already
+ *   quantised (anchor, feat_q, scaling_q) form the row's context (in_dim 71), or level_anchor[r,3]
+ *   (in_dim 15).  noise[n_rows,86] != NULL selects training-mode `x + U*Q`, NULL selects
+ *   STE_multistep rounding (utils/encodings.py:203-213).  Quantised values are scattered into
+ *   feat_q/scaling_q/offsets_q at orig_idx; bits of rows with choose[orig] != 0 are added to
+ *   bit_sums[0..2] (feat, scaling, masked offsets) and their count to bit_sums[3] (fp64). */
+CGS_API int cgs_context_level_forward(int in_dim, const float *packed_w, const int32_t *orig_idx,
+                                      const int32_t *ctx_src, const float *level_anchor, int n_rows,
+                                      const float *anchor, const float *hyper_q, const float *feat,
+                                      const float *scaling, const float *offsets, const float *mask,
+                                      const uint8_t *choose, const float *noise, float feat_mean, float scaling_mean,
+                                      float offset_mean, float *feat_q, float *scaling_q, float *offsets_q,
+                                      float *bits_out, double *bit_sums, void *stream);
+
+/* Replaces `Entropy_gaussian.forward` (utils/entropy_models.py:34-50) and its autograd backward
+ * incl. `Low_bound` (:141-156).  x/mean/scale/bits are [n,D]; Q is [n] (q_per_elem=0) or [n,D]. */
+CGS_API int cgs_gaussian_bits_forward(const float *x, const float *mean, const float *scale, const float *Q,
+                                      int q_per_elem, float x_mean, int64_t n, int D, float *bits, void *stream);
+CGS_API int cgs_gaussian_bits_backward(const float *x, const float *mean, const float *scale, const float *Q,
+                                       int q_per_elem, float x_mean, int64_t n, int D, const float *grad_bits,
+                                       float *dx, float *dmean, float *dscale, float *dQ, void *stream);
+
+/* Replaces `STE_multistep.forward` (utils/encodings.py:203-213): x[n,D], Q[n] -> out[n,D]. */
+CGS_API int cgs_ste_multistep(const float *x, const float *Q, int64_t n, int D, float *out, void *stream);
+
+/* Replaces `Quantize_anchor.forward` (utils/encodings.py:219-227): anchors[n,3], HOST min/max[3]
+ * -> anchors_q[n,3], quantized_v[n,3] (0..65535 as float). */
+CGS_API int cgs_quantize_anchor(const float *anchors, const float *min_host, const float *max_host, int64_t n,
+                                float *anchors_q, float *quantized_v, void *stream);
+
 /* Stand-alone access to the library's own stable LSD radix sort of (uint32 key, uint32 value)
  * pairs on key bits [begin_bit, end_bit) -- exported for tests and for the level-division path.
  * n lives on the device (n_dev) and is bounded by n_cap; vals_in may be NULL (= 0..n-1).

@@ -39,3 +39,26 @@ def rel_l2(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def cuda_model(scene, pc, **kw):
+    """Product-side GaussianModel on the GPU sharing the oracle model's parameters."""
+    from contextgs_b200.gaussian_model import GaussianModel
+    m = GaussianModel.from_tensors(scene, pc.mlps, pc.latent_codec, **kw)
+    m.level_scale = None if pc.level_scale is None else list(pc.level_scale)
+    return m
+
+
+def reference_noise(N, level_sizes, seed=7, K=10):
+    """Noise tensors drawn in the reference's call order (EB noise on the permuted [C,1,N] tensor,
+    then per level feat/scaling/offsets, then the 15% choose mask), see oracle.multi_scale_generating."""
+    torch.manual_seed(seed)
+    eb = torch.empty(12, 1, N).uniform_(-0.5, 0.5)
+    levels = []
+    for n in level_sizes:
+        f = torch.empty(n, 50).uniform_(-0.5, 0.5)
+        s = torch.empty(n, 6).uniform_(-0.5, 0.5)
+        o = torch.empty(n, K, 3).uniform_(-0.5, 0.5)
+        levels.append(torch.cat([f, s, o.reshape(n, 3 * K)], dim=1))
+    choose = torch.rand(N) <= 0.15
+    return dict(eb=eb.reshape(12, N).t().contiguous(), levels=levels, choose=choose)

@@ -1,0 +1,174 @@
+"""GPU parity: fused context / entropy model kernels vs golden vectors from the reference's own
+Python and vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from contextgs_b200 import synthetic
+from contextgs_b200.context_model import build_level_plan, multi_scale_generating
+from contextgs_b200.encodings import Quantize_anchor, STE_multistep
+from contextgs_b200.entropy_models import Entropy_gaussian
+from oracle import entropy_ref as er
+from tests.helpers import T, cuda_model, fixture_model, load_npz, reference_noise, rel_l2
+
+pytestmark = pytest.mark.gpu
+REL_L2 = 1e-4
+
+
+def symbol_mismatch(a, b, Q):
+    """Fraction of quantised values that differ by more than rounding noise of one step."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float((np.abs(a - b) > 1e-3 * Q + 1e-6 * np.abs(b)).mean())
+
+
+def test_elementwise_pieces_match_reference_golden():
+    g = load_npz("pieces.npz")
+    x, Q, mean, scale = (T(g[k]).cuda() for k in ("x", "Q", "mean", "scale"))
+    assert np.array_equal(STE_multistep.apply(x, Q).cpu().numpy(), g["ste"])            # bit exact
+    assert np.array_equal(STE_multistep.apply(x * 1e5, Q).cpu().numpy(), g["ste_big"])  # clamp branch
+    xq = STE_multistep.apply(x, Q)
+    bits = Entropy_gaussian(Q=1)(xq, mean, scale, Q, x.mean())
+    assert rel_l2(bits.cpu().numpy(), g["bits"]) < 1e-5
+    aq, qv = Quantize_anchor.apply(T(g["anc"]).cuda(), T(g["anc_min"]).cuda(), T(g["anc_max"]).cuda())
+    assert np.array_equal(aq.cpu().numpy(), g["anc_q"]) and np.array_equal(qv.cpu().numpy(), g["anc_qv"])
+
+
+def test_entropy_gaussian_backward_matches_autograd():
+    g = torch.Generator().manual_seed(5)
+    n, D = 300, 30
+    x = torch.round(torch.randn(n, D, generator=g) * 3) * 0.7
+    mean = torch.randn(n, D, generator=g)
+    scale = torch.rand(n, D, generator=g) * 2 + 0.05
+    scale[::7] = -0.5          # below the 1e-9 clamp -> zero scale gradient
+    mean[::11] += 40.0         # likelihood under the 1e-6 bound -> zero gradient everywhere (quirk Q2)
+    Q = torch.rand(n, 1, generator=g) + 0.2
+    w = torch.randn(n, D, generator=g)
+    leaves = [t.clone().requires_grad_(True) for t in (x, mean, scale, Q)]
+    (er.gaussian_bits(*leaves, x.mean()) * w).sum().backward()
+    cl = [t.clone().cuda().requires_grad_(True) for t in (x, mean, scale, Q)]
+    bits = Entropy_gaussian(Q=1)(cl[0], cl[1], cl[2], cl[3], float(x.mean()))
+    (bits * w.cuda()).sum().backward()
+    for name, a, b in zip("x mean scale Q".split(), cl, leaves):
+        assert rel_l2(a.grad.cpu().numpy(), b.grad.numpy()) < REL_L2, name
+
+
+def test_level_plan_matches_oracle():
+    gold = load_npz("context_model.npz")
+    scene, pc = fixture_model(gold)
+    model = cuda_model(scene, pc)
+    plan = build_level_plan(model, model.get_anchor, model.get_mask_anchor)
+    for i in range(2):
+        assert np.array_equal(plan.inverse[i].cpu().numpy(), gold[f"div_inverse.{i}"])
+        assert np.array_equal(plan.first[i].cpu().numpy(), gold[f"div_first.{i}"])
+    _, inv, first = er.divide_levels(pc.get_anchor, pc.voxel_size, pc.level_scale, pc.get_mask_anchor)
+    ref = er.level_plan(pc.get_anchor.shape[0], inv, first)
+    for a, b in zip(plan.levels, ref):
+        assert np.array_equal(a.orig.cpu().numpy(), b.orig.numpy())
+        if b.ctx_src is not None:
+            assert np.array_equal(a.ctx_src.cpu().numpy(), b.ctx_src.numpy())
+
+
+def test_eval_paths_match_reference_golden():
+    gold = load_npz("context_model.npz")
+    scene, pc = fixture_model(gold)
+    model = cuda_model(scene, pc).eval()
+    fq, sq, oq = multi_scale_generating(model, model.get_anchor, model._hyper_latent, model._anchor_feat,
+                                        model._offset, model.get_scaling, model.get_mask, model.get_mask_anchor)
+    assert symbol_mismatch(fq.cpu().numpy(), gold["eval_feat_q"], 1.0) < 2e-4
+    assert symbol_mismatch(sq.cpu().numpy(), gold["eval_scaling_q"], 1e-3) < 2e-4
+    assert symbol_mismatch(oq.cpu().numpy(), gold["eval_offsets_q"], 0.2) < 2e-4
+    assert rel_l2(fq.cpu().numpy(), gold["eval_feat_q"]) < 1e-3
+    sums = model.estimate_final_bits(return_values=True)
+    assert np.allclose(np.asarray(sums, np.float64), gold["sum_bits"], rtol=2e-4)
+
+
+def test_fixed_step_symbols_are_bit_exact():
+    """With the Q-adjust heads zeroed the steps are exactly Q0, so every quantised value must be
+    bit-identical to the oracle (north_star: bit-exact symbols)."""
+    gold = load_npz("context_model.npz")
+    scene, pc = fixture_model(gold)
+    for w in pc.mlps["grid"]:
+        w[2][172:175] = 0
+        w[3][172:175] = 0
+    model = cuda_model(scene, pc).eval()
+    with torch.no_grad():
+        rf, rs, ro = er.multi_scale_generating(pc, pc.get_anchor, pc._hyper_latent, pc._anchor_feat, pc._offset,
+                                               pc.get_scaling, pc.get_mask, pc.get_mask_anchor)
+    fq, sq, oq = multi_scale_generating(model, model.get_anchor, model._hyper_latent, model._anchor_feat,
+                                        model._offset, model.get_scaling, model.get_mask, model.get_mask_anchor)
+    assert np.array_equal(fq.cpu().numpy(), rf.numpy())
+    assert np.array_equal(sq.cpu().numpy(), rs.numpy())
+    assert np.array_equal(oq.cpu().numpy(), ro.numpy())
+
+
+def test_training_path_matches_reference_golden():
+    gold = load_npz("context_model.npz")
+    scene, pc = fixture_model(gold)
+    model = cuda_model(scene, pc).train()
+    plan = build_level_plan(model, model.get_anchor, model.get_mask_anchor)
+    noise = reference_noise(model._anchor.shape[0], [lv.n for lv in plan.levels], seed=7)
+    res = multi_scale_generating(model, model.get_anchor, model._hyper_latent, model._anchor_feat, model._offset,
+                                 model.get_scaling, model.get_mask, model.get_mask_anchor, predict_bpp=True,
+                                 training=True, noise=noise)
+    assert rel_l2(res[0].cpu().numpy(), gold["train_feat_q"]) < REL_L2
+    assert rel_l2(res[1].cpu().numpy(), gold["train_scaling_q"]) < REL_L2
+    assert rel_l2(res[2].cpu().numpy(), gold["train_offsets_q"]) < REL_L2
+    got = np.asarray([float(v) for v in res[3:7]])
+    assert np.allclose(got, gold["train_bits"], rtol=2e-4), (got, gold["train_bits"])
+    lb = res[7]
+    flat = np.asarray([lb[0], lb[1]] + [v for p in lb[2:] for v in p], np.float64)
+    assert np.allclose(flat, gold["train_level_bpp"], rtol=2e-4)
+
+
+def test_matches_oracle_config1_size_per_element_bits():
+    N = 50_000
+    scene = synthetic.make_scene("chair", N, seed=2)
+    pc = er.make_model(scene)
+    sel = pc.get_mask_anchor
+    with torch.no_grad():
+        ref, det = er.multi_scale_generating(pc, pc.get_anchor[sel], pc._hyper_latent[sel], pc._anchor_feat[sel],
+                                             pc._offset[sel], pc.get_scaling[sel], pc.get_mask[sel],
+                                             predict_bpp=True, return_sum_bits=True, return_details=True)
+    model = cuda_model(scene, pc).eval()
+    msel = model.get_mask_anchor
+    got, gd = multi_scale_generating(model, model.get_anchor[msel], model._hyper_latent[msel],
+                                     model._anchor_feat[msel], model._offset[msel], model.get_scaling[msel],
+                                     model.get_mask[msel], predict_bpp=True, return_sum_bits=True,
+                                     return_details=True)
+    assert np.allclose(np.asarray(got, np.float64), np.asarray(ref, np.float64), rtol=2e-4)
+    assert symbol_mismatch(gd["feat_q"].cpu().numpy(), det["feat_q"].numpy(), 1.0) < 2e-4
+    ref_bits = torch.cat([det["bit_feat"], det["bit_scaling"], det["bit_offsets"]], dim=1).numpy()
+    assert rel_l2(gd["bits"].cpu().numpy(), ref_bits) < 5e-3   # a flipped symbol moves one element's bits
+    assert rel_l2(gd["hyper_q"].cpu().numpy(), det["hyper_q"].numpy()) < 1e-6
+    assert rel_l2(gd["lik_hyper"].cpu().numpy(), det["lik_hyper"].numpy()) < REL_L2
+
+
+def test_full_size_properties():
+    """BASELINE config-3 scale (1.5 M anchors): size-independent properties of the scoring pass."""
+    N = 1_500_000
+    scene = synthetic.make_scene("bicycle", N, seed=0)
+    pc = er.make_model(scene)
+    model = cuda_model(scene, pc).eval()
+    a, mk = model.get_anchor, model.get_mask_anchor
+    (sums, det) = multi_scale_generating(model, a, model._hyper_latent, model._anchor_feat, model._offset,
+                                         model.get_scaling, model.get_mask, mk, predict_bpp=True,
+                                         return_sum_bits=True, return_details=True)
+    plan = det["plan"]
+    assert sum(lv.n for lv in plan.levels) == N                       # every anchor is coded exactly once
+    allidx = torch.cat([lv.orig for lv in plan.levels]).long()
+    assert int(torch.bincount(allidx, minlength=N).max()) == 1
+    ratios = [lv.n / N for lv in plan.levels]
+    assert ratios[0] < ratios[1] < ratios[2]
+    assert all(np.isfinite(v) and v >= 0 for v in sums)
+    bits = det["bits"]
+    assert bool(torch.isfinite(bits).all()) and float(bits.min()) >= 0
+    assert float(bits.max()) <= -np.log2(1e-6) + 1e-3                 # Low_bound caps a symbol at 19.93 bits
+    assert bool((bits[~det["choose"]] == 0).all())                    # masked-out anchors cost nothing
+    # linearity of the accounting: per-element bits add up to the reported sums
+    tot = bits.double().sum().item()
+    assert abs(tot - (sums[2] + sums[3] + sums[4])) / tot < 1e-6
+    # idempotence of the quantiser on its own output (steps are >= 1e-9 and values are on the grid)
+    fq = det["feat_q"]
+    again = multi_scale_generating(model, a, model._hyper_latent, fq, det["offsets_q"], det["scaling_q"],
+                                   model.get_mask, mk)[0]
+    assert float((again - fq).abs().max()) <= 1e-3
