@@ -166,7 +166,7 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
     choose_u8 = choose.contiguous().view(torch.uint8)
 
     sums = torch.zeros(16, dtype=torch.float64, device=dev)  # [4*i..4*i+3] level i (coarse->fine); [12] hyper
-    hyper_q, lik = pc.latent_codec(hyper, training=training, noise=None if noise is None else noise["eb"],
+    hyper_q, lik = pc.latent_codec(hyper, training=training, noise=None if noise is None else noise["eb"].to(dev),
                                    choose=choose_u8, bit_sum=sums[12:13])
     if getattr(pc, "disable_hyper", False):
         hyper_q = hyper_q * 0

@@ -64,6 +64,8 @@ class EntropyBottleneck(nn.Module):
             training = self.training
         x = x.contiguous()
         N, C = x.shape
+        if noise is not None and (not noise.is_cuda or noise.shape != x.shape):
+            raise ValueError("EntropyBottleneck: noise must be a CUDA tensor shaped like x")
         if training and noise is None:
             noise = torch.empty_like(x).uniform_(-0.5, 0.5)
         out, lik = torch.empty_like(x), torch.empty_like(x)

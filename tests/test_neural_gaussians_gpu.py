@@ -41,7 +41,7 @@ def test_matches_reference_golden():
     g = load_npz("neural_gaussians.npz")
     scene, pc = fixture_model(load_npz("context_model.npz"))
     model = cuda_model(scene, pc)
-    assert np.array_equal(model.get_anchor.cpu().numpy(), pc.get_anchor.numpy())  # Quantize_anchor bit exact
+    assert np.array_equal(model.get_anchor.detach().cpu().numpy(), pc.get_anchor.numpy())  # Quantize_anchor bit exact
     cam = synthetic.make_cameras("train", 3, device="cuda")[1]
     assert np.allclose(cam.camera_center.cpu().numpy(), g["camera_center"])
     vis = T(g["visible"]).cuda()
