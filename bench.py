@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract of contextgs_b200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): rendered frames/s @1080p (+ anchor Mbit/s scored, reported beside it).
+Workload at every N: BASELINE.json configs[2] -- the mipnerf360/bicycle-shaped synthetic scene,
+1.5 M anchors, 1920x1080, decoded model (the reference's published-FPS path, train.py:409-414:
+prefilter_voxel + generate_neural_gaussians + rasterize per frame).  One STEP = one frame of one
+camera.  With N > 1 every rank holds a replica and renders its own cameras (weak scaling, no
+data-path collective -- SURVEY.md 8e).
+
+  value : frames/s with the camera matrices already resident on the device.
+  e2e   : the same through the public `render()` call with the camera in HOST memory and the
+          rendered image copied back to pinned host memory inside the timed region.
+  roofline : dominant kernel (by summed device time in a separate stage-timed pass with CUDA
+          events on the launching stream), algorithmic bytes per SURVEY.md 8d / DESIGN.md.
+  cpu_baseline / --impl reference : the CPU oracle (oracle/, OpenMP + torch CPU threads) on the
+          same frame workload, time-bounded.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+N_ANCHORS = 1_500_000
+SCENE_KIND = "bicycle"
+GAUSSIAN_SCALE = 3.0     # base Gaussian size multiplier of the synthetic scene (instances / Gaussian ~ real scenes)
+N_CAMERAS = 16
+METRIC = "rendered frames/sec @1080p"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--anchors", type=int, default=N_ANCHORS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="time budget of the reference arm")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------ helpers
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(n_anchors):
+    """Synthetic scene + decoded values + cameras (CPU tensors; identical bits for both arms)."""
+    from contextgs_b200 import synthetic
+    scene = synthetic.make_scene(SCENE_KIND, n_anchors, seed=0, gaussian_scale=GAUSSIAN_SCALE)
+    dec = synthetic.decoded_scene(scene)
+    cams = synthetic.make_cameras(SCENE_KIND, N_CAMERAS, device="cpu")
+    return scene, dec, cams
+
+
+def make_model(scene, device):
+    """Random-init weights of the reference architecture, seed 6 (identical on every rank and arm:
+    nn.Linear initialises on the CPU generator before the move to `device`)."""
+    from contextgs_b200.gaussian_model import GaussianModel
+    torch.manual_seed(6)
+    m = GaussianModel.from_tensors(scene, device=device)
+    with torch.no_grad():  # break the symmetric EntropyBottleneck init a little (as training would)
+        g = torch.Generator().manual_seed(9)
+        for plist in (m.latent_codec.matrices, m.latent_codec.biases, m.latent_codec.factors):
+            for p in plist:
+                p.add_((torch.randn(p.shape, generator=g) * 0.3).to(p.device))
+    return m
+
+
+def cam_to(cam, device):
+    from types import SimpleNamespace
+    d = dict(vars(cam))
+    for k in ("world_view_transform", "full_proj_transform", "camera_center"):
+        d[k] = d[k].to(device).contiguous()
+    return SimpleNamespace(**d)
+
+
+ALGO_BYTES = {
+    # SURVEY.md 8d / DESIGN.md section 4: compulsory fp32 traffic of an ideal fused implementation
+    "visible_filter": lambda c: 44 * c["N"],
+    "compact_indices": lambda c: 1 * c["N"] + 4 * c["Nv"],
+    "neural_gaussians_fwd": lambda c: 396 * c["Nv"] + 50 * c["Nv"] + 56 * c["P"],
+    "preprocess": lambda c: 116 * c["P"],
+    "depth_sort": lambda c: c["P"] * (4 + 4 * 16),
+    "scan_tiles": lambda c: 12 * c["P"],
+    "emit_instances": lambda c: 20 * c["P"] + 8 * c["R"],
+    "tile_sort": lambda c: c["R"] * (4 + 2 * 16),
+    "tile_ranges": lambda c: 4 * c["R"] + 8 * c["tiles"],
+    "render_fwd": lambda c: 40 * c["R"] + 20 * c["W"] * c["H"],
+    "render_bwd": lambda c: 40 * c["R"] + 20 * c["W"] * c["H"] + 44 * c["P"],
+    "preprocess_bwd": lambda c: 140 * c["P"],
+}
+
+
+# ------------------------------------------------------------------------------------ CPU oracle arm
+
+def oracle_model(scene, dec, m_cpu):
+    """Oracle-side decoded model sharing the product model's weights."""
+    from oracle import entropy_ref
+    pc = entropy_ref.make_model(scene)
+    W = lambda seq: [seq[0].weight.detach(), seq[0].bias.detach(), seq[2].weight.detach(), seq[2].bias.detach()]
+    pc.mlps = {"opacity": W(m_cpu.mlp_opacity), "cov": W(m_cpu.mlp_cov), "color": W(m_cpu.mlp_color),
+               "grid": [W(s) for s in m_cpu.mlp_grid]}
+    eb = pc.latent_codec
+    eb.matrices = [p.detach() for p in m_cpu.latent_codec.matrices]
+    eb.biases = [p.detach() for p in m_cpu.latent_codec.biases]
+    eb.factors = [p.detach() for p in m_cpu.latent_codec.factors]
+    eb.quantiles = m_cpu.latent_codec.quantiles.detach()
+    pc.dec = dec
+    return pc
+
+
+def oracle_frame(pc, cam):
+    """prefilter_voxel + generate_neural_gaussians + rasterize forward on the CPU oracle."""
+    from oracle import entropy_ref, raster_ref
+    d = pc.dec
+    st = raster_ref.make_settings(cam.image_width, cam.image_height, math.tan(cam.FoVx * 0.5),
+                                  math.tan(cam.FoVy * 0.5), (0, 0, 0), 1.0, cam.world_view_transform.numpy(),
+                                  cam.full_proj_transform.numpy())
+    N = d["anchor"].shape[0]
+    ident = np.zeros((N, 4), np.float32)
+    ident[:, 0] = 1
+    radii = raster_ref.preprocess(st, d["anchor"].numpy(), d["scaling"][:, :3].numpy(), ident, filter_only=True)
+    vis = torch.from_numpy(radii > 0)
+    g = entropy_ref.generate_neural_gaussians(pc, cam.camera_center, d["anchor"][vis], d["feat"][vis],
+                                              d["offsets"][vis], d["scaling"][vis], d["masks"][vis])
+    out = raster_ref.forward(st, g["xyz"].numpy(), g["color"].numpy(), g["opacity"].numpy(), g["scaling"].numpy(),
+                             g["rot"].numpy())
+    return out
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference path's CPU restatement (oracle/) on the host cores."""
+    if rank != 0:
+        return
+    from contextgs_b200.gaussian_model import GaussianModel  # parameter container only (CPU tensors, no kernels)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    scene, dec, cams = make_inputs(args.anchors)
+    m_cpu = make_model(scene, "cpu")
+    pc = oracle_model(scene, dec, m_cpu)
+    t_budget = args.cpu_budget_s
+    t_start = time.perf_counter()
+    done_w = 0
+    for i in range(min(args.warmup, 1)):  # CPU code has no clocks / caches to warm beyond one frame
+        oracle_frame(pc, cams[i % len(cams)])
+        done_w += 1
+    per_frame = time.perf_counter() - t_start if done_w else None
+    k_max = args.steps
+    if per_frame is not None:
+        k_max = max(1, min(args.steps, int((t_budget - per_frame) / max(per_frame, 1e-3))))
+    t0 = time.perf_counter()
+    k = 0
+    while k < k_max:
+        oracle_frame(pc, cams[(done_w + k) % len(cams)])
+        k += 1
+        if time.perf_counter() - t0 > t_budget:
+            break
+    dt = time.perf_counter() - t0
+    fps = k / dt
+    sample = (f"{k} full frames (all {args.anchors} anchors, 1920x1080) of the requested {args.steps}; "
+              f"time-bounded to {t_budget:.0f} s of CPU work")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": k,
+        "warmup": done_w, "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference rasterizer / compressai / torchac sources are not in /root/reference; this arm runs the "
+                "CPU oracle restatement (oracle/raster_ref.c with OpenMP + oracle/entropy_ref.py on torch CPU threads)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE configs[2]: mipnerf360/bicycle-shaped synthetic scene, {args.anchors} anchors x 10 "
+                        "offsets, 1920x1080, decoded model, per frame prefilter_voxel + generate_neural_gaussians + "
+                        "rasterize forward; camera batch sharded over ranks",
+            "anchors": args.anchors, "image": [1920, 1080], "cameras": N_CAMERAS, "gaussian_scale": GAUSSIAN_SCALE,
+            "l2_policy": "per-frame inputs (anchor attributes, 464 B x anchors = 696 MB at 1.5 M) exceed the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------ product arm
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from contextgs_b200 import _lib
+    from contextgs_b200.renderer import prefilter_voxel, render
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: contextgs_b200 has no CPU path (use --impl reference for "
+                         "the CPU oracle arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    scene, dec, cams_cpu = make_inputs(args.anchors)
+    pc = make_model(scene, dev)
+    pc_train = pc  # non-decoded replica for the entropy / training extras
+    pc = make_model(scene, dev).replace_with_decoded(**{k: v.to(dev) for k, v in dec.items()})
+    pc.eval()
+    cams_dev = [cam_to(c, dev) for c in cams_cpu]
+    pipe = type("Pipe", (), {"debug": False})()
+    bg = torch.zeros(3, device=dev)
+    W, H = cams_cpu[0].image_width, cams_cpu[0].image_height
+    my_cam = lambda i: (i * world + rank) % N_CAMERAS  # rank r renders cameras r, r+world, ...
+
+    stats = {}
+
+    def frame(cam):
+        with torch.no_grad():
+            vis = prefilter_voxel(cam, pc, pipe, bg)
+            out = render(cam, pc, pipe, bg, visible_mask=vis)
+        stats["P"] = out["radii"].shape[0]
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident pass (value) ------------------------------------------------------
+    _lib.launch_counts(reset=True)
+    with ClockSampler(local_rank) as clk:
+        ms = timed(lambda i: frame(cams_dev[my_cam(i)]), args.steps, args.warmup)
+    launches_total = sum(_lib.launch_counts().values())
+    clocks = clk.summary()
+    fps = world * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end pass: camera in host memory, image to pinned host memory -----------------
+    host_img = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
+    cam_bytes = 4 * (16 + 16 + 3)
+
+    def e2e_step(i):
+        out = frame(cams_cpu[my_cam(i)])              # matrices read on the host, passed by value to the kernels
+        host_img.copy_(out["render"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # the caller owns the pixels before the next frame starts
+    ms_e2e = timed(e2e_step, args.steps, max(args.warmup, 3))
+    fps_e2e = world * args.steps / (ms_e2e * 1e-3)
+
+    # ---- stage-timed pass (separate, so that event records do not perturb `value`) -------------
+    _lib.stage_timing(True)
+    n_prof = max(4, min(args.steps, 16))
+    for i in range(n_prof):
+        out = frame(cams_dev[my_cam(i)])
+    torch.cuda.synchronize()
+    stage_ms, stage_n = _lib.stage_timing_read()
+    _lib.stage_timing(False)
+    saved = None
+    # instance counts of one representative frame (camera 0 of this rank) for the byte model
+    with torch.no_grad():
+        vis = prefilter_voxel(cams_dev[my_cam(0)], pc, pipe, bg)
+        out = render(cams_dev[my_cam(0)], pc, pipe, bg, visible_mask=vis)
+    counts = {"N": args.anchors, "Nv": int(vis.sum()), "P": int(out["radii"].shape[0]), "W": W, "H": H,
+              "tiles": ((W + 15) // 16) * ((H + 15) // 16)}
+    from contextgs_b200 import rasterizer as _r
+    st = _r._state(dev)
+    counts["R"] = int(getattr(st, "last_num_rendered", 0) or 0)
+    per_frame = {k: stage_ms[k] / n_prof for k in stage_ms if stage_n[k] > 0}
+    top = max(per_frame, key=per_frame.get)
+    peak, peak_src = peaks()
+    launches_per_frame_top = stage_n[top] / n_prof
+    top_ms = per_frame[top] / launches_per_frame_top
+    algo = ALGO_BYTES.get(top, lambda c: 0)(counts) / launches_per_frame_top
+    achieved = algo / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo, "ms_per_launch": top_ms,
+                "note": "render_fwd/bwd are FP32/SFU-issue bound per (pixel, instance), not HBM bound (SURVEY 8a R6); "
+                        "HBM fraction reported as the contract requires"}
+
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": cam_bytes,
+                "d2h_bytes_per_step": 3 * H * W * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches_total), "clocks": clocks, "roofline": roofline,
+        "stage_ms_per_frame": {k: round(v, 4) for k, v in sorted(per_frame.items(), key=lambda kv: -kv[1])},
+        "counts": counts,
+    }
+
+    # ---- extras: training-side rasterizer fwd+bwd and the entropy scoring pass -----------------
+    if not args.no_extras:
+        line["extras"] = extras(args, pc, pc_train, cams_dev, my_cam, pipe, bg, timed, world, dev)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, scene, dec, cams_cpu)
+    elif "cpu_baseline" not in line:
+        line["cpu_baseline"] = None
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def extras(args, pc, pc_train, cams_dev, my_cam, pipe, bg, timed, world, dev):
+    from contextgs_b200.neural_gaussians import generate_neural_gaussians
+    from contextgs_b200.rasterizer import GaussianRasterizer
+    from contextgs_b200.renderer import _settings, prefilter_voxel
+    ex = {}
+    H, W = cams_dev[0].image_height, cams_dev[0].image_width
+    gt = torch.rand(3, H, W, device=dev)
+    k = max(4, args.steps // 4)
+
+    def train_raster_step(i):
+        cam = cams_dev[my_cam(i)]
+        with torch.no_grad():
+            vis = prefilter_voxel(cam, pc, pipe, bg)
+            xyz, color, opacity, scaling, rot, _ = generate_neural_gaussians(cam, pc, vis, is_training=False)
+        leaves = [t.detach().requires_grad_(True) for t in (xyz, color, opacity, scaling, rot)]
+        m2d = torch.zeros_like(leaves[0], requires_grad=True)
+        rast = GaussianRasterizer(_settings(cam, pipe, bg, 1.0))
+        img, _ = rast(means3D=leaves[0], means2D=m2d, shs=None, colors_precomp=leaves[1], opacities=leaves[2],
+                      scales=leaves[3], rotations=leaves[4], cov3D_precomp=None)
+        (img - gt).abs().mean().backward()
+    ms = timed(train_raster_step, k, 3)
+    ex["render_fwd_bwd_frames_per_s"] = world * k / (ms * 1e-3)
+
+    # entropy scoring: estimate_final_bits = 3-level context model + likelihoods over ALL anchors
+    pc_train.eval()
+    res = {}
+
+    def score(i, drop_plan):
+        if drop_plan and hasattr(pc_train, "_cgs_level_plan"):
+            del pc_train._cgs_level_plan
+        res["sums"] = pc_train.estimate_final_bits(return_values=True)
+    score(0, True)  # find_divide_scale once (cached in pc.level_scale like the reference, gaussian_model.py:1559)
+    ke = 5
+    ms = timed(lambda i: score(i, True), ke, 2)
+    bits = float(sum(res["sums"][1:5]))
+    ex["anchor_mbits_per_s"] = world * bits * ke / (ms * 1e-3) / 1e6
+    ex["entropy_pass_ms"] = ms / ke
+    ms = timed(lambda i: score(i, False), ke, 2)
+    ex["anchor_mbits_per_s_cached_level_plan"] = world * bits * ke / (ms * 1e-3) / 1e6
+    ex["entropy_pass_ms_cached_level_plan"] = ms / ke
+    ex["scored_mbits"] = bits / 1e6
+    ex["entropy_note"] = ("anchor Mbit/s = estimated bits (hyper+feat+scaling+masked offsets of every valid anchor, "
+                          "what estimate_final_bits sums, gaussian_model.py:1685) / wall time of the full 3-level "
+                          "scoring pass; first figure rebuilds the level division every call like the reference")
+    return ex
+
+
+def cpu_baseline(args, scene, dec, cams_cpu):
+    from contextgs_b200.gaussian_model import GaussianModel  # noqa: F401  (parameter container on the CPU)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m_cpu = make_model(scene, "cpu")
+    pc = oracle_model(scene, dec, m_cpu)
+    t0 = time.perf_counter()
+    k = 0
+    while True:
+        oracle_frame(pc, cams_cpu[k % len(cams_cpu)])
+        k += 1
+        if time.perf_counter() - t0 > 12.0 or k >= 8:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": k / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{k} full frame(s) of the same workload ({args.anchors} anchors, 1920x1080) on the CPU oracle "
+                      f"(oracle/raster_ref.c OpenMP + oracle/entropy_ref.py torch CPU), {dt:.1f} s"}
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,11 @@ _PTR = c_void_p
 SIGNATURES = {
     "cgs_abi_version": (c_int, []),
     "cgs_last_error": (ctypes.c_char_p, []),
+    "cgs_stage_count": (c_int, []),
+    "cgs_stage_name": (ctypes.c_char_p, [c_int]),
+    "cgs_stage_timing_enable": (c_int, [c_int]),
+    "cgs_stage_timing_read": (c_int, [_PTR, _PTR]),
+    "cgs_launch_counts": (c_int, [_PTR, c_int]),
     "cgs_visible_filter": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR]),
     "cgs_mark_visible": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR]),
     "cgs_raster_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int]),
@@ -105,6 +110,35 @@ def ptr(t):
         return None
     assert t.is_contiguous(), "contextgs_b200 kernels need contiguous tensors"
     return t.data_ptr()
+
+
+def stage_names():
+    L = lib()
+    return [L.cgs_stage_name(i).decode() for i in range(L.cgs_stage_count())]
+
+
+def launch_counts(reset=False):
+    """Kernels launched per stage since the last reset (dict name -> count)."""
+    L = lib()
+    n = L.cgs_stage_count()
+    buf = (ctypes.c_int64 * n)()
+    check(L.cgs_launch_counts(buf, int(reset)), "cgs_launch_counts")
+    return dict(zip(stage_names(), list(buf)))
+
+
+def stage_timing(enable):
+    check(lib().cgs_stage_timing_enable(int(enable)), "cgs_stage_timing_enable")
+
+
+def stage_timing_read():
+    """(ms_sum, scopes) dicts per stage; synchronises on the recorded events."""
+    L = lib()
+    n = L.cgs_stage_count()
+    ms = (ctypes.c_double * n)()
+    sc = (ctypes.c_int64 * n)()
+    check(L.cgs_stage_timing_read(ms, sc), "cgs_stage_timing_read")
+    names = stage_names()
+    return dict(zip(names, list(ms))), dict(zip(names, list(sc)))
 
 
 def stream_ptr():

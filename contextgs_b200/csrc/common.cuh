@@ -19,6 +19,23 @@ enum { G_X = 0, G_Y, G_CA, G_CB, G_CC, G_OP, G_R, G_G, G_B, G_DEPTH, G_RADIUS, G
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);
 
+// ---- per-stage device timing + launch accounting (raster_api.cu) ------------------------
+// Every launcher wraps its kernels in a StageScope.  The kernel-launch counter is always kept;
+// CUDA events are recorded around the stage only after cgs_stage_timing_enable(1) (bench.py's
+// separate roofline pass), so the product path pays one predictable branch.
+enum Stage {
+    ST_FILTER = 0, ST_COMPACT, ST_G1_FWD, ST_G1_BWD, ST_PREPROCESS, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT,
+    ST_RANGES, ST_RENDER_FWD, ST_RENDER_BWD, ST_PRE_BWD, ST_EB, ST_CTX_LEVEL, ST_CTX_LEVEL_BWD, ST_BITS, ST_ELEMWISE,
+    ST_LEVEL_DIVIDE, ST_COUNT
+};
+struct StageScope {
+    int stage;
+    cudaStream_t st;
+    int slot;
+    StageScope(int stage, cudaStream_t st, int kernels);
+    ~StageScope();
+};
+
 #define CGS_CHECK_PTR(p)                                   \
     do {                                                   \
         if ((p) == nullptr) {                              \

@@ -380,6 +380,7 @@ static int launch_level(const LevelArgs &a, cudaStream_t st)
         cudaFuncSetAttribute(context_level_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
         attr_set = true;
     }
+    StageScope sc(ST_CTX_LEVEL, st, 1);
     context_level_kernel<K1><<<(a.n_rows + kTM - 1) / kTM, kMlpThreads, sizeof(SM), st>>>(a);
     return check_launch("cgs_context_level_forward");
 }
@@ -402,6 +403,7 @@ extern "C" int cgs_eb_forward(const float *packed_params, int C, const float *hy
         set_error("%s: unsupported channel count %d", __func__, C);
         return -2;
     }
+    StageScope sc(ST_EB, static_cast<cudaStream_t>(stream), 1);
     eb_forward_kernel<<<ew_grid((size_t)N * C), 256, C * kEbParams * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
         packed_params, C, hyper, noise, N, hyper_q, likelihood, choose, bit_sum);
     return check_launch(__func__);
@@ -459,6 +461,7 @@ extern "C" int cgs_gaussian_bits_forward(const float *x, const float *mean, cons
 {
     if (n <= 0 || D <= 0) return 0;
     CGS_CHECK_PTR(x); CGS_CHECK_PTR(mean); CGS_CHECK_PTR(scale); CGS_CHECK_PTR(Q); CGS_CHECK_PTR(bits);
+    StageScope sc(ST_BITS, static_cast<cudaStream_t>(stream), 1);
     gaussian_bits_forward_kernel<<<ew_grid((size_t)n * D), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, mean, scale, Q, q_per_elem, x_mean, (size_t)n, D, bits);
     return check_launch(__func__);
@@ -473,6 +476,7 @@ extern "C" int cgs_gaussian_bits_backward(const float *x, const float *mean, con
     CGS_CHECK_PTR(dx); CGS_CHECK_PTR(dmean); CGS_CHECK_PTR(dscale); CGS_CHECK_PTR(dQ);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!q_per_elem) cudaMemsetAsync(dQ, 0, (size_t)n * sizeof(float), st);
+    StageScope sc(ST_BITS, st, 1);
     gaussian_bits_backward_kernel<<<ew_grid((size_t)n * D), 256, 0, st>>>(x, mean, scale, Q, q_per_elem, x_mean,
                                                                           (size_t)n, D, grad_bits, dx, dmean, dscale,
                                                                           dQ);
@@ -483,6 +487,7 @@ extern "C" int cgs_ste_multistep(const float *x, const float *Q, int64_t n, int 
 {
     if (n <= 0 || D <= 0) return 0;
     CGS_CHECK_PTR(x); CGS_CHECK_PTR(Q); CGS_CHECK_PTR(out);
+    StageScope sc(ST_ELEMWISE, static_cast<cudaStream_t>(stream), 1);
     ste_multistep_kernel<<<ew_grid((size_t)n * D), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, Q, (size_t)n, D,
                                                                                               out);
     return check_launch(__func__);
@@ -494,6 +499,7 @@ extern "C" int cgs_quantize_anchor(const float *anchors, const float *min_host, 
     if (n <= 0) return 0;
     CGS_CHECK_PTR(anchors); CGS_CHECK_PTR(min_host); CGS_CHECK_PTR(max_host); CGS_CHECK_PTR(anchors_q);
     CGS_CHECK_PTR(quantized_v);
+    StageScope sc(ST_ELEMWISE, static_cast<cudaStream_t>(stream), 1);
     quantize_anchor_kernel<<<ew_grid((size_t)n * 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         anchors, make_float3(min_host[0], min_host[1], min_host[2]), make_float3(max_host[0], max_host[1], max_host[2]),
         (size_t)n, anchors_q, quantized_v);

@@ -333,6 +333,7 @@ extern "C" int cgs_neural_gaussians_forward(const float *packed_weights, const i
                              (int)sizeof(NgSmem));
         attr_set = true;
     }
+    StageScope sc(ST_G1_FWD, st, 1);
     neural_gaussians_forward_kernel<<<tiles, kMlpThreads, sizeof(NgSmem), st>>>(
         packed_weights, vis_idx, Nv, anchor, feat, offsets, scaling, mask, campos_host[0], campos_host[1],
         campos_host[2], o_xyz, o_color, o_opacity, o_scaling, o_rot, o_neural_opacity, o_mask, tile_prefix, scan_state,
@@ -369,6 +370,7 @@ extern "C" int cgs_compact_indices(const uint8_t *mask, int N, int32_t *out_idx,
     const int tiles = (N + kCompactTile - 1) / kCompactTile;
     char *ws = static_cast<char *>(workspace);
     cudaMemsetAsync(ws, 0, cgs_compact_workspace_bytes(N), st);
+    StageScope sc(ST_COMPACT, st, 1);
     compact_indices_kernel<<<tiles, kCompactThreads, 0, st>>>(
         mask, N, out_idx, reinterpret_cast<unsigned long long *>(ws),
         reinterpret_cast<uint32_t *>(ws + align_up((size_t)tiles * 8)), count_dev);

@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace cgs {
@@ -24,6 +28,47 @@ int check_launch(const char *what)
         return -100 - (int)e;
     }
     return 0;
+}
+
+// ---- stage timing --------------------------------------------------------------------------
+static const char *const kStageNames[ST_COUNT] = {
+    "visible_filter", "compact_indices", "neural_gaussians_fwd", "neural_gaussians_bwd", "preprocess", "depth_sort",
+    "scan_tiles", "emit_instances", "tile_sort", "tile_ranges", "render_fwd", "render_bwd", "preprocess_bwd",
+    "entropy_bottleneck", "context_level_fwd", "context_level_bwd", "gaussian_bits", "elementwise", "level_divide"};
+
+struct StageTimer {
+    std::mutex mu;
+    bool enabled = false;
+    std::vector<cudaEvent_t> pool;      // event pairs: [2*i] begin, [2*i+1] end
+    std::vector<int> slot_stage;        // stage of each used pair
+    double ms_sum[ST_COUNT] = {0};
+    int64_t scopes[ST_COUNT] = {0};
+};
+static StageTimer g_timer;
+static std::atomic<int64_t> g_launches[ST_COUNT];
+
+StageScope::StageScope(int stage_, cudaStream_t st_, int kernels) : stage(stage_), st(st_), slot(-1)
+{
+    g_launches[stage].fetch_add(kernels, std::memory_order_relaxed);
+    if (!g_timer.enabled) return;
+    std::lock_guard<std::mutex> lk(g_timer.mu);
+    slot = (int)g_timer.slot_stage.size();
+    if (g_timer.pool.size() < (size_t)(2 * slot + 2)) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        g_timer.pool.push_back(a);
+        g_timer.pool.push_back(b);
+    }
+    g_timer.slot_stage.push_back(stage);
+    cudaEventRecord(g_timer.pool[2 * slot], st);
+}
+
+StageScope::~StageScope()
+{
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_timer.mu);
+    cudaEventRecord(g_timer.pool[2 * slot + 1], st);
 }
 
 // launchers defined in the kernel translation units
@@ -111,6 +156,52 @@ using namespace cgs;
 extern "C" int cgs_abi_version(void) { return CGS_ABI_VERSION; }
 extern "C" const char *cgs_last_error(void) { return g_error; }
 
+extern "C" int cgs_stage_count(void) { return ST_COUNT; }
+extern "C" const char *cgs_stage_name(int i) { return i >= 0 && i < ST_COUNT ? kStageNames[i] : ""; }
+
+extern "C" int cgs_stage_timing_enable(int on)
+{
+    std::lock_guard<std::mutex> lk(g_timer.mu);
+    g_timer.enabled = on != 0;
+    g_timer.slot_stage.clear();
+    for (int i = 0; i < ST_COUNT; ++i) {
+        g_timer.ms_sum[i] = 0;
+        g_timer.scopes[i] = 0;
+    }
+    return 0;
+}
+
+extern "C" int cgs_stage_timing_read(double *ms_sum, int64_t *scopes)
+{
+    std::lock_guard<std::mutex> lk(g_timer.mu);
+    for (size_t i = 0; i < g_timer.slot_stage.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(g_timer.pool[2 * i + 1]) != cudaSuccess ||
+            cudaEventElapsedTime(&ms, g_timer.pool[2 * i], g_timer.pool[2 * i + 1]) != cudaSuccess) {
+            set_error("cgs_stage_timing_read: event query failed");
+            cudaGetLastError();
+            return -1;
+        }
+        g_timer.ms_sum[g_timer.slot_stage[i]] += ms;
+        g_timer.scopes[g_timer.slot_stage[i]] += 1;
+    }
+    g_timer.slot_stage.clear();
+    for (int i = 0; i < ST_COUNT; ++i) {
+        if (ms_sum) ms_sum[i] = g_timer.ms_sum[i];
+        if (scopes) scopes[i] = g_timer.scopes[i];
+    }
+    return 0;
+}
+
+extern "C" int cgs_launch_counts(int64_t *launches, int reset)
+{
+    for (int i = 0; i < ST_COUNT; ++i) {
+        if (launches) launches[i] = g_launches[i].load();
+        if (reset) g_launches[i].store(0);
+    }
+    return 0;
+}
+
 static int validate_settings(const cgs_raster_settings *s, const char *fn)
 {
     if (!s) {
@@ -137,6 +228,7 @@ extern "C" int cgs_visible_filter(const cgs_raster_settings *s, int N, const flo
     CGS_CHECK_PTR(scales);
     CGS_CHECK_PTR(rotations);
     CGS_CHECK_PTR(radii);
+    StageScope sc(ST_FILTER, static_cast<cudaStream_t>(stream), 1);
     launch_filter(make_cam(s), N, means3D, scales, rotations, radii, static_cast<cudaStream_t>(stream));
     return check_launch(__func__);
 }
@@ -148,6 +240,7 @@ extern "C" int cgs_mark_visible(const cgs_raster_settings *s, int N, const float
     if (N <= 0) return 0;
     CGS_CHECK_PTR(means3D);
     CGS_CHECK_PTR(visible);
+    StageScope sc(ST_FILTER, static_cast<cudaStream_t>(stream), 1);
     launch_mark_visible(make_cam(s), N, means3D, visible, static_cast<cudaStream_t>(stream));
     return check_launch(__func__);
 }
@@ -207,27 +300,46 @@ extern "C" int cgs_rasterize_forward(const cgs_raster_settings *s, int P, const 
         uint32_t *scan_ticket = reinterpret_cast<uint32_t *>(ws + plan.scan_ticket_off);
         // the element count of the depth sort is P (host-known); park it in the zeroed ticket block
         uint32_t *p_dev = scan_ticket + 1;
-        set_u32_kernel<<<1, 1, 0, st>>>(p_dev, (uint32_t)P);
 
-        launch_preprocess(cam, P, means3D, colors, opacities, scales, rotations, radii, geom, dkeys_in, st);
+        {
+            StageScope sc(ST_PREPROCESS, st, 2);
+            set_u32_kernel<<<1, 1, 0, st>>>(p_dev, (uint32_t)P);
+            launch_preprocess(cam, P, means3D, colors, opacities, scales, rotations, radii, geom, dkeys_in, st);
+        }
         // 1. Gaussians by depth (value = Gaussian id, implicit iota on the first pass)
-        if (int e = sort_pairs(dkeys_in, nullptr, dkeys_out, order, dkeys_tmp, dvals_tmp, p_dev, P, 0, 32,
-                               ws + plan.depth_ws_off, false, st))
-            return e;
+        {
+            StageScope sc(ST_DEPTH_SORT, st, 2 + plan.depth_sort.npass);
+            if (int e = sort_pairs(dkeys_in, nullptr, dkeys_out, order, dkeys_tmp, dvals_tmp, p_dev, P, 0, 32,
+                                   ws + plan.depth_ws_off, false, st))
+                return e;
+        }
         // 2. instance offsets in depth order, R stays on the device
-        launch_scan_tiles(order, geom, P, R_cap, offsets, scan_state, scan_ticket, status, st);
+        {
+            StageScope sc(ST_SCAN, st, 1);
+            launch_scan_tiles(order, geom, P, R_cap, offsets, scan_state, scan_ticket, status, st);
+        }
         if (R_cap > 0) {
             // 3. emit (tile, id)
-            launch_emit_instances(order, geom, offsets, P, cam.grid_x, cam.grid_y, R_cap, tkeys_in, tvals_in, st);
+            {
+                StageScope sc(ST_EMIT, st, 1);
+                launch_emit_instances(order, geom, offsets, P, cam.grid_x, cam.grid_y, R_cap, tkeys_in, tvals_in, st);
+            }
             // 4. stable sort by tile id; last pass writes the ids straight into point_list
             const uint32_t *n_sorted = reinterpret_cast<const uint32_t *>(status + CGS_STATUS_NUM_SORTED);
-            if (int e = sort_pairs(tkeys_in, tvals_in, tkeys_out, point_list, tkeys_tmp, tvals_tmp, n_sorted, R_cap, 0,
-                                   plan.tbits, ws + plan.tile_ws_off, false, st))
-                return e;
+            {
+                StageScope sc(ST_TILE_SORT, st, 2 + plan.tile_sort.npass);
+                if (int e = sort_pairs(tkeys_in, tvals_in, tkeys_out, point_list, tkeys_tmp, tvals_tmp, n_sorted, R_cap,
+                                       0, plan.tbits, ws + plan.tile_ws_off, false, st))
+                    return e;
+            }
+            StageScope sc(ST_RANGES, st, 1);
             launch_tile_ranges(tkeys_out, status, R_cap, ranges, st);
         }
     }
-    launch_render_forward(cam, ranges, point_list, geom, out_color, final_T, n_contrib, st);
+    {
+        StageScope sc(ST_RENDER_FWD, st, 1);
+        launch_render_forward(cam, ranges, point_list, geom, out_color, final_T, n_contrib, st);
+    }
     return check_launch(__func__);
 }
 
@@ -266,7 +378,11 @@ extern "C" int cgs_rasterize_backward(const cgs_raster_settings *s, int P, const
     const CamParams cam = make_cam(s);
     float *acc = static_cast<float *>(workspace);
     cudaMemsetAsync(acc, 0, (size_t)P * 9 * sizeof(float), st);
-    launch_render_backward(cam, ranges, point_list, geom, final_T, n_contrib, dL_dpix, acc, st);
+    {
+        StageScope sc(ST_RENDER_BWD, st, 1);
+        launch_render_backward(cam, ranges, point_list, geom, final_T, n_contrib, dL_dpix, acc, st);
+    }
+    StageScope sc(ST_PRE_BWD, st, 1);
     launch_preprocess_backward(cam, P, means3D, scales, rotations, radii, acc, dL_dmeans3D, dL_dmeans2D, dL_dcolors,
                                dL_dopacity, dL_dscales, dL_drots, st);
     return check_launch(__func__);

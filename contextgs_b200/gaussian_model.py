@@ -208,6 +208,20 @@ class GaussianModel(nn.Module):
         self.x_bound_min = torch.where(mn < 0, mn * 1.2, mn * 0.8)
         self.x_bound_max = torch.where(mx > 0, mx * 1.2, mx * 0.8)
 
+    @torch.no_grad()
+    def replace_with_decoded(self, anchor, hyper, feat, offsets, scaling, masks):
+        """Parameter replacement at the end of `conduct_decoding` (scene/gaussian_model.py:1503-1533):
+        the model afterwards holds DECODED values (quantised anchors, dequantised feat / offsets,
+        scaling already exponentiated, binary masks) and `decoded_version` is True, so rendering
+        skips the context model (gaussian_renderer/__init__.py:103-104) -- the published-FPS path."""
+        P = lambda t: nn.Parameter(t.detach().clone().float().contiguous())
+        self._hyper_latent, self._anchor_feat, self._offset = P(hyper), P(feat), P(offsets)
+        self.decoded_version = True
+        self._anchor, self._scaling, self._mask = P(anchor), P(scaling), P(masks)
+        if hasattr(self, "_cgs_level_plan"):
+            del self._cgs_level_plan
+        return self
+
     def eval(self):
         for m in (self.mlp_opacity, self.mlp_cov, self.mlp_color, self.latent_codec, self.mlp_grid):
             m.eval()

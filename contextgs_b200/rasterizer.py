@@ -78,6 +78,7 @@ class _DeviceState:
     def __init__(self):
         self.workspace = None
         self.r_cap_hint = 0
+        self.last_num_rendered = None
 
 
 _states = {}
@@ -145,6 +146,7 @@ def rasterize_forward_raw(c_settings, means3D, colors, opacities, scales, rotati
         if num_rendered >= 0x7fffffff:
             raise _lib.CgsError("number of (Gaussian, tile) instances exceeds 2^31")
         r_cap = int(num_rendered * 1.25) + 4096
+    st.last_num_rendered = num_rendered
     st.r_cap_hint = max(st.r_cap_hint, min(r_cap, int((num_rendered or r_cap) * 1.5) + 4096))
     saved = dict(geom=geom, point_list=point_list, ranges=ranges, final_T=final_T, n_contrib=n_contrib, status=status,
                  num_rendered=num_rendered, r_cap=r_cap)

@@ -147,7 +147,9 @@ def _anchors(kind, N, voxel, g):
         raise ValueError(kind)
     g.shuffle(x)
     x = np.round(x / voxel)
-    _, first = np.unique(x, axis=0, return_index=True)
+    q = x.astype(np.int64) + (1 << 20)  # |coordinate / voxel| < 2^20 for every scene kind
+    assert q.min() >= 0 and q.max() < (1 << 21)
+    _, first = np.unique((q[:, 0] << 42) | (q[:, 1] << 21) | q[:, 2], return_index=True)
     x = x[np.sort(first)] * voxel
     if x.shape[0] < N:
         raise RuntimeError(f"synthetic scene '{kind}' produced only {x.shape[0]} unique anchors < {N}")
@@ -180,3 +182,24 @@ def make_cameras(kind, n, device="cpu", W=None, H=None):
     if spec["cams"] == "sphere":
         return sphere_cameras(n, W, H, spec["fovx"], spec["radius"], device=device)
     return ring_cameras(n, W, H, spec["fovx"], spec["radius"], spec["height"], device=device)
+
+
+def decoded_scene(scene, x_bound_min=None, x_bound_max=None):
+    """The values a ContextGS model holds AFTER `conduct_decoding` (scene/gaussian_model.py:1503-1533,
+    `decoded_version=True`): anchors on the 16-bit grid (utils/encodings.py:219-227), features /
+    offsets on their base quantisation grids Q = 1 / 0.2 (gaussian_renderer/__init__.py:40-42),
+    scaling already exponentiated (left un-rounded: the synthetic sizes are of the order of the
+    base step 1e-3 and would collapse to zero), binary offset masks.
+    Plain CPU torch: this is synthetic-data construction shared by both bench arms."""
+    a = scene["anchor"]
+    if x_bound_min is None:
+        mn, mx = a.min(dim=0, keepdim=True)[0], a.max(dim=0, keepdim=True)[0]
+        x_bound_min = torch.where(mn < 0, mn * 1.2, mn * 0.8)
+        x_bound_max = torch.where(mx > 0, mx * 1.2, mx * 0.8)
+    interval = (x_bound_max - x_bound_min) / (2 ** 16 - 1) + 1e-6
+    q = torch.clamp(torch.div(a - x_bound_min, interval, rounding_mode="floor"), 0, 2 ** 16 - 1)
+    anchor = q * interval + x_bound_min
+    rnd = lambda x, Q: torch.round(x / Q) * Q
+    mask = (torch.sigmoid(scene["mask"]) > 0.01).float()
+    return dict(anchor=anchor, hyper=torch.round(scene["hyper"]), feat=rnd(scene["feat"], 1.0),
+                offsets=rnd(scene["offset"], 0.2), scaling=torch.exp(scene["scaling"]), masks=mask)

@@ -63,6 +63,18 @@ enum {
 CGS_API int cgs_abi_version(void);
 CGS_API const char *cgs_last_error(void);
 
+/* Measurement hooks (no reference counterpart; the reference only brackets whole iterations with
+ * torch.cuda.Event, train.py:116-117,142,213).  Launch accounting is always on; per-stage CUDA
+ * events are recorded on the caller's stream only between cgs_stage_timing_enable(1) and (0).
+ * cgs_stage_timing_read synchronises on the recorded events and returns, per stage, the summed
+ * milliseconds and the number of timed scopes since enable.  cgs_launch_counts returns the number
+ * of kernels launched per stage (reset != 0 clears the counters). */
+CGS_API int cgs_stage_count(void);
+CGS_API const char *cgs_stage_name(int stage);
+CGS_API int cgs_stage_timing_enable(int on);
+CGS_API int cgs_stage_timing_read(double *ms_sum, int64_t *scopes);
+CGS_API int cgs_launch_counts(int64_t *launches, int reset);
+
 /* ------------------------------------------------------------------ rasterizer (P1, R0-R7) */
 
 /* Replaces `GaussianRasterizer.visible_filter(means3D, scales, rotations)`

@@ -1,7 +1,9 @@
 /*
  * oracle/raster_ref.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
- * Plain-C, single-thread CPU restatement of the tile-based differentiable
+ * Plain-C CPU restatement (OpenMP over Gaussians in preprocess and over pixel rows in the
+ * forward blend -- every pixel/Gaussian is computed independently, results do not depend on the
+ * thread count; the sort and the backward are single-thread) of the tile-based differentiable
  * Gaussian rasterizer that ContextGS calls through `diff_gaussian_rasterization`
  * (reference call sites: gaussian_renderer/__init__.py:179-205 `rasterizer(...)`
  * and :250-285 `rasterizer.visible_filter(...)`).
@@ -156,6 +158,7 @@ void ref_preprocess(const ref_settings *st, int P, const float *means, const flo
     float fx = (float)st->W / (2.0f * st->tanfovx);
     float fy = (float)st->H / (2.0f * st->tanfovy);
     const float *vm = st->view, *pm = st->proj;
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < P; ++i) {
         radii[i] = 0;
         if (!filter_only) {
@@ -275,6 +278,7 @@ void ref_render_forward(const ref_settings *st, const uint32_t *ranges, const ui
 {
     int W = st->W, H = st->H;
     int gx = (W + TILE - 1) / TILE;
+#pragma omp parallel for schedule(dynamic, 4)
     for (int py = 0; py < H; ++py)
         for (int px = 0; px < W; ++px) {
             int tile = (py / TILE) * gx + (px / TILE);
