@@ -1,41 +1,120 @@
 // Per-tile front-to-back alpha blending (forward) and back-to-front gradient pass (backward).
-// One CTA (256 threads = 16x16 pixels) per tile; the tile's depth-ordered 48-byte Gaussian records
-// are gathered into shared memory in 256-record batches with cp.async (LDGSTS, 3 x 16 B per
-// thread), double-buffered so the gather of batch k+1 overlaps the blend of batch k; the blend
-// loop reads the staged records as warp-broadcast LDS.128.
 //
-// Replaces upstream renderCUDA<3> forward/backward (forward.cu / backward.cu, not in the
-// reference tree; call site gaussian_renderer/__init__.py:197-205).
+// One CTA (256 threads) per 16x16 tile, as in upstream renderCUDA<3> (forward.cu / backward.cu, not
+// in the reference tree; call site gaussian_renderer/__init__.py:197-205) -- but the work inside a
+// tile is organised for Blackwell's issue-bound regime (the loop is FP32/SFU-issue bound, not HBM
+// bound: ncu r01 showed 90 % issue-slot utilisation at 1.3 % DRAM):
+//
+//   * each WARP owns an 8x4 pixel block, so a Gaussian's footprint maps to few warps;
+//   * the tile's depth-ordered records are staged 256 at a time (one per thread, register
+//     prefetch of the next batch) into double-buffered shared memory, pre-scaled to the log2
+//     domain (one ex2 per evaluation, no extra multiplies);
+//   * while staging, each thread runs an exact-bound test of ITS record against the 8 warp
+//     blocks (is alpha >= 1/255 reachable anywhere in the block?) and publishes an 8-bit mask;
+//     every warp then compacts the 256 masks into its own index list and blends only records
+//     that can touch its pixels.  `point_list` / `ranges` remain the reference's bounding-square
+//     binning, bit for bit; the masks only drop (record, block) pairs the per-pixel test would
+//     reject for every pixel of the block, so image, final_T and n_contrib are unchanged;
+//   * one __syncthreads per batch; warps whose 32 pixels have saturated skip their lists.
 #include "common.cuh"
 
 namespace cgs {
 
 constexpr int kBatch = 256;
+constexpr int kWarps = kTilePixels / 32;   // 8 warps, each an 8x4 pixel block: 2 across, 4 down
+constexpr int kBlockW = 8, kBlockH = 4;
 constexpr float kAlphaMax = 0.99f;
-constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kTEps = 0.0001f;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+// Conservative test: can a Gaussian with centre (gx, gy), log2-domain conic (A2, B2, C2)
+//   p2(u, v) = A2 u^2 + B2 u v + C2 v^2   (A2 = -a/2 log2e, B2 = -b log2e, C2 = -c/2 log2e),
+// reach p2 >= thr2 (i.e. alpha >= 1/255) at ANY point of the pixel rectangle [x0,x1] x [y0,y1]?
+// p2 is a concave quadratic in (u, v) = pixel - centre; over a rectangle that does not contain
+// the centre its maximum lies on one of the (at most two) edges facing the centre, and on an edge
+// it is a 1-D parabola whose clamped vertex is exact.
+__device__ __forceinline__ bool rect_may_contribute(float gx, float gy, float A2, float B2, float C2, float thr2,
+                                                    float x0, float y0, float x1, float y1)
 {
-    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
-
-// Stage one batch: thread t gathers the record of instance (first + t).
-__device__ __forceinline__ void stage_batch(float4 *dst, const float *__restrict__ geom, uint32_t gid, bool valid)
-{
-    if (valid) {
-        const float4 *src = reinterpret_cast<const float4 *>(geom + (size_t)gid * kGeomStride);
-        cp_async16(dst + 0, src + 0);
-        cp_async16(dst + 1, src + 1);
-        cp_async16(dst + 2, src + 2);
+    const float u0 = x0 - gx, u1 = x1 - gx, v0 = y0 - gy, v1 = y1 - gy;
+    const bool in_x = u0 <= 0.0f && u1 >= 0.0f, in_y = v0 <= 0.0f && v1 >= 0.0f;
+    if (in_x && in_y) return true;
+    float best = -3.0e38f, mag = 0.0f;
+    if (!in_x) {
+        const float u = u0 > 0.0f ? u0 : u1;
+        const float v = fminf(v1, fmaxf(v0, -0.5f * B2 * u / C2));
+        const float m = A2 * u * u + C2 * v * v;   // <= 0
+        const float q = m + B2 * u * v;
+        if (q > best) { best = q; mag = -m; }
     }
+    if (!in_y) {
+        const float v = v0 > 0.0f ? v0 : v1;
+        const float u = fminf(u1, fmaxf(u0, -0.5f * B2 * v / A2));
+        const float m = A2 * u * u + C2 * v * v;
+        const float q = m + B2 * u * v;
+        if (q > best) { best = q; mag = -m; }
+    }
+    return best >= thr2 - (0.02f + 2.0e-5f * mag);  // margin covers the fp32 rounding of both sides
+}
+
+struct StagedRecord {
+    float4 a;  // x y A2 B2
+    float4 b;  // C2 thr2 opacity r
+    float2 c;  // g b
+    uint32_t mask;  // bit w: warp block w may receive a contribution
+};
+
+// Build the staged form of one geom record and its warp-block mask for the tile at (tx0, ty0).
+__device__ __forceinline__ StagedRecord stage_record(const float4 g0, const float4 g1, const float4 g2, bool valid,
+                                                     int tx0, int ty0, int W, int H)
+{
+    StagedRecord s;
+    const float ca = g0.z, cb = g0.w, cc = g1.x, op = g1.y;
+    const float A2 = (-0.5f * kLog2e) * ca, B2 = -kLog2e * cb, C2 = (-0.5f * kLog2e) * cc;
+    const float thr2 = -__log2f(255.0f * op);  // op <= 0 -> NaN/inf: `p2 >= thr2` is then never true
+    s.a = make_float4(g0.x, g0.y, A2, B2);
+    s.b = make_float4(C2, thr2, op, g1.z);
+    s.c = make_float2(g1.w, g2.x);
+    uint32_t mask = 0;
+    if (valid && op > 0.0f && thr2 <= 0.02f) {
+        const bool ellipse = ca > 0.0f && cc > 0.0f && ca * cc > cb * cb;
+        if (!ellipse) {
+            mask = 0xffu;  // degenerate conic: let the per-pixel test decide
+        } else if (rect_may_contribute(g0.x, g0.y, A2, B2, C2, thr2, (float)tx0, (float)ty0,
+                                       (float)min(tx0 + kTile - 1, W - 1), (float)min(ty0 + kTile - 1, H - 1))) {
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const int bx = tx0 + (w & 1) * kBlockW, by = ty0 + (w >> 1) * kBlockH;
+                if (bx < W && by < H &&
+                    rect_may_contribute(g0.x, g0.y, A2, B2, C2, thr2, (float)bx, (float)by,
+                                        (float)min(bx + kBlockW - 1, W - 1), (float)min(by + kBlockH - 1, H - 1)))
+                    mask |= 1u << w;
+            }
+        }
+    } else if (valid && !(op <= 0.0f) && !(op > 0.0f)) {
+        mask = 0xffu;  // NaN opacity: keep the reference's per-pixel behaviour
+    }
+    s.mask = mask;
+    return s;
+}
+
+// Each warp compacts the batch's masks into its own ascending index list.  Returns the list length.
+__device__ __forceinline__ int build_warp_list(const uint8_t *__restrict__ s_mask, uint8_t *__restrict__ list, int warp,
+                                               int lane)
+{
+    int cnt = 0;
+    const uint32_t lt = (1u << lane) - 1;
+#pragma unroll
+    for (int i = 0; i < kBatch / 32; ++i) {
+        const uint32_t m = s_mask[i * 32 + lane];
+        const bool bit = (m >> warp) & 1u;
+        const uint32_t b = __ballot_sync(0xffffffffu, bit);
+        if (bit) list[cnt + __popc(b & lt)] = (uint8_t)(i * 32 + lane);
+        cnt += __popc(b);
+    }
+    __syncwarp();
+    return cnt;
 }
 
 __global__ void __launch_bounds__(kTilePixels)
@@ -43,11 +122,17 @@ render_forward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__res
                       const float *__restrict__ geom, int W, int H, float bg0, float bg1, float bg2,
                       float *__restrict__ out_color, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib)
 {
-    __shared__ __align__(16) float4 s_rec[2][kBatch * 3];
+    __shared__ __align__(16) float4 s_a[2][kBatch];
+    __shared__ __align__(16) float4 s_b[2][kBatch];
+    __shared__ __align__(8) float2 s_c[2][kBatch];
+    __shared__ uint8_t s_mask[2][kBatch];
+    __shared__ uint8_t s_list[kWarps][kBatch];
 
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-    const int tx = threadIdx.x & (kTile - 1), ty = threadIdx.x / kTile;
-    const int px = blockIdx.x * kTile + tx, py = blockIdx.y * kTile + ty;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx0 = blockIdx.x * kTile, ty0 = blockIdx.y * kTile;
+    const int px = tx0 + (warp & 1) * kBlockW + (lane & (kBlockW - 1));
+    const int py = ty0 + (warp >> 1) * kBlockH + (lane >> 3);
     const bool inside = px < W && py < H;
     const float fx = (float)px, fy = (float)py;
 
@@ -56,59 +141,71 @@ render_forward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__res
     const int rounds = (todo + kBatch - 1) / kBatch;
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    uint32_t contributor = 0, last_contributor = 0;
+    uint32_t last_contributor = 0;
     bool done = !inside;
 
-    // prologue: ids for batch 0 and 1, records for batch 0
+    // software pipeline: the record of batch r+1 and the id of batch r+2 are in flight while batch r blends
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
+    bool gv = (int)threadIdx.x < todo;
     uint32_t next_id = 0;
-    {
-        const bool v0 = (int)threadIdx.x < todo;
-        const uint32_t id0 = v0 ? point_list[rb + threadIdx.x] : 0;
-        stage_batch(&s_rec[0][threadIdx.x * 3], geom, id0, v0);
-        cp_async_commit();
-        const int i1 = kBatch + threadIdx.x;
-        if (i1 < todo) next_id = point_list[rb + i1];
+    if (gv) {
+        const uint32_t id0 = point_list[rb + threadIdx.x];
+        const float4 *src = reinterpret_cast<const float4 *>(geom + (size_t)id0 * kGeomStride);
+        g0 = __ldg(src); g1 = __ldg(src + 1); g2 = __ldg(src + 2);
     }
+    if (kBatch + (int)threadIdx.x < todo) next_id = point_list[rb + kBatch + threadIdx.x];
 
     for (int r = 0; r < rounds; ++r) {
         const int buf = r & 1;
-        // issue the gather of batch r+1 (its ids were fetched one round ago), prefetch ids of r+2
         {
+            const StagedRecord s = stage_record(g0, g1, g2, gv, tx0, ty0, W, H);
+            s_a[buf][threadIdx.x] = s.a;
+            s_b[buf][threadIdx.x] = s.b;
+            s_c[buf][threadIdx.x] = s.c;
+            s_mask[buf][threadIdx.x] = (uint8_t)s.mask;
             const int i1 = (r + 1) * kBatch + threadIdx.x;
-            stage_batch(&s_rec[buf ^ 1][threadIdx.x * 3], geom, next_id, i1 < todo);
-            cp_async_commit();
+            gv = i1 < todo;
+            if (gv) {
+                const float4 *src = reinterpret_cast<const float4 *>(geom + (size_t)next_id * kGeomStride);
+                g0 = __ldg(src); g1 = __ldg(src + 1); g2 = __ldg(src + 2);
+            }
             const int i2 = (r + 2) * kBatch + threadIdx.x;
             if (i2 < todo) next_id = point_list[rb + i2];
         }
-        cp_async_wait<1>();
+        // one barrier per batch: publishes buffer `buf`; buffer buf^1 (batch r-1) is free again
+        // because every thread finished blending it before arriving here
         if (__syncthreads_count(done) == kTilePixels) break;
+        if (__all_sync(0xffffffffu, done)) continue;
 
-        const int count = min(kBatch, todo - r * kBatch);
-        const float4 *rec = s_rec[buf];
-        for (int j = 0; !done && j < count; ++j) {
-            ++contributor;
-            const float4 a = rec[3 * j + 0];  // x y ca cb
-            const float4 b = rec[3 * j + 1];  // cc op r g
+        const int n = build_warp_list(s_mask[buf], s_list[warp], warp, lane);
+        const float4 *ra = s_a[buf];
+        const float4 *rbv = s_b[buf];
+        const float2 *rc = s_c[buf];
+        const uint8_t *list = s_list[warp];
+        const uint32_t pos_base = (uint32_t)(r * kBatch + 1);
+        for (int j = 0; j < n; ++j) {
+            if (done) continue;
+            const int idx = list[j];
+            const float4 a = ra[idx];   // x y A2 B2
+            const float4 b = rbv[idx];  // C2 thr2 op r
             const float dx = a.x - fx, dy = a.y - fy;
-            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-            if (power > 0.0f) continue;
-            const float alpha = fminf(kAlphaMax, b.y * __expf(power));
-            if (alpha < kAlphaMin) continue;
+            const float p2 = dx * (a.z * dx + a.w * dy) + b.x * (dy * dy);
+            if (!(p2 >= b.y) || p2 > 0.0f) continue;   // alpha < 1/255, or the reference's `power > 0` guard
+            const float alpha = fminf(kAlphaMax, b.z * exp2f(p2));
             const float test_T = T * (1.0f - alpha);
             if (test_T < kTEps) {
                 done = true;
                 continue;
             }
+            const float2 c = rc[idx];
             const float w = alpha * T;
-            C0 += b.z * w;
-            C1 += b.w * w;
-            C2 += rec[3 * j + 2].x * w;
+            C0 += b.w * w;
+            C1 += c.x * w;
+            C2 += c.y * w;
             T = test_T;
-            last_contributor = contributor;
+            last_contributor = pos_base + (uint32_t)idx;
         }
-        __syncthreads();  // everyone is done with s_rec[buf] before round r+1 overwrites it
     }
-    cp_async_wait<0>();
 
     if (inside) {
         const size_t pid = (size_t)py * W + px;
@@ -123,10 +220,11 @@ render_forward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__res
 
 // ---------------------------------------------------------------------------------------
 // Backward.  Per pixel the upstream recurrence is followed exactly (T rebuilt by division,
-// suffix colour `accum`, bg term).  Per-Gaussian gradients are reduced across the warp with
-// shuffles BEFORE touching memory: one lane issues one red.global.add per value per warp
-// instead of upstream's one atomic per pixel (32x fewer atomics, and whole warps that do not
-// touch a Gaussian skip it with a single ballot).
+// suffix colour `accum`, bg term); the skip tests are the forward's, on the same staged values.
+// Per-Gaussian gradients are reduced across the warp BEFORE touching memory with a
+// transpose-reduce butterfly (8 values in 4+2+1+1+1 = 9 shuffles instead of 40; the 9th value
+// with a plain 5-step reduction), then 9 lanes issue one red.global.add each: one atomic per
+// value per warp instead of upstream's one per pixel.
 // acc[P,9] = {dL/dx, dL/dy, dL/da, dL/db, dL/dc, dL/dopacity, dL/dr, dL/dg, dL/dblue}.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v)
@@ -136,25 +234,56 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+// After the call, lane L with (L & 3) == 0 holds the warp sum of v[id], id = (L >> 2) bit-reversed
+// over 3 bits: id = 4*bit4(L) + 2*bit3(L) + bit2(L).
+__device__ __forceinline__ float warp_transpose_reduce8(float (&v)[8], int lane)
+{
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h16 ? v[i] : v[i + 4];
+        const float keep = h16 ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h8 ? v[i] : v[i + 2];
+        const float keep = h8 ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        const float send = h4 ? v[0] : v[1];
+        const float keep = h4 ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+
 __global__ void __launch_bounds__(kTilePixels)
 render_backward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__restrict__ point_list,
                        const float *__restrict__ geom, int W, int H, float bg0, float bg1, float bg2,
                        const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
                        const float *__restrict__ dL_dpix, float *__restrict__ acc)
 {
-    __shared__ __align__(16) float4 s_rec[kBatch * 3];
-    __shared__ uint32_t s_id[kBatch];
+    __shared__ __align__(16) float4 s_a[2][kBatch];
+    __shared__ __align__(16) float4 s_b[2][kBatch];
+    __shared__ __align__(8) float2 s_c[2][kBatch];
+    __shared__ uint32_t s_id[2][kBatch];
+    __shared__ uint8_t s_mask[2][kBatch];
+    __shared__ uint8_t s_list[kWarps][kBatch];
+    __shared__ int s_max_contrib;
 
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-    const int tx = threadIdx.x & (kTile - 1), ty = threadIdx.x / kTile;
-    const int px = blockIdx.x * kTile + tx, py = blockIdx.y * kTile + ty;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx0 = blockIdx.x * kTile, ty0 = blockIdx.y * kTile;
+    const int px = tx0 + (warp & 1) * kBlockW + (lane & (kBlockW - 1));
+    const int py = ty0 + (warp >> 1) * kBlockH + (lane >> 3);
     const bool inside = px < W && py < H;
     const float fx = (float)px, fy = (float)py;
-    const int lane = threadIdx.x & 31;
 
-    const uint32_t rb = ranges[2 * tile], re = ranges[2 * tile + 1];
-    const int todo = (int)(re - rb);
-    const int rounds = (todo + kBatch - 1) / kBatch;
+    const uint32_t rb = ranges[2 * tile];
 
     const size_t pid = (size_t)py * W + px;
     const size_t HW = (size_t)H * W;
@@ -170,79 +299,105 @@ render_backward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__re
     const float bg_dot = bg0 * d0 + bg1 * d1 + bg2 * d2;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
 
-    // the deepest contributor of any pixel in this tile bounds the work
-    __shared__ int s_max_contrib;
+    // the deepest contributor of any pixel in this tile / warp block bounds the work
     if (threadIdx.x == 0) s_max_contrib = 0;
     __syncthreads();
-    {
-        int m = last_contributor;
+    int warp_max = last_contributor;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) atomicMax(&s_max_contrib, m);
-    }
+    for (int o = 16; o > 0; o >>= 1) warp_max = max(warp_max, __shfl_xor_sync(0xffffffffu, warp_max, o));
+    if (lane == 0) atomicMax(&s_max_contrib, warp_max);
     __syncthreads();
-    const int max_contrib = s_max_contrib;  // positions >= max_contrib contribute to no pixel
-    (void)rounds;
+    const int max_contrib = s_max_contrib;  // list positions >= max_contrib contribute to no pixel
+    const int rounds = (max_contrib + kBatch - 1) / kBatch;
 
-    // walk positions max_contrib-1 .. 0 in batches
-    for (int hi = max_contrib; hi > 0; hi -= kBatch) {
-        const int count = min(kBatch, hi);
-        __syncthreads();
-        if ((int)threadIdx.x < count) {
-            const uint32_t gid = point_list[rb + hi - 1 - threadIdx.x];
-            s_id[threadIdx.x] = gid;
-            const float4 *src = reinterpret_cast<const float4 *>(geom + (size_t)gid * kGeomStride);
-            s_rec[threadIdx.x * 3 + 0] = src[0];
-            s_rec[threadIdx.x * 3 + 1] = src[1];
-            s_rec[threadIdx.x * 3 + 2] = src[2];
+    // batch r covers list positions hi-1 .. hi-count (descending), hi = max_contrib - r*kBatch;
+    // thread t stages position hi-1-t
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
+    uint32_t gid = 0, next_id = 0;
+    bool gv = (int)threadIdx.x < max_contrib;
+    if (gv) {
+        gid = point_list[rb + max_contrib - 1 - threadIdx.x];
+        const float4 *src = reinterpret_cast<const float4 *>(geom + (size_t)gid * kGeomStride);
+        g0 = __ldg(src); g1 = __ldg(src + 1); g2 = __ldg(src + 2);
+    }
+    if (max_contrib - kBatch - 1 - (int)threadIdx.x >= 0) next_id = point_list[rb + max_contrib - kBatch - 1 - threadIdx.x];
+
+    for (int r = 0; r < rounds; ++r) {
+        const int buf = r & 1;
+        const int hi = max_contrib - r * kBatch;
+        {
+            const StagedRecord s = stage_record(g0, g1, g2, gv, tx0, ty0, W, H);
+            s_a[buf][threadIdx.x] = s.a;
+            s_b[buf][threadIdx.x] = s.b;
+            s_c[buf][threadIdx.x] = s.c;
+            s_id[buf][threadIdx.x] = gid;
+            s_mask[buf][threadIdx.x] = (uint8_t)s.mask;
+            const int p1 = hi - kBatch - 1 - (int)threadIdx.x;
+            gv = p1 >= 0;
+            gid = next_id;
+            if (gv) {
+                const float4 *src = reinterpret_cast<const float4 *>(geom + (size_t)gid * kGeomStride);
+                g0 = __ldg(src); g1 = __ldg(src + 1); g2 = __ldg(src + 2);
+            }
+            const int p2i = hi - 2 * kBatch - 1 - (int)threadIdx.x;
+            if (p2i >= 0) next_id = point_list[rb + p2i];
         }
         __syncthreads();
-        for (int j = 0; j < count; ++j) {
-            const int pos = hi - 1 - j;  // 0-based position in the tile's list
-            float g_x = 0.f, g_y = 0.f, g_a = 0.f, g_b = 0.f, g_c = 0.f, g_o = 0.f, g_r = 0.f, g_g = 0.f, g_bl = 0.f;
+        if (hi - kBatch >= warp_max) continue;  // the whole batch lies behind this warp's deepest contributor
+
+        const int n = build_warp_list(s_mask[buf], s_list[warp], warp, lane);
+        const float4 *ra = s_a[buf];
+        const float4 *rbv = s_b[buf];
+        const float2 *rc = s_c[buf];
+        const uint32_t *rid = s_id[buf];
+        const uint8_t *list = s_list[warp];
+        for (int j = 0; j < n; ++j) {
+            const int idx = list[j];
+            const int pos = hi - 1 - idx;  // 0-based position in the tile's list
+            float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float g_bl = 0.f;
             bool active = false;
             if (pos < last_contributor) {
-                const float4 a = s_rec[3 * j + 0];
-                const float4 b = s_rec[3 * j + 1];
+                const float4 a = ra[idx];   // x y A2 B2
+                const float4 b = rbv[idx];  // C2 thr2 op r
                 const float dx = a.x - fx, dy = a.y - fy;
-                const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-                if (power <= 0.0f) {
-                    const float G = __expf(power);
-                    const float alpha = fminf(kAlphaMax, b.y * G);
-                    if (alpha >= kAlphaMin) {
-                        active = true;
-                        const float cb = s_rec[3 * j + 2].x;
-                        T = T / (1.0f - alpha);
-                        const float dch = alpha * T;
-                        acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0;
-                        acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1;
-                        acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2;
-                        lc0 = b.z; lc1 = b.w; lc2 = cb;
-                        float dL_dalpha = (b.z - acc0) * d0 + (b.w - acc1) * d1 + (cb - acc2) * d2;
-                        g_r = dch * d0; g_g = dch * d1; g_bl = dch * d2;
-                        dL_dalpha *= T;
-                        last_alpha = alpha;
-                        dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
-                        const float dL_dG = b.y * dL_dalpha;
-                        const float gdx = G * dx, gdy = G * dy;
-                        g_x = dL_dG * (-gdx * a.z - gdy * a.w);
-                        g_y = dL_dG * (-gdy * b.x - gdx * a.w);
-                        g_a = -0.5f * gdx * dx * dL_dG;
-                        g_b = -gdx * dy * dL_dG;
-                        g_c = -0.5f * gdy * dy * dL_dG;
-                        g_o = G * dL_dalpha;
-                    }
+                const float p2 = dx * (a.z * dx + a.w * dy) + b.x * (dy * dy);
+                if (p2 >= b.y && !(p2 > 0.0f)) {
+                    active = true;
+                    const float2 c = rc[idx];
+                    const float G = exp2f(p2);
+                    const float alpha = fminf(kAlphaMax, b.z * G);
+                    const float ca = a.z * (-2.0f * kLn2), cb = a.w * (-kLn2), cc = b.x * (-2.0f * kLn2);
+                    T = T / (1.0f - alpha);
+                    const float dch = alpha * T;
+                    acc0 = last_alpha * lc0 + (1.0f - last_alpha) * acc0;
+                    acc1 = last_alpha * lc1 + (1.0f - last_alpha) * acc1;
+                    acc2 = last_alpha * lc2 + (1.0f - last_alpha) * acc2;
+                    lc0 = b.w; lc1 = c.x; lc2 = c.y;
+                    float dL_dalpha = (b.w - acc0) * d0 + (c.x - acc1) * d1 + (c.y - acc2) * d2;
+                    g[6] = dch * d0; g[7] = dch * d1; g_bl = dch * d2;
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
+                    const float dL_dG = b.z * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    g[0] = dL_dG * (-gdx * ca - gdy * cb);
+                    g[1] = dL_dG * (-gdy * cc - gdx * cb);
+                    g[2] = -0.5f * gdx * dx * dL_dG;
+                    g[3] = -gdx * dy * dL_dG;
+                    g[4] = -0.5f * gdy * dy * dL_dG;
+                    g[5] = G * dL_dalpha;
                 }
             }
             if (__ballot_sync(0xffffffffu, active) == 0u) continue;
-            g_x = warp_sum(g_x); g_y = warp_sum(g_y); g_a = warp_sum(g_a);
-            g_b = warp_sum(g_b); g_c = warp_sum(g_c); g_o = warp_sum(g_o);
-            g_r = warp_sum(g_r); g_g = warp_sum(g_g); g_bl = warp_sum(g_bl);
-            if (lane == 0) {
-                float *dst = acc + (size_t)s_id[j] * 9;
-                atomicAdd(dst + 0, g_x); atomicAdd(dst + 1, g_y); atomicAdd(dst + 2, g_a);
-                atomicAdd(dst + 3, g_b); atomicAdd(dst + 4, g_c); atomicAdd(dst + 5, g_o);
-                atomicAdd(dst + 6, g_r); atomicAdd(dst + 7, g_g); atomicAdd(dst + 8, g_bl);
+            const float s8 = warp_transpose_reduce8(g, lane);
+            g_bl = warp_sum(g_bl);
+            float *dst = acc + (size_t)rid[idx] * 9;
+            if ((lane & 3) == 0) {
+                const int id = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                atomicAdd(dst + id, s8);
+            } else if (lane == 1) {
+                atomicAdd(dst + 8, g_bl);
             }
         }
     }
