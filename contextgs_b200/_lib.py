@@ -42,6 +42,7 @@ SIGNATURES = {
     "cgs_stage_timing_enable": (c_int, [c_int]),
     "cgs_stage_timing_read": (c_int, [_PTR, _PTR]),
     "cgs_launch_counts": (c_int, [_PTR, c_int]),
+    "cgs_umma_selftest": (c_int, [_PTR, _PTR, c_int, c_int, c_int, _PTR, _PTR, _PTR]),
     "cgs_visible_filter": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR]),
     "cgs_mark_visible": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR]),
     "cgs_raster_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int]),
@@ -54,6 +55,10 @@ SIGNATURES = {
     "cgs_neural_gaussians_workspace_bytes": (c_size_t, [c_int]),
     "cgs_neural_gaussians_forward": (c_int, [_PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
                                              _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
+    "cgs_neural_gaussians_umma_packed_floats": (c_int, []),
+    "cgs_neural_gaussians_umma_workspace_bytes": (c_size_t, [c_int]),
+    "cgs_neural_gaussians_umma_forward": (c_int, [_PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
+                                                  _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
     "cgs_compact_workspace_bytes": (c_size_t, [c_int]),
     "cgs_compact_indices": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, c_size_t, _PTR]),
     "cgs_eb_param_floats": (c_int, []),

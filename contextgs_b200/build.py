@@ -33,6 +33,8 @@ SOURCES = {
     # inner loops use explicit fmaf() and are unaffected.
     "neural_gaussians.cu": ["-fmad=false"],
     "context_model.cu": ["-fmad=false"],
+    "umma_selftest.cu": [],
+    "neural_gaussians_umma.cu": ["-fmad=false"],
 }
 
 

@@ -1,0 +1,394 @@
+// Fused anchor -> neural-Gaussian generation on the tcgen05 tensor cores.
+//
+// Same contract as neural_gaussians.cu (reference: gaussian_renderer/__init__.py:106-145 and the
+// decoder MLPs scene/gaussian_model.py:153-174), but the two MLP layers run as 3xTF32 tcgen05.mma
+// (fp32-grade accuracy, see umma.cuh) with every activation resident in TENSOR MEMORY:
+//
+//   persistent CTA (one per SM, 256 threads = 8 warps), tile = 128 anchors = 128 TMEM lanes;
+//   thread (row = 32*(warp%4) + lane, half = warp/4): two threads share a row and split its columns.
+//
+//   TMEM columns (496 of 512):
+//     [  0,176)  layer-1 input  x_hi [0,56) | x_lo [56,112)      -> later hidden_lo [0,176)
+//     [176,352)  layer-1 accumulator D1 (3 heads x 56: 50 units + 6 zero pads, + 8 pad)
+//                -> overwritten IN PLACE by hidden_hi = tf32(relu(D1 + b1))
+//     [352,496)  layer-2 accumulators: opacity 16 | color 48 | cov 80
+//   shared memory (137 KB): W1 hi/lo [14][176][4], W2 per head hi/lo [14][N_h][4], biases.
+//
+//   per tile:  load + split rows -> tcgen05.st  |  21 MMAs (128x176x8)  |  ReLU epilogue in TMEM
+//              |  63 MMAs (128x{16,32,80}x8)    |  selection, ordered compaction (block scan +
+//              decoupled look-back across tiles), post-processing, 56 B per emitted Gaussian.
+//
+// HBM traffic is the algorithmic minimum (446 B per visible anchor + 56 B per Gaussian): nothing
+// but the final attributes is written.
+#include "umma.cuh"
+
+namespace cgs {
+
+namespace ngu {
+constexpr int kFeat = 50, kK = 10;
+constexpr int kRows = 128;                  // anchors per tile
+constexpr int kThreads = 256;
+constexpr int kK1 = 56;                     // 54 inputs padded to a multiple of 8
+constexpr int kHeadStride = 56;             // hidden units per head incl. zero pads
+constexpr int kN1 = 176;                    // 3 * 56 = 168 padded to a multiple of 16
+// layer-2 output widths.  Output columns are arranged so that every thread's tcgen05.ld starts on
+// an aligned column: opacity of offset k at column 8*(k/5) + k%5, colour channel c of offset k
+// at 4k + c, covariance value i of offset k at 8k + i (the host packs W2 / b2 rows accordingly).
+constexpr int kNo = 16, kNc = 48, kNv = 80;
+// TMEM columns
+constexpr uint32_t kColXHi = 0, kColXLo = 56, kColHLo = 0, kColD1 = 176, kColDo = 352, kColDc = 368, kColDv = 416;
+constexpr uint32_t kTmemCols = 512;
+// packed weight block (floats)
+constexpr int kW1 = (kK1 / 4) * kN1 * 4;    // 9856
+constexpr int kW2o = (kK1 / 4) * kNo * 4;   // 896
+constexpr int kW2c = (kK1 / 4) * kNc * 4;   // 2688
+constexpr int kW2v = (kK1 / 4) * kNv * 4;   // 4480
+constexpr int kOffW1Hi = 0, kOffW1Lo = kOffW1Hi + kW1;
+constexpr int kOffW2oHi = kOffW1Lo + kW1, kOffW2oLo = kOffW2oHi + kW2o;
+constexpr int kOffW2cHi = kOffW2oLo + kW2o, kOffW2cLo = kOffW2cHi + kW2c;
+constexpr int kOffW2vHi = kOffW2cLo + kW2c, kOffW2vLo = kOffW2vHi + kW2v;
+constexpr int kOffB1 = kOffW2vLo + kW2v;
+constexpr int kOffB2o = kOffB1 + kN1, kOffB2c = kOffB2o + kNo, kOffB2v = kOffB2c + kNc;
+constexpr int kPacked = kOffB2v + kNv;      // 36160 floats = 144640 B
+
+struct Smem {
+    float w[kPacked];
+    float anchor[kRows * 3];
+    float scaling[kRows * 6];
+    int src[kRows];
+    uint32_t cnt[kThreads];       // kept Gaussians per (row, half), index = row*2 + half
+    uint32_t excl[kThreads];
+    uint32_t wsum[kThreads / 32];
+    uint32_t tile_base;
+    int tile;
+    uint32_t tmem;
+    int timeout;
+    alignas(8) uint64_t bar[2];
+};
+constexpr uint64_t kAggregate = 1ull << 62, kInclusive = 2ull << 62, kMask = (1ull << 62) - 1;
+}  // namespace ngu
+
+__global__ void __launch_bounds__(ngu::kThreads, 1)
+neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__restrict__ vis_idx, int Nv,
+                             const float *__restrict__ anchor, const float *__restrict__ feat,
+                             const float *__restrict__ offsets, const float *__restrict__ scaling,
+                             const float *__restrict__ mask, float cx, float cy, float cz,
+                             float *__restrict__ o_xyz, float *__restrict__ o_color, float *__restrict__ o_opacity,
+                             float *__restrict__ o_scaling, float *__restrict__ o_rot,
+                             float *__restrict__ o_neural_opacity, uint8_t *__restrict__ o_mask,
+                             unsigned long long *scan_state, uint32_t *ctrl, int32_t *__restrict__ count_out)
+{
+    using namespace ngu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = warp >> 2;
+    const int row = 32 * (warp & 3) + lane;
+    const int num_tiles = (Nv + kRows - 1) / kRows;
+
+    if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
+    if (tid == 0) {
+        umma::mbar_init(&S.bar[0], 1);
+        umma::mbar_init(&S.bar[1], 1);
+        umma::fence_mbar_init();
+        S.timeout = 0;
+        S.tile = (int)atomicAdd(&ctrl[0], 1u);  // tiles are handed out in order: look-back predecessors are running
+    }
+    {
+        const float4 *s4 = reinterpret_cast<const float4 *>(packed_w);
+        float4 *d4 = reinterpret_cast<float4 *>(S.w);
+        for (int i = tid; i < kPacked / 4; i += kThreads) d4[i] = __ldg(s4 + i);
+    }
+    umma::fence_proxy_async_smem();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = S.tmem;
+    const uint32_t tl = tbase + ((uint32_t)(32 * (warp & 3)) << 16);  // this warp's lane quadrant
+
+    uint32_t it = 0;
+    for (int tile = S.tile; tile < num_tiles; tile = S.tile, ++it) {
+        const uint32_t parity = it & 1u;
+        const int row0 = tile * kRows;
+        const int grow = row0 + row;
+        int a = -1;
+        if (grow < Nv) a = vis_idx ? vis_idx[grow] : grow;
+
+        // ---- stage the layer-1 input row: half 0 -> k in [0,32), half 1 -> k in [32,56) ---------
+        {
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = 0.f;
+            if (a >= 0) {
+                const float2 *f2 = reinterpret_cast<const float2 *>(feat + (size_t)a * kFeat);
+                if (half == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 v = __ldg(f2 + j);
+                        x[2 * j] = v.x;
+                        x[2 * j + 1] = v.y;
+                    }
+                    const float ax = anchor[3 * (size_t)a], ay = anchor[3 * (size_t)a + 1], az = anchor[3 * (size_t)a + 2];
+                    S.anchor[3 * row] = ax; S.anchor[3 * row + 1] = ay; S.anchor[3 * row + 2] = az;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) S.scaling[6 * row + k] = scaling[(size_t)a * 6 + k];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) {
+                        const float2 v = __ldg(f2 + 16 + j);
+                        x[2 * j] = v.x;
+                        x[2 * j + 1] = v.y;
+                    }
+                    const float ax = anchor[3 * (size_t)a], ay = anchor[3 * (size_t)a + 1], az = anchor[3 * (size_t)a + 2];
+                    const float vx = ax - cx, vy = ay - cy, vz = az - cz;
+                    const float d = sqrtf(vx * vx + vy * vy + vz * vz);
+                    x[18] = vx / d; x[19] = vy / d; x[20] = vz / d; x[21] = d;
+                }
+            }
+            if (half == 0) S.src[row] = a;
+            const int nchunk = half == 0 ? 4 : 3;
+            const uint32_t k0 = half == 0 ? 0u : 32u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < nchunk) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) umma::split_tf32(x[8 * c + j], hi[j], lo[j]);
+                    umma::tmem_st8(tl + kColXHi + k0 + 8 * c, hi);
+                    umma::tmem_st8(tl + kColXLo + k0 + 8 * c, lo);
+                }
+            }
+        }
+        umma::tmem_wait_st();
+        umma::fence_before_thread_sync();
+        __syncthreads();
+
+        // ---- layer 1: D1[128 x 176] = x[128 x 56] * W1^T ----------------------------------------
+        if (tid == 0) {
+            umma::fence_after_thread_sync();
+            umma::gemm_3xtf32(tbase + kColD1, tbase + kColXHi, tbase + kColXLo, S.w + kOffW1Hi, S.w + kOffW1Lo, kN1, kK1,
+                              true);
+            umma::umma_commit(&S.bar[0]);
+        }
+        if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
+        umma::fence_after_thread_sync();
+
+        // ---- epilogue 1: hidden = relu(D1 + b1), split, back into TMEM (cols 88*half .. +88) ------
+#pragma unroll 1
+        for (int c = 0; c < 11; ++c) {
+            const uint32_t col = (uint32_t)(88 * half + 8 * c);
+            uint32_t v[8], hi[8], lo[8];
+            umma::tmem_ld8(tl + kColD1 + col, v);
+            umma::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float h = fmaxf(__uint_as_float(v[j]) + S.w[kOffB1 + col + j], 0.f);
+                umma::split_tf32(h, hi[j], lo[j]);
+            }
+            umma::tmem_st8(tl + kColD1 + col, hi);
+            umma::tmem_st8(tl + kColHLo + col, lo);
+        }
+        umma::tmem_wait_st();
+        umma::fence_before_thread_sync();
+        __syncthreads();
+
+        // ---- layer 2: three heads -----------------------------------------------------------------
+        if (tid == 0) {
+            umma::fence_after_thread_sync();
+            umma::gemm_3xtf32(tbase + kColDo, tbase + kColD1 + 0 * kHeadStride, tbase + kColHLo + 0 * kHeadStride,
+                              S.w + kOffW2oHi, S.w + kOffW2oLo, kNo, kK1, true);
+            umma::gemm_3xtf32(tbase + kColDc, tbase + kColD1 + 1 * kHeadStride, tbase + kColHLo + 1 * kHeadStride,
+                              S.w + kOffW2cHi, S.w + kOffW2cLo, kNc, kK1, true);
+            umma::gemm_3xtf32(tbase + kColDv, tbase + kColD1 + 2 * kHeadStride, tbase + kColHLo + 2 * kHeadStride,
+                              S.w + kOffW2vHi, S.w + kOffW2vLo, kNv, kK1, true);
+            umma::umma_commit(&S.bar[1]);
+        }
+        if (!umma::mbar_wait(&S.bar[1], parity)) S.timeout = 1;
+        umma::fence_after_thread_sync();
+
+        // ---- epilogue 2: offsets k = 5*half + j ---------------------------------------------------
+        const int kbase = 5 * half;
+        float nop[5];
+        uint32_t keepbits = 0;
+        {
+            uint32_t v[8];
+            umma::tmem_ld8(tl + kColDo + 8 * half, v);
+            umma::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                nop[j] = 0.f;
+                if (a >= 0) {
+                    const int k = kbase + j;
+                    nop[j] = tanhf(__uint_as_float(v[j]) + S.w[kOffB2o + 8 * half + j]) * mask[(size_t)a * kK + k];
+                    const bool keep = nop[j] > 0.0f;
+                    keepbits |= keep ? (1u << j) : 0u;
+                    const size_t gp = (size_t)grow * kK + k;
+                    o_neural_opacity[gp] = nop[j];
+                    o_mask[gp] = keep ? 1 : 0;
+                }
+            }
+        }
+        // ordered ranks: order index = row*2 + half
+        S.cnt[row * 2 + half] = __popc(keepbits);
+        __syncthreads();
+        {
+            const uint32_t v = S.cnt[tid];
+            uint32_t incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (lane == 31) S.wsum[warp] = incl;
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) {
+                const uint32_t c = S.wsum[w];
+                before += w < warp ? c : 0u;
+                total += c;
+            }
+            S.excl[tid] = before + incl - v;
+            if (tid == 0) {
+                // decoupled look-back across tiles (all CTAs are co-resident: grid <= #SMs)
+                volatile unsigned long long *st = scan_state;
+                uint64_t excl = 0;
+                if (tile == 0) {
+                    st[0] = kInclusive | total;
+                } else {
+                    st[tile] = kAggregate | total;
+                    int t = tile - 1;
+                    while (true) {
+                        uint64_t s = st[t];
+                        while ((s >> 62) == 0) s = st[t];
+                        excl += s & kMask;
+                        if ((s >> 62) == 2ull) break;
+                        --t;
+                    }
+                    st[tile] = kInclusive | (excl + total);
+                }
+                S.tile_base = (uint32_t)excl;
+                if (tile == num_tiles - 1) *count_out = (int32_t)(excl + total);
+            }
+            __syncthreads();
+        }
+        uint32_t pos = S.tile_base + S.excl[row * 2 + half];
+
+        // ---- emit (TMEM loads are warp-collective: every thread loads, kept offsets write) ---------
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int k = kbase + j;
+            uint32_t vc[4], vv[8];
+            umma::tmem_ld4(tl + kColDc + 4 * k, vc);
+            umma::tmem_ld8(tl + kColDv + 8 * k, vv);
+            umma::tmem_wait_ld();
+            if (keepbits & (1u << j)) {
+                const float *of = offsets + ((size_t)a * kK + k) * 3;
+                const float *sc = S.scaling + 6 * row;
+                const size_t p = pos++;
+                o_xyz[3 * p + 0] = S.anchor[3 * row + 0] + of[0] * sc[0];
+                o_xyz[3 * p + 1] = S.anchor[3 * row + 1] + of[1] * sc[1];
+                o_xyz[3 * p + 2] = S.anchor[3 * row + 2] + of[2] * sc[2];
+                const float c0 = __uint_as_float(vc[0]) + S.w[kOffB2c + 4 * k + 0];
+                const float c1 = __uint_as_float(vc[1]) + S.w[kOffB2c + 4 * k + 1];
+                const float c2 = __uint_as_float(vc[2]) + S.w[kOffB2c + 4 * k + 2];
+                o_color[3 * p + 0] = 1.0f / (1.0f + expf(-c0));
+                o_color[3 * p + 1] = 1.0f / (1.0f + expf(-c1));
+                o_color[3 * p + 2] = 1.0f / (1.0f + expf(-c2));
+                o_opacity[p] = nop[j];
+                float cv[7];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) cv[i] = __uint_as_float(vv[i]) + S.w[kOffB2v + 8 * k + i];
+                o_scaling[3 * p + 0] = sc[3] * (1.0f / (1.0f + expf(-cv[0])));
+                o_scaling[3 * p + 1] = sc[4] * (1.0f / (1.0f + expf(-cv[1])));
+                o_scaling[3 * p + 2] = sc[5] * (1.0f / (1.0f + expf(-cv[2])));
+                const float nrm = fmaxf(sqrtf(cv[3] * cv[3] + cv[4] * cv[4] + cv[5] * cv[5] + cv[6] * cv[6]), 1e-12f);
+                reinterpret_cast<float4 *>(o_rot)[p] = make_float4(cv[3] / nrm, cv[4] / nrm, cv[5] / nrm, cv[6] / nrm);
+            }
+        }
+        // all TMEM reads of this tile are complete before the next tile's stores / MMAs reuse the columns
+        if (tid == 0) S.tile = (int)atomicAdd(&ctrl[0], 1u);
+        umma::fence_before_thread_sync();
+        __syncthreads();
+        umma::fence_after_thread_sync();
+    }
+
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    if (tid == 0) {
+        // a tensor-core completion that timed out poisons the result: the LAST CTA to leave reports
+        // it through the count (-1), which the host reads anyway
+        if (S.timeout) atomicExch(&ctrl[1], 1u);
+        __threadfence();
+        if (atomicAdd(&ctrl[2], 1u) == gridDim.x - 1 && atomicAdd(&ctrl[1], 0u) != 0u) *count_out = -1;
+    }
+    if (warp == 0) umma::tmem_dealloc(tbase, kTmemCols);
+}
+
+}  // namespace cgs
+
+using namespace cgs;
+
+extern "C" int cgs_neural_gaussians_umma_packed_floats(void) { return ngu::kPacked; }
+
+extern "C" size_t cgs_neural_gaussians_umma_workspace_bytes(int Nv)
+{
+    const size_t tiles = (size_t)(Nv > 0 ? (Nv + ngu::kRows - 1) / ngu::kRows : 1);
+    return align_up(tiles * 8) + align_up(16);
+}
+
+extern "C" int cgs_neural_gaussians_umma_forward(const float *packed_weights, const int32_t *vis_idx, int Nv,
+                                                 const float *anchor, const float *feat, const float *offsets,
+                                                 const float *scaling, const float *mask, const float *campos_host,
+                                                 float *o_xyz, float *o_color, float *o_opacity, float *o_scaling,
+                                                 float *o_rot, float *o_neural_opacity, uint8_t *o_mask,
+                                                 int32_t *count_dev, void *workspace, size_t workspace_bytes,
+                                                 void *stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CGS_CHECK_PTR(count_dev);
+    if (Nv <= 0) {
+        cudaMemsetAsync(count_dev, 0, sizeof(int32_t), st);
+        return check_launch(__func__);
+    }
+    CGS_CHECK_PTR(packed_weights);
+    CGS_CHECK_PTR(anchor);
+    CGS_CHECK_PTR(feat);
+    CGS_CHECK_PTR(offsets);
+    CGS_CHECK_PTR(scaling);
+    CGS_CHECK_PTR(mask);
+    CGS_CHECK_PTR(campos_host);
+    CGS_CHECK_PTR(o_xyz);
+    CGS_CHECK_PTR(o_color);
+    CGS_CHECK_PTR(o_opacity);
+    CGS_CHECK_PTR(o_scaling);
+    CGS_CHECK_PTR(o_rot);
+    CGS_CHECK_PTR(o_neural_opacity);
+    CGS_CHECK_PTR(o_mask);
+    CGS_CHECK_PTR(workspace);
+    if (workspace_bytes < cgs_neural_gaussians_umma_workspace_bytes(Nv)) {
+        set_error("%s: workspace too small", __func__);
+        return -3;
+    }
+    const int tiles = (Nv + ngu::kRows - 1) / ngu::kRows;
+    char *ws = static_cast<char *>(workspace);
+    unsigned long long *scan_state = reinterpret_cast<unsigned long long *>(ws);
+    uint32_t *ctrl = reinterpret_cast<uint32_t *>(ws + align_up((size_t)tiles * 8));  // ticket, error, finished
+    cudaMemsetAsync(ws, 0, align_up((size_t)tiles * 8) + align_up(16), st);
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(neural_gaussians_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(ngu::Smem));
+        if (sm_count <= 0) sm_count = kNumSMs;
+    }
+    const int grid = tiles < sm_count ? tiles : sm_count;
+    StageScope sc(ST_G1_FWD, st, 1);
+    neural_gaussians_umma_kernel<<<grid, ngu::kThreads, sizeof(ngu::Smem), st>>>(
+        packed_weights, vis_idx, Nv, anchor, feat, offsets, scaling, mask, campos_host[0], campos_host[1],
+        campos_host[2], o_xyz, o_color, o_opacity, o_scaling, o_rot, o_neural_opacity, o_mask, scan_state, ctrl,
+        count_dev);
+    return check_launch(__func__);
+}

@@ -1,0 +1,108 @@
+// Stand-alone check of the tcgen05 building blocks in umma.cuh: one CTA computes
+// D[128 x N] = A[128 x K] * W[N x K]^T with the A operand written to TMEM by tcgen05.st, the B
+// operand staged in shared memory in the K-major no-swizzle core-matrix layout, tcgen05.mma
+// (kind::tf32) issued by one thread, completion through tcgen05.commit -> mbarrier, and the result
+// read back with tcgen05.ld.  tests/test_umma_gpu.py compares it with an fp64 product; the fused
+// MLP kernels (neural_gaussians_umma.cu) are built from exactly these pieces.
+#include "umma.cuh"
+
+namespace cgs {
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ W, int N, int K, int mode,
+                     float *__restrict__ D, int32_t *__restrict__ err)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *w_hi = reinterpret_cast<float *>(smem_raw);
+    float *w_lo = w_hi + (size_t)N * K;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
+    if (tid == 0) {
+        umma::mbar_init(&s_bar, 1);
+        umma::fence_mbar_init();
+    }
+    // B operand: element (n, k) -> [(k/4)][n][k%4]
+    for (int i = tid; i < N * K; i += blockDim.x) {
+        const int n = i / K, k = i - n * K;
+        uint32_t hi, lo;
+        umma::split_tf32(W[i], hi, lo);
+        const int dst = (k >> 2) * (N * 4) + n * 4 + (k & 3);
+        w_hi[dst] = __uint_as_float(hi);
+        w_lo[dst] = __uint_as_float(lo);
+    }
+    umma::fence_proxy_async_smem();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = s_tmem;
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    const uint32_t A_HI = 0, A_LO = 64, D_COL = 128;  // K <= 64, N <= 256
+
+    // A operand: thread `tid` owns row tid
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) umma::split_tf32(A[(size_t)tid * K + k0 + j], hi[j], lo[j]);
+        umma::tmem_st8(lane_base + A_HI + k0, hi);
+        umma::tmem_st8(lane_base + A_LO + k0, lo);
+    }
+    umma::tmem_wait_st();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+
+    if (tid == 0) {
+        umma::fence_after_thread_sync();
+        if (mode == 0) {
+            const uint32_t idesc = umma::idesc_tf32(128, N);
+            const uint32_t lbo = (uint32_t)N * 16u;
+            for (int s = 0; s < K / 8; ++s)
+                umma::mma_tf32_ts(tbase + D_COL, tbase + A_HI + 8 * s,
+                                  umma::smem_desc_kmajor(umma::smem_u32(w_hi) + (uint32_t)s * 2u * lbo, lbo, 128u), idesc,
+                                  s > 0 ? 1u : 0u);
+        } else {
+            umma::gemm_3xtf32(tbase + D_COL, tbase + A_HI, tbase + A_LO, w_hi, w_lo, N, K, true);
+        }
+        umma::umma_commit(&s_bar);
+    }
+    const bool ok = umma::mbar_wait(&s_bar, 0);
+    umma::fence_after_thread_sync();
+    if (!ok && lane == 0) atomicExch(err, 1);
+
+    for (int n0 = 0; n0 < N; n0 += 8) {
+        uint32_t v[8];
+        umma::tmem_ld8(lane_base + D_COL + n0, v);
+        umma::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) D[(size_t)tid * N + n0 + j] = __uint_as_float(v[j]);
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tbase, 512);
+}
+
+}  // namespace cgs
+
+using namespace cgs;
+
+extern "C" int cgs_umma_selftest(const float *A, const float *W, int N, int K, int mode, float *D, int32_t *err,
+                                 void *stream)
+{
+    CGS_CHECK_PTR(A);
+    CGS_CHECK_PTR(W);
+    CGS_CHECK_PTR(D);
+    CGS_CHECK_PTR(err);
+    if (N < 16 || N > 256 || (N % 16) || K < 8 || K > 64 || (K % 8)) {
+        set_error("%s: need 16 <= N <= 256 (N %% 16 == 0) and 8 <= K <= 64 (K %% 8 == 0)", __func__);
+        return -2;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)2 * N * K * sizeof(float);
+    cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaMemsetAsync(err, 0, sizeof(int32_t), st);
+    StageScope sc(ST_ELEMWISE, st, 1);
+    umma_selftest_kernel<<<1, 128, smem, st>>>(A, W, N, K, mode, D, err);
+    return check_launch(__func__);
+}

@@ -42,6 +42,75 @@ def pack_decoder_weights(pc):
     return packed
 
 
+def tf32_split(w):
+    """w = hi + lo with both parts exactly representable in TF32 (10 explicit mantissa bits):
+    round-to-nearest on the magnitude, as cvt.rna.tf32.f32 does (contextgs_b200/csrc/umma.cuh)."""
+    def rna(x):
+        return ((x.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    hi = rna(w)
+    return hi, rna(w - hi)
+
+
+def umma_b_operand(W, n_pad, k_pad):
+    """nn.Linear weight W[n, k] -> tcgen05 B operand [k_pad/4][n_pad][4] (K-major core matrices,
+    see umma.cuh), zero padded, split into TF32 hi / lo parts.  Returns (hi.flat, lo.flat)."""
+    n, k = W.shape
+    full = torch.zeros(n_pad, k_pad, device=W.device)
+    full[:n, :k] = W
+    hi, lo = tf32_split(full)
+    lay = lambda t: t.view(n_pad, k_pad // 4, 4).permute(1, 0, 2).contiguous().reshape(-1)
+    return lay(hi), lay(lo)
+
+
+_pack_cache_umma = {}
+
+
+def pack_decoder_weights_umma(pc):
+    """Packed block of the tcgen05 G1 kernel (layout: csrc/neural_gaussians_umma.cu `ngu::kOff*`).
+    Layer-1 rows: head h (opacity, color, cov) occupies rows 56h .. 56h+49.  Layer-2 rows are placed
+    where the epilogue reads them: opacity of offset k at row 8(k/5)+k%5, colour (k, c) at 4k+c,
+    covariance (k, i) at 8k+i."""
+    mods = (pc.get_opacity_mlp, pc.get_color_mlp, pc.get_cov_mlp)
+    params = [p for m in mods for p in (m[0].weight, m[0].bias, m[2].weight, m[2].bias)]
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    ent = _pack_cache_umma.get(id(pc))
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    with torch.no_grad():
+        dev = params[0].device
+        K = pc.n_offsets
+        W1 = torch.zeros(176, 54, device=dev)
+        b1 = torch.zeros(176, device=dev)
+        for h, m in enumerate(mods):
+            W1[56 * h:56 * h + 50] = m[0].weight
+            b1[56 * h:56 * h + 50] = m[0].bias
+        ko = torch.arange(K, device=dev)
+        rows_o = 8 * (ko // 5) + ko % 5
+        rows_c = (4 * ko.view(K, 1) + torch.arange(3, device=dev).view(1, 3)).reshape(-1)
+        rows_v = (8 * ko.view(K, 1) + torch.arange(7, device=dev).view(1, 7)).reshape(-1)
+        parts, biases = list(umma_b_operand(W1, 176, 56)), [b1]
+        for m, rows, n_pad in zip(mods, (rows_o, rows_c, rows_v), (16, 48, 80)):
+            W2 = torch.zeros(n_pad, 50, device=dev)
+            b2 = torch.zeros(n_pad, device=dev)
+            W2[rows] = m[2].weight
+            b2[rows] = m[2].bias
+            parts += list(umma_b_operand(W2, n_pad, 56))
+            biases.append(b2)
+        packed = torch.cat(parts + biases).float().contiguous()
+    assert packed.numel() == _lib.lib().cgs_neural_gaussians_umma_packed_floats()
+    _pack_cache_umma[id(pc)] = (key, packed)
+    return packed
+
+
+def g1_impl():
+    """'umma' (tcgen05 tensor cores, default) or 'simt' (fp32 FMA tiles; kept for cross-checks)."""
+    import os
+    v = os.environ.get("CGS_G1_IMPL", "umma")
+    if v not in ("umma", "simt"):
+        raise ValueError("CGS_G1_IMPL must be 'umma' or 'simt'")
+    return v
+
+
 def compact_indices(mask):
     """Order-preserving device-side `nonzero` of a bool/uint8 mask -> (idx[int32, capacity N], count_dev)."""
     L = _lib.lib()
@@ -56,7 +125,7 @@ def compact_indices(mask):
 
 
 def generate_raw(pc, camera_center, anchor, feat, grid_offsets, grid_scaling, binary_grid_masks, vis_idx=None,
-                 n_vis=None):
+                 n_vis=None, impl=None):
     """Launch the fused kernel.  Inputs are the FULL per-anchor arrays plus an optional visible-index
     list; returns capacity-sized outputs and the device-side Gaussian count."""
     L = _lib.lib()
@@ -69,11 +138,18 @@ def generate_raw(pc, camera_center, anchor, feat, grid_offsets, grid_scaling, bi
         opacity=torch.empty((cap, 1), dtype=f32, device=dev), scaling=torch.empty((cap, 3), dtype=f32, device=dev),
         rot=torch.empty((cap, 4), dtype=f32, device=dev), neural_opacity=torch.empty((cap, 1), dtype=f32, device=dev),
         mask=torch.empty((cap,), dtype=torch.uint8, device=dev), count=torch.empty((1,), dtype=torch.int32, device=dev))
-    ws = torch.empty((L.cgs_neural_gaussians_workspace_bytes(Nv),), dtype=torch.uint8, device=dev)
+    impl = impl or g1_impl()
+    if impl == "umma":
+        ws_bytes, fn, packed = L.cgs_neural_gaussians_umma_workspace_bytes(Nv), L.cgs_neural_gaussians_umma_forward, \
+            pack_decoder_weights_umma(pc)
+    else:
+        ws_bytes, fn, packed = L.cgs_neural_gaussians_workspace_bytes(Nv), L.cgs_neural_gaussians_forward, \
+            pack_decoder_weights(pc)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     from .rasterizer import _host_floats
     campos = (ctypes.c_float * 3)(*_host_floats(camera_center, 3))
-    _lib.check(L.cgs_neural_gaussians_forward(
-        _lib.ptr(pack_decoder_weights(pc)), _lib.ptr(vis_idx), Nv, _lib.ptr(anchor.contiguous()),
+    _lib.check(fn(
+        _lib.ptr(packed), _lib.ptr(vis_idx), Nv, _lib.ptr(anchor.contiguous()),
         _lib.ptr(feat.contiguous()), _lib.ptr(grid_offsets.contiguous()), _lib.ptr(grid_scaling.contiguous()),
         _lib.ptr(binary_grid_masks.contiguous()), campos, _lib.ptr(out["xyz"]), _lib.ptr(out["color"]),
         _lib.ptr(out["opacity"]), _lib.ptr(out["scaling"]), _lib.ptr(out["rot"]), _lib.ptr(out["neural_opacity"]),
@@ -122,6 +198,8 @@ def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_traini
     raw = generate_raw(pc, viewpoint_camera.camera_center, anchor_all, feat, grid_offsets.reshape(N, -1),
                        grid_scaling, binary_grid_masks.reshape(N, -1), vis_idx=vis_idx, n_vis=n_vis)
     P = int(raw["count"].item())
+    if P < 0:
+        raise _lib.CgsError("cgs_neural_gaussians_umma_forward: a tensor-core completion barrier timed out")
     K = pc.n_offsets
     xyz, color, opacity = raw["xyz"][:P], raw["color"][:P], raw["opacity"][:P]
     scaling, rot = raw["scaling"][:P], raw["rot"][:P]

@@ -75,6 +75,12 @@ CGS_API int cgs_stage_timing_enable(int on);
 CGS_API int cgs_stage_timing_read(double *ms_sum, int64_t *scopes);
 CGS_API int cgs_launch_counts(int64_t *launches, int reset);
 
+/* Diagnostic: one 128-row tile GEMM D[128,N] = A[128,K] * W[N,K]^T on the tcgen05 tensor cores with
+ * the building blocks the fused MLP kernels use (A in TMEM, W in shared memory, 3xTF32 when mode = 1,
+ * plain TF32 when mode = 0).  *err (device) is set to 1 if the completion barrier timed out. */
+CGS_API int cgs_umma_selftest(const float *A, const float *W, int N, int K, int mode, float *D, int32_t *err,
+                              void *stream);
+
 /* ------------------------------------------------------------------ rasterizer (P1, R0-R7) */
 
 /* Replaces `GaussianRasterizer.visible_filter(means3D, scales, rotations)`
@@ -147,6 +153,20 @@ CGS_API int cgs_neural_gaussians_forward(const float *packed_weights, const int3
                                          float *o_xyz, float *o_color, float *o_opacity, float *o_scaling,
                                          float *o_rot, float *o_neural_opacity, uint8_t *o_mask, int32_t *count_dev,
                                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* The same operation with the two MLP layers on the tcgen05 tensor cores (3xTF32, activations resident
+ * in tensor memory; csrc/neural_gaussians_umma.cu).  Identical arguments and outputs; the packed
+ * weight block differs (TF32 hi/lo split, K-major core-matrix layout: contextgs_b200/neural_gaussians.py
+ * pack_decoder_weights_umma).  *count_dev = -1 reports a tensor-core completion time-out. */
+CGS_API int cgs_neural_gaussians_umma_packed_floats(void);
+CGS_API size_t cgs_neural_gaussians_umma_workspace_bytes(int Nv);
+CGS_API int cgs_neural_gaussians_umma_forward(const float *packed_weights, const int32_t *vis_idx, int Nv,
+                                              const float *anchor, const float *feat, const float *offsets,
+                                              const float *scaling, const float *mask, const float *campos_host,
+                                              float *o_xyz, float *o_color, float *o_opacity, float *o_scaling,
+                                              float *o_rot, float *o_neural_opacity, uint8_t *o_mask,
+                                              int32_t *count_dev, void *workspace, size_t workspace_bytes,
+                                              void *stream);
 
 /* Order-preserving compaction of a byte mask into an index list (the device-side replacement of
  * the reference's `tensor[bool_mask]` / torch.nonzero host-synchronising idiom, e.g.

@@ -13,6 +13,13 @@ pytestmark = pytest.mark.gpu
 REL_L2 = 1e-4
 
 
+@pytest.fixture(params=["umma", "simt"], autouse=True)
+def g1_impl(request, monkeypatch):
+    """Every test runs against the tcgen05 kernel (default) and the fp32-FMA kernel."""
+    monkeypatch.setenv("CGS_G1_IMPL", request.param)
+    return request.param
+
+
 def _check_against(out, ref_mask, ref, pre_opacity=None):
     xyz, color, opacity, scaling, rot, neural_opacity, mask = out[:7]
     m = mask.cpu().numpy()
