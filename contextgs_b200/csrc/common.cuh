@@ -88,6 +88,41 @@ __device__ __forceinline__ void get_rect(float px, float py, int radius, int gx,
     y1 = min(gy, max(0, (int)((py + r + (float)(kTile - 1)) / (float)kTile)));
 }
 
+// ---- decoupled look-back, warp-wide ------------------------------------------------------------
+// Chained scan across CTA tiles: state[t] packs a 2-bit flag (0 empty, 1 aggregate, 2 inclusive
+// prefix) with a 62-bit value in ONE 64-bit word, so no fence is needed between value and flag.
+// Called by all 32 lanes of one warp; `tile` and `total` are warp-uniform.  Returns the exclusive
+// prefix of `tile`.  The warp inspects 32 predecessors per round (one global round trip instead of
+// 32 dependent ones), which matters when ~148 persistent CTAs publish at about the same time.
+constexpr uint64_t kLbAggregate = 1ull << 62, kLbInclusive = 2ull << 62, kLbMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t lookback_exclusive(unsigned long long *state, int tile, uint64_t total)
+{
+    volatile unsigned long long *st = state;
+    const int lane = threadIdx.x & 31;
+    if (tile == 0) {
+        if (lane == 0) st[0] = kLbInclusive | total;
+        return 0;
+    }
+    if (lane == 0) st[tile] = kLbAggregate | total;
+    uint64_t excl = 0;
+    for (int base = tile - 1;; base -= 32) {
+        const int t = base - lane;
+        uint64_t s = t >= 0 ? st[t] : kLbInclusive;  // a virtual inclusive zero precedes tile 0
+        while (__any_sync(0xffffffffu, (s >> 62) == 0))
+            if ((s >> 62) == 0) s = st[t];
+        const uint32_t incl = __ballot_sync(0xffffffffu, (s >> 62) == 2ull);
+        const int first = incl ? __ffs(incl) - 1 : 32;
+        uint64_t v = lane <= first ? (s & kLbMask) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (incl) break;
+    }
+    if (lane == 0) st[tile] = kLbInclusive | (excl + total);
+    return excl;
+}
+
 // ---- sort / scan primitives (radix_sort.cu) -------------------------------------------
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;

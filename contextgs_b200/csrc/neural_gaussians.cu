@@ -49,7 +49,6 @@ struct NgSmem {
     uint32_t tile_id;
 };
 
-constexpr uint64_t kNgAggregate = 1ull << 62, kNgInclusive = 2ull << 62, kNgMask = (1ull << 62) - 1;
 
 __global__ void __launch_bounds__(kMlpThreads, 1)
 neural_gaussians_forward_kernel(const float *__restrict__ packed_w, const int *__restrict__ vis_idx, int Nv,
@@ -157,26 +156,13 @@ neural_gaussians_forward_kernel(const float *__restrict__ packed_w, const int *_
     (void)cnt;
 
     // ---- chained scan over tiles -----------------------------------------------------------
-    if (tid == 0) {
-        volatile unsigned long long *st = scan_state;
-        uint64_t excl = 0;
-        if (tile == 0) {
-            st[0] = kNgInclusive | tile_total;
-        } else {
-            st[tile] = kNgAggregate | tile_total;
-            int t = tile - 1;
-            while (true) {
-                uint64_t s = st[t];
-                while ((s >> 62) == 0) s = st[t];
-                excl += s & kNgMask;
-                if ((s >> 62) == 2ull) break;
-                --t;
-            }
-            st[tile] = kNgInclusive | (excl + tile_total);
+    if (warp == 0) {
+        const uint64_t excl = lookback_exclusive(scan_state, tile, tile_total);
+        if (lane == 0) {
+            S.tile_base = (uint32_t)excl;
+            tile_prefix[tile] = (uint32_t)excl;
+            if (tile == num_tiles - 1) *count_out = (int32_t)(excl + tile_total);
         }
-        S.tile_base = (uint32_t)excl;
-        tile_prefix[tile] = (uint32_t)excl;
-        if (tile == num_tiles - 1) *count_out = (int32_t)(excl + tile_total);
     }
     __syncthreads();
     const uint32_t base = S.tile_base;
@@ -251,25 +237,12 @@ compact_indices_kernel(const uint8_t *__restrict__ mask, int N, int *__restrict_
         wex += w < warp ? s_warp[w] : 0u;
         total += s_warp[w];
     }
-    if (threadIdx.x == 0) {
-        volatile unsigned long long *st = scan_state;
-        uint64_t excl = 0;
-        if (tile == 0) {
-            st[0] = kNgInclusive | total;
-        } else {
-            st[tile] = kNgAggregate | total;
-            int t = tile - 1;
-            while (true) {
-                uint64_t s = st[t];
-                while ((s >> 62) == 0) s = st[t];
-                excl += s & kNgMask;
-                if ((s >> 62) == 2ull) break;
-                --t;
-            }
-            st[tile] = kNgInclusive | (excl + total);
+    if (warp == 0) {
+        const uint64_t excl = lookback_exclusive(scan_state, tile, total);
+        if (lane == 0) {
+            s_base = (uint32_t)excl;
+            if (tile == (N - 1) / kCompactTile) *count_out = (int32_t)(excl + total);
         }
-        s_base = (uint32_t)excl;
-        if (tile == (N - 1) / kCompactTile) *count_out = (int32_t)(excl + total);
     }
     __syncthreads();
     uint32_t pos = s_base + wex + incl - c;

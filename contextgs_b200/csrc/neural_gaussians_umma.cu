@@ -51,21 +51,92 @@ constexpr int kOffB1 = kOffW2vLo + kW2v;
 constexpr int kOffB2o = kOffB1 + kN1, kOffB2c = kOffB2o + kNo, kOffB2v = kOffB2c + kNc;
 constexpr int kPacked = kOffB2v + kNv;      // 36160 floats = 144640 B
 
+constexpr int kTileGauss = kRows * kK;       // 1280 (anchor, offset) pairs per tile
+
 struct Smem {
     float w[kPacked];
-    float anchor[kRows * 3];
-    float scaling[kRows * 6];
-    int src[kRows];
+    // per-tile output staging: Gaussians are written here at their tile-local rank and then copied
+    // to HBM as contiguous, fully coalesced segments
+    float o_xyz[kTileGauss * 3], o_color[kTileGauss * 3], o_opacity[kTileGauss], o_scaling[kTileGauss * 3];
+    float4 o_rot[kTileGauss];
+    float o_nop[kTileGauss];
+    uint8_t o_keep[kTileGauss];
     uint32_t cnt[kThreads];       // kept Gaussians per (row, half), index = row*2 + half
     uint32_t excl[kThreads];
     uint32_t wsum[kThreads / 32];
-    uint32_t tile_base;
-    int tile;
+    uint32_t tile_base, tile_total;
     uint32_t tmem;
     int timeout;
-    alignas(8) uint64_t bar[2];
+    alignas(8) uint64_t bar[3];
 };
-constexpr uint64_t kAggregate = 1ull << 62, kInclusive = 2ull << 62, kMask = (1ull << 62) - 1;
+
+// Everything one thread reads from HBM for one tile row (its half of the MLP input + what its five
+// offsets need in the last epilogue).  Loaded one tile AHEAD into registers so that the ~1 us of
+// HBM latency hides behind the previous tile's MMAs and epilogues.
+struct RowInputs {
+    float x[32];      // half 0: feat[0..31]; half 1: feat[32..49], view dir (3), distance, 0, 0, ...
+    float mask[5];
+    float off[15];
+    float anchor[3];
+    float sc[6];
+    int a;            // source anchor (-1: padding row)
+};
+
+__device__ __forceinline__ void load_row(RowInputs &r, int a, int half, const float *__restrict__ anchor,
+                                         const float *__restrict__ feat, const float *__restrict__ offsets,
+                                         const float *__restrict__ scaling, const float *__restrict__ mask, float cx,
+                                         float cy, float cz)
+{
+    r.a = a;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r.x[j] = 0.f;
+    if (a < 0) return;
+    const float2 *f2 = reinterpret_cast<const float2 *>(feat + (size_t)a * kFeat);
+    if (half == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float2 v = __ldg(f2 + j);
+            r.x[2 * j] = v.x;
+            r.x[2 * j + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const float2 v = __ldg(f2 + 16 + j);
+            r.x[2 * j] = v.x;
+            r.x[2 * j + 1] = v.y;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r.anchor[i] = __ldg(anchor + 3 * (size_t)a + i);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.sc[i] = __ldg(scaling + 6 * (size_t)a + i);
+    const int kbase = 5 * half;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) r.mask[j] = __ldg(mask + (size_t)a * kK + kbase + j);
+#pragma unroll
+    for (int j = 0; j < 15; ++j) r.off[j] = __ldg(offsets + ((size_t)a * kK + kbase) * 3 + j);
+}
+
+// view direction / distance (gaussian_renderer/__init__.py:106-110) -- computed when the row is staged,
+// not when it is loaded, so that nothing waits on the prefetch
+__device__ __forceinline__ void finish_row(RowInputs &r, int half, float cx, float cy, float cz)
+{
+    if (half == 1 && r.a >= 0) {
+        const float vx = r.anchor[0] - cx, vy = r.anchor[1] - cy, vz = r.anchor[2] - cz;
+        const float d = sqrtf(vx * vx + vy * vy + vz * vz);
+        r.x[18] = vx / d; r.x[19] = vy / d; r.x[20] = vz / d; r.x[21] = d;
+    }
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// tanh(x) = 1 - 2 / (exp(2x) + 1): absolute error ~1e-7 (the selection `tanh(x) * mask > 0` can only
+// flip where |x| is at rounding level, as for any fp32 evaluation of the MLP)
+__device__ __forceinline__ float fast_tanh(float x)
+{
+    const float e = __expf(2.0f * fminf(fmaxf(x, -15.0f), 15.0f));
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
 }  // namespace ngu
 
 __global__ void __launch_bounds__(ngu::kThreads, 1)
@@ -90,9 +161,9 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
     if (tid == 0) {
         umma::mbar_init(&S.bar[0], 1);
         umma::mbar_init(&S.bar[1], 1);
+        umma::mbar_init(&S.bar[2], 1);
         umma::fence_mbar_init();
         S.timeout = 0;
-        S.tile = (int)atomicAdd(&ctrl[0], 1u);  // tiles are handed out in order: look-back predecessors are running
     }
     {
         const float4 *s4 = reinterpret_cast<const float4 *>(packed_w);
@@ -105,55 +176,35 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
     umma::fence_after_thread_sync();
     const uint32_t tbase = S.tmem;
     const uint32_t tl = tbase + ((uint32_t)(32 * (warp & 3)) << 16);  // this warp's lane quadrant
+    // Static round-robin tile order: the grid never exceeds the SM count and a CTA needs a whole SM
+    // (145 KB shared memory, all 512 TMEM columns), so every CTA is resident and the tiles of one
+    // round run concurrently -- the look-back predecessor of a tile is at most one round behind.
+    int tile = blockIdx.x, next_tile = blockIdx.x + gridDim.x;
 
-    uint32_t it = 0;
-    for (int tile = S.tile; tile < num_tiles; tile = S.tile, ++it) {
+    auto source_of = [&](int t) -> int {
+        const int g = t * kRows + row;
+        if (t >= num_tiles || g >= Nv) return -1;
+        return vis_idx ? __ldg(vis_idx + g) : g;
+    };
+
+    RowInputs cur;
+    load_row(cur, source_of(tile), half, anchor, feat, offsets, scaling, mask, cx, cy, cz);
+
+    for (uint32_t it = 0; tile < num_tiles; ++it) {
         const uint32_t parity = it & 1u;
-        const int row0 = tile * kRows;
-        const int grow = row0 + row;
-        int a = -1;
-        if (grow < Nv) a = vis_idx ? vis_idx[grow] : grow;
+        const int grow = tile * kRows + row;
+        const int a = cur.a;
 
         // ---- stage the layer-1 input row: half 0 -> k in [0,32), half 1 -> k in [32,56) ---------
         {
-            float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = 0.f;
-            if (a >= 0) {
-                const float2 *f2 = reinterpret_cast<const float2 *>(feat + (size_t)a * kFeat);
-                if (half == 0) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float2 v = __ldg(f2 + j);
-                        x[2 * j] = v.x;
-                        x[2 * j + 1] = v.y;
-                    }
-                    const float ax = anchor[3 * (size_t)a], ay = anchor[3 * (size_t)a + 1], az = anchor[3 * (size_t)a + 2];
-                    S.anchor[3 * row] = ax; S.anchor[3 * row + 1] = ay; S.anchor[3 * row + 2] = az;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) S.scaling[6 * row + k] = scaling[(size_t)a * 6 + k];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) {
-                        const float2 v = __ldg(f2 + 16 + j);
-                        x[2 * j] = v.x;
-                        x[2 * j + 1] = v.y;
-                    }
-                    const float ax = anchor[3 * (size_t)a], ay = anchor[3 * (size_t)a + 1], az = anchor[3 * (size_t)a + 2];
-                    const float vx = ax - cx, vy = ay - cy, vz = az - cz;
-                    const float d = sqrtf(vx * vx + vy * vy + vz * vz);
-                    x[18] = vx / d; x[19] = vy / d; x[20] = vz / d; x[21] = d;
-                }
-            }
-            if (half == 0) S.src[row] = a;
-            const int nchunk = half == 0 ? 4 : 3;
+            finish_row(cur, half, cx, cy, cz);
             const uint32_t k0 = half == 0 ? 0u : 32u;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                if (c < nchunk) {
+                if (c < 3 || half == 0) {
                     uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) umma::split_tf32(x[8 * c + j], hi[j], lo[j]);
+                    for (int j = 0; j < 8; ++j) umma::split_tf32(cur.x[8 * c + j], hi[j], lo[j]);
                     umma::tmem_st8(tl + kColXHi + k0 + 8 * c, hi);
                     umma::tmem_st8(tl + kColXLo + k0 + 8 * c, lo);
                 }
@@ -170,6 +221,8 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                               true);
             umma::umma_commit(&S.bar[0]);
         }
+        // while the tensor core works: start the next tile's HBM reads (index first, rows below)
+        const int a_next = source_of(next_tile);
         if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
         umma::fence_after_thread_sync();
 
@@ -192,21 +245,25 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
         umma::fence_before_thread_sync();
         __syncthreads();
 
-        // ---- layer 2: three heads -----------------------------------------------------------------
+        // ---- layer 2: opacity head first (it decides the selection), then colour and covariance ----
         if (tid == 0) {
             umma::fence_after_thread_sync();
             umma::gemm_3xtf32(tbase + kColDo, tbase + kColD1 + 0 * kHeadStride, tbase + kColHLo + 0 * kHeadStride,
                               S.w + kOffW2oHi, S.w + kOffW2oLo, kNo, kK1, true);
+            umma::umma_commit(&S.bar[1]);
             umma::gemm_3xtf32(tbase + kColDc, tbase + kColD1 + 1 * kHeadStride, tbase + kColHLo + 1 * kHeadStride,
                               S.w + kOffW2cHi, S.w + kOffW2cLo, kNc, kK1, true);
             umma::gemm_3xtf32(tbase + kColDv, tbase + kColD1 + 2 * kHeadStride, tbase + kColHLo + 2 * kHeadStride,
                               S.w + kOffW2vHi, S.w + kOffW2vLo, kNv, kK1, true);
-            umma::umma_commit(&S.bar[1]);
+            umma::umma_commit(&S.bar[2]);
         }
+        // the next tile's rows travel while layer 2 and the epilogues run
+        RowInputs nxt;
+        load_row(nxt, a_next, half, anchor, feat, offsets, scaling, mask, cx, cy, cz);
         if (!umma::mbar_wait(&S.bar[1], parity)) S.timeout = 1;
         umma::fence_after_thread_sync();
 
-        // ---- epilogue 2: offsets k = 5*half + j ---------------------------------------------------
+        // ---- epilogue 2a: selection of offsets k = 5*half + j, ordered ranks -------------------------
         const int kbase = 5 * half;
         float nop[5];
         uint32_t keepbits = 0;
@@ -218,19 +275,16 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
             for (int j = 0; j < 5; ++j) {
                 nop[j] = 0.f;
                 if (a >= 0) {
-                    const int k = kbase + j;
-                    nop[j] = tanhf(__uint_as_float(v[j]) + S.w[kOffB2o + 8 * half + j]) * mask[(size_t)a * kK + k];
-                    const bool keep = nop[j] > 0.0f;
-                    keepbits |= keep ? (1u << j) : 0u;
-                    const size_t gp = (size_t)grow * kK + k;
-                    o_neural_opacity[gp] = nop[j];
-                    o_mask[gp] = keep ? 1 : 0;
+                    nop[j] = fast_tanh(__uint_as_float(v[j]) + S.w[kOffB2o + 8 * half + j]) * cur.mask[j];
+                    keepbits |= nop[j] > 0.0f ? (1u << j) : 0u;
                 }
+                S.o_nop[row * kK + kbase + j] = nop[j];
+                S.o_keep[row * kK + kbase + j] = (keepbits >> j) & 1u;
             }
         }
-        // ordered ranks: order index = row*2 + half
-        S.cnt[row * 2 + half] = __popc(keepbits);
+        S.cnt[row * 2 + half] = __popc(keepbits);  // order index = row*2 + half
         __syncthreads();
+        uint32_t total = 0;
         {
             const uint32_t v = S.cnt[tid];
             uint32_t incl = v;
@@ -241,7 +295,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
             }
             if (lane == 31) S.wsum[warp] = incl;
             __syncthreads();
-            uint32_t before = 0, total = 0;
+            uint32_t before = 0;
 #pragma unroll
             for (int w = 0; w < kThreads / 32; ++w) {
                 const uint32_t c = S.wsum[w];
@@ -249,32 +303,24 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                 total += c;
             }
             S.excl[tid] = before + incl - v;
-            if (tid == 0) {
-                // decoupled look-back across tiles (all CTAs are co-resident: grid <= #SMs)
-                volatile unsigned long long *st = scan_state;
-                uint64_t excl = 0;
-                if (tile == 0) {
-                    st[0] = kInclusive | total;
-                } else {
-                    st[tile] = kAggregate | total;
-                    int t = tile - 1;
-                    while (true) {
-                        uint64_t s = st[t];
-                        while ((s >> 62) == 0) s = st[t];
-                        excl += s & kMask;
-                        if ((s >> 62) == 2ull) break;
-                        --t;
-                    }
-                    st[tile] = kInclusive | (excl + total);
-                }
+        }
+        __syncthreads();  // tile-local ranks complete
+        if (warp == 0) {
+            // decoupled look-back across tiles.  Only warp 0 waits here: the other warps already
+            // post-process their offsets (they need tile_base only for the final copy), so the
+            // cross-CTA latency hides behind the colour / covariance MMAs and epilogue 2b.
+            const uint64_t excl = lookback_exclusive(scan_state, tile, total);
+            if (lane == 0) {
                 S.tile_base = (uint32_t)excl;
+                S.tile_total = total;
                 if (tile == num_tiles - 1) *count_out = (int32_t)(excl + total);
             }
-            __syncthreads();
         }
-        uint32_t pos = S.tile_base + S.excl[row * 2 + half];
+        uint32_t pos = S.excl[row * 2 + half];
 
-        // ---- emit (TMEM loads are warp-collective: every thread loads, kept offsets write) ---------
+        // ---- epilogue 2b: post-process the kept offsets into the staging buffers -----------------------
+        if (!umma::mbar_wait(&S.bar[2], parity)) S.timeout = 1;
+        umma::fence_after_thread_sync();
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
             const int k = kbase + j;
@@ -283,34 +329,53 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
             umma::tmem_ld8(tl + kColDv + 8 * k, vv);
             umma::tmem_wait_ld();
             if (keepbits & (1u << j)) {
-                const float *of = offsets + ((size_t)a * kK + k) * 3;
-                const float *sc = S.scaling + 6 * row;
-                const size_t p = pos++;
-                o_xyz[3 * p + 0] = S.anchor[3 * row + 0] + of[0] * sc[0];
-                o_xyz[3 * p + 1] = S.anchor[3 * row + 1] + of[1] * sc[1];
-                o_xyz[3 * p + 2] = S.anchor[3 * row + 2] + of[2] * sc[2];
-                const float c0 = __uint_as_float(vc[0]) + S.w[kOffB2c + 4 * k + 0];
-                const float c1 = __uint_as_float(vc[1]) + S.w[kOffB2c + 4 * k + 1];
-                const float c2 = __uint_as_float(vc[2]) + S.w[kOffB2c + 4 * k + 2];
-                o_color[3 * p + 0] = 1.0f / (1.0f + expf(-c0));
-                o_color[3 * p + 1] = 1.0f / (1.0f + expf(-c1));
-                o_color[3 * p + 2] = 1.0f / (1.0f + expf(-c2));
-                o_opacity[p] = nop[j];
+                const uint32_t p = pos++;
+                S.o_xyz[3 * p + 0] = cur.anchor[0] + cur.off[3 * j + 0] * cur.sc[0];
+                S.o_xyz[3 * p + 1] = cur.anchor[1] + cur.off[3 * j + 1] * cur.sc[1];
+                S.o_xyz[3 * p + 2] = cur.anchor[2] + cur.off[3 * j + 2] * cur.sc[2];
+                S.o_color[3 * p + 0] = fast_sigmoid(__uint_as_float(vc[0]) + S.w[kOffB2c + 4 * k + 0]);
+                S.o_color[3 * p + 1] = fast_sigmoid(__uint_as_float(vc[1]) + S.w[kOffB2c + 4 * k + 1]);
+                S.o_color[3 * p + 2] = fast_sigmoid(__uint_as_float(vc[2]) + S.w[kOffB2c + 4 * k + 2]);
+                S.o_opacity[p] = nop[j];
                 float cv[7];
 #pragma unroll
                 for (int i = 0; i < 7; ++i) cv[i] = __uint_as_float(vv[i]) + S.w[kOffB2v + 8 * k + i];
-                o_scaling[3 * p + 0] = sc[3] * (1.0f / (1.0f + expf(-cv[0])));
-                o_scaling[3 * p + 1] = sc[4] * (1.0f / (1.0f + expf(-cv[1])));
-                o_scaling[3 * p + 2] = sc[5] * (1.0f / (1.0f + expf(-cv[2])));
-                const float nrm = fmaxf(sqrtf(cv[3] * cv[3] + cv[4] * cv[4] + cv[5] * cv[5] + cv[6] * cv[6]), 1e-12f);
-                reinterpret_cast<float4 *>(o_rot)[p] = make_float4(cv[3] / nrm, cv[4] / nrm, cv[5] / nrm, cv[6] / nrm);
+                S.o_scaling[3 * p + 0] = cur.sc[3] * fast_sigmoid(cv[0]);
+                S.o_scaling[3 * p + 1] = cur.sc[4] * fast_sigmoid(cv[1]);
+                S.o_scaling[3 * p + 2] = cur.sc[5] * fast_sigmoid(cv[2]);
+                const float ss = cv[3] * cv[3] + cv[4] * cv[4] + cv[5] * cv[5] + cv[6] * cv[6];
+                const float inv = rsqrtf(fmaxf(ss, 1e-24f));  // F.normalize: v / max(|v|, 1e-12)
+                S.o_rot[p] = make_float4(cv[3] * inv, cv[4] * inv, cv[5] * inv, cv[6] * inv);
             }
         }
-        // all TMEM reads of this tile are complete before the next tile's stores / MMAs reuse the columns
-        if (tid == 0) S.tile = (int)atomicAdd(&ctrl[0], 1u);
         umma::fence_before_thread_sync();
-        __syncthreads();
+        __syncthreads();  // staging complete, tile_base published, all TMEM reads of this tile done
         umma::fence_after_thread_sync();
+
+        // ---- coalesced copy-out ----------------------------------------------------------------------
+        {
+            const uint32_t n = S.tile_total;
+            const size_t base = S.tile_base;
+            for (uint32_t i = tid; i < 3 * n; i += kThreads) {
+                o_xyz[3 * base + i] = S.o_xyz[i];
+                o_color[3 * base + i] = S.o_color[i];
+                o_scaling[3 * base + i] = S.o_scaling[i];
+            }
+            for (uint32_t i = tid; i < n; i += kThreads) {
+                o_opacity[base + i] = S.o_opacity[i];
+                reinterpret_cast<float4 *>(o_rot)[base + i] = S.o_rot[i];
+            }
+            const int valid = min(kRows, Nv - tile * kRows) * kK;
+            const size_t gp0 = (size_t)tile * kTileGauss;
+            for (int i = tid; i < valid; i += kThreads) {
+                o_neural_opacity[gp0 + i] = S.o_nop[i];
+                o_mask[gp0 + i] = S.o_keep[i];
+            }
+        }
+        __syncthreads();  // staging buffers are free again
+        cur = nxt;
+        tile = next_tile;
+        next_tile += gridDim.x;
     }
 
     umma::fence_before_thread_sync();

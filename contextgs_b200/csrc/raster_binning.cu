@@ -17,9 +17,6 @@ namespace cgs {
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
-constexpr uint64_t kScanAggregate = 1ull << 62;
-constexpr uint64_t kScanInclusive = 2ull << 62;
-constexpr uint64_t kScanValueMask = (1ull << 62) - 1;
 
 // Inclusive scan of tiles_touched gathered in depth order; the last tile publishes R.
 __global__ void __launch_bounds__(kScanThreads)
@@ -53,32 +50,22 @@ scan_tiles_kernel(const uint32_t *__restrict__ order, const float *__restrict__ 
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    uint64_t warp_excl = 0;
-    for (int w = 0; w < warp; ++w) warp_excl += s_warp[w];
-    if (threadIdx.x == kScanThreads - 1) {
-        const uint64_t total = warp_excl + incl;
-        volatile unsigned long long *st = state;
-        uint64_t excl = 0;
-        if (tile == 0) {
-            st[0] = kScanInclusive | total;
-        } else {
-            st[tile] = kScanAggregate | total;
-            int64_t t = (int64_t)tile - 1;
-            while (true) {
-                uint64_t s = st[t];
-                while ((s >> 62) == 0) s = st[t];
-                excl += s & kScanValueMask;
-                if ((s >> 62) == 2ull) break;
-                --t;
+    uint64_t warp_excl = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) {
+        warp_excl += w < warp ? s_warp[w] : 0ull;
+        total += s_warp[w];
+    }
+    if (warp == 0) {
+        const uint64_t excl = lookback_exclusive(state, (int)tile, total);
+        if (lane == 0) {
+            s_prefix = excl;
+            if ((int64_t)tile == ((int64_t)P - 1) / kScanTile) {
+                const uint64_t R = excl + total;
+                status[CGS_STATUS_NUM_RENDERED] = (int32_t)(R > 0x7fffffffull ? 0x7fffffff : R);
+                status[CGS_STATUS_OVERFLOW] = R > (uint64_t)R_cap ? 1 : 0;
+                status[CGS_STATUS_NUM_SORTED] = (int32_t)(R > (uint64_t)R_cap ? (uint64_t)R_cap : R);
             }
-            st[tile] = kScanInclusive | (excl + total);
-        }
-        s_prefix = excl;
-        if ((int64_t)tile == ((int64_t)P - 1) / kScanTile) {
-            const uint64_t R = excl + total;
-            status[CGS_STATUS_NUM_RENDERED] = (int32_t)(R > 0x7fffffffull ? 0x7fffffff : R);
-            status[CGS_STATUS_OVERFLOW] = R > (uint64_t)R_cap ? 1 : 0;
-            status[CGS_STATUS_NUM_SORTED] = (int32_t)(R > (uint64_t)R_cap ? (uint64_t)R_cap : R);
         }
     }
     __syncthreads();

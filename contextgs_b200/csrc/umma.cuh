@@ -130,11 +130,13 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- 3xTF32 split ----------------------------------------------------------------------------
+// hi = x with the 13 low mantissa bits cleared (what the tensor core would read anyway), lo = the
+// same truncation of the exact remainder x - hi: hi + lo carries >= 21 significant bits of x.
+// (cvt.rna.tf32.f32 lowers to a ~6-instruction integer sequence on sm_100a; truncation is 1 LOP3.)
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
 {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
 }
 
 // Issue the three TF32 products of one logical fp32 GEMM  D[128 x N] (+)= A[128 x K] * W[N x K]^T :
