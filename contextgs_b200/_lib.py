@@ -59,6 +59,9 @@ SIGNATURES = {
     "cgs_neural_gaussians_umma_workspace_bytes": (c_size_t, [c_int]),
     "cgs_neural_gaussians_umma_forward": (c_int, [_PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
                                                   _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
+    "cgs_neural_gaussians_backward_packed_floats": (c_int, []),
+    "cgs_neural_gaussians_backward_workspace_bytes": (c_size_t, [c_int]),
+    "cgs_neural_gaussians_backward": (c_int, [_PTR, _PTR, _PTR, c_int] + [_PTR] * 19 + [c_size_t, _PTR]),
     "cgs_compact_workspace_bytes": (c_size_t, [c_int]),
     "cgs_compact_indices": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, c_size_t, _PTR]),
     "cgs_eb_param_floats": (c_int, []),

@@ -35,6 +35,7 @@ SOURCES = {
     "context_model.cu": ["-fmad=false"],
     "umma_selftest.cu": [],
     "neural_gaussians_umma.cu": ["-fmad=false"],
+    "neural_gaussians_bwd.cu": [],
 }
 
 

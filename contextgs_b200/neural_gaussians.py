@@ -159,13 +159,113 @@ def generate_raw(pc, camera_center, anchor, feat, grid_offsets, grid_scaling, bi
     return out
 
 
-@torch.no_grad()
-def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False, step=0):
-    """Same signature and return tuples as gaussian_renderer/__init__.py:25-150.
+def pack_decoder_weights_transposed(pc):
+    """Backward-GEMM block: W1T[150][56] (= the three Linear(54,50).weight stacked), then the
+    Linear(50,n).weight of each head as [n][52] (layout: csrc/neural_gaussians_bwd.cu `ngb::kOff*T`)."""
+    mods = (pc.get_opacity_mlp, pc.get_color_mlp, pc.get_cov_mlp)
+    with torch.no_grad():
+        dev = mods[0][0].weight.device
+        W1T = torch.zeros(150, 56, device=dev)
+        for i, m in enumerate(mods):
+            W1T[50 * i:50 * i + 50, :54] = m[0].weight
+        parts = [W1T.reshape(-1)]
+        for m in mods:
+            n = m[2].weight.shape[0]
+            W2T = torch.zeros(n, 52, device=dev)
+            W2T[:, :50] = m[2].weight
+            parts.append(W2T.reshape(-1))
+        packed = torch.cat(parts).float().contiguous()
+    assert packed.numel() == _lib.lib().cgs_neural_gaussians_backward_packed_floats()
+    return packed
 
-    NOTE (round 1): forward only -- outputs carry no autograd graph.  The differentiable G1 backward
-    kernel is the next row of the build plan; training-mode calls work for
-    evaluation of the forward values (bit_per_param etc.)."""
+
+def unpack_decoder_weight_grads(d_packed):
+    """Gradient block in the forward layout (`pack_decoder_weights`) -> 12 tensors shaped like
+    (opacity, color, cov) x (l0.weight, l0.bias, l2.weight, l2.bias)."""
+    o = 0
+    W1 = d_packed[o:o + 54 * 152].view(54, 152); o += 54 * 152
+    b1 = d_packed[o:o + 152]; o += 152
+    out = []
+    heads = []
+    for n, ld in ((10, 12), (30, 32), (70, 72)):
+        W2 = d_packed[o:o + 50 * ld].view(50, ld); o += 50 * ld
+        b2 = d_packed[o:o + ld]; o += ld
+        heads.append((W2[:, :n].t().contiguous(), b2[:n].contiguous()))
+    for i in range(3):
+        out += [W1[:, 50 * i:50 * i + 50].t().contiguous(), b1[50 * i:50 * i + 50].contiguous(), heads[i][0], heads[i][1]]
+    return out
+
+
+def _decoder_params(pc):
+    mods = (pc.get_opacity_mlp, pc.get_color_mlp, pc.get_cov_mlp)
+    return [p for m in mods for p in (m[0].weight, m[0].bias, m[2].weight, m[2].bias)]
+
+
+class _NeuralGaussians(torch.autograd.Function):
+    """Differentiable fused G1: forward = cgs_neural_gaussians_(umma_)forward, backward =
+    cgs_neural_gaussians_backward.  Replaces the autograd graph of
+    gaussian_renderer/__init__.py:106-145."""
+
+    @staticmethod
+    def forward(ctx, pc, campos, vis_idx, n_vis, anchor, feat, offsets, scaling, mask, *params):
+        N = anchor.shape[0]
+        K = pc.n_offsets
+        a, f, o = anchor.detach().contiguous(), feat.detach().contiguous(), offsets.detach().reshape(N, -1).contiguous()
+        sc, m = scaling.detach().contiguous(), mask.detach().reshape(N, -1).contiguous()
+        raw = generate_raw(pc, campos, a, f, o, sc, m, vis_idx=vis_idx, n_vis=n_vis)
+        P = int(raw["count"].item())  # the reference synchronises here too (boolean indexing, :119,136)
+        if P < 0:
+            raise _lib.CgsError("cgs_neural_gaussians_umma_forward: a tensor-core completion barrier timed out")
+        ctx.pc, ctx.campos, ctx.n_vis, ctx.P = pc, campos, n_vis, P
+        ctx.shapes = (offsets.shape, mask.shape)
+        ctx.save_for_backward(a, f, o, sc, m, vis_idx, raw["mask"])
+        nop = raw["neural_opacity"][:n_vis * K]
+        keep = raw["mask"][:n_vis * K]
+        ctx.mark_non_differentiable(nop, keep)
+        return (raw["xyz"][:P], raw["color"][:P], raw["opacity"][:P], raw["scaling"][:P], raw["rot"][:P], nop, keep)
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_color, g_opacity, g_scaling, g_rot, _g_nop, _g_keep):
+        L = _lib.lib()
+        a, f, o, sc, m, vis_idx, keep = ctx.saved_tensors
+        pc, P, n_vis = ctx.pc, ctx.P, ctx.n_vis
+        N, dev = a.shape[0], a.device
+        z = lambda t: torch.zeros_like(t)
+        d_a, d_f, d_o, d_sc, d_m = z(a), z(f), z(o), z(sc), z(m)
+        d_w = torch.zeros(L.cgs_neural_gaussians_packed_floats(), device=dev)
+        if P > 0 and n_vis > 0:
+            c = lambda g, shape: (torch.zeros(shape, device=dev) if g is None else g.contiguous().float())
+            g_xyz, g_color, g_scaling = c(g_xyz, (P, 3)), c(g_color, (P, 3)), c(g_scaling, (P, 3))
+            g_opacity, g_rot = c(g_opacity, (P, 1)), c(g_rot, (P, 4))
+            ws = torch.empty((L.cgs_neural_gaussians_backward_workspace_bytes(n_vis),), dtype=torch.uint8, device=dev)
+            from .rasterizer import _host_floats
+            campos = (ctypes.c_float * 3)(*_host_floats(ctx.campos, 3))
+            _lib.check(L.cgs_neural_gaussians_backward(
+                _lib.ptr(pack_decoder_weights(pc)), _lib.ptr(pack_decoder_weights_transposed(pc)), _lib.ptr(vis_idx),
+                n_vis, _lib.ptr(a), _lib.ptr(f), _lib.ptr(o), _lib.ptr(sc), _lib.ptr(m), campos, _lib.ptr(keep),
+                _lib.ptr(g_xyz), _lib.ptr(g_color), _lib.ptr(g_opacity), _lib.ptr(g_scaling), _lib.ptr(g_rot),
+                _lib.ptr(d_a), _lib.ptr(d_f), _lib.ptr(d_o), _lib.ptr(d_sc), _lib.ptr(d_m), _lib.ptr(d_w), _lib.ptr(ws),
+                ws.numel(), _lib.stream_ptr()), "cgs_neural_gaussians_backward")
+        off_shape, mask_shape = ctx.shapes
+        return (None, None, None, None, d_a, d_f, d_o.view(off_shape), d_sc, d_m.view(mask_shape),
+                *unpack_decoder_weight_grads(d_w))
+
+
+def neural_gaussians(pc, camera_center, anchor, feat, grid_offsets, grid_scaling, binary_grid_masks, vis_idx, n_vis):
+    """Differentiable anchor -> Gaussian generation on the visible anchors `vis_idx[:n_vis]`.
+    Returns (xyz, color, opacity, scaling, rot, neural_opacity, selection_mask[bool])."""
+    out = _NeuralGaussians.apply(pc, camera_center, vis_idx, n_vis, anchor, feat, grid_offsets, grid_scaling,
+                                 binary_grid_masks, *_decoder_params(pc))
+    xyz, color, opacity, scaling, rot, nop, keep = out
+    return xyz, color, opacity, scaling, rot, nop, keep.bool()
+
+
+def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False, step=0):
+    """Same signature and return tuples as gaussian_renderer/__init__.py:25-150.  Differentiable
+    w.r.t. the per-anchor parameters and the decoder MLPs through `_NeuralGaussians` (autograd is
+    recorded whenever torch.is_grad_enabled()).  The context-model outputs (step > 10000) are
+    produced by the fused forward kernels; their backward is the next row of the build plan
+    (DESIGN.md section 9)."""
     from .context_model import multi_scale_generating
     anchor_all = pc.get_anchor
     N = anchor_all.shape[0]
@@ -193,19 +293,13 @@ def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_traini
             pc, anchor_all, pc._hyper_latent, feat, grid_offsets, grid_scaling, binary_grid_masks, mask_anchor_bool,
             predict_bpp=False, training=False)
 
-    vis_idx, cnt = compact_indices(visible_mask)
-    n_vis = int(cnt.item())  # the reference synchronises here too (boolean indexing, :44-50)
-    raw = generate_raw(pc, viewpoint_camera.camera_center, anchor_all, feat, grid_offsets.reshape(N, -1),
-                       grid_scaling, binary_grid_masks.reshape(N, -1), vis_idx=vis_idx, n_vis=n_vis)
-    P = int(raw["count"].item())
-    if P < 0:
-        raise _lib.CgsError("cgs_neural_gaussians_umma_forward: a tensor-core completion barrier timed out")
-    K = pc.n_offsets
-    xyz, color, opacity = raw["xyz"][:P], raw["color"][:P], raw["opacity"][:P]
-    scaling, rot = raw["scaling"][:P], raw["rot"][:P]
+    with torch.no_grad():
+        vis_idx, cnt = compact_indices(visible_mask)
+        n_vis = int(cnt.item())  # the reference synchronises here too (boolean indexing, :44-50)
+    xyz, color, opacity, scaling, rot, neural_opacity, mask = neural_gaussians(
+        pc, viewpoint_camera.camera_center, anchor_all, feat, grid_offsets, grid_scaling, binary_grid_masks, vis_idx,
+        n_vis)
     if is_training:
-        neural_opacity = raw["neural_opacity"][:n_vis * K]
-        mask = raw["mask"][:n_vis * K].bool()
         return (xyz, color, opacity, scaling, rot, neural_opacity, mask, bit_per_param, 16, bit_per_feat_param,
                 bit_per_scaling_param, bit_per_offsets_param, bpp_per_level)
     return xyz, color, opacity, scaling, rot, 0

@@ -168,6 +168,25 @@ CGS_API int cgs_neural_gaussians_umma_forward(const float *packed_weights, const
                                               int32_t *count_dev, void *workspace, size_t workspace_bytes,
                                               void *stream);
 
+/* Backward of the two entry points above = what autograd does for gaussian_renderer/__init__.py:106-145
+ * plus scene/gaussian_model.py:153-174 in the reference (SURVEY 8a row T1 lists the gradients train.py
+ * consumes).  g_* are the gradients of the emitted Gaussians in emission order ([P,3] [P,3] [P] [P,3]
+ * [P,4]); keep_mask is the forward's o_mask.  Rows of visible anchors of d_anchor[N,3] d_feat[N,50]
+ * d_offsets[N,30] d_scaling[N,6] d_mask[N,10] are OVERWRITTEN (the caller zero-fills the arrays);
+ * d_packed_fwd (cgs_neural_gaussians_packed_floats() floats, forward layout) is ACCUMULATED into.
+ * packed_bwd: transposed weights, cgs_neural_gaussians_backward_packed_floats() floats
+ * (contextgs_b200/neural_gaussians.py pack_decoder_weights_transposed). */
+CGS_API int cgs_neural_gaussians_backward_packed_floats(void);
+CGS_API size_t cgs_neural_gaussians_backward_workspace_bytes(int Nv);
+CGS_API int cgs_neural_gaussians_backward(const float *packed_fwd, const float *packed_bwd, const int32_t *vis_idx,
+                                          int Nv, const float *anchor, const float *feat, const float *offsets,
+                                          const float *scaling, const float *mask, const float *campos_host,
+                                          const uint8_t *keep_mask, const float *g_xyz, const float *g_color,
+                                          const float *g_opacity, const float *g_scaling, const float *g_rot,
+                                          float *d_anchor, float *d_feat, float *d_offsets, float *d_scaling,
+                                          float *d_mask, float *d_packed_fwd, void *workspace, size_t workspace_bytes,
+                                          void *stream);
+
 /* Order-preserving compaction of a byte mask into an index list (the device-side replacement of
  * the reference's `tensor[bool_mask]` / torch.nonzero host-synchronising idiom, e.g.
  * gaussian_renderer/__init__.py:44-50).  mask must be 8-byte aligned. *count_dev = popcount. */

@@ -88,3 +88,49 @@ def test_no_visible_anchor():
     model.train()
     out = generate_neural_gaussians(cam, model, vis, is_training=True, step=0)
     assert out[0].shape == (0, 3) and out[5].shape == (0, 1) and out[6].numel() == 0
+
+
+def test_backward_matches_autograd_of_the_oracle():
+    """Gradients of the fused G1 backward kernel vs torch autograd through the oracle's restatement of
+    gaussian_renderer/__init__.py:106-145 (float64 on the CPU)."""
+    N = 3000
+    scene = synthetic.make_scene("chair", N, seed=2, gaussian_scale=3.0)
+    pc = er.make_model(scene)
+    model = cuda_model(scene, pc)
+    cam_cpu = synthetic.make_cameras("chair", 4)[1]
+    cam = synthetic.make_cameras("chair", 4, device="cuda")[1]
+    g = torch.Generator().manual_seed(9)
+    vis = torch.rand(N, generator=g) < 0.6
+
+    # ---- oracle, float64 leaves
+    leaf = lambda t: t.detach().double().clone().requires_grad_(True)
+    a, f, o, sc, m = (leaf(t) for t in (pc.get_anchor, pc._anchor_feat, pc._offset, pc.get_scaling, pc.get_mask))
+    pc64 = type("PC", (), {})()
+    pc64.n_offsets = pc.n_offsets
+    pc64.mlps = {k: [leaf(t) for t in pc.mlps[k]] for k in ("opacity", "cov", "color")}
+    ref = er.generate_neural_gaussians(pc64, cam_cpu.camera_center.double(), a[vis], f[vis], o[vis], sc[vis], m[vis])
+    P = ref["xyz"].shape[0]
+    ws = {k: torch.randn(ref[k].shape, generator=g, dtype=torch.float64) for k in ("xyz", "color", "opacity", "scaling", "rot")}
+    sum((ref[k] * ws[k]).sum() for k in ws).backward()
+
+    # ---- CUDA
+    model.train()
+    leaves = {n: getattr(model, n) for n in ("_anchor_feat", "_offset", "_scaling", "_mask", "_anchor")}
+    out = generate_neural_gaussians(cam, model, vis.cuda(), is_training=True, step=0)
+    xyz, color, opacity, scaling, rot = out[:5]
+    if xyz.shape[0] != P or not np.array_equal(out[6].cpu().numpy(), ref["mask"].numpy()):
+        pytest.skip("selection flipped at a rounding-level zero crossing")
+    loss = sum((t * ws[k].float().cuda()).sum() for k, t in zip(("xyz", "color", "opacity", "scaling", "rot"),
+                                                               (xyz, color, opacity, scaling, rot)))
+    loss.backward()
+    # per-anchor parameters (chain rule through exp / the STE mask is torch on both sides)
+    assert rel_l2(model._anchor_feat.grad.cpu().numpy(), f.grad.numpy()) < REL_L2
+    assert rel_l2(model._offset.grad.cpu().numpy(), o.grad.numpy()) < REL_L2
+    assert rel_l2(model._scaling.grad.cpu().numpy(), (sc.grad * sc.detach()).numpy()) < REL_L2     # d/d log-scale
+    sig = torch.sigmoid(pc._mask.double())
+    assert rel_l2(model._mask.grad.cpu().numpy(), (m.grad * sig * (1 - sig)).numpy()) < REL_L2   # STE: d sigmoid
+    assert rel_l2(model._anchor.grad.cpu().numpy(), a.grad.numpy()) < 1e-3   # view-direction path cancels heavily
+    for name, seq in (("opacity", model.mlp_opacity), ("cov", model.mlp_cov), ("color", model.mlp_color)):
+        W1, b1, W2, b2 = pc64.mlps[name]
+        for ours, theirs in ((seq[0].weight, W1), (seq[0].bias, b1), (seq[2].weight, W2), (seq[2].bias, b2)):
+            assert rel_l2(ours.grad.cpu().numpy(), theirs.grad.numpy()) < REL_L2, name
