@@ -136,10 +136,13 @@ def get_level_plan(pc, anchor, mask_anchor_bool):
 @torch.no_grad()
 def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, binary_grid_masks,
                            mask_anchor_bool=None, training=False, predict_bpp=False, return_sum_bits=False,
-                           noise=None, return_details=False):
+                           noise=None, return_details=False, plan=None, group=None):
     """Same signature and the same three return arities as scene/gaussian_model.py:1541-1707.
     `noise` (optional, for reproducible parity runs): dict(eb=[N,12], levels=[[n_i,86] x3 coarse->fine],
-    choose=bool[N]); otherwise drawn with the CUDA generator."""
+    choose=bool[N]); otherwise drawn with the CUDA generator.
+    `plan` (optional): a shard of the level plan (contextgs_b200.distributed.shard_level_plan) -- only
+    its rows are coded and scored, and the bit sums are all-reduced over `group`, so that every rank
+    returns the whole-scene totals (anchors sharded, scalar all-reduce only)."""
     L = _lib.lib()
     dev = anchor.device
     N, K = anchor.shape[0], pc.n_offsets
@@ -151,7 +154,9 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
     hyper = hyper.contiguous()
     if pc.level_scale is None:
         pc.level_scale = find_divide_scale(pc, anchor[mask_anchor_bool], pc.target_ratio, pc.level_num)
-    plan = get_level_plan(pc, anchor, mask_anchor_bool)
+    sharded = plan is not None
+    if plan is None:
+        plan = get_level_plan(pc, anchor, mask_anchor_bool)
 
     if predict_bpp:
         if noise is not None and "choose" in noise:
@@ -163,6 +168,11 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
             choose = choose & mask_anchor_bool
     else:
         choose = torch.zeros(N, dtype=torch.bool, device=dev)
+    if sharded:  # hyper bits are summed over the anchors this shard codes
+        owned = torch.zeros(N, dtype=torch.bool, device=dev)
+        for lv in plan.levels:
+            owned[lv.orig.long()] = True
+        choose = choose & owned
     choose_u8 = choose.contiguous().view(torch.uint8)
 
     sums = torch.zeros(16, dtype=torch.float64, device=dev)  # [4*i..4*i+3] level i (coarse->fine); [12] hyper
@@ -196,6 +206,9 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
     if not predict_bpp:
         return feat_q, scaling_q, offsets_q3
 
+    if sharded:
+        from .distributed import all_reduce_sums
+        all_reduce_sums(sums, group)
     s = sums.tolist()  # one host read-back (the reference has several .item() calls here)
     bit_feat, bit_scaling, bit_offsets = (sum(s[4 * i + c] for i in range(3)) for c in range(3))
     n_chosen = sum(s[4 * i + 3] for i in range(3))

@@ -188,3 +188,30 @@ def test_full_size_properties():
     again = multi_scale_generating(model, a, model._hyper_latent, fq, det["offsets_q"], det["scaling_q"],
                                    model.get_mask, mk)[0]
     assert float((again - fq).abs().max()) <= 1e-3
+
+
+def test_sharded_scoring_adds_up_fake_world():
+    """anchors sharded by dependency root; each shard runs its three levels without any
+    exchange.  One process plays all ranks in turn ("fake world"); the sums must add up to the
+    unsharded pass and every anchor must receive exactly the same quantised values."""
+    from contextgs_b200.context_model import get_level_plan
+    from contextgs_b200.distributed import shard_level_plan
+    gold = load_npz("context_model.npz")
+    scene, pc = fixture_model(gold)
+    model = cuda_model(scene, pc).eval()
+    sel = model.get_mask_anchor
+    args = (model.get_anchor[sel].detach(), model._hyper_latent[sel].detach(), model._anchor_feat[sel].detach(),
+            model._offset[sel].detach(), model.get_scaling[sel].detach())
+    kw = dict(binary_grid_masks=model.get_mask[sel].detach(), predict_bpp=True, return_sum_bits=True, return_details=True)
+    full, det = multi_scale_generating(model, *args, **kw)
+    plan = det["plan"]
+    world = 4
+    acc = np.zeros(5)
+    fq = torch.zeros_like(det["feat_q"])
+    for r in range(world):
+        part, d = multi_scale_generating(model, *args, plan=shard_level_plan(plan, r, world), **kw)
+        acc += np.asarray(part[:5], np.float64)
+        fq += d["feat_q"]                      # shards write disjoint rows
+        assert part[5] == full[5]              # mask bits are global
+    assert np.allclose(acc, np.asarray(full[:5], np.float64), rtol=1e-7)   # fp32 partial sums regroup
+    assert torch.equal(fq, det["feat_q"])
