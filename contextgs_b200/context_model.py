@@ -131,9 +131,112 @@ def get_level_plan(pc, anchor, mask_anchor_bool):
     return plan
 
 
+# ----------------------------------------------------------------------------- forward core + training autograd
+
+def _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choose_u8, noise, training, return_details):
+    """EntropyBottleneck kernel + one fused kernel per level (coarse -> fine).  All inputs are detached,
+    contiguous [N, .] tensors.  Returns a dict with the quantised attributes, the fp64 bit sums
+    ([4i..4i+3] level i: feat, scaling, offsets, chosen rows; [12] hyper) and what the backward needs."""
+    L = _lib.lib()
+    dev, N = anchor.device, anchor.shape[0]
+    sums = torch.zeros(16, dtype=torch.float64, device=dev)
+    hyper_q, lik = pc.latent_codec(hyper, training=training, noise=None if noise is None else noise["eb"].to(dev),
+                                   choose=choose_u8, bit_sum=sums[12:13])
+    if getattr(pc, "disable_hyper", False):
+        hyper_q = hyper_q * 0
+    feat_q, scaling_q, offsets_q = torch.zeros_like(feat), torch.zeros_like(scaling), torch.zeros_like(offsets)
+    bits_out = torch.zeros((N, N_CODED), dtype=torch.float32, device=dev) if return_details else None
+    means = (float(pc._anchor_feat.mean()), float(pc.get_scaling.mean()), float(pc._offset.mean()))
+    stream = _lib.stream_ptr()
+    level_noise = []
+    for li, lv in enumerate(plan.levels):
+        nz = None
+        if training and lv.n:
+            nz = noise["levels"][li].to(dev).contiguous() if noise is not None else \
+                torch.empty((lv.n, N_CODED), device=dev).uniform_(-0.5, 0.5)
+        level_noise.append(nz)
+        if lv.n == 0:
+            continue
+        packed, in_dim = pack_grid_weights(pc, lv.level)
+        _lib.check(L.cgs_context_level_forward(
+            in_dim, _lib.ptr(packed), _lib.ptr(lv.orig), _lib.ptr(lv.ctx_src), _lib.ptr(lv.level_anchor), lv.n,
+            _lib.ptr(anchor), _lib.ptr(hyper_q), _lib.ptr(feat), _lib.ptr(scaling), _lib.ptr(offsets), _lib.ptr(masks),
+            _lib.ptr(choose_u8), _lib.ptr(nz), means[0], means[1], means[2], _lib.ptr(feat_q), _lib.ptr(scaling_q),
+            _lib.ptr(offsets_q), _lib.ptr(bits_out), _lib.ptr(sums[4 * li:4 * li + 4]), stream),
+            "cgs_context_level_forward")
+    return dict(feat_q=feat_q, scaling_q=scaling_q, offsets_q=offsets_q, hyper_q=hyper_q, lik=lik, sums=sums,
+                bits_out=bits_out, level_noise=level_noise, means=means)
+
+
+def pack_grid_weights_bwd(m):
+    """DIFFERENTIABLE packing of one context MLP into the layout of the backward kernel
+    (csrc/context_model_bwd.cu: W1[in][101] | b1[100] | W2[100][177] | b2[176], odd leading dimensions).
+    The kernel returns the gradient in the same layout; autograd un-packs it into the parameters."""
+    F = torch.nn.functional
+    W1 = F.pad(m[0].weight.t(), (0, 1))
+    W2 = F.pad(m[2].weight.t(), (0, 2))
+    flat = torch.cat([W1.reshape(-1), m[0].bias, W2.reshape(-1), F.pad(m[2].bias, (0, 1))])
+    return F.pad(flat, (0, (-flat.numel()) % 4)).float()
+
+
+class _ContextModelTrain(torch.autograd.Function):
+    """Training-mode context model (x_q = x + U * Q, bit_per_param over the chosen anchors) with the
+    fused backward kernels: replaces the autograd graph of scene/gaussian_model.py:1556-1707."""
+
+    @staticmethod
+    def forward(ctx, pc, plan, choose_u8, noise, rate, return_details, info, anchor, hyper, feat, offsets, scaling,
+                masks, eb_packed, *w_bwd):
+        d = lambda t: t.detach().contiguous()
+        anchor, hyper, feat, offsets, scaling, masks = (d(t) for t in (anchor, hyper, feat, offsets, scaling, masks))
+        out = _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choose_u8, noise, True,
+                              return_details)
+        s = out["sums"].tolist()  # the one host read-back of the forward
+        out["sums_host"] = s
+        info.update(out)
+        n_chosen = sum(s[4 * i + 3] for i in range(3))
+        total_bits = sum(s[4 * i + c] for i in range(3) for c in range(3)) + s[12]
+        factor = rate / (max(n_chosen, 1e-30) * N_CODED)
+        per_param = torch.tensor(total_bits * factor, dtype=torch.float32, device=anchor.device)
+        ctx.pc, ctx.plan, ctx.factor, ctx.means = pc, plan, factor, out["means"]
+        ctx.level_noise = out["level_noise"]
+        ctx.save_for_backward(anchor, out["hyper_q"], out["feat_q"], out["scaling_q"], out["offsets_q"], masks, choose_u8,
+                              eb_packed.detach(), *[w.detach() for w in w_bwd])
+        return out["feat_q"], out["scaling_q"], out["offsets_q"], per_param
+
+    @staticmethod
+    def backward(ctx, g_feat, g_scaling, g_offsets, g_bpp):
+        L = _lib.lib()
+        anchor, hyper_q, feat_q, scaling_q, offsets_q, masks, choose_u8, eb_packed, *w_bwd = ctx.saved_tensors
+        plan, dev, N = ctx.plan, anchor.device, anchor.shape[0]
+        G = lambda g, like: torch.zeros_like(like) if g is None else g.contiguous().clone().float()
+        G_f, G_s, G_o = G(g_feat, feat_q), G(g_scaling, scaling_q), G(g_offsets, offsets_q)
+        d_mask, d_hyper, d_anchor = torch.zeros_like(masks), torch.zeros_like(hyper_q), torch.zeros_like(anchor)
+        d_w = [torch.zeros_like(w) for w in w_bwd]
+        d_eb = torch.zeros_like(eb_packed)
+        ticket = torch.zeros(4, dtype=torch.int32, device=dev)
+        g_ptr = None if g_bpp is None else _lib.ptr(g_bpp.contiguous().float())
+        stream = _lib.stream_ptr()
+        for li in reversed(range(len(plan.levels))):       # fine -> coarse
+            lv = plan.levels[li]
+            if lv.n == 0:
+                continue
+            in_dim = 15 if lv.ctx_src is None else 71
+            _lib.check(L.cgs_context_level_backward(
+                in_dim, _lib.ptr(w_bwd[li]), _lib.ptr(lv.orig), _lib.ptr(lv.ctx_src), _lib.ptr(lv.level_anchor), lv.n,
+                _lib.ptr(anchor), _lib.ptr(hyper_q), _lib.ptr(feat_q), _lib.ptr(scaling_q), _lib.ptr(offsets_q),
+                _lib.ptr(masks), _lib.ptr(choose_u8), _lib.ptr(ctx.level_noise[li]), ctx.means[0], ctx.means[1],
+                ctx.means[2], g_ptr, ctx.factor, _lib.ptr(G_f), _lib.ptr(G_s), _lib.ptr(G_o), _lib.ptr(d_mask),
+                _lib.ptr(d_hyper), _lib.ptr(d_anchor), _lib.ptr(d_w[li]), _lib.ptr(ticket), stream),
+                "cgs_context_level_backward")
+        if g_ptr is not None:
+            _lib.check(L.cgs_eb_backward(_lib.ptr(eb_packed), eb_packed.shape[0], _lib.ptr(hyper_q), N,
+                                         _lib.ptr(choose_u8), g_ptr, ctx.factor, _lib.ptr(d_hyper), _lib.ptr(d_eb),
+                                         stream), "cgs_eb_backward")
+        return (None,) * 7 + (d_anchor, d_hyper, G_f, G_o, G_s, d_mask, d_eb, *d_w)
+
+
 # ----------------------------------------------------------------------------- the fused forward
 
-@torch.no_grad()
 def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, binary_grid_masks,
                            mask_anchor_bool=None, training=False, predict_bpp=False, return_sum_bits=False,
                            noise=None, return_details=False, plan=None, group=None):
@@ -152,11 +255,12 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
     offsets = grid_offsets.reshape(N, 3 * K).contiguous()
     masks = binary_grid_masks.reshape(N, K).contiguous()
     hyper = hyper.contiguous()
-    if pc.level_scale is None:
-        pc.level_scale = find_divide_scale(pc, anchor[mask_anchor_bool], pc.target_ratio, pc.level_num)
     sharded = plan is not None
-    if plan is None:
-        plan = get_level_plan(pc, anchor, mask_anchor_bool)
+    with torch.no_grad():
+        if pc.level_scale is None:
+            pc.level_scale = find_divide_scale(pc, anchor[mask_anchor_bool], pc.target_ratio, pc.level_num)
+        if plan is None:
+            plan = get_level_plan(pc, anchor, mask_anchor_bool)
 
     if predict_bpp:
         if noise is not None and "choose" in noise:
@@ -175,33 +279,21 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
         choose = choose & owned
     choose_u8 = choose.contiguous().view(torch.uint8)
 
-    sums = torch.zeros(16, dtype=torch.float64, device=dev)  # [4*i..4*i+3] level i (coarse->fine); [12] hyper
-    hyper_q, lik = pc.latent_codec(hyper, training=training, noise=None if noise is None else noise["eb"].to(dev),
-                                   choose=choose_u8, bit_sum=sums[12:13])
-    if getattr(pc, "disable_hyper", False):
-        hyper_q = hyper_q * 0
-    feat_q = torch.zeros_like(feat)
-    scaling_q = torch.zeros_like(scaling)
-    offsets_q = torch.zeros_like(offsets)
-    bits_out = torch.zeros((N, N_CODED), dtype=torch.float32, device=dev) if return_details else None
-    f_mean = float(pc._anchor_feat.mean())
-    s_mean = float(pc.get_scaling.mean())
-    o_mean = float(pc._offset.mean())
-    stream = _lib.stream_ptr()
-    for li, lv in enumerate(plan.levels):
-        if lv.n == 0:
-            continue
-        packed, in_dim = pack_grid_weights(pc, lv.level)
-        nz = None
-        if training:
-            nz = noise["levels"][li].to(dev).contiguous() if noise is not None else \
-                torch.empty((lv.n, N_CODED), device=dev).uniform_(-0.5, 0.5)
-        _lib.check(L.cgs_context_level_forward(
-            in_dim, _lib.ptr(packed), _lib.ptr(lv.orig), _lib.ptr(lv.ctx_src), _lib.ptr(lv.level_anchor), lv.n,
-            _lib.ptr(anchor), _lib.ptr(hyper_q), _lib.ptr(feat), _lib.ptr(scaling), _lib.ptr(offsets), _lib.ptr(masks),
-            _lib.ptr(choose_u8), _lib.ptr(nz), f_mean, s_mean, o_mean, _lib.ptr(feat_q), _lib.ptr(scaling_q),
-            _lib.ptr(offsets_q), _lib.ptr(bits_out), _lib.ptr(sums[4 * li:4 * li + 4]), stream),
-            "cgs_context_level_forward")
+    rate = float(mask_anchor_bool.sum()) / mask_anchor_bool.numel() if mask_anchor_bool is not None else 1.0
+    differentiable = (training and predict_bpp and not return_sum_bits and not sharded and torch.is_grad_enabled()
+                      and any(t.requires_grad for t in (hyper, feat, grid_offsets, grid_scaling, binary_grid_masks,
+                                                        *pc.get_grid_mlp.parameters())))
+    info = {}
+    if differentiable:
+        wb = [pack_grid_weights_bwd(pc.get_grid_mlp[lv.level]) for lv in plan.levels]
+        feat_q, scaling_q, offsets_q, per_param_t = _ContextModelTrain.apply(
+            pc, plan, choose_u8, noise, rate, return_details, info, anchor, hyper, feat, offsets, scaling, masks,
+            pc.latent_codec.packed_diff(), *wb)
+    else:
+        info = _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choose_u8, noise, training,
+                               return_details)
+        feat_q, scaling_q, offsets_q, per_param_t = info["feat_q"], info["scaling_q"], info["offsets_q"], None
+    sums, hyper_q, lik, bits_out = info["sums"], info["hyper_q"], info["lik"], info["bits_out"]
     offsets_q3 = offsets_q.view(N, K, 3)
     if not predict_bpp:
         return feat_q, scaling_q, offsets_q3
@@ -209,7 +301,7 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
     if sharded:
         from .distributed import all_reduce_sums
         all_reduce_sums(sums, group)
-    s = sums.tolist()  # one host read-back (the reference has several .item() calls here)
+    s = info["sums_host"] if "sums_host" in info else sums.tolist()  # one host read-back (the reference: several .item())
     bit_feat, bit_scaling, bit_offsets = (sum(s[4 * i + c] for i in range(3)) for c in range(3))
     n_chosen = sum(s[4 * i + 3] for i in range(3))
     bit_hyper = s[12]
@@ -220,17 +312,14 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
         bit_masks = get_binary_vxl_size(binary_grid_masks)[1].item()
         res = (bit_anchor, bit_hyper, bit_feat, bit_scaling, bit_offsets, bit_masks)
         return (res, details) if return_details else res
-    if mask_anchor_bool is not None:
-        rate = float(mask_anchor_bool.sum()) / mask_anchor_bool.numel()
-    else:
-        rate = 1.0
     nc = max(n_chosen, 1e-30)
     t = lambda v: torch.tensor(v, dtype=torch.float32, device=dev)
     per_hyper = bit_hyper / (nc * 12) * rate
     per_feat = t(bit_feat / (nc * 50) * rate)
     per_scaling = t(bit_scaling / (nc * 6) * rate)
     per_offsets = t(bit_offsets / (nc * 30) * rate)
-    per_param = t((bit_feat + bit_scaling + bit_offsets + bit_hyper) / (nc * N_CODED) * rate)
+    per_param = per_param_t if per_param_t is not None else \
+        t((bit_feat + bit_scaling + bit_offsets + bit_hyper) / (nc * N_CODED) * rate)
     level_bpp = [1 - rate, per_hyper]
     for li, lv in enumerate(plan.levels):
         cnt = s[4 * li + 3]

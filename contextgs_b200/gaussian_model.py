@@ -55,6 +55,18 @@ class EntropyBottleneck(nn.Module):
             self._packed_key = key
         return self._packed
 
+    def packed_diff(self):
+        """The same [C, 59] block built with autograd recording: the backward kernel returns the gradient
+        of this tensor (cgs_eb_backward) and autograd carries it through softplus / tanh into the parameters."""
+        cols = []
+        for i in range(len(self.filters) + 1):
+            cols.append(torch.nn.functional.softplus(self.matrices[i]).reshape(self.channels, -1))
+            cols.append(self.biases[i].reshape(self.channels, -1))
+            if i < len(self.filters):
+                cols.append(torch.tanh(self.factors[i]).reshape(self.channels, -1))
+        cols.append(self.quantiles[:, 0, 1:2])
+        return torch.cat(cols, dim=1).float().contiguous()
+
     @torch.no_grad()
     def forward(self, x, training=None, noise=None, choose=None, bit_sum=None):
         """x [N,C] -> (x_hat, likelihood).  training=True adds U(-.5,.5) (pass `noise` [N,C] for

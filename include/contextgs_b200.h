@@ -228,6 +228,33 @@ CGS_API int cgs_context_level_forward(int in_dim, const float *packed_w, const i
                                       float offset_mean, float *feat_q, float *scaling_q, float *offsets_q,
                                       float *bits_out, double *bit_sums, void *stream);
 
+/* Backward of one level in TRAINING mode (noise != NULL in the forward): what autograd does in the
+ * reference for the loop body scene/gaussian_model.py:1562-1652 plus the Entropy_gaussian terms of
+ * bit_per_param (:1666-1693).  Launch fine -> coarse.  G_feat/G_scaling/G_offsets [N,*] hold the gradient
+ * arriving on the quantised attributes and receive (a) in place, the gradient of the unquantised
+ * attributes for the rows of this level, (b) by atomic add, the gradient flowing to the quantised
+ * attributes of the coarser-level context sources.  d L / d bit_per_param is read from the device
+ * scalar g_bits_dev (NULL = no rate term); bits_factor = mask_anchor_rate / (n_chosen * 86).
+ * packed_w / d_packed_w use the backward layout W1[in][101] | b1[100] | W2[100][177] | b2[176]
+ * (cgs_context_level_backward_packed_floats); d_packed_w, d_mask, d_anchor are accumulated into,
+ * d_hyper_q rows of this level are overwritten.  ticket_dev: one device uint32 of scratch. */
+CGS_API int cgs_context_level_backward_packed_floats(int in_dim);
+CGS_API int cgs_context_level_backward(int in_dim, const float *packed_w, const int32_t *orig_idx,
+                                       const int32_t *ctx_src, const float *level_anchor, int n_rows,
+                                       const float *anchor, const float *hyper_q, const float *feat_q,
+                                       const float *scaling_q, const float *offsets_q, const float *mask,
+                                       const uint8_t *choose, const float *noise, float feat_mean, float scaling_mean,
+                                       float offset_mean, const float *g_bits_dev, float bits_factor, float *G_feat,
+                                       float *G_scaling, float *G_offsets, float *d_mask, float *d_hyper_q,
+                                       float *d_anchor, float *d_packed_w, uint32_t *ticket_dev, void *stream);
+
+/* Backward of cgs_eb_forward's bit term: d_hyper[N,C] += w * d(-log2 likelihood)/d hyper_q for the chosen
+ * anchors, d_packed_params[C,59] += the same w.r.t. the packed parameters (w = *g_bits_dev * bits_factor).
+ * CompressAI's LowerBound gradient rule is followed. */
+CGS_API int cgs_eb_backward(const float *packed_params, int C, const float *hyper_q, int N, const uint8_t *choose,
+                            const float *g_bits_dev, float bits_factor, float *d_hyper, float *d_packed_params,
+                            void *stream);
+
 /* Replaces `Entropy_gaussian.forward` (utils/entropy_models.py:34-50) and its autograd backward
  * incl. `Low_bound` (:141-156).  x/mean/scale/bits are [n,D]; Q is [n] (q_per_elem=0) or [n,D]. */
 CGS_API int cgs_gaussian_bits_forward(const float *x, const float *mean, const float *scale, const float *Q,

@@ -215,3 +215,52 @@ def test_sharded_scoring_adds_up_fake_world():
         assert part[5] == full[5]              # mask bits are global
     assert np.allclose(acc, np.asarray(full[:5], np.float64), rtol=1e-7)   # fp32 partial sums regroup
     assert torch.equal(fq, det["feat_q"])
+
+
+def test_training_backward_matches_autograd_of_the_oracle():
+    """Fused level / EntropyBottleneck backward kernels vs torch autograd through the oracle's
+    restatement of scene/gaussian_model.py:1541-1707 (training=True, predict_bpp=True), same noise."""
+    gold = load_npz("context_model.npz")
+    scene, pc = fixture_model(gold)
+    model = cuda_model(scene, pc).train()
+    N = pc.get_anchor.shape[0]
+    g = torch.Generator().manual_seed(3)
+    wf, ws, wo = torch.randn(N, 50, generator=g), torch.randn(N, 6, generator=g), torch.randn(N, 10, 3, generator=g)
+    LAM = 50.0
+
+    # ---- oracle (CPU fp32 autograd)
+    leaf = lambda t: t.detach().clone().requires_grad_(True)
+    hyper, feat, offs, scal, mask = (leaf(t) for t in (pc._hyper_latent, pc._anchor_feat, pc._offset, pc.get_scaling,
+                                                       pc.get_mask))
+    pc.mlps["grid"] = [[leaf(t) for t in lvl] for lvl in pc.mlps["grid"]]
+    eb = pc.latent_codec
+    eb.matrices, eb.biases, eb.factors = [leaf(t) for t in eb.matrices], [leaf(t) for t in eb.biases], \
+        [leaf(t) for t in eb.factors]
+    torch.manual_seed(7)
+    ref = er.multi_scale_generating(pc, pc.get_anchor, hyper, feat, offs, scal, mask, pc.get_mask_anchor,
+                                    training=True, predict_bpp=True)
+    ((ref[0] * wf).sum() + (ref[1] * ws).sum() + (ref[2] * wo).sum() + LAM * ref[3]).backward()
+
+    # ---- CUDA
+    plan = build_level_plan(model, model.get_anchor.detach(), model.get_mask_anchor)
+    noise = reference_noise(N, [lv.n for lv in plan.levels], seed=7)
+    cl = lambda t: t.detach().clone().cuda().requires_grad_(True)
+    c_hyper, c_feat, c_offs, c_scal, c_mask = (cl(t) for t in (pc._hyper_latent, pc._anchor_feat, pc._offset,
+                                                               pc.get_scaling, pc.get_mask))
+    res = multi_scale_generating(model, model.get_anchor.detach(), c_hyper, c_feat, c_offs, c_scal, c_mask,
+                                 model.get_mask_anchor, predict_bpp=True, training=True, noise=noise)
+    assert rel_l2(res[0].detach().cpu().numpy(), ref[0].detach().numpy()) < REL_L2
+    assert abs(float(res[3]) - float(ref[3])) / float(ref[3]) < 2e-4
+    ((res[0] * wf.cuda()).sum() + (res[1] * ws.cuda()).sum() + (res[2] * wo.cuda()).sum() + LAM * res[3]).backward()
+
+    TOL = 2e-3  # composite gradient: the rate term's erf tails amplify last-ulp differences (see the bits test)
+    for name, a, b in (("hyper", c_hyper, hyper), ("feat", c_feat, feat), ("offsets", c_offs, offs),
+                       ("scaling", c_scal, scal), ("mask", c_mask, mask)):
+        assert rel_l2(a.grad.cpu().numpy(), b.grad.numpy()) < TOL, name
+    for lvl in range(3):
+        seq = model.mlp_grid[lvl]
+        for ours, theirs in zip((seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias), pc.mlps["grid"][lvl]):
+            assert rel_l2(ours.grad.cpu().numpy(), theirs.grad.numpy()) < TOL, ("grid", lvl)
+    for ours, theirs in zip(list(model.latent_codec.matrices) + list(model.latent_codec.biases) +
+                            list(model.latent_codec.factors), eb.matrices + eb.biases + eb.factors):
+        assert rel_l2(ours.grad.cpu().numpy(), theirs.grad.numpy()) < TOL, "entropy bottleneck"
