@@ -401,27 +401,39 @@ def main():
 
 
 def extras(args, pc, pc_train, cams_dev, my_cam, pipe, bg, timed, world, dev):
-    from contextgs_b200.neural_gaussians import generate_neural_gaussians
-    from contextgs_b200.rasterizer import GaussianRasterizer
-    from contextgs_b200.renderer import _settings, prefilter_voxel
+    from contextgs_b200.renderer import prefilter_voxel
     ex = {}
     H, W = cams_dev[0].image_height, cams_dev[0].image_width
     gt = torch.rand(3, H, W, device=dev)
     k = max(4, args.steps // 4)
 
-    def train_raster_step(i):
+    from contextgs_b200.renderer import render
+
+    def train_step(i, step):
+        """One training iteration of train.py:158-211 without the optimizer: prefilter, render (G1 + rasterizer,
+        for step > 10000 also the whole-scene context model), L1 + lambda * bit_per_param, backward."""
         cam = cams_dev[my_cam(i)]
         with torch.no_grad():
-            vis = prefilter_voxel(cam, pc, pipe, bg)
-            xyz, color, opacity, scaling, rot, _ = generate_neural_gaussians(cam, pc, vis, is_training=False)
-        leaves = [t.detach().requires_grad_(True) for t in (xyz, color, opacity, scaling, rot)]
-        m2d = torch.zeros_like(leaves[0], requires_grad=True)
-        rast = GaussianRasterizer(_settings(cam, pipe, bg, 1.0))
-        img, _ = rast(means3D=leaves[0], means2D=m2d, shs=None, colors_precomp=leaves[1], opacities=leaves[2],
-                      scales=leaves[3], rotations=leaves[4], cov3D_precomp=None)
-        (img - gt).abs().mean().backward()
-    ms = timed(train_raster_step, k, 3)
-    ex["render_fwd_bwd_frames_per_s"] = world * k / (ms * 1e-3)
+            vis = prefilter_voxel(cam, pc_train, pipe, bg)
+        out = render(cam, pc_train, pipe, bg, visible_mask=vis, retain_grad=False, step=step)
+        loss = (out["render"] - gt).abs().mean() + 0.01 * out["scaling"].prod(dim=1).mean()
+        if out["bit_per_param"] is not None:
+            loss = loss + 0.004 * out["bit_per_param"]
+        loss.backward()
+        for p in pc_train.parameters():
+            p.grad = None
+        for p in (pc_train._anchor, pc_train._anchor_feat, pc_train._offset, pc_train._scaling, pc_train._mask,
+                  pc_train._hyper_latent):
+            p.grad = None
+
+    pc_train.train()
+    ms = timed(lambda i: train_step(i, 100), k, 3)
+    ex["train_iter_per_s_render_only"] = world * k / (ms * 1e-3)
+    ms = timed(lambda i: train_step(i, 20000), k, 3)
+    ex["train_iter_per_s_with_context_model"] = world * k / (ms * 1e-3)
+    ex["train_note"] = ("forward + backward of one camera per rank on the NON-decoded model (train.py:158-211 without "
+                        "optimizer.step): render_only = step <= 3000 regime; with_context_model = step > 10000 regime "
+                        "(3-level context model over all anchors, forward and backward, every iteration)")
 
     # entropy scoring: estimate_final_bits = 3-level context model + likelihoods over ALL anchors
     pc_train.eval()

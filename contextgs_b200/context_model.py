@@ -146,7 +146,8 @@ def _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choo
         hyper_q = hyper_q * 0
     feat_q, scaling_q, offsets_q = torch.zeros_like(feat), torch.zeros_like(scaling), torch.zeros_like(offsets)
     bits_out = torch.zeros((N, N_CODED), dtype=torch.float32, device=dev) if return_details else None
-    means = (float(pc._anchor_feat.mean()), float(pc.get_scaling.mean()), float(pc._offset.mean()))
+    with torch.no_grad():  # the three global means the reference passes as x_mean (gaussian_model.py:1667-1669)
+        means = tuple(torch.stack([pc._anchor_feat.mean(), pc.get_scaling.mean(), pc._offset.mean()]).tolist())
     stream = _lib.stream_ptr()
     level_noise = []
     for li, lv in enumerate(plan.levels):

@@ -263,9 +263,9 @@ def neural_gaussians(pc, camera_center, anchor, feat, grid_offsets, grid_scaling
 def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False, step=0):
     """Same signature and return tuples as gaussian_renderer/__init__.py:25-150.  Differentiable
     w.r.t. the per-anchor parameters and the decoder MLPs through `_NeuralGaussians` (autograd is
-    recorded whenever torch.is_grad_enabled()).  The context-model outputs (step > 10000) are
-    produced by the fused forward kernels; their backward is the next row of the build plan
-    (DESIGN.md section 9)."""
+    recorded whenever torch.is_grad_enabled()); for step > 10000 the context model is differentiable
+    too (`context_model._ContextModelTrain`), so `loss.backward()` of train.py:199-211 reaches every
+    parameter the reference trains."""
     from .context_model import multi_scale_generating
     anchor_all = pc.get_anchor
     N = anchor_all.shape[0]
