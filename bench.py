@@ -77,12 +77,16 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < 3.0:
+            time.sleep(0.01)  # nvidia-smi needs ~0.5 s to start: do not begin timing before it samples
+        self.n_before = len(self.lines)
         return self
 
     def _pump(self):
@@ -101,7 +105,7 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "n_before", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -305,10 +309,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, after_warmup=None):
         for i in range(warmup):
             fn(i)
         barrier()
+        if after_warmup is not None:
+            after_warmup()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
@@ -324,10 +330,11 @@ def main():
 
     # ---- device-resident pass (value) ------------------------------------------------------
     _lib.launch_counts(reset=True)
-    with ClockSampler(local_rank) as clk:
-        ms = timed(lambda i: frame(cams_dev[my_cam(i)]), args.steps, args.warmup)
-    launches_total = sum(_lib.launch_counts().values())
-    clocks = clk.summary()
+    clk = ClockSampler(local_rank)
+    clk.__enter__()
+    ms = timed(lambda i: frame(cams_dev[my_cam(i)]), args.steps, args.warmup,
+               after_warmup=lambda: _lib.launch_counts(reset=True))
+    launches_total = sum(_lib.launch_counts().values())  # kernels of libcontextgs_b200.so inside the timed region
     fps = world * args.steps / (ms * 1e-3)
 
     # ---- end-to-end pass: camera in host memory, image to pinned host memory -----------------
@@ -340,6 +347,8 @@ def main():
         torch.cuda.current_stream().synchronize()     # the caller owns the pixels before the next frame starts
     ms_e2e = timed(e2e_step, args.steps, max(args.warmup, 3))
     fps_e2e = world * args.steps / (ms_e2e * 1e-3)
+    clk.__exit__()
+    clocks = clk.summary()  # sampled over the device-resident and the end-to-end timed regions
 
     # ---- stage-timed pass (separate, so that event records do not perturb `value`) -------------
     _lib.stage_timing(True)

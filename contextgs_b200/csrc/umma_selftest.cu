@@ -55,14 +55,14 @@ umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ W, i
 
     if (tid == 0) {
         umma::fence_after_thread_sync();
-        if (mode == 0) {
+        if (mode == 0) {  // plain TF32
             const uint32_t idesc = umma::idesc_tf32(128, N);
             const uint32_t lbo = (uint32_t)N * 16u;
             for (int s = 0; s < K / 8; ++s)
                 umma::mma_tf32_ts(tbase + D_COL, tbase + A_HI + 8 * s,
                                   umma::smem_desc_kmajor(umma::smem_u32(w_hi) + (uint32_t)s * 2u * lbo, lbo, 128u), idesc,
                                   s > 0 ? 1u : 0u);
-        } else {
+        } else {          // modes 1, 2: 3xTF32
             umma::gemm_3xtf32(tbase + D_COL, tbase + A_HI, tbase + A_LO, w_hi, w_lo, N, K, true);
         }
         umma::umma_commit(&s_bar);
@@ -71,12 +71,27 @@ umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ W, i
     umma::fence_after_thread_sync();
     if (!ok && lane == 0) atomicExch(err, 1);
 
-    for (int n0 = 0; n0 < N; n0 += 8) {
+    // mode 2 reads the accumulator with UNALIGNED column starts (3, 11, 19, ...): the fused kernels read
+    // per-anchor column groups that do not start on a multiple of the load width
+    const int start = mode == 2 ? 3 : 0;
+    if (mode == 2) {
+        uint32_t v[8];
+        umma::tmem_ld8(lane_base + D_COL, v);
+        umma::tmem_wait_ld();
+        for (int j = 0; j < 3; ++j) D[(size_t)tid * N + j] = __uint_as_float(v[j]);
+    }
+    for (int n0 = start; n0 + 8 <= N; n0 += 8) {
         uint32_t v[8];
         umma::tmem_ld8(lane_base + D_COL + n0, v);
         umma::tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j) D[(size_t)tid * N + n0 + j] = __uint_as_float(v[j]);
+    }
+    if (mode == 2) {  // tail: the last 5 columns
+        uint32_t v[8];
+        umma::tmem_ld8(lane_base + D_COL + N - 8, v);
+        umma::tmem_wait_ld();
+        for (int j = 0; j < 8; ++j) D[(size_t)tid * N + N - 8 + j] = __uint_as_float(v[j]);
     }
     umma::fence_before_thread_sync();
     __syncthreads();

@@ -33,6 +33,7 @@ def test_tile_gemm_matches_fp64(N, K):
     assert np.isfinite(d1).all() and np.isfinite(d3).all()
     assert rel_l2(d1, ref) < 2e-3          # plain TF32: 10-bit mantissas
     assert rel_l2(d3, ref) < 2e-6          # 3xTF32: fp32-grade
+    assert np.array_equal(run(A, W, 2).cpu().numpy(), d3)   # tcgen05.ld at unaligned column offsets
     # structure: each output element depends on its own row / column only
     A2 = A.clone()
     A2[5] = 0
