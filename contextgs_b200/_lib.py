@@ -70,6 +70,10 @@ SIGNATURES = {
     "cgs_context_level_forward": (c_int, [c_int, _PTR, _PTR, _PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
                                           _PTR, _PTR, ctypes.c_float, ctypes.c_float, ctypes.c_float, _PTR, _PTR,
                                           _PTR, _PTR, _PTR, _PTR]),
+    "cgs_context_level_umma_packed_floats": (c_int, [c_int]),
+    "cgs_context_level_umma_forward": (c_int, [c_int, _PTR, _PTR, _PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
+                                               _PTR, _PTR, ctypes.c_float, ctypes.c_float, ctypes.c_float, _PTR, _PTR,
+                                               _PTR, _PTR, _PTR, _PTR, _PTR]),
     "cgs_context_level_backward_packed_floats": (c_int, [c_int]),
     "cgs_context_level_backward": (c_int, [c_int, _PTR, _PTR, _PTR, _PTR, c_int] + [_PTR] * 8 +
                                    [ctypes.c_float] * 3 + [_PTR, ctypes.c_float] + [_PTR] * 9),

@@ -37,6 +37,7 @@ SOURCES = {
     "neural_gaussians_umma.cu": ["-fmad=false"],
     "neural_gaussians_bwd.cu": [],
     "context_model_bwd.cu": [],
+    "context_model_umma.cu": ["-fmad=false"],
 }
 
 

@@ -40,6 +40,43 @@ def pack_grid_weights(pc, level):
     return packed, in_dim
 
 
+_grid_pack_cache_umma = {}
+
+
+def pack_grid_weights_umma(pc, level):
+    """tcgen05 block of `pc.get_grid_mlp[level]` (csrc/context_model_umma.cu `cmu::Layout`):
+    W1 hi | W1 lo ([K1p/4][112][4]) | W2 hi | W2 lo ([26][176][4]) | b1[112] | b2[176]."""
+    from .neural_gaussians import umma_b_operand
+    m = pc.get_grid_mlp[level]
+    params = (m[0].weight, m[0].bias, m[2].weight, m[2].bias)
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    ent = _grid_pack_cache_umma.get((id(pc), level))
+    if ent is not None and ent[0] == key:
+        return ent[1], ent[2]
+    with torch.no_grad():
+        dev = params[0].device
+        in_dim = m[0].weight.shape[1]
+        k1p = (in_dim + 7) // 8 * 8
+        b1 = torch.zeros(112, device=dev)
+        b1[:100] = m[0].bias
+        b2 = torch.zeros(176, device=dev)
+        b2[:175] = m[2].bias
+        packed = torch.cat([*umma_b_operand(m[0].weight, 112, k1p), *umma_b_operand(m[2].weight, 176, 104), b1, b2])
+        packed = packed.float().contiguous()
+    assert packed.numel() == _lib.lib().cgs_context_level_umma_packed_floats(in_dim)
+    _grid_pack_cache_umma[(id(pc), level)] = (key, packed, in_dim)
+    return packed, in_dim
+
+
+def ctx_impl():
+    """'umma' (tcgen05 tensor cores, default) or 'simt' (fp32 FMA tiles; kept for cross-checks)."""
+    import os
+    v = os.environ.get("CGS_CTX_IMPL", "umma")
+    if v not in ("umma", "simt"):
+        raise ValueError("CGS_CTX_IMPL must be 'umma' or 'simt'")
+    return v
+
+
 # ----------------------------------------------------------------------------- level division (E1-E3)
 
 def _unique_rows_first_index(rows):
@@ -150,6 +187,8 @@ def _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choo
         means = tuple(torch.stack([pc._anchor_feat.mean(), pc.get_scaling.mean(), pc._offset.mean()]).tolist())
     stream = _lib.stream_ptr()
     level_noise = []
+    umma = ctx_impl() == "umma"
+    err = torch.zeros(1, dtype=torch.int32, device=dev) if umma else None
     for li, lv in enumerate(plan.levels):
         nz = None
         if training and lv.n:
@@ -158,15 +197,19 @@ def _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choo
         level_noise.append(nz)
         if lv.n == 0:
             continue
-        packed, in_dim = pack_grid_weights(pc, lv.level)
-        _lib.check(L.cgs_context_level_forward(
-            in_dim, _lib.ptr(packed), _lib.ptr(lv.orig), _lib.ptr(lv.ctx_src), _lib.ptr(lv.level_anchor), lv.n,
-            _lib.ptr(anchor), _lib.ptr(hyper_q), _lib.ptr(feat), _lib.ptr(scaling), _lib.ptr(offsets), _lib.ptr(masks),
-            _lib.ptr(choose_u8), _lib.ptr(nz), means[0], means[1], means[2], _lib.ptr(feat_q), _lib.ptr(scaling_q),
-            _lib.ptr(offsets_q), _lib.ptr(bits_out), _lib.ptr(sums[4 * li:4 * li + 4]), stream),
-            "cgs_context_level_forward")
+        args = (_lib.ptr(lv.orig), _lib.ptr(lv.ctx_src), _lib.ptr(lv.level_anchor), lv.n, _lib.ptr(anchor),
+                _lib.ptr(hyper_q), _lib.ptr(feat), _lib.ptr(scaling), _lib.ptr(offsets), _lib.ptr(masks),
+                _lib.ptr(choose_u8), _lib.ptr(nz), means[0], means[1], means[2], _lib.ptr(feat_q), _lib.ptr(scaling_q),
+                _lib.ptr(offsets_q), _lib.ptr(bits_out), _lib.ptr(sums[4 * li:4 * li + 4]))
+        if umma:
+            packed, in_dim = pack_grid_weights_umma(pc, lv.level)
+            _lib.check(L.cgs_context_level_umma_forward(in_dim, _lib.ptr(packed), *args, _lib.ptr(err), stream),
+                       "cgs_context_level_umma_forward")
+        else:
+            packed, in_dim = pack_grid_weights(pc, lv.level)
+            _lib.check(L.cgs_context_level_forward(in_dim, _lib.ptr(packed), *args, stream), "cgs_context_level_forward")
     return dict(feat_q=feat_q, scaling_q=scaling_q, offsets_q=offsets_q, hyper_q=hyper_q, lik=lik, sums=sums,
-                bits_out=bits_out, level_noise=level_noise, means=means)
+                bits_out=bits_out, level_noise=level_noise, means=means, err=err)
 
 
 def pack_grid_weights_bwd(m):
@@ -303,6 +346,8 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
         from .distributed import all_reduce_sums
         all_reduce_sums(sums, group)
     s = info["sums_host"] if "sums_host" in info else sums.tolist()  # one host read-back (the reference: several .item())
+    if info.get("err") is not None and int(info["err"].item()):
+        raise _lib.CgsError("cgs_context_level_umma_forward: a tensor-core completion barrier timed out")
     bit_feat, bit_scaling, bit_offsets = (sum(s[4 * i + c] for i in range(3)) for c in range(3))
     n_chosen = sum(s[4 * i + 3] for i in range(3))
     bit_hyper = s[12]

@@ -10,17 +10,10 @@
 //    leave shared memory.
 //  * gaussian_bits_{forward,backward}, ste_multistep, quantize_anchor : stand-alone elementwise
 //    kernels behind the drop-in utils.entropy_models / utils.encodings surface.
+#include "entropy_math.cuh"
 #include "mlp_tile.cuh"
 
 namespace cgs {
-
-constexpr int kCF = 50, kCS = 6, kCO = 30, kCE = kCF + kCS + kCO;  // 86 coded values per anchor
-constexpr int kCtx = 3 + kCF + kCS;                               // 59
-constexpr int kHyper = 12;
-constexpr int kGH = 100, kGO = 175, kLdG2 = 176;
-constexpr float kQf0 = 1.0f, kQs0 = 0.001f, kQo0 = 0.2f;
-constexpr float kClampSteps = 15000.0f;
-constexpr int kEbParams = 59;
 
 // ------------------------------------------------------------------------------------ E4
 __device__ __forceinline__ float eb_logits(const float *__restrict__ p, float v)
@@ -85,30 +78,6 @@ eb_forward_kernel(const float *__restrict__ params, int C, const float *__restri
         for (int o = 16; o > 0; o >>= 1) local_bits += __shfl_xor_sync(0xffffffffu, local_bits, o);
         if ((threadIdx.x & 31) == 0 && local_bits != 0.f) atomicAdd(bit_sum, (double)local_bits);
     }
-}
-
-// ------------------------------------------------------------------------------------ E6 core
-__device__ __forceinline__ float normal_cdf(float v, float mean, float inv_scale)
-{
-    // torch.distributions.Normal.cdf: 0.5 * (1 + erf((v - loc) * scale.reciprocal() / sqrt(2)))
-    return 0.5f * (1.0f + erff(__fdiv_rn((v - mean) * inv_scale, 1.41421356237309515f)));
-}
-
-__device__ __forceinline__ float gaussian_bits_one(float x, float mean, float scale, float Q, float x_mean)
-{
-    x = fminf(fmaxf(x, x_mean - kClampSteps * Q), x_mean + kClampSteps * Q);
-    scale = fmaxf(scale, 1e-9f);
-    const float inv = __frcp_rn(scale);
-    const float upper = normal_cdf(x + 0.5f * Q, mean, inv);
-    const float lower = normal_cdf(x - 0.5f * Q, mean, inv);
-    const float lk = fmaxf(fabsf(upper - lower), 1e-6f);
-    return -log2f(lk);
-}
-
-__device__ __forceinline__ float ste_round(float x, float Q)
-{
-    x = fminf(fmaxf(x, -kClampSteps * Q), kClampSteps * Q);
-    return rintf(__fdiv_rn(x, Q)) * Q;
 }
 
 // ------------------------------------------------------------------------------------ E5-E7

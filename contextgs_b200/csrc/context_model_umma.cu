@@ -1,0 +1,358 @@
+// One level of the anchor-level context model on the tcgen05 tensor cores.
+//
+// Same contract as context_level_kernel in context_model.cu (reference loop body
+// scene/gaussian_model.py:1562-1652 + Entropy_gaussian :1666-1670 + the sums :1685-1693): gather the
+// coarser-level context -> context MLP (71|15 -> 100 ReLU -> 175) -> adaptive steps -> quantise ->
+// scatter -> discretised-Gaussian bits -> fp64 bit sums.  The two MLP layers run as 3xTF32
+// tcgen05.mma with every activation resident in TENSOR MEMORY (see umma.cuh and
+// neural_gaussians_umma.cu for the scheme):
+//
+//   persistent CTA per SM, 256 threads, tile = 128 level rows = 128 TMEM lanes;
+//   thread (row = 32*(warp%4) + lane, half = warp/4): two threads share a row.
+//   TMEM columns (432 of 512):
+//     [  0,144)  input x_hi [0,72) | x_lo [72,144)            -> later hidden_lo [0,112)
+//     [144,256)  layer-1 accumulator (100 units + 12 zero pads) -> hidden_hi in place
+//     [256,432)  layer-2 accumulator: mu_f 50 | sigma_f 50 | mu_s 6 | sigma_s 6 | mu_o 30 | sigma_o 30 |
+//                dQ_f dQ_s dQ_o | pad
+//   shared memory: W1 hi/lo [K1p/4][112][4], W2 hi/lo [26][176][4], biases (212 KB for K1 = 71).
+//   The next tile's gathered rows are prefetched into registers while the MMAs and epilogues run.
+#include "entropy_math.cuh"
+#include "umma.cuh"
+
+namespace cgs {
+namespace cmu {
+constexpr int kRows = 128, kThreads = 256;
+constexpr int kN1 = 112, kK2 = 104, kN2 = 176;
+constexpr uint32_t kColXHi = 0, kColXLo = 72, kColHLo = 0, kColD1 = 144, kColD2 = 256, kTmemCols = 512;
+
+template <int K1>
+struct Layout {
+    static constexpr int kK1p = (K1 + 7) / 8 * 8;                 // 72 | 16
+    static constexpr int kW1 = (kK1p / 4) * kN1 * 4;              // floats per hi / lo part
+    static constexpr int kW2 = (kK2 / 4) * kN2 * 4;
+    static constexpr int kOffW1Hi = 0, kOffW1Lo = kW1, kOffW2Hi = 2 * kW1, kOffW2Lo = 2 * kW1 + kW2;
+    static constexpr int kOffB1 = 2 * kW1 + 2 * kW2, kOffB2 = kOffB1 + kN1, kPacked = kOffB2 + kN2;
+    static constexpr int kHalf0 = K1 == 71 ? 40 : 8;              // layer-1 inputs staged by half 0
+    static constexpr int kXRegs = K1 == 71 ? 40 : 8;              // registers per thread for its share
+};
+
+template <int K1>
+struct Smem {
+    float w[Layout<K1>::kPacked];
+    uint32_t tmem;
+    int timeout;
+    alignas(8) uint64_t bar[2];
+};
+
+struct Args {
+    const float *packed_w;
+    const int *orig_idx, *ctx_src;
+    const float *level_anchor;
+    int n_rows;
+    const float *anchor, *hyper_q, *feat, *scaling, *offsets, *mask;
+    const uint8_t *choose;
+    const float *noise;
+    float feat_mean, scaling_mean, offset_mean;
+    float *feat_q, *scaling_q, *offsets_q, *bits_out;
+    double *bit_sums;
+    int32_t *err_flag;
+};
+
+template <int K1>
+struct RowInputs {
+    float x[Layout<K1>::kXRegs];
+    int o;   // original anchor index of the row (-1: padding)
+};
+
+// half 0 stages inputs k in [0, kHalf0), half 1 the rest (K1 = 71: [anchor 3 | feat_q 50 | scaling_q 6 |
+// hyper_q 12]; K1 = 15: [level anchor 3 | hyper_q 12]).
+template <int K1>
+__device__ __forceinline__ void load_row(RowInputs<K1> &r, const Args &A, int row, int half)
+{
+    constexpr int XR = Layout<K1>::kXRegs;
+#pragma unroll
+    for (int j = 0; j < XR; ++j) r.x[j] = 0.f;
+    r.o = -1;
+    if (row >= A.n_rows) return;
+    const int o = __ldg(A.orig_idx + row);
+    r.o = o;
+    const float *hq = A.hyper_q + (size_t)o * kHyper;
+    if (K1 == 71) {
+        const int s = __ldg(A.ctx_src + row);
+        const float *fq = A.feat_q + (size_t)s * kCF;
+        if (half == 0) {  // k 0..39 = anchor[s] (3) | feat_q[s][0..36]
+#pragma unroll
+            for (int j = 0; j < 3; ++j) r.x[j] = __ldg(A.anchor + 3 * (size_t)s + j);
+#pragma unroll
+            for (int j = 0; j < 37; ++j) r.x[3 + j] = fq[j];
+        } else {          // k 40..70 = feat_q[s][37..49] | scaling_q[s] (6) | hyper_q[o] (12)
+#pragma unroll
+            for (int j = 0; j < 13; ++j) r.x[j] = fq[37 + j];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) r.x[13 + j] = A.scaling_q[(size_t)s * kCS + j];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) r.x[19 + j] = __ldg(hq + j);
+        }
+    } else {
+        if (half == 0) {  // k 0..7 = level anchor (3) | hyper_q[0..4]
+#pragma unroll
+            for (int j = 0; j < 3; ++j) r.x[j] = __ldg(A.level_anchor + 3 * (size_t)row + j);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) r.x[3 + j] = __ldg(hq + j);
+        } else {          // k 8..14 = hyper_q[5..11]
+#pragma unroll
+            for (int j = 0; j < 7; ++j) r.x[j] = __ldg(hq + 5 + j);
+        }
+    }
+}
+
+template <int K1>
+__global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
+{
+    using LY = Layout<K1>;
+    using SM = Smem<K1>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SM &S = *reinterpret_cast<SM *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = warp >> 2;
+    const int row = 32 * (warp & 3) + lane;
+    const int num_tiles = (A.n_rows + kRows - 1) / kRows;
+
+    if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
+    if (tid == 0) {
+        umma::mbar_init(&S.bar[0], 1);
+        umma::mbar_init(&S.bar[1], 1);
+        umma::fence_mbar_init();
+        S.timeout = 0;
+    }
+    {
+        const float4 *s4 = reinterpret_cast<const float4 *>(A.packed_w);
+        float4 *d4 = reinterpret_cast<float4 *>(S.w);
+        for (int i = tid; i < LY::kPacked / 4; i += kThreads) d4[i] = __ldg(s4 + i);
+    }
+    umma::fence_proxy_async_smem();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = S.tmem;
+    const uint32_t tl = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+
+    float sum_f = 0.f, sum_s = 0.f, sum_o = 0.f, n_chosen = 0.f;
+    int tile = blockIdx.x;
+    RowInputs<K1> cur;
+    load_row<K1>(cur, A, tile * kRows + row, half);
+
+    for (uint32_t it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
+        const uint32_t parity = it & 1u;
+        const int grow = tile * kRows + row;
+        const int o = cur.o;
+
+        // ---- stage the layer-1 input --------------------------------------------------------------
+        {
+            const uint32_t k0 = half == 0 ? 0u : (uint32_t)LY::kHalf0;
+            constexpr int kChunks0 = LY::kHalf0 / 8, kChunks1 = (LY::kK1p - LY::kHalf0) / 8;
+#pragma unroll
+            for (int c = 0; c < (kChunks0 > kChunks1 ? kChunks0 : kChunks1); ++c) {
+                if (c < (half == 0 ? kChunks0 : kChunks1)) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) umma::split_tf32(cur.x[8 * c + j], hi[j], lo[j]);
+                    umma::tmem_st8(tl + kColXHi + k0 + 8 * c, hi);
+                    umma::tmem_st8(tl + kColXLo + k0 + 8 * c, lo);
+                }
+            }
+        }
+        umma::tmem_wait_st();
+        umma::fence_before_thread_sync();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_thread_sync();
+            umma::gemm_3xtf32(tbase + kColD1, tbase + kColXHi, tbase + kColXLo, S.w + LY::kOffW1Hi, S.w + LY::kOffW1Lo,
+                              kN1, LY::kK1p, true);
+            umma::umma_commit(&S.bar[0]);
+        }
+        // prefetch the next tile's gathered rows while the tensor core works
+        RowInputs<K1> nxt;
+        load_row<K1>(nxt, A, (tile + (int)gridDim.x) * kRows + row, half);
+        if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
+        umma::fence_after_thread_sync();
+
+        // ---- epilogue 1: hidden = relu(D1 + b1) -> hi in place, lo to region 0 (cols 56*half .. +56) ----
+#pragma unroll 1
+        for (int c = 0; c < 7; ++c) {
+            const uint32_t col = (uint32_t)(56 * half + 8 * c);
+            uint32_t v[8], hi[8], lo[8];
+            umma::tmem_ld8(tl + kColD1 + col, v);
+            umma::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float h = fmaxf(__uint_as_float(v[j]) + S.w[LY::kOffB1 + col + j], 0.f);
+                umma::split_tf32(h, hi[j], lo[j]);
+            }
+            umma::tmem_st8(tl + kColD1 + col, hi);
+            umma::tmem_st8(tl + kColHLo + col, lo);
+        }
+        umma::tmem_wait_st();
+        umma::fence_before_thread_sync();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_thread_sync();
+            umma::gemm_3xtf32(tbase + kColD2, tbase + kColD1, tbase + kColHLo, S.w + LY::kOffW2Hi, S.w + LY::kOffW2Lo, kN2,
+                              kK2, true);
+            umma::umma_commit(&S.bar[1]);
+        }
+        if (!umma::mbar_wait(&S.bar[1], parity)) S.timeout = 1;
+        umma::fence_after_thread_sync();
+
+        // ---- epilogue 2: steps, quantise, scatter, bits ----------------------------------------------
+        float Qf, Qs, Qo;
+        {
+            uint32_t v[4];
+            umma::tmem_ld4(tl + kColD2 + 172, v);
+            umma::tmem_wait_ld();
+            Qf = fmaxf(kQf0 * (1.0f + tanhf(__uint_as_float(v[0]) + S.w[LY::kOffB2 + 172])), 1e-9f);
+            Qs = fmaxf(kQs0 * (1.0f + tanhf(__uint_as_float(v[1]) + S.w[LY::kOffB2 + 173])), 1e-9f);
+            Qo = fmaxf(kQo0 * (1.0f + tanhf(__uint_as_float(v[2]) + S.w[LY::kOffB2 + 174])), 1e-9f);
+        }
+        const bool chosen = o >= 0 && (A.choose ? A.choose[o] != 0 : true);
+        if (half == 0 && chosen) n_chosen += 1.f;
+        const float *nz = A.noise ? A.noise + (size_t)grow * kCE : nullptr;
+
+        // one group of up to 8 consecutive coded values j0 .. j0+cnt-1 (all of the same attribute)
+        auto chunk = [&](int j0, int cnt, uint32_t mu_col, uint32_t sg_col, const float *src, float *dst, int dim,
+                         int k0, float Q, float x_mean, int grp, float &acc) {
+            uint32_t vm[8], vs[8];
+            umma::tmem_ld8(tl + kColD2 + mu_col, vm);
+            umma::tmem_ld8(tl + kColD2 + sg_col, vs);
+            umma::tmem_wait_ld();
+            if (o < 0) return;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < cnt) {
+                    const int k = k0 + j;  // index inside the attribute
+                    const float x = src[(size_t)o * dim + k];
+                    const float xq = nz ? x + nz[j0 + j] * Q : ste_round(x, Q);
+                    dst[(size_t)o * dim + k] = xq;
+                    float bits = 0.f;
+                    if (chosen) {
+                        const float mean = __uint_as_float(vm[j]) + S.w[LY::kOffB2 + mu_col + j];
+                        const float scale = __uint_as_float(vs[j]) + S.w[LY::kOffB2 + sg_col + j];
+                        bits = gaussian_bits_one(xq, mean, scale, Q, x_mean);
+                        if (grp == 2) bits *= A.mask[(size_t)o * 10 + k / 3];
+                        acc += bits;
+                    }
+                    if (A.bits_out) A.bits_out[(size_t)o * kCE + j0 + j] = bits;
+                }
+            }
+        };
+        if (half == 0) {
+            // feat 0 .. 42
+#pragma unroll 1
+            for (int c = 0; c < 6; ++c) {
+                const int k0 = 8 * c, cnt = k0 + 8 <= 43 ? 8 : 43 - k0;
+                chunk(k0, cnt, (uint32_t)k0, (uint32_t)(kCF + k0), A.feat, A.feat_q, kCF, k0, Qf, A.feat_mean, 0, sum_f);
+            }
+        } else {
+            // feat 43 .. 49
+            chunk(43, 7, 43u, (uint32_t)(kCF + 43), A.feat, A.feat_q, kCF, 43, Qf, A.feat_mean, 0, sum_f);
+            // scaling 0 .. 5   (mu cols 100..105, sigma cols 106..111)
+            chunk(kCF, 6, 100u, 106u, A.scaling, A.scaling_q, kCS, 0, Qs, A.scaling_mean, 1, sum_s);
+            // offsets 0 .. 29  (mu cols 112..141, sigma cols 142..171)
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int k0 = 8 * c, cnt = k0 + 8 <= 30 ? 8 : 30 - k0;
+                chunk(kCF + kCS + k0, cnt, (uint32_t)(112 + k0), (uint32_t)(142 + k0), A.offsets, A.offsets_q, kCO, k0, Qo,
+                      A.offset_mean, 2, sum_o);
+            }
+        }
+        // all TMEM reads of this tile are complete before the next tile's stores / MMAs reuse the columns
+        umma::fence_before_thread_sync();
+        __syncthreads();
+        umma::fence_after_thread_sync();
+        cur = nxt;
+    }
+
+    // ---- per-CTA reduction of the bit sums -> one fp64 atomic per sum ----------------------------------
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sum_f += __shfl_xor_sync(0xffffffffu, sum_f, off);
+        sum_s += __shfl_xor_sync(0xffffffffu, sum_s, off);
+        sum_o += __shfl_xor_sync(0xffffffffu, sum_o, off);
+        n_chosen += __shfl_xor_sync(0xffffffffu, n_chosen, off);
+    }
+    __shared__ double s_red[4][kThreads / 32];
+    if (lane == 0) {
+        s_red[0][warp] = sum_f; s_red[1][warp] = sum_s; s_red[2][warp] = sum_o; s_red[3][warp] = n_chosen;
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    if (tid < 4) {
+        double v = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
+        if (v != 0.0) atomicAdd(A.bit_sums + tid, v);
+    }
+    if (tid == 0 && S.timeout) atomicExch(A.err_flag, 1);
+    if (warp == 0) umma::tmem_dealloc(tbase, kTmemCols);
+}
+
+template <int K1>
+static int launch(const Args &a, cudaStream_t st)
+{
+    using SM = Smem<K1>;
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(context_level_umma_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
+        if (sm_count <= 0) sm_count = kNumSMs;
+    }
+    const int tiles = (a.n_rows + kRows - 1) / kRows;
+    StageScope sc(ST_CTX_LEVEL, st, 1);
+    context_level_umma_kernel<K1><<<tiles < sm_count ? tiles : sm_count, kThreads, sizeof(SM), st>>>(a);
+    return check_launch("cgs_context_level_umma_forward");
+}
+}  // namespace cmu
+}  // namespace cgs
+
+using namespace cgs;
+
+extern "C" int cgs_context_level_umma_packed_floats(int in_dim)
+{
+    if (in_dim == 71) return cmu::Layout<71>::kPacked;
+    if (in_dim == 15) return cmu::Layout<15>::kPacked;
+    return -1;
+}
+
+extern "C" int cgs_context_level_umma_forward(int in_dim, const float *packed_w, const int32_t *orig_idx,
+                                              const int32_t *ctx_src, const float *level_anchor, int n_rows,
+                                              const float *anchor, const float *hyper_q, const float *feat,
+                                              const float *scaling, const float *offsets, const float *mask,
+                                              const uint8_t *choose, const float *noise, float feat_mean,
+                                              float scaling_mean, float offset_mean, float *feat_q, float *scaling_q,
+                                              float *offsets_q, float *bits_out, double *bit_sums, int32_t *err_flag,
+                                              void *stream)
+{
+    if (n_rows <= 0) return 0;
+    CGS_CHECK_PTR(packed_w); CGS_CHECK_PTR(orig_idx); CGS_CHECK_PTR(anchor); CGS_CHECK_PTR(hyper_q);
+    CGS_CHECK_PTR(feat); CGS_CHECK_PTR(scaling); CGS_CHECK_PTR(offsets); CGS_CHECK_PTR(mask);
+    CGS_CHECK_PTR(feat_q); CGS_CHECK_PTR(scaling_q); CGS_CHECK_PTR(offsets_q); CGS_CHECK_PTR(bit_sums);
+    CGS_CHECK_PTR(err_flag);
+    cmu::Args a;
+    a.packed_w = packed_w; a.orig_idx = orig_idx; a.ctx_src = ctx_src; a.level_anchor = level_anchor; a.n_rows = n_rows;
+    a.anchor = anchor; a.hyper_q = hyper_q; a.feat = feat; a.scaling = scaling; a.offsets = offsets; a.mask = mask;
+    a.choose = choose; a.noise = noise; a.feat_mean = feat_mean; a.scaling_mean = scaling_mean;
+    a.offset_mean = offset_mean; a.feat_q = feat_q; a.scaling_q = scaling_q; a.offsets_q = offsets_q;
+    a.bits_out = bits_out; a.bit_sums = bit_sums; a.err_flag = err_flag;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (in_dim == 71) {
+        CGS_CHECK_PTR(ctx_src);
+        return cmu::launch<71>(a, st);
+    }
+    if (in_dim == 15) {
+        CGS_CHECK_PTR(level_anchor);
+        return cmu::launch<15>(a, st);
+    }
+    set_error("%s: unsupported context-MLP input width %d", __func__, in_dim);
+    return -2;
+}

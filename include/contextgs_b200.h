@@ -228,6 +228,20 @@ CGS_API int cgs_context_level_forward(int in_dim, const float *packed_w, const i
                                       float offset_mean, float *feat_q, float *scaling_q, float *offsets_q,
                                       float *bits_out, double *bit_sums, void *stream);
 
+/* The same level on the tcgen05 tensor cores (3xTF32, activations resident in tensor memory;
+ * csrc/context_model_umma.cu).  Identical arguments and results; the packed block is the TF32 hi/lo split
+ * in the K-major core-matrix layout (contextgs_b200/context_model.py pack_grid_weights_umma).
+ * *err_flag (device int32) is set to 1 if a tensor-core completion barrier timed out. */
+CGS_API int cgs_context_level_umma_packed_floats(int in_dim);
+CGS_API int cgs_context_level_umma_forward(int in_dim, const float *packed_w, const int32_t *orig_idx,
+                                           const int32_t *ctx_src, const float *level_anchor, int n_rows,
+                                           const float *anchor, const float *hyper_q, const float *feat,
+                                           const float *scaling, const float *offsets, const float *mask,
+                                           const uint8_t *choose, const float *noise, float feat_mean,
+                                           float scaling_mean, float offset_mean, float *feat_q, float *scaling_q,
+                                           float *offsets_q, float *bits_out, double *bit_sums, int32_t *err_flag,
+                                           void *stream);
+
 /* Backward of one level in TRAINING mode (noise != NULL in the forward): what autograd does in the
  * reference for the loop body scene/gaussian_model.py:1562-1652 plus the Entropy_gaussian terms of
  * bit_per_param (:1666-1693).  Launch fine -> coarse.  G_feat/G_scaling/G_offsets [N,*] hold the gradient

@@ -15,6 +15,13 @@ pytestmark = pytest.mark.gpu
 REL_L2 = 1e-4
 
 
+@pytest.fixture(params=["umma", "simt"], autouse=True)
+def ctx_impl(request, monkeypatch):
+    """Every test runs against the tcgen05 level kernel (default) and the fp32-FMA one."""
+    monkeypatch.setenv("CGS_CTX_IMPL", request.param)
+    return request.param
+
+
 def symbol_mismatch(a, b, Q):
     """Fraction of quantised values that differ by more than rounding noise of one step."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
