@@ -462,6 +462,14 @@ def extras(args, pc, pc_train, cams_dev, my_cam, pipe, bg, timed, world, dev):
     ex["anchor_mbits_per_s_cached_level_plan"] = world * bits * ke / (ms * 1e-3) / 1e6
     ex["entropy_pass_ms_cached_level_plan"] = ms / ke
     ex["scored_mbits"] = bits / 1e6
+    from contextgs_b200 import _lib
+    _lib.stage_timing(True)
+    for i in range(3):
+        score(i, False)
+    torch.cuda.synchronize()
+    st_ms, st_n = _lib.stage_timing_read()
+    _lib.stage_timing(False)
+    ex["entropy_stage_ms_per_pass"] = {k: round(v / 3, 4) for k, v in st_ms.items() if st_n[k] > 0}
     ex["entropy_note"] = ("anchor Mbit/s = estimated bits (hyper+feat+scaling+masked offsets of every valid anchor, "
                           "what estimate_final_bits sums, gaussian_model.py:1685) / wall time of the full 3-level "
                           "scoring pass; first figure rebuilds the level division every call like the reference")

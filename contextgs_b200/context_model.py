@@ -302,7 +302,10 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
     sharded = plan is not None
     with torch.no_grad():
         if pc.level_scale is None:
-            pc.level_scale = find_divide_scale(pc, anchor[mask_anchor_bool], pc.target_ratio, pc.level_num)
+            # (the reference indexes with mask_anchor_bool even when it is None, scene/gaussian_model.py:1559;
+            #  it only ever reaches this line from training, where the mask is given)
+            pc.level_scale = find_divide_scale(pc, anchor if mask_anchor_bool is None else anchor[mask_anchor_bool],
+                                               pc.target_ratio, pc.level_num)
         if plan is None:
             plan = get_level_plan(pc, anchor, mask_anchor_bool)
 

@@ -106,6 +106,32 @@ __device__ __forceinline__ void load_row(RowInputs<K1> &r, const Args &A, int ro
     }
 }
 
+// The 43 coded values of a thread are processed in 6 groups of <= 8 consecutive values of one attribute:
+//   half 0: feat 0..42;   half 1: feat 43..49 | scaling 0..5 | offsets 0..29
+struct ChunkDesc {
+    int j0;              // index among the 86 coded values
+    int cnt;             // values in the group
+    uint32_t mu_col, sg_col;  // accumulator columns of mean / scale
+    int grp, dim, k0;    // attribute (0 feat, 1 scaling, 2 offsets), its row width, first index inside it
+};
+__device__ __forceinline__ ChunkDesc chunk_desc(int c, int half)
+{
+    ChunkDesc d;
+    if (half == 0) {
+        d.j0 = 8 * c; d.cnt = 8 * c + 8 <= 43 ? 8 : 43 - 8 * c; d.mu_col = 8 * c; d.sg_col = kCF + 8 * c;
+        d.grp = 0; d.dim = kCF; d.k0 = 8 * c;
+    } else if (c == 0) {
+        d.j0 = 43; d.cnt = 7; d.mu_col = 43; d.sg_col = kCF + 43; d.grp = 0; d.dim = kCF; d.k0 = 43;
+    } else if (c == 1) {
+        d.j0 = kCF; d.cnt = 6; d.mu_col = 100; d.sg_col = 106; d.grp = 1; d.dim = kCS; d.k0 = 0;
+    } else {
+        const int cc = c - 2;
+        d.j0 = kCF + kCS + 8 * cc; d.cnt = 8 * cc + 8 <= 30 ? 8 : 30 - 8 * cc; d.mu_col = 112 + 8 * cc;
+        d.sg_col = 142 + 8 * cc; d.grp = 2; d.dim = kCO; d.k0 = 8 * cc;
+    }
+    return d;
+}
+
 template <int K1>
 __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
 {
@@ -137,7 +163,8 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
     const uint32_t tbase = S.tmem;
     const uint32_t tl = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
 
-    float sum_f = 0.f, sum_s = 0.f, sum_o = 0.f, n_chosen = 0.f;
+    double tot_f = 0.0, tot_s = 0.0, tot_o = 0.0;   // fp64 across tiles: the sums are exact to ~1e-7
+    float n_chosen = 0.f;
     int tile = blockIdx.x;
     RowInputs<K1> cur;
     load_row<K1>(cur, A, tile * kRows + row, half);
@@ -146,6 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
         const uint32_t parity = it & 1u;
         const int grow = tile * kRows + row;
         const int o = cur.o;
+        float sum_f = 0.f, sum_s = 0.f, sum_o = 0.f;
 
         // ---- stage the layer-1 input --------------------------------------------------------------
         {
@@ -171,7 +199,19 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                               kN1, LY::kK1p, true);
             umma::umma_commit(&S.bar[0]);
         }
-        // prefetch the next tile's gathered rows while the tensor core works
+        // while the tensor core works: this row's share of the attributes to be coded (43 values per thread)
+        // and the next tile's gathered context rows travel from HBM
+        const bool chosen = o >= 0 && (A.choose ? A.choose[o] != 0 : true);
+        float xv[48], mk[10];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const ChunkDesc cd = chunk_desc(c, half);
+            const float *src = (cd.grp == 0 ? A.feat : (cd.grp == 1 ? A.scaling : A.offsets)) + (o < 0 ? 0 : o) * cd.dim + cd.k0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[8 * c + j] = (o >= 0 && j < cd.cnt) ? __ldg(src + j) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) mk[k] = (o >= 0 && half == 1 && chosen) ? __ldg(A.mask + o * 10 + k) : 1.f;
         RowInputs<K1> nxt;
         load_row<K1>(nxt, A, (tile + (int)gridDim.x) * kRows + row, half);
         if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
@@ -214,57 +254,42 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             Qs = fmaxf(kQs0 * (1.0f + tanhf(__uint_as_float(v[1]) + S.w[LY::kOffB2 + 173])), 1e-9f);
             Qo = fmaxf(kQo0 * (1.0f + tanhf(__uint_as_float(v[2]) + S.w[LY::kOffB2 + 174])), 1e-9f);
         }
-        const bool chosen = o >= 0 && (A.choose ? A.choose[o] != 0 : true);
         if (half == 0 && chosen) n_chosen += 1.f;
         const float *nz = A.noise ? A.noise + (size_t)grow * kCE : nullptr;
-
-        // one group of up to 8 consecutive coded values j0 .. j0+cnt-1 (all of the same attribute)
-        auto chunk = [&](int j0, int cnt, uint32_t mu_col, uint32_t sg_col, const float *src, float *dst, int dim,
-                         int k0, float Q, float x_mean, int grp, float &acc) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const ChunkDesc cd = chunk_desc(c, half);
             uint32_t vm[8], vs[8];
-            umma::tmem_ld8(tl + kColD2 + mu_col, vm);
-            umma::tmem_ld8(tl + kColD2 + sg_col, vs);
+            umma::tmem_ld8(tl + kColD2 + cd.mu_col, vm);
+            umma::tmem_ld8(tl + kColD2 + cd.sg_col, vs);
             umma::tmem_wait_ld();
-            if (o < 0) return;
+            if (o < 0) continue;
+            const float Q = cd.grp == 0 ? Qf : (cd.grp == 1 ? Qs : Qo);
+            const float x_mean = cd.grp == 0 ? A.feat_mean : (cd.grp == 1 ? A.scaling_mean : A.offset_mean);
+            float *dst = (cd.grp == 0 ? A.feat_q : (cd.grp == 1 ? A.scaling_q : A.offsets_q)) + o * cd.dim + cd.k0;
+            float acc = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                if (j < cnt) {
-                    const int k = k0 + j;  // index inside the attribute
-                    const float x = src[(size_t)o * dim + k];
-                    const float xq = nz ? x + nz[j0 + j] * Q : ste_round(x, Q);
-                    dst[(size_t)o * dim + k] = xq;
+                if (j < cd.cnt) {
+                    const float x = xv[8 * c + j];
+                    const float xq = nz ? x + nz[cd.j0 + j] * Q : ste_round(x, Q);
+                    dst[j] = xq;
                     float bits = 0.f;
                     if (chosen) {
-                        const float mean = __uint_as_float(vm[j]) + S.w[LY::kOffB2 + mu_col + j];
-                        const float scale = __uint_as_float(vs[j]) + S.w[LY::kOffB2 + sg_col + j];
+                        const float mean = __uint_as_float(vm[j]) + S.w[LY::kOffB2 + cd.mu_col + j];
+                        const float scale = __uint_as_float(vs[j]) + S.w[LY::kOffB2 + cd.sg_col + j];
                         bits = gaussian_bits_one(xq, mean, scale, Q, x_mean);
-                        if (grp == 2) bits *= A.mask[(size_t)o * 10 + k / 3];
+                        if (cd.grp == 2) bits *= mk[c >= 2 ? (8 * (c - 2) + j) / 3 : 0];  // grp 2 <=> half 1, c >= 2
                         acc += bits;
                     }
-                    if (A.bits_out) A.bits_out[(size_t)o * kCE + j0 + j] = bits;
+                    if (A.bits_out) A.bits_out[(size_t)o * kCE + cd.j0 + j] = bits;
                 }
             }
-        };
-        if (half == 0) {
-            // feat 0 .. 42
-#pragma unroll 1
-            for (int c = 0; c < 6; ++c) {
-                const int k0 = 8 * c, cnt = k0 + 8 <= 43 ? 8 : 43 - k0;
-                chunk(k0, cnt, (uint32_t)k0, (uint32_t)(kCF + k0), A.feat, A.feat_q, kCF, k0, Qf, A.feat_mean, 0, sum_f);
-            }
-        } else {
-            // feat 43 .. 49
-            chunk(43, 7, 43u, (uint32_t)(kCF + 43), A.feat, A.feat_q, kCF, 43, Qf, A.feat_mean, 0, sum_f);
-            // scaling 0 .. 5   (mu cols 100..105, sigma cols 106..111)
-            chunk(kCF, 6, 100u, 106u, A.scaling, A.scaling_q, kCS, 0, Qs, A.scaling_mean, 1, sum_s);
-            // offsets 0 .. 29  (mu cols 112..141, sigma cols 142..171)
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int k0 = 8 * c, cnt = k0 + 8 <= 30 ? 8 : 30 - k0;
-                chunk(kCF + kCS + k0, cnt, (uint32_t)(112 + k0), (uint32_t)(142 + k0), A.offsets, A.offsets_q, kCO, k0, Qo,
-                      A.offset_mean, 2, sum_o);
-            }
+            if (cd.grp == 0) sum_f += acc;
+            else if (cd.grp == 1) sum_s += acc;
+            else sum_o += acc;
         }
+        tot_f += (double)sum_f; tot_s += (double)sum_s; tot_o += (double)sum_o;
         // all TMEM reads of this tile are complete before the next tile's stores / MMAs reuse the columns
         umma::fence_before_thread_sync();
         __syncthreads();
@@ -275,14 +300,14 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
     // ---- per-CTA reduction of the bit sums -> one fp64 atomic per sum ----------------------------------
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        sum_f += __shfl_xor_sync(0xffffffffu, sum_f, off);
-        sum_s += __shfl_xor_sync(0xffffffffu, sum_s, off);
-        sum_o += __shfl_xor_sync(0xffffffffu, sum_o, off);
+        tot_f += __shfl_xor_sync(0xffffffffu, tot_f, off);
+        tot_s += __shfl_xor_sync(0xffffffffu, tot_s, off);
+        tot_o += __shfl_xor_sync(0xffffffffu, tot_o, off);
         n_chosen += __shfl_xor_sync(0xffffffffu, n_chosen, off);
     }
     __shared__ double s_red[4][kThreads / 32];
     if (lane == 0) {
-        s_red[0][warp] = sum_f; s_red[1][warp] = sum_s; s_red[2][warp] = sum_o; s_red[3][warp] = n_chosen;
+        s_red[0][warp] = tot_f; s_red[1][warp] = tot_s; s_red[2][warp] = tot_o; s_red[3][warp] = (double)n_chosen;
     }
     umma::fence_before_thread_sync();
     __syncthreads();

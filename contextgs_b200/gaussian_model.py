@@ -249,9 +249,12 @@ class GaussianModel(nn.Module):
         """scene/gaussian_model.py:981-1004 (without the side-effect files at :1681-1682)."""
         from .context_model import multi_scale_generating
         sel = self.get_mask_anchor
-        sums = multi_scale_generating(self, self.get_anchor[sel], self._hyper_latent[sel], self._anchor_feat[sel],
-                                      self._offset[sel], self.get_scaling[sel], binary_grid_masks=self.get_mask[sel],
-                                      predict_bpp=True, return_sum_bits=True)
+        tensors = (self.get_anchor, self._hyper_latent, self._anchor_feat, self._offset, self.get_scaling, self.get_mask)
+        if not bool(sel.all()):  # one index list for the six gathers (the reference runs six boolean-mask selects)
+            idx = torch.nonzero(sel)[:, 0]
+            tensors = tuple(t.index_select(0, idx) for t in tensors)
+        a, h, f, o, s, m = tensors
+        sums = multi_scale_generating(self, a, h, f, o, s, binary_grid_masks=m, predict_bpp=True, return_sum_bits=True)
         if return_values:
             return sums
         names = ["anchor", "hyper", "feat", "scaling", "offsets", "masks"]
