@@ -30,8 +30,8 @@ def _check_against(out, ref_mask, ref, pre_opacity=None):
         pytest.skip("selection flipped at a rounding-level zero crossing; positional comparison skipped")
     for name, t in zip(("xyz", "color", "opacity", "scaling", "rot"), (xyz, color, opacity, scaling, rot)):
         assert t.shape[0] == int(ref_mask.sum())
-        assert rel_l2(t.cpu().numpy(), ref[name]) < REL_L2, name
-    assert rel_l2(neural_opacity.cpu().numpy(), ref["neural_opacity"]) < REL_L2
+        assert rel_l2(t.detach().cpu().numpy(), ref[name]) < REL_L2, name
+    assert rel_l2(neural_opacity.detach().cpu().numpy(), ref["neural_opacity"]) < REL_L2
 
 
 @pytest.mark.parametrize("n", [0, 1, 7, 8, 2047, 2048, 2049, 100003])
@@ -59,7 +59,7 @@ def test_matches_reference_golden():
     model.eval()
     model.decoded_version = False  # non-decoded eval path also runs the context model; decoded path below
     xyz = generate_neural_gaussians(cam, model, vis, is_training=True, step=0)[0]
-    assert rel_l2(xyz.cpu().numpy(), g["eval_xyz"]) < REL_L2
+    assert rel_l2(xyz.detach().cpu().numpy(), g["eval_xyz"]) < REL_L2
 
 
 def test_matches_oracle_config1_size():
