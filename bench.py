@@ -214,6 +214,7 @@ def run_reference(args, rank, world):
         return
     from contextgs_b200.gaussian_model import GaussianModel  # parameter container only (CPU tensors, no kernels)
     cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1; the oracle is loaded below
     torch.set_num_threads(cores)
     scene, dec, cams = make_inputs(args.anchors)
     m_cpu = make_model(scene, "cpu")
@@ -479,6 +480,7 @@ def extras(args, pc, pc_train, cams_dev, my_cam, pipe, bg, timed, world, dev):
 def cpu_baseline(args, scene, dec, cams_cpu):
     from contextgs_b200.gaussian_model import GaussianModel  # noqa: F401  (parameter container on the CPU)
     cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     torch.set_num_threads(cores)
     m_cpu = make_model(scene, "cpu")
     pc = oracle_model(scene, dec, m_cpu)

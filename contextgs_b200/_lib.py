@@ -83,6 +83,9 @@ SIGNATURES = {
                                            _PTR, _PTR, _PTR, _PTR]),
     "cgs_ste_multistep": (c_int, [_PTR, _PTR, c_int64, c_int, _PTR, _PTR]),
     "cgs_quantize_anchor": (c_int, [_PTR, _PTR, _PTR, c_int64, _PTR, _PTR, _PTR]),
+    "cgs_unique_voxels_workspace_bytes": (c_size_t, [c_int]),
+    "cgs_unique_voxels": (c_int, [_PTR, _PTR, c_int, ctypes.c_float, ctypes.c_float, _PTR, _PTR, _PTR, _PTR, c_size_t,
+                                  _PTR]),
     "cgs_sort_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "cgs_sort_pairs_u32": (c_int, [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, c_int64, c_int, c_int, _PTR, c_size_t,
                                    _PTR]),

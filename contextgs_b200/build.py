@@ -38,6 +38,7 @@ SOURCES = {
     "neural_gaussians_bwd.cu": [],
     "context_model_bwd.cu": [],
     "context_model_umma.cu": ["-fmad=false"],
+    "level_divide.cu": ["-fmad=false"],
 }
 
 

@@ -79,12 +79,33 @@ def ctx_impl():
 
 # ----------------------------------------------------------------------------- level division (E1-E3)
 
-def _unique_rows_first_index(rows):
-    """utils/multi_level.py:3-31 semantics on the device: sorted unique rows, inverse, min source index."""
-    uniq, inverse = torch.unique(rows, return_inverse=True, dim=0)
-    first = torch.full((uniq.shape[0],), rows.shape[0], dtype=torch.long, device=rows.device)
-    first.scatter_reduce_(0, inverse, torch.arange(rows.shape[0], device=rows.device), reduce="amin")
-    return uniq, inverse, first
+def unique_voxels(points, voxel_size, scale, keep=None):
+    """rows = round(points / voxel_size / scale) -> (count, inverse[n] int64, first[count] int64) with the
+    semantics of utils/multi_level.py:3-31 (sorted unique rows, minimum source index).  CUDA tensors go
+    through cgs_unique_voxels (own radix sort + chained scan, no host sync besides reading `count`);
+    CPU tensors (host-logic tests only) use the same torch calls as the reference."""
+    n = points.shape[0]
+    if not points.is_cuda:
+        rows = torch.round((points if keep is None else points * keep.unsqueeze(1)) / voxel_size / scale)
+        uniq, inverse = torch.unique(rows, return_inverse=True, dim=0)
+        first = torch.full((uniq.shape[0],), n, dtype=torch.long)
+        first.scatter_reduce_(0, inverse, torch.arange(n), reduce="amin")
+        return uniq.shape[0], inverse, first
+    L = _lib.lib()
+    dev = points.device
+    pts = points.detach().contiguous().float()
+    inverse = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    first = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    status = torch.empty(2, dtype=torch.int32, device=dev)
+    ws = torch.empty(L.cgs_unique_voxels_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    k = None if keep is None else keep.contiguous().view(torch.uint8)
+    _lib.check(L.cgs_unique_voxels(_lib.ptr(pts), _lib.ptr(k), n, float(voxel_size), float(scale), _lib.ptr(inverse),
+                                   _lib.ptr(first), _lib.ptr(status), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+               "cgs_unique_voxels")
+    count, overflow = status.tolist()
+    if overflow:
+        raise _lib.CgsError("cgs_unique_voxels: |round(anchor / voxel / scale)| exceeds 2^20")
+    return count, inverse[:n].long(), first[:count].long()
 
 
 def find_divide_scale(pc, anchor, target_ratio, level_num):
@@ -95,15 +116,18 @@ def find_divide_scale(pc, anchor, target_ratio, level_num):
         hi, lo = upper0, lower
         while True:
             scale = (hi + lo) / 2
-            uniq = torch.unique(torch.round(cur / pc.voxel_size / scale), dim=0) * pc.voxel_size * scale
-            ratio = uniq.shape[0] / cur.shape[0]
+            count, _, first = unique_voxels(cur, pc.voxel_size, scale)
+            ratio = count / cur.shape[0]
             if abs(ratio - target_ratio) < 0.01 or abs(hi - lo) < 1:
                 break
             if ratio < target_ratio:
                 hi = scale
             else:
                 lo = scale
-        cur, lower = uniq, scale
+        # the reference continues with the unique voxel centres; their rows at any coarser scale are
+        # what matters for the next search
+        cur = torch.round(cur[first] / pc.voxel_size / scale) * pc.voxel_size * scale
+        lower = scale
         scales.append(float(scale))
     return scales
 
@@ -113,9 +137,10 @@ def divide_levels(pc, anchor, mask_anchor_bool=None):
     level_anchor, inverse, first = [anchor], [], []
     cur = anchor
     for i in range(1, pc.level_num):
-        if i == 1 and mask_anchor_bool is not None:
-            cur = cur * mask_anchor_bool.unsqueeze(1)
-        _, inv, fst = _unique_rows_first_index(torch.round(cur / pc.voxel_size / pc.level_scale[i - 1]))
+        keep = mask_anchor_bool if (i == 1 and mask_anchor_bool is not None) else None
+        _, inv, fst = unique_voxels(cur, pc.voxel_size, pc.level_scale[i - 1], keep)
+        if keep is not None:
+            cur = cur * keep.unsqueeze(1)
         cur = cur[fst]
         level_anchor.append(cur)
         inverse.append(inv)

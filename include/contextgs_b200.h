@@ -285,6 +285,18 @@ CGS_API int cgs_ste_multistep(const float *x, const float *Q, int64_t n, int D, 
 CGS_API int cgs_quantize_anchor(const float *anchors, const float *min_host, const float *max_host, int64_t n,
                                 float *anchors_q, float *quantized_v, void *stream);
 
+/* Level division of the anchor set: rows = round(points / voxel_size / level_scale)
+ * (scene/gaussian_model.py:1760; points of anchors with keep[i] == 0 are first multiplied by 0, :1758-1759),
+ * then what `torch_unique_with_indices` returns (utils/multi_level.py:3-31) for those rows:
+ *   inverse[n]  : index of each point's row among the lexicographically SORTED unique rows,
+ *   first[count]: minimum source index of every unique row   (capacity n),
+ *   status_dev[0] = count, status_dev[1] = 1 if a rounded coordinate left the supported +-2^20 range.
+ * keep may be NULL.  No host synchronisation; the library's own radix sort does the ordering. */
+CGS_API size_t cgs_unique_voxels_workspace_bytes(int n);
+CGS_API int cgs_unique_voxels(const float *points, const uint8_t *keep, int n, float voxel_size, float level_scale,
+                              int32_t *inverse, int32_t *first, int32_t *status_dev, void *workspace,
+                              size_t workspace_bytes, void *stream);
+
 /* Stand-alone access to the library's own stable LSD radix sort of (uint32 key, uint32 value)
  * pairs on key bits [begin_bit, end_bit) -- exported for tests and for the level-division path.
  * n lives on the device (n_dev) and is bounded by n_cap; vals_in may be NULL (= 0..n-1).

@@ -276,3 +276,22 @@ def test_training_backward_matches_autograd_of_the_oracle(LAM, TOL):
         for ours, theirs in zip(list(model.latent_codec.matrices) + list(model.latent_codec.biases) +
                                 list(model.latent_codec.factors), eb.matrices + eb.biases + eb.factors):
             assert rel_l2(ours.grad.cpu().numpy(), theirs.grad.numpy()) < TOL, "entropy bottleneck"
+
+
+@pytest.mark.parametrize("n,scale", [(1, 2.0), (7, 1.5), (2048, 3.0), (2049, 1.0), (300_001, 7.3)])
+def test_unique_voxels_matches_torch_unique(n, scale):
+    """cgs_unique_voxels (own radix sort + chained scan) vs the reference's torch.unique(dim=0) +
+    scatter-min (utils/multi_level.py:3-31), incl. the mask-to-origin rule of divide_levels."""
+    from contextgs_b200.context_model import unique_voxels
+    g = torch.Generator().manual_seed(n)
+    pts = (torch.randn(n, 3, generator=g) * 0.05).round(decimals=3)      # many duplicates, both signs
+    keep = torch.rand(n, generator=g) < 0.8
+    voxel = 0.001
+    for k in (None, keep):
+        rows = torch.round((pts if k is None else pts * k.unsqueeze(1)) / voxel / scale)
+        uniq, inv = torch.unique(rows, return_inverse=True, dim=0)
+        first = torch.full((uniq.shape[0],), n, dtype=torch.long)
+        first.scatter_reduce_(0, inv, torch.arange(n), reduce="amin")
+        cnt, inv_c, first_c = unique_voxels(pts.cuda(), voxel, scale, None if k is None else k.cuda())
+        assert cnt == uniq.shape[0]
+        assert torch.equal(inv_c.cpu(), inv) and torch.equal(first_c.cpu(), first)
