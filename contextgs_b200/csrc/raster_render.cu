@@ -58,6 +58,15 @@ __device__ __forceinline__ bool rect_may_contribute(float gx, float gy, float A2
     return best >= thr2 - (0.02f + 2.0e-5f * mag);  // margin covers the fp32 rounding of both sides
 }
 
+// 2^x for x <= 0 with flush-to-zero: one MUFU.EX2 (exp2f adds a denormal-range fix-up of 3 instructions;
+// alphas that small are far below the 1/255 threshold anyway)
+__device__ __forceinline__ float fast_exp2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct StagedRecord {
     float4 a;  // x y A2 B2
     float4 b;  // C2 thr2 opacity r
@@ -83,12 +92,18 @@ __device__ __forceinline__ StagedRecord stage_record(const float4 g0, const floa
             mask = 0xffu;  // degenerate conic: let the per-pixel test decide
         } else if (rect_may_contribute(g0.x, g0.y, A2, B2, C2, thr2, (float)tx0, (float)ty0,
                                        (float)min(tx0 + kTile - 1, W - 1), (float)min(ty0 + kTile - 1, H - 1))) {
+            // axis-aligned box of the ellipse {p2 >= thr2} (inflated): most warp blocks are rejected by
+            // four comparisons, the exact edge test only runs for blocks that overlap the box
+            const float det = A2 * C2 - 0.25f * B2 * B2;                 // > 0
+            const float t = fminf(thr2, 0.0f) - 0.05f;                    // < 0
+            const float hx = sqrtf(t * C2 / det) * 1.01f + 0.01f, hy = sqrtf(t * A2 / det) * 1.01f + 0.01f;
+            const float x_lo = g0.x - hx, x_hi = g0.x + hx, y_lo = g0.y - hy, y_hi = g0.y + hy;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) {
                 const int bx = tx0 + (w & 1) * kBlockW, by = ty0 + (w >> 1) * kBlockH;
-                if (bx < W && by < H &&
-                    rect_may_contribute(g0.x, g0.y, A2, B2, C2, thr2, (float)bx, (float)by,
-                                        (float)min(bx + kBlockW - 1, W - 1), (float)min(by + kBlockH - 1, H - 1)))
+                const float bx1 = (float)min(bx + kBlockW - 1, W - 1), by1 = (float)min(by + kBlockH - 1, H - 1);
+                if (bx < W && by < H && x_hi >= (float)bx && x_lo <= bx1 && y_hi >= (float)by && y_lo <= by1 &&
+                    rect_may_contribute(g0.x, g0.y, A2, B2, C2, thr2, (float)bx, (float)by, bx1, by1))
                     mask |= 1u << w;
             }
         }
@@ -184,26 +199,26 @@ render_forward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__res
         const uint8_t *list = s_list[warp];
         const uint32_t pos_base = (uint32_t)(r * kBatch + 1);
         for (int j = 0; j < n; ++j) {
-            if (done) continue;
             const int idx = list[j];
             const float4 a = ra[idx];   // x y A2 B2
             const float4 b = rbv[idx];  // C2 thr2 op r
             const float dx = a.x - fx, dy = a.y - fy;
             const float p2 = dx * (a.z * dx + a.w * dy) + b.x * (dy * dy);
-            if (!(p2 >= b.y) || p2 > 0.0f) continue;   // alpha < 1/255, or the reference's `power > 0` guard
-            const float alpha = fminf(kAlphaMax, b.z * exp2f(p2));
+            // skip: alpha < 1/255, the reference's `power > 0` guard, or a pixel that has saturated
+            if (!(p2 >= b.y) || p2 > 0.0f || done) continue;
+            const float alpha = fminf(kAlphaMax, b.z * fast_exp2(p2));
             const float test_T = T * (1.0f - alpha);
             if (test_T < kTEps) {
                 done = true;
-                continue;
+            } else {
+                const float2 c = rc[idx];
+                const float w = alpha * T;
+                C0 += b.w * w;
+                C1 += c.x * w;
+                C2 += c.y * w;
+                T = test_T;
+                last_contributor = pos_base + (uint32_t)idx;
             }
-            const float2 c = rc[idx];
-            const float w = alpha * T;
-            C0 += b.w * w;
-            C1 += c.x * w;
-            C2 += c.y * w;
-            T = test_T;
-            last_contributor = pos_base + (uint32_t)idx;
         }
     }
 
@@ -365,7 +380,7 @@ render_backward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__re
                 if (p2 >= b.y && !(p2 > 0.0f)) {
                     active = true;
                     const float2 c = rc[idx];
-                    const float G = exp2f(p2);
+                    const float G = fast_exp2(p2);
                     const float alpha = fminf(kAlphaMax, b.z * G);
                     const float ca = a.z * (-2.0f * kLn2), cb = a.w * (-kLn2), cc = b.x * (-2.0f * kLn2);
                     T = T / (1.0f - alpha);
