@@ -376,8 +376,15 @@ def main():
     top_ms = per_frame[top] / launches_per_frame_top
     algo = ALGO_BYTES.get(top, lambda c: 0)(counts) / launches_per_frame_top
     achieved = algo / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch (committed)
+        with open(tpath) as f:
+            t = json.load(f).get(top)
+        if t:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo, "ms_per_launch": top_ms,
                 "note": "render_fwd/bwd are FP32/SFU-issue bound per (pixel, instance), not HBM bound (SURVEY 8a R6); "
                         "HBM fraction reported as the contract requires"}
