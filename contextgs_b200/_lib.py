@@ -30,6 +30,7 @@ class RasterSettings(ctypes.Structure):
 
 
 STATUS_NUM_RENDERED, STATUS_OVERFLOW, STATUS_NUM_SORTED, STATUS_WORDS = 0, 1, 2, 8
+STATUS_NUM_GAUSSIANS, STATUS_GAUSSIAN_OVERFLOW = 3, 4
 GEOM_STRIDE = 12
 
 # name -> (restype, argtypes); every symbol declared in include/contextgs_b200.h
@@ -48,6 +49,8 @@ SIGNATURES = {
     "cgs_raster_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int]),
     "cgs_rasterize_forward": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, c_int64, _PTR, _PTR, _PTR, _PTR, _PTR,
                                       _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
+    "cgs_rasterize_forward_dev": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, c_int64, _PTR, _PTR, _PTR, _PTR,
+                                          _PTR, _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
     "cgs_raster_backward_workspace_bytes": (c_size_t, [c_int]),
     "cgs_rasterize_backward": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
                                        _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
@@ -62,6 +65,10 @@ SIGNATURES = {
     "cgs_neural_gaussians_backward_packed_floats": (c_int, []),
     "cgs_neural_gaussians_backward_workspace_bytes": (c_size_t, [c_int]),
     "cgs_neural_gaussians_backward": (c_int, [_PTR, _PTR, _PTR, c_int] + [_PTR] * 19 + [c_size_t, _PTR]),
+    "cgs_neural_gaussians_umma_forward_dev": (c_int, [_PTR, _PTR, c_int, _PTR, c_int64, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
+                                                      _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, c_size_t,
+                                                      _PTR]),
+    "cgs_compact_positive_i32": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, c_size_t, _PTR]),
     "cgs_compact_workspace_bytes": (c_size_t, [c_int]),
     "cgs_compact_indices": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, c_size_t, _PTR]),
     "cgs_eb_param_floats": (c_int, []),

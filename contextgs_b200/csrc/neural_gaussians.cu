@@ -200,8 +200,10 @@ neural_gaussians_forward_kernel(const float *__restrict__ packed_w, const int *_
 // Ordered stream compaction of a boolean mask into an index list (decoupled look-back scan).
 constexpr int kCompactItems = 8, kCompactThreads = 256, kCompactTile = kCompactItems * kCompactThreads;
 
+// MaskT = uint8_t: select mask[i] != 0;  MaskT = int32_t: select mask[i] > 0 (screen radii of visible_filter)
+template <typename MaskT>
 __global__ void __launch_bounds__(kCompactThreads)
-compact_indices_kernel(const uint8_t *__restrict__ mask, int N, int *__restrict__ out_idx,
+compact_indices_kernel(const MaskT *__restrict__ mask, int N, int *__restrict__ out_idx,
                        unsigned long long *scan_state, uint32_t *ticket, int32_t *__restrict__ count_out)
 {
     __shared__ uint32_t s_tile, s_warp[kCompactThreads / 32], s_base;
@@ -211,7 +213,18 @@ compact_indices_kernel(const uint8_t *__restrict__ mask, int N, int *__restrict_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int base_i = tile * kCompactTile + threadIdx.x * kCompactItems;
     uint32_t bits = 0;
-    if (base_i + kCompactItems <= N) {
+    if (sizeof(MaskT) == 4) {
+        if (base_i + kCompactItems <= N) {
+            const int4 v0 = *reinterpret_cast<const int4 *>(mask + base_i);
+            const int4 v1 = *reinterpret_cast<const int4 *>(mask + base_i + 4);
+            const int v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bits |= v[i] > 0 ? (1u << i) : 0u;
+        } else {
+            for (int i = 0; i < kCompactItems; ++i)
+                if (base_i + i < N && (int)mask[base_i + i] > 0) bits |= 1u << i;
+        }
+    } else if (base_i + kCompactItems <= N) {
         const uint2 v = *reinterpret_cast<const uint2 *>(mask + base_i);  // 8 mask bytes
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -344,8 +357,38 @@ extern "C" int cgs_compact_indices(const uint8_t *mask, int N, int32_t *out_idx,
     char *ws = static_cast<char *>(workspace);
     cudaMemsetAsync(ws, 0, cgs_compact_workspace_bytes(N), st);
     StageScope sc(ST_COMPACT, st, 1);
-    compact_indices_kernel<<<tiles, kCompactThreads, 0, st>>>(
+    compact_indices_kernel<uint8_t><<<tiles, kCompactThreads, 0, st>>>(
         mask, N, out_idx, reinterpret_cast<unsigned long long *>(ws),
+        reinterpret_cast<uint32_t *>(ws + align_up((size_t)tiles * 8)), count_dev);
+    return check_launch(__func__);
+}
+
+extern "C" int cgs_compact_positive_i32(const int32_t *values, int N, int32_t *out_idx, int32_t *count_dev,
+                                        void *workspace, size_t workspace_bytes, void *stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CGS_CHECK_PTR(count_dev);
+    if (N <= 0) {
+        cudaMemsetAsync(count_dev, 0, sizeof(int32_t), st);
+        return check_launch(__func__);
+    }
+    CGS_CHECK_PTR(values);
+    CGS_CHECK_PTR(out_idx);
+    CGS_CHECK_PTR(workspace);
+    if (reinterpret_cast<uintptr_t>(values) & 15) {
+        set_error("%s: values must be 16-byte aligned", __func__);
+        return -2;
+    }
+    if (workspace_bytes < cgs_compact_workspace_bytes(N)) {
+        set_error("%s: workspace too small", __func__);
+        return -3;
+    }
+    const int tiles = (N + kCompactTile - 1) / kCompactTile;
+    char *ws = static_cast<char *>(workspace);
+    cudaMemsetAsync(ws, 0, cgs_compact_workspace_bytes(N), st);
+    StageScope sc(ST_COMPACT, st, 1);
+    compact_indices_kernel<int32_t><<<tiles, kCompactThreads, 0, st>>>(
+        values, N, out_idx, reinterpret_cast<unsigned long long *>(ws),
         reinterpret_cast<uint32_t *>(ws + align_up((size_t)tiles * 8)), count_dev);
     return check_launch(__func__);
 }

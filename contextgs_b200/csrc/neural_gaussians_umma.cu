@@ -140,8 +140,8 @@ __device__ __forceinline__ float fast_tanh(float x)
 }  // namespace ngu
 
 __global__ void __launch_bounds__(ngu::kThreads, 1)
-neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__restrict__ vis_idx, int Nv,
-                             const float *__restrict__ anchor, const float *__restrict__ feat,
+neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__restrict__ vis_idx, int Nv_cap,
+                             const int *__restrict__ nv_dev, uint32_t out_cap, const float *__restrict__ anchor, const float *__restrict__ feat,
                              const float *__restrict__ offsets, const float *__restrict__ scaling,
                              const float *__restrict__ mask, float cx, float cy, float cz,
                              float *__restrict__ o_xyz, float *__restrict__ o_color, float *__restrict__ o_opacity,
@@ -155,7 +155,13 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = warp >> 2;
     const int row = 32 * (warp & 3) + lane;
+    // the number of visible anchors may live on the device (no host read-back between the stages)
+    const int Nv = nv_dev ? min(max(__ldg(nv_dev), 0), Nv_cap) : Nv_cap;
     const int num_tiles = (Nv + kRows - 1) / kRows;
+    if (num_tiles == 0) {
+        if (blockIdx.x == 0 && tid == 0) *count_out = 0;
+        return;
+    }
 
     if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
     if (tid == 0) {
@@ -354,8 +360,9 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
 
         // ---- coalesced copy-out ----------------------------------------------------------------------
         {
-            const uint32_t n = S.tile_total;
             const size_t base = S.tile_base;
+            // Gaussians beyond the output capacity are dropped (count_out still reports the true total)
+            const uint32_t n = base >= out_cap ? 0u : min(S.tile_total, (uint32_t)(out_cap - base));
             for (uint32_t i = tid; i < 3 * n; i += kThreads) {
                 o_xyz[3 * base + i] = S.o_xyz[i];
                 o_color[3 * base + i] = S.o_color[i];
@@ -365,11 +372,13 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                 o_opacity[base + i] = S.o_opacity[i];
                 reinterpret_cast<float4 *>(o_rot)[base + i] = S.o_rot[i];
             }
-            const int valid = min(kRows, Nv - tile * kRows) * kK;
-            const size_t gp0 = (size_t)tile * kTileGauss;
-            for (int i = tid; i < valid; i += kThreads) {
-                o_neural_opacity[gp0 + i] = S.o_nop[i];
-                o_mask[gp0 + i] = S.o_keep[i];
+            if (o_neural_opacity) {   // training-side outputs (gaussian_renderer/__init__.py:147-148); NULL at inference
+                const int valid = min(kRows, Nv - tile * kRows) * kK;
+                const size_t gp0 = (size_t)tile * kTileGauss;
+                for (int i = tid; i < valid; i += kThreads) {
+                    o_neural_opacity[gp0 + i] = S.o_nop[i];
+                    o_mask[gp0 + i] = S.o_keep[i];
+                }
             }
         }
         __syncthreads();  // staging buffers are free again
@@ -410,6 +419,24 @@ extern "C" int cgs_neural_gaussians_umma_forward(const float *packed_weights, co
                                                  int32_t *count_dev, void *workspace, size_t workspace_bytes,
                                                  void *stream)
 {
+    if (Nv > 0) {
+        CGS_CHECK_PTR(o_neural_opacity);
+        CGS_CHECK_PTR(o_mask);
+    }
+    return cgs_neural_gaussians_umma_forward_dev(packed_weights, vis_idx, Nv, nullptr, (int64_t)Nv * ngu::kK, anchor, feat,
+                                                 offsets, scaling, mask, campos_host, o_xyz, o_color, o_opacity, o_scaling,
+                                                 o_rot, o_neural_opacity, o_mask, count_dev, workspace, workspace_bytes,
+                                                 stream);
+}
+
+extern "C" int cgs_neural_gaussians_umma_forward_dev(const float *packed_weights, const int32_t *vis_idx, int Nv,
+                                                     const int32_t *nv_dev, int64_t out_cap, const float *anchor,
+                                                     const float *feat, const float *offsets, const float *scaling,
+                                                     const float *mask, const float *campos_host, float *o_xyz,
+                                                     float *o_color, float *o_opacity, float *o_scaling, float *o_rot,
+                                                     float *o_neural_opacity, uint8_t *o_mask, int32_t *count_dev,
+                                                     void *workspace, size_t workspace_bytes, void *stream)
+{
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CGS_CHECK_PTR(count_dev);
     if (Nv <= 0) {
@@ -428,9 +455,15 @@ extern "C" int cgs_neural_gaussians_umma_forward(const float *packed_weights, co
     CGS_CHECK_PTR(o_opacity);
     CGS_CHECK_PTR(o_scaling);
     CGS_CHECK_PTR(o_rot);
-    CGS_CHECK_PTR(o_neural_opacity);
-    CGS_CHECK_PTR(o_mask);
     CGS_CHECK_PTR(workspace);
+    if ((o_neural_opacity == nullptr) != (o_mask == nullptr)) {
+        set_error("%s: o_neural_opacity and o_mask must both be given or both be NULL", __func__);
+        return -2;
+    }
+    if (out_cap < 0 || out_cap > 0x7fffffffll) {
+        set_error("%s: invalid output capacity", __func__);
+        return -2;
+    }
     if (workspace_bytes < cgs_neural_gaussians_umma_workspace_bytes(Nv)) {
         set_error("%s: workspace too small", __func__);
         return -3;
@@ -452,8 +485,8 @@ extern "C" int cgs_neural_gaussians_umma_forward(const float *packed_weights, co
     const int grid = tiles < sm_count ? tiles : sm_count;
     StageScope sc(ST_G1_FWD, st, 1);
     neural_gaussians_umma_kernel<<<grid, ngu::kThreads, sizeof(ngu::Smem), st>>>(
-        packed_weights, vis_idx, Nv, anchor, feat, offsets, scaling, mask, campos_host[0], campos_host[1],
-        campos_host[2], o_xyz, o_color, o_opacity, o_scaling, o_rot, o_neural_opacity, o_mask, scan_state, ctrl,
-        count_dev);
+        packed_weights, vis_idx, Nv, nv_dev, (uint32_t)out_cap, anchor, feat, offsets, scaling, mask, campos_host[0],
+        campos_host[1], campos_host[2], o_xyz, o_color, o_opacity, o_scaling, o_rot, o_neural_opacity, o_mask, scan_state,
+        ctrl, count_dev);
     return check_launch(__func__);
 }

@@ -72,16 +72,16 @@ StageScope::~StageScope()
 }
 
 // launchers defined in the kernel translation units
-void launch_preprocess(const CamParams &, int, const float *, const float *, const float *, const float *,
-                       const float *, int32_t *, float *, uint32_t *, cudaStream_t);
+void launch_preprocess(const CamParams &, int, const uint32_t *, const float *, const float *, const float *,
+                       const float *, const float *, int32_t *, float *, uint32_t *, cudaStream_t);
 void launch_filter(const CamParams &, int, const float *, const float *, const float *, int32_t *, cudaStream_t);
 void launch_mark_visible(const CamParams &, int, const float *, uint8_t *, cudaStream_t);
 void launch_preprocess_backward(const CamParams &, int, const float *, const float *, const float *, const int32_t *,
                                 const float *, float *, float *, float *, float *, float *, float *, cudaStream_t);
-void launch_scan_tiles(const uint32_t *, const float *, int, int64_t, uint32_t *, unsigned long long *, uint32_t *,
-                       int32_t *, cudaStream_t);
-void launch_emit_instances(const uint32_t *, const float *, const uint32_t *, int, int, int, int64_t, uint32_t *,
-                           uint32_t *, cudaStream_t);
+void launch_scan_tiles(const uint32_t *, const float *, int, const uint32_t *, int64_t, uint32_t *,
+                       unsigned long long *, uint32_t *, int32_t *, cudaStream_t);
+void launch_emit_instances(const uint32_t *, const float *, const uint32_t *, int, const uint32_t *, int, int, int64_t,
+                           uint32_t *, uint32_t *, cudaStream_t);
 void launch_tile_ranges(const uint32_t *, const int32_t *, int64_t, uint32_t *, cudaStream_t);
 int scan_tiles_count(int P);
 void launch_render_forward(const CamParams &, const uint32_t *, const uint32_t *, const float *, float *, float *,
@@ -90,6 +90,15 @@ void launch_render_backward(const CamParams &, const uint32_t *, const uint32_t 
                             const uint32_t *, const float *, float *, cudaStream_t);
 
 __global__ void set_u32_kernel(uint32_t *p, uint32_t v) { *p = v; }
+// device-side Gaussian count, clamped to the capacity the buffers were sized for
+__global__ void copy_count_kernel(uint32_t *p, const int32_t *src, uint32_t cap, int32_t *status)
+{
+    const int32_t v = *src;
+    const uint32_t c = v < 0 ? 0u : (uint32_t)v;
+    *p = c < cap ? c : cap;
+    status[3] = v;                    // CGS_STATUS_NUM_GAUSSIANS
+    status[4] = c > cap ? 1 : 0;      // CGS_STATUS_GAUSSIAN_OVERFLOW
+}
 
 static int tile_bits(int tiles)
 {
@@ -256,6 +265,18 @@ extern "C" int cgs_rasterize_forward(const cgs_raster_settings *s, int P, const 
                                      uint32_t *point_list, uint32_t *ranges, float *final_T, uint32_t *n_contrib,
                                      int32_t *status, void *workspace, size_t workspace_bytes, void *stream)
 {
+    return cgs_rasterize_forward_dev(s, P, nullptr, means3D, colors, opacities, scales, rotations, R_cap, out_color, radii,
+                                     geom, point_list, ranges, final_T, n_contrib, status, workspace, workspace_bytes,
+                                     stream);
+}
+
+extern "C" int cgs_rasterize_forward_dev(const cgs_raster_settings *s, int P, const int32_t *P_dev, const float *means3D,
+                                         const float *colors, const float *opacities, const float *scales,
+                                         const float *rotations, int64_t R_cap, float *out_color, int32_t *radii,
+                                         float *geom, uint32_t *point_list, uint32_t *ranges, float *final_T,
+                                         uint32_t *n_contrib, int32_t *status, void *workspace, size_t workspace_bytes,
+                                         void *stream)
+{
     if (int e = validate_settings(s, __func__)) return e;
     CGS_CHECK_PTR(out_color);
     CGS_CHECK_PTR(ranges);
@@ -303,8 +324,9 @@ extern "C" int cgs_rasterize_forward(const cgs_raster_settings *s, int P, const 
 
         {
             StageScope sc(ST_PREPROCESS, st, 2);
-            set_u32_kernel<<<1, 1, 0, st>>>(p_dev, (uint32_t)P);
-            launch_preprocess(cam, P, means3D, colors, opacities, scales, rotations, radii, geom, dkeys_in, st);
+            if (P_dev) copy_count_kernel<<<1, 1, 0, st>>>(p_dev, P_dev, (uint32_t)P, status);
+            else set_u32_kernel<<<1, 1, 0, st>>>(p_dev, (uint32_t)P);
+            launch_preprocess(cam, P, p_dev, means3D, colors, opacities, scales, rotations, radii, geom, dkeys_in, st);
         }
         // 1. Gaussians by depth (value = Gaussian id, implicit iota on the first pass)
         {
@@ -316,13 +338,14 @@ extern "C" int cgs_rasterize_forward(const cgs_raster_settings *s, int P, const 
         // 2. instance offsets in depth order, R stays on the device
         {
             StageScope sc(ST_SCAN, st, 1);
-            launch_scan_tiles(order, geom, P, R_cap, offsets, scan_state, scan_ticket, status, st);
+            launch_scan_tiles(order, geom, P, p_dev, R_cap, offsets, scan_state, scan_ticket, status, st);
         }
         if (R_cap > 0) {
             // 3. emit (tile, id)
             {
                 StageScope sc(ST_EMIT, st, 1);
-                launch_emit_instances(order, geom, offsets, P, cam.grid_x, cam.grid_y, R_cap, tkeys_in, tvals_in, st);
+                launch_emit_instances(order, geom, offsets, P, p_dev, cam.grid_x, cam.grid_y, R_cap, tkeys_in, tvals_in,
+                                      st);
             }
             // 4. stable sort by tile id; last pass writes the ids straight into point_list
             const uint32_t *n_sorted = reinterpret_cast<const uint32_t *>(status + CGS_STATUS_NUM_SORTED);

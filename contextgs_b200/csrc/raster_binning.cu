@@ -20,16 +20,26 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 
 // Inclusive scan of tiles_touched gathered in depth order; the last tile publishes R.
 __global__ void __launch_bounds__(kScanThreads)
-scan_tiles_kernel(const uint32_t *__restrict__ order, const float *__restrict__ geom, int P, int64_t R_cap,
-                  uint32_t *__restrict__ offsets, unsigned long long *state, uint32_t *ticket,
-                  int32_t *__restrict__ status)
+scan_tiles_kernel(const uint32_t *__restrict__ order, const float *__restrict__ geom,
+                  const uint32_t *__restrict__ p_dev, int64_t R_cap, uint32_t *__restrict__ offsets,
+                  unsigned long long *state, uint32_t *ticket, int32_t *__restrict__ status)
 {
+    const int P = (int)*p_dev;  // device-side Gaussian count (the grid is sized by the host's capacity)
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_warp[kScanThreads / 32];
     __shared__ uint64_t s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (P <= 0) {  // nothing to draw: publish R = 0 once
+        if (tile == 0 && threadIdx.x == 0) {
+            status[CGS_STATUS_NUM_RENDERED] = 0;
+            status[CGS_STATUS_OVERFLOW] = 0;
+            status[CGS_STATUS_NUM_SORTED] = 0;
+        }
+        return;
+    }
+    if ((int64_t)tile * kScanTile >= (int64_t)P) return;  // tiles beyond the device-side count
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int base = tile * kScanTile + threadIdx.x * kScanItems;
     uint32_t v[kScanItems];
@@ -83,11 +93,11 @@ scan_tiles_kernel(const uint32_t *__restrict__ order, const float *__restrict__ 
 // Emit (tile id, Gaussian id) for every covered tile, y-major / x-minor, in depth order.
 __global__ void __launch_bounds__(256)
 emit_instances_kernel(const uint32_t *__restrict__ order, const float *__restrict__ geom,
-                      const uint32_t *__restrict__ offsets, int P, int grid_x, int grid_y, int64_t R_cap,
-                      uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ inst_vals)
+                      const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ p_dev, int grid_x, int grid_y,
+                      int64_t R_cap, uint32_t *__restrict__ tile_keys, uint32_t *__restrict__ inst_vals)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
+    if (i >= (int)*p_dev) return;
     const uint32_t gid = order[i];
     const float4 g0 = *reinterpret_cast<const float4 *>(geom + (size_t)gid * kGeomStride);
     const float4 g2 = *reinterpret_cast<const float4 *>(geom + (size_t)gid * kGeomStride + 8);
@@ -126,20 +136,21 @@ tile_ranges_kernel(const uint32_t *__restrict__ tile_keys, const int32_t *__rest
     }
 }
 
-void launch_scan_tiles(const uint32_t *order, const float *geom, int P, int64_t R_cap, uint32_t *offsets,
-                       unsigned long long *state, uint32_t *ticket, int32_t *status, cudaStream_t st)
+void launch_scan_tiles(const uint32_t *order, const float *geom, int P_cap, const uint32_t *p_dev, int64_t R_cap,
+                       uint32_t *offsets, unsigned long long *state, uint32_t *ticket, int32_t *status, cudaStream_t st)
 {
-    if (P <= 0) return;
-    scan_tiles_kernel<<<(P + kScanTile - 1) / kScanTile, kScanThreads, 0, st>>>(order, geom, P, R_cap, offsets, state,
-                                                                              ticket, status);
+    if (P_cap <= 0) return;
+    scan_tiles_kernel<<<(P_cap + kScanTile - 1) / kScanTile, kScanThreads, 0, st>>>(order, geom, p_dev, R_cap, offsets,
+                                                                                  state, ticket, status);
 }
 
-void launch_emit_instances(const uint32_t *order, const float *geom, const uint32_t *offsets, int P, int grid_x,
-                           int grid_y, int64_t R_cap, uint32_t *tile_keys, uint32_t *inst_vals, cudaStream_t st)
+void launch_emit_instances(const uint32_t *order, const float *geom, const uint32_t *offsets, int P_cap,
+                           const uint32_t *p_dev, int grid_x, int grid_y, int64_t R_cap, uint32_t *tile_keys,
+                           uint32_t *inst_vals, cudaStream_t st)
 {
-    if (P <= 0) return;
-    emit_instances_kernel<<<(P + 255) / 256, 256, 0, st>>>(order, geom, offsets, P, grid_x, grid_y, R_cap, tile_keys,
-                                                           inst_vals);
+    if (P_cap <= 0) return;
+    emit_instances_kernel<<<(P_cap + 255) / 256, 256, 0, st>>>(order, geom, offsets, p_dev, grid_x, grid_y, R_cap,
+                                                               tile_keys, inst_vals);
 }
 
 void launch_tile_ranges(const uint32_t *tile_keys, const int32_t *status, int64_t R_cap, uint32_t *ranges,

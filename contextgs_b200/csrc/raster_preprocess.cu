@@ -132,12 +132,12 @@ __device__ __forceinline__ int project_one(const CamParams &cam, const float3 p,
 }
 
 __global__ void __launch_bounds__(256)
-preprocess_kernel(CamParams cam, int P, const float *__restrict__ means, const float *__restrict__ colors,
+preprocess_kernel(CamParams cam, const uint32_t *__restrict__ p_dev, const float *__restrict__ means, const float *__restrict__ colors,
                   const float *__restrict__ opac, const float *__restrict__ scales, const float *__restrict__ rots,
                   int32_t *__restrict__ radii, float *__restrict__ geom, uint32_t *__restrict__ depth_keys)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
+    if (i >= (int)*p_dev) return;  // P lives on the device: the host only knows a capacity
     const float3 p = load3(means, i);
     const float3 sc = load3(scales, i);
     const float4 q = reinterpret_cast<const float4 *>(rots)[i];
@@ -309,13 +309,13 @@ preprocess_backward_kernel(CamParams cam, int P, const float *__restrict__ means
 }
 
 // ---- launchers used by raster_api.cu ---------------------------------------------------
-void launch_preprocess(const CamParams &cam, int P, const float *means, const float *colors, const float *opac,
-                       const float *scales, const float *rots, int32_t *radii, float *geom, uint32_t *depth_keys,
-                       cudaStream_t st)
+void launch_preprocess(const CamParams &cam, int P_cap, const uint32_t *p_dev, const float *means, const float *colors,
+                       const float *opac, const float *scales, const float *rots, int32_t *radii, float *geom,
+                       uint32_t *depth_keys, cudaStream_t st)
 {
-    if (P <= 0) return;
-    preprocess_kernel<<<(P + 255) / 256, 256, 0, st>>>(cam, P, means, colors, opac, scales, rots, radii, geom,
-                                                       depth_keys);
+    if (P_cap <= 0) return;
+    preprocess_kernel<<<(P_cap + 255) / 256, 256, 0, st>>>(cam, p_dev, means, colors, opac, scales, rots, radii, geom,
+                                                           depth_keys);
 }
 
 void launch_filter(const CamParams &cam, int N, const float *means, const float *scales, const float *rots,

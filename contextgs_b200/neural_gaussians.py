@@ -125,14 +125,33 @@ def compact_indices(mask):
 
 
 def generate_raw(pc, camera_center, anchor, feat, grid_offsets, grid_scaling, binary_grid_masks, vis_idx=None,
-                 n_vis=None, impl=None):
+                 n_vis=None, impl=None, nv_dev=None, out_cap=None):
     """Launch the fused kernel.  Inputs are the FULL per-anchor arrays plus an optional visible-index
-    list; returns capacity-sized outputs and the device-side Gaussian count."""
+    list; returns capacity-sized outputs and the device-side Gaussian count.
+    nv_dev / out_cap (tcgen05 kernel only): the visible-anchor count stays on the device (n_vis is then the
+    capacity of vis_idx), at most out_cap Gaussians are written and the training-side outputs are skipped."""
     L = _lib.lib()
     dev = anchor.device
     Nv = int(anchor.shape[0] if vis_idx is None else (n_vis if n_vis is not None else vis_idx.shape[0]))
-    cap = max(Nv * pc.n_offsets, 1)
     f32 = torch.float32
+    if nv_dev is not None:
+        cap = max(int(out_cap), 1)
+        out = dict(
+            xyz=torch.empty((cap, 3), dtype=f32, device=dev), color=torch.empty((cap, 3), dtype=f32, device=dev),
+            opacity=torch.empty((cap, 1), dtype=f32, device=dev), scaling=torch.empty((cap, 3), dtype=f32, device=dev),
+            rot=torch.empty((cap, 4), dtype=f32, device=dev), count=torch.empty((1,), dtype=torch.int32, device=dev))
+        ws = torch.empty((L.cgs_neural_gaussians_umma_workspace_bytes(Nv),), dtype=torch.uint8, device=dev)
+        from .rasterizer import _host_floats
+        campos = (ctypes.c_float * 3)(*_host_floats(camera_center, 3))
+        _lib.check(L.cgs_neural_gaussians_umma_forward_dev(
+            _lib.ptr(pack_decoder_weights_umma(pc)), _lib.ptr(vis_idx), Nv, _lib.ptr(nv_dev), cap,
+            _lib.ptr(anchor.contiguous()), _lib.ptr(feat.contiguous()), _lib.ptr(grid_offsets.contiguous()),
+            _lib.ptr(grid_scaling.contiguous()), _lib.ptr(binary_grid_masks.contiguous()), campos, _lib.ptr(out["xyz"]),
+            _lib.ptr(out["color"]), _lib.ptr(out["opacity"]), _lib.ptr(out["scaling"]), _lib.ptr(out["rot"]), None, None,
+            _lib.ptr(out["count"]), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "cgs_neural_gaussians_umma_forward_dev")
+        out["n_vis"] = Nv
+        return out
+    cap = max(Nv * pc.n_offsets, 1)
     out = dict(
         xyz=torch.empty((cap, 3), dtype=f32, device=dev), color=torch.empty((cap, 3), dtype=f32, device=dev),
         opacity=torch.empty((cap, 1), dtype=f32, device=dev), scaling=torch.empty((cap, 3), dtype=f32, device=dev),
@@ -260,18 +279,12 @@ def neural_gaussians(pc, camera_center, anchor, feat, grid_offsets, grid_scaling
     return xyz, color, opacity, scaling, rot, nop, keep.bool()
 
 
-def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False, step=0):
-    """Same signature and return tuples as gaussian_renderer/__init__.py:25-150.  Differentiable
-    w.r.t. the per-anchor parameters and the decoder MLPs through `_NeuralGaussians` (autograd is
-    recorded whenever torch.is_grad_enabled()); for step > 10000 the context model is differentiable
-    too (`context_model._ContextModelTrain`), so `loss.backward()` of train.py:199-211 reaches every
-    parameter the reference trains."""
+def select_attributes(pc, is_training, step):
+    """The per-anchor attributes `generate_neural_gaussians` feeds to the decoder MLPs, by training stage
+    (gaussian_renderer/__init__.py:31-104) -> (anchor, feat, offsets, scaling, masks, bit outputs ...)."""
     from .context_model import multi_scale_generating
     anchor_all = pc.get_anchor
-    N = anchor_all.shape[0]
-    if visible_mask is None:
-        visible_mask = torch.ones(N, dtype=torch.bool, device=anchor_all.device)
-    bit_per_param = bit_per_feat_param = bit_per_scaling_param = bit_per_offsets_param = bpp_per_level = None
+    bits = (None, None, None, None, None)
     feat, grid_offsets, grid_scaling = pc._anchor_feat, pc._offset, pc.get_scaling
     binary_grid_masks = pc.get_mask
     if is_training:
@@ -283,8 +296,7 @@ def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_traini
             pc.update_anchor_bound()
         if step > 10000:
             mask_anchor_bool = pc.get_mask_anchor.to(torch.bool)
-            (feat, grid_scaling, grid_offsets, bit_per_param, bit_per_feat_param, bit_per_scaling_param,
-             bit_per_offsets_param, bpp_per_level) = multi_scale_generating(
+            feat, grid_scaling, grid_offsets, *bits = multi_scale_generating(
                 pc, anchor_all, pc._hyper_latent, feat, grid_offsets, grid_scaling, binary_grid_masks,
                 mask_anchor_bool, predict_bpp=True, training=True)
     elif not pc.decoded_version:
@@ -292,6 +304,20 @@ def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_traini
         feat, grid_scaling, grid_offsets = multi_scale_generating(
             pc, anchor_all, pc._hyper_latent, feat, grid_offsets, grid_scaling, binary_grid_masks, mask_anchor_bool,
             predict_bpp=False, training=False)
+    return anchor_all, feat, grid_offsets, grid_scaling, binary_grid_masks, tuple(bits)
+
+
+def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False, step=0):
+    """Same signature and return tuples as gaussian_renderer/__init__.py:25-150.  Differentiable
+    w.r.t. the per-anchor parameters and the decoder MLPs through `_NeuralGaussians` (autograd is
+    recorded whenever torch.is_grad_enabled()); for step > 10000 the context model is differentiable
+    too (`context_model._ContextModelTrain`), so `loss.backward()` of train.py:199-211 reaches every
+    parameter the reference trains."""
+    anchor_all, feat, grid_offsets, grid_scaling, binary_grid_masks, bits = select_attributes(pc, is_training, step)
+    bit_per_param, bit_per_feat_param, bit_per_scaling_param, bit_per_offsets_param, bpp_per_level = bits
+    N = anchor_all.shape[0]
+    if visible_mask is None:
+        visible_mask = torch.ones(N, dtype=torch.bool, device=anchor_all.device)
 
     with torch.no_grad():
         vis_idx, cnt = compact_indices(visible_mask)

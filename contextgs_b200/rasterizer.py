@@ -105,11 +105,16 @@ def _f32c(t, name):
     return t.contiguous()
 
 
-def rasterize_forward_raw(c_settings, means3D, colors, opacities, scales, rotations, r_cap=None, sync=None):
-    """Enqueue the full forward.  Returns (color, radii, saved-state dict)."""
+def rasterize_forward_raw(c_settings, means3D, colors, opacities, scales, rotations, r_cap=None, sync=None,
+                          count_dev=None):
+    """Enqueue the full forward.  Returns (color, radii, saved-state dict).
+    count_dev (optional int32 device scalar): the number of valid Gaussians; the tensors then only give
+    the CAPACITY and nothing is read back here (sync is forced off; the caller inspects saved['status'])."""
     L = _lib.lib()
     dev = means3D.device
     P = int(means3D.shape[0])
+    if count_dev is not None:
+        sync = False
     H, W = c_settings.image_height, c_settings.image_width
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     st = _state(dev)
@@ -131,11 +136,11 @@ def rasterize_forward_raw(c_settings, means3D, colors, opacities, scales, rotati
         if st.workspace is None or st.workspace.numel() < need:
             st.workspace = None
             st.workspace = torch.empty((int(need * 1.25) + 1024,), dtype=torch.uint8, device=dev)
-        _lib.check(L.cgs_rasterize_forward(
-            _lib.ctypes.byref(c_settings), P, _lib.ptr(means3D), _lib.ptr(colors), _lib.ptr(opacities),
+        _lib.check(L.cgs_rasterize_forward_dev(
+            _lib.ctypes.byref(c_settings), P, _lib.ptr(count_dev), _lib.ptr(means3D), _lib.ptr(colors), _lib.ptr(opacities),
             _lib.ptr(scales), _lib.ptr(rotations), r_cap, _lib.ptr(color), _lib.ptr(radii), _lib.ptr(geom),
             _lib.ptr(point_list), _lib.ptr(ranges), _lib.ptr(final_T), _lib.ptr(n_contrib), _lib.ptr(status),
-            _lib.ptr(st.workspace), st.workspace.numel(), stream), "cgs_rasterize_forward")
+            _lib.ptr(st.workspace), st.workspace.numel(), stream), "cgs_rasterize_forward_dev")
         if not sync:
             num_rendered = None
             break
@@ -146,7 +151,8 @@ def rasterize_forward_raw(c_settings, means3D, colors, opacities, scales, rotati
         if num_rendered >= 0x7fffffff:
             raise _lib.CgsError("number of (Gaussian, tile) instances exceeds 2^31")
         r_cap = int(num_rendered * 1.25) + 4096
-    st.last_num_rendered = num_rendered
+    if num_rendered is not None:
+        st.last_num_rendered = num_rendered
     st.r_cap_hint = max(st.r_cap_hint, min(r_cap, int((num_rendered or r_cap) * 1.5) + 4096))
     saved = dict(geom=geom, point_list=point_list, ranges=ranges, final_T=final_T, n_contrib=n_contrib, status=status,
                  num_rendered=num_rendered, r_cap=r_cap)

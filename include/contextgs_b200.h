@@ -57,6 +57,8 @@ enum {
     CGS_STATUS_NUM_RENDERED = 0, /* R = number of (Gaussian, tile) instances (low 31 bits) */
     CGS_STATUS_OVERFLOW = 1,     /* 1 if R > R_cap: the image is incomplete, re-run with a larger R_cap */
     CGS_STATUS_NUM_SORTED = 2,   /* min(R, R_cap) */
+    CGS_STATUS_NUM_GAUSSIANS = 3,      /* cgs_rasterize_forward_dev: *P_dev as read on the device */
+    CGS_STATUS_GAUSSIAN_OVERFLOW = 4,  /* 1 if *P_dev exceeded the capacity P the buffers were sized for */
     CGS_STATUS_WORDS = 8
 };
 
@@ -114,6 +116,19 @@ CGS_API int cgs_rasterize_forward(const cgs_raster_settings *s, int P, const flo
                           float *out_color, int32_t *radii, float *geom, uint32_t *point_list, uint32_t *ranges,
                           float *final_T, uint32_t *n_contrib, int32_t *status, void *workspace,
                           size_t workspace_bytes, void *stream);
+
+/* The same forward with the Gaussian count on the DEVICE: P is only the capacity of the per-Gaussian
+ * buffers, the kernels read the actual count from *P_dev (e.g. the count_dev written by
+ * cgs_neural_gaussians_*_forward), so the host never has to read it back between the two stages
+ * (the reference synchronises twice there: boolean indexing at gaussian_renderer/__init__.py:119,136).
+ * status[CGS_STATUS_NUM_GAUSSIANS / _GAUSSIAN_OVERFLOW] report the count and a capacity overflow.
+ * P_dev == NULL is cgs_rasterize_forward. */
+CGS_API int cgs_rasterize_forward_dev(const cgs_raster_settings *s, int P, const int32_t *P_dev, const float *means3D,
+                                      const float *colors, const float *opacities, const float *scales,
+                                      const float *rotations, int64_t R_cap, float *out_color, int32_t *radii,
+                                      float *geom, uint32_t *point_list, uint32_t *ranges, float *final_T,
+                                      uint32_t *n_contrib, int32_t *status, void *workspace, size_t workspace_bytes,
+                                      void *stream);
 
 /* Scratch bytes needed by cgs_rasterize_backward. */
 CGS_API size_t cgs_raster_backward_workspace_bytes(int P);
@@ -193,6 +208,24 @@ CGS_API int cgs_neural_gaussians_backward(const float *packed_fwd, const float *
 CGS_API size_t cgs_compact_workspace_bytes(int N);
 CGS_API int cgs_compact_indices(const uint8_t *mask, int N, int32_t *out_idx, int32_t *count_dev, void *workspace,
                                 size_t workspace_bytes, void *stream);
+
+/* The same for `values[i] > 0` on int32 input (the radii of cgs_visible_filter): replaces
+ * `visible_mask = radii_pure > 0` + boolean indexing (gaussian_renderer/__init__.py:287, :44-50).
+ * values must be 16-byte aligned. */
+CGS_API int cgs_compact_positive_i32(const int32_t *values, int N, int32_t *out_idx, int32_t *count_dev,
+                                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* cgs_neural_gaussians_umma_forward with the visible-anchor count on the DEVICE: Nv is the capacity of
+ * vis_idx, the kernel reads the count from *nv_dev (NULL = Nv), writes at most out_cap Gaussians (count_dev
+ * always receives the true total, so the caller can detect an overflow), and skips the training-side
+ * outputs when o_neural_opacity / o_mask are NULL. */
+CGS_API int cgs_neural_gaussians_umma_forward_dev(const float *packed_weights, const int32_t *vis_idx, int Nv,
+                                                  const int32_t *nv_dev, int64_t out_cap, const float *anchor,
+                                                  const float *feat, const float *offsets, const float *scaling,
+                                                  const float *mask, const float *campos_host, float *o_xyz,
+                                                  float *o_color, float *o_opacity, float *o_scaling, float *o_rot,
+                                                  float *o_neural_opacity, uint8_t *o_mask, int32_t *count_dev,
+                                                  void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------ context / entropy model (E4-E7, G2) */
 

@@ -1,0 +1,66 @@
+"""The inference fast path of `render` (one host read-back per frame, device-side counts) must give
+exactly what the synchronous path gives, and must recover from capacity overflows."""
+import pytest
+import torch
+
+from contextgs_b200 import renderer, synthetic
+from contextgs_b200.gaussian_model import GaussianModel
+from contextgs_b200.renderer import prefilter_voxel, render
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(N=30000, W=400, H=240):
+    scene = synthetic.make_scene("chair", N, seed=5, gaussian_scale=4.0)
+    torch.manual_seed(6)
+    pc = GaussianModel.from_tensors(scene, device="cuda")
+    pc.replace_with_decoded(**{k: v.cuda() for k, v in synthetic.decoded_scene(scene).items()})
+    pc.eval()
+    cams = synthetic.make_cameras("chair", 4, device="cuda", W=W, H=H)
+    pipe = type("Pipe", (), {"debug": False})()
+    return pc, cams, pipe, torch.zeros(3, device="cuda")
+
+
+def test_fast_path_equals_synchronous_path(monkeypatch):
+    pc, cams, pipe, bg = _setup()
+    for cam in cams:
+        with torch.no_grad():
+            vis = prefilter_voxel(cam, pc, pipe, bg)
+            fast = render(cam, pc, pipe, bg, visible_mask=vis)
+        with torch.enable_grad():                     # grad mode selects the synchronous (autograd) path
+            slow = render(cam, pc, pipe, bg, visible_mask=vis)
+        assert torch.equal(fast["render"], slow["render"].detach())
+        assert torch.equal(fast["radii"], slow["radii"])
+        assert fast["viewspace_points"].shape == slow["viewspace_points"].shape
+        assert torch.equal(fast["visibility_filter"], slow["visibility_filter"])
+        assert float(fast["render"].max()) > 0
+
+
+def test_fast_path_recovers_from_capacity_overflow():
+    pc, cams, pipe, bg = _setup()
+    cam = cams[0]
+    with torch.no_grad():
+        vis = prefilter_voxel(cam, pc, pipe, bg)
+        ref = render(cam, pc, pipe, bg, visible_mask=vis)
+        dev = ref["render"].device
+        renderer._p_cap_hint[dev.index] = 1000                       # far too small: Gaussian overflow
+        from contextgs_b200.rasterizer import _state
+        _state(dev).r_cap_hint = 0
+        again = render(cam, pc, pipe, bg, visible_mask=vis)
+    assert torch.equal(again["render"], ref["render"]) and torch.equal(again["radii"], ref["radii"])
+    assert renderer._p_cap_hint[dev.index] >= ref["radii"].shape[0]
+
+
+def test_compact_positive_i32_matches_nonzero():
+    from contextgs_b200 import _lib
+    L = _lib.lib()
+    for n in (1, 9, 4096, 100_003):
+        g = torch.Generator().manual_seed(n)
+        v = torch.randint(-3, 4, (n,), generator=g, dtype=torch.int32).cuda()
+        idx = torch.empty(n, dtype=torch.int32, device="cuda")
+        cnt = torch.empty(1, dtype=torch.int32, device="cuda")
+        ws = torch.empty(L.cgs_compact_workspace_bytes(n), dtype=torch.uint8, device="cuda")
+        _lib.check(L.cgs_compact_positive_i32(_lib.ptr(v), n, _lib.ptr(idx), _lib.ptr(cnt), _lib.ptr(ws), ws.numel(),
+                                              _lib.stream_ptr()), "cgs_compact_positive_i32")
+        ref = torch.nonzero(v > 0)[:, 0].to(torch.int32)
+        assert int(cnt.item()) == ref.numel() and torch.equal(idx[: ref.numel()], ref)
