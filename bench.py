@@ -12,8 +12,9 @@ camera.  With N > 1 every rank holds a replica and renders its own cameras (weak
 data-path collective -- SURVEY.md 8e).
 
   value : frames/s with the camera matrices already resident on the device.
-  e2e   : the same through the public `render()` call with the camera in HOST memory and the
-          rendered image copied back to pinned host memory inside the timed region.
+  e2e   : the same through the public `render()` call with the camera in HOST memory and every
+          rendered image copied back to pinned host memory inside the timed region (second stream,
+          double buffered, all copies complete before the closing event).
   roofline : dominant kernel (by summed device time in a separate stage-timed pass with CUDA
           events on the launching stream), algorithmic bytes per SURVEY.md 8d / DESIGN.md.
   cpu_baseline / --impl reference : the CPU oracle (oracle/, OpenMP + torch CPU threads) on the
@@ -310,7 +311,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, after_warmup=None):
+    def timed(fn, steps, warmup, after_warmup=None, before_end=None):
         for i in range(warmup):
             fn(i)
         barrier()
@@ -320,6 +321,8 @@ def main():
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        if before_end is not None:
+            before_end()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -339,14 +342,26 @@ def main():
     fps = world * args.steps / (ms * 1e-3)
 
     # ---- end-to-end pass: camera in host memory, image to pinned host memory -----------------
-    host_img = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
+    # Every frame's image is copied to pinned host memory on a second stream, double buffered: the copy of
+    # frame i (24.9 MB over PCIe) overlaps the kernels of frame i+1; the timed region ends only after the
+    # last copy has landed (the main stream waits for the copy stream before the closing event).
+    host_imgs = [torch.empty((3, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    copy_done = [None, None]
     cam_bytes = 4 * (16 + 16 + 3)
 
     def e2e_step(i):
-        out = frame(cams_cpu[my_cam(i)])              # matrices read on the host, passed by value to the kernels
-        host_img.copy_(out["render"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()     # the caller owns the pixels before the next frame starts
-    ms_e2e = timed(e2e_step, args.steps, max(args.warmup, 3))
+        out = frame(cams_cpu[my_cam(i)])              # matrices read on the host, passed by value to the kernels;
+        b = i & 1                                     # render() returns after its status read-back: pixels complete
+        if copy_done[b] is not None:
+            copy_done[b].synchronize()                # the caller has consumed host buffer b (two frames ago)
+        with torch.cuda.stream(copy_stream):
+            host_imgs[b].copy_(out["render"], non_blocking=True)
+            copy_done[b] = torch.cuda.Event()
+            copy_done[b].record(copy_stream)
+        out["render"].record_stream(copy_stream)
+    ms_e2e = timed(e2e_step, args.steps, max(args.warmup, 3),
+                   before_end=lambda: torch.cuda.current_stream().wait_stream(copy_stream))
     fps_e2e = world * args.steps / (ms_e2e * 1e-3)
     clk.__exit__()
     clocks = clk.summary()  # sampled over the device-resident and the end-to-end timed regions

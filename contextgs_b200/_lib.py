@@ -45,6 +45,10 @@ SIGNATURES = {
     "cgs_launch_counts": (c_int, [_PTR, c_int]),
     "cgs_umma_selftest": (c_int, [_PTR, _PTR, c_int, c_int, c_int, _PTR, _PTR, _PTR]),
     "cgs_visible_filter": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR]),
+    "cgs_prefilter_workspace_bytes": (c_size_t, [c_int]),
+    "cgs_prefilter_anchors": (c_int, [_PTR, c_int, _PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
+    "cgs_render_anchors_forward": (c_int, [_PTR, _PTR, _PTR, c_int, _PTR, c_int] + [_PTR] * 12 + [c_size_t, c_int64] +
+                                   [_PTR] * 9 + [c_size_t, _PTR]),
     "cgs_mark_visible": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR]),
     "cgs_raster_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int]),
     "cgs_rasterize_forward": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, c_int64, _PTR, _PTR, _PTR, _PTR, _PTR,

@@ -126,9 +126,6 @@ __device__ __forceinline__ uint64_t lookback_exclusive(unsigned long long *state
 // ---- sort / scan primitives (radix_sort.cu) -------------------------------------------
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;
-constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per CTA
 
 struct SortPlan {
     int npass;

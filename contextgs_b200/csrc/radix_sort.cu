@@ -2,13 +2,15 @@
 // style: one upfront histogram read for all digit places, then one chained-scan ("decoupled
 // look-back") scatter kernel per 8-bit digit.  Per pass each key is read once and written once.
 //
-// B200 sizing: 4096 keys per CTA (256 threads x 16 keys), tiles handed out by an atomic ticket so
+// B200 sizing: 6144 keys per CTA (384 threads x 16 keys), tiles handed out by an atomic ticket so
 // that look-back predecessors are always resident; the element count lives on the device
 // (*n_dev) so the rasterizer never has to read `num_rendered` back to the host.
 //
 // Replaces the cub::DeviceRadixSort::SortPairs call of the upstream rasterizer
 // (rasterizer_impl.cu, not in the reference tree) -- see raster_binning.cu for how the 64-bit
 // (tile<<32 | depth) sort is decomposed into two narrower sorts with an identical result.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cgs {
@@ -16,7 +18,6 @@ namespace cgs {
 constexpr uint32_t kFlagAggregate = 1u << 30;
 constexpr uint32_t kFlagInclusive = 2u << 30;
 constexpr uint32_t kValueMask = (1u << 30) - 1;
-constexpr int kSortWarps = kSortThreads / 32;
 
 // hist[pass][256]: digit counts of every pass, one read of the keys.
 __global__ void __launch_bounds__(256)
@@ -62,76 +63,128 @@ __global__ void __launch_bounds__(256) radix_scan_hist_kernel(uint32_t *__restri
 
 // One digit pass.  lookback[tile][256] holds (flag | count) words; ticket hands out tiles.
 //
-// Per tile of 4096 pairs: (1) warp-local stable ranking with match.any, (2) thread d owns digit d:
-// prefix over the 8 warps, a block scan over the 256 digits (tile-local sorted position of each
-// digit's run) and the chained look-back across tiles, (3) the pairs are first scattered into SHARED
-// memory in tile-sorted order and only then copied out, so that consecutive threads write
-// consecutive global addresses (one run per digit) instead of 32 scattered 4-byte stores per warp.
-__global__ void __launch_bounds__(kSortThreads, 4)
+// Per tile of THREADS x ITEMS pairs: (1) warp-local stable ranking: the match.any masks of a chunk of
+// items are computed back to back, then one leader lane per digit group bumps the per-warp digit counter; (2) thread d owns digit d: prefix over the warps, a block scan over the 256 digits
+// (tile-local sorted position of each digit's run) and the chained look-back across tiles; (3) the pairs
+// are first scattered into SHARED memory in tile-sorted order and only then copied out, so that
+// consecutive threads write consecutive global addresses (one run per digit) instead of 32 scattered
+// 4-byte stores per warp.  Values are fetched right after the keys, so their HBM latency hides behind
+// the ranking.
+template <int THREADS, int ITEMS>
+struct SortSmem {
+    static constexpr int kWarps = THREADS / 32, kTileKeys = THREADS * ITEMS;
+    uint32_t warp_hist[kWarps][kRadix];
+    uint32_t digit_start[kRadix];   // tile-local sorted position of the first key of each digit
+    uint32_t digit_gbase[kRadix];   // global position of that key minus digit_start
+    uint32_t wsum[8];
+    uint32_t tile;
+    uint32_t key[kTileKeys];
+    uint32_t val[kTileKeys];
+};
+
+template <int THREADS, int ITEMS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                      const uint32_t *__restrict__ n_dev, uint32_t n_cap, int shift, int bits,
                      const uint32_t *__restrict__ global_base, uint32_t *lookback, uint32_t tiles_cap,
                      uint32_t *ticket)
 {
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t warp_hist[kSortWarps][kRadix];
-    __shared__ uint32_t digit_start[kRadix];   // tile-local sorted position of the first key of each digit
-    __shared__ uint32_t digit_gbase[kRadix];   // global position of that key minus digit_start
-    __shared__ uint32_t s_wsum[kSortWarps];
-    __shared__ uint32_t s_key[kSortTile];
-    __shared__ uint32_t s_val[kSortTile];
+    using Smem = SortSmem<THREADS, ITEMS>;
+    constexpr int kWarps = Smem::kWarps, kTileKeys = Smem::kTileKeys;
+    constexpr int kChunk = ITEMS < 8 ? ITEMS : 8;
+    static_assert(THREADS >= kRadix && ITEMS % kChunk == 0 && ITEMS % 2 == 0, "tile shape");
+    extern __shared__ __align__(16) unsigned char sort_smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(sort_smem_raw);
 
     const uint32_t n = min(*n_dev, n_cap);
-    const uint32_t num_tiles = (n + kSortTile - 1) / kSortTile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < kSortWarps * kRadix; i += kSortThreads) (&warp_hist[0][0])[i] = 0;
+    const uint32_t num_tiles = (n + kTileKeys - 1) / kTileKeys;
+    if (threadIdx.x == 0) S.tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < kWarps * kRadix; i += THREADS) (&S.warp_hist[0][0])[i] = 0;
     __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = S.tile;
     if (tile >= num_tiles) return;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lane_lt = (1u << lane) - 1;
     const uint32_t mask = (1u << bits) - 1;
-    const uint32_t tile_base = tile * kSortTile;
-    const uint32_t warp_base = tile_base + warp * (32 * kSortItems);
-    const uint32_t tile_count = min((uint32_t)kSortTile, n - tile_base);
+    const uint32_t tile_base = tile * kTileKeys;
+    const uint32_t warp_base = tile_base + warp * (32 * ITEMS);
+    const uint32_t tile_count = min((uint32_t)kTileKeys, n - tile_base);
+    const bool full = tile_count == (uint32_t)kTileKeys;
 
-    uint32_t key[kSortItems];
-    uint16_t rank[kSortItems];
+    uint32_t key[ITEMS], val[ITEMS];
+    uint32_t rank2[ITEMS / 2];  // two 16-bit warp-local ranks per register
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
-        const uint32_t idx = warp_base + i * 32 + lane;
-        key[i] = idx < n ? keys_in[idx] : 0xFFFFFFFFu;
-    }
-    // warp-local stable ranking (match-any), items visited in memory order
+        for (int i = 0; i < ITEMS; ++i) key[i] = keys_in[warp_base + i * 32 + lane];
+        if (vals_in) {
 #pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
-        const uint32_t idx = warp_base + i * 32 + lane;
-        const bool valid = idx < n;
-        const uint32_t digit = valid ? ((key[i] >> shift) & mask) : kRadix;  // invalid lanes form their own group
-        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (lane == leader && valid) {
-            old = warp_hist[warp][digit];
-            warp_hist[warp][digit] = old + __popc(peers);
+            for (int i = 0; i < ITEMS; ++i) val[i] = vals_in[warp_base + i * 32 + lane];
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) val[i] = warp_base + i * 32 + lane;
         }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[i] = (uint16_t)(old + __popc(peers & lane_lt));
-        __syncwarp();
+    } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t idx = warp_base + i * 32 + lane;
+            key[i] = idx < n ? keys_in[idx] : 0xFFFFFFFFu;
+            val[i] = idx < n ? (vals_in ? vals_in[idx] : idx) : 0u;
+        }
+    }
+    // warp-local stable ranking (match-any), items visited in memory order, kChunk items in flight
+    uint32_t *wh = S.warp_hist[warp];
+#pragma unroll
+    for (int c = 0; c < ITEMS; c += kChunk) {
+        uint32_t peers[kChunk];
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) {
+            // Peers = lanes holding the same digit, built from one ballot per digit bit.  MATCH.ANY retires one
+            // distinct value per step, and a warp of depth- or tile-ordered keys holds ~25 distinct digits:
+            // ncu (profiles/r01_sort3_*) showed ~1000 stall cycles per item on its consumer.  Eight independent
+            // ballots cost more issue slots but no serialisation.
+            const bool valid = full || (warp_base + (c + i) * 32 + lane) < n;
+            const uint32_t digit = (key[c + i] >> shift) & mask;
+            uint32_t p = full ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+            for (int b = 0; b < kRadixBits; ++b) {
+                if (b < bits) {   // warp-uniform
+                    const bool bit = (digit >> b) & 1u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                    p &= bit ? bal : ~bal;
+                }
+            }
+            peers[i] = valid ? p : (1u << lane);   // invalid lanes: a group of their own, never written
+        }
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) {
+            const bool valid = full || (warp_base + (c + i) * 32 + lane) < n;
+            const int leader = __ffs(peers[i]) - 1;
+            uint32_t o = 0;
+            if (lane == leader && valid) {   // one lane per digit group: plain read-modify-write (ATOMS costs 2 cyc/lane)
+                const uint32_t digit = (key[c + i] >> shift) & mask;
+                o = wh[digit];
+                wh[digit] = o + __popc(peers[i]);
+            }
+            o = __shfl_sync(0xffffffffu, o, leader);
+            const uint32_t r = o + __popc(peers[i] & lane_lt);
+            if ((i & 1) == 0) rank2[(c + i) / 2] = r;
+            else rank2[(c + i) / 2] |= r << 16;
+            __syncwarp();
+        }
     }
     __syncthreads();
 
     // thread d owns digit d: prefix over the warps, aggregate published EARLY, block scan over digits
-    uint32_t my_sum;
-    {
+    uint32_t my_sum = 0;
+    if (threadIdx.x < kRadix) {
         const int d = threadIdx.x;
         uint32_t sum = 0;
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) {
-            const uint32_t c = warp_hist[w][d];
-            warp_hist[w][d] = sum;
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t c = S.warp_hist[w][d];
+            S.warp_hist[w][d] = sum;
             sum += c;
         }
         my_sum = sum;
@@ -143,59 +196,108 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
+        if (lane == 31) S.wsum[warp] = incl;
+        // (the second half of the scan needs all eight warp sums)
+        asm volatile("bar.sync 1, 256;");
         uint32_t before = 0;
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) before += w < warp ? s_wsum[w] : 0u;
-        digit_start[d] = before + incl - sum;
+        for (int w = 0; w < kRadix / 32; ++w) before += w < warp ? S.wsum[w] : 0u;
+        S.digit_start[d] = before + incl - sum;
     }
     __syncthreads();
 
     // scatter into shared memory in tile-sorted order (frees the key / rank registers)
 #pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
-        const uint32_t idx = warp_base + i * 32 + lane;
-        if (idx < n) {
+    for (int i = 0; i < ITEMS; ++i) {
+        if (full || (warp_base + i * 32 + lane) < n) {
             const uint32_t digit = (key[i] >> shift) & mask;
-            const uint32_t lp = digit_start[digit] + warp_hist[warp][digit] + rank[i];
-            s_key[lp] = key[i];
-            s_val[lp] = vals_in ? vals_in[idx] : idx;
+            const uint32_t lp = S.digit_start[digit] + wh[digit] + ((rank2[i / 2] >> (16 * (i & 1))) & 0xffffu);
+            S.key[lp] = key[i];
+            S.val[lp] = val[i];
         }
     }
 
     // Chained look-back, one thread per digit.  (A warp-wide variant that reads 32 predecessor tiles
     // x 32 digits per round trip was measured 2x SLOWER here: the extra L2 traffic costs more than the
     // shorter chains save -- the aggregates are published early, so chains are short already.)
-    {
+    if (threadIdx.x < kRadix) {
         const int d = threadIdx.x;
         volatile uint32_t *lb = lookback;
         uint32_t excl = 0;
         if (tile != 0) {
+            // The walk reads kLook predecessors per round trip (independent loads in flight) and consumes them
+            // in order: with hundreds of tiles resident the nearest INCLUSIVE prefix is often dozens of tiles
+            // back, and one dependent L2 round trip per predecessor was the critical path of the whole pass.
+            constexpr int kLook = 8;
             int64_t t = (int64_t)tile - 1;
-            while (true) {
-                uint32_t v = lb[(size_t)t * kRadix + d];
-                while ((v >> 30) == 0) v = lb[(size_t)t * kRadix + d];
-                excl += v & kValueMask;
-                if ((v >> 30) == 2u) break;
-                --t;
+            bool done = false;
+            while (!done) {
+                uint32_t v[kLook];
+#pragma unroll
+                for (int j = 0; j < kLook; ++j)
+                    v[j] = t - j >= 0 ? lb[(size_t)(t - j) * kRadix + d] : (2u << 30);  // virtual inclusive zero before tile 0
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < kLook; ++j) {
+                    if (!done && used == j) {
+                        if ((v[j] >> 30) != 0) {
+                            excl += v[j] & kValueMask;
+                            done = (v[j] >> 30) == 2u;
+                            used = j + 1;
+                        }
+                    }
+                }
+                t -= used;   // used == 0: the nearest predecessor has not published yet -- poll again
             }
             lb[(size_t)tile * kRadix + d] = kFlagInclusive | (excl + my_sum);
         }
-        digit_gbase[d] = global_base[d] + excl - digit_start[d];
+        S.digit_gbase[d] = global_base[d] + excl - S.digit_start[d];
     }
     __syncthreads();
     // coalesced copy-out: position j of the tile-sorted order goes to digit_gbase[digit] + j
 #pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
-        const uint32_t j = i * kSortThreads + threadIdx.x;
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint32_t j = i * THREADS + threadIdx.x;
         if (j < tile_count) {
-            const uint32_t k = s_key[j];
-            const uint32_t pos = digit_gbase[(k >> shift) & mask] + j;
+            const uint32_t k = S.key[j];
+            const uint32_t pos = S.digit_gbase[(k >> shift) & mask] + j;
             keys_out[pos] = k;
-            vals_out[pos] = s_val[j];
+            vals_out[pos] = S.val[j];
         }
     }
+}
+
+// Tile shape of the digit pass.  The default was chosen by measurement on B200 (profiles/); the
+// environment variable CGS_SORT_VARIANT (read once) selects another one for experiments.
+struct SortVariant {
+    int threads, items;
+};
+static const SortVariant kSortVariants[] = {{256, 16}, {512, 16}, {512, 8}, {256, 24}, {384, 16}, {1024, 8}, {256, 16}, {512, 16}};
+static int sort_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CGS_SORT_VARIANT");
+        v = e ? atoi(e) : 4;   // 384 x 16: fastest of the measured shapes (profiles/r01_sort_variants.txt)
+        if (v < 0 || v >= (int)(sizeof(kSortVariants) / sizeof(kSortVariants[0]))) v = 4;
+    }
+    return v;
+}
+static int sort_tile_keys() { return kSortVariants[sort_variant()].threads * kSortVariants[sort_variant()].items; }
+
+template <int THREADS, int ITEMS, int MIN_BLOCKS>
+static void launch_onesweep(unsigned grid, cudaStream_t stream, const uint32_t *kin, const uint32_t *vin, uint32_t *ko,
+                            uint32_t *vo, const uint32_t *n_dev, uint32_t n_cap, int shift, int bits,
+                            const uint32_t *gbase, uint32_t *lookback, uint32_t tiles_cap, uint32_t *ticket)
+{
+    auto kern = onesweep_pass_kernel<THREADS, ITEMS, MIN_BLOCKS>;
+    constexpr size_t smem = sizeof(SortSmem<THREADS, ITEMS>);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    kern<<<grid, THREADS, smem, stream>>>(kin, vin, ko, vo, n_dev, n_cap, shift, bits, gbase, lookback, tiles_cap, ticket);
 }
 
 SortPlan make_sort_plan(int64_t n_cap, int begin_bit, int end_bit)
@@ -204,7 +306,7 @@ SortPlan make_sort_plan(int64_t n_cap, int begin_bit, int end_bit)
     const int nbits = end_bit > begin_bit ? end_bit - begin_bit : 1;
     p.npass = (nbits + kRadixBits - 1) / kRadixBits;
     if (p.npass > 4) p.npass = 4;
-    p.tiles_cap = ceil_div64(n_cap > 0 ? n_cap : 1, kSortTile);
+    p.tiles_cap = ceil_div64(n_cap > 0 ? n_cap : 1, sort_tile_keys());
     size_t off = 0;
     p.hist_off = off;
     off += align_up((size_t)p.npass * kRadix * sizeof(uint32_t));
@@ -254,9 +356,21 @@ int sort_pairs(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_
         (void)last;
         const int shift = begin_bit + p * kRadixBits;
         const int bits = min(kRadixBits, end_bit - shift);
-        onesweep_pass_kernel<<<(unsigned)plan.tiles_cap, kSortThreads, 0, stream>>>(
-            kin, vin, ko, vo, n_dev, (uint32_t)n_cap, shift, bits, hist + p * kRadix,
-            lookback + (size_t)p * plan.tiles_cap * kRadix, (uint32_t)plan.tiles_cap, ticket + p);
+        const unsigned grid = (unsigned)plan.tiles_cap;
+        const uint32_t *gb = hist + p * kRadix;
+        uint32_t *lb = lookback + (size_t)p * plan.tiles_cap * kRadix;
+        const uint32_t tc = (uint32_t)plan.tiles_cap;
+        switch (sort_variant()) {
+        default:
+        case 0: launch_onesweep<256, 16, 3>(grid, stream, kin, vin, ko, vo, n_dev, (uint32_t)n_cap, shift, bits, gb, lb, tc, ticket + p); break;
+        case 1: launch_onesweep<512, 16, 2>(grid, stream, kin, vin, ko, vo, n_dev, (uint32_t)n_cap, shift, bits, gb, lb, tc, ticket + p); break;
+        case 2: launch_onesweep<512, 8, 2>(grid, stream, kin, vin, ko, vo, n_dev, (uint32_t)n_cap, shift, bits, gb, lb, tc, ticket + p); break;
+        case 3: launch_onesweep<256, 24, 2>(grid, stream, kin, vin, ko, vo, n_dev, (uint32_t)n_cap, shift, bits, gb, lb, tc, ticket + p); break;
+        case 4: launch_onesweep<384, 16, 2>(grid, stream, kin, vin, ko, vo, n_dev, (uint32_t)n_cap, shift, bits, gb, lb, tc, ticket + p); break;
+        case 5: launch_onesweep<1024, 8, 1>(grid, stream, kin, vin, ko, vo, n_dev, (uint32_t)n_cap, shift, bits, gb, lb, tc, ticket + p); break;
+        case 6: launch_onesweep<256, 16, 2>(grid, stream, kin, vin, ko, vo, n_dev, (uint32_t)n_cap, shift, bits, gb, lb, tc, ticket + p); break;
+        case 7: launch_onesweep<512, 16, 1>(grid, stream, kin, vin, ko, vo, n_dev, (uint32_t)n_cap, shift, bits, gb, lb, tc, ticket + p); break;
+        }
         kin = ko;
         vin = vo;
     }

@@ -76,6 +76,8 @@ void launch_preprocess(const CamParams &, int, const uint32_t *, const float *, 
                        const float *, const float *, int32_t *, float *, uint32_t *, cudaStream_t);
 void launch_filter(const CamParams &, int, const float *, const float *, const float *, int32_t *, cudaStream_t);
 void launch_mark_visible(const CamParams &, int, const float *, uint8_t *, cudaStream_t);
+void launch_prefilter_anchors(const CamParams &, int, const float *, const float *, int, const float *, uint8_t *, int *,
+                              unsigned long long *, uint32_t *, int32_t *, cudaStream_t);
 void launch_preprocess_backward(const CamParams &, int, const float *, const float *, const float *, const int32_t *,
                                 const float *, float *, float *, float *, float *, float *, float *, cudaStream_t);
 void launch_scan_tiles(const uint32_t *, const float *, int, const uint32_t *, int64_t, uint32_t *,
@@ -240,6 +242,67 @@ extern "C" int cgs_visible_filter(const cgs_raster_settings *s, int N, const flo
     StageScope sc(ST_FILTER, static_cast<cudaStream_t>(stream), 1);
     launch_filter(make_cam(s), N, means3D, scales, rotations, radii, static_cast<cudaStream_t>(stream));
     return check_launch(__func__);
+}
+
+extern "C" size_t cgs_prefilter_workspace_bytes(int N)
+{
+    const size_t tiles = (size_t)(N > 0 ? (N + 255) / 256 : 1);
+    return align_up(tiles * 8) + align_up(16);
+}
+
+extern "C" int cgs_prefilter_anchors(const cgs_raster_settings *s, int N, const float *anchor, const float *scales,
+                                     int scale_stride, const float *rotation_row, uint8_t *visible, int32_t *vis_idx,
+                                     int32_t *count_dev, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (int e = validate_settings(s, __func__)) return e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CGS_CHECK_PTR(count_dev);
+    if (N <= 0) {
+        cudaMemsetAsync(count_dev, 0, sizeof(int32_t), st);
+        return check_launch(__func__);
+    }
+    CGS_CHECK_PTR(anchor);
+    CGS_CHECK_PTR(scales);
+    CGS_CHECK_PTR(rotation_row);
+    CGS_CHECK_PTR(visible);
+    CGS_CHECK_PTR(vis_idx);
+    CGS_CHECK_PTR(workspace);
+    if (scale_stride < 3) {
+        set_error("%s: scale_stride %d < 3", __func__, scale_stride);
+        return -2;
+    }
+    if (workspace_bytes < cgs_prefilter_workspace_bytes(N)) {
+        set_error("%s: workspace too small", __func__);
+        return -3;
+    }
+    const size_t tiles = (size_t)(N + 255) / 256;
+    char *ws = static_cast<char *>(workspace);
+    cudaMemsetAsync(ws, 0, cgs_prefilter_workspace_bytes(N), st);
+    StageScope sc(ST_FILTER, st, 1);
+    launch_prefilter_anchors(make_cam(s), N, anchor, scales, scale_stride, rotation_row, visible, vis_idx,
+                             reinterpret_cast<unsigned long long *>(ws),
+                             reinterpret_cast<uint32_t *>(ws + align_up(tiles * 8)), count_dev, st);
+    return check_launch(__func__);
+}
+
+extern "C" int cgs_render_anchors_forward(const cgs_raster_settings *s, const float *packed_weights,
+                                          const int32_t *vis_idx, int Nv_cap, const int32_t *nv_dev, int P_cap,
+                                          const float *anchor, const float *feat, const float *offsets,
+                                          const float *scaling, const float *mask, float *g_xyz, float *g_color,
+                                          float *g_opacity, float *g_scaling, float *g_rot, int32_t *g_count,
+                                          void *g1_workspace, size_t g1_workspace_bytes, int64_t R_cap, float *out_color,
+                                          int32_t *radii, float *geom, uint32_t *point_list, uint32_t *ranges,
+                                          float *final_T, uint32_t *n_contrib, int32_t *status, void *workspace,
+                                          size_t workspace_bytes, void *stream)
+{
+    if (int e = validate_settings(s, __func__)) return e;
+    if (int e = cgs_neural_gaussians_umma_forward_dev(packed_weights, vis_idx, Nv_cap, nv_dev, P_cap, anchor, feat, offsets,
+                                                      scaling, mask, s->campos, g_xyz, g_color, g_opacity, g_scaling, g_rot,
+                                                      nullptr, nullptr, g_count, g1_workspace, g1_workspace_bytes, stream))
+        return e;
+    return cgs_rasterize_forward_dev(s, P_cap, g_count, g_xyz, g_color, g_opacity, g_scaling, g_rot, R_cap, out_color, radii,
+                                     geom, point_list, ranges, final_T, n_contrib, status, workspace, workspace_bytes,
+                                     stream);
 }
 
 extern "C" int cgs_mark_visible(const cgs_raster_settings *s, int N, const float *means3D, uint8_t *visible,

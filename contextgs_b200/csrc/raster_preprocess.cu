@@ -174,6 +174,71 @@ filter_kernel(CamParams cam, int N, const float *__restrict__ means, const float
                            depth, conic, tiles);
 }
 
+// prefilter_voxel in ONE pass (gaussian_renderer/__init__.py:232-287): radius test of every anchor with
+// scales = get_scaling[:, :3] (row stride `scale_stride` floats) and the rotation of anchor 0 for all
+// anchors (the reference passes rotations[[0], :].repeat(N, 1)), fused with the ordered compaction
+// of the visible anchors (decoupled look-back across 1024-anchor tiles).  Writes the boolean mask the
+// reference returns AND the index list + device-side count the G1 kernel consumes, so neither
+// `radii > 0` nor a separate compaction pass (nor the N x 4 rotation copy) ever touches HBM.
+constexpr int kPrefilterItems = 4, kPrefilterTile = 256 * kPrefilterItems;
+
+__global__ void __launch_bounds__(256)
+prefilter_anchors_kernel(CamParams cam, int N, const float *__restrict__ means, const float *__restrict__ scales,
+                         int scale_stride, const float *__restrict__ rot_row, uint8_t *__restrict__ visible,
+                         int *__restrict__ out_idx, unsigned long long *scan_state, uint32_t *ticket,
+                         int32_t *__restrict__ count_out)
+{
+    // item k of thread t is anchor tile*1024 + k*256 + t: coalesced loads, and the index order is (k, warp, lane)
+    __shared__ uint32_t s_tile, s_cnt[kPrefilterItems * 8], s_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 q = make_float4(rot_row[0], rot_row[1], rot_row[2], rot_row[3]);
+    const float nrm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);  // F.normalize
+    q = make_float4(q.x / nrm, q.y / nrm, q.z / nrm, q.w / nrm);
+    uint32_t ball[kPrefilterItems];
+    bool vis[kPrefilterItems];
+#pragma unroll
+    for (int k = 0; k < kPrefilterItems; ++k) {
+        const int i = tile * kPrefilterTile + k * 256 + threadIdx.x;
+        vis[k] = false;
+        if (i < N) {
+            const float *sp = scales + (size_t)i * scale_stride;
+            float px, py, depth;
+            float3 conic;
+            int tiles;
+            vis[k] = project_one(cam, load3(means, i), make_float3(sp[0], sp[1], sp[2]), q, px, py, depth, conic, tiles) > 0;
+            visible[i] = vis[k] ? 1 : 0;
+        }
+        ball[k] = __ballot_sync(0xffffffffu, vis[k]);
+        if (lane == 0) s_cnt[k * 8 + warp] = __popc(ball[k]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive scan of the 32 (item, warp) counts, then the chained scan across tiles
+        const uint32_t c = s_cnt[lane];
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        s_cnt[lane] = incl - c;
+        const uint64_t excl = lookback_exclusive(scan_state, tile, total);
+        if (lane == 0) {
+            s_base = (uint32_t)excl;
+            if (tile == (N - 1) / kPrefilterTile) *count_out = (int32_t)(excl + total);
+        }
+    }
+    __syncthreads();
+    const uint32_t base = s_base, lt = (1u << lane) - 1;
+#pragma unroll
+    for (int k = 0; k < kPrefilterItems; ++k)
+        if (vis[k]) out_idx[base + s_cnt[k * 8 + warp] + __popc(ball[k] & lt)] = tile * kPrefilterTile + k * 256 + threadIdx.x;
+}
+
 __global__ void __launch_bounds__(256)
 mark_visible_kernel(CamParams cam, int N, const float *__restrict__ means, uint8_t *__restrict__ visible)
 {
@@ -323,6 +388,15 @@ void launch_filter(const CamParams &cam, int N, const float *means, const float 
 {
     if (N <= 0) return;
     filter_kernel<<<(N + 255) / 256, 256, 0, st>>>(cam, N, means, scales, rots, radii);
+}
+
+void launch_prefilter_anchors(const CamParams &cam, int N, const float *means, const float *scales, int scale_stride,
+                              const float *rot_row, uint8_t *visible, int *out_idx, unsigned long long *scan_state,
+                              uint32_t *ticket, int32_t *count_out, cudaStream_t st)
+{
+    if (N <= 0) return;
+    prefilter_anchors_kernel<<<(N + kPrefilterTile - 1) / kPrefilterTile, 256, 0, st>>>(cam, N, means, scales, scale_stride, rot_row, visible,
+                                                              out_idx, scan_state, ticket, count_out);
 }
 
 void launch_mark_visible(const CamParams &cam, int N, const float *means, uint8_t *visible, cudaStream_t st)

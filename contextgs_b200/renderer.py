@@ -5,8 +5,9 @@ import math
 import torch
 
 from . import _lib
-from .neural_gaussians import compact_indices, generate_neural_gaussians, generate_raw, g1_impl, select_attributes
-from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_forward_raw, to_c_settings)
+from .neural_gaussians import (compact_indices, generate_neural_gaussians, g1_impl, pack_decoder_weights_umma,
+                               select_attributes)
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, to_c_settings
 
 _p_cap_hint = {}   # device index -> capacity (in Gaussians) that was enough for the recent frames
 
@@ -20,30 +21,96 @@ def _settings(viewpoint_camera, pipe, bg_color, scaling_modifier):
         prefiltered=False, debug=bool(getattr(pipe, "debug", False)))
 
 
+class _FrameScratch:
+    """Per-device buffers of the inference frame that never leave this module (Gaussian attributes, packed
+    records, binning lists, sort workspace): allocated once, grown on demand and reused frame after frame
+    (frames are stream-ordered and every frame ends with the status read-back, so reuse is safe)."""
+
+    def __init__(self):
+        self.p_cap = self.r_cap = self.hw = self.n = 0
+        self.ws = self.g1_ws = None
+
+    def ensure(self, L, dev, N, p_cap, r_cap, W, H):
+        f32, i32 = torch.float32, torch.int32
+        if p_cap > self.p_cap:
+            self.p_cap = p_cap
+            self.xyz, self.color = torch.empty((p_cap, 3), dtype=f32, device=dev), torch.empty((p_cap, 3), dtype=f32, device=dev)
+            self.opacity, self.scaling = torch.empty((p_cap, 1), dtype=f32, device=dev), torch.empty((p_cap, 3), dtype=f32, device=dev)
+            self.rot, self.geom = torch.empty((p_cap, 4), dtype=f32, device=dev), torch.empty((p_cap, _lib.GEOM_STRIDE), dtype=f32, device=dev)
+            self.count = torch.empty((1,), dtype=i32, device=dev)
+        if r_cap > self.r_cap:
+            self.r_cap = r_cap
+            self.point_list = torch.empty((r_cap,), dtype=i32, device=dev)
+        if H * W != self.hw:
+            self.hw = H * W
+            tiles = ((W + 15) // 16) * ((H + 15) // 16)
+            self.ranges = torch.empty((tiles, 2), dtype=i32, device=dev)
+            self.final_T, self.n_contrib = torch.empty((H, W), dtype=f32, device=dev), torch.empty((H, W), dtype=i32, device=dev)
+        if N > self.n:
+            self.n = N
+            self.g1_ws = torch.empty((L.cgs_neural_gaussians_umma_workspace_bytes(N),), dtype=torch.uint8, device=dev)
+            self.n_all = None
+        need = L.cgs_raster_workspace_bytes(self.p_cap, self.r_cap, W, H)
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = None
+            self.ws = torch.empty((need + 1024,), dtype=torch.uint8, device=dev)
+
+
+_scratch = {}   # (device index, stream) -> _FrameScratch
+
+
 @torch.no_grad()
 def _render_inference(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, visible_mask):
     """Inference frame with ONE host read-back at the very end.  The reference synchronises three times
     inside a frame (boolean indexing of the visible anchors, `tensor[mask]` of the Gaussians,
     `num_rendered`); here the visible-anchor count, the Gaussian count and the instance count stay on the
     device -- buffers are sized by capacities learnt from earlier frames -- and a single 8-word status
-    block is read after everything has been enqueued.  A capacity overflow re-runs the frame."""
+    block is read after everything has been enqueued by ONE library call (cgs_render_anchors_forward).
+    A capacity overflow re-runs the frame."""
+    from .rasterizer import _state
+    L = _lib.lib()
     anchor, feat, offsets, scaling, masks, _ = select_attributes(pc, False, 0)
     N, K, dev = anchor.shape[0], pc.n_offsets, anchor.device
     cs = to_c_settings(_settings(viewpoint_camera, pipe, bg_color, scaling_modifier))
+    H, W = cs.image_height, cs.image_width
     if visible_mask is None:
         vis_idx, nv_dev = None, None
     else:
-        vis_idx, nv_dev = compact_indices(visible_mask)
-    offsets2, masks2 = offsets.reshape(N, -1), masks.reshape(N, -1)
+        cached = getattr(visible_mask, "_cgs_compact", None)   # prefilter_voxel already compacted the mask
+        if cached is not None and cached[2] == visible_mask._version:
+            vis_idx, nv_dev = cached[0], cached[1]
+        else:
+            vis_idx, nv_dev = compact_indices(visible_mask)
+    anchor, feat, scaling = anchor.contiguous(), feat.contiguous(), scaling.contiguous()
+    offsets2, masks2 = offsets.reshape(N, -1).contiguous(), masks.reshape(N, -1).contiguous()
+    packed = pack_decoder_weights_umma(pc)
+    stream = _lib.stream_ptr()
+    rst = _state(dev)
+    sc = _scratch.get((dev.index, stream))
+    if sc is None:
+        sc = _scratch[(dev.index, stream)] = _FrameScratch()
     p_cap = _p_cap_hint.get(dev.index, min(N * K, max(4 * N, 1 << 16)))
     while True:
+        r_cap = max(rst.r_cap_hint, 4 * p_cap, 1 << 16)
+        sc.ensure(L, dev, N, p_cap, r_cap, W, H)
         if nv_dev is None:
-            nv_dev = torch.full((1,), N, dtype=torch.int32, device=dev)
-        raw = generate_raw(pc, viewpoint_camera.camera_center, anchor, feat, offsets2, scaling, masks2, vis_idx=vis_idx,
-                           n_vis=N, nv_dev=nv_dev, out_cap=p_cap)
-        color, radii, saved = rasterize_forward_raw(cs, raw["xyz"], raw["color"], raw["opacity"], raw["scaling"],
-                                                    raw["rot"], count_dev=raw["count"])
-        st = saved["status"].tolist()  # the frame's only synchronisation
+            if sc.n_all is None or int(sc.n_all_n) != N:
+                sc.n_all, sc.n_all_n = torch.full((1,), N, dtype=torch.int32, device=dev), N
+            nv_dev = sc.n_all
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((sc.p_cap,), dtype=torch.int32, device=dev)
+        status = torch.empty((_lib.STATUS_WORDS,), dtype=torch.int32, device=dev)
+        _lib.check(L.cgs_render_anchors_forward(
+            _lib.ctypes.byref(cs), _lib.ptr(packed), _lib.ptr(vis_idx), N, _lib.ptr(nv_dev), sc.p_cap, _lib.ptr(anchor),
+            _lib.ptr(feat), _lib.ptr(offsets2), _lib.ptr(scaling), _lib.ptr(masks2), _lib.ptr(sc.xyz), _lib.ptr(sc.color),
+            _lib.ptr(sc.opacity), _lib.ptr(sc.scaling), _lib.ptr(sc.rot), _lib.ptr(sc.count), _lib.ptr(sc.g1_ws),
+            sc.g1_ws.numel(), sc.r_cap, _lib.ptr(color), _lib.ptr(radii), _lib.ptr(sc.geom), _lib.ptr(sc.point_list),
+            _lib.ptr(sc.ranges), _lib.ptr(sc.final_T), _lib.ptr(sc.n_contrib), _lib.ptr(status), _lib.ptr(sc.ws),
+            sc.ws.numel(), stream), "cgs_render_anchors_forward")
+        # everything the caller gets is enqueued BEFORE the read-back, so no kernel follows the synchronisation
+        vis_filter = radii > 0
+        screenspace = torch.zeros((sc.p_cap, 3), dtype=torch.float32, device=dev)
+        st = status.tolist()  # the frame's only synchronisation
         P, R = st[_lib.STATUS_NUM_GAUSSIANS], st[_lib.STATUS_NUM_RENDERED]
         if P < 0:
             raise _lib.CgsError("cgs_neural_gaussians_umma_forward: a tensor-core completion barrier timed out")
@@ -51,16 +118,17 @@ def _render_inference(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, vi
             p_cap = min(N * K, int(P * 1.25) + 4096)
             continue
         if st[_lib.STATUS_OVERFLOW]:
-            from .rasterizer import _state
-            _state(dev).r_cap_hint = int(R * 1.25) + 4096
+            if R >= 0x7fffffff:
+                raise _lib.CgsError("number of (Gaussian, tile) instances exceeds 2^31")
+            rst.r_cap_hint = int(R * 1.25) + 4096
             continue
         break
     _p_cap_hint[dev.index] = max(p_cap, min(N * K, int(P * 1.25) + 4096))
-    from .rasterizer import _state
-    _state(dev).last_num_rendered = R
+    rst.r_cap_hint = max(rst.r_cap_hint, int(R * 1.25) + 4096)
+    rst.last_num_rendered = R
     radii = radii[:P]
-    return {"render": color, "viewspace_points": torch.zeros((P, 3), dtype=torch.float32, device=dev),
-            "visibility_filter": radii > 0, "radii": radii, "time_sub": 0}
+    return {"render": color, "viewspace_points": screenspace[:P], "visibility_filter": vis_filter[:P], "radii": radii,
+            "time_sub": 0}
 
 
 def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, visible_mask=None, retain_grad=False, step=0):
@@ -95,11 +163,27 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, visible_m
 
 
 def prefilter_voxel(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_color=None):
-    rasterizer = GaussianRasterizer(raster_settings=_settings(viewpoint_camera, pipe, bg_color, scaling_modifier))
-    means3D = pc.get_anchor
-    scales = pc.get_scaling
-    rotations = pc.get_rotation
-    radii_pure = rasterizer.visible_filter(means3D=means3D, scales=scales[:, :3],
-                                           rotations=rotations[[0], :].repeat(means3D.shape[0], 1),
-                                           cov3D_precomp=None)
-    return radii_pure > 0
+    """gaussian_renderer/__init__.py:232-287 -> bool[N].  One fused kernel (cgs_prefilter_anchors): radius test
+    with scales = get_scaling[:, :3] and the rotation of anchor 0 for every anchor, as the reference passes them.
+    The returned mask also carries the compacted index list + device-side count (`_cgs_compact`), which
+    `render` picks up instead of compacting the mask again."""
+    with torch.no_grad():
+        L = _lib.lib()
+        cs = to_c_settings(_settings(viewpoint_camera, pipe, bg_color, scaling_modifier))
+        means3D = pc.get_anchor.detach()
+        scales = pc.get_scaling.detach()
+        rot_row = pc._rotation.detach()[0]
+        if means3D.dtype != torch.float32 or not means3D.is_cuda:
+            raise TypeError("prefilter_voxel: anchors must be float32 CUDA tensors (contextgs_b200 has no CPU path)")
+        means3D, scales, rot_row = means3D.contiguous(), scales.contiguous(), rot_row.contiguous()
+        N, dev = means3D.shape[0], means3D.device
+        vis = torch.empty((N,), dtype=torch.bool, device=dev)
+        idx = torch.empty((max(N, 1),), dtype=torch.int32, device=dev)
+        cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+        ws = torch.empty((L.cgs_prefilter_workspace_bytes(N),), dtype=torch.uint8, device=dev)
+        _lib.check(L.cgs_prefilter_anchors(_lib.ctypes.byref(cs), N, _lib.ptr(means3D), _lib.ptr(scales),
+                                           int(scales.shape[1]), _lib.ptr(rot_row), _lib.ptr(vis), _lib.ptr(idx),
+                                           _lib.ptr(cnt), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "cgs_prefilter_anchors")
+    vis._cgs_compact = (idx, cnt, vis._version)
+    return vis

@@ -91,6 +91,18 @@ CGS_API int cgs_umma_selftest(const float *A, const float *W, int N, int K, int 
 CGS_API int cgs_visible_filter(const cgs_raster_settings *s, int N, const float *means3D, const float *scales,
                        const float *rotations, int32_t *radii, void *stream);
 
+/* `prefilter_voxel` in one pass (gaussian_renderer/__init__.py:232-287): the radius test of
+ * `visible_filter` over all anchors with scales = get_scaling[:, :3] (scales has a row stride of
+ * scale_stride floats, 6 for the reference's [N,6] tensor) and the normalised rotation row
+ * rotation_row[4] applied to every anchor (the reference passes rotations[[0], :].repeat(N, 1)),
+ * fused with the ordered compaction of the visible anchors:
+ *   visible[N] uint8 (the bool mask the reference returns), vis_idx[N] int32 (ascending indices of the
+ *   visible anchors), *count_dev = their number.  workspace: cgs_prefilter_workspace_bytes(N). */
+CGS_API size_t cgs_prefilter_workspace_bytes(int N);
+CGS_API int cgs_prefilter_anchors(const cgs_raster_settings *s, int N, const float *anchor, const float *scales,
+                                  int scale_stride, const float *rotation_row, uint8_t *visible, int32_t *vis_idx,
+                                  int32_t *count_dev, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Replaces `GaussianRasterizer.markVisible(positions)` (upstream checkFrustum). visible[N] uint8. */
 CGS_API int cgs_mark_visible(const cgs_raster_settings *s, int N, const float *means3D, uint8_t *visible, void *stream);
 
@@ -226,6 +238,22 @@ CGS_API int cgs_neural_gaussians_umma_forward_dev(const float *packed_weights, c
                                                   float *o_color, float *o_opacity, float *o_scaling, float *o_rot,
                                                   float *o_neural_opacity, uint8_t *o_mask, int32_t *count_dev,
                                                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* One inference frame after prefilter_voxel = `render` of gaussian_renderer/__init__.py:155-229 on a decoded
+ * model: cgs_neural_gaussians_umma_forward_dev followed by cgs_rasterize_forward_dev on its outputs, enqueued
+ * by ONE call (no host work between the stages).  g_* are the capacity-sized (P_cap rows) Gaussian attribute
+ * buffers written by the first stage and read by the second; g_count (device int32) is the Gaussian count.
+ * All other arguments as in the two entry points. */
+CGS_API int cgs_render_anchors_forward(const cgs_raster_settings *s, const float *packed_weights,
+                                       const int32_t *vis_idx, int Nv_cap, const int32_t *nv_dev, int P_cap,
+                                       const float *anchor, const float *feat, const float *offsets,
+                                       const float *scaling, const float *mask, float *g_xyz, float *g_color,
+                                       float *g_opacity, float *g_scaling, float *g_rot, int32_t *g_count,
+                                       void *g1_workspace, size_t g1_workspace_bytes, int64_t R_cap, float *out_color,
+                                       int32_t *radii, float *geom, uint32_t *point_list, uint32_t *ranges,
+                                       float *final_T, uint32_t *n_contrib, int32_t *status, void *workspace,
+                                       size_t workspace_bytes, void *stream);
+
 
 /* ------------------------------------------------------------------ context / entropy model (E4-E7, G2) */
 

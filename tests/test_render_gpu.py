@@ -10,13 +10,13 @@ from contextgs_b200.renderer import prefilter_voxel, render
 pytestmark = pytest.mark.gpu
 
 
-def _setup(N=30000, W=400, H=240):
-    scene = synthetic.make_scene("chair", N, seed=5, gaussian_scale=4.0)
+def _setup(N=30000, W=400, H=240, kind="chair"):
+    scene = synthetic.make_scene(kind, N, seed=5, gaussian_scale=4.0)
     torch.manual_seed(6)
     pc = GaussianModel.from_tensors(scene, device="cuda")
     pc.replace_with_decoded(**{k: v.cuda() for k, v in synthetic.decoded_scene(scene).items()})
     pc.eval()
-    cams = synthetic.make_cameras("chair", 4, device="cuda", W=W, H=H)
+    cams = synthetic.make_cameras(kind, 4, device="cuda", W=W, H=H)
     pipe = type("Pipe", (), {"debug": False})()
     return pc, cams, pipe, torch.zeros(3, device="cuda")
 
@@ -64,3 +64,52 @@ def test_compact_positive_i32_matches_nonzero():
                                               _lib.stream_ptr()), "cgs_compact_positive_i32")
         ref = torch.nonzero(v > 0)[:, 0].to(torch.int32)
         assert int(cnt.item()) == ref.numel() and torch.equal(idx[: ref.numel()], ref)
+
+
+def test_prefilter_voxel_fused_equals_visible_filter():
+    """cgs_prefilter_anchors (fused radius test + compaction) against the reference's own call sequence
+    (gaussian_renderer/__init__.py:250-287): visible_filter(get_anchor, get_scaling[:, :3], rotation row 0
+    repeated) > 0, and against the CPU oracle's radii."""
+    import numpy as np
+    from contextgs_b200.rasterizer import GaussianRasterizer
+    from oracle import raster_ref
+    pc, cams, pipe, bg = _setup(N=20011, kind="bicycle")   # cameras inside the scene: part of the anchors is culled
+    partial = 0
+    with torch.no_grad():
+        pc._rotation[0] = torch.tensor([0.9, 0.1, -0.3, 0.2], device="cuda")   # non-trivial row 0 (normalised inside)
+    for cam in cams:
+        vis = prefilter_voxel(cam, pc, pipe, bg)
+        rast = GaussianRasterizer(renderer._settings(cam, pipe, bg, 1.0))
+        rots = pc.get_rotation[[0], :].repeat(pc.get_anchor.shape[0], 1)
+        radii = rast.visible_filter(pc.get_anchor, pc.get_scaling[:, :3], rots)
+        assert vis.dtype == torch.bool and torch.equal(vis, radii > 0)
+        idx, cnt, ver = vis._cgs_compact
+        ref_idx = torch.nonzero(vis)[:, 0].to(torch.int32)
+        assert int(cnt.item()) == ref_idx.numel() and torch.equal(idx[: ref_idx.numel()], ref_idx)
+        st = raster_ref.make_settings(cam.image_width, cam.image_height, np.tan(cam.FoVx * 0.5), np.tan(cam.FoVy * 0.5),
+                                      (0, 0, 0), 1.0, cam.world_view_transform.cpu().numpy(),
+                                      cam.full_proj_transform.cpu().numpy())
+        o_radii = raster_ref.preprocess(st, pc.get_anchor.detach().cpu().numpy(),
+                                        pc.get_scaling[:, :3].detach().contiguous().cpu().numpy(),
+                                        rots.detach().cpu().numpy(), filter_only=True)
+        assert np.array_equal(o_radii > 0, vis.cpu().numpy())
+        assert int(cnt.item()) > 0
+        partial += int(cnt.item()) < vis.numel()
+    assert partial > 0
+
+
+def test_render_accepts_plain_and_modified_masks():
+    """A mask that did not come from prefilter_voxel (or was modified afterwards) is compacted again."""
+    pc, cams, pipe, bg = _setup()
+    cam = cams[1]
+    with torch.no_grad():
+        vis = prefilter_voxel(cam, pc, pipe, bg)
+        ref = render(cam, pc, pipe, bg, visible_mask=vis)
+        plain = render(cam, pc, pipe, bg, visible_mask=vis.clone())
+        assert torch.equal(plain["render"], ref["render"])
+        vis2 = prefilter_voxel(cam, pc, pipe, bg)
+        vis2[::2] = False                                   # in-place edit invalidates the cached index list
+        a = render(cam, pc, pipe, bg, visible_mask=vis2)
+        b = render(cam, pc, pipe, bg, visible_mask=vis2.clone())
+        assert torch.equal(a["render"], b["render"]) and a["radii"].shape == b["radii"].shape
+        assert a["radii"].shape[0] < ref["radii"].shape[0]
