@@ -162,10 +162,10 @@ ALGO_BYTES = {
     "neural_gaussians_fwd": lambda c: 396 * c["Nv"] + 50 * c["Nv"] + 56 * c["P"],
     "preprocess": lambda c: 116 * c["P"],
     "depth_sort": lambda c: c["P"] * (4 + 4 * 16),
-    "scan_tiles": lambda c: 12 * c["P"],
-    "emit_instances": lambda c: 20 * c["P"] + 8 * c["R"],
-    "tile_sort": lambda c: c["R"] * (4 + 2 * 16),
-    "tile_ranges": lambda c: 4 * c["R"] + 8 * c["tiles"],
+    # binning (csrc/raster_binning.cu): S = (super-tile, Gaussian) pairs, ~1.4 per Gaussian
+    "scan_emit_pairs": lambda c: 12 * c["P"] + 8 * c["S"],
+    "pair_sort": lambda c: c["S"] * (4 + 16 * max(1, -(-max(1, (c["supertiles"] - 1).bit_length()) // 8))),
+    "bin_expand": lambda c: 2 * 16 * c["S"] + 4 * c["R"] + 12 * c["tiles"],
     "render_fwd": lambda c: 40 * c["R"] + 20 * c["W"] * c["H"],
     "render_bwd": lambda c: 40 * c["R"] + 20 * c["W"] * c["H"] + 44 * c["P"],
     "preprocess_bwd": lambda c: 140 * c["P"],
@@ -384,6 +384,8 @@ def main():
     from contextgs_b200 import rasterizer as _r
     st = _r._state(dev)
     counts["R"] = int(getattr(st, "last_num_rendered", 0) or 0)
+    counts["S"] = int(getattr(st, "last_num_pairs", 0) or 0)
+    counts["supertiles"] = ((W + 127) // 128) * ((H + 63) // 64)
     per_frame = {k: stage_ms[k] / n_prof for k in stage_ms if stage_n[k] > 0}
     top = max(per_frame, key=per_frame.get)
     peak, peak_src = peaks()

@@ -30,7 +30,7 @@ class RasterSettings(ctypes.Structure):
 
 
 STATUS_NUM_RENDERED, STATUS_OVERFLOW, STATUS_NUM_SORTED, STATUS_WORDS = 0, 1, 2, 8
-STATUS_NUM_GAUSSIANS, STATUS_GAUSSIAN_OVERFLOW = 3, 4
+STATUS_NUM_GAUSSIANS, STATUS_GAUSSIAN_OVERFLOW, STATUS_NUM_PAIRS = 3, 4, 5
 GEOM_STRIDE = 12
 
 # name -> (restype, argtypes); every symbol declared in include/contextgs_b200.h

@@ -33,7 +33,7 @@ int check_launch(const char *what)
 // ---- stage timing --------------------------------------------------------------------------
 static const char *const kStageNames[ST_COUNT] = {
     "visible_filter", "compact_indices", "neural_gaussians_fwd", "neural_gaussians_bwd", "preprocess", "depth_sort",
-    "scan_tiles", "emit_instances", "tile_sort", "tile_ranges", "render_fwd", "render_bwd", "preprocess_bwd",
+    "scan_emit_pairs", "bin_expand", "pair_sort", "tile_ranges", "render_fwd", "render_bwd", "preprocess_bwd",
     "entropy_bottleneck", "context_level_fwd", "context_level_bwd", "gaussian_bits", "elementwise", "level_divide"};
 
 struct StageTimer {
@@ -73,18 +73,19 @@ StageScope::~StageScope()
 
 // launchers defined in the kernel translation units
 void launch_preprocess(const CamParams &, int, const uint32_t *, const float *, const float *, const float *,
-                       const float *, const float *, int32_t *, float *, uint32_t *, cudaStream_t);
+                       const float *, const float *, int32_t *, float *, uint32_t *, uint2 *, cudaStream_t);
 void launch_filter(const CamParams &, int, const float *, const float *, const float *, int32_t *, cudaStream_t);
 void launch_mark_visible(const CamParams &, int, const float *, uint8_t *, cudaStream_t);
 void launch_prefilter_anchors(const CamParams &, int, const float *, const float *, int, const float *, uint8_t *, int *,
                               unsigned long long *, uint32_t *, int32_t *, cudaStream_t);
 void launch_preprocess_backward(const CamParams &, int, const float *, const float *, const float *, const int32_t *,
                                 const float *, float *, float *, float *, float *, float *, float *, cudaStream_t);
-void launch_scan_tiles(const uint32_t *, const float *, int, const uint32_t *, int64_t, uint32_t *,
-                       unsigned long long *, uint32_t *, int32_t *, cudaStream_t);
-void launch_emit_instances(const uint32_t *, const float *, const uint32_t *, int, const uint32_t *, int, int, int64_t,
-                           uint32_t *, uint32_t *, cudaStream_t);
-void launch_tile_ranges(const uint32_t *, const int32_t *, int64_t, uint32_t *, cudaStream_t);
+void launch_scan_emit_pairs(const uint32_t *, const uint2 *, int, const uint32_t *, int64_t, int, uint32_t *, uint32_t *,
+                            unsigned long long *, uint32_t *, unsigned long long *, uint32_t *, uint32_t *, int32_t *,
+                            cudaStream_t);
+int bin_chunks_cap(int64_t R_cap);
+void launch_bin_expand(const uint32_t *, const uint32_t *, const uint2 *, const uint32_t *, int64_t, int, int, uint32_t *,
+                       uint32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, cudaStream_t);
 int scan_tiles_count(int P);
 void launch_render_forward(const CamParams &, const uint32_t *, const uint32_t *, const float *, float *, float *,
                            uint32_t *, cudaStream_t);
@@ -112,31 +113,37 @@ static int tile_bits(int tiles)
 // Workspace layout of the forward pass.  Everything that must start at zero is grouped at the
 // front so that one memset covers it.
 struct RasterPlan {
-    SortPlan depth_sort, tile_sort;
-    size_t depth_ws_off, tile_ws_off, scan_state_off, scan_ticket_off, zero_bytes;
-    size_t depth_keys_off[3], depth_vals_off[2], offsets_off;  // keys: in / tmp / out ; vals: tmp / out
-    size_t tile_keys_off[3], tile_vals_off[2];                 // keys: in / tmp / out ; vals: in / tmp
+    SortPlan depth_sort, pair_sort;
+    size_t depth_ws_off, pair_ws_off, scan_state_off, scan_ticket_off, tile_total_off, seg_off, zero_bytes;
+    size_t depth_keys_off[3], depth_vals_off[2], rects_off;    // keys: in / tmp / out ; vals: tmp / out
+    size_t pair_keys_off[3], pair_vals_off[3];                 // in / tmp / out
+    size_t tail_cnt_off, run_prefix_off, tile_start_off;
     size_t total;
-    int tbits;
+    int sbits, num_super;
 };
 
 static RasterPlan make_plan(int P, int64_t R_cap, int W, int H)
 {
     RasterPlan p;
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
-    p.tbits = tile_bits(gx * gy);
+    p.num_super = ((gx + CGS_SUPER_X - 1) / CGS_SUPER_X) * ((gy + CGS_SUPER_Y - 1) / CGS_SUPER_Y);
+    p.sbits = tile_bits(p.num_super);
     const int64_t Pc = P > 0 ? P : 1, Rc = R_cap > 0 ? R_cap : 1;
     p.depth_sort = make_sort_plan(Pc, 0, 32);
-    p.tile_sort = make_sort_plan(Rc, 0, p.tbits);
+    p.pair_sort = make_sort_plan(Rc, 0, p.sbits);
     size_t off = 0;
     p.depth_ws_off = off;
     off += p.depth_sort.total_bytes;
-    p.tile_ws_off = off;
-    off += p.tile_sort.total_bytes;
+    p.pair_ws_off = off;
+    off += p.pair_sort.total_bytes;
     p.scan_state_off = off;
     off += align_up((size_t)scan_tiles_count((int)Pc) * sizeof(unsigned long long));
-    p.scan_ticket_off = off;
-    off += align_up(4 * sizeof(uint32_t));
+    p.scan_ticket_off = off;   // ticket, P, pair count, done counter, [4..5] 64-bit instance accumulator
+    off += align_up(8 * sizeof(uint32_t));
+    p.tile_total_off = off;
+    off += align_up((size_t)gx * gy * sizeof(uint32_t));
+    p.seg_off = off;           // list begin / end per super-tile
+    off += align_up((size_t)p.num_super * 2 * sizeof(uint32_t));
     p.zero_bytes = off;
     for (int i = 0; i < 3; ++i) {
         p.depth_keys_off[i] = off;
@@ -146,16 +153,23 @@ static RasterPlan make_plan(int P, int64_t R_cap, int W, int H)
         p.depth_vals_off[i] = off;
         off += align_up((size_t)Pc * 4);
     }
-    p.offsets_off = off;
-    off += align_up((size_t)Pc * 4);
+    p.rects_off = off;
+    off += align_up((size_t)Pc * 8);
     for (int i = 0; i < 3; ++i) {
-        p.tile_keys_off[i] = off;
+        p.pair_keys_off[i] = off;
         off += align_up((size_t)Rc * 4);
     }
-    for (int i = 0; i < 2; ++i) {
-        p.tile_vals_off[i] = off;
+    for (int i = 0; i < 3; ++i) {
+        p.pair_vals_off[i] = off;
         off += align_up((size_t)Rc * 4);
     }
+    const size_t chunks = (size_t)bin_chunks_cap(Rc) + 2;
+    p.tail_cnt_off = off;
+    off += align_up(chunks * 32 * sizeof(uint32_t));
+    p.run_prefix_off = off;
+    off += align_up(chunks * 32 * sizeof(uint32_t));
+    p.tile_start_off = off;
+    off += align_up((size_t)gx * gy * sizeof(uint32_t));
     p.total = off;
     return p;
 }
@@ -349,8 +363,8 @@ extern "C" int cgs_rasterize_forward_dev(const cgs_raster_settings *s, int P, co
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const CamParams cam = make_cam(s);
     const int tiles = cam.grid_x * cam.grid_y;
-    if (P < 0 || R_cap < 0) {
-        set_error("%s: negative size", __func__);
+    if (P < 0 || R_cap < 0 || R_cap >= (1ll << 30)) {
+        set_error("%s: invalid size (P %d, R_cap %lld; R_cap must be in [0, 2^30))", __func__, P, (long long)R_cap);
         return -2;
     }
     cudaMemsetAsync(status, 0, CGS_STATUS_WORDS * sizeof(int32_t), st);
@@ -376,20 +390,24 @@ extern "C" int cgs_rasterize_forward_dev(const cgs_raster_settings *s, int P, co
         uint32_t *dkeys_in = u32(plan.depth_keys_off[0]), *dkeys_tmp = u32(plan.depth_keys_off[1]);
         uint32_t *dkeys_out = u32(plan.depth_keys_off[2]);
         uint32_t *dvals_tmp = u32(plan.depth_vals_off[0]), *order = u32(plan.depth_vals_off[1]);
-        uint32_t *offsets = u32(plan.offsets_off);
-        uint32_t *tkeys_in = u32(plan.tile_keys_off[0]), *tkeys_tmp = u32(plan.tile_keys_off[1]);
-        uint32_t *tkeys_out = u32(plan.tile_keys_off[2]);
-        uint32_t *tvals_in = u32(plan.tile_vals_off[0]), *tvals_tmp = u32(plan.tile_vals_off[1]);
+        uint2 *rects = reinterpret_cast<uint2 *>(ws + plan.rects_off);
+        uint32_t *pkeys_in = u32(plan.pair_keys_off[0]), *pkeys_tmp = u32(plan.pair_keys_off[1]);
+        uint32_t *pkeys_out = u32(plan.pair_keys_off[2]);
+        uint32_t *pvals_in = u32(plan.pair_vals_off[0]), *pvals_tmp = u32(plan.pair_vals_off[1]);
+        uint32_t *pvals_out = u32(plan.pair_vals_off[2]);
         unsigned long long *scan_state = reinterpret_cast<unsigned long long *>(ws + plan.scan_state_off);
         uint32_t *scan_ticket = reinterpret_cast<uint32_t *>(ws + plan.scan_ticket_off);
-        // the element count of the depth sort is P (host-known); park it in the zeroed ticket block
-        uint32_t *p_dev = scan_ticket + 1;
+        // device-side counts parked in the zeroed ticket block
+        uint32_t *p_dev = scan_ticket + 1, *n_pairs_dev = scan_ticket + 2, *scan_done = scan_ticket + 3;
+        unsigned long long *r_acc = reinterpret_cast<unsigned long long *>(scan_ticket + 4);
+        uint32_t *tile_total = u32(plan.tile_total_off), *seg_begin = u32(plan.seg_off);
+        uint32_t *seg_end = seg_begin + plan.num_super;
 
         {
             StageScope sc(ST_PREPROCESS, st, 2);
             if (P_dev) copy_count_kernel<<<1, 1, 0, st>>>(p_dev, P_dev, (uint32_t)P, status);
             else set_u32_kernel<<<1, 1, 0, st>>>(p_dev, (uint32_t)P);
-            launch_preprocess(cam, P, p_dev, means3D, colors, opacities, scales, rotations, radii, geom, dkeys_in, st);
+            launch_preprocess(cam, P, p_dev, means3D, colors, opacities, scales, rotations, radii, geom, dkeys_in, rects, st);
         }
         // 1. Gaussians by depth (value = Gaussian id, implicit iota on the first pass)
         {
@@ -398,28 +416,25 @@ extern "C" int cgs_rasterize_forward_dev(const cgs_raster_settings *s, int P, co
                                    ws + plan.depth_ws_off, false, st))
                 return e;
         }
-        // 2. instance offsets in depth order, R stays on the device
+        // 2. (super-tile, id) pairs in depth order; R and the pair count stay on the device
         {
             StageScope sc(ST_SCAN, st, 1);
-            launch_scan_tiles(order, geom, P, p_dev, R_cap, offsets, scan_state, scan_ticket, status, st);
+            launch_scan_emit_pairs(order, rects, P, p_dev, R_cap, (cam.grid_x + CGS_SUPER_X - 1) / CGS_SUPER_X, pkeys_in,
+                                   pvals_in, scan_state, scan_ticket, r_acc, scan_done, n_pairs_dev, status, st);
         }
         if (R_cap > 0) {
-            // 3. emit (tile, id)
+            // 3. stable sort of the pairs by super-tile
             {
-                StageScope sc(ST_EMIT, st, 1);
-                launch_emit_instances(order, geom, offsets, P, p_dev, cam.grid_x, cam.grid_y, R_cap, tkeys_in, tvals_in,
-                                      st);
-            }
-            // 4. stable sort by tile id; last pass writes the ids straight into point_list
-            const uint32_t *n_sorted = reinterpret_cast<const uint32_t *>(status + CGS_STATUS_NUM_SORTED);
-            {
-                StageScope sc(ST_TILE_SORT, st, 2 + plan.tile_sort.npass);
-                if (int e = sort_pairs(tkeys_in, tvals_in, tkeys_out, point_list, tkeys_tmp, tvals_tmp, n_sorted, R_cap,
-                                       0, plan.tbits, ws + plan.tile_ws_off, false, st))
+                StageScope sc(ST_TILE_SORT, st, 2 + plan.pair_sort.npass);
+                if (int e = sort_pairs(pkeys_in, pvals_in, pkeys_out, pvals_out, pkeys_tmp, pvals_tmp, n_pairs_dev, R_cap, 0,
+                                       plan.sbits, ws + plan.pair_ws_off, false, st))
                     return e;
             }
-            StageScope sc(ST_RANGES, st, 1);
-            launch_tile_ranges(tkeys_out, status, R_cap, ranges, st);
+            // 4. expansion into per-tile lists + ranges
+            StageScope sc(ST_EMIT, st, 4);
+            launch_bin_expand(pkeys_out, pvals_out, rects, n_pairs_dev, R_cap, cam.grid_x, cam.grid_y,
+                              u32(plan.tail_cnt_off), u32(plan.run_prefix_off), seg_begin, seg_end, tile_total,
+                              u32(plan.tile_start_off), ranges, point_list, st);
         }
     }
     {

@@ -98,7 +98,8 @@ __device__ __forceinline__ float3 load3(const float *p, int i)
 
 // Shared front half of preprocess / filter: returns radius (0 = culled) and fills the outputs.
 __device__ __forceinline__ int project_one(const CamParams &cam, const float3 p, const float3 scale, const float4 q,
-                                           float &px, float &py, float &depth, float3 &conic, int &tiles)
+                                           float &px, float &py, float &depth, float3 &conic, int &tiles,
+                                           uint2 *rect = nullptr)
 {
     const float *vm = cam.view, *pm = cam.proj;
     const float vz = vm[2] * p.x + vm[6] * p.y + vm[10] * p.z + vm[14];
@@ -126,6 +127,7 @@ __device__ __forceinline__ int project_one(const CamParams &cam, const float3 p,
     get_rect(px, py, radius, cam.grid_x, cam.grid_y, x0, y0, x1, y1);
     tiles = (x1 - x0) * (y1 - y0);
     if (tiles == 0) return 0;
+    if (rect) *rect = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
     depth = vz;
     conic = make_float3(cz * det_inv, -cy * det_inv, cx * det_inv);
     return radius;
@@ -134,7 +136,8 @@ __device__ __forceinline__ int project_one(const CamParams &cam, const float3 p,
 __global__ void __launch_bounds__(256)
 preprocess_kernel(CamParams cam, const uint32_t *__restrict__ p_dev, const float *__restrict__ means, const float *__restrict__ colors,
                   const float *__restrict__ opac, const float *__restrict__ scales, const float *__restrict__ rots,
-                  int32_t *__restrict__ radii, float *__restrict__ geom, uint32_t *__restrict__ depth_keys)
+                  int32_t *__restrict__ radii, float *__restrict__ geom, uint32_t *__restrict__ depth_keys,
+                  uint2 *__restrict__ rects)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int)*p_dev) return;  // P lives on the device: the host only knows a capacity
@@ -144,7 +147,9 @@ preprocess_kernel(CamParams cam, const uint32_t *__restrict__ p_dev, const float
     float px = 0.f, py = 0.f, depth = 0.f;
     float3 conic = make_float3(0.f, 0.f, 0.f);
     int tiles = 0;
-    const int radius = project_one(cam, p, sc, q, px, py, depth, conic, tiles);
+    uint2 rect = make_uint2(0u, 0u);   // tile rectangle {x0 | x1 << 16, y0 | y1 << 16}: all the binning stages need
+    const int radius = project_one(cam, p, sc, q, px, py, depth, conic, tiles, &rect);
+    rects[i] = radius > 0 ? rect : make_uint2(0u, 0u);
     float4 *g = reinterpret_cast<float4 *>(geom + (size_t)i * kGeomStride);
     if (radius > 0) {
         const float3 c = load3(colors, i);
@@ -376,11 +381,11 @@ preprocess_backward_kernel(CamParams cam, int P, const float *__restrict__ means
 // ---- launchers used by raster_api.cu ---------------------------------------------------
 void launch_preprocess(const CamParams &cam, int P_cap, const uint32_t *p_dev, const float *means, const float *colors,
                        const float *opac, const float *scales, const float *rots, int32_t *radii, float *geom,
-                       uint32_t *depth_keys, cudaStream_t st)
+                       uint32_t *depth_keys, uint2 *rects, cudaStream_t st)
 {
     if (P_cap <= 0) return;
     preprocess_kernel<<<(P_cap + 255) / 256, 256, 0, st>>>(cam, p_dev, means, colors, opac, scales, rots, radii, geom,
-                                                           depth_keys);
+                                                           depth_keys, rects);
 }
 
 void launch_filter(const CamParams &cam, int N, const float *means, const float *scales, const float *rots,

@@ -79,6 +79,7 @@ class _DeviceState:
         self.workspace = None
         self.r_cap_hint = 0
         self.last_num_rendered = None
+        self.last_num_pairs = None
 
 
 _states = {}
@@ -144,7 +145,7 @@ def rasterize_forward_raw(c_settings, means3D, colors, opacities, scales, rotati
         if not sync:
             num_rendered = None
             break
-        host = status[:3].tolist()  # the one host read-back (upstream does it mid-pipeline)
+        host = status.tolist()  # the one host read-back (upstream does it mid-pipeline)
         num_rendered = host[_lib.STATUS_NUM_RENDERED]
         if not host[_lib.STATUS_OVERFLOW]:
             break
@@ -153,6 +154,7 @@ def rasterize_forward_raw(c_settings, means3D, colors, opacities, scales, rotati
         r_cap = int(num_rendered * 1.25) + 4096
     if num_rendered is not None:
         st.last_num_rendered = num_rendered
+        st.last_num_pairs = host[_lib.STATUS_NUM_PAIRS]
     st.r_cap_hint = max(st.r_cap_hint, min(r_cap, int((num_rendered or r_cap) * 1.5) + 4096))
     saved = dict(geom=geom, point_list=point_list, ranges=ranges, final_T=final_T, n_contrib=n_contrib, status=status,
                  num_rendered=num_rendered, r_cap=r_cap)

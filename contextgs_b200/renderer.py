@@ -126,6 +126,7 @@ def _render_inference(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, vi
     _p_cap_hint[dev.index] = max(p_cap, min(N * K, int(P * 1.25) + 4096))
     rst.r_cap_hint = max(rst.r_cap_hint, int(R * 1.25) + 4096)
     rst.last_num_rendered = R
+    rst.last_num_pairs = st[_lib.STATUS_NUM_PAIRS]
     radii = radii[:P]
     return {"render": color, "viewspace_points": screenspace[:P], "visibility_filter": vis_filter[:P], "radii": radii,
             "time_sub": 0}

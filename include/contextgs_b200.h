@@ -32,6 +32,8 @@ extern "C" {
 #define CGS_ABI_VERSION 1
 #define CGS_TILE 16            /* tile edge in pixels */
 #define CGS_GEOM_STRIDE 12     /* floats per packed per-Gaussian record (48 B) */
+#define CGS_SUPER_X 8          /* binning super-tile: 8 x 4 tiles (one 32-bit footprint mask per Gaussian) */
+#define CGS_SUPER_Y 4
 
 /* Field-for-field mirror of `GaussianRasterizationSettings`
  * (reference: gaussian_renderer/__init__.py:179-192 and :250-263).
@@ -59,6 +61,7 @@ enum {
     CGS_STATUS_NUM_SORTED = 2,   /* min(R, R_cap) */
     CGS_STATUS_NUM_GAUSSIANS = 3,      /* cgs_rasterize_forward_dev: *P_dev as read on the device */
     CGS_STATUS_GAUSSIAN_OVERFLOW = 4,  /* 1 if *P_dev exceeded the capacity P the buffers were sized for */
+    CGS_STATUS_NUM_PAIRS = 5,          /* (super-tile, Gaussian) pairs the binning sorted (<= num_rendered) */
     CGS_STATUS_WORDS = 8
 };
 
@@ -120,9 +123,11 @@ CGS_API size_t cgs_raster_workspace_bytes(int P, int64_t R_cap, int W, int H);
  *        ranges[tiles,2]   uint32  [first, last+1) per tile
  *        final_T[H,W], n_contrib[H,W] uint32
  *        status[CGS_STATUS_WORDS] int32 (device)
- * Pipeline: preprocess -> 4-pass radix sort of Gaussians by depth -> look-back scan of
- * tiles_touched in depth order -> emit (tile, id) -> radix sort by tile id -> ranges -> blend.
- * The resulting point_list/ranges are identical to the classical 64-bit (tile<<32|depth) sort. */
+ * Pipeline: preprocess -> 4-pass radix sort of Gaussians by depth -> look-back scan in depth order
+ * emitting one (super-tile, id) pair per covered 8x4-tile super-tile -> radix sort of the pairs by
+ * super-tile -> ballot-ranked expansion into per-tile lists + ranges -> blend (csrc/raster_binning.cu).
+ * The resulting point_list/ranges are identical to the classical 64-bit (tile<<32|depth) sort.
+ * R_cap must be below 2^30. */
 CGS_API int cgs_rasterize_forward(const cgs_raster_settings *s, int P, const float *means3D, const float *colors,
                           const float *opacities, const float *scales, const float *rotations, int64_t R_cap,
                           float *out_color, int32_t *radii, float *geom, uint32_t *point_list, uint32_t *ranges,
