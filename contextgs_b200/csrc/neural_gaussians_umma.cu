@@ -4,15 +4,17 @@
 // decoder MLPs scene/gaussian_model.py:153-174), but the two MLP layers run as 3xTF32 tcgen05.mma
 // (fp32-grade accuracy, see umma.cuh) with every activation resident in TENSOR MEMORY:
 //
-//   persistent CTA (one per SM, 256 threads = 8 warps), tile = 128 anchors = 128 TMEM lanes;
-//   thread (row = 32*(warp%4) + lane, half = warp/4): two threads share a row and split its columns.
+//   persistent CTA (one per SM, 512 threads = 16 warps), tile = 128 anchors = 128 TMEM lanes;
+//   thread (row = 32*(warp%4) + lane, quarter = warp/4): FOUR threads share a row and split its columns
+//   and its ten offsets (3 + 3 + 2 + 2).  The kernel is bound by the issue latency of the epilogues, not by
+//   the tensor core or HBM, so four warps per scheduler (instead of two) is what buys time.
 //
 //   TMEM columns (496 of 512):
 //     [  0,176)  layer-1 input  x_hi [0,56) | x_lo [56,112)      -> later hidden_lo [0,176)
 //     [176,352)  layer-1 accumulator D1 (3 heads x 56: 50 units + 6 zero pads, + 8 pad)
 //                -> overwritten IN PLACE by hidden_hi = tf32(relu(D1 + b1))
 //     [352,496)  layer-2 accumulators: opacity 16 | color 48 | cov 80
-//   shared memory (137 KB): W1 hi/lo [14][176][4], W2 per head hi/lo [14][N_h][4], biases.
+//   shared memory (145 KB weights + 77 KB staging): W1 hi/lo [14][176][4], W2 per head hi/lo [14][N_h][4], biases.
 //
 //   per tile:  load + split rows -> tcgen05.st  |  21 MMAs (128x176x8)  |  ReLU epilogue in TMEM
 //              |  63 MMAs (128x{16,32,80}x8)    |  selection, ordered compaction (block scan +
@@ -27,12 +29,13 @@ namespace cgs {
 namespace ngu {
 constexpr int kFeat = 50, kK = 10;
 constexpr int kRows = 128;                  // anchors per tile
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kK1 = 56;                     // 54 inputs padded to a multiple of 8
 constexpr int kHeadStride = 56;             // hidden units per head incl. zero pads
 constexpr int kN1 = 176;                    // 3 * 56 = 168 padded to a multiple of 16
+constexpr int kQCols = kN1 / 4;             // 44 hidden columns per quarter in the ReLU epilogue
 // layer-2 output widths.  Output columns are arranged so that every thread's tcgen05.ld starts on
-// an aligned column: opacity of offset k at column 8*(k/5) + k%5, colour channel c of offset k
+// an aligned column: opacity of the j-th offset of quarter q at column 4q + j, colour channel c of offset k
 // at 4k + c, covariance value i of offset k at 8k + i (the host packs W2 / b2 rows accordingly).
 constexpr int kNo = 16, kNc = 48, kNv = 80;
 // TMEM columns
@@ -52,6 +55,10 @@ constexpr int kOffB2o = kOffB1 + kN1, kOffB2c = kOffB2o + kNo, kOffB2v = kOffB2c
 constexpr int kPacked = kOffB2v + kNv;      // 36160 floats = 144640 B
 
 constexpr int kTileGauss = kRows * kK;       // 1280 (anchor, offset) pairs per tile
+constexpr int kMaxOff = 3;                   // offsets per thread: quarters own {0,1,2} {3,4,5} {6,7} {8,9}
+
+__device__ __forceinline__ int quarter_first(int q) { return q == 0 ? 0 : q == 1 ? 3 : q == 2 ? 6 : 8; }
+__device__ __forceinline__ int quarter_count(int q) { return q < 2 ? 3 : 2; }
 
 struct Smem {
     float w[kPacked];
@@ -61,7 +68,7 @@ struct Smem {
     float4 o_rot[kTileGauss];
     float o_nop[kTileGauss];
     uint8_t o_keep[kTileGauss];
-    uint32_t cnt[kThreads];       // kept Gaussians per (row, half), index = row*2 + half
+    uint32_t cnt[kThreads];       // kept Gaussians per (row, quarter), index = row*4 + quarter
     uint32_t excl[kThreads];
     uint32_t wsum[kThreads / 32];
     uint32_t tile_base, tile_total;
@@ -70,62 +77,99 @@ struct Smem {
     alignas(8) uint64_t bar[3];
 };
 
-// Everything one thread reads from HBM for one tile row (its half of the MLP input + what its five
+// Everything one thread reads from HBM for one tile row (its quarter of the MLP input + what its
 // offsets need in the last epilogue).  Loaded one tile AHEAD into registers so that the ~1 us of
 // HBM latency hides behind the previous tile's MMAs and epilogues.
 struct RowInputs {
-    float x[32];      // half 0: feat[0..31]; half 1: feat[32..49], view dir (3), distance, 0, 0, ...
-    float mask[5];
-    float off[15];
+    float x[16];      // quarters 0-2: feat[16q .. 16q+15]; quarter 3: feat[48], feat[49], view dir (3), distance, 0, 0
+    float mask[kMaxOff];
+    float off[3 * kMaxOff];
     float anchor[3];
     float sc[6];
     int a;            // source anchor (-1: padding row)
 };
 
-__device__ __forceinline__ void load_row(RowInputs &r, int a, int half, const float *__restrict__ anchor,
-                                         const float *__restrict__ feat, const float *__restrict__ offsets,
-                                         const float *__restrict__ scaling, const float *__restrict__ mask, float cx,
-                                         float cy, float cz)
+// The loads are split in two parts issued at different points of the tile loop (the load/store unit throttles
+// when 512 threads issue ~40 loads each at once -- ncu r01: 31 % of the samples sat on these instructions),
+// and use 64-bit accesses wherever the reference's row strides (200 / 120 / 40 / 24 B) keep them aligned.
+__device__ __forceinline__ void load_row_feat(RowInputs &r, int a, int q, const float *__restrict__ feat)
 {
     r.a = a;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) r.x[j] = 0.f;
+    for (int j = 0; j < 16; ++j) r.x[j] = 0.f;
     if (a < 0) return;
     const float2 *f2 = reinterpret_cast<const float2 *>(feat + (size_t)a * kFeat);
-    if (half == 0) {
+    if (q < 3) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float2 v = __ldg(f2 + j);
+        for (int j = 0; j < 8; ++j) {
+            const float2 v = __ldg(f2 + 8 * q + j);
             r.x[2 * j] = v.x;
             r.x[2 * j + 1] = v.y;
         }
     } else {
-#pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            const float2 v = __ldg(f2 + 16 + j);
-            r.x[2 * j] = v.x;
-            r.x[2 * j + 1] = v.y;
-        }
+        const float2 v = __ldg(f2 + 24);
+        r.x[0] = v.x;
+        r.x[1] = v.y;
     }
+}
+
+__device__ __forceinline__ void load_row_rest(RowInputs &r, int q, const float *__restrict__ anchor,
+                                              const float *__restrict__ offsets, const float *__restrict__ scaling,
+                                              const float *__restrict__ mask)
+{
+    const int a = r.a;
+#pragma unroll
+    for (int j = 0; j < kMaxOff; ++j) r.mask[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3 * kMaxOff; ++j) r.off[j] = 0.f;
+    if (a < 0) return;
 #pragma unroll
     for (int i = 0; i < 3; ++i) r.anchor[i] = __ldg(anchor + 3 * (size_t)a + i);
+    {
+        const float2 *s2 = reinterpret_cast<const float2 *>(scaling + 6 * (size_t)a);   // 24-byte rows: 8-byte aligned
 #pragma unroll
-    for (int i = 0; i < 6; ++i) r.sc[i] = __ldg(scaling + 6 * (size_t)a + i);
-    const int kbase = 5 * half;
+        for (int i = 0; i < 3; ++i) {
+            const float2 v = __ldg(s2 + i);
+            r.sc[2 * i] = v.x;
+            r.sc[2 * i + 1] = v.y;
+        }
+    }
+    const int kbase = quarter_first(q);
+    const float *mp = mask + (size_t)a * kK + kbase;
+    const float *op = offsets + ((size_t)a * kK + kbase) * 3;
+    if (q == 0) {          // offsets 0,1,2: mask 3 floats at +0 B, offsets 9 floats at +0 B (rows of 40 / 120 B)
+        const float2 m = __ldg(reinterpret_cast<const float2 *>(mp));
+        r.mask[0] = m.x; r.mask[1] = m.y; r.mask[2] = __ldg(mp + 2);
 #pragma unroll
-    for (int j = 0; j < 5; ++j) r.mask[j] = __ldg(mask + (size_t)a * kK + kbase + j);
+        for (int j = 0; j < 4; ++j) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(op) + j);
+            r.off[2 * j] = v.x; r.off[2 * j + 1] = v.y;
+        }
+        r.off[8] = __ldg(op + 8);
+    } else if (q == 1) {   // offsets 3,4,5: +12 B / +36 B, only 4-byte aligned
 #pragma unroll
-    for (int j = 0; j < 15; ++j) r.off[j] = __ldg(offsets + ((size_t)a * kK + kbase) * 3 + j);
+        for (int j = 0; j < 3; ++j) r.mask[j] = __ldg(mp + j);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) r.off[j] = __ldg(op + j);
+    } else {               // offsets 6,7 / 8,9: mask 2 floats at +24 / +32 B, offsets 6 floats at +72 / +96 B
+        const float2 m = __ldg(reinterpret_cast<const float2 *>(mp));
+        r.mask[0] = m.x; r.mask[1] = m.y;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(op) + j);
+            r.off[2 * j] = v.x; r.off[2 * j + 1] = v.y;
+        }
+    }
 }
 
 // view direction / distance (gaussian_renderer/__init__.py:106-110) -- computed when the row is staged,
 // not when it is loaded, so that nothing waits on the prefetch
-__device__ __forceinline__ void finish_row(RowInputs &r, int half, float cx, float cy, float cz)
+__device__ __forceinline__ void finish_row(RowInputs &r, int q, float cx, float cy, float cz)
 {
-    if (half == 1 && r.a >= 0) {
+    if (q == 3 && r.a >= 0) {
         const float vx = r.anchor[0] - cx, vy = r.anchor[1] - cy, vz = r.anchor[2] - cz;
         const float d = sqrtf(vx * vx + vy * vy + vz * vz);
-        r.x[18] = vx / d; r.x[19] = vy / d; r.x[20] = vz / d; r.x[21] = d;
+        r.x[2] = vx / d; r.x[3] = vy / d; r.x[4] = vz / d; r.x[5] = d;
     }
 }
 
@@ -136,6 +180,25 @@ __device__ __forceinline__ float fast_tanh(float x)
 {
     const float e = __expf(2.0f * fminf(fmaxf(x, -15.0f), 15.0f));
     return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
+// hidden = relu(D1 + b1) of 8 (or 4) accumulator columns, split into TF32 hi / lo, written back to TMEM
+template <int N>
+__device__ __forceinline__ void relu_split_store(const Smem &S, uint32_t tl, uint32_t col, const uint32_t (&v)[N])
+{
+    uint32_t hi[N], lo[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const float h = fmaxf(__uint_as_float(v[j]) + S.w[kOffB1 + col + j], 0.f);
+        umma::split_tf32(h, hi[j], lo[j]);
+    }
+    if constexpr (N == 8) {
+        umma::tmem_st8(tl + kColD1 + col, hi);
+        umma::tmem_st8(tl + kColHLo + col, lo);
+    } else {
+        umma::tmem_st4(tl + kColD1 + col, hi);
+        umma::tmem_st4(tl + kColHLo + col, lo);
+    }
 }
 }  // namespace ngu
 
@@ -153,8 +216,9 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = warp >> 2;
+    const int q = warp >> 2;                      // quarter of the row's columns / offsets
     const int row = 32 * (warp & 3) + lane;
+    const int kbase = quarter_first(q), nq = quarter_count(q);
     // the number of visible anchors may live on the device (no host read-back between the stages)
     const int Nv = nv_dev ? min(max(__ldg(nv_dev), 0), Nv_cap) : Nv_cap;
     const int num_tiles = (Nv + kRows - 1) / kRows;
@@ -183,7 +247,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
     const uint32_t tbase = S.tmem;
     const uint32_t tl = tbase + ((uint32_t)(32 * (warp & 3)) << 16);  // this warp's lane quadrant
     // Static round-robin tile order: the grid never exceeds the SM count and a CTA needs a whole SM
-    // (145 KB shared memory, all 512 TMEM columns), so every CTA is resident and the tiles of one
+    // (222 KB shared memory, all 512 TMEM columns), so every CTA is resident and the tiles of one
     // round run concurrently -- the look-back predecessor of a tile is at most one round behind.
     int tile = blockIdx.x, next_tile = blockIdx.x + gridDim.x;
 
@@ -194,25 +258,25 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
     };
 
     RowInputs cur;
-    load_row(cur, source_of(tile), half, anchor, feat, offsets, scaling, mask, cx, cy, cz);
+    load_row_feat(cur, source_of(tile), q, feat);
+    load_row_rest(cur, q, anchor, offsets, scaling, mask);
+    int a_next = source_of(next_tile);   // the anchor index is fetched TWO tiles ahead: the row loads depend on it
 
     for (uint32_t it = 0; tile < num_tiles; ++it) {
         const uint32_t parity = it & 1u;
-        const int grow = tile * kRows + row;
         const int a = cur.a;
 
-        // ---- stage the layer-1 input row: half 0 -> k in [0,32), half 1 -> k in [32,56) ---------
+        // ---- stage the layer-1 input row: quarter q -> k in [16q, 16q+16) (quarter 3: [48, 56)) -------
         {
-            finish_row(cur, half, cx, cy, cz);
-            const uint32_t k0 = half == 0 ? 0u : 32u;
+            finish_row(cur, q, cx, cy, cz);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c < 3 || half == 0) {
+            for (int c = 0; c < 2; ++c) {
+                if (c == 0 || q < 3) {
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) umma::split_tf32(cur.x[8 * c + j], hi[j], lo[j]);
-                    umma::tmem_st8(tl + kColXHi + k0 + 8 * c, hi);
-                    umma::tmem_st8(tl + kColXLo + k0 + 8 * c, lo);
+                    umma::tmem_st8(tl + kColXHi + 16 * q + 8 * c, hi);
+                    umma::tmem_st8(tl + kColXLo + 16 * q + 8 * c, lo);
                 }
             }
         }
@@ -227,25 +291,36 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                               true);
             umma::umma_commit(&S.bar[0]);
         }
-        // while the tensor core works: start the next tile's HBM reads (index first, rows below)
-        const int a_next = source_of(next_tile);
+        // while the tensor core works: start the next tile's HBM reads (features now, the rest below)
+        RowInputs nxt;
+        load_row_feat(nxt, a_next, q, feat);
+        a_next = source_of(next_tile + (int)gridDim.x);
         if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
         umma::fence_after_thread_sync();
 
-        // ---- epilogue 1: hidden = relu(D1 + b1), split, back into TMEM (cols 88*half .. +88) ------
-#pragma unroll 1
-        for (int c = 0; c < 11; ++c) {
-            const uint32_t col = (uint32_t)(88 * half + 8 * c);
-            uint32_t v[8], hi[8], lo[8];
-            umma::tmem_ld8(tl + kColD1 + col, v);
-            umma::tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float h = fmaxf(__uint_as_float(v[j]) + S.w[kOffB1 + col + j], 0.f);
-                umma::split_tf32(h, hi[j], lo[j]);
-            }
-            umma::tmem_st8(tl + kColD1 + col, hi);
-            umma::tmem_st8(tl + kColHLo + col, lo);
+        // ---- epilogue 1: hidden = relu(D1 + b1), split, back into TMEM (cols 44q .. 44q+43) -----------
+        // software pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+        {
+            const uint32_t col0 = (uint32_t)(kQCols * q);
+            uint32_t va[8], vb[8], v4[4];
+            umma::tmem_ld8(tl + kColD1 + col0, va);
+            umma::tmem_wait_ld8(va);
+            umma::tmem_ld8(tl + kColD1 + col0 + 8, vb);
+            relu_split_store<8>(S, tl, col0, va);
+            umma::tmem_wait_ld8(vb);
+            umma::tmem_ld8(tl + kColD1 + col0 + 16, va);
+            relu_split_store<8>(S, tl, col0 + 8, vb);
+            umma::tmem_wait_ld8(va);
+            umma::tmem_ld8(tl + kColD1 + col0 + 24, vb);
+            relu_split_store<8>(S, tl, col0 + 16, va);
+            umma::tmem_wait_ld8(vb);
+            umma::tmem_ld8(tl + kColD1 + col0 + 32, va);
+            relu_split_store<8>(S, tl, col0 + 24, vb);
+            umma::tmem_wait_ld8(va);
+            umma::tmem_ld4(tl + kColD1 + col0 + 40, v4);
+            relu_split_store<8>(S, tl, col0 + 32, va);
+            umma::tmem_wait_ld4(v4);
+            relu_split_store<4>(S, tl, col0 + 40, v4);
         }
         umma::tmem_wait_st();
         umma::fence_before_thread_sync();
@@ -263,32 +338,32 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                               S.w + kOffW2vHi, S.w + kOffW2vLo, kNv, kK1, true);
             umma::umma_commit(&S.bar[2]);
         }
-        // the next tile's rows travel while layer 2 and the epilogues run
-        RowInputs nxt;
-        load_row(nxt, a_next, half, anchor, feat, offsets, scaling, mask, cx, cy, cz);
+        // the rest of the next tile's rows travels while layer 2 and the epilogues run
+        load_row_rest(nxt, q, anchor, offsets, scaling, mask);
         if (!umma::mbar_wait(&S.bar[1], parity)) S.timeout = 1;
         umma::fence_after_thread_sync();
 
-        // ---- epilogue 2a: selection of offsets k = 5*half + j, ordered ranks -------------------------
-        const int kbase = 5 * half;
-        float nop[5];
+        // ---- epilogue 2a: selection of offsets k = kbase + j, ordered ranks ------------------------------
+        float nop[kMaxOff];
         uint32_t keepbits = 0;
         {
-            uint32_t v[8];
-            umma::tmem_ld8(tl + kColDo + 8 * half, v);
-            umma::tmem_wait_ld();
+            uint32_t v[4];
+            umma::tmem_ld4(tl + kColDo + 4 * q, v);
+            umma::tmem_wait_ld4(v);
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
+            for (int j = 0; j < kMaxOff; ++j) {
                 nop[j] = 0.f;
-                if (a >= 0) {
-                    nop[j] = fast_tanh(__uint_as_float(v[j]) + S.w[kOffB2o + 8 * half + j]) * cur.mask[j];
-                    keepbits |= nop[j] > 0.0f ? (1u << j) : 0u;
+                if (j < nq) {
+                    if (a >= 0) {
+                        nop[j] = fast_tanh(__uint_as_float(v[j]) + S.w[kOffB2o + 4 * q + j]) * cur.mask[j];
+                        keepbits |= nop[j] > 0.0f ? (1u << j) : 0u;
+                    }
+                    S.o_nop[row * kK + kbase + j] = nop[j];
+                    S.o_keep[row * kK + kbase + j] = (keepbits >> j) & 1u;
                 }
-                S.o_nop[row * kK + kbase + j] = nop[j];
-                S.o_keep[row * kK + kbase + j] = (keepbits >> j) & 1u;
             }
         }
-        S.cnt[row * 2 + half] = __popc(keepbits);  // order index = row*2 + half
+        S.cnt[row * 4 + q] = __popc(keepbits);  // order index = row*4 + quarter
         __syncthreads();
         uint32_t total = 0;
         {
@@ -322,36 +397,39 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                 if (tile == num_tiles - 1) *count_out = (int32_t)(excl + total);
             }
         }
-        uint32_t pos = S.excl[row * 2 + half];
+        uint32_t pos = S.excl[row * 4 + q];
 
         // ---- epilogue 2b: post-process the kept offsets into the staging buffers -----------------------
         if (!umma::mbar_wait(&S.bar[2], parity)) S.timeout = 1;
         umma::fence_after_thread_sync();
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const int k = kbase + j;
-            uint32_t vc[4], vv[8];
-            umma::tmem_ld4(tl + kColDc + 4 * k, vc);
-            umma::tmem_ld8(tl + kColDv + 8 * k, vv);
-            umma::tmem_wait_ld();
-            if (keepbits & (1u << j)) {
-                const uint32_t p = pos++;
-                S.o_xyz[3 * p + 0] = cur.anchor[0] + cur.off[3 * j + 0] * cur.sc[0];
-                S.o_xyz[3 * p + 1] = cur.anchor[1] + cur.off[3 * j + 1] * cur.sc[1];
-                S.o_xyz[3 * p + 2] = cur.anchor[2] + cur.off[3 * j + 2] * cur.sc[2];
-                S.o_color[3 * p + 0] = fast_sigmoid(__uint_as_float(vc[0]) + S.w[kOffB2c + 4 * k + 0]);
-                S.o_color[3 * p + 1] = fast_sigmoid(__uint_as_float(vc[1]) + S.w[kOffB2c + 4 * k + 1]);
-                S.o_color[3 * p + 2] = fast_sigmoid(__uint_as_float(vc[2]) + S.w[kOffB2c + 4 * k + 2]);
-                S.o_opacity[p] = nop[j];
-                float cv[7];
+        for (int j = 0; j < kMaxOff; ++j) {
+            if (j < nq) {   // warp-uniform
+                const int k = kbase + j;
+                uint32_t vc[4], vv[8];
+                umma::tmem_ld4(tl + kColDc + 4 * k, vc);
+                umma::tmem_ld8(tl + kColDv + 8 * k, vv);
+                umma::tmem_wait_ld4(vc);
+                umma::tmem_wait_ld8(vv);
+                if (keepbits & (1u << j)) {
+                    const uint32_t p = pos++;
+                    S.o_xyz[3 * p + 0] = cur.anchor[0] + cur.off[3 * j + 0] * cur.sc[0];
+                    S.o_xyz[3 * p + 1] = cur.anchor[1] + cur.off[3 * j + 1] * cur.sc[1];
+                    S.o_xyz[3 * p + 2] = cur.anchor[2] + cur.off[3 * j + 2] * cur.sc[2];
+                    S.o_color[3 * p + 0] = fast_sigmoid(__uint_as_float(vc[0]) + S.w[kOffB2c + 4 * k + 0]);
+                    S.o_color[3 * p + 1] = fast_sigmoid(__uint_as_float(vc[1]) + S.w[kOffB2c + 4 * k + 1]);
+                    S.o_color[3 * p + 2] = fast_sigmoid(__uint_as_float(vc[2]) + S.w[kOffB2c + 4 * k + 2]);
+                    S.o_opacity[p] = nop[j];
+                    float cv[7];
 #pragma unroll
-                for (int i = 0; i < 7; ++i) cv[i] = __uint_as_float(vv[i]) + S.w[kOffB2v + 8 * k + i];
-                S.o_scaling[3 * p + 0] = cur.sc[3] * fast_sigmoid(cv[0]);
-                S.o_scaling[3 * p + 1] = cur.sc[4] * fast_sigmoid(cv[1]);
-                S.o_scaling[3 * p + 2] = cur.sc[5] * fast_sigmoid(cv[2]);
-                const float ss = cv[3] * cv[3] + cv[4] * cv[4] + cv[5] * cv[5] + cv[6] * cv[6];
-                const float inv = rsqrtf(fmaxf(ss, 1e-24f));  // F.normalize: v / max(|v|, 1e-12)
-                S.o_rot[p] = make_float4(cv[3] * inv, cv[4] * inv, cv[5] * inv, cv[6] * inv);
+                    for (int i = 0; i < 7; ++i) cv[i] = __uint_as_float(vv[i]) + S.w[kOffB2v + 8 * k + i];
+                    S.o_scaling[3 * p + 0] = cur.sc[3] * fast_sigmoid(cv[0]);
+                    S.o_scaling[3 * p + 1] = cur.sc[4] * fast_sigmoid(cv[1]);
+                    S.o_scaling[3 * p + 2] = cur.sc[5] * fast_sigmoid(cv[2]);
+                    const float ss = cv[3] * cv[3] + cv[4] * cv[4] + cv[5] * cv[5] + cv[6] * cv[6];
+                    const float inv = rsqrtf(fmaxf(ss, 1e-24f));  // F.normalize: v / max(|v|, 1e-12)
+                    S.o_rot[p] = make_float4(cv[3] * inv, cv[4] * inv, cv[5] * inv, cv[6] * inv);
+                }
             }
         }
         umma::fence_before_thread_sync();
