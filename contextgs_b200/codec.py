@@ -1,0 +1,320 @@
+"""GPU bitstream codec: the `conduct_encoding` / `conduct_decoding` pair of the reference
+(scene/gaussian_model.py:1005-1300 and :1302-1538) on top of csrc/entropy_codec.cu.
+
+Same structure as the reference -- anchors as raw 16-bit grid indices, offset masks as one Bernoulli
+stream, hyper latents under the factorised prior, then feat / scaling / masked offsets level by level
+(coarse -> fine), each level predicted by the context MLP from what has been decoded so far -- and the
+same file names in the output directory (anchor.npy, masks.b, hyper.b, feat{L}.b, scaling{L}.b,
+offsets{L}.b, meta.b, mlp.pt).  The byte format of the .b streams is this library's own range coder
+(torchac is not part of the reference tree and cannot be pinned): what is guaranteed and tested is that
+decoding returns the encoder's quantised tensors bit for bit.
+
+Everything heavy runs on the GPU: one level kernel (cgs_context_level_umma_forward_ex) produces the
+(mean, scale, Q) of every coded value, one thread per 128-row chunk range-codes it in closed form.
+The host only builds two tiny frequency tables and concatenates streams.
+"""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _lib
+from .context_model import build_level_plan, find_divide_scale, pack_grid_weights_umma
+from .encodings import Q_anchor, Quantize_anchor
+
+CHUNK_ROWS = 128          # level rows per independently coded chunk (the reference: 1000 anchors)
+ATTRS = (("feat", 50), ("scaling", 6), ("offsets", 30))
+PARAM_LD = 176
+
+
+def dequantize_anchor(q, x_bound_min, x_bound_max):
+    """utils/encodings.py:224-227: grid index -> position (the exact expression the encoder's anchors come from)."""
+    interval = (x_bound_max - x_bound_min) * Q_anchor + 1e-6
+    return q.float() * interval + x_bound_min
+
+
+def frequency_tables(pmf):
+    """pmf [T, L] (any positive weights) -> uint32 [T, L + 1] cumulative 16-bit frequencies with every symbol
+    codable: C(i) = floor(cum_i / cum_L * (65536 - L)) + i, C(0) = 0, C(L) = 65536."""
+    pmf = pmf.detach().to("cpu", torch.float64).clamp_min(0)
+    T, L = pmf.shape
+    if L >= 32768:
+        raise ValueError("alphabet too large for 16-bit frequencies")
+    cum = torch.cumsum(pmf, dim=1)
+    total = cum[:, -1:].clamp_min(1e-300)
+    body = torch.floor(cum / total * (65536 - L)).to(torch.int64) + torch.arange(1, L + 1).view(1, L)
+    body[:, -1] = 65536
+    return torch.cat([torch.zeros(T, 1, dtype=torch.int64), body], dim=1).to(torch.int32)
+
+
+def _pack(scratch, cap, lens, dev):
+    """fixed-stride chunks -> (packed uint8 tensor, offsets int64)"""
+    L = _lib.lib()
+    n = lens.numel()
+    off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens.to(torch.int64), 0, out=off[1:])
+    total = int(off[-1].item())
+    packed = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+    _lib.check(L.cgs_codec_pack_streams(_lib.ptr(scratch), cap, _lib.ptr(lens), _lib.ptr(off), n, _lib.ptr(packed),
+                                        _lib.stream_ptr()), "cgs_codec_pack_streams")
+    return packed[:total], off[:-1].contiguous()
+
+
+def _table_encode(symbols, tables, chunk_rows, err):
+    L = _lib.lib()
+    dev = symbols.device
+    n, C = symbols.shape
+    n_chunks = (n + chunk_rows - 1) // chunk_rows
+    cap = (2 * C * chunk_rows + 16 + 3) // 4 * 4
+    scratch = torch.empty(max(n_chunks, 1) * cap // 4, dtype=torch.int32, device=dev)
+    lens = torch.zeros(max(n_chunks, 1), dtype=torch.int32, device=dev)
+    tb = tables.to(dev).contiguous()
+    _lib.check(L.cgs_codec_table_encode(_lib.ptr(symbols), n, C, chunk_rows, _lib.ptr(tb), tb.shape[0], tb.shape[1],
+                                        _lib.ptr(scratch), cap, _lib.ptr(lens), _lib.ptr(err), _lib.stream_ptr()),
+               "cgs_codec_table_encode")
+    packed, _ = _pack(scratch, cap, lens[:n_chunks], dev)
+    return packed, lens[:n_chunks]
+
+
+def _table_decode(packed, lens, n, C, tables, chunk_rows):
+    L = _lib.lib()
+    dev = packed.device
+    off = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens.to(torch.int64), 0, out=off[1:])
+    tb = tables.to(dev).contiguous()
+    tlen = torch.full((tb.shape[0],), tb.shape[1] - 1, dtype=torch.int32, device=dev)
+    sym = torch.empty((n, C), dtype=torch.int16, device=dev)
+    _lib.check(L.cgs_codec_table_decode(_lib.ptr(packed), _lib.ptr(off), _lib.ptr(lens.contiguous()), n, C, chunk_rows,
+                                        _lib.ptr(tb), _lib.ptr(tlen), tb.shape[0], tb.shape[1], _lib.ptr(sym),
+                                        _lib.stream_ptr()), "cgs_codec_table_decode")
+    return sym
+
+
+def _hyper_tables(pc, smin, smax):
+    """Factorised-prior pmf of the integer symbols smin..smax per channel (EntropyBottleneck likelihood at
+    median + s, the quantity `latent_codec.update()` tabulates) -> 16-bit cumulative frequencies."""
+    dev = pc.latent_codec.quantiles.device
+    median = pc.latent_codec.quantiles[:, 0, 1].detach()
+    grid = torch.arange(smin, smax + 1, device=dev, dtype=torch.float32).view(-1, 1) + median.view(1, -1)
+    _, lik = pc.latent_codec(grid.contiguous(), training=False)
+    return frequency_tables(lik.t().contiguous() + 1e-12)
+
+
+def _level_params(pc, lv, anchor, hyper_q, feat, scaling, offsets, masks, feat_q, scaling_q, offsets_q, sums, err, means,
+                  predict_only):
+    """(mean, scale, Q) of every coded value of one level (and, when encoding, the level's quantised values)."""
+    L = _lib.lib()
+    packed, in_dim = pack_grid_weights_umma(pc, lv.level)
+    params = torch.empty((lv.n, PARAM_LD), dtype=torch.float32, device=anchor.device)
+    p = _lib.ptr
+    _lib.check(L.cgs_context_level_umma_forward_ex(
+        in_dim, p(packed), p(lv.orig), p(lv.ctx_src), p(lv.level_anchor), lv.n, p(anchor), p(hyper_q), p(feat), p(scaling),
+        p(offsets), p(masks), None, None, means[0], means[1], means[2], p(feat_q), p(scaling_q), p(offsets_q), None,
+        p(sums), p(err), p(params), int(predict_only), _lib.stream_ptr()), "cgs_context_level_umma_forward_ex")
+    return params
+
+
+@torch.no_grad()
+def encode_model(pc, chunk_rows=CHUNK_ROWS):
+    """Encode every valid anchor of `pc`.  Returns a SimpleNamespace with the byte streams (CUDA uint8 tensors),
+    the metadata the decoder needs, the quantised tensors that were coded (for parity checks) and the
+    estimated bits of the same pass."""
+    L = _lib.lib()
+    sel = pc.get_mask_anchor
+    dev = sel.device
+    tensors = (pc._anchor, pc._hyper_latent, pc._anchor_feat, pc._offset, pc.get_scaling, pc.get_mask)
+    if not bool(sel.all()):
+        idx = torch.nonzero(sel)[:, 0]
+        tensors = tuple(t.index_select(0, idx) for t in tensors)
+    a_raw, hyper, feat, offsets, scaling, masks = (t.detach().contiguous().float() for t in tensors)
+    N, K = a_raw.shape[0], pc.n_offsets
+    offsets, masks = offsets.reshape(N, 3 * K).contiguous(), masks.reshape(N, K).contiguous()
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    # anchors: 16-bit grid indices (saved raw, like the reference's anchor.npy)
+    _, qv = Quantize_anchor.apply(a_raw, pc.x_bound_min, pc.x_bound_max)
+    anchor_q = qv.to(torch.int32)
+    anchor = dequantize_anchor(anchor_q, pc.x_bound_min, pc.x_bound_max).contiguous()
+
+    # offset masks: one Bernoulli table
+    p1 = float(masks.mean())
+    mask_tables = frequency_tables(torch.tensor([[max(1.0 - p1, 1e-9), max(p1, 1e-9)]]))
+    mask_bytes, mask_lens = _table_encode(masks.to(torch.int16).contiguous(), mask_tables, chunk_rows * 8, err)
+
+    # hyper latents under the factorised prior
+    hyper_q, _ = pc.latent_codec(hyper, training=False)
+    median = pc.latent_codec.quantiles[:, 0, 1].detach()
+    hsym = torch.round(hyper_q - median.view(1, -1)).to(torch.int32)
+    hmin, hmax = int(hsym.min()), int(hsym.max())
+    hyper_tables = _hyper_tables(pc, hmin, hmax)
+    hyper_bytes, hyper_lens = _table_encode((hsym - hmin).to(torch.int16).contiguous(), hyper_tables, chunk_rows * 8, err)
+    if getattr(pc, "disable_hyper", False):
+        hyper_q = hyper_q * 0
+
+    # level division on the DEQUANTISED anchors (what the decoder will see)
+    if pc.level_scale is None:
+        pc.level_scale = find_divide_scale(pc, anchor, pc.target_ratio, pc.level_num)
+    plan = build_level_plan(pc, anchor, None)
+
+    feat_q, scaling_q, offsets_q = torch.zeros_like(feat), torch.zeros_like(scaling), torch.zeros_like(offsets)
+    sums = torch.zeros(16, dtype=torch.float64, device=dev)
+    terr = torch.zeros(1, dtype=torch.int32, device=dev)
+    means = tuple(torch.stack([pc._anchor_feat.mean(), pc.get_scaling.mean(), pc._offset.mean()]).tolist())
+    levels = []
+    for li, lv in enumerate(plan.levels):
+        entry = SimpleNamespace(level=lv.level, n=lv.n, streams={})
+        levels.append(entry)
+        if lv.n == 0:
+            continue
+        params = _level_params(pc, lv, anchor, hyper_q, feat, scaling, offsets, masks, feat_q, scaling_q, offsets_q,
+                               sums[4 * li:4 * li + 4], terr, means, False)
+        n_chunks = (lv.n + chunk_rows - 1) // chunk_rows
+        for attr, (name, dim) in enumerate(ATTRS):
+            cap = int(L.cgs_codec_gauss_stream_capacity(attr, chunk_rows))
+            scratch = torch.empty(n_chunks * cap // 4, dtype=torch.int32, device=dev)
+            lens = torch.zeros(n_chunks, dtype=torch.int32, device=dev)
+            minmax = torch.zeros((n_chunks, 2), dtype=torch.int32, device=dev)
+            nsym = torch.zeros(n_chunks, dtype=torch.int32, device=dev)
+            values = (feat_q, scaling_q, offsets_q)[attr]
+            _lib.check(L.cgs_codec_gauss_encode(attr, _lib.ptr(lv.orig), lv.n, chunk_rows, _lib.ptr(params), _lib.ptr(masks),
+                                                _lib.ptr(values), _lib.ptr(scratch), cap, _lib.ptr(lens), _lib.ptr(minmax),
+                                                _lib.ptr(nsym), _lib.ptr(err), _lib.stream_ptr()), "cgs_codec_gauss_encode")
+            packed, _ = _pack(scratch, cap, lens, dev)
+            entry.streams[name] = SimpleNamespace(bytes=packed, lens=lens, minmax=minmax.to(torch.int16), nsym=nsym)
+    e, te = int(err.item()), int(terr.item())
+    if te:
+        raise _lib.CgsError("cgs_context_level_umma_forward_ex: a tensor-core completion barrier timed out")
+    if e:
+        raise _lib.CgsError({1: "a symbol has an empty coding interval", 2: "a chunk's alphabet exceeds 32768 symbols",
+                             3: "a stream outgrew its capacity"}.get(e, f"codec error {e}"))
+    meta = dict(version=1, N_total=int(pc._anchor.shape[0]), N=N, chunk_rows=chunk_rows, voxel_size=float(pc.voxel_size),
+                level_scale=[float(s) for s in pc.level_scale], x_bound_min=pc.x_bound_min.detach().cpu(),
+                x_bound_max=pc.x_bound_max.detach().cpu(), prob_masks=p1, hyper_min=hmin, hyper_max=hmax,
+                means=means, N_levels=[lv.n for lv in plan.levels])
+    s = sums.tolist()
+    est = dict(hyper=None, feat=sum(s[4 * i] for i in range(3)), scaling=sum(s[4 * i + 1] for i in range(3)),
+               offsets=sum(s[4 * i + 2] for i in range(3)))
+    return SimpleNamespace(meta=meta, anchor_q=anchor_q.to(torch.int16), mask_bytes=mask_bytes, mask_lens=mask_lens,
+                           hyper_bytes=hyper_bytes, hyper_lens=hyper_lens, levels=levels, valid=sel,
+                           quantised=dict(anchor=anchor, hyper=hyper_q, feat=feat_q, scaling=scaling_q, offsets=offsets_q,
+                                          masks=masks), estimated_bits=est, plan=plan)
+
+
+def encoded_bits(enc):
+    """Size of every part of the encoding in bits (payload + per-chunk side information)."""
+    side = lambda lens: 32 * lens.numel()
+    bits = dict(anchor=16 * enc.anchor_q.numel(), masks=8 * enc.mask_bytes.numel() + side(enc.mask_lens) + 32,
+                hyper=8 * enc.hyper_bytes.numel() + side(enc.hyper_lens) + 32, feat=0, scaling=0, offsets=0)
+    for lv in enc.levels:
+        for name, st in lv.streams.items():
+            bits[name] += 8 * st.bytes.numel() + (32 + 32) * st.lens.numel()   # length + (min, max) as 2 x int16
+    bits["total"] = sum(bits.values())
+    return bits
+
+
+@torch.no_grad()
+def decode_model(pc, meta, anchor_q, mask_bytes, mask_lens, hyper_bytes, hyper_lens, levels):
+    """Inverse of encode_model.  `pc` supplies the MLPs / entropy bottleneck (mlp.pt) and receives bounds and
+    level scales from `meta`.  Returns dict(anchor, hyper, feat, offsets [N,10,3], scaling, masks [N,10,1])."""
+    L = _lib.lib()
+    dev = pc.latent_codec.quantiles.device
+    N, K, chunk_rows = meta["N"], pc.n_offsets, meta["chunk_rows"]
+    pc.x_bound_min, pc.x_bound_max = meta["x_bound_min"].to(dev), meta["x_bound_max"].to(dev)
+    pc.level_scale = list(meta["level_scale"])
+    pc.voxel_size = meta["voxel_size"]
+    anchor = dequantize_anchor(anchor_q.to(dev).to(torch.int32) & 0xffff, pc.x_bound_min, pc.x_bound_max).contiguous()
+
+    p1 = meta["prob_masks"]
+    mask_tables = frequency_tables(torch.tensor([[max(1.0 - p1, 1e-9), max(p1, 1e-9)]]))
+    masks = _table_decode(mask_bytes.to(dev), mask_lens.to(dev), N, K, mask_tables, chunk_rows * 8).float().contiguous()
+
+    hmin, hmax = meta["hyper_min"], meta["hyper_max"]
+    median = pc.latent_codec.quantiles[:, 0, 1].detach()
+    hsym = _table_decode(hyper_bytes.to(dev), hyper_lens.to(dev), N, median.numel(), _hyper_tables(pc, hmin, hmax),
+                         chunk_rows * 8)
+    hyper_q = ((hsym.to(torch.int32) + hmin).float() + median.view(1, -1)).contiguous()
+    hyper_ctx = hyper_q * 0 if getattr(pc, "disable_hyper", False) else hyper_q
+
+    plan = build_level_plan(pc, anchor, None)
+    if [lv.n for lv in plan.levels] != list(meta["N_levels"]):
+        raise _lib.CgsError("decode: the level division of the decoded anchors differs from the encoder's")
+    feat_q = torch.zeros((N, 50), dtype=torch.float32, device=dev)
+    scaling_q = torch.zeros((N, 6), dtype=torch.float32, device=dev)
+    offsets_q = torch.zeros((N, 3 * K), dtype=torch.float32, device=dev)
+    sums = torch.zeros(16, dtype=torch.float64, device=dev)
+    terr = torch.zeros(1, dtype=torch.int32, device=dev)
+    means = tuple(meta["means"])
+    for li, (lv, coded) in enumerate(zip(plan.levels, levels)):
+        if lv.n == 0:
+            continue
+        params = _level_params(pc, lv, anchor, hyper_ctx, None, None, None, None, feat_q, scaling_q, offsets_q,
+                               sums[4 * li:4 * li + 4], terr, means, True)
+        for attr, (name, dim) in enumerate(ATTRS):
+            st = coded.streams[name]
+            lens = st.lens.to(dev).contiguous()
+            off = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(lens.to(torch.int64), 0, out=off[1:])
+            values = (feat_q, scaling_q, offsets_q)[attr]
+            _lib.check(L.cgs_codec_gauss_decode(attr, _lib.ptr(lv.orig), lv.n, chunk_rows, _lib.ptr(params), _lib.ptr(masks),
+                                                _lib.ptr(st.bytes.to(dev)), _lib.ptr(off), _lib.ptr(lens),
+                                                _lib.ptr(st.minmax.to(dev).to(torch.int32).contiguous()), _lib.ptr(values),
+                                                _lib.stream_ptr()), "cgs_codec_gauss_decode")
+    if int(terr.item()):
+        raise _lib.CgsError("cgs_context_level_umma_forward_ex: a tensor-core completion barrier timed out")
+    return dict(anchor=anchor, hyper=hyper_q, feat=feat_q, offsets=offsets_q.view(N, K, 3), scaling=scaling_q,
+                masks=masks.view(N, K, 1))
+
+
+# ----------------------------------------------------------------------------- directory layout of the reference
+
+def _mlp_state(pc):
+    return {"opacity_mlp": pc.mlp_opacity.state_dict(), "cov_mlp": pc.mlp_cov.state_dict(),
+            "color_mlp": pc.mlp_color.state_dict(), "grid_mlp": pc.mlp_grid.state_dict(),
+            "latent_codec": pc.latent_codec.state_dict()}
+
+
+def conduct_encoding(pc, pre_path_name, chunk_rows=CHUNK_ROWS):
+    """scene/gaussian_model.py:1005-1300: writes anchor.npy, masks.b, hyper.b, {feat,scaling,offsets}{level}.b,
+    meta.b, mlp.pt under `pre_path_name`; returns the reference's size summary string."""
+    os.makedirs(pre_path_name, exist_ok=True)
+    enc = encode_model(pc, chunk_rows)
+    np.save(os.path.join(pre_path_name, "anchor.npy"), enc.anchor_q.cpu().numpy().view(np.uint16))
+    wr = lambda name, t: t.cpu().numpy().tofile(os.path.join(pre_path_name, name))
+    wr("masks.b", enc.mask_bytes)
+    wr("hyper.b", enc.hyper_bytes)
+    side = dict(mask_lens=enc.mask_lens.cpu(), hyper_lens=enc.hyper_lens.cpu(), levels=[])
+    for lv in enc.levels:
+        ent = dict(level=lv.level, n=lv.n, streams={})
+        for name, st in lv.streams.items():
+            wr(f"{name}{lv.level}.b", st.bytes)
+            ent["streams"][name] = dict(lens=st.lens.cpu(), minmax=st.minmax.cpu())
+        side["levels"].append(ent)
+    torch.save(dict(meta=enc.meta, side=side), os.path.join(pre_path_name, "meta.b"))
+    torch.save(_mlp_state(pc), os.path.join(pre_path_name, "mlp.pt"))
+    bits = encoded_bits(enc)
+    mb = 8 * 1024 * 1024
+    return enc, "\nEncoded sizes in MB: " + ", ".join(f"{k} {round(v / mb, 4)}" for k, v in bits.items())
+
+
+def conduct_decoding(pc, pre_path_name):
+    """scene/gaussian_model.py:1302-1538: reads the directory written by conduct_encoding and replaces the model's
+    parameters with the decoded values (`decoded_version = True`)."""
+    dev = pc.latent_codec.quantiles.device
+    state = torch.load(os.path.join(pre_path_name, "mlp.pt"), map_location=dev)
+    pc.mlp_opacity.load_state_dict(state["opacity_mlp"]); pc.mlp_cov.load_state_dict(state["cov_mlp"])
+    pc.mlp_color.load_state_dict(state["color_mlp"]); pc.mlp_grid.load_state_dict(state["grid_mlp"])
+    pc.latent_codec.load_state_dict(state["latent_codec"])
+    blob = torch.load(os.path.join(pre_path_name, "meta.b"), weights_only=False)
+    meta, side = blob["meta"], blob["side"]
+    rd = lambda name: torch.from_numpy(np.fromfile(os.path.join(pre_path_name, name), dtype=np.uint8)).to(dev)
+    anchor_q = torch.from_numpy(np.load(os.path.join(pre_path_name, "anchor.npy")).astype(np.int32)).to(dev)
+    levels = []
+    for ent in side["levels"]:
+        lv = SimpleNamespace(level=ent["level"], n=ent["n"], streams={})
+        for name, st in ent["streams"].items():
+            lv.streams[name] = SimpleNamespace(bytes=rd(f"{name}{ent['level']}.b"), lens=st["lens"], minmax=st["minmax"])
+        levels.append(lv)
+    out = decode_model(pc, meta, anchor_q, rd("masks.b"), side["mask_lens"], rd("hyper.b"), side["hyper_lens"], levels)
+    pc.replace_with_decoded(out["anchor"], out["hyper"], out["feat"], out["offsets"], out["scaling"], out["masks"])
+    return out

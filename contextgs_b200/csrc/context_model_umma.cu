@@ -56,6 +56,8 @@ struct Args {
     float *feat_q, *scaling_q, *offsets_q, *bits_out;
     double *bit_sums;
     int32_t *err_flag;
+    float *params_out;   // [n_rows][176]: mean[86] | scale[86] | Q_feat Q_scaling Q_offsets | 0 (codec; optional)
+    int predict_only;    // 1: only params_out is produced (decoder: the attributes are not known yet)
 };
 
 template <int K1>
@@ -201,14 +203,15 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
         }
         // while the tensor core works: this row's share of the attributes to be coded (43 values per thread)
         // and the next tile's gathered context rows travel from HBM
-        const bool chosen = o >= 0 && (A.choose ? A.choose[o] != 0 : true);
+        const bool pred = A.predict_only != 0;
+        const bool chosen = !pred && o >= 0 && (A.choose ? A.choose[o] != 0 : true);
         float xv[48], mk[10];
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
             const ChunkDesc cd = chunk_desc(c, half);
             const float *src = (cd.grp == 0 ? A.feat : (cd.grp == 1 ? A.scaling : A.offsets)) + (o < 0 ? 0 : o) * cd.dim + cd.k0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xv[8 * c + j] = (o >= 0 && j < cd.cnt) ? __ldg(src + j) : 0.f;
+            for (int j = 0; j < 8; ++j) xv[8 * c + j] = (!pred && o >= 0 && j < cd.cnt) ? __ldg(src + j) : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < 10; ++k) mk[k] = (o >= 0 && half == 1 && chosen) ? __ldg(A.mask + o * 10 + k) : 1.f;
@@ -255,6 +258,10 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             Qo = fmaxf(kQo0 * (1.0f + tanhf(__uint_as_float(v[2]) + S.w[LY::kOffB2 + 174])), 1e-9f);
         }
         if (half == 0 && chosen) n_chosen += 1.f;
+        float *prow = (A.params_out && o >= 0) ? A.params_out + (size_t)grow * kLdG2 : nullptr;
+        if (prow && half == 0) {
+            prow[172] = Qf; prow[173] = Qs; prow[174] = Qo; prow[175] = 0.f;
+        }
         const float *nz = A.noise ? A.noise + (size_t)grow * kCE : nullptr;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
@@ -271,13 +278,18 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 if (j < cd.cnt) {
+                    const float mean = __uint_as_float(vm[j]) + S.w[LY::kOffB2 + cd.mu_col + j];
+                    const float scale = __uint_as_float(vs[j]) + S.w[LY::kOffB2 + cd.sg_col + j];
+                    if (prow) {
+                        prow[cd.j0 + j] = mean;
+                        prow[kCE + cd.j0 + j] = scale;
+                    }
+                    if (pred) continue;
                     const float x = xv[8 * c + j];
                     const float xq = nz ? x + nz[cd.j0 + j] * Q : ste_round(x, Q);
                     dst[j] = xq;
                     float bits = 0.f;
                     if (chosen) {
-                        const float mean = __uint_as_float(vm[j]) + S.w[LY::kOffB2 + cd.mu_col + j];
-                        const float scale = __uint_as_float(vs[j]) + S.w[LY::kOffB2 + cd.sg_col + j];
                         bits = gaussian_bits_one(xq, mean, scale, Q, x_mean);
                         if (cd.grp == 2) bits *= mk[c >= 2 ? (8 * (c - 2) + j) / 3 : 0];  // grp 2 <=> half 1, c >= 2
                         acc += bits;
@@ -358,12 +370,30 @@ extern "C" int cgs_context_level_umma_forward(int in_dim, const float *packed_w,
                                               float *offsets_q, float *bits_out, double *bit_sums, int32_t *err_flag,
                                               void *stream)
 {
+    return cgs_context_level_umma_forward_ex(in_dim, packed_w, orig_idx, ctx_src, level_anchor, n_rows, anchor, hyper_q, feat,
+                                             scaling, offsets, mask, choose, noise, feat_mean, scaling_mean, offset_mean,
+                                             feat_q, scaling_q, offsets_q, bits_out, bit_sums, err_flag, nullptr, 0, stream);
+}
+
+extern "C" int cgs_context_level_umma_forward_ex(int in_dim, const float *packed_w, const int32_t *orig_idx,
+                                                 const int32_t *ctx_src, const float *level_anchor, int n_rows,
+                                                 const float *anchor, const float *hyper_q, const float *feat,
+                                                 const float *scaling, const float *offsets, const float *mask,
+                                                 const uint8_t *choose, const float *noise, float feat_mean,
+                                                 float scaling_mean, float offset_mean, float *feat_q, float *scaling_q,
+                                                 float *offsets_q, float *bits_out, double *bit_sums, int32_t *err_flag,
+                                                 float *params_out, int predict_only, void *stream)
+{
     if (n_rows <= 0) return 0;
     CGS_CHECK_PTR(packed_w); CGS_CHECK_PTR(orig_idx); CGS_CHECK_PTR(anchor); CGS_CHECK_PTR(hyper_q);
-    CGS_CHECK_PTR(feat); CGS_CHECK_PTR(scaling); CGS_CHECK_PTR(offsets); CGS_CHECK_PTR(mask);
-    CGS_CHECK_PTR(feat_q); CGS_CHECK_PTR(scaling_q); CGS_CHECK_PTR(offsets_q); CGS_CHECK_PTR(bit_sums);
-    CGS_CHECK_PTR(err_flag);
+    CGS_CHECK_PTR(feat_q); CGS_CHECK_PTR(scaling_q); CGS_CHECK_PTR(bit_sums); CGS_CHECK_PTR(err_flag);
+    if (predict_only) {
+        CGS_CHECK_PTR(params_out);
+    } else {
+        CGS_CHECK_PTR(feat); CGS_CHECK_PTR(scaling); CGS_CHECK_PTR(offsets); CGS_CHECK_PTR(mask); CGS_CHECK_PTR(offsets_q);
+    }
     cmu::Args a;
+    a.params_out = params_out; a.predict_only = predict_only;
     a.packed_w = packed_w; a.orig_idx = orig_idx; a.ctx_src = ctx_src; a.level_anchor = level_anchor; a.n_rows = n_rows;
     a.anchor = anchor; a.hyper_q = hyper_q; a.feat = feat; a.scaling = scaling; a.offsets = offsets; a.mask = mask;
     a.choose = choose; a.noise = noise; a.feat_mean = feat_mean; a.scaling_mean = scaling_mean;

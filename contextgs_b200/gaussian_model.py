@@ -230,9 +230,24 @@ class GaussianModel(nn.Module):
         self._hyper_latent, self._anchor_feat, self._offset = P(hyper), P(feat), P(offsets)
         self.decoded_version = True
         self._anchor, self._scaling, self._mask = P(anchor), P(scaling), P(masks)
+        if self._rotation.shape[0] != self._anchor.shape[0]:   # identity rotations, as conduct_decoding creates them
+            rot = torch.zeros((self._anchor.shape[0], 4), device=self._anchor.device)
+            rot[:, 0] = 1
+            self._rotation = nn.Parameter(rot, requires_grad=False)
         if hasattr(self, "_cgs_level_plan"):
             del self._cgs_level_plan
         return self
+
+    def conduct_encoding(self, pre_path_name):
+        """scene/gaussian_model.py:1005-1300 on the GPU codec (contextgs_b200/codec.py); returns the size summary."""
+        from .codec import conduct_encoding
+        return conduct_encoding(self, pre_path_name)[1]
+
+    def conduct_decoding(self, pre_path_name):
+        """scene/gaussian_model.py:1302-1538."""
+        from .codec import conduct_decoding
+        conduct_decoding(self, pre_path_name)
+        return ""
 
     def eval(self):
         for m in (self.mlp_opacity, self.mlp_cov, self.mlp_color, self.latent_codec, self.mlp_grid):

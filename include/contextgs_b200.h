@@ -308,6 +308,21 @@ CGS_API int cgs_context_level_umma_forward(int in_dim, const float *packed_w, co
                                            float *offsets_q, float *bits_out, double *bit_sums, int32_t *err_flag,
                                            void *stream);
 
+/* The same level kernel for the BITSTREAM CODEC (replaces the per-level prediction inside the loops of
+ * `conduct_encoding` / `conduct_decoding`, scene/gaussian_model.py:1112-1232,1380-1477):
+ *   params_out[n_rows][176] (optional) receives what the entropy coder needs for every level row:
+ *     mean[86] | scale[86] (raw MLP outputs, feat 50 | scaling 6 | offsets 30) | Q_feat Q_scaling Q_offsets | 0;
+ *   predict_only != 0 : ONLY params_out is produced -- the decoder calls this before the level's attributes exist
+ *     (feat / scaling / offsets / mask / offsets_q may be NULL; feat_q / scaling_q are read as context only). */
+CGS_API int cgs_context_level_umma_forward_ex(int in_dim, const float *packed_w, const int32_t *orig_idx,
+                                              const int32_t *ctx_src, const float *level_anchor, int n_rows,
+                                              const float *anchor, const float *hyper_q, const float *feat,
+                                              const float *scaling, const float *offsets, const float *mask,
+                                              const uint8_t *choose, const float *noise, float feat_mean,
+                                              float scaling_mean, float offset_mean, float *feat_q, float *scaling_q,
+                                              float *offsets_q, float *bits_out, double *bit_sums, int32_t *err_flag,
+                                              float *params_out, int predict_only, void *stream);
+
 /* Backward of one level in TRAINING mode (noise != NULL in the forward): what autograd does in the
  * reference for the loop body scene/gaussian_model.py:1562-1652 plus the Entropy_gaussian terms of
  * bit_per_param (:1666-1693).  Launch fine -> coarse.  G_feat/G_scaling/G_offsets [N,*] hold the gradient
@@ -371,6 +386,41 @@ CGS_API size_t cgs_sort_workspace_bytes(int64_t n_cap, int begin_bit, int end_bi
 CGS_API int cgs_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
                        uint32_t *keys_tmp, uint32_t *vals_tmp, const uint32_t *n_dev, int64_t n_cap, int begin_bit,
                        int end_bit, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------ bitstream codec
+ * GPU replacement of `encoder_gaussian` / `decoder_gaussian` + torchac (utils/encodings.py:83-144; chunk loops
+ * scene/gaussian_model.py:1192-1232,1422-1477), of `latent_codec.compress/decompress` (:1088,1331) and of the
+ * binary-mask `encoder` / `decoder` (utils/encodings.py:147-183).  One GPU thread codes one chunk of one
+ * stream with a byte-wise 32-bit range coder; Gaussian CDFs are evaluated in closed form from params
+ * (cgs_context_level_umma_forward_ex), never tabulated.  Container format: this library's own
+ * (csrc/entropy_codec.cu), torchac's is not pinnable.
+ *
+ * Gaussian streams, per level and attribute (attr 0 feat[.,50] / 1 scaling[.,6] / 2 offsets[.,30]; offsets whose
+ * mask[anchor][k/3] is 0 are not coded and decode to 0):
+ *   chunk c = level rows [c*chunk_rows, (c+1)*chunk_rows); symbol = rint(value / Q), alphabet = the chunk's
+ *   [stream_minmax[2c], stream_minmax[2c+1]]; encode writes chunk c at scratch + c*cap_bytes (cap_bytes >=
+ *   cgs_codec_gauss_stream_capacity) and its byte count to stream_len[c]; *err != 0 reports an uncodable symbol (1),
+ *   an alphabet over 32768 (2) or a capacity overflow (3).  decode reads chunk c at bytes + stream_off[c] and
+ *   writes value = symbol * Q at values[orig_idx[row]][k] -- bit-identical to the encoder's input. */
+CGS_API int64_t cgs_codec_gauss_stream_capacity(int attr, int chunk_rows);
+CGS_API int cgs_codec_gauss_encode(int attr, const int32_t *orig_idx, int n_rows, int chunk_rows, const float *params,
+                                   const float *mask, const float *values, uint32_t *scratch, int64_t cap_bytes,
+                                   int32_t *stream_len, int32_t *stream_minmax, int32_t *stream_syms, int32_t *err,
+                                   void *stream);
+CGS_API int cgs_codec_gauss_decode(int attr, const int32_t *orig_idx, int n_rows, int chunk_rows, const float *params,
+                                   const float *mask, const uint8_t *bytes, const int64_t *stream_off,
+                                   const int32_t *stream_len, const int32_t *stream_minmax, float *values, void *stream);
+/* Static-table streams: symbols[n_rows][C] int16 (index into the table of channel c, tables[c % T][0..table_ld),
+ * cumulative 16-bit frequencies, tables[.][len] = 65536); chunking and outputs as above. */
+CGS_API int cgs_codec_table_encode(const int16_t *symbols, int n_rows, int C, int chunk_rows, const uint32_t *tables,
+                                   int T, int table_ld, uint32_t *scratch, int64_t cap_bytes, int32_t *stream_len,
+                                   int32_t *err, void *stream);
+CGS_API int cgs_codec_table_decode(const uint8_t *bytes, const int64_t *stream_off, const int32_t *stream_len,
+                                   int n_rows, int C, int chunk_rows, const uint32_t *tables, const int32_t *table_len,
+                                   int T, int table_ld, int16_t *symbols, void *stream);
+/* Gathers the fixed-stride chunks of an encode call into one byte string: chunk c -> packed + stream_off[c]. */
+CGS_API int cgs_codec_pack_streams(const uint32_t *scratch, int64_t cap_bytes, const int32_t *stream_len,
+                                   const int64_t *stream_off, int n_streams, uint8_t *packed, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,31 @@
+"""Host logic of the bitstream codec and the CPU restatement of its range coder (no GPU)."""
+import random
+
+import torch
+
+from contextgs_b200.codec import frequency_tables
+from oracle import codec_ref
+
+
+def test_frequency_tables_are_strictly_increasing_16_bit():
+    g = torch.Generator().manual_seed(0)
+    for L in (2, 3, 17, 300):
+        pmf = torch.rand(4, L, generator=g) ** 8        # very skewed, many near-zero entries
+        pmf[0, L // 2] = 0.0
+        tb = frequency_tables(pmf)
+        assert tb.shape == (4, L + 1) and tb.dtype == torch.int32
+        assert (tb[:, 0] == 0).all() and (tb[:, -1] == 65536).all()
+        assert (tb[:, 1:] > tb[:, :-1]).all()
+
+
+def test_range_coder_restatement_round_trips():
+    rnd = random.Random(1)
+    tables = [frequency_tables(torch.tensor([[0.9, 0.1]]))[0].tolist(),
+              frequency_tables(torch.tensor([[0.02, 0.5, 0.3, 0.18]]))[0].tolist()]
+    for n in (0, 1, 7, 5000):
+        syms = [rnd.choices(range(2), weights=[0.9, 0.1])[0] if i % 2 == 0 else rnd.choices(range(4), weights=[2, 50, 30, 18])[0]
+                for i in range(n)]
+        data = codec_ref.encode(syms, lambda i: i % 2, tables)
+        assert codec_ref.decode(data, n, lambda i: i % 2, tables) == syms
+        if n == 5000:   # close to the entropy of the source (0.47 + 1.58 bits per pair)
+            assert len(data) * 8 < 1.05 * n / 2 * (0.469 + 1.58) + 64

@@ -1,0 +1,136 @@
+"""Bitstream codec parity: encode -> decode returns the encoder's quantised tensors bit for bit,
+the streams are byte-identical to the CPU restatement of the range coder (table streams), their size matches the
+estimated bits, and a model decoded from disk renders exactly what the in-memory decoded model renders."""
+import numpy as np
+import pytest
+import torch
+
+from contextgs_b200 import codec, synthetic
+from contextgs_b200.context_model import multi_scale_generating
+from contextgs_b200.gaussian_model import GaussianModel
+from contextgs_b200.renderer import prefilter_voxel, render
+from oracle import codec_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(N=6000, seed=11, kind="chair"):
+    scene = synthetic.make_scene(kind, N, seed=seed)
+    torch.manual_seed(6)
+    pc = GaussianModel.from_tensors(scene, device="cuda")
+    with torch.no_grad():   # break the symmetric EntropyBottleneck init, kill a few anchors entirely
+        g = torch.Generator().manual_seed(9)
+        for plist in (pc.latent_codec.matrices, pc.latent_codec.biases, pc.latent_codec.factors):
+            for p in plist:
+                p.add_((torch.randn(p.shape, generator=g) * 0.3).cuda())
+        pc._mask[::17] = -8.0
+    pc.eval()
+    return pc
+
+
+@pytest.mark.parametrize("N,chunk", [(6000, 128), (1500, 64), (300, 1000)])
+def test_encode_decode_round_trip_is_bit_exact(N, chunk):
+    pc = _model(N)
+    enc = codec.encode_model(pc, chunk_rows=chunk)
+    q = enc.quantised
+    # the coded values are what the scoring pass quantises (same kernels): feat_q etc. of multi_scale_generating
+    sel = pc.get_mask_anchor
+    assert int(sel.sum()) == q["feat"].shape[0] < pc._anchor.shape[0]
+    fresh = GaussianModel(device="cuda")
+    fresh.load_state_dict({k: v for k, v in pc.state_dict().items() if not k.startswith("_")}, strict=False)
+    fresh.eval()
+    out = codec.decode_model(fresh, enc.meta, enc.anchor_q, enc.mask_bytes, enc.mask_lens, enc.hyper_bytes, enc.hyper_lens,
+                             enc.levels)
+    K = pc.n_offsets
+    assert torch.equal(out["anchor"], q["anchor"])
+    assert torch.equal(out["masks"].view(-1, K), q["masks"])
+    assert torch.equal(out["hyper"], q["hyper"])
+    assert torch.equal(out["feat"], q["feat"])
+    assert torch.equal(out["scaling"], q["scaling"])
+    m3 = q["masks"].repeat_interleave(3, dim=1)
+    assert torch.equal(out["offsets"].reshape(-1, 3 * K), q["offsets"] * m3)
+    assert float(out["feat"].abs().max()) > 0 and float(out["offsets"].abs().max()) > 0
+
+
+def test_quantised_values_equal_the_scoring_pass_and_sizes_match_estimates():
+    pc = _model(6000)
+    enc = codec.encode_model(pc)
+    sel = pc.get_mask_anchor
+    idx = torch.nonzero(sel)[:, 0]
+    t = lambda x: x.detach().index_select(0, idx)
+    a = enc.quantised["anchor"]
+    (res, det) = multi_scale_generating(pc, a, t(pc._hyper_latent), t(pc._anchor_feat), t(pc._offset), t(pc.get_scaling),
+                                        binary_grid_masks=t(pc.get_mask), predict_bpp=True, return_sum_bits=True,
+                                        return_details=True)
+    assert torch.equal(det["feat_q"], enc.quantised["feat"]) and torch.equal(det["scaling_q"], enc.quantised["scaling"])
+    assert torch.allclose(a, t(pc.get_anchor), atol=0, rtol=0)
+    bits = codec.encoded_bits(enc)
+    est = dict(hyper=res[1], feat=res[2], scaling=res[3], offsets=res[4], masks=res[5])
+    for k in ("feat", "scaling", "offsets", "hyper", "masks"):
+        # 16-bit frequencies floor every probability at 2^-16 (the estimate floors at 1e-6 ~ 2^-20), so the real
+        # stream may be SHORTER than the estimate where the model is badly wrong; it must never be much longer
+        assert bits[k] < 1.03 * est[k] + 64 * (sum(lv.n for lv in enc.levels) // codec.CHUNK_ROWS + 8), (k, bits[k], est[k])
+    assert bits["anchor"] == 48 * a.shape[0]
+
+
+def test_table_streams_are_byte_identical_to_the_cpu_range_coder():
+    pc = _model(700)
+    enc = codec.encode_model(pc, chunk_rows=32)
+    q = enc.quantised
+    p1 = enc.meta["prob_masks"]
+    tb = codec.frequency_tables(torch.tensor([[max(1.0 - p1, 1e-9), max(p1, 1e-9)]]))[0].tolist()
+    rows = 32 * 8
+    data = enc.mask_bytes.cpu().numpy().tobytes()
+    lens = enc.mask_lens.tolist()
+    masks = q["masks"].to(torch.int64).cpu()
+    off = 0
+    for c, n in enumerate(lens):
+        syms = masks[c * rows:(c + 1) * rows].reshape(-1).tolist()
+        chunk = data[off:off + n]
+        assert codec_ref.encode(syms, lambda i: 0, [tb]) == chunk
+        assert codec_ref.decode(chunk, len(syms), lambda i: 0, [tb]) == syms
+        off += n
+    assert off == len(data)
+    # hyper stream of the first chunk: one table per channel
+    median = pc.latent_codec.quantiles[:, 0, 1].detach()
+    hsym = (torch.round(q["hyper"] - median.view(1, -1)).to(torch.int64) - enc.meta["hyper_min"]).cpu()
+    tabs = codec._hyper_tables(pc, enc.meta["hyper_min"], enc.meta["hyper_max"]).tolist()
+    n0 = enc.hyper_lens.tolist()[0]
+    syms = hsym[:rows].reshape(-1).tolist()
+    assert codec_ref.encode(syms, lambda i: i % 12, tabs) == enc.hyper_bytes.cpu().numpy().tobytes()[:n0]
+
+
+def test_directory_round_trip_and_render(tmp_path):
+    pc = _model(5000, kind="chair")
+    summary = pc.conduct_encoding(str(tmp_path))
+    assert "Encoded sizes in MB" in summary
+    for f in ("anchor.npy", "masks.b", "hyper.b", "feat0.b", "scaling1.b", "offsets2.b", "meta.b", "mlp.pt"):
+        assert (tmp_path / f).exists()
+    assert np.load(tmp_path / "anchor.npy").dtype == np.uint16
+    dec = GaussianModel(device="cuda")
+    dec.conduct_decoding(str(tmp_path))
+    dec.eval()
+    assert dec.decoded_version
+    # reference: the same model decoded in memory through the scoring pass (train.py:301-314 -> replace parameters)
+    sel = pc.get_mask_anchor
+    idx = torch.nonzero(sel)[:, 0]
+    t = lambda x: x.detach().index_select(0, idx)
+    a = t(pc.get_anchor)
+    fq, sq, oq = multi_scale_generating(pc, a, t(pc._hyper_latent), t(pc._anchor_feat), t(pc._offset), t(pc.get_scaling),
+                                        binary_grid_masks=t(pc.get_mask))
+    assert torch.equal(dec._anchor_feat, fq) and torch.equal(dec._scaling, sq) and torch.equal(dec._anchor, a)
+    assert torch.equal(dec._offset * dec._mask, oq * t(pc.get_mask))
+    cams = synthetic.make_cameras("chair", 2, device="cuda", W=320, H=200)
+    pipe = type("Pipe", (), {"debug": False})()
+    bg = torch.zeros(3, device="cuda")
+    ref = GaussianModel(device="cuda")
+    ref.load_state_dict({k: v for k, v in pc.state_dict().items() if not k.startswith("_")}, strict=False)
+    ref._rotation = torch.nn.Parameter(t(pc._rotation), requires_grad=False)
+    ref.replace_with_decoded(a, t(pc._hyper_latent), fq, oq, sq, t(pc.get_mask))
+    ref.eval()
+    dec._rotation = torch.nn.Parameter(t(pc._rotation), requires_grad=False)
+    for cam in cams:
+        with torch.no_grad():
+            i1 = render(cam, dec, pipe, bg, visible_mask=prefilter_voxel(cam, dec, pipe, bg))["render"]
+            i2 = render(cam, ref, pipe, bg, visible_mask=prefilter_voxel(cam, ref, pipe, bg))["render"]
+        assert torch.equal(i1, i2) and float(i1.max()) > 0
