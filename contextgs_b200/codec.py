@@ -10,7 +10,7 @@ offsets{L}.b, meta.b, mlp.pt).  The byte format of the .b streams is this librar
 decoding returns the encoder's quantised tensors bit for bit.
 
 Everything heavy runs on the GPU: one level kernel (cgs_context_level_umma_forward_ex) produces the
-(mean, scale, Q) of every coded value, one thread per 128-row chunk range-codes it in closed form.
+(mean, scale, Q) of every coded value, one thread per ~1600-symbol chunk range-codes it in closed form.
 The host only builds two tiny frequency tables and concatenates streams.
 """
 import os
@@ -23,8 +23,14 @@ from . import _lib
 from .context_model import build_level_plan, find_divide_scale, pack_grid_weights_umma
 from .encodings import Q_anchor, Quantize_anchor
 
-CHUNK_ROWS = 128          # level rows per independently coded chunk (the reference: 1000 anchors)
+# Level rows per independently coded chunk of a feat stream (the reference: 1000 anchors, coded one after the
+# other on the host).  One GPU thread codes one chunk, so the chunk size sets the parallelism: 32 rows = 1600 feat
+# symbols give ~47 k concurrent coders per million anchors for 0.3 % of side information (4-byte length + two
+# 16-bit alphabet bounds per chunk).  Streams with fewer values per row use proportionally more rows per chunk.
+CHUNK_ROWS = 32
 ATTRS = (("feat", 50), ("scaling", 6), ("offsets", 30))
+ATTR_CHUNK_MULT = (1, 8, 2)     # rows per chunk = CHUNK_ROWS * mult: ~1600 / 1536 / 1920 symbols per chunk
+TABLE_CHUNK_MULT = 4            # hyper (12 per row) and mask (10 per row) streams
 PARAM_LD = 176
 
 
@@ -140,7 +146,7 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS):
     # offset masks: one Bernoulli table
     p1 = float(masks.mean())
     mask_tables = frequency_tables(torch.tensor([[max(1.0 - p1, 1e-9), max(p1, 1e-9)]]))
-    mask_bytes, mask_lens = _table_encode(masks.to(torch.int16).contiguous(), mask_tables, chunk_rows * 8, err)
+    mask_bytes, mask_lens = _table_encode(masks.to(torch.int16).contiguous(), mask_tables, chunk_rows * TABLE_CHUNK_MULT, err)
 
     # hyper latents under the factorised prior
     hyper_q, _ = pc.latent_codec(hyper, training=False)
@@ -148,7 +154,8 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS):
     hsym = torch.round(hyper_q - median.view(1, -1)).to(torch.int32)
     hmin, hmax = int(hsym.min()), int(hsym.max())
     hyper_tables = _hyper_tables(pc, hmin, hmax)
-    hyper_bytes, hyper_lens = _table_encode((hsym - hmin).to(torch.int16).contiguous(), hyper_tables, chunk_rows * 8, err)
+    hyper_bytes, hyper_lens = _table_encode((hsym - hmin).to(torch.int16).contiguous(), hyper_tables,
+                                            chunk_rows * TABLE_CHUNK_MULT, err)
     if getattr(pc, "disable_hyper", False):
         hyper_q = hyper_q * 0
 
@@ -169,15 +176,16 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS):
             continue
         params = _level_params(pc, lv, anchor, hyper_q, feat, scaling, offsets, masks, feat_q, scaling_q, offsets_q,
                                sums[4 * li:4 * li + 4], terr, means, False)
-        n_chunks = (lv.n + chunk_rows - 1) // chunk_rows
         for attr, (name, dim) in enumerate(ATTRS):
-            cap = int(L.cgs_codec_gauss_stream_capacity(attr, chunk_rows))
+            rows = chunk_rows * ATTR_CHUNK_MULT[attr]
+            n_chunks = (lv.n + rows - 1) // rows
+            cap = int(L.cgs_codec_gauss_stream_capacity(attr, rows))
             scratch = torch.empty(n_chunks * cap // 4, dtype=torch.int32, device=dev)
             lens = torch.zeros(n_chunks, dtype=torch.int32, device=dev)
             minmax = torch.zeros((n_chunks, 2), dtype=torch.int32, device=dev)
             nsym = torch.zeros(n_chunks, dtype=torch.int32, device=dev)
             values = (feat_q, scaling_q, offsets_q)[attr]
-            _lib.check(L.cgs_codec_gauss_encode(attr, _lib.ptr(lv.orig), lv.n, chunk_rows, _lib.ptr(params), _lib.ptr(masks),
+            _lib.check(L.cgs_codec_gauss_encode(attr, _lib.ptr(lv.orig), lv.n, rows, _lib.ptr(params), _lib.ptr(masks),
                                                 _lib.ptr(values), _lib.ptr(scratch), cap, _lib.ptr(lens), _lib.ptr(minmax),
                                                 _lib.ptr(nsym), _lib.ptr(err), _lib.stream_ptr()), "cgs_codec_gauss_encode")
             packed, _ = _pack(scratch, cap, lens, dev)
@@ -227,12 +235,13 @@ def decode_model(pc, meta, anchor_q, mask_bytes, mask_lens, hyper_bytes, hyper_l
 
     p1 = meta["prob_masks"]
     mask_tables = frequency_tables(torch.tensor([[max(1.0 - p1, 1e-9), max(p1, 1e-9)]]))
-    masks = _table_decode(mask_bytes.to(dev), mask_lens.to(dev), N, K, mask_tables, chunk_rows * 8).float().contiguous()
+    masks = _table_decode(mask_bytes.to(dev), mask_lens.to(dev), N, K, mask_tables,
+                          chunk_rows * TABLE_CHUNK_MULT).float().contiguous()
 
     hmin, hmax = meta["hyper_min"], meta["hyper_max"]
     median = pc.latent_codec.quantiles[:, 0, 1].detach()
     hsym = _table_decode(hyper_bytes.to(dev), hyper_lens.to(dev), N, median.numel(), _hyper_tables(pc, hmin, hmax),
-                         chunk_rows * 8)
+                         chunk_rows * TABLE_CHUNK_MULT)
     hyper_q = ((hsym.to(torch.int32) + hmin).float() + median.view(1, -1)).contiguous()
     hyper_ctx = hyper_q * 0 if getattr(pc, "disable_hyper", False) else hyper_q
 
@@ -256,7 +265,8 @@ def decode_model(pc, meta, anchor_q, mask_bytes, mask_lens, hyper_bytes, hyper_l
             off = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=dev)
             torch.cumsum(lens.to(torch.int64), 0, out=off[1:])
             values = (feat_q, scaling_q, offsets_q)[attr]
-            _lib.check(L.cgs_codec_gauss_decode(attr, _lib.ptr(lv.orig), lv.n, chunk_rows, _lib.ptr(params), _lib.ptr(masks),
+            _lib.check(L.cgs_codec_gauss_decode(attr, _lib.ptr(lv.orig), lv.n, chunk_rows * ATTR_CHUNK_MULT[attr],
+                                                _lib.ptr(params), _lib.ptr(masks),
                                                 _lib.ptr(st.bytes.to(dev)), _lib.ptr(off), _lib.ptr(lens),
                                                 _lib.ptr(st.minmax.to(dev).to(torch.int32).contiguous()), _lib.ptr(values),
                                                 _lib.stream_ptr()), "cgs_codec_gauss_decode")
