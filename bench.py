@@ -157,10 +157,10 @@ def cam_to(cam, device):
 
 ALGO_BYTES = {
     # SURVEY.md 8d / DESIGN.md section 4: compulsory fp32 traffic of an ideal fused implementation
-    "visible_filter": lambda c: 44 * c["N"],
+    "visible_filter": lambda c: 37 * c["N"] + 4 * c["Nv"],   # fused prefilter: anchor 12 + scaling row 24 + mask 1; index list
     "compact_indices": lambda c: 1 * c["N"] + 4 * c["Nv"],
     "neural_gaussians_fwd": lambda c: 396 * c["Nv"] + 50 * c["Nv"] + 56 * c["P"],
-    "preprocess": lambda c: 116 * c["P"],
+    "preprocess": lambda c: 124 * c["P"],                    # 56 in + 60 out + 8 (packed tile rectangle)
     "depth_sort": lambda c: c["P"] * (4 + 4 * 16),
     # binning (csrc/raster_binning.cu): S = (super-tile, Gaussian) pairs, ~1.4 per Gaussian
     "scan_emit_pairs": lambda c: 12 * c["P"] + 8 * c["S"],
