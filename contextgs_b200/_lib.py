@@ -89,8 +89,8 @@ SIGNATURES = {
                                                   _PTR, _PTR, ctypes.c_float, ctypes.c_float, ctypes.c_float, _PTR, _PTR,
                                                   _PTR, _PTR, _PTR, _PTR, _PTR, c_int, _PTR]),
     "cgs_codec_gauss_stream_capacity": (c_int64, [c_int, c_int]),
-    "cgs_codec_gauss_encode": (c_int, [c_int, _PTR, c_int, c_int, _PTR, _PTR, _PTR, _PTR, c_int64, _PTR, _PTR, _PTR, _PTR,
-                                       _PTR]),
+    "cgs_codec_gauss_minmax": (c_int, [c_int, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR]),
+    "cgs_codec_gauss_encode": (c_int, [c_int, _PTR, c_int, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, c_int64, _PTR, _PTR, _PTR]),
     "cgs_codec_gauss_decode": (c_int, [c_int, _PTR, c_int, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR]),
     "cgs_codec_table_encode": (c_int, [_PTR, c_int, c_int, c_int, _PTR, c_int, c_int, _PTR, c_int64, _PTR, _PTR, _PTR]),
     "cgs_codec_table_decode": (c_int, [_PTR, _PTR, _PTR, c_int, c_int, c_int, _PTR, _PTR, c_int, c_int, _PTR, _PTR]),

@@ -24,13 +24,14 @@ from .context_model import build_level_plan, find_divide_scale, pack_grid_weight
 from .encodings import Q_anchor, Quantize_anchor
 
 # Level rows per independently coded chunk of a feat stream (the reference: 1000 anchors, coded one after the
-# other on the host).  One GPU thread codes one chunk, so the chunk size sets the parallelism: 32 rows = 1600 feat
-# symbols give ~47 k concurrent coders per million anchors for 0.3 % of side information (4-byte length + two
-# 16-bit alphabet bounds per chunk).  Streams with fewer values per row use proportionally more rows per chunk.
-CHUNK_ROWS = 32
+# other on the host).  One GPU thread codes one chunk and the kernel time is the serial latency of one coder, so
+# the chunk size sets the speed: 8 rows = 400 feat symbols give ~190 k concurrent coders per million anchors.
+# Side information per chunk: a 16-bit length (+ the coder's 5 flush bytes), ~1 % of a 700-byte chunk; the
+# alphabet bounds are per (level, attribute) stream.  Streams with fewer values per row use more rows per chunk.
+CHUNK_ROWS = 8
 ATTRS = (("feat", 50), ("scaling", 6), ("offsets", 30))
 ATTR_CHUNK_MULT = (1, 8, 2)     # rows per chunk = CHUNK_ROWS * mult: ~1600 / 1536 / 1920 symbols per chunk
-TABLE_CHUNK_MULT = 4            # hyper (12 per row) and mask (10 per row) streams
+TABLE_CHUNK_MULT = 4            # hyper (12 per row) and mask (10 per row) streams: 32 rows per chunk
 PARAM_LD = 176
 
 
@@ -182,14 +183,15 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS):
             cap = int(L.cgs_codec_gauss_stream_capacity(attr, rows))
             scratch = torch.empty(n_chunks * cap // 4, dtype=torch.int32, device=dev)
             lens = torch.zeros(n_chunks, dtype=torch.int32, device=dev)
-            minmax = torch.zeros((n_chunks, 2), dtype=torch.int32, device=dev)
-            nsym = torch.zeros(n_chunks, dtype=torch.int32, device=dev)
+            minmax = torch.empty(2, dtype=torch.int32, device=dev)
             values = (feat_q, scaling_q, offsets_q)[attr]
+            _lib.check(L.cgs_codec_gauss_minmax(attr, _lib.ptr(lv.orig), lv.n, _lib.ptr(params), _lib.ptr(masks),
+                                                _lib.ptr(values), _lib.ptr(minmax), _lib.stream_ptr()), "cgs_codec_gauss_minmax")
             _lib.check(L.cgs_codec_gauss_encode(attr, _lib.ptr(lv.orig), lv.n, rows, _lib.ptr(params), _lib.ptr(masks),
-                                                _lib.ptr(values), _lib.ptr(scratch), cap, _lib.ptr(lens), _lib.ptr(minmax),
-                                                _lib.ptr(nsym), _lib.ptr(err), _lib.stream_ptr()), "cgs_codec_gauss_encode")
+                                                _lib.ptr(values), _lib.ptr(minmax), _lib.ptr(scratch), cap, _lib.ptr(lens),
+                                                _lib.ptr(err), _lib.stream_ptr()), "cgs_codec_gauss_encode")
             packed, _ = _pack(scratch, cap, lens, dev)
-            entry.streams[name] = SimpleNamespace(bytes=packed, lens=lens, minmax=minmax.to(torch.int16), nsym=nsym)
+            entry.streams[name] = SimpleNamespace(bytes=packed, lens=lens, minmax=minmax)
     e, te = int(err.item()), int(terr.item())
     if te:
         raise _lib.CgsError("cgs_context_level_umma_forward_ex: a tensor-core completion barrier timed out")
@@ -211,12 +213,12 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS):
 
 def encoded_bits(enc):
     """Size of every part of the encoding in bits (payload + per-chunk side information)."""
-    side = lambda lens: 32 * lens.numel()
+    side = lambda lens: 16 * lens.numel()    # chunk lengths are stored as 16-bit integers
     bits = dict(anchor=16 * enc.anchor_q.numel(), masks=8 * enc.mask_bytes.numel() + side(enc.mask_lens) + 32,
                 hyper=8 * enc.hyper_bytes.numel() + side(enc.hyper_lens) + 32, feat=0, scaling=0, offsets=0)
     for lv in enc.levels:
         for name, st in lv.streams.items():
-            bits[name] += 8 * st.bytes.numel() + (32 + 32) * st.lens.numel()   # length + (min, max) as 2 x int16
+            bits[name] += 8 * st.bytes.numel() + 16 * st.lens.numel() + 64   # 16-bit chunk lengths + the stream's (min, max)
     bits["total"] = sum(bits.values())
     return bits
 
@@ -288,17 +290,19 @@ def conduct_encoding(pc, pre_path_name, chunk_rows=CHUNK_ROWS):
     """scene/gaussian_model.py:1005-1300: writes anchor.npy, masks.b, hyper.b, {feat,scaling,offsets}{level}.b,
     meta.b, mlp.pt under `pre_path_name`; returns the reference's size summary string."""
     os.makedirs(pre_path_name, exist_ok=True)
+    if chunk_rows * max(ATTR_CHUNK_MULT) * 6 * 2 + 16 > 65535 or chunk_rows * TABLE_CHUNK_MULT * 12 * 2 + 16 > 65535:
+        raise ValueError("chunk_rows too large for the 16-bit chunk lengths of the directory format")
     enc = encode_model(pc, chunk_rows)
     np.save(os.path.join(pre_path_name, "anchor.npy"), enc.anchor_q.cpu().numpy().view(np.uint16))
     wr = lambda name, t: t.cpu().numpy().tofile(os.path.join(pre_path_name, name))
     wr("masks.b", enc.mask_bytes)
     wr("hyper.b", enc.hyper_bytes)
-    side = dict(mask_lens=enc.mask_lens.cpu(), hyper_lens=enc.hyper_lens.cpu(), levels=[])
+    side = dict(mask_lens=enc.mask_lens.cpu().to(torch.int16), hyper_lens=enc.hyper_lens.cpu().to(torch.int16), levels=[])
     for lv in enc.levels:
         ent = dict(level=lv.level, n=lv.n, streams={})
         for name, st in lv.streams.items():
             wr(f"{name}{lv.level}.b", st.bytes)
-            ent["streams"][name] = dict(lens=st.lens.cpu(), minmax=st.minmax.cpu())
+            ent["streams"][name] = dict(lens=st.lens.cpu().to(torch.int16), minmax=st.minmax.cpu())
         side["levels"].append(ent)
     torch.save(dict(meta=enc.meta, side=side), os.path.join(pre_path_name, "meta.b"))
     torch.save(_mlp_state(pc), os.path.join(pre_path_name, "mlp.pt"))
@@ -318,13 +322,15 @@ def conduct_decoding(pc, pre_path_name):
     blob = torch.load(os.path.join(pre_path_name, "meta.b"), weights_only=False)
     meta, side = blob["meta"], blob["side"]
     rd = lambda name: torch.from_numpy(np.fromfile(os.path.join(pre_path_name, name), dtype=np.uint8)).to(dev)
+    u16 = lambda t: t.to(torch.int32) & 0xffff
     anchor_q = torch.from_numpy(np.load(os.path.join(pre_path_name, "anchor.npy")).astype(np.int32)).to(dev)
     levels = []
     for ent in side["levels"]:
         lv = SimpleNamespace(level=ent["level"], n=ent["n"], streams={})
         for name, st in ent["streams"].items():
-            lv.streams[name] = SimpleNamespace(bytes=rd(f"{name}{ent['level']}.b"), lens=st["lens"], minmax=st["minmax"])
+            lv.streams[name] = SimpleNamespace(bytes=rd(f"{name}{ent['level']}.b"), lens=u16(st["lens"]), minmax=st["minmax"])
         levels.append(lv)
-    out = decode_model(pc, meta, anchor_q, rd("masks.b"), side["mask_lens"], rd("hyper.b"), side["hyper_lens"], levels)
+    out = decode_model(pc, meta, anchor_q, rd("masks.b"), u16(side["mask_lens"]), rd("hyper.b"), u16(side["hyper_lens"]),
+                       levels)
     pc.replace_with_decoded(out["anchor"], out["hyper"], out["feat"], out["offsets"], out["scaling"], out["masks"])
     return out

@@ -12,7 +12,8 @@
 // tree, its stream format cannot be pinned): parity = encode -> decode returns the quantised tensors bit
 // for bit, and the stream length matches the estimated bits.
 //
-// Cumulative frequency of symbol index i in [0, L] (alphabet = the stream's [smin, smax], L = smax - smin + 1):
+// Cumulative frequency of symbol index i in [0, L] (alphabet = [smin, smax] of the whole (level, attribute)
+// stream, found by a parallel pre-pass; L = smax - smin + 1):
 //   C(i) = min(rn(Phi(((smin + i) - 0.5) * Q; mean, scale) * (65536 - L)), 65536 - L) + i
 // (the "+ i" keeps every symbol codable, as torchac's _convert_to_int_and_normalize does).
 #include "entropy_math.cuh"
@@ -111,7 +112,7 @@ struct Decoder {
 __device__ __forceinline__ uint32_t gauss_cum(int s, int smin, int L, float Q, float mean, float inv_scale)
 {
     const float z = ((float)s - 0.5f) * Q;
-    const float phi = normal_cdf(z, mean, inv_scale);
+    const float phi = 0.5f * (1.0f + erff((z - mean) * inv_scale * 0.70710678118654752f));
     const uint32_t M = 65536u - (uint32_t)L;
     uint32_t c = __float2uint_rn(phi * (float)M);
     c = c > M ? M : c;
@@ -130,18 +131,14 @@ __device__ __forceinline__ bool coded(const GaussStream &g, int o, int k)
     return g.attr != 2 || g.mask[(size_t)o * 10 + k / 3] != 0.0f;
 }
 
-// One thread per chunk: [stream_minmax] pass (alphabet of the chunk) then the coding pass.
-__global__ void __launch_bounds__(64)
-gauss_encode_kernel(GaussStream g, const float *__restrict__ values /* [N][dim], quantised */, uint32_t *__restrict__ out,
-                    uint32_t cap_bytes, int32_t *__restrict__ stream_len, int32_t *__restrict__ stream_minmax,
-                    int32_t *__restrict__ stream_syms, int32_t *__restrict__ err)
+// Alphabet of one (level, attribute) stream: min / max of rint(value / Q) over all its coded values.
+// One thread per level row, warp-reduced, two atomics per warp.
+__global__ void __launch_bounds__(256)
+gauss_minmax_kernel(GaussStream g, const float *__restrict__ values, int32_t *__restrict__ minmax)
 {
-    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_chunks = (g.n_rows + g.chunk_rows - 1) / g.chunk_rows;
-    if (chunk >= n_chunks) return;
-    const int r0 = chunk * g.chunk_rows, r1 = min(r0 + g.chunk_rows, g.n_rows);
-    int smin = 0x7fffffff, smax = -0x7fffffff, nsym = 0;
-    for (int r = r0; r < r1; ++r) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int smin = 0x7fffffff, smax = -0x7fffffff;
+    if (r < g.n_rows) {
         const int o = g.orig_idx[r];
         const float Q = g.params[(size_t)r * kLdG2 + 172 + g.attr];
         const float *x = values + (size_t)o * g.dim;
@@ -150,16 +147,34 @@ gauss_encode_kernel(GaussStream g, const float *__restrict__ values /* [N][dim],
             const int s = (int)rintf(__fdiv_rn(x[k], Q));
             smin = min(smin, s);
             smax = max(smax, s);
-            ++nsym;
         }
     }
-    if (nsym == 0) { smin = 0; smax = 0; }
-    stream_minmax[2 * chunk] = smin;
-    stream_minmax[2 * chunk + 1] = smax;
-    stream_syms[chunk] = nsym;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+        smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && smin <= smax) {
+        atomicMin(&minmax[0], smin);
+        atomicMax(&minmax[1], smax);
+    }
+}
+
+// One thread per chunk.  The next symbol's value / mean / scale are fetched before the current symbol is coded:
+// the coder's carried state (low, range) is the only true dependency between symbols.
+__global__ void __launch_bounds__(64)
+gauss_encode_kernel(GaussStream g, const float *__restrict__ values /* [N][dim], quantised */,
+                    const int32_t *__restrict__ minmax, uint32_t *__restrict__ out, uint32_t cap_bytes,
+                    int32_t *__restrict__ stream_len, int32_t *__restrict__ err)
+{
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_chunks = (g.n_rows + g.chunk_rows - 1) / g.chunk_rows;
+    if (chunk >= n_chunks) return;
+    const int r0 = chunk * g.chunk_rows, r1 = min(r0 + g.chunk_rows, g.n_rows);
+    const int smin = minmax[0], smax = minmax[1];
     const int L = smax - smin + 1;
-    if (L > 32768) {   // cannot happen after the +-15000-step clamp of STE_multistep (utils/encodings.py:203-216)
-        atomicExch(err, 2);
+    if (smax < smin || L > 32768) {   // empty stream / cannot happen after the +-15000-step clamp of STE_multistep
+        if (smax >= smin) atomicExch(err, 2);
         stream_len[chunk] = 0;
         return;
     }
@@ -170,13 +185,17 @@ gauss_encode_kernel(GaussStream g, const float *__restrict__ values /* [N][dim],
         const float *pr = g.params + (size_t)r * kLdG2;
         const float Q = pr[172 + g.attr];
         const float *x = values + (size_t)o * g.dim;
+        float xv = x[0], mv = pr[g.col0], sv = pr[kCE + g.col0];
         for (int k = 0; k < g.dim; ++k) {
+            const float xc = xv, mean = mv, sc = sv;
+            if (k + 1 < g.dim) {
+                xv = x[k + 1]; mv = pr[g.col0 + k + 1]; sv = pr[kCE + g.col0 + k + 1];
+            }
             if (!coded(g, o, k)) continue;
-            const int s = (int)rintf(__fdiv_rn(x[k], Q));
-            const float mean = pr[g.col0 + k];
-            const float inv = __frcp_rn(fmaxf(pr[kCE + g.col0 + k], 1e-9f));
+            const int s = (int)rintf(__fdiv_rn(xc, Q));
+            const float inv = __frcp_rn(fmaxf(sc, 1e-9f));
             const uint32_t lo = gauss_cum(s, smin, L, Q, mean, inv), hi = gauss_cum(s + 1, smin, L, Q, mean, inv);
-            if (hi <= lo) {   // erf not monotone at rounding level: the symbol would be undecodable
+            if (hi <= lo || s < smin || s > smax) {   // erf not monotone at rounding level: the symbol would be undecodable
                 atomicExch(err, 1);
                 continue;
             }
@@ -189,14 +208,14 @@ gauss_encode_kernel(GaussStream g, const float *__restrict__ values /* [N][dim],
 
 __global__ void __launch_bounds__(64)
 gauss_decode_kernel(GaussStream g, const uint8_t *__restrict__ bytes, const int64_t *__restrict__ stream_off,
-                    const int32_t *__restrict__ stream_len, const int32_t *__restrict__ stream_minmax,
+                    const int32_t *__restrict__ stream_len, const int32_t *__restrict__ minmax,
                     float *__restrict__ values /* [N][dim] out */)
 {
     const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_chunks = (g.n_rows + g.chunk_rows - 1) / g.chunk_rows;
     if (chunk >= n_chunks) return;
     const int r0 = chunk * g.chunk_rows, r1 = min(r0 + g.chunk_rows, g.n_rows);
-    const int smin = stream_minmax[2 * chunk], smax = stream_minmax[2 * chunk + 1];
+    const int smin = minmax[0], smax = minmax[1];
     const int L = smax - smin + 1;
     Decoder dec;
     dec.init(bytes + stream_off[chunk], (uint32_t)stream_len[chunk]);
@@ -316,16 +335,33 @@ extern "C" int64_t cgs_codec_gauss_stream_capacity(int attr, int chunk_rows)
     return ((int64_t)2 * dim * chunk_rows + 16 + 3) / 4 * 4;   // <= 16 bits per symbol + flush
 }
 
+extern "C" int cgs_codec_gauss_minmax(int attr, const int32_t *orig_idx, int n_rows, const float *params,
+                                      const float *mask, const float *values, int32_t *minmax, void *stream)
+{
+    codec::GaussStream g;
+    if (int e = attr_layout(attr, &g.dim, &g.col0)) return e;
+    CGS_CHECK_PTR(minmax);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(minmax, 0x7f, sizeof(int32_t), st);        // +2139062143
+    cudaMemsetAsync(minmax + 1, 0x80, sizeof(int32_t), st);    // -2139062144: an empty stream keeps max < min
+    if (n_rows <= 0) return check_launch(__func__);
+    CGS_CHECK_PTR(orig_idx); CGS_CHECK_PTR(params); CGS_CHECK_PTR(values);
+    if (attr == 2) CGS_CHECK_PTR(mask);
+    g.orig_idx = orig_idx; g.params = params; g.mask = mask; g.n_rows = n_rows; g.chunk_rows = 1; g.attr = attr;
+    StageScope sc(ST_CODEC, st, 1);
+    codec::gauss_minmax_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(g, values, minmax);
+    return check_launch(__func__);
+}
+
 extern "C" int cgs_codec_gauss_encode(int attr, const int32_t *orig_idx, int n_rows, int chunk_rows, const float *params,
-                                      const float *mask, const float *values, uint32_t *scratch, int64_t cap_bytes,
-                                      int32_t *stream_len, int32_t *stream_minmax, int32_t *stream_syms, int32_t *err,
-                                      void *stream)
+                                      const float *mask, const float *values, const int32_t *minmax, uint32_t *scratch,
+                                      int64_t cap_bytes, int32_t *stream_len, int32_t *err, void *stream)
 {
     if (n_rows <= 0) return 0;
     codec::GaussStream g;
     if (int e = attr_layout(attr, &g.dim, &g.col0)) return e;
     CGS_CHECK_PTR(orig_idx); CGS_CHECK_PTR(params); CGS_CHECK_PTR(values); CGS_CHECK_PTR(scratch);
-    CGS_CHECK_PTR(stream_len); CGS_CHECK_PTR(stream_minmax); CGS_CHECK_PTR(stream_syms); CGS_CHECK_PTR(err);
+    CGS_CHECK_PTR(stream_len); CGS_CHECK_PTR(minmax); CGS_CHECK_PTR(err);
     if (attr == 2) CGS_CHECK_PTR(mask);
     if (chunk_rows <= 0 || cap_bytes < cgs_codec_gauss_stream_capacity(attr, chunk_rows) || (cap_bytes & 3)) {
         set_error("%s: invalid chunk size / stream capacity", __func__);
@@ -335,19 +371,19 @@ extern "C" int cgs_codec_gauss_encode(int attr, const int32_t *orig_idx, int n_r
     const int n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
     StageScope sc(ST_CODEC, static_cast<cudaStream_t>(stream), 1);
     codec::gauss_encode_kernel<<<(n_chunks + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-        g, values, scratch, (uint32_t)cap_bytes, stream_len, stream_minmax, stream_syms, err);
+        g, values, minmax, scratch, (uint32_t)cap_bytes, stream_len, err);
     return check_launch(__func__);
 }
 
 extern "C" int cgs_codec_gauss_decode(int attr, const int32_t *orig_idx, int n_rows, int chunk_rows, const float *params,
                                       const float *mask, const uint8_t *bytes, const int64_t *stream_off,
-                                      const int32_t *stream_len, const int32_t *stream_minmax, float *values, void *stream)
+                                      const int32_t *stream_len, const int32_t *minmax, float *values, void *stream)
 {
     if (n_rows <= 0) return 0;
     codec::GaussStream g;
     if (int e = attr_layout(attr, &g.dim, &g.col0)) return e;
     CGS_CHECK_PTR(orig_idx); CGS_CHECK_PTR(params); CGS_CHECK_PTR(bytes); CGS_CHECK_PTR(stream_off);
-    CGS_CHECK_PTR(stream_len); CGS_CHECK_PTR(stream_minmax); CGS_CHECK_PTR(values);
+    CGS_CHECK_PTR(stream_len); CGS_CHECK_PTR(minmax); CGS_CHECK_PTR(values);
     if (attr == 2) CGS_CHECK_PTR(mask);
     if (chunk_rows <= 0) {
         set_error("%s: invalid chunk size", __func__);
@@ -357,7 +393,7 @@ extern "C" int cgs_codec_gauss_decode(int attr, const int32_t *orig_idx, int n_r
     const int n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
     StageScope sc(ST_CODEC, static_cast<cudaStream_t>(stream), 1);
     codec::gauss_decode_kernel<<<(n_chunks + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-        g, bytes, stream_off, stream_len, stream_minmax, values);
+        g, bytes, stream_off, stream_len, minmax, values);
     return check_launch(__func__);
 }
 

@@ -397,19 +397,22 @@ CGS_API int cgs_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in,
  *
  * Gaussian streams, per level and attribute (attr 0 feat[.,50] / 1 scaling[.,6] / 2 offsets[.,30]; offsets whose
  * mask[anchor][k/3] is 0 are not coded and decode to 0):
- *   chunk c = level rows [c*chunk_rows, (c+1)*chunk_rows); symbol = rint(value / Q), alphabet = the chunk's
- *   [stream_minmax[2c], stream_minmax[2c+1]]; encode writes chunk c at scratch + c*cap_bytes (cap_bytes >=
- *   cgs_codec_gauss_stream_capacity) and its byte count to stream_len[c]; *err != 0 reports an uncodable symbol (1),
- *   an alphabet over 32768 (2) or a capacity overflow (3).  decode reads chunk c at bytes + stream_off[c] and
- *   writes value = symbol * Q at values[orig_idx[row]][k] -- bit-identical to the encoder's input. */
+ *   symbol = rint(value / Q); alphabet = minmax[0..1] (device int32 x2) = min / max symbol of the whole stream,
+ *   computed by cgs_codec_gauss_minmax (parallel pre-pass) and stored with the stream;
+ *   chunk c = level rows [c*chunk_rows, (c+1)*chunk_rows) is coded by ONE thread: encode writes it at
+ *   scratch + c*cap_bytes (cap_bytes >= cgs_codec_gauss_stream_capacity) and its byte count to stream_len[c];
+ *   *err != 0 reports an uncodable symbol (1), an alphabet over 32768 (2) or a capacity overflow (3).
+ *   decode reads chunk c at bytes + stream_off[c] and writes value = symbol * Q at values[orig_idx[row]][k] --
+ *   bit-identical to the encoder's input. */
 CGS_API int64_t cgs_codec_gauss_stream_capacity(int attr, int chunk_rows);
+CGS_API int cgs_codec_gauss_minmax(int attr, const int32_t *orig_idx, int n_rows, const float *params, const float *mask,
+                                   const float *values, int32_t *minmax, void *stream);
 CGS_API int cgs_codec_gauss_encode(int attr, const int32_t *orig_idx, int n_rows, int chunk_rows, const float *params,
-                                   const float *mask, const float *values, uint32_t *scratch, int64_t cap_bytes,
-                                   int32_t *stream_len, int32_t *stream_minmax, int32_t *stream_syms, int32_t *err,
-                                   void *stream);
+                                   const float *mask, const float *values, const int32_t *minmax, uint32_t *scratch,
+                                   int64_t cap_bytes, int32_t *stream_len, int32_t *err, void *stream);
 CGS_API int cgs_codec_gauss_decode(int attr, const int32_t *orig_idx, int n_rows, int chunk_rows, const float *params,
                                    const float *mask, const uint8_t *bytes, const int64_t *stream_off,
-                                   const int32_t *stream_len, const int32_t *stream_minmax, float *values, void *stream);
+                                   const int32_t *stream_len, const int32_t *minmax, float *values, void *stream);
 /* Static-table streams: symbols[n_rows][C] int16 (index into the table of channel c, tables[c % T][0..table_ld),
  * cumulative 16-bit frequencies, tables[.][len] = 65536); chunking and outputs as above. */
 CGS_API int cgs_codec_table_encode(const int16_t *symbols, int n_rows, int C, int chunk_rows, const uint32_t *tables,
