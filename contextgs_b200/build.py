@@ -40,6 +40,7 @@ SOURCES = {
     "context_model_umma.cu": ["-fmad=false"],
     "level_divide.cu": ["-fmad=false"],
     "entropy_codec.cu": ["-fmad=false"],
+    "loss.cu": [],
 }
 
 

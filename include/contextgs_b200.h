@@ -425,6 +425,18 @@ CGS_API int cgs_codec_table_decode(const uint8_t *bytes, const int64_t *stream_o
 CGS_API int cgs_codec_pack_streams(const uint32_t *scratch, int64_t cap_bytes, const int32_t *stream_len,
                                    const int64_t *stream_off, int n_streams, uint8_t *packed, void *stream);
 
+/* ------------------------------------------------------------------ photometric loss
+ * Fused replacement of `l1_loss` and `ssim` (utils/loss_utils.py:17-18,33-64; consumer train.py:200-204) for
+ * [3,H,W] fp32 images: 11x11 Gaussian window (sigma 1.5, zero padding), C1 = 0.01^2, C2 = 0.03^2.
+ *   forward : sums[0] = sum |img - gt|, sums[1] = sum of the SSIM map (device fp64; divide by 3*H*W for the means);
+ *             dm / dp / dq [3,H,W] (optional, all or none) receive d ssim / d (G*x), d (G*x^2), d (G*xy) for the backward.
+ *   backward: d_img = g_l1 * sign(img - gt) / n + g_ssim * d mean(ssim) / d img, n = 3*H*W; g_l1 / g_ssim are DEVICE
+ *             scalars (the gradients arriving on the two means; NULL = term absent).  gt receives no gradient. */
+CGS_API int cgs_l1_ssim_forward(const float *img, const float *gt, int H, int W, float *dm, float *dp, float *dq,
+                                double *sums, void *stream);
+CGS_API int cgs_l1_ssim_backward(const float *img, const float *gt, int H, int W, const float *dm, const float *dp,
+                                 const float *dq, const float *g_l1, const float *g_ssim, float *d_img, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
