@@ -442,6 +442,7 @@ def extras(args, pc, pc_train, cams_dev, my_cam, pipe, bg, timed, world, dev):
     k = max(4, args.steps // 4)
 
     from contextgs_b200.renderer import render
+    from contextgs_b200.loss_utils import l1_ssim
 
     def train_step(i, step):
         """One training iteration of train.py:158-211 without the optimizer: prefilter, render (G1 + rasterizer,
@@ -450,7 +451,8 @@ def extras(args, pc, pc_train, cams_dev, my_cam, pipe, bg, timed, world, dev):
         with torch.no_grad():
             vis = prefilter_voxel(cam, pc_train, pipe, bg)
         out = render(cam, pc_train, pipe, bg, visible_mask=vis, retain_grad=False, step=step)
-        loss = (out["render"] - gt).abs().mean() + 0.01 * out["scaling"].prod(dim=1).mean()
+        Ll1, ssim_v = l1_ssim(out["render"], gt)                       # train.py:200-204, lambda_dssim = 0.2
+        loss = 0.8 * Ll1 + 0.2 * (1.0 - ssim_v) + 0.01 * out["scaling"].prod(dim=1).mean()
         if out["bit_per_param"] is not None:
             loss = loss + 0.004 * out["bit_per_param"]
         loss.backward()
@@ -465,8 +467,30 @@ def extras(args, pc, pc_train, cams_dev, my_cam, pipe, bg, timed, world, dev):
     ex["train_iter_per_s_render_only"] = world * k / (ms * 1e-3)
     ms = timed(lambda i: train_step(i, 20000), k, 3)
     ex["train_iter_per_s_with_context_model"] = world * k / (ms * 1e-3)
+    # the photometric loss alone: fused kernels vs the reference's expression (5 grouped 11x11 convolutions + autograd)
+    img = torch.rand(3, H, W, device=dev)
+
+    def loss_fused(i):
+        a = img.detach().requires_grad_(True)
+        l1, sv = l1_ssim(a, gt)
+        (0.8 * l1 + 0.2 * (1.0 - sv)).backward()
+
+    def loss_torch(i):
+        import torch.nn.functional as F
+        a = img.detach().requires_grad_(True)
+        g1 = torch.tensor([math.exp(-(x - 5) ** 2 / 4.5) for x in range(11)], device=dev)
+        g1 = (g1 / g1.sum()).unsqueeze(1)
+        w = g1.mm(g1.t()).expand(3, 1, 11, 11).contiguous()
+        c = lambda t: F.conv2d(t, w, padding=5, groups=3)
+        mu1, mu2 = c(a), c(gt)
+        s11, s22, s12 = c(a * a) - mu1 * mu1, c(gt * gt) - mu2 * mu2, c(a * gt) - mu1 * mu2
+        sm = ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 * mu1 + mu2 * mu2 + 1e-4) * (s11 + s22 + 9e-4))
+        (0.8 * (a - gt).abs().mean() + 0.2 * (1.0 - sm.mean())).backward()
+    ex["loss_fwd_bwd_ms_fused"] = timed(loss_fused, 20, 3) / 20
+    ex["loss_fwd_bwd_ms_torch_expression"] = timed(loss_torch, 20, 3) / 20
     ex["train_note"] = ("forward + backward of one camera per rank on the NON-decoded model (train.py:158-211 without "
-                        "optimizer.step): render_only = step <= 3000 regime; with_context_model = step > 10000 regime "
+                        "optimizer.step; loss = 0.8 L1 + 0.2 (1 - SSIM) + 0.01 scaling reg (+ lambda bit_per_param), fused "
+                        "L1/SSIM kernels): render_only = step <= 3000 regime; with_context_model = step > 10000 regime "
                         "(3-level context model over all anchors, forward and backward, every iteration)")
 
     # entropy scoring: estimate_final_bits = 3-level context model + likelihoods over ALL anchors
