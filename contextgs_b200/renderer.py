@@ -128,6 +128,8 @@ def _render_inference(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, vi
     rst.last_num_rendered = R
     rst.last_num_pairs = st[_lib.STATUS_NUM_PAIRS]
     radii = radii[:P]
+    if P == 0:
+        color.zero_()   # upstream returns an all-zero image (not the background) when there is nothing to draw
     return {"render": color, "viewspace_points": screenspace[:P], "visibility_filter": vis_filter[:P], "radii": radii,
             "time_sub": 0}
 

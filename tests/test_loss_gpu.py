@@ -56,3 +56,18 @@ def test_identical_images_and_argument_checks():
         l1_ssim(x.cpu(), x.cpu())
     with pytest.raises(NotImplementedError):
         ssim(x, x, window_size=7)
+
+
+def test_images_smaller_than_the_window():
+    g = torch.Generator().manual_seed(7)
+    for H, W in ((1, 1), (3, 5), (11, 4)):
+        gt = torch.rand(3, H, W, generator=g)
+        img = torch.rand(3, H, W, generator=g)
+        a = img.cuda().requires_grad_(True)
+        l1, s = l1_ssim(a, gt.cuda())
+        (l1 - s).backward()
+        b = img.clone().requires_grad_(True)
+        r1, rs = loss_ref.l1_loss(b, gt), loss_ref.ssim(b, gt)
+        (r1 - rs).backward()
+        assert abs(float(l1) - float(r1)) < 1e-6 and abs(float(s) - float(rs)) < 1e-5
+        assert _rel(a.grad.cpu().numpy(), b.grad.numpy()) < 1e-4

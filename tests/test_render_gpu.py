@@ -113,3 +113,31 @@ def test_render_accepts_plain_and_modified_masks():
         b = render(cam, pc, pipe, bg, visible_mask=vis2.clone())
         assert torch.equal(a["render"], b["render"]) and a["radii"].shape == b["radii"].shape
         assert a["radii"].shape[0] < ref["radii"].shape[0]
+
+
+def test_nothing_visible_and_everything_masked_out():
+    """Edge cases of the fused frame: no visible anchor (camera looks away) and no Gaussian surviving the mask."""
+    import copy
+    pc, cams, pipe, bg = _setup()
+    bg = torch.tensor([0.2, 0.4, 0.6], device="cuda")
+    cam = copy.copy(cams[0])
+    # rotate the camera by 180 degrees about its own y axis: everything is behind it
+    flip = torch.diag(torch.tensor([-1.0, 1.0, -1.0, 1.0], device="cuda"))
+    cam.world_view_transform = (cam.world_view_transform @ flip).contiguous()
+    cam.full_proj_transform = (flip @ cam.full_proj_transform).contiguous() if False else \
+        (cam.world_view_transform @ (torch.linalg.inv(cams[0].world_view_transform) @ cams[0].full_proj_transform)).contiguous()
+    with torch.no_grad():
+        vis = prefilter_voxel(cam, pc, pipe, bg)
+        assert int(vis.sum()) == 0 and int(vis._cgs_compact[1].item()) == 0
+        out = render(cam, pc, pipe, bg, visible_mask=vis)
+    assert out["radii"].shape[0] == 0 and out["viewspace_points"].shape == (0, 3)
+    assert float(out["render"].abs().max()) == 0.0          # upstream: zeros, not the background, when P == 0
+    with torch.enable_grad():
+        slow = render(cam, pc, pipe, bg, visible_mask=vis)
+    assert torch.equal(out["render"], slow["render"].detach())
+    # all offsets masked out: anchors visible, no Gaussian emitted
+    with torch.no_grad():
+        pc._mask.zero_()
+        vis = prefilter_voxel(cams[0], pc, pipe, bg)
+        out = render(cams[0], pc, pipe, bg, visible_mask=vis)
+    assert int(vis.sum()) > 0 and out["radii"].shape[0] == 0 and float(out["render"].abs().max()) == 0.0
