@@ -100,6 +100,8 @@ SIGNATURES = {
     "cgs_context_level_backward_packed_floats": (c_int, [c_int]),
     "cgs_context_level_backward": (c_int, [c_int, _PTR, _PTR, _PTR, _PTR, c_int] + [_PTR] * 8 +
                                    [ctypes.c_float] * 3 + [_PTR, ctypes.c_float] + [_PTR] * 9),
+    "cgs_context_level_backward_rows": (c_int, [c_int, _PTR, _PTR, _PTR, _PTR, _PTR, c_int, c_int] + [_PTR] * 8 +
+                                        [ctypes.c_float] * 3 + [_PTR, ctypes.c_float] + [_PTR] * 9),
     "cgs_eb_backward": (c_int, [_PTR, c_int, _PTR, c_int, _PTR, _PTR, ctypes.c_float, _PTR, _PTR, _PTR]),
     "cgs_gaussian_bits_forward": (c_int, [_PTR, _PTR, _PTR, _PTR, c_int, ctypes.c_float, c_int64, c_int, _PTR, _PTR]),
     "cgs_gaussian_bits_backward": (c_int, [_PTR, _PTR, _PTR, _PTR, c_int, ctypes.c_float, c_int64, c_int, _PTR, _PTR,

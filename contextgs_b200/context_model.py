@@ -268,6 +268,16 @@ class _ContextModelTrain(torch.autograd.Function):
         per_param = torch.tensor(total_bits * factor, dtype=torch.float32, device=anchor.device)
         ctx.pc, ctx.plan, ctx.factor, ctx.means = pc, plan, factor, out["means"]
         ctx.level_noise = out["level_noise"]
+        # Row lists of the backward, without a host synchronisation: a stable sort moves the rows chosen for the
+        # bit-rate term to the front (their count per level came back with the bit sums above).
+        ctx.row_lists = []
+        for li, lv in enumerate(plan.levels):
+            if lv.n == 0:
+                ctx.row_lists.append(None)
+                continue
+            not_chosen = choose_u8[lv.orig.long()] == 0
+            perm = torch.argsort(not_chosen, stable=True).to(torch.int32)
+            ctx.row_lists.append((perm, int(round(s[4 * li + 3]))))
         ctx.save_for_backward(anchor, out["hyper_q"], out["feat_q"], out["scaling_q"], out["offsets_q"], masks, choose_u8,
                               eb_packed.detach(), *[w.detach() for w in w_bwd])
         return out["feat_q"], out["scaling_q"], out["offsets_q"], per_param
@@ -290,13 +300,19 @@ class _ContextModelTrain(torch.autograd.Function):
             if lv.n == 0:
                 continue
             in_dim = 15 if lv.ctx_src is None else 71
-            _lib.check(L.cgs_context_level_backward(
-                in_dim, _lib.ptr(w_bwd[li]), _lib.ptr(lv.orig), _lib.ptr(lv.ctx_src), _lib.ptr(lv.level_anchor), lv.n,
-                _lib.ptr(anchor), _lib.ptr(hyper_q), _lib.ptr(feat_q), _lib.ptr(scaling_q), _lib.ptr(offsets_q),
-                _lib.ptr(masks), _lib.ptr(choose_u8), _lib.ptr(ctx.level_noise[li]), ctx.means[0], ctx.means[1],
-                ctx.means[2], g_ptr, ctx.factor, _lib.ptr(G_f), _lib.ptr(G_s), _lib.ptr(G_o), _lib.ptr(d_mask),
-                _lib.ptr(d_hyper), _lib.ptr(d_anchor), _lib.ptr(d_w[li]), _lib.ptr(ticket), stream),
-                "cgs_context_level_backward")
+            # rows chosen for the bit-rate term take the full kernel, the other ~85 % the 3-output one
+            perm, n_full = ctx.row_lists[li]
+            row_lists = ((perm[:n_full], 0), (perm[n_full:], 1))
+            for rows, lite in row_lists:
+                if rows.numel() == 0:
+                    continue
+                _lib.check(L.cgs_context_level_backward_rows(
+                    in_dim, _lib.ptr(w_bwd[li]), _lib.ptr(lv.orig), _lib.ptr(lv.ctx_src), _lib.ptr(lv.level_anchor),
+                    _lib.ptr(rows), rows.numel(), lite, _lib.ptr(anchor), _lib.ptr(hyper_q), _lib.ptr(feat_q),
+                    _lib.ptr(scaling_q), _lib.ptr(offsets_q), _lib.ptr(masks), _lib.ptr(choose_u8),
+                    _lib.ptr(ctx.level_noise[li]), ctx.means[0], ctx.means[1], ctx.means[2], g_ptr, ctx.factor,
+                    _lib.ptr(G_f), _lib.ptr(G_s), _lib.ptr(G_o), _lib.ptr(d_mask), _lib.ptr(d_hyper), _lib.ptr(d_anchor),
+                    _lib.ptr(d_w[li]), _lib.ptr(ticket), stream), "cgs_context_level_backward_rows")
         if g_ptr is not None:
             _lib.check(L.cgs_eb_backward(_lib.ptr(eb_packed), eb_packed.shape[0], _lib.ptr(hyper_q), N,
                                          _lib.ptr(choose_u8), g_ptr, ctx.factor, _lib.ptr(d_hyper), _lib.ptr(d_eb),

@@ -39,6 +39,7 @@ struct Smem {
     float dQ[3 * kTM];
     int orig[kTM];
     int src[kTM];
+    int lrow[kTM];       // level row of each tile row (identity unless a row list is given)
     uint8_t chosen[kTM];
     int tile;
 };
@@ -60,6 +61,7 @@ struct Args {
     float *d_mask, *d_hyper_q, *d_anchor;          // [N,10] (+=), [N,12] (=), [N,3] (+=)
     float *d_w;                                    // packed layout, +=
     uint32_t *ticket;
+    const int *row_list;                           // optional: the level rows this launch processes (n_rows = its length)
 };
 
 // derivatives of bits = -log2(max(|Phi_hi - Phi_lo|, 1e-6)) * keep   (Low_bound: zero below the bound)
@@ -90,7 +92,11 @@ __device__ __forceinline__ void bits_grad(float x0, float mu, float s0, float q,
     }
 }
 
-template <int K1>
+// LITE = true: every row of the launch is NOT chosen for the bit-rate term (85 % of the anchors in training,
+// scene/gaussian_model.py:1658-1659), so its only path into the context MLP is through the three adaptive
+// quantisation steps (x_q = x + n Q): 3 of the 175 outputs.  The second-layer product, the W2 gradient and the
+// W2^T back-projection shrink from 175 to 3 columns and the likelihood derivative disappears.
+template <int K1, bool LITE>
 __global__ void __launch_bounds__(kMlpThreads, 1) context_level_backward_kernel(Args A)
 {
     using SM = Smem<K1>;
@@ -123,12 +129,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) context_level_backward_kernel(
         // ---- stage inputs exactly as the forward ------------------------------------------------
         {
             const int r = tid >> 2, q = tid & 3;
-            const int row = row0 + r;
-            if (row < A.n_rows) {
+            const int lrow_i = row0 + r;
+            if (lrow_i < A.n_rows) {
+                const int row = A.row_list ? A.row_list[lrow_i] : lrow_i;
                 const int o = A.orig_idx[row];
                 if (q == 0) {
                     S.orig[r] = o;
-                    S.chosen[r] = A.choose ? A.choose[o] : 1;
+                    S.lrow[r] = row;
+                    S.chosen[r] = LITE ? 0 : (A.choose ? A.choose[o] : 1);
                 }
                 if (K1 == kCtx + kHyper) {
                     const int s = A.ctx_src[row];
@@ -152,6 +160,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) context_level_backward_kernel(
                 if (q == 0) {
                     S.orig[r] = -1;
                     S.src[r] = -1;
+                    S.lrow[r] = 0;
                     S.chosen[r] = 0;
                 }
                 for (int k = q; k < K1; k += 4) S.x[k * kTMp + r] = 0.f;
@@ -162,7 +171,24 @@ __global__ void __launch_bounds__(kMlpThreads, 1) context_level_backward_kernel(
         // ---- recompute the forward activations ----------------------------------------------------
         tile_gemm<4, ACT_RELU>(S.x, K1, S.w + SM::kW1, kLd1, S.w + SM::kB1, kGH, S.h);
         __syncthreads();
-        tile_gemm<6, ACT_NONE>(S.h, kGH, S.w + SM::kW2, kLd2, S.w + SM::kB2, kGO, S.out);
+        if (!LITE) {
+            tile_gemm<6, ACT_NONE>(S.h, kGH, S.w + SM::kW2, kLd2, S.w + SM::kB2, kGO, S.out);
+        } else {
+            // only the three step outputs (columns 172..174); columns 168..171 share their weight-gradient block
+            // and must read as zero
+            if (tid < 3 * kTM) {
+                const int g = tid / kTM, r = tid - g * kTM;
+                const int n = 2 * kCE + g;
+                float acc = S.w[SM::kB2 + n];
+                for (int hh = 0; hh < kGH; ++hh) acc = fmaf(S.h[hh * kTMp + r], S.w[SM::kW2 + hh * kLd2 + n], acc);
+                S.out[n * kTMp + r] = acc;
+            } else if (tid < 4 * kTM) {
+                const int r = tid - 3 * kTM;
+#pragma unroll
+                for (int n = 168; n < 172; ++n) S.out[n * kTMp + r] = 0.f;
+                S.out[175 * kTMp + r] = 0.f;
+            }
+        }
         __syncthreads();
         if (tid < 3 * kTM) {
             const int g = tid / kTM, r = tid - g * kTM;
@@ -171,6 +197,32 @@ __global__ void __launch_bounds__(kMlpThreads, 1) context_level_backward_kernel(
         __syncthreads();
 
         // ---- per coded value: gradient of x_q, mean, scale, Q ----------------------------------------
+        if (LITE) {
+            // no bit-rate term on these rows: d x = d x_q (G stays as it is) and dQ_g = sum_j noise_j * G_j is a pure
+            // reduction -- four threads per row, no store between the loads, so all of them are in flight at once
+            const int r = tid >> 2, q = tid & 3;
+            const int o = S.orig[r];
+            float dq0 = 0.f, dq1 = 0.f, dq2 = 0.f;
+            if (o >= 0) {
+                const float *nz = A.noise + (size_t)S.lrow[r] * kCE;
+                const float *gf = A.G_feat + (size_t)o * kCF, *gs = A.G_scaling + (size_t)o * kCS;
+                const float *go = A.G_offsets + (size_t)o * kCO;
+                for (int j = q; j < kCF; j += 4) dq0 = fmaf(nz[j], gf[j], dq0);
+                for (int j = q; j < kCS; j += 4) dq1 = fmaf(nz[kCF + j], gs[j], dq1);
+                for (int j = q; j < kCO; j += 4) dq2 = fmaf(nz[kCF + kCS + j], go[j], dq2);
+            }
+#pragma unroll
+            for (int sft = 1; sft < 4; sft <<= 1) {
+                dq0 += __shfl_xor_sync(0xffffffffu, dq0, sft);
+                dq1 += __shfl_xor_sync(0xffffffffu, dq1, sft);
+                dq2 += __shfl_xor_sync(0xffffffffu, dq2, sft);
+            }
+            if (q == 0) {
+                S.dQ[0 * kTM + r] = dq0;
+                S.dQ[1 * kTM + r] = dq1;
+                S.dQ[2 * kTM + r] = dq2;
+            }
+        } else
         for (int e = tid; e < kTM * kCE; e += kMlpThreads) {
             const int r = e / kCE, j = e - r * kCE;
             const int o = S.orig[r];
@@ -207,11 +259,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) context_level_backward_kernel(
                     if (grp == 2) atomicAdd(A.d_mask + (size_t)o * 10 + (j - kCF - kCS) / 3, wbits * bits);
                 }
                 *G = gx_total;  // x_q = x + n Q  ->  d x = d x_q
-                dq += A.noise[(size_t)(row0 + r) * kCE + j] * gx_total;
+                dq += A.noise[(size_t)S.lrow[r] * kCE + j] * gx_total;
                 if (dq != 0.f) atomicAdd(&S.dQ[grp * kTM + r], dq);
             }
-            S.out[mrow * kTMp + r] = d_mean;
-            S.out[srow * kTMp + r] = d_scale;
+            if (!LITE) {
+                S.out[mrow * kTMp + r] = d_mean;
+                S.out[srow * kTMp + r] = d_scale;
+            }
         }
         __syncthreads();
         if (tid < 3 * kTM) {
@@ -225,15 +279,25 @@ __global__ void __launch_bounds__(kMlpThreads, 1) context_level_backward_kernel(
         __syncthreads();
 
         // ---- dW2 += h (x) d_out, db2 -------------------------------------------------------------------
-        if (tid < 250) outer_accumulate<7, 10>(S.out, 7 * w2_nb, kGO, S.h, 10 * w2_hb, kGH, gw2);
-        if (tid < kGO) {
+        if (tid < 250 && (!LITE || w2_nb == 24)) outer_accumulate<7, 10>(S.out, 7 * w2_nb, kGO, S.h, 10 * w2_hb, kGH, gw2);
+        if (tid < kGO && (!LITE || tid >= 2 * kCE)) {
             float s = 0.f;
             for (int r = 0; r < kTM; ++r) s += S.out[tid * kTMp + r];
             gb2 += s;
         }
         __syncthreads();
         // ---- d_h = (W2^T d_out) * relu'(h), in place ------------------------------------------------------
-        tile_gemm_relu_mask<4, true>(S.out, kGO, S.w + SM::kW2, kLd2, kGH, S.h);
+        if (!LITE) {
+            tile_gemm_relu_mask<4, true>(S.out, kGO, S.w + SM::kW2, kLd2, kGH, S.h);
+        } else {
+            for (int e = tid; e < kGH * kTM; e += kMlpThreads) {
+                const int hh = e / kTM, r = e - hh * kTM;
+                float acc = 0.f;
+#pragma unroll
+                for (int g = 0; g < 3; ++g) acc = fmaf(S.out[(2 * kCE + g) * kTMp + r], S.w[SM::kW2 + hh * kLd2 + 2 * kCE + g], acc);
+                S.h[hh * kTMp + r] = S.h[hh * kTMp + r] > 0.f ? acc : 0.f;
+            }
+        }
         __syncthreads();
         // ---- dW1 += x (x) d_h, db1 ---------------------------------------------------------------------------
         if (tid < 225 && 8 * w1_ib < K1) outer_accumulate<8, 4>(S.x, 8 * w1_ib, K1, S.h, 4 * w1_hb, kGH, gw1);
@@ -434,7 +498,7 @@ eb_backward_kernel(const float *__restrict__ params, int C, const float *__restr
 }
 
 template <int K1>
-static int launch_level_backward(const cmb::Args &a, cudaStream_t st)
+static int launch_level_backward(const cmb::Args &a, bool lite, cudaStream_t st)
 {
     using SM = cmb::Smem<K1>;
     static int sm_count = 0;
@@ -442,13 +506,18 @@ static int launch_level_backward(const cmb::Args &a, cudaStream_t st)
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(cmb::context_level_backward_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(cmb::context_level_backward_kernel<K1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(SM));
+        cudaFuncSetAttribute(cmb::context_level_backward_kernel<K1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(SM));
         if (sm_count <= 0) sm_count = kNumSMs;
     }
     const int tiles = (a.n_rows + kTM - 1) / kTM;
     StageScope sc(ST_CTX_LEVEL_BWD, st, 1);
-    cmb::context_level_backward_kernel<K1><<<tiles < sm_count ? tiles : sm_count, kMlpThreads, sizeof(SM), st>>>(a);
+    if (lite)
+        cmb::context_level_backward_kernel<K1, true><<<tiles < sm_count ? tiles : sm_count, kMlpThreads, sizeof(SM), st>>>(a);
+    else
+        cmb::context_level_backward_kernel<K1, false><<<tiles < sm_count ? tiles : sm_count, kMlpThreads, sizeof(SM), st>>>(a);
     return check_launch("cgs_context_level_backward");
 }
 
@@ -473,6 +542,22 @@ extern "C" int cgs_context_level_backward(int in_dim, const float *packed_w, con
                                           float *G_scaling, float *G_offsets, float *d_mask, float *d_hyper_q,
                                           float *d_anchor, float *d_packed_w, uint32_t *ticket_dev, void *stream)
 {
+    return cgs_context_level_backward_rows(in_dim, packed_w, orig_idx, ctx_src, level_anchor, nullptr, n_rows, 0, anchor,
+                                           hyper_q, feat_q, scaling_q, offsets_q, mask, choose, noise, feat_mean,
+                                           scaling_mean, offset_mean, g_bits_dev, bits_factor, G_feat, G_scaling, G_offsets,
+                                           d_mask, d_hyper_q, d_anchor, d_packed_w, ticket_dev, stream);
+}
+
+extern "C" int cgs_context_level_backward_rows(int in_dim, const float *packed_w, const int32_t *orig_idx,
+                                          const int32_t *ctx_src, const float *level_anchor, const int32_t *row_list,
+                                          int n_rows, int lite,
+                                          const float *anchor, const float *hyper_q, const float *feat_q,
+                                          const float *scaling_q, const float *offsets_q, const float *mask,
+                                          const uint8_t *choose, const float *noise, float feat_mean, float scaling_mean,
+                                          float offset_mean, const float *g_bits_dev, float bits_factor, float *G_feat,
+                                          float *G_scaling, float *G_offsets, float *d_mask, float *d_hyper_q,
+                                          float *d_anchor, float *d_packed_w, uint32_t *ticket_dev, void *stream)
+{
     if (n_rows <= 0) return 0;
     CGS_CHECK_PTR(packed_w); CGS_CHECK_PTR(orig_idx); CGS_CHECK_PTR(anchor); CGS_CHECK_PTR(hyper_q);
     CGS_CHECK_PTR(feat_q); CGS_CHECK_PTR(scaling_q); CGS_CHECK_PTR(offsets_q); CGS_CHECK_PTR(mask);
@@ -485,16 +570,16 @@ extern "C" int cgs_context_level_backward(int in_dim, const float *packed_w, con
     a.mask = mask; a.choose = choose; a.noise = noise; a.feat_mean = feat_mean; a.scaling_mean = scaling_mean;
     a.offset_mean = offset_mean; a.g_bits_dev = g_bits_dev; a.bits_factor = bits_factor; a.G_feat = G_feat;
     a.G_scaling = G_scaling; a.G_offsets = G_offsets; a.d_mask = d_mask; a.d_hyper_q = d_hyper_q; a.d_anchor = d_anchor;
-    a.d_w = d_packed_w; a.ticket = ticket_dev;
+    a.d_w = d_packed_w; a.ticket = ticket_dev; a.row_list = row_list;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaMemsetAsync(ticket_dev, 0, sizeof(uint32_t), st);
     if (in_dim == 71) {
         CGS_CHECK_PTR(ctx_src);
-        return cmb::launch_level_backward<71>(a, st);
+        return cmb::launch_level_backward<71>(a, lite != 0, st);
     }
     if (in_dim == 15) {
         CGS_CHECK_PTR(level_anchor);
-        return cmb::launch_level_backward<15>(a, st);
+        return cmb::launch_level_backward<15>(a, lite != 0, st);
     }
     set_error("%s: unsupported context-MLP input width %d", __func__, in_dim);
     return -2;

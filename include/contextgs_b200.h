@@ -343,6 +343,20 @@ CGS_API int cgs_context_level_backward(int in_dim, const float *packed_w, const 
                                        float *G_scaling, float *G_offsets, float *d_mask, float *d_hyper_q,
                                        float *d_anchor, float *d_packed_w, uint32_t *ticket_dev, void *stream);
 
+/* The same backward restricted to the level rows row_list[0..n_rows) (NULL: rows 0..n_rows-1).  lite != 0 promises
+ * that none of these rows is chosen for the bit-rate term (choose[orig] == 0): such rows reach the context MLP only
+ * through the three adaptive quantisation steps, so the kernel back-propagates 3 of the 175 outputs (the host splits
+ * every level into its chosen rows -- full kernel -- and the other ~85 % -- lite kernel). */
+CGS_API int cgs_context_level_backward_rows(int in_dim, const float *packed_w, const int32_t *orig_idx,
+                                            const int32_t *ctx_src, const float *level_anchor, const int32_t *row_list,
+                                            int n_rows, int lite, const float *anchor, const float *hyper_q,
+                                            const float *feat_q, const float *scaling_q, const float *offsets_q,
+                                            const float *mask, const uint8_t *choose, const float *noise, float feat_mean,
+                                            float scaling_mean, float offset_mean, const float *g_bits_dev,
+                                            float bits_factor, float *G_feat, float *G_scaling, float *G_offsets,
+                                            float *d_mask, float *d_hyper_q, float *d_anchor, float *d_packed_w,
+                                            uint32_t *ticket_dev, void *stream);
+
 /* Backward of cgs_eb_forward's bit term: d_hyper[N,C] += w * d(-log2 likelihood)/d hyper_q for the chosen
  * anchors, d_packed_params[C,59] += the same w.r.t. the packed parameters (w = *g_bits_dev * bits_factor).
  * CompressAI's LowerBound gradient rule is followed. */
