@@ -263,6 +263,39 @@ compact_indices_kernel(const MaskT *__restrict__ mask, int N, int *__restrict__ 
         if (bits & (1u << i)) out_idx[pos++] = base_i + i;
 }
 
+
+// ---- densification statistics (scene/gaussian_model.py:696-713 `training_statis`) --------------------------
+// One thread per visible anchor: opacity_accum += sum_k max(neural_opacity, 0), anchor_demon += 1.
+__global__ void __launch_bounds__(256)
+statis_anchor_kernel(const int *__restrict__ vis_idx, const int32_t *__restrict__ n_vis, int K,
+                     const float *__restrict__ opacity, float *__restrict__ opacity_accum, float *__restrict__ anchor_demon)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= *n_vis) return;
+    const int a = vis_idx[v];
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += fmaxf(opacity[(size_t)v * K + k], 0.f);
+    opacity_accum[a] += s;
+    anchor_demon[a] += 1.0f;
+}
+
+// One thread per emitted Gaussian p (= the p-th kept (visible anchor, offset) slot): if it was drawn
+// (update_filter), add the norm of its screen-space gradient to the offset's accumulator.
+__global__ void __launch_bounds__(256)
+statis_offset_kernel(const int *__restrict__ vis_idx, const int *__restrict__ kept_slot, const int32_t *__restrict__ n_kept,
+                     int P, int K, const float *__restrict__ vgrad, const uint8_t *__restrict__ update_filter,
+                     float *__restrict__ grad_accum, float *__restrict__ denom)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P || p >= *n_kept || !update_filter[p]) return;
+    const int slot = kept_slot[p];
+    const int v = slot / K, k = slot - v * K;
+    const size_t dst = (size_t)vis_idx[v] * K + k;
+    const float gx = vgrad[3 * (size_t)p], gy = vgrad[3 * (size_t)p + 1];
+    grad_accum[dst] += sqrtf(gx * gx + gy * gy);
+    denom[dst] += 1.0f;
+}
+
 }  // namespace cgs
 
 using namespace cgs;
@@ -390,5 +423,56 @@ extern "C" int cgs_compact_positive_i32(const int32_t *values, int N, int32_t *o
     compact_indices_kernel<int32_t><<<tiles, kCompactThreads, 0, st>>>(
         values, N, out_idx, reinterpret_cast<unsigned long long *>(ws),
         reinterpret_cast<uint32_t *>(ws + align_up((size_t)tiles * 8)), count_dev);
+    return check_launch(__func__);
+}
+
+extern "C" size_t cgs_training_statis_workspace_bytes(int N, int K)
+{
+    const size_t n = (size_t)(N > 0 ? N : 1), slots = n * (size_t)(K > 0 ? K : 1);
+    return align_up(n * 4) + align_up(slots * 4) + 2 * cgs_compact_workspace_bytes((int)slots) + align_up(16);
+}
+
+extern "C" int cgs_training_statis(int N, int K, const uint8_t *anchor_visible, const uint8_t *offset_selection, int n_slots,
+                                   const float *neural_opacity, const float *viewspace_grad, const uint8_t *update_filter,
+                                   int P, float *opacity_accum, float *anchor_demon, float *offset_gradient_accum,
+                                   float *offset_denom, void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (N <= 0 || n_slots <= 0) return 0;
+    CGS_CHECK_PTR(anchor_visible); CGS_CHECK_PTR(offset_selection); CGS_CHECK_PTR(neural_opacity);
+    CGS_CHECK_PTR(opacity_accum); CGS_CHECK_PTR(anchor_demon); CGS_CHECK_PTR(offset_gradient_accum);
+    CGS_CHECK_PTR(offset_denom); CGS_CHECK_PTR(workspace);
+    if (P > 0) {
+        CGS_CHECK_PTR(viewspace_grad);
+        CGS_CHECK_PTR(update_filter);
+    }
+    if (K <= 0 || n_slots % K != 0 || n_slots > (int64_t)N * K) {
+        set_error("%s: n_slots must be (visible anchors) * K", __func__);
+        return -2;
+    }
+    if (workspace_bytes < cgs_training_statis_workspace_bytes(N, K)) {
+        set_error("%s: workspace too small", __func__);
+        return -3;
+    }
+    if ((reinterpret_cast<uintptr_t>(anchor_visible) | reinterpret_cast<uintptr_t>(offset_selection)) & 7) {
+        set_error("%s: masks must be 8-byte aligned", __func__);
+        return -2;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char *ws = static_cast<char *>(workspace);
+    int *vis_idx = reinterpret_cast<int *>(ws);
+    ws += align_up((size_t)N * 4);
+    int *kept = reinterpret_cast<int *>(ws);
+    ws += align_up((size_t)N * K * 4);
+    int32_t *counts = reinterpret_cast<int32_t *>(ws);   // [0] visible anchors, [1] kept slots
+    ws += align_up(16);
+    const size_t cws = cgs_compact_workspace_bytes(N * K);
+    if (int e = cgs_compact_indices(anchor_visible, N, vis_idx, counts, ws, cws, stream)) return e;
+    if (int e = cgs_compact_indices(offset_selection, n_slots, kept, counts + 1, ws + cws, cws, stream)) return e;
+    StageScope sc(ST_ELEMWISE, st, 2);
+    const int nv_cap = n_slots / K;
+    statis_anchor_kernel<<<(nv_cap + 255) / 256, 256, 0, st>>>(vis_idx, counts, K, neural_opacity, opacity_accum, anchor_demon);
+    if (P > 0)
+        statis_offset_kernel<<<(P + 255) / 256, 256, 0, st>>>(vis_idx, kept, counts + 1, P, K, viewspace_grad, update_filter,
+                                                            offset_gradient_accum, offset_denom);
     return check_launch(__func__);
 }

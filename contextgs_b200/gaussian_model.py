@@ -238,6 +238,39 @@ class GaussianModel(nn.Module):
             del self._cgs_level_plan
         return self
 
+    # ---- densification statistics (scene/gaussian_model.py:429-433, 696-713) ---------------------------------
+    def _ensure_statis(self):
+        N, K, dev = self._anchor.shape[0], self.n_offsets, self._anchor.device
+        if getattr(self, "opacity_accum", None) is None or self.opacity_accum.shape[0] != N:
+            self.opacity_accum = torch.zeros((N, 1), device=dev)
+            self.anchor_demon = torch.zeros((N, 1), device=dev)
+            self.offset_gradient_accum = torch.zeros((N * K, 1), device=dev)
+            self.offset_denom = torch.zeros((N * K, 1), device=dev)
+
+    @torch.no_grad()
+    def training_statis(self, viewspace_point_tensor, opacity, update_filter, offset_selection_mask, anchor_visible_mask):
+        """Same signature and effect as scene/gaussian_model.py:696-713, one library call, no host synchronisation
+        (the reference synchronises on every boolean-index assignment)."""
+        self._ensure_statis()
+        L = _lib.lib()
+        N, K = self._anchor.shape[0], self.n_offsets
+        grad = viewspace_point_tensor.grad
+        P = int(update_filter.shape[0])
+        if P and (grad is None or grad.shape[0] != P):
+            raise ValueError("training_statis: viewspace_point_tensor.grad must hold one row per emitted Gaussian")
+        u8 = lambda t: t.contiguous().view(torch.uint8) if t.dtype == torch.bool else t.contiguous().to(torch.uint8)
+        vis, keep, upd = u8(anchor_visible_mask), u8(offset_selection_mask.reshape(-1)), u8(update_filter)
+        op = opacity.detach().reshape(-1).float().contiguous()
+        if op.numel() != keep.numel():
+            raise ValueError("training_statis: opacity and offset_selection_mask must cover the same (visible anchor, offset) slots")
+        ws = torch.empty((L.cgs_training_statis_workspace_bytes(N, K),), dtype=torch.uint8, device=vis.device)
+        g = grad.detach().float().contiguous() if P else None
+        _lib.check(L.cgs_training_statis(N, K, _lib.ptr(vis), _lib.ptr(keep), keep.numel(), _lib.ptr(op), _lib.ptr(g),
+                                         _lib.ptr(upd) if P else None, P, _lib.ptr(self.opacity_accum),
+                                         _lib.ptr(self.anchor_demon), _lib.ptr(self.offset_gradient_accum),
+                                         _lib.ptr(self.offset_denom), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "cgs_training_statis")
+
     def conduct_encoding(self, pre_path_name):
         """scene/gaussian_model.py:1005-1300 on the GPU codec (contextgs_b200/codec.py); returns the size summary."""
         from .codec import conduct_encoding

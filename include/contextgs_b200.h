@@ -451,6 +451,20 @@ CGS_API int cgs_l1_ssim_forward(const float *img, const float *gt, int H, int W,
 CGS_API int cgs_l1_ssim_backward(const float *img, const float *gt, int H, int W, const float *dm, const float *dp,
                                  const float *dq, const float *g_l1, const float *g_ssim, float *d_img, void *stream);
 
+/* ------------------------------------------------------------------ densification statistics
+ * Replaces `GaussianModel.training_statis` (scene/gaussian_model.py:696-713; called every iteration in
+ * 1500 < it < update_until, train.py:243) without its five boolean-index synchronisations:
+ *   anchor_visible[N] uint8, offset_selection[n_slots = visible anchors * K] uint8 (the `mask` G1 returns),
+ *   neural_opacity[n_slots], viewspace_grad[P,3] (dL/d means2D of the P emitted Gaussians), update_filter[P] uint8;
+ *   opacity_accum[N] += sum_k max(opacity, 0), anchor_demon[N] += 1 for visible anchors;
+ *   offset_gradient_accum[N*K] += |grad_xy|, offset_denom[N*K] += 1 for drawn Gaussians.
+ * Masks must be 8-byte aligned. */
+CGS_API size_t cgs_training_statis_workspace_bytes(int N, int K);
+CGS_API int cgs_training_statis(int N, int K, const uint8_t *anchor_visible, const uint8_t *offset_selection, int n_slots,
+                                const float *neural_opacity, const float *viewspace_grad, const uint8_t *update_filter,
+                                int P, float *opacity_accum, float *anchor_demon, float *offset_gradient_accum,
+                                float *offset_denom, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
