@@ -467,6 +467,39 @@ def extras(args, pc, pc_train, cams_dev, my_cam, pipe, bg, timed, world, dev):
     ex["train_iter_per_s_render_only"] = world * k / (ms * 1e-3)
     ms = timed(lambda i: train_step(i, 20000), k, 3)
     ex["train_iter_per_s_with_context_model"] = world * k / (ms * 1e-3)
+    if world > 1:
+        # data-parallel training step (BASELINE configs[4]): every rank renders its own camera, the
+        # gradients of all parameters land in ONE flat fp32 bucket that is all-reduced (NCCL, sum / world) per step
+        from contextgs_b200.distributed import GradientBucket
+        params = [pp for pp in list(pc_train.parameters()) + [pc_train._anchor_feat, pc_train._offset, pc_train._scaling,
+                                                               pc_train._mask, pc_train._hyper_latent]
+                  if pp.requires_grad]
+        seen, uniq = set(), []
+        for pp in params:
+            if id(pp) not in seen:
+                seen.add(id(pp))
+                uniq.append(pp)
+        bucket = GradientBucket(uniq).attach()
+
+        def train_step_dp(i, step):
+            bucket.zero()
+            cam = cams_dev[my_cam(i)]
+            with torch.no_grad():
+                vis = prefilter_voxel(cam, pc_train, pipe, bg)
+            out = render(cam, pc_train, pipe, bg, visible_mask=vis, retain_grad=False, step=step)
+            Ll1, ssim_v = l1_ssim(out["render"], gt)
+            loss = 0.8 * Ll1 + 0.2 * (1.0 - ssim_v) + 0.01 * out["scaling"].prod(dim=1).mean()
+            if out["bit_per_param"] is not None:
+                loss = loss + 0.004 * out["bit_per_param"]
+            loss.backward()
+            bucket.all_reduce()
+        ms = timed(lambda i: train_step_dp(i, 100), k, 3)
+        ex["train_iter_per_s_render_only_dp_allreduce"] = world * k / (ms * 1e-3)
+        ms = timed(lambda i: train_step_dp(i, 20000), k, 3)
+        ex["train_iter_per_s_with_context_model_dp_allreduce"] = world * k / (ms * 1e-3)
+        ex["grad_bucket_mb"] = bucket.flat.numel() * 4 / 1e6
+        for pp in uniq:
+            pp.grad = None
     # the photometric loss alone: fused kernels vs the reference's expression (5 grouped 11x11 convolutions + autograd)
     img = torch.rand(3, H, W, device=dev)
 
