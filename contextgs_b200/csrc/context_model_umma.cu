@@ -205,16 +205,13 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
         // and the next tile's gathered context rows travel from HBM
         const bool pred = A.predict_only != 0;
         const bool chosen = !pred && o >= 0 && (A.choose ? A.choose[o] != 0 : true);
-        float xv[48], mk[10];
+        // offset masks of the row as bits (values are exactly 0 / 1: utils/entropy_models / gaussian_model.py:1670)
+        uint32_t mkbits = 0x3ffu;
+        if (o >= 0 && half == 1 && chosen) {
+            mkbits = 0;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            const ChunkDesc cd = chunk_desc(c, half);
-            const float *src = (cd.grp == 0 ? A.feat : (cd.grp == 1 ? A.scaling : A.offsets)) + (o < 0 ? 0 : o) * cd.dim + cd.k0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) xv[8 * c + j] = (!pred && o >= 0 && j < cd.cnt) ? __ldg(src + j) : 0.f;
+            for (int k = 0; k < 10; ++k) mkbits |= __ldg(A.mask + o * 10 + k) != 0.f ? (1u << k) : 0u;
         }
-#pragma unroll
-        for (int k = 0; k < 10; ++k) mk[k] = (o >= 0 && half == 1 && chosen) ? __ldg(A.mask + o * 10 + k) : 1.f;
         RowInputs<K1> nxt;
         load_row<K1>(nxt, A, (tile + (int)gridDim.x) * kRows + row, half);
         if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
@@ -263,12 +260,28 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             prow[172] = Qf; prow[173] = Qs; prow[174] = Qo; prow[175] = 0.f;
         }
         const float *nz = A.noise ? A.noise + (size_t)grow * kCE : nullptr;
+        // The six groups run as a ROLLED loop: fully unrolled (with the attributes prefetched into 48 registers) the
+        // kernel was 24.9 k SASS instructions and spent its time waiting for the instruction cache ("no instruction"
+        // was the top stall reason, profiles/r01_ctx2_*).  The attributes of group c+1 are fetched while group c is
+        // evaluated.
+        auto fetch_x = [&](int c, float (&x8)[8]) {
+            const ChunkDesc cd = chunk_desc(c, half);
+            const float *src = (cd.grp == 0 ? A.feat : (cd.grp == 1 ? A.scaling : A.offsets)) + (size_t)(o < 0 ? 0 : o) * cd.dim + cd.k0;
 #pragma unroll
+            for (int j = 0; j < 8; ++j) x8[j] = (!pred && o >= 0 && j < cd.cnt) ? __ldg(src + j) : 0.f;
+        };
+        float xn[8];
+        fetch_x(0, xn);
+#pragma unroll 1
         for (int c = 0; c < 6; ++c) {
             const ChunkDesc cd = chunk_desc(c, half);
             uint32_t vm[8], vs[8];
+            float xc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xc[j] = xn[j];
             umma::tmem_ld8(tl + kColD2 + cd.mu_col, vm);
             umma::tmem_ld8(tl + kColD2 + cd.sg_col, vs);
+            if (c + 1 < 6) fetch_x(c + 1, xn);
             umma::tmem_wait_ld();
             if (o < 0) continue;
             const float Q = cd.grp == 0 ? Qf : (cd.grp == 1 ? Qs : Qo);
@@ -285,13 +298,13 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                         prow[kCE + cd.j0 + j] = scale;
                     }
                     if (pred) continue;
-                    const float x = xv[8 * c + j];
+                    const float x = xc[j];
                     const float xq = nz ? x + nz[cd.j0 + j] * Q : ste_round(x, Q);
                     dst[j] = xq;
                     float bits = 0.f;
                     if (chosen) {
                         bits = gaussian_bits_one(xq, mean, scale, Q, x_mean);
-                        if (cd.grp == 2) bits *= mk[c >= 2 ? (8 * (c - 2) + j) / 3 : 0];  // grp 2 <=> half 1, c >= 2
+                        if (cd.grp == 2 && !((mkbits >> ((cd.k0 + j) / 3)) & 1u)) bits = 0.f;
                         acc += bits;
                     }
                     if (A.bits_out) A.bits_out[(size_t)o * kCE + cd.j0 + j] = bits;
