@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .context_model import build_level_plan, find_divide_scale, pack_grid_weights_umma
+from .context_model import build_level_plan, find_divide_scale, global_means, pack_grid_weights_umma
 from .encodings import Q_anchor, Quantize_anchor
 
 # Level rows per independently coded chunk of a feat stream (the reference: 1000 anchors, coded one after the
@@ -168,7 +168,7 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS):
     feat_q, scaling_q, offsets_q = torch.zeros_like(feat), torch.zeros_like(scaling), torch.zeros_like(offsets)
     sums = torch.zeros(16, dtype=torch.float64, device=dev)
     terr = torch.zeros(1, dtype=torch.int32, device=dev)
-    means = tuple(torch.stack([pc._anchor_feat.mean(), pc.get_scaling.mean(), pc._offset.mean()]).tolist())
+    means = global_means(pc)
     levels = []
     for li, lv in enumerate(plan.levels):
         entry = SimpleNamespace(level=lv.level, n=lv.n, streams={})

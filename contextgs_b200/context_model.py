@@ -193,6 +193,24 @@ def get_level_plan(pc, anchor, mask_anchor_bool):
     return plan
 
 
+def global_means(pc):
+    """The three global means the reference passes as x_mean (gaussian_model.py:1667-1669), as host floats.  They
+    only change when the parameters do, so they are cached per parameter version (three 100 MB reductions and a
+    host synchronisation per call otherwise)."""
+    srcs = (pc._anchor_feat, pc._scaling, pc._offset)
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in srcs) + (bool(pc.decoded_version),)
+    ent = getattr(pc, "_cgs_means", None)
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    with torch.no_grad():
+        means = tuple(torch.stack([pc._anchor_feat.mean(), pc.get_scaling.mean(), pc._offset.mean()]).tolist())
+    try:
+        pc._cgs_means = (key, means)
+    except Exception:
+        pass
+    return means
+
+
 # ----------------------------------------------------------------------------- forward core + training autograd
 
 def _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choose_u8, noise, training, return_details):
@@ -208,8 +226,7 @@ def _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choo
         hyper_q = hyper_q * 0
     feat_q, scaling_q, offsets_q = torch.zeros_like(feat), torch.zeros_like(scaling), torch.zeros_like(offsets)
     bits_out = torch.zeros((N, N_CODED), dtype=torch.float32, device=dev) if return_details else None
-    with torch.no_grad():  # the three global means the reference passes as x_mean (gaussian_model.py:1667-1669)
-        means = tuple(torch.stack([pc._anchor_feat.mean(), pc.get_scaling.mean(), pc._offset.mean()]).tolist())
+    means = global_means(pc)
     stream = _lib.stream_ptr()
     level_noise = []
     umma = ctx_impl() == "umma"
