@@ -134,3 +134,26 @@ def test_directory_round_trip_and_render(tmp_path):
             i1 = render(cam, dec, pipe, bg, visible_mask=prefilter_voxel(cam, dec, pipe, bg))["render"]
             i2 = render(cam, ref, pipe, bg, visible_mask=prefilter_voxel(cam, ref, pipe, bg))["render"]
         assert torch.equal(i1, i2) and float(i1.max()) > 0
+
+
+def test_tiny_model_and_fully_masked_offsets():
+    """Ragged edges: fewer anchors than one chunk, levels with a handful of rows, and an offsets stream that is
+    empty because every offset mask is 0 (decodes to zeros)."""
+    for N, kill_all in ((40, False), (257, True)):
+        pc = _model(N)
+        if kill_all:
+            with torch.no_grad():
+                pc._mask.fill_(-8.0)
+                pc._mask[::2, 0] = 8.0        # every second anchor keeps exactly one offset (others are pruned anchors)
+        enc = codec.encode_model(pc)
+        q = enc.quantised
+        fresh = GaussianModel(device="cuda")
+        fresh.load_state_dict({k: v for k, v in pc.state_dict().items() if not k.startswith("_")}, strict=False)
+        out = codec.decode_model(fresh, enc.meta, enc.anchor_q, enc.mask_bytes, enc.mask_lens, enc.hyper_bytes,
+                                 enc.hyper_lens, enc.levels)
+        K = pc.n_offsets
+        assert out["feat"].shape[0] == int(pc.get_mask_anchor.sum()) > 0
+        assert torch.equal(out["feat"], q["feat"]) and torch.equal(out["scaling"], q["scaling"])
+        assert torch.equal(out["hyper"], q["hyper"]) and torch.equal(out["masks"].view(-1, K), q["masks"])
+        m3 = q["masks"].repeat_interleave(3, dim=1)
+        assert torch.equal(out["offsets"].reshape(-1, 3 * K), q["offsets"] * m3)
