@@ -580,6 +580,27 @@ def extras(args, pc, pc_train, cams_dev, my_cam, pipe, bg, timed, world, dev):
     ex["codec_round_trip_exact"] = bool(torch.equal(enc_box["out"]["feat"], enc.quantised["feat"]) and
                                         torch.equal(enc_box["out"]["scaling"], enc.quantised["scaling"]) and
                                         torch.equal(enc_box["out"]["hyper"], enc.quantised["hyper"]))
+    if world > 1:
+        # BASELINE configs[3]: ONE model, anchors sharded over the ranks by dependency root; no data-path collective while
+        # coding, one scalar all-reduce for the size, one all-reduce (sum) to assemble the decoded attributes
+        box = {}
+
+        def enc_sh(i):
+            box["enc"], box["bits"] = codec.encode_model_sharded(pc_train)
+        ms = timed(enc_sh, kc, 1)
+        ex["anchor_mbits_per_s_encoded_sharded"] = box["bits"] * kc / (ms * 1e-3) / 1e6
+        ex["encode_sharded_ms"] = ms / kc
+        from contextgs_b200.gaussian_model import GaussianModel
+        dec_sh_model = GaussianModel(device=dev)
+        dec_sh_model.load_state_dict({k: v for k, v in pc_train.state_dict().items() if not k.startswith("_")}, strict=False)
+
+        def dec_sh(i):
+            box["out"] = codec.decode_model_sharded(dec_sh_model, box["enc"])
+        ms = timed(dec_sh, kc, 1)
+        ex["anchor_mbits_per_s_decoded_sharded"] = box["bits"] * kc / (ms * 1e-3) / 1e6
+        ex["decode_sharded_ms"] = ms / kc
+        ex["codec_sharded_round_trip_exact"] = bool(torch.equal(box["out"]["feat"], enc.quantised["feat"]) and
+                                                    torch.equal(box["out"]["scaling"], enc.quantised["scaling"]))
     ex["codec_note"] = ("encoded = bytes actually produced by the GPU range coder (anchors 16 bit raw + masks + hyper + "
                         "feat / scaling / offsets streams + per-chunk side info) / time of the whole encode_model call "
                         "(level division cached in the model, context model, coding, packing; streams stay in HBM)")

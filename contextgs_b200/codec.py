@@ -108,6 +108,26 @@ def _hyper_tables(pc, smin, smax):
     return frequency_tables(lik.t().contiguous() + 1e-12)
 
 
+def _plan_for(pc, anchor, key, rank, world):
+    """(full level sizes, plan or shard of it), cached on the model while the coded anchors (`key`) and the level
+    scales are unchanged: the division and especially its dependency-root sharding are index gymnastics with host
+    synchronisations that would otherwise dominate a sharded encode / decode call."""
+    key = (key, tuple(pc.level_scale), float(pc.voxel_size), rank, world)
+    ent = getattr(pc, "_cgs_codec_plan", None)
+    if ent is not None and ent[0] == key:
+        return ent[1], ent[2]
+    plan = build_level_plan(pc, anchor, None)
+    sizes = [lv.n for lv in plan.levels]
+    if world > 1:
+        from .distributed import shard_level_plan
+        plan = shard_level_plan(plan, rank, world)
+    try:
+        pc._cgs_codec_plan = (key, sizes, plan)
+    except Exception:
+        pass
+    return sizes, plan
+
+
 def _level_params(pc, lv, anchor, hyper_q, feat, scaling, offsets, masks, feat_q, scaling_q, offsets_q, sums, err, means,
                   predict_only):
     """(mean, scale, Q) of every coded value of one level (and, when encoding, the level's quantised values)."""
@@ -123,10 +143,14 @@ def _level_params(pc, lv, anchor, hyper_q, feat, scaling, offsets, masks, feat_q
 
 
 @torch.no_grad()
-def encode_model(pc, chunk_rows=CHUNK_ROWS):
+def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1):
     """Encode every valid anchor of `pc`.  Returns a SimpleNamespace with the byte streams (CUDA uint8 tensors),
     the metadata the decoder needs, the quantised tensors that were coded (for parity checks) and the
-    estimated bits of the same pass."""
+    estimated bits of the same pass.
+    world > 1 (BASELINE configs[3]: anchors sharded over the GPUs): the level plan is split by
+    dependency root (distributed.shard_level_plan), so rank `rank` predicts and codes only its own rows of every
+    level, with no exchange; the small anchor / mask / hyper streams are produced identically on every rank (they
+    are inputs of every shard).  The per-rank level streams simply sit side by side in the container."""
     L = _lib.lib()
     sel = pc.get_mask_anchor
     dev = sel.device
@@ -163,7 +187,9 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS):
     # level division on the DEQUANTISED anchors (what the decoder will see)
     if pc.level_scale is None:
         pc.level_scale = find_divide_scale(pc, anchor, pc.target_ratio, pc.level_num)
-    plan = build_level_plan(pc, anchor, None)
+    src = pc._anchor
+    n_levels_full, plan = _plan_for(pc, anchor, ("enc", src.data_ptr(), src._version, tuple(src.shape), pc._mask.data_ptr(), pc._mask._version),
+                                    rank, world)
 
     feat_q, scaling_q, offsets_q = torch.zeros_like(feat), torch.zeros_like(scaling), torch.zeros_like(offsets)
     sums = torch.zeros(16, dtype=torch.float64, device=dev)
@@ -201,7 +227,7 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS):
     meta = dict(version=1, N_total=int(pc._anchor.shape[0]), N=N, chunk_rows=chunk_rows, voxel_size=float(pc.voxel_size),
                 level_scale=[float(s) for s in pc.level_scale], x_bound_min=pc.x_bound_min.detach().cpu(),
                 x_bound_max=pc.x_bound_max.detach().cpu(), prob_masks=p1, hyper_min=hmin, hyper_max=hmax,
-                means=means, N_levels=[lv.n for lv in plan.levels])
+                means=means, N_levels=n_levels_full, world=world)
     s = sums.tolist()
     est = dict(hyper=None, feat=sum(s[4 * i] for i in range(3)), scaling=sum(s[4 * i + 1] for i in range(3)),
                offsets=sum(s[4 * i + 2] for i in range(3)))
@@ -224,9 +250,11 @@ def encoded_bits(enc):
 
 
 @torch.no_grad()
-def decode_model(pc, meta, anchor_q, mask_bytes, mask_lens, hyper_bytes, hyper_lens, levels):
+def decode_model(pc, meta, anchor_q, mask_bytes, mask_lens, hyper_bytes, hyper_lens, levels, rank=0, world=1):
     """Inverse of encode_model.  `pc` supplies the MLPs / entropy bottleneck (mlp.pt) and receives bounds and
-    level scales from `meta`.  Returns dict(anchor, hyper, feat, offsets [N,10,3], scaling, masks [N,10,1])."""
+    level scales from `meta`.  Returns dict(anchor, hyper, feat, offsets [N,10,3], scaling, masks [N,10,1]).
+    world > 1: `levels` are the streams rank `rank` encoded; only that shard's rows of feat / scaling / offsets are
+    filled (the rest stays zero), so the SUM over the ranks (one all-reduce) is the decoded model."""
     L = _lib.lib()
     dev = pc.latent_codec.quantiles.device
     N, K, chunk_rows = meta["N"], pc.n_offsets, meta["chunk_rows"]
@@ -247,8 +275,8 @@ def decode_model(pc, meta, anchor_q, mask_bytes, mask_lens, hyper_bytes, hyper_l
     hyper_q = ((hsym.to(torch.int32) + hmin).float() + median.view(1, -1)).contiguous()
     hyper_ctx = hyper_q * 0 if getattr(pc, "disable_hyper", False) else hyper_q
 
-    plan = build_level_plan(pc, anchor, None)
-    if [lv.n for lv in plan.levels] != list(meta["N_levels"]):
+    sizes, plan = _plan_for(pc, anchor, ("dec", anchor_q.data_ptr(), anchor_q._version, tuple(anchor_q.shape)), rank, world)
+    if sizes != list(meta["N_levels"]):
         raise _lib.CgsError("decode: the level division of the decoded anchors differs from the encoder's")
     feat_q = torch.zeros((N, 50), dtype=torch.float32, device=dev)
     scaling_q = torch.zeros((N, 6), dtype=torch.float32, device=dev)
@@ -333,4 +361,40 @@ def conduct_decoding(pc, pre_path_name):
     out = decode_model(pc, meta, anchor_q, rd("masks.b"), u16(side["mask_lens"]), rd("hyper.b"), u16(side["hyper_lens"]),
                        levels)
     pc.replace_with_decoded(out["anchor"], out["hyper"], out["feat"], out["offsets"], out["scaling"], out["masks"])
+    return out
+
+
+# ----------------------------------------------------------------------------- anchors sharded over the GPUs
+
+def encode_model_sharded(pc, group=None, chunk_rows=CHUNK_ROWS):
+    """encode_model on this rank's shard of the level plan (one process per GPU, torch.distributed).  Returns
+    (enc, total_bits): the level streams of this rank and the size of the WHOLE encoding (level streams summed over
+    the ranks by one scalar all-reduce; anchors / masks / hyper counted once)."""
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if on else (0, 1)
+    enc = encode_model(pc, chunk_rows, rank, world)
+    bits = encoded_bits(enc)
+    level_bits = torch.tensor([bits["feat"] + bits["scaling"] + bits["offsets"]], dtype=torch.float64,
+                              device=enc.anchor_q.device)
+    if world > 1:
+        dist.all_reduce(level_bits, op=dist.ReduceOp.SUM, group=group)
+    return enc, int(level_bits.item()) + bits["anchor"] + bits["masks"] + bits["hyper"]
+
+
+def decode_model_sharded(pc, enc, group=None):
+    """decode_model on this rank's streams, then ONE all-reduce (sum) of the three attribute arrays assembles the
+    decoded model on every rank."""
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if on else (0, 1)
+    out = decode_model(pc, enc.meta, enc.anchor_q, enc.mask_bytes, enc.mask_lens, enc.hyper_bytes, enc.hyper_lens,
+                       enc.levels, rank, world)
+    if world > 1:
+        flat = torch.cat([out["feat"].reshape(-1), out["scaling"].reshape(-1), out["offsets"].reshape(-1)])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        nf, ns = out["feat"].numel(), out["scaling"].numel()
+        out["feat"] = flat[:nf].view_as(out["feat"])
+        out["scaling"] = flat[nf:nf + ns].view_as(out["scaling"])
+        out["offsets"] = flat[nf + ns:].view_as(out["offsets"])
     return out

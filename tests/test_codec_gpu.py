@@ -157,3 +157,35 @@ def test_tiny_model_and_fully_masked_offsets():
         assert torch.equal(out["hyper"], q["hyper"]) and torch.equal(out["masks"].view(-1, K), q["masks"])
         m3 = q["masks"].repeat_interleave(3, dim=1)
         assert torch.equal(out["offsets"].reshape(-1, 3 * K), q["offsets"] * m3)
+
+
+def test_sharded_encode_decode_fake_world():
+    """Anchors sharded over 4 ranks (BASELINE configs[3]) emulated on one GPU: every rank encodes / decodes only its
+    dependency-closed shard; the shards' decoded rows are disjoint, their sum is the unsharded result, and the level
+    streams together are about as long as the unsharded ones."""
+    pc = _model(6000)
+    full = codec.encode_model(pc)
+    q = full.quantised
+    world = 4
+    K = pc.n_offsets
+    acc = {k: torch.zeros_like(q[k]) for k in ("feat", "scaling", "offsets")}
+    touched = torch.zeros(q["feat"].shape[0], device="cuda")
+    level_bits = 0
+    for rank in range(world):
+        enc = codec.encode_model(pc, rank=rank, world=world)
+        b = codec.encoded_bits(enc)
+        level_bits += b["feat"] + b["scaling"] + b["offsets"]
+        assert torch.equal(enc.hyper_bytes, full.hyper_bytes) and torch.equal(enc.mask_bytes, full.mask_bytes)
+        fresh = GaussianModel(device="cuda")
+        fresh.load_state_dict({k: v for k, v in pc.state_dict().items() if not k.startswith("_")}, strict=False)
+        out = codec.decode_model(fresh, enc.meta, enc.anchor_q, enc.mask_bytes, enc.mask_lens, enc.hyper_bytes,
+                                 enc.hyper_lens, enc.levels, rank=rank, world=world)
+        touched += (out["feat"].abs().sum(dim=1) > 0).float()
+        acc["feat"] += out["feat"]; acc["scaling"] += out["scaling"]; acc["offsets"] += out["offsets"].reshape(-1, 3 * K)
+    assert float(touched.max()) <= 1.0
+    m3 = q["masks"].repeat_interleave(3, dim=1)
+    assert torch.equal(acc["feat"], q["feat"]) and torch.equal(acc["scaling"], q["scaling"])
+    assert torch.equal(acc["offsets"], q["offsets"] * m3)
+    fb = codec.encoded_bits(full)
+    ref_bits = fb["feat"] + fb["scaling"] + fb["offsets"]
+    assert abs(level_bits - ref_bits) < 0.02 * ref_bits
