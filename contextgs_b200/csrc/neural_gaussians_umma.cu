@@ -4,21 +4,24 @@
 // decoder MLPs scene/gaussian_model.py:153-174), but the two MLP layers run as 3xTF32 tcgen05.mma
 // (fp32-grade accuracy, see umma.cuh) with every activation resident in TENSOR MEMORY:
 //
-//   persistent CTA (one per SM, 512 threads = 16 warps), tile = 128 anchors = 128 TMEM lanes;
-//   thread (row = 32*(warp%4) + lane, quarter = warp/4): FOUR threads share a row and split its columns
-//   and its ten offsets (3 + 3 + 2 + 2).  The kernel is bound by the issue latency of the epilogues, not by
-//   the tensor core or HBM, so four warps per scheduler (instead of two) is what buys time.
+//   persistent CTA (one per SM), tile = 128 anchors = 128 TMEM lanes, 512 threads in TWO WARP GROUPS that
+//   work on DIFFERENT tiles at the same time (the kernel is bound by the latency of its serial phases, not by
+//   the tensor core, HBM or issue slots -- doubling the threads per phase bought nothing, overlapping the
+//   phases of two tiles does):
+//     FRONT (warps 0-7):  stage the layer-1 input of tile t+1 -> layer-1 MMA -> ReLU epilogue in TMEM
+//                         -> issue the layer-2 MMAs as soon as BACK has released the accumulators of tile t;
+//     BACK  (warps 8-15): selection, ordered compaction (block scan + decoupled look-back across tiles),
+//                         post-processing and coalesced copy-out of tile t.
+//   Inside a group, thread (row = 32*(warp%4) + lane, half = (warp%8)/4): two threads share a row.
 //
 //   TMEM columns (496 of 512):
 //     [  0,176)  layer-1 input  x_hi [0,56) | x_lo [56,112)      -> later hidden_lo [0,176)
 //     [176,352)  layer-1 accumulator D1 (3 heads x 56: 50 units + 6 zero pads, + 8 pad)
 //                -> overwritten IN PLACE by hidden_hi = tf32(relu(D1 + b1))
 //     [352,496)  layer-2 accumulators: opacity 16 | color 48 | cov 80
+//   Columns [0,352) belong to FRONT (free again once the layer-2 MMAs of the tile have completed),
+//   [352,496) go back and forth: written by the layer-2 MMAs, read by BACK, released through an mbarrier.
 //   shared memory (145 KB weights + 77 KB staging): W1 hi/lo [14][176][4], W2 per head hi/lo [14][N_h][4], biases.
-//
-//   per tile:  load + split rows -> tcgen05.st  |  21 MMAs (128x176x8)  |  ReLU epilogue in TMEM
-//              |  63 MMAs (128x{16,32,80}x8)    |  selection, ordered compaction (block scan +
-//              decoupled look-back across tiles), post-processing, 56 B per emitted Gaussian.
 //
 // HBM traffic is the algorithmic minimum (446 B per visible anchor + 56 B per Gaussian): nothing
 // but the final attributes is written.
@@ -29,13 +32,12 @@ namespace cgs {
 namespace ngu {
 constexpr int kFeat = 50, kK = 10;
 constexpr int kRows = 128;                  // anchors per tile
-constexpr int kThreads = 512;
+constexpr int kThreads = 512, kGroup = 256; // two warp groups of 8 warps
 constexpr int kK1 = 56;                     // 54 inputs padded to a multiple of 8
 constexpr int kHeadStride = 56;             // hidden units per head incl. zero pads
 constexpr int kN1 = 176;                    // 3 * 56 = 168 padded to a multiple of 16
-constexpr int kQCols = kN1 / 4;             // 44 hidden columns per quarter in the ReLU epilogue
 // layer-2 output widths.  Output columns are arranged so that every thread's tcgen05.ld starts on
-// an aligned column: opacity of the j-th offset of quarter q at column 4q + j, colour channel c of offset k
+// an aligned column: opacity of offset k at column 8*(k/5) + k%5, colour channel c of offset k
 // at 4k + c, covariance value i of offset k at 8k + i (the host packs W2 / b2 rows accordingly).
 constexpr int kNo = 16, kNc = 48, kNv = 80;
 // TMEM columns
@@ -55,10 +57,9 @@ constexpr int kOffB2o = kOffB1 + kN1, kOffB2c = kOffB2o + kNo, kOffB2v = kOffB2c
 constexpr int kPacked = kOffB2v + kNv;      // 36160 floats = 144640 B
 
 constexpr int kTileGauss = kRows * kK;       // 1280 (anchor, offset) pairs per tile
-constexpr int kMaxOff = 3;                   // offsets per thread: quarters own {0,1,2} {3,4,5} {6,7} {8,9}
 
-__device__ __forceinline__ int quarter_first(int q) { return q == 0 ? 0 : q == 1 ? 3 : q == 2 ? 6 : 8; }
-__device__ __forceinline__ int quarter_count(int q) { return q < 2 ? 3 : 2; }
+// mbarriers
+enum { BAR_L1 = 0, BAR_L2O, BAR_L2ALL, BAR_ACCFREE, BAR_COUNT };
 
 struct Smem {
     float w[kPacked];
@@ -68,60 +69,84 @@ struct Smem {
     float4 o_rot[kTileGauss];
     float o_nop[kTileGauss];
     uint8_t o_keep[kTileGauss];
-    uint32_t cnt[kThreads];       // kept Gaussians per (row, quarter), index = row*4 + quarter
-    uint32_t excl[kThreads];
-    uint32_t wsum[kThreads / 32];
+    uint32_t cnt[kGroup];         // kept Gaussians per (row, half), index = row*2 + half
+    uint32_t excl[kGroup];
+    uint32_t wsum[kGroup / 32];
     uint32_t tile_base, tile_total;
     uint32_t tmem;
     int timeout;
-    alignas(8) uint64_t bar[3];
+    alignas(8) uint64_t bar[BAR_COUNT];
 };
 
-// Everything one thread reads from HBM for one tile row (its quarter of the MLP input + what its
-// offsets need in the last epilogue).  Loaded one tile AHEAD into registers so that the ~1 us of
-// HBM latency hides behind the previous tile's MMAs and epilogues.
-struct RowInputs {
-    float x[16];      // quarters 0-2: feat[16q .. 16q+15]; quarter 3: feat[48], feat[49], view dir (3), distance, 0, 0
-    float mask[kMaxOff];
-    float off[3 * kMaxOff];
-    float anchor[3];
-    float sc[6];
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kGroup) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+
+// FRONT: this thread's share of the layer-1 input of one row.  Loaded one tile AHEAD into registers.
+struct FrontInputs {
+    float x[32];      // half 0: feat[0..31]; half 1: feat[32..49], view dir (3), distance, 0, 0, ...
+    float anchor[3];  // half 1 only (view direction)
     int a;            // source anchor (-1: padding row)
 };
+// BACK: what the last epilogue needs for the five offsets of this thread.
+struct BackInputs {
+    float mask[5];
+    float off[15];
+    float anchor[3];
+    float sc[6];
+    int a;
+};
 
-// The loads are split in two parts issued at different points of the tile loop (the load/store unit throttles
-// when 512 threads issue ~40 loads each at once -- ncu r01: 31 % of the samples sat on these instructions),
-// and use 64-bit accesses wherever the reference's row strides (200 / 120 / 40 / 24 B) keep them aligned.
-__device__ __forceinline__ void load_row_feat(RowInputs &r, int a, int q, const float *__restrict__ feat)
+__device__ __forceinline__ void load_front(FrontInputs &r, int a, int half, const float *__restrict__ anchor,
+                                           const float *__restrict__ feat)
 {
     r.a = a;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) r.x[j] = 0.f;
+    for (int j = 0; j < 32; ++j) r.x[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) r.anchor[i] = 0.f;
     if (a < 0) return;
     const float2 *f2 = reinterpret_cast<const float2 *>(feat + (size_t)a * kFeat);
-    if (q < 3) {
+    if (half == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float2 v = __ldg(f2 + 8 * q + j);
+        for (int j = 0; j < 16; ++j) {
+            const float2 v = __ldg(f2 + j);
             r.x[2 * j] = v.x;
             r.x[2 * j + 1] = v.y;
         }
     } else {
-        const float2 v = __ldg(f2 + 24);
-        r.x[0] = v.x;
-        r.x[1] = v.y;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const float2 v = __ldg(f2 + 16 + j);
+            r.x[2 * j] = v.x;
+            r.x[2 * j + 1] = v.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r.anchor[i] = __ldg(anchor + 3 * (size_t)a + i);
     }
 }
 
-__device__ __forceinline__ void load_row_rest(RowInputs &r, int q, const float *__restrict__ anchor,
-                                              const float *__restrict__ offsets, const float *__restrict__ scaling,
-                                              const float *__restrict__ mask)
+// view direction / distance (gaussian_renderer/__init__.py:106-110) -- computed when the row is staged
+__device__ __forceinline__ void finish_front(FrontInputs &r, int half, float cx, float cy, float cz)
 {
-    const int a = r.a;
+    if (half == 1 && r.a >= 0) {
+        const float vx = r.anchor[0] - cx, vy = r.anchor[1] - cy, vz = r.anchor[2] - cz;
+        const float d = sqrtf(vx * vx + vy * vy + vz * vz);
+        r.x[18] = vx / d; r.x[19] = vy / d; r.x[20] = vz / d; r.x[21] = d;
+    }
+}
+
+__device__ __forceinline__ void load_back(BackInputs &r, int a, int half, const float *__restrict__ anchor,
+                                          const float *__restrict__ offsets, const float *__restrict__ scaling,
+                                          const float *__restrict__ mask)
+{
+    r.a = a;
 #pragma unroll
-    for (int j = 0; j < kMaxOff; ++j) r.mask[j] = 0.f;
+    for (int j = 0; j < 5; ++j) r.mask[j] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 3 * kMaxOff; ++j) r.off[j] = 0.f;
+    for (int j = 0; j < 15; ++j) r.off[j] = 0.f;
     if (a < 0) return;
 #pragma unroll
     for (int i = 0; i < 3; ++i) r.anchor[i] = __ldg(anchor + 3 * (size_t)a + i);
@@ -134,43 +159,13 @@ __device__ __forceinline__ void load_row_rest(RowInputs &r, int q, const float *
             r.sc[2 * i + 1] = v.y;
         }
     }
-    const int kbase = quarter_first(q);
-    const float *mp = mask + (size_t)a * kK + kbase;
-    const float *op = offsets + ((size_t)a * kK + kbase) * 3;
-    if (q == 0) {          // offsets 0,1,2: mask 3 floats at +0 B, offsets 9 floats at +0 B (rows of 40 / 120 B)
-        const float2 m = __ldg(reinterpret_cast<const float2 *>(mp));
-        r.mask[0] = m.x; r.mask[1] = m.y; r.mask[2] = __ldg(mp + 2);
+    const int kbase = 5 * half;
+    const float *mp = mask + (size_t)a * kK + kbase;               // +0 / +20 B: 4-byte aligned in general
+    const float *op = offsets + ((size_t)a * kK + kbase) * 3;      // +0 / +60 B
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 v = __ldg(reinterpret_cast<const float2 *>(op) + j);
-            r.off[2 * j] = v.x; r.off[2 * j + 1] = v.y;
-        }
-        r.off[8] = __ldg(op + 8);
-    } else if (q == 1) {   // offsets 3,4,5: +12 B / +36 B, only 4-byte aligned
+    for (int j = 0; j < 5; ++j) r.mask[j] = __ldg(mp + j);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) r.mask[j] = __ldg(mp + j);
-#pragma unroll
-        for (int j = 0; j < 9; ++j) r.off[j] = __ldg(op + j);
-    } else {               // offsets 6,7 / 8,9: mask 2 floats at +24 / +32 B, offsets 6 floats at +72 / +96 B
-        const float2 m = __ldg(reinterpret_cast<const float2 *>(mp));
-        r.mask[0] = m.x; r.mask[1] = m.y;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const float2 v = __ldg(reinterpret_cast<const float2 *>(op) + j);
-            r.off[2 * j] = v.x; r.off[2 * j + 1] = v.y;
-        }
-    }
-}
-
-// view direction / distance (gaussian_renderer/__init__.py:106-110) -- computed when the row is staged,
-// not when it is loaded, so that nothing waits on the prefetch
-__device__ __forceinline__ void finish_row(RowInputs &r, int q, float cx, float cy, float cz)
-{
-    if (q == 3 && r.a >= 0) {
-        const float vx = r.anchor[0] - cx, vy = r.anchor[1] - cy, vz = r.anchor[2] - cz;
-        const float d = sqrtf(vx * vx + vy * vy + vz * vz);
-        r.x[2] = vx / d; r.x[3] = vy / d; r.x[4] = vz / d; r.x[5] = d;
-    }
+    for (int j = 0; j < 15; ++j) r.off[j] = __ldg(op + j);
 }
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -182,23 +177,17 @@ __device__ __forceinline__ float fast_tanh(float x)
     return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
-// hidden = relu(D1 + b1) of 8 (or 4) accumulator columns, split into TF32 hi / lo, written back to TMEM
-template <int N>
-__device__ __forceinline__ void relu_split_store(const Smem &S, uint32_t tl, uint32_t col, const uint32_t (&v)[N])
+// hidden = relu(D1 + b1) of 8 accumulator columns, split into TF32 hi / lo, written back to TMEM
+__device__ __forceinline__ void relu_split_store(const Smem &S, uint32_t tl, uint32_t col, const uint32_t (&v)[8])
 {
-    uint32_t hi[N], lo[N];
+    uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
+    for (int j = 0; j < 8; ++j) {
         const float h = fmaxf(__uint_as_float(v[j]) + S.w[kOffB1 + col + j], 0.f);
         umma::split_tf32(h, hi[j], lo[j]);
     }
-    if constexpr (N == 8) {
-        umma::tmem_st8(tl + kColD1 + col, hi);
-        umma::tmem_st8(tl + kColHLo + col, lo);
-    } else {
-        umma::tmem_st4(tl + kColD1 + col, hi);
-        umma::tmem_st4(tl + kColHLo + col, lo);
-    }
+    umma::tmem_st8(tl + kColD1 + col, hi);
+    umma::tmem_st8(tl + kColHLo + col, lo);
 }
 }  // namespace ngu
 
@@ -216,9 +205,10 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = warp >> 2;                      // quarter of the row's columns / offsets
-    const int row = 32 * (warp & 3) + lane;
-    const int kbase = quarter_first(q), nq = quarter_count(q);
+    const bool front = tid < kGroup;
+    const int gtid = tid & (kGroup - 1), gwarp = gtid >> 5;   // inside the group
+    const int half = gwarp >> 2;
+    const int row = 32 * (warp & 3) + lane;                   // warp % 4 == gwarp % 4: the lane quadrant this warp may touch
     // the number of visible anchors may live on the device (no host read-back between the stages)
     const int Nv = nv_dev ? min(max(__ldg(nv_dev), 0), Nv_cap) : Nv_cap;
     const int num_tiles = (Nv + kRows - 1) / kRows;
@@ -229,9 +219,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
 
     if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
     if (tid == 0) {
-        umma::mbar_init(&S.bar[0], 1);
-        umma::mbar_init(&S.bar[1], 1);
-        umma::mbar_init(&S.bar[2], 1);
+        for (int i = 0; i < BAR_COUNT; ++i) umma::mbar_init(&S.bar[i], 1);
         umma::fence_mbar_init();
         S.timeout = 0;
     }
@@ -249,7 +237,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
     // Static round-robin tile order: the grid never exceeds the SM count and a CTA needs a whole SM
     // (222 KB shared memory, all 512 TMEM columns), so every CTA is resident and the tiles of one
     // round run concurrently -- the look-back predecessor of a tile is at most one round behind.
-    int tile = blockIdx.x, next_tile = blockIdx.x + gridDim.x;
+    const int stride = (int)gridDim.x;
 
     auto source_of = [&](int t) -> int {
         const int g = t * kRows + row;
@@ -257,154 +245,163 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
         return vis_idx ? __ldg(vis_idx + g) : g;
     };
 
-    RowInputs cur;
-    load_row_feat(cur, source_of(tile), q, feat);
-    load_row_rest(cur, q, anchor, offsets, scaling, mask);
-    int a_next = source_of(next_tile);   // the anchor index is fetched TWO tiles ahead: the row loads depend on it
-
-    for (uint32_t it = 0; tile < num_tiles; ++it) {
-        const uint32_t parity = it & 1u;
-        const int a = cur.a;
-
-        // ---- stage the layer-1 input row: quarter q -> k in [16q, 16q+16) (quarter 3: [48, 56)) -------
-        {
-            finish_row(cur, q, cx, cy, cz);
+    if (front) {
+        // =============================== FRONT: input staging, layer 1, ReLU epilogue, MMA issue ===============
+        int tile = blockIdx.x;
+        FrontInputs cur;
+        load_front(cur, source_of(tile), half, anchor, feat);
+        int a_next = source_of(tile + stride);
+        for (uint32_t it = 0; tile < num_tiles; ++it, tile += stride) {
+            const uint32_t parity = it & 1u;
+            // columns [0,352) are free once the layer-2 MMAs of the previous tile have read the hidden activations
+            if (it > 0) {
+                if (!umma::mbar_wait(&S.bar[BAR_L2ALL], parity ^ 1u)) S.timeout = 1;
+                umma::fence_after_thread_sync();
+            }
+            // ---- stage the layer-1 input row: half 0 -> k in [0,32), half 1 -> k in [32,56) ---------
+            finish_front(cur, half, cx, cy, cz);
+            {
+                const uint32_t k0 = half == 0 ? 0u : 32u;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (c == 0 || q < 3) {
-                    uint32_t hi[8], lo[8];
+                for (int c = 0; c < 4; ++c) {
+                    if (c < 3 || half == 0) {
+                        uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) umma::split_tf32(cur.x[8 * c + j], hi[j], lo[j]);
-                    umma::tmem_st8(tl + kColXHi + 16 * q + 8 * c, hi);
-                    umma::tmem_st8(tl + kColXLo + 16 * q + 8 * c, lo);
+                        for (int j = 0; j < 8; ++j) umma::split_tf32(cur.x[8 * c + j], hi[j], lo[j]);
+                        umma::tmem_st8(tl + kColXHi + k0 + 8 * c, hi);
+                        umma::tmem_st8(tl + kColXLo + k0 + 8 * c, lo);
+                    }
                 }
             }
-        }
-        umma::tmem_wait_st();
-        umma::fence_before_thread_sync();
-        __syncthreads();
-
-        // ---- layer 1: D1[128 x 176] = x[128 x 56] * W1^T ----------------------------------------
-        if (tid == 0) {
+            umma::tmem_wait_st();
+            umma::fence_before_thread_sync();
+            group_sync(1);
+            // ---- layer 1: D1[128 x 176] = x[128 x 56] * W1^T ----------------------------------------
+            if (gtid == 0) {
+                umma::fence_after_thread_sync();
+                umma::gemm_3xtf32(tbase + kColD1, tbase + kColXHi, tbase + kColXLo, S.w + kOffW1Hi, S.w + kOffW1Lo, kN1,
+                                  kK1, true);
+                umma::umma_commit(&S.bar[BAR_L1]);
+            }
+            // while the tensor core works: the next tile's input rows start travelling (index fetched a tile earlier)
+            FrontInputs nxt;
+            load_front(nxt, a_next, half, anchor, feat);
+            a_next = source_of(tile + 2 * stride);
+            if (!umma::mbar_wait(&S.bar[BAR_L1], parity)) S.timeout = 1;
             umma::fence_after_thread_sync();
-            umma::gemm_3xtf32(tbase + kColD1, tbase + kColXHi, tbase + kColXLo, S.w + kOffW1Hi, S.w + kOffW1Lo, kN1, kK1,
-                              true);
-            umma::umma_commit(&S.bar[0]);
-        }
-        // while the tensor core works: start the next tile's HBM reads (features now, the rest below)
-        RowInputs nxt;
-        load_row_feat(nxt, a_next, q, feat);
-        a_next = source_of(next_tile + (int)gridDim.x);
-        if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
-        umma::fence_after_thread_sync();
-
-        // ---- epilogue 1: hidden = relu(D1 + b1), split, back into TMEM (cols 44q .. 44q+43) -----------
-        // software pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
-        {
-            const uint32_t col0 = (uint32_t)(kQCols * q);
-            uint32_t va[8], vb[8], v4[4];
-            umma::tmem_ld8(tl + kColD1 + col0, va);
-            umma::tmem_wait_ld8(va);
-            umma::tmem_ld8(tl + kColD1 + col0 + 8, vb);
-            relu_split_store<8>(S, tl, col0, va);
-            umma::tmem_wait_ld8(vb);
-            umma::tmem_ld8(tl + kColD1 + col0 + 16, va);
-            relu_split_store<8>(S, tl, col0 + 8, vb);
-            umma::tmem_wait_ld8(va);
-            umma::tmem_ld8(tl + kColD1 + col0 + 24, vb);
-            relu_split_store<8>(S, tl, col0 + 16, va);
-            umma::tmem_wait_ld8(vb);
-            umma::tmem_ld8(tl + kColD1 + col0 + 32, va);
-            relu_split_store<8>(S, tl, col0 + 24, vb);
-            umma::tmem_wait_ld8(va);
-            umma::tmem_ld4(tl + kColD1 + col0 + 40, v4);
-            relu_split_store<8>(S, tl, col0 + 32, va);
-            umma::tmem_wait_ld4(v4);
-            relu_split_store<4>(S, tl, col0 + 40, v4);
-        }
-        umma::tmem_wait_st();
-        umma::fence_before_thread_sync();
-        __syncthreads();
-
-        // ---- layer 2: opacity head first (it decides the selection), then colour and covariance ----
-        if (tid == 0) {
-            umma::fence_after_thread_sync();
-            umma::gemm_3xtf32(tbase + kColDo, tbase + kColD1 + 0 * kHeadStride, tbase + kColHLo + 0 * kHeadStride,
-                              S.w + kOffW2oHi, S.w + kOffW2oLo, kNo, kK1, true);
-            umma::umma_commit(&S.bar[1]);
-            umma::gemm_3xtf32(tbase + kColDc, tbase + kColD1 + 1 * kHeadStride, tbase + kColHLo + 1 * kHeadStride,
-                              S.w + kOffW2cHi, S.w + kOffW2cLo, kNc, kK1, true);
-            umma::gemm_3xtf32(tbase + kColDv, tbase + kColD1 + 2 * kHeadStride, tbase + kColHLo + 2 * kHeadStride,
-                              S.w + kOffW2vHi, S.w + kOffW2vLo, kNv, kK1, true);
-            umma::umma_commit(&S.bar[2]);
-        }
-        // the rest of the next tile's rows travels while layer 2 and the epilogues run
-        load_row_rest(nxt, q, anchor, offsets, scaling, mask);
-        if (!umma::mbar_wait(&S.bar[1], parity)) S.timeout = 1;
-        umma::fence_after_thread_sync();
-
-        // ---- epilogue 2a: selection of offsets k = kbase + j, ordered ranks ------------------------------
-        float nop[kMaxOff];
-        uint32_t keepbits = 0;
-        {
-            uint32_t v[4];
-            umma::tmem_ld4(tl + kColDo + 4 * q, v);
-            umma::tmem_wait_ld4(v);
+            // ---- epilogue 1: hidden = relu(D1 + b1), split, back into TMEM (cols 88*half .. +88) ------
+            // software pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+            {
+                const uint32_t col0 = (uint32_t)(88 * half);
+                uint32_t va[8], vb[8];
+                umma::tmem_ld8(tl + kColD1 + col0, va);
+                umma::tmem_wait_ld8(va);
 #pragma unroll
-            for (int j = 0; j < kMaxOff; ++j) {
-                nop[j] = 0.f;
-                if (j < nq) {
+                for (int c = 0; c < 10; c += 2) {
+                    umma::tmem_ld8(tl + kColD1 + col0 + 8 * (c + 1), vb);
+                    relu_split_store(S, tl, col0 + 8 * c, va);
+                    umma::tmem_wait_ld8(vb);
+                    umma::tmem_ld8(tl + kColD1 + col0 + 8 * (c + 2), va);
+                    relu_split_store(S, tl, col0 + 8 * (c + 1), vb);
+                    umma::tmem_wait_ld8(va);
+                }
+                relu_split_store(S, tl, col0 + 80, va);
+            }
+            umma::tmem_wait_st();
+            umma::fence_before_thread_sync();
+            group_sync(1);
+            // ---- layer 2: opacity head first (it decides the selection), then colour and covariance ----
+            if (gtid == 0) {
+                umma::fence_after_thread_sync();
+                if (it > 0) {   // BACK must have finished reading the accumulators of the previous tile
+                    if (!umma::mbar_wait(&S.bar[BAR_ACCFREE], parity ^ 1u)) S.timeout = 1;
+                    umma::fence_after_thread_sync();
+                }
+                umma::gemm_3xtf32(tbase + kColDo, tbase + kColD1 + 0 * kHeadStride, tbase + kColHLo + 0 * kHeadStride,
+                                  S.w + kOffW2oHi, S.w + kOffW2oLo, kNo, kK1, true);
+                umma::umma_commit(&S.bar[BAR_L2O]);
+                umma::gemm_3xtf32(tbase + kColDc, tbase + kColD1 + 1 * kHeadStride, tbase + kColHLo + 1 * kHeadStride,
+                                  S.w + kOffW2cHi, S.w + kOffW2cLo, kNc, kK1, true);
+                umma::gemm_3xtf32(tbase + kColDv, tbase + kColD1 + 2 * kHeadStride, tbase + kColHLo + 2 * kHeadStride,
+                                  S.w + kOffW2vHi, S.w + kOffW2vLo, kNv, kK1, true);
+                umma::umma_commit(&S.bar[BAR_L2ALL]);
+            }
+            cur = nxt;
+        }
+    } else {
+        // =============================== BACK: selection, ordered compaction, post-processing, copy-out ==========
+        int tile = blockIdx.x;
+        BackInputs cur;
+        load_back(cur, source_of(tile), half, anchor, offsets, scaling, mask);
+        int a_next = source_of(tile + stride);
+        const int kbase = 5 * half;
+        for (uint32_t it = 0; tile < num_tiles; ++it, tile += stride) {
+            const uint32_t parity = it & 1u;
+            const int a = cur.a;
+            // the next tile's rows travel while this tile is post-processed
+            BackInputs nxt;
+            load_back(nxt, a_next, half, anchor, offsets, scaling, mask);
+            a_next = source_of(tile + 2 * stride);
+            if (!umma::mbar_wait(&S.bar[BAR_L2O], parity)) S.timeout = 1;
+            umma::fence_after_thread_sync();
+            // ---- epilogue 2a: selection of offsets k = 5*half + j, ordered ranks -------------------------
+            float nop[5];
+            uint32_t keepbits = 0;
+            {
+                uint32_t v[8];
+                umma::tmem_ld8(tl + kColDo + 8 * half, v);
+                umma::tmem_wait_ld8(v);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    nop[j] = 0.f;
                     if (a >= 0) {
-                        nop[j] = fast_tanh(__uint_as_float(v[j]) + S.w[kOffB2o + 4 * q + j]) * cur.mask[j];
+                        nop[j] = fast_tanh(__uint_as_float(v[j]) + S.w[kOffB2o + 8 * half + j]) * cur.mask[j];
                         keepbits |= nop[j] > 0.0f ? (1u << j) : 0u;
                     }
                     S.o_nop[row * kK + kbase + j] = nop[j];
                     S.o_keep[row * kK + kbase + j] = (keepbits >> j) & 1u;
                 }
             }
-        }
-        S.cnt[row * 4 + q] = __popc(keepbits);  // order index = row*4 + quarter
-        __syncthreads();
-        uint32_t total = 0;
-        {
-            const uint32_t v = S.cnt[tid];
-            uint32_t incl = v;
+            S.cnt[row * 2 + half] = __popc(keepbits);  // order index = row*2 + half
+            group_sync(2);
+            uint32_t total = 0;
+            {
+                const uint32_t v = S.cnt[gtid];
+                uint32_t incl = v;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            if (lane == 31) S.wsum[warp] = incl;
-            __syncthreads();
-            uint32_t before = 0;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (lane == 31) S.wsum[gwarp] = incl;
+                group_sync(2);
+                uint32_t before = 0;
 #pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w) {
-                const uint32_t c = S.wsum[w];
-                before += w < warp ? c : 0u;
-                total += c;
+                for (int w = 0; w < kGroup / 32; ++w) {
+                    const uint32_t c = S.wsum[w];
+                    before += w < gwarp ? c : 0u;
+                    total += c;
+                }
+                S.excl[gtid] = before + incl - v;
             }
-            S.excl[tid] = before + incl - v;
-        }
-        __syncthreads();  // tile-local ranks complete
-        if (warp == 0) {
-            // decoupled look-back across tiles.  Only warp 0 waits here: the other warps already
-            // post-process their offsets (they need tile_base only for the final copy), so the
-            // cross-CTA latency hides behind the colour / covariance MMAs and epilogue 2b.
-            const uint64_t excl = lookback_exclusive(scan_state, tile, total);
-            if (lane == 0) {
-                S.tile_base = (uint32_t)excl;
-                S.tile_total = total;
-                if (tile == num_tiles - 1) *count_out = (int32_t)(excl + total);
+            group_sync(2);  // tile-local ranks complete
+            if (gwarp == 0) {
+                // decoupled look-back across tiles.  Only one warp waits here: the others already post-process
+                // their offsets (they need tile_base only for the final copy).
+                const uint64_t excl = lookback_exclusive(scan_state, tile, total);
+                if (lane == 0) {
+                    S.tile_base = (uint32_t)excl;
+                    S.tile_total = total;
+                    if (tile == num_tiles - 1) *count_out = (int32_t)(excl + total);
+                }
             }
-        }
-        uint32_t pos = S.excl[row * 4 + q];
+            uint32_t pos = S.excl[row * 2 + half];
 
-        // ---- epilogue 2b: post-process the kept offsets into the staging buffers -----------------------
-        if (!umma::mbar_wait(&S.bar[2], parity)) S.timeout = 1;
-        umma::fence_after_thread_sync();
+            // ---- epilogue 2b: post-process the kept offsets into the staging buffers -----------------------
+            if (!umma::mbar_wait(&S.bar[BAR_L2ALL], parity)) S.timeout = 1;
+            umma::fence_after_thread_sync();
 #pragma unroll
-        for (int j = 0; j < kMaxOff; ++j) {
-            if (j < nq) {   // warp-uniform
+            for (int j = 0; j < 5; ++j) {
                 const int k = kbase + j;
                 uint32_t vc[4], vv[8];
                 umma::tmem_ld4(tl + kColDc + 4 * k, vc);
@@ -431,38 +428,36 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                     S.o_rot[p] = make_float4(cv[3] * inv, cv[4] * inv, cv[5] * inv, cv[6] * inv);
                 }
             }
-        }
-        umma::fence_before_thread_sync();
-        __syncthreads();  // staging complete, tile_base published, all TMEM reads of this tile done
-        umma::fence_after_thread_sync();
+            umma::fence_before_thread_sync();
+            group_sync(2);  // staging complete, tile_base published, all TMEM reads of this tile done
+            if (gtid == 0) mbar_arrive(&S.bar[BAR_ACCFREE]);   // FRONT may overwrite the layer-2 accumulators
 
-        // ---- coalesced copy-out ----------------------------------------------------------------------
-        {
-            const size_t base = S.tile_base;
-            // Gaussians beyond the output capacity are dropped (count_out still reports the true total)
-            const uint32_t n = base >= out_cap ? 0u : min(S.tile_total, (uint32_t)(out_cap - base));
-            for (uint32_t i = tid; i < 3 * n; i += kThreads) {
-                o_xyz[3 * base + i] = S.o_xyz[i];
-                o_color[3 * base + i] = S.o_color[i];
-                o_scaling[3 * base + i] = S.o_scaling[i];
-            }
-            for (uint32_t i = tid; i < n; i += kThreads) {
-                o_opacity[base + i] = S.o_opacity[i];
-                reinterpret_cast<float4 *>(o_rot)[base + i] = S.o_rot[i];
-            }
-            if (o_neural_opacity) {   // training-side outputs (gaussian_renderer/__init__.py:147-148); NULL at inference
-                const int valid = min(kRows, Nv - tile * kRows) * kK;
-                const size_t gp0 = (size_t)tile * kTileGauss;
-                for (int i = tid; i < valid; i += kThreads) {
-                    o_neural_opacity[gp0 + i] = S.o_nop[i];
-                    o_mask[gp0 + i] = S.o_keep[i];
+            // ---- coalesced copy-out ----------------------------------------------------------------------
+            {
+                const size_t base = S.tile_base;
+                // Gaussians beyond the output capacity are dropped (count_out still reports the true total)
+                const uint32_t n = base >= out_cap ? 0u : min(S.tile_total, (uint32_t)(out_cap - base));
+                for (uint32_t i = gtid; i < 3 * n; i += kGroup) {
+                    o_xyz[3 * base + i] = S.o_xyz[i];
+                    o_color[3 * base + i] = S.o_color[i];
+                    o_scaling[3 * base + i] = S.o_scaling[i];
+                }
+                for (uint32_t i = gtid; i < n; i += kGroup) {
+                    o_opacity[base + i] = S.o_opacity[i];
+                    reinterpret_cast<float4 *>(o_rot)[base + i] = S.o_rot[i];
+                }
+                if (o_neural_opacity) {   // training-side outputs (gaussian_renderer/__init__.py:147-148); NULL at inference
+                    const int valid = min(kRows, Nv - tile * kRows) * kK;
+                    const size_t gp0 = (size_t)tile * kTileGauss;
+                    for (int i = gtid; i < valid; i += kGroup) {
+                        o_neural_opacity[gp0 + i] = S.o_nop[i];
+                        o_mask[gp0 + i] = S.o_keep[i];
+                    }
                 }
             }
+            group_sync(2);  // staging buffers are free again
+            cur = nxt;
         }
-        __syncthreads();  // staging buffers are free again
-        cur = nxt;
-        tile = next_tile;
-        next_tile += gridDim.x;
     }
 
     umma::fence_before_thread_sync();

@@ -68,8 +68,8 @@ _pack_cache_umma = {}
 def pack_decoder_weights_umma(pc):
     """Packed block of the tcgen05 G1 kernel (layout: csrc/neural_gaussians_umma.cu `ngu::kOff*`).
     Layer-1 rows: head h (opacity, color, cov) occupies rows 56h .. 56h+49.  Layer-2 rows are placed
-    where the epilogue reads them: opacity of the j-th offset of quarter q (quarters own offsets
-    {0,1,2} {3,4,5} {6,7} {8,9}) at row 4q+j, colour (k, c) at 4k+c, covariance (k, i) at 8k+i."""
+    where the epilogue reads them: opacity of offset k at row 8(k/5)+k%5, colour (k, c) at 4k+c,
+    covariance (k, i) at 8k+i."""
     mods = (pc.get_opacity_mlp, pc.get_color_mlp, pc.get_cov_mlp)
     params = [p for m in mods for p in (m[0].weight, m[0].bias, m[2].weight, m[2].bias)]
     key = tuple((p.data_ptr(), p._version) for p in params)
@@ -87,7 +87,7 @@ def pack_decoder_weights_umma(pc):
         ko = torch.arange(K, device=dev)
         if K != 10:
             raise NotImplementedError("the tcgen05 G1 kernel is specialised for n_offsets = 10")
-        rows_o = torch.tensor([0, 1, 2, 4, 5, 6, 8, 9, 12, 13], device=dev)
+        rows_o = 8 * (ko // 5) + ko % 5
         rows_c = (4 * ko.view(K, 1) + torch.arange(3, device=dev).view(1, 3)).reshape(-1)
         rows_v = (8 * ko.view(K, 1) + torch.arange(7, device=dev).view(1, 7)).reshape(-1)
         parts, biases = list(umma_b_operand(W1, 176, 56)), [b1]
