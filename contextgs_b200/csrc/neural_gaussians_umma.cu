@@ -9,9 +9,10 @@
 //   the tensor core, HBM or issue slots -- doubling the threads per phase bought nothing, overlapping the
 //   phases of two tiles does):
 //     FRONT (warps 0-7):  stage the layer-1 input of tile t+1 -> layer-1 MMA -> ReLU epilogue in TMEM
-//                         -> issue the layer-2 MMAs as soon as BACK has released the accumulators of tile t;
-//     BACK  (warps 8-15): selection, ordered compaction (block scan + decoupled look-back across tiles),
-//                         post-processing and coalesced copy-out of tile t.
+//                         -> issue the layer-2 MMAs as soon as BACK has released the accumulators of tile t
+//                         -> coalesced copy-out of tile t from the staging area BACK has just filled;
+//     BACK  (warps 8-15): selection, ordered compaction (block scan + decoupled look-back across tiles) and
+//                         post-processing of tile t into the staging area.
 //   Inside a group, thread (row = 32*(warp%4) + lane, half = (warp%8)/4): two threads share a row.
 //
 //   TMEM columns (496 of 512):
@@ -59,7 +60,7 @@ constexpr int kPacked = kOffB2v + kNv;      // 36160 floats = 144640 B
 constexpr int kTileGauss = kRows * kK;       // 1280 (anchor, offset) pairs per tile
 
 // mbarriers
-enum { BAR_L1 = 0, BAR_L2O, BAR_L2ALL, BAR_ACCFREE, BAR_COUNT };
+enum { BAR_L1 = 0, BAR_L2O, BAR_L2ALL, BAR_ACCFREE, BAR_STAGEFREE, BAR_COUNT };
 
 struct Smem {
     float w[kPacked];
@@ -67,12 +68,10 @@ struct Smem {
     // to HBM as contiguous, fully coalesced segments
     float o_xyz[kTileGauss * 3], o_color[kTileGauss * 3], o_opacity[kTileGauss], o_scaling[kTileGauss * 3];
     float4 o_rot[kTileGauss];
-    float o_nop[kTileGauss];
-    uint8_t o_keep[kTileGauss];
     uint32_t cnt[kGroup];         // kept Gaussians per (row, half), index = row*2 + half
     uint32_t excl[kGroup];
     uint32_t wsum[kGroup / 32];
-    uint32_t tile_base, tile_total;
+    uint32_t tile_base[2], tile_total[2];   // by tile parity: FRONT copies tile t out while BACK already scans tile t+1
     uint32_t tmem;
     int timeout;
     alignas(8) uint64_t bar[BAR_COUNT];
@@ -251,8 +250,26 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
         FrontInputs cur;
         load_front(cur, source_of(tile), half, anchor, feat);
         int a_next = source_of(tile + stride);
+        // coalesced copy-out of a staged tile (its base / size were parked by tile parity)
+        auto copy_out = [&](uint32_t par) {
+            const size_t base = S.tile_base[par];
+            // Gaussians beyond the output capacity are dropped (count_out still reports the true total)
+            const uint32_t n = base >= out_cap ? 0u : min(S.tile_total[par], (uint32_t)(out_cap - base));
+            for (uint32_t i = gtid; i < 3 * n; i += kGroup) {
+                o_xyz[3 * base + i] = S.o_xyz[i];
+                o_color[3 * base + i] = S.o_color[i];
+                o_scaling[3 * base + i] = S.o_scaling[i];
+            }
+            for (uint32_t i = gtid; i < n; i += kGroup) {
+                o_opacity[base + i] = S.o_opacity[i];
+                reinterpret_cast<float4 *>(o_rot)[base + i] = S.o_rot[i];
+            }
+        };
+        uint32_t last_it = 0;
+        bool any = false;
         for (uint32_t it = 0; tile < num_tiles; ++it, tile += stride) {
             const uint32_t parity = it & 1u;
+            any = true;
             // columns [0,352) are free once the layer-2 MMAs of the previous tile have read the hidden activations
             if (it > 0) {
                 if (!umma::mbar_wait(&S.bar[BAR_L2ALL], parity ^ 1u)) S.timeout = 1;
@@ -311,12 +328,12 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
             umma::fence_before_thread_sync();
             group_sync(1);
             // ---- layer 2: opacity head first (it decides the selection), then colour and covariance ----
+            if (it > 0) {   // BACK has finished reading the accumulators of the previous tile and filled the staging area
+                if (!umma::mbar_wait(&S.bar[BAR_ACCFREE], parity ^ 1u)) S.timeout = 1;
+                umma::fence_after_thread_sync();
+            }
             if (gtid == 0) {
                 umma::fence_after_thread_sync();
-                if (it > 0) {   // BACK must have finished reading the accumulators of the previous tile
-                    if (!umma::mbar_wait(&S.bar[BAR_ACCFREE], parity ^ 1u)) S.timeout = 1;
-                    umma::fence_after_thread_sync();
-                }
                 umma::gemm_3xtf32(tbase + kColDo, tbase + kColD1 + 0 * kHeadStride, tbase + kColHLo + 0 * kHeadStride,
                                   S.w + kOffW2oHi, S.w + kOffW2oLo, kNo, kK1, true);
                 umma::umma_commit(&S.bar[BAR_L2O]);
@@ -326,7 +343,17 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                                   S.w + kOffW2vHi, S.w + kOffW2vLo, kNv, kK1, true);
                 umma::umma_commit(&S.bar[BAR_L2ALL]);
             }
+            if (it > 0) {   // copy the previous tile out while the tensor core and BACK work on
+                copy_out((it - 1) & 1u);
+                group_sync(1);
+                if (gtid == 0) mbar_arrive(&S.bar[BAR_STAGEFREE]);
+            }
+            last_it = it;
             cur = nxt;
+        }
+        if (any) {   // the last tile of this CTA
+            if (!umma::mbar_wait(&S.bar[BAR_ACCFREE], last_it & 1u)) S.timeout = 1;
+            copy_out(last_it & 1u);
         }
     } else {
         // =============================== BACK: selection, ordered compaction, post-processing, copy-out ==========
@@ -358,8 +385,11 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                         nop[j] = fast_tanh(__uint_as_float(v[j]) + S.w[kOffB2o + 8 * half + j]) * cur.mask[j];
                         keepbits |= nop[j] > 0.0f ? (1u << j) : 0u;
                     }
-                    S.o_nop[row * kK + kbase + j] = nop[j];
-                    S.o_keep[row * kK + kbase + j] = (keepbits >> j) & 1u;
+                    if (o_neural_opacity && tile * kRows + row < Nv) {   // training-side outputs (gaussian_renderer/__init__.py:147-148)
+                        const size_t gp = ((size_t)tile * kRows + row) * kK + kbase + j;
+                        o_neural_opacity[gp] = nop[j];
+                        o_mask[gp] = (keepbits >> j) & 1u;
+                    }
                 }
             }
             S.cnt[row * 2 + half] = __popc(keepbits);  // order index = row*2 + half
@@ -390,8 +420,8 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                 // their offsets (they need tile_base only for the final copy).
                 const uint64_t excl = lookback_exclusive(scan_state, tile, total);
                 if (lane == 0) {
-                    S.tile_base = (uint32_t)excl;
-                    S.tile_total = total;
+                    S.tile_base[parity] = (uint32_t)excl;
+                    S.tile_total[parity] = total;
                     if (tile == num_tiles - 1) *count_out = (int32_t)(excl + total);
                 }
             }
@@ -400,6 +430,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
             // ---- epilogue 2b: post-process the kept offsets into the staging buffers -----------------------
             if (!umma::mbar_wait(&S.bar[BAR_L2ALL], parity)) S.timeout = 1;
             umma::fence_after_thread_sync();
+            if (it > 0 && !umma::mbar_wait(&S.bar[BAR_STAGEFREE], parity ^ 1u)) S.timeout = 1;   // FRONT has copied tile t-1 out
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
                 const int k = kbase + j;
@@ -430,32 +461,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
             }
             umma::fence_before_thread_sync();
             group_sync(2);  // staging complete, tile_base published, all TMEM reads of this tile done
-            if (gtid == 0) mbar_arrive(&S.bar[BAR_ACCFREE]);   // FRONT may overwrite the layer-2 accumulators
-
-            // ---- coalesced copy-out ----------------------------------------------------------------------
-            {
-                const size_t base = S.tile_base;
-                // Gaussians beyond the output capacity are dropped (count_out still reports the true total)
-                const uint32_t n = base >= out_cap ? 0u : min(S.tile_total, (uint32_t)(out_cap - base));
-                for (uint32_t i = gtid; i < 3 * n; i += kGroup) {
-                    o_xyz[3 * base + i] = S.o_xyz[i];
-                    o_color[3 * base + i] = S.o_color[i];
-                    o_scaling[3 * base + i] = S.o_scaling[i];
-                }
-                for (uint32_t i = gtid; i < n; i += kGroup) {
-                    o_opacity[base + i] = S.o_opacity[i];
-                    reinterpret_cast<float4 *>(o_rot)[base + i] = S.o_rot[i];
-                }
-                if (o_neural_opacity) {   // training-side outputs (gaussian_renderer/__init__.py:147-148); NULL at inference
-                    const int valid = min(kRows, Nv - tile * kRows) * kK;
-                    const size_t gp0 = (size_t)tile * kTileGauss;
-                    for (int i = gtid; i < valid; i += kGroup) {
-                        o_neural_opacity[gp0 + i] = S.o_nop[i];
-                        o_mask[gp0 + i] = S.o_keep[i];
-                    }
-                }
-            }
-            group_sync(2);  // staging buffers are free again
+            if (gtid == 0) mbar_arrive(&S.bar[BAR_ACCFREE]);   // FRONT may overwrite the layer-2 accumulators and copy the tile out
             cur = nxt;
         }
     }
