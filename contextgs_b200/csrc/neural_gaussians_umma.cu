@@ -431,32 +431,40 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
             if (!umma::mbar_wait(&S.bar[BAR_L2ALL], parity)) S.timeout = 1;
             umma::fence_after_thread_sync();
             if (it > 0 && !umma::mbar_wait(&S.bar[BAR_STAGEFREE], parity ^ 1u)) S.timeout = 1;   // FRONT has copied tile t-1 out
+            {
+                // tcgen05.ld of offset j+1 is in flight while offset j is post-processed
+                uint32_t vc[2][4], vv[2][8];
+                umma::tmem_ld4(tl + kColDc + 4 * kbase, vc[0]);
+                umma::tmem_ld8(tl + kColDv + 8 * kbase, vv[0]);
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const int k = kbase + j;
-                uint32_t vc[4], vv[8];
-                umma::tmem_ld4(tl + kColDc + 4 * k, vc);
-                umma::tmem_ld8(tl + kColDv + 8 * k, vv);
-                umma::tmem_wait_ld4(vc);
-                umma::tmem_wait_ld8(vv);
-                if (keepbits & (1u << j)) {
-                    const uint32_t p = pos++;
-                    S.o_xyz[3 * p + 0] = cur.anchor[0] + cur.off[3 * j + 0] * cur.sc[0];
-                    S.o_xyz[3 * p + 1] = cur.anchor[1] + cur.off[3 * j + 1] * cur.sc[1];
-                    S.o_xyz[3 * p + 2] = cur.anchor[2] + cur.off[3 * j + 2] * cur.sc[2];
-                    S.o_color[3 * p + 0] = fast_sigmoid(__uint_as_float(vc[0]) + S.w[kOffB2c + 4 * k + 0]);
-                    S.o_color[3 * p + 1] = fast_sigmoid(__uint_as_float(vc[1]) + S.w[kOffB2c + 4 * k + 1]);
-                    S.o_color[3 * p + 2] = fast_sigmoid(__uint_as_float(vc[2]) + S.w[kOffB2c + 4 * k + 2]);
-                    S.o_opacity[p] = nop[j];
-                    float cv[7];
+                for (int j = 0; j < 5; ++j) {
+                    const int k = kbase + j;
+                    const int b = j & 1;
+                    umma::tmem_wait_ld4(vc[b]);
+                    umma::tmem_wait_ld8(vv[b]);
+                    if (j + 1 < 5) {
+                        umma::tmem_ld4(tl + kColDc + 4 * (k + 1), vc[b ^ 1]);
+                        umma::tmem_ld8(tl + kColDv + 8 * (k + 1), vv[b ^ 1]);
+                    }
+                    if (keepbits & (1u << j)) {
+                        const uint32_t p = pos++;
+                        S.o_xyz[3 * p + 0] = cur.anchor[0] + cur.off[3 * j + 0] * cur.sc[0];
+                        S.o_xyz[3 * p + 1] = cur.anchor[1] + cur.off[3 * j + 1] * cur.sc[1];
+                        S.o_xyz[3 * p + 2] = cur.anchor[2] + cur.off[3 * j + 2] * cur.sc[2];
+                        S.o_color[3 * p + 0] = fast_sigmoid(__uint_as_float(vc[b][0]) + S.w[kOffB2c + 4 * k + 0]);
+                        S.o_color[3 * p + 1] = fast_sigmoid(__uint_as_float(vc[b][1]) + S.w[kOffB2c + 4 * k + 1]);
+                        S.o_color[3 * p + 2] = fast_sigmoid(__uint_as_float(vc[b][2]) + S.w[kOffB2c + 4 * k + 2]);
+                        S.o_opacity[p] = nop[j];
+                        float cv[7];
 #pragma unroll
-                    for (int i = 0; i < 7; ++i) cv[i] = __uint_as_float(vv[i]) + S.w[kOffB2v + 8 * k + i];
-                    S.o_scaling[3 * p + 0] = cur.sc[3] * fast_sigmoid(cv[0]);
-                    S.o_scaling[3 * p + 1] = cur.sc[4] * fast_sigmoid(cv[1]);
-                    S.o_scaling[3 * p + 2] = cur.sc[5] * fast_sigmoid(cv[2]);
-                    const float ss = cv[3] * cv[3] + cv[4] * cv[4] + cv[5] * cv[5] + cv[6] * cv[6];
-                    const float inv = rsqrtf(fmaxf(ss, 1e-24f));  // F.normalize: v / max(|v|, 1e-12)
-                    S.o_rot[p] = make_float4(cv[3] * inv, cv[4] * inv, cv[5] * inv, cv[6] * inv);
+                        for (int i = 0; i < 7; ++i) cv[i] = __uint_as_float(vv[b][i]) + S.w[kOffB2v + 8 * k + i];
+                        S.o_scaling[3 * p + 0] = cur.sc[3] * fast_sigmoid(cv[0]);
+                        S.o_scaling[3 * p + 1] = cur.sc[4] * fast_sigmoid(cv[1]);
+                        S.o_scaling[3 * p + 2] = cur.sc[5] * fast_sigmoid(cv[2]);
+                        const float ss = cv[3] * cv[3] + cv[4] * cv[4] + cv[5] * cv[5] + cv[6] * cv[6];
+                        const float inv = rsqrtf(fmaxf(ss, 1e-24f));  // F.normalize: v / max(|v|, 1e-12)
+                        S.o_rot[p] = make_float4(cv[3] * inv, cv[4] * inv, cv[5] * inv, cv[6] * inv);
+                    }
                 }
             }
             umma::fence_before_thread_sync();
