@@ -21,7 +21,7 @@
 
 namespace cgs {
 namespace cmu {
-constexpr int kRows = 128, kThreads = 256;
+constexpr int kRows = 128, kThreads = 512, kGroup = 256;   // two warp groups of 8 warps (see the kernel)
 constexpr int kN1 = 112, kK2 = 104, kN2 = 176;
 constexpr uint32_t kColXHi = 0, kColXLo = 72, kColHLo = 0, kColD1 = 144, kColD2 = 256, kTmemCols = 512;
 
@@ -41,8 +41,14 @@ struct Smem {
     float w[Layout<K1>::kPacked];
     uint32_t tmem;
     int timeout;
-    alignas(8) uint64_t bar[2];
+    alignas(8) uint64_t bar[3];   // layer-1 done | layer-2 done | layer-2 accumulator released by BACK
 };
+
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kGroup) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
 
 struct Args {
     const float *packed_w;
@@ -142,14 +148,22 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SM &S = *reinterpret_cast<SM *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = warp >> 2;
+    // Two warp groups work on DIFFERENT tiles (as in neural_gaussians_umma.cu): FRONT (warps 0-7) gathers and stages
+    // the context rows of tile t+1, runs layer 1 and the ReLU epilogue and issues layer 2 as soon as BACK has released
+    // the layer-2 accumulator of tile t; BACK (warps 8-15) runs the likelihood epilogue of tile t.  TMEM columns
+    // [0,256) belong to FRONT (free once the layer-2 MMAs have read the hidden activations), [256,432) change hands.
+    const bool front = tid < kGroup;
+    const int gwarp = (tid & (kGroup - 1)) >> 5, gtid = tid & (kGroup - 1);
+    const int half = gwarp >> 2;
     const int row = 32 * (warp & 3) + lane;
     const int num_tiles = (A.n_rows + kRows - 1) / kRows;
+    const int stride = (int)gridDim.x;
 
     if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
     if (tid == 0) {
         umma::mbar_init(&S.bar[0], 1);
         umma::mbar_init(&S.bar[1], 1);
+        umma::mbar_init(&S.bar[2], 1);
         umma::fence_mbar_init();
         S.timeout = 0;
     }
@@ -167,159 +181,179 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
 
     double tot_f = 0.0, tot_s = 0.0, tot_o = 0.0;   // fp64 across tiles: the sums are exact to ~1e-7
     float n_chosen = 0.f;
-    int tile = blockIdx.x;
-    RowInputs<K1> cur;
-    load_row<K1>(cur, A, tile * kRows + row, half);
+    const bool pred = A.predict_only != 0;
 
-    for (uint32_t it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
-        const uint32_t parity = it & 1u;
-        const int grow = tile * kRows + row;
-        const int o = cur.o;
-        float sum_f = 0.f, sum_s = 0.f, sum_o = 0.f;
-
-        // ---- stage the layer-1 input --------------------------------------------------------------
-        {
-            const uint32_t k0 = half == 0 ? 0u : (uint32_t)LY::kHalf0;
-            constexpr int kChunks0 = LY::kHalf0 / 8, kChunks1 = (LY::kK1p - LY::kHalf0) / 8;
+    if (front) {
+        // =============================== FRONT: gather + stage, layer 1, ReLU epilogue, MMA issue ===============
+        int tile = blockIdx.x;
+        RowInputs<K1> cur;
+        load_row<K1>(cur, A, tile * kRows + row, half);
+        for (uint32_t it = 0; tile < num_tiles; ++it, tile += stride) {
+            const uint32_t parity = it & 1u;
+            if (it > 0) {   // the layer-2 MMAs of the previous tile have read the hidden activations: columns [0,256) are free
+                if (!umma::mbar_wait(&S.bar[1], parity ^ 1u)) S.timeout = 1;
+                umma::fence_after_thread_sync();
+            }
+            // ---- stage the layer-1 input --------------------------------------------------------------
+            {
+                const uint32_t k0 = half == 0 ? 0u : (uint32_t)LY::kHalf0;
+                constexpr int kChunks0 = LY::kHalf0 / 8, kChunks1 = (LY::kK1p - LY::kHalf0) / 8;
 #pragma unroll
-            for (int c = 0; c < (kChunks0 > kChunks1 ? kChunks0 : kChunks1); ++c) {
-                if (c < (half == 0 ? kChunks0 : kChunks1)) {
-                    uint32_t hi[8], lo[8];
+                for (int c = 0; c < (kChunks0 > kChunks1 ? kChunks0 : kChunks1); ++c) {
+                    if (c < (half == 0 ? kChunks0 : kChunks1)) {
+                        uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) umma::split_tf32(cur.x[8 * c + j], hi[j], lo[j]);
-                    umma::tmem_st8(tl + kColXHi + k0 + 8 * c, hi);
-                    umma::tmem_st8(tl + kColXLo + k0 + 8 * c, lo);
+                        for (int j = 0; j < 8; ++j) umma::split_tf32(cur.x[8 * c + j], hi[j], lo[j]);
+                        umma::tmem_st8(tl + kColXHi + k0 + 8 * c, hi);
+                        umma::tmem_st8(tl + kColXLo + k0 + 8 * c, lo);
+                    }
                 }
             }
-        }
-        umma::tmem_wait_st();
-        umma::fence_before_thread_sync();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_thread_sync();
-            umma::gemm_3xtf32(tbase + kColD1, tbase + kColXHi, tbase + kColXLo, S.w + LY::kOffW1Hi, S.w + LY::kOffW1Lo,
-                              kN1, LY::kK1p, true);
-            umma::umma_commit(&S.bar[0]);
-        }
-        // while the tensor core works: this row's share of the attributes to be coded (43 values per thread)
-        // and the next tile's gathered context rows travel from HBM
-        const bool pred = A.predict_only != 0;
-        const bool chosen = !pred && o >= 0 && (A.choose ? A.choose[o] != 0 : true);
-        // offset masks of the row as bits (values are exactly 0 / 1: utils/entropy_models / gaussian_model.py:1670)
-        uint32_t mkbits = 0x3ffu;
-        if (o >= 0 && half == 1 && chosen) {
-            mkbits = 0;
-#pragma unroll
-            for (int k = 0; k < 10; ++k) mkbits |= __ldg(A.mask + o * 10 + k) != 0.f ? (1u << k) : 0u;
-        }
-        RowInputs<K1> nxt;
-        load_row<K1>(nxt, A, (tile + (int)gridDim.x) * kRows + row, half);
-        if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
-        umma::fence_after_thread_sync();
-
-        // ---- epilogue 1: hidden = relu(D1 + b1) -> hi in place, lo to region 0 (cols 56*half .. +56) ----
-#pragma unroll 1
-        for (int c = 0; c < 7; ++c) {
-            const uint32_t col = (uint32_t)(56 * half + 8 * c);
-            uint32_t v[8], hi[8], lo[8];
-            umma::tmem_ld8(tl + kColD1 + col, v);
-            umma::tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float h = fmaxf(__uint_as_float(v[j]) + S.w[LY::kOffB1 + col + j], 0.f);
-                umma::split_tf32(h, hi[j], lo[j]);
+            umma::tmem_wait_st();
+            umma::fence_before_thread_sync();
+            group_sync(1);
+            if (gtid == 0) {
+                umma::fence_after_thread_sync();
+                umma::gemm_3xtf32(tbase + kColD1, tbase + kColXHi, tbase + kColXLo, S.w + LY::kOffW1Hi, S.w + LY::kOffW1Lo,
+                                  kN1, LY::kK1p, true);
+                umma::umma_commit(&S.bar[0]);
             }
-            umma::tmem_st8(tl + kColD1 + col, hi);
-            umma::tmem_st8(tl + kColHLo + col, lo);
-        }
-        umma::tmem_wait_st();
-        umma::fence_before_thread_sync();
-        __syncthreads();
-        if (tid == 0) {
+            // while the tensor core works: the next tile's gathered context rows travel from HBM
+            RowInputs<K1> nxt;
+            load_row<K1>(nxt, A, (tile + stride) * kRows + row, half);
+            if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
             umma::fence_after_thread_sync();
-            umma::gemm_3xtf32(tbase + kColD2, tbase + kColD1, tbase + kColHLo, S.w + LY::kOffW2Hi, S.w + LY::kOffW2Lo, kN2,
-                              kK2, true);
-            umma::umma_commit(&S.bar[1]);
-        }
-        if (!umma::mbar_wait(&S.bar[1], parity)) S.timeout = 1;
-        umma::fence_after_thread_sync();
-
-        // ---- epilogue 2: steps, quantise, scatter, bits ----------------------------------------------
-        float Qf, Qs, Qo;
-        {
-            uint32_t v[4];
-            umma::tmem_ld4(tl + kColD2 + 172, v);
-            umma::tmem_wait_ld();
-            Qf = fmaxf(kQf0 * (1.0f + tanhf(__uint_as_float(v[0]) + S.w[LY::kOffB2 + 172])), 1e-9f);
-            Qs = fmaxf(kQs0 * (1.0f + tanhf(__uint_as_float(v[1]) + S.w[LY::kOffB2 + 173])), 1e-9f);
-            Qo = fmaxf(kQo0 * (1.0f + tanhf(__uint_as_float(v[2]) + S.w[LY::kOffB2 + 174])), 1e-9f);
-        }
-        if (half == 0 && chosen) n_chosen += 1.f;
-        float *prow = (A.params_out && o >= 0) ? A.params_out + (size_t)grow * kLdG2 : nullptr;
-        if (prow && half == 0) {
-            prow[172] = Qf; prow[173] = Qs; prow[174] = Qo; prow[175] = 0.f;
-        }
-        const float *nz = A.noise ? A.noise + (size_t)grow * kCE : nullptr;
-        // The six groups run as a ROLLED loop: fully unrolled (with the attributes prefetched into 48 registers) the
-        // kernel was 24.9 k SASS instructions and spent its time waiting for the instruction cache ("no instruction"
-        // was the top stall reason, profiles/r01_ctx2_*).  The attributes of group c+1 are fetched while group c is
-        // evaluated.
-        auto fetch_x = [&](int c, float (&x8)[8]) {
-            const ChunkDesc cd = chunk_desc(c, half);
-            const float *src = (cd.grp == 0 ? A.feat : (cd.grp == 1 ? A.scaling : A.offsets)) + (size_t)(o < 0 ? 0 : o) * cd.dim + cd.k0;
+            // ---- epilogue 1: hidden = relu(D1 + b1) -> hi in place, lo to region 0 (cols 56*half .. +56) ----
+#pragma unroll 1
+            for (int c = 0; c < 7; ++c) {
+                const uint32_t col = (uint32_t)(56 * half + 8 * c);
+                uint32_t v[8], hi[8], lo[8];
+                umma::tmem_ld8(tl + kColD1 + col, v);
+                umma::tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x8[j] = (!pred && o >= 0 && j < cd.cnt) ? __ldg(src + j) : 0.f;
+                for (int j = 0; j < 8; ++j) {
+                    const float h = fmaxf(__uint_as_float(v[j]) + S.w[LY::kOffB1 + col + j], 0.f);
+                    umma::split_tf32(h, hi[j], lo[j]);
+                }
+                umma::tmem_st8(tl + kColD1 + col, hi);
+                umma::tmem_st8(tl + kColHLo + col, lo);
+            }
+            umma::tmem_wait_st();
+            umma::fence_before_thread_sync();
+            group_sync(1);
+            if (gtid == 0) {
+                umma::fence_after_thread_sync();
+                if (it > 0) {   // BACK has finished reading the layer-2 accumulator of the previous tile
+                    if (!umma::mbar_wait(&S.bar[2], parity ^ 1u)) S.timeout = 1;
+                    umma::fence_after_thread_sync();
+                }
+                umma::gemm_3xtf32(tbase + kColD2, tbase + kColD1, tbase + kColHLo, S.w + LY::kOffW2Hi, S.w + LY::kOffW2Lo,
+                                  kN2, kK2, true);
+                umma::umma_commit(&S.bar[1]);
+            }
+            cur = nxt;
+        }
+    } else {
+        // =============================== BACK: steps, quantise, scatter, likelihood ===============================
+        int tile = blockIdx.x;
+        auto orig_of = [&](int t) -> int {
+            const int g = t * kRows + row;
+            return (t < num_tiles && g < A.n_rows) ? __ldg(A.orig_idx + g) : -1;
         };
-        float xn[8];
-        fetch_x(0, xn);
-#pragma unroll 1
-        for (int c = 0; c < 6; ++c) {
-            const ChunkDesc cd = chunk_desc(c, half);
-            uint32_t vm[8], vs[8];
-            float xc[8];
+        int o_next = orig_of(tile);
+        for (uint32_t it = 0; tile < num_tiles; ++it, tile += stride) {
+            const uint32_t parity = it & 1u;
+            const int grow = tile * kRows + row;
+            const int o = o_next;
+            o_next = orig_of(tile + stride);
+            float sum_f = 0.f, sum_s = 0.f, sum_o = 0.f;
+            const bool chosen = !pred && o >= 0 && (A.choose ? A.choose[o] != 0 : true);
+            // offset masks of the row as bits (values are exactly 0 / 1: utils/entropy_models / gaussian_model.py:1670)
+            uint32_t mkbits = 0x3ffu;
+            if (o >= 0 && half == 1 && chosen) {
+                mkbits = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xc[j] = xn[j];
-            umma::tmem_ld8(tl + kColD2 + cd.mu_col, vm);
-            umma::tmem_ld8(tl + kColD2 + cd.sg_col, vs);
-            if (c + 1 < 6) fetch_x(c + 1, xn);
-            umma::tmem_wait_ld();
-            if (o < 0) continue;
-            const float Q = cd.grp == 0 ? Qf : (cd.grp == 1 ? Qs : Qo);
-            const float x_mean = cd.grp == 0 ? A.feat_mean : (cd.grp == 1 ? A.scaling_mean : A.offset_mean);
-            float *dst = (cd.grp == 0 ? A.feat_q : (cd.grp == 1 ? A.scaling_q : A.offsets_q)) + o * cd.dim + cd.k0;
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < cd.cnt) {
-                    const float mean = __uint_as_float(vm[j]) + S.w[LY::kOffB2 + cd.mu_col + j];
-                    const float scale = __uint_as_float(vs[j]) + S.w[LY::kOffB2 + cd.sg_col + j];
-                    if (prow) {
-                        prow[cd.j0 + j] = mean;
-                        prow[kCE + cd.j0 + j] = scale;
-                    }
-                    if (pred) continue;
-                    const float x = xc[j];
-                    const float xq = nz ? x + nz[cd.j0 + j] * Q : ste_round(x, Q);
-                    dst[j] = xq;
-                    float bits = 0.f;
-                    if (chosen) {
-                        bits = gaussian_bits_one(xq, mean, scale, Q, x_mean);
-                        if (cd.grp == 2 && !((mkbits >> ((cd.k0 + j) / 3)) & 1u)) bits = 0.f;
-                        acc += bits;
-                    }
-                    if (A.bits_out) A.bits_out[(size_t)o * kCE + cd.j0 + j] = bits;
-                }
+                for (int k = 0; k < 10; ++k) mkbits |= __ldg(A.mask + o * 10 + k) != 0.f ? (1u << k) : 0u;
             }
-            if (cd.grp == 0) sum_f += acc;
-            else if (cd.grp == 1) sum_s += acc;
-            else sum_o += acc;
+            // The six groups run as a ROLLED loop: fully unrolled (with the attributes prefetched into 48 registers) the
+            // kernel was 24.9 k SASS instructions and spent its time waiting for the instruction cache ("no instruction"
+            // was the top stall reason, profiles/r01_ctx2_*).  The attributes of group c+1 are fetched while group c is
+            // evaluated; those of group 0 while the layer-2 MMAs run.
+            auto fetch_x = [&](int c, float (&x8)[8]) {
+                const ChunkDesc cd = chunk_desc(c, half);
+                const float *src = (cd.grp == 0 ? A.feat : (cd.grp == 1 ? A.scaling : A.offsets)) + (size_t)(o < 0 ? 0 : o) * cd.dim + cd.k0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x8[j] = (!pred && o >= 0 && j < cd.cnt) ? __ldg(src + j) : 0.f;
+            };
+            float xn[8];
+            fetch_x(0, xn);
+            if (!umma::mbar_wait(&S.bar[1], parity)) S.timeout = 1;
+            umma::fence_after_thread_sync();
+
+            // ---- epilogue 2: steps, quantise, scatter, bits ----------------------------------------------
+            float Qf, Qs, Qo;
+            {
+                uint32_t v[4];
+                umma::tmem_ld4(tl + kColD2 + 172, v);
+                umma::tmem_wait_ld();
+                Qf = fmaxf(kQf0 * (1.0f + tanhf(__uint_as_float(v[0]) + S.w[LY::kOffB2 + 172])), 1e-9f);
+                Qs = fmaxf(kQs0 * (1.0f + tanhf(__uint_as_float(v[1]) + S.w[LY::kOffB2 + 173])), 1e-9f);
+                Qo = fmaxf(kQo0 * (1.0f + tanhf(__uint_as_float(v[2]) + S.w[LY::kOffB2 + 174])), 1e-9f);
+            }
+            if (half == 0 && chosen) n_chosen += 1.f;
+            float *prow = (A.params_out && o >= 0) ? A.params_out + (size_t)grow * kLdG2 : nullptr;
+            if (prow && half == 0) {
+                prow[172] = Qf; prow[173] = Qs; prow[174] = Qo; prow[175] = 0.f;
+            }
+            const float *nz = A.noise ? A.noise + (size_t)grow * kCE : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < 6; ++c) {
+                const ChunkDesc cd = chunk_desc(c, half);
+                uint32_t vm[8], vs[8];
+                float xc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xc[j] = xn[j];
+                umma::tmem_ld8(tl + kColD2 + cd.mu_col, vm);
+                umma::tmem_ld8(tl + kColD2 + cd.sg_col, vs);
+                if (c + 1 < 6) fetch_x(c + 1, xn);
+                umma::tmem_wait_ld();
+                if (o < 0) continue;
+                const float Q = cd.grp == 0 ? Qf : (cd.grp == 1 ? Qs : Qo);
+                const float x_mean = cd.grp == 0 ? A.feat_mean : (cd.grp == 1 ? A.scaling_mean : A.offset_mean);
+                float *dst = (cd.grp == 0 ? A.feat_q : (cd.grp == 1 ? A.scaling_q : A.offsets_q)) + o * cd.dim + cd.k0;
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < cd.cnt) {
+                        const float mean = __uint_as_float(vm[j]) + S.w[LY::kOffB2 + cd.mu_col + j];
+                        const float scale = __uint_as_float(vs[j]) + S.w[LY::kOffB2 + cd.sg_col + j];
+                        if (prow) {
+                            prow[cd.j0 + j] = mean;
+                            prow[kCE + cd.j0 + j] = scale;
+                        }
+                        if (pred) continue;
+                        const float x = xc[j];
+                        const float xq = nz ? x + nz[cd.j0 + j] * Q : ste_round(x, Q);
+                        dst[j] = xq;
+                        float bits = 0.f;
+                        if (chosen) {
+                            bits = gaussian_bits_one(xq, mean, scale, Q, x_mean);
+                            if (cd.grp == 2 && !((mkbits >> ((cd.k0 + j) / 3)) & 1u)) bits = 0.f;
+                            acc += bits;
+                        }
+                        if (A.bits_out) A.bits_out[(size_t)o * kCE + cd.j0 + j] = bits;
+                    }
+                }
+                if (cd.grp == 0) sum_f += acc;
+                else if (cd.grp == 1) sum_s += acc;
+                else sum_o += acc;
+            }
+            tot_f += (double)sum_f; tot_s += (double)sum_s; tot_o += (double)sum_o;
+            // all TMEM reads of this tile are complete: FRONT may issue the next tile's layer-2 MMAs
+            umma::fence_before_thread_sync();
+            group_sync(2);
+            if (gtid == 0) mbar_arrive(&S.bar[2]);
         }
-        tot_f += (double)sum_f; tot_s += (double)sum_s; tot_o += (double)sum_o;
-        // all TMEM reads of this tile are complete before the next tile's stores / MMAs reuse the columns
-        umma::fence_before_thread_sync();
-        __syncthreads();
-        umma::fence_after_thread_sync();
-        cur = nxt;
     }
 
     // ---- per-CTA reduction of the bit sums -> one fp64 atomic per sum ----------------------------------
