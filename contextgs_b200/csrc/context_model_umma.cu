@@ -21,7 +21,7 @@
 
 namespace cgs {
 namespace cmu {
-constexpr int kRows = 128, kThreads = 512, kGroup = 256;   // two warp groups of 8 warps (see the kernel)
+constexpr int kRows = 128, kFront = 256, kBack = 512, kThreads = kFront + kBack;   // FRONT: 8 warps, BACK: 16 warps (see the kernel)
 constexpr int kN1 = 112, kK2 = 104, kN2 = 176;
 constexpr uint32_t kColXHi = 0, kColXLo = 72, kColHLo = 0, kColD1 = 144, kColD2 = 256, kTmemCols = 512;
 
@@ -44,7 +44,8 @@ struct Smem {
     alignas(8) uint64_t bar[3];   // layer-1 done | layer-2 done | layer-2 accumulator released by BACK
 };
 
-__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kGroup) : "memory"); }
+template <int kCount>
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kCount) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
@@ -114,28 +115,33 @@ __device__ __forceinline__ void load_row(RowInputs<K1> &r, const Args &A, int ro
     }
 }
 
-// The 43 coded values of a thread are processed in 6 groups of <= 8 consecutive values of one attribute:
-//   half 0: feat 0..42;   half 1: feat 43..49 | scaling 0..5 | offsets 0..29
 struct ChunkDesc {
     int j0;              // index among the 86 coded values
     int cnt;             // values in the group
     uint32_t mu_col, sg_col;  // accumulator columns of mean / scale
     int grp, dim, k0;    // attribute (0 feat, 1 scaling, 2 offsets), its row width, first index inside it
 };
-__device__ __forceinline__ ChunkDesc chunk_desc(int c, int half)
+
+// BACK: four threads share a row; the 86 coded values are split into quarters of three groups of <= 8 values each:
+//   q0: feat 0..23;  q1: feat 24..47;  q2: feat 48..49 | scaling 0..5 | offsets 0..7;  q3: offsets 8..29
+__device__ __forceinline__ ChunkDesc chunk_desc_q(int c, int q)
 {
     ChunkDesc d;
-    if (half == 0) {
-        d.j0 = 8 * c; d.cnt = 8 * c + 8 <= 43 ? 8 : 43 - 8 * c; d.mu_col = 8 * c; d.sg_col = kCF + 8 * c;
-        d.grp = 0; d.dim = kCF; d.k0 = 8 * c;
-    } else if (c == 0) {
-        d.j0 = 43; d.cnt = 7; d.mu_col = 43; d.sg_col = kCF + 43; d.grp = 0; d.dim = kCF; d.k0 = 43;
-    } else if (c == 1) {
-        d.j0 = kCF; d.cnt = 6; d.mu_col = 100; d.sg_col = 106; d.grp = 1; d.dim = kCS; d.k0 = 0;
+    if (q < 2) {
+        const int k0 = 24 * q + 8 * c;
+        d.j0 = k0; d.cnt = 8; d.mu_col = k0; d.sg_col = kCF + k0; d.grp = 0; d.dim = kCF; d.k0 = k0;
+    } else if (q == 2) {
+        if (c == 0) {
+            d.j0 = 48; d.cnt = 2; d.mu_col = 48; d.sg_col = kCF + 48; d.grp = 0; d.dim = kCF; d.k0 = 48;
+        } else if (c == 1) {
+            d.j0 = kCF; d.cnt = 6; d.mu_col = 100; d.sg_col = 106; d.grp = 1; d.dim = kCS; d.k0 = 0;
+        } else {
+            d.j0 = kCF + kCS; d.cnt = 8; d.mu_col = 112; d.sg_col = 142; d.grp = 2; d.dim = kCO; d.k0 = 0;
+        }
     } else {
-        const int cc = c - 2;
-        d.j0 = kCF + kCS + 8 * cc; d.cnt = 8 * cc + 8 <= 30 ? 8 : 30 - 8 * cc; d.mu_col = 112 + 8 * cc;
-        d.sg_col = 142 + 8 * cc; d.grp = 2; d.dim = kCO; d.k0 = 8 * cc;
+        const int k0 = 8 + 8 * c;
+        d.j0 = kCF + kCS + k0; d.cnt = k0 + 8 <= 30 ? 8 : 30 - k0; d.mu_col = 112 + k0; d.sg_col = 142 + k0;
+        d.grp = 2; d.dim = kCO; d.k0 = k0;
     }
     return d;
 }
@@ -148,13 +154,14 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SM &S = *reinterpret_cast<SM *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // Two warp groups work on DIFFERENT tiles (as in neural_gaussians_umma.cu): FRONT (warps 0-7) gathers and stages
-    // the context rows of tile t+1, runs layer 1 and the ReLU epilogue and issues layer 2 as soon as BACK has released
-    // the layer-2 accumulator of tile t; BACK (warps 8-15) runs the likelihood epilogue of tile t.  TMEM columns
-    // [0,256) belong to FRONT (free once the layer-2 MMAs have read the hidden activations), [256,432) change hands.
-    const bool front = tid < kGroup;
-    const int gwarp = (tid & (kGroup - 1)) >> 5, gtid = tid & (kGroup - 1);
-    const int half = gwarp >> 2;
+    // Two warp groups work on DIFFERENT tiles (as in neural_gaussians_umma.cu): FRONT (warps 0-7, two threads per row)
+    // gathers and stages the context rows of tile t+1, runs layer 1 and the ReLU epilogue and issues layer 2 as soon as
+    // BACK has released the layer-2 accumulator of tile t; BACK (warps 8-23, FOUR threads per row: the likelihood
+    // epilogue is the long pole) quantises and scores tile t.  TMEM columns [0,256) belong to FRONT (free once the
+    // layer-2 MMAs have read the hidden activations), [256,432) change hands through an mbarrier.
+    const bool front = tid < kFront;
+    const int gtid = front ? tid : tid - kFront, gwarp = gtid >> 5;
+    const int half = gwarp >> 2;      // FRONT: half of the row's inputs / hidden units; BACK: quarter of its coded values
     const int row = 32 * (warp & 3) + lane;
     const int num_tiles = (A.n_rows + kRows - 1) / kRows;
     const int stride = (int)gridDim.x;
@@ -186,10 +193,12 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
     if (front) {
         // =============================== FRONT: gather + stage, layer 1, ReLU epilogue, MMA issue ===============
         int tile = blockIdx.x;
-        RowInputs<K1> cur;
-        load_row<K1>(cur, A, tile * kRows + row, half);
         for (uint32_t it = 0; tile < num_tiles; ++it, tile += stride) {
             const uint32_t parity = it & 1u;
+            // the gathered context rows of this tile travel while FRONT waits for its TMEM columns (FRONT has slack:
+            // no register double buffer, which keeps the 768-thread CTA inside 85 registers per thread)
+            RowInputs<K1> cur;
+            load_row<K1>(cur, A, tile * kRows + row, half);
             if (it > 0) {   // the layer-2 MMAs of the previous tile have read the hidden activations: columns [0,256) are free
                 if (!umma::mbar_wait(&S.bar[1], parity ^ 1u)) S.timeout = 1;
                 umma::fence_after_thread_sync();
@@ -211,16 +220,13 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             }
             umma::tmem_wait_st();
             umma::fence_before_thread_sync();
-            group_sync(1);
+            group_sync<kFront>(1);
             if (gtid == 0) {
                 umma::fence_after_thread_sync();
                 umma::gemm_3xtf32(tbase + kColD1, tbase + kColXHi, tbase + kColXLo, S.w + LY::kOffW1Hi, S.w + LY::kOffW1Lo,
                                   kN1, LY::kK1p, true);
                 umma::umma_commit(&S.bar[0]);
             }
-            // while the tensor core works: the next tile's gathered context rows travel from HBM
-            RowInputs<K1> nxt;
-            load_row<K1>(nxt, A, (tile + stride) * kRows + row, half);
             if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
             umma::fence_after_thread_sync();
             // ---- epilogue 1: hidden = relu(D1 + b1) -> hi in place, lo to region 0 (cols 56*half .. +56) ----
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             }
             umma::tmem_wait_st();
             umma::fence_before_thread_sync();
-            group_sync(1);
+            group_sync<kFront>(1);
             if (gtid == 0) {
                 umma::fence_after_thread_sync();
                 if (it > 0) {   // BACK has finished reading the layer-2 accumulator of the previous tile
@@ -251,7 +257,6 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                                   kN2, kK2, true);
                 umma::umma_commit(&S.bar[1]);
             }
-            cur = nxt;
         }
     } else {
         // =============================== BACK: steps, quantise, scatter, likelihood ===============================
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             const bool chosen = !pred && o >= 0 && (A.choose ? A.choose[o] != 0 : true);
             // offset masks of the row as bits (values are exactly 0 / 1: utils/entropy_models / gaussian_model.py:1670)
             uint32_t mkbits = 0x3ffu;
-            if (o >= 0 && half == 1 && chosen) {
+            if (o >= 0 && half >= 2 && chosen) {
                 mkbits = 0;
 #pragma unroll
                 for (int k = 0; k < 10; ++k) mkbits |= __ldg(A.mask + o * 10 + k) != 0.f ? (1u << k) : 0u;
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             // was the top stall reason, profiles/r01_ctx2_*).  The attributes of group c+1 are fetched while group c is
             // evaluated; those of group 0 while the layer-2 MMAs run.
             auto fetch_x = [&](int c, float (&x8)[8]) {
-                const ChunkDesc cd = chunk_desc(c, half);
+                const ChunkDesc cd = chunk_desc_q(c, half);
                 const float *src = (cd.grp == 0 ? A.feat : (cd.grp == 1 ? A.scaling : A.offsets)) + (size_t)(o < 0 ? 0 : o) * cd.dim + cd.k0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x8[j] = (!pred && o >= 0 && j < cd.cnt) ? __ldg(src + j) : 0.f;
@@ -307,15 +312,15 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             }
             const float *nz = A.noise ? A.noise + (size_t)grow * kCE : nullptr;
 #pragma unroll 1
-            for (int c = 0; c < 6; ++c) {
-                const ChunkDesc cd = chunk_desc(c, half);
+            for (int c = 0; c < 3; ++c) {
+                const ChunkDesc cd = chunk_desc_q(c, half);
                 uint32_t vm[8], vs[8];
                 float xc[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) xc[j] = xn[j];
                 umma::tmem_ld8(tl + kColD2 + cd.mu_col, vm);
                 umma::tmem_ld8(tl + kColD2 + cd.sg_col, vs);
-                if (c + 1 < 6) fetch_x(c + 1, xn);
+                if (c + 1 < 3) fetch_x(c + 1, xn);
                 umma::tmem_wait_ld();
                 if (o < 0) continue;
                 const float Q = cd.grp == 0 ? Qf : (cd.grp == 1 ? Qs : Qo);
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             tot_f += (double)sum_f; tot_s += (double)sum_s; tot_o += (double)sum_o;
             // all TMEM reads of this tile are complete: FRONT may issue the next tile's layer-2 MMAs
             umma::fence_before_thread_sync();
-            group_sync(2);
+            group_sync<kBack>(2);
             if (gtid == 0) mbar_arrive(&S.bar[2]);
         }
     }
