@@ -123,6 +123,32 @@ __device__ __forceinline__ uint64_t lookback_exclusive(unsigned long long *state
     return excl;
 }
 
+// The walk alone, for kernels that publish the aggregate of a tile EARLY (kLbAggregate | total, or kLbInclusive | total
+// for tile 0, written by whoever knows the total first) and resolve the prefix LATER, when it is actually needed:
+// by then the predecessors have long published, so nobody waits on another CTA's progress.
+__device__ __forceinline__ uint64_t lookback_walk(unsigned long long *state, int tile, uint64_t total)
+{
+    volatile unsigned long long *st = state;
+    const int lane = threadIdx.x & 31;
+    if (tile == 0) return 0;
+    uint64_t excl = 0;
+    for (int base = tile - 1;; base -= 32) {
+        const int t = base - lane;
+        uint64_t s = t >= 0 ? st[t] : kLbInclusive;  // a virtual inclusive zero precedes tile 0
+        while (__any_sync(0xffffffffu, (s >> 62) == 0))
+            if ((s >> 62) == 0) s = st[t];
+        const uint32_t incl = __ballot_sync(0xffffffffu, (s >> 62) == 2ull);
+        const int first = incl ? __ffs(incl) - 1 : 32;
+        uint64_t v = lane <= first ? (s & kLbMask) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (incl) break;
+    }
+    if (lane == 0) st[tile] = kLbInclusive | (excl + total);
+    return excl;
+}
+
 // ---- sort / scan primitives (radix_sort.cu) -------------------------------------------
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;

@@ -265,6 +265,19 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                 reinterpret_cast<float4 *>(o_rot)[base + i] = S.o_rot[i];
             }
         };
+        // exclusive prefix of a tile whose count BACK has published: one FRONT warp walks the chain (the predecessors
+        // published long ago), everybody else picks the result up after the group barrier
+        auto resolve_base = [&](int t, uint32_t par) {
+            if (gwarp == 0) {
+                const uint32_t total = S.tile_total[par];
+                const uint64_t excl = lookback_walk(scan_state, t, total);
+                if (lane == 0) {
+                    S.tile_base[par] = (uint32_t)excl;
+                    if (t == num_tiles - 1) *count_out = (int32_t)(excl + total);
+                }
+            }
+            group_sync(1);
+        };
         uint32_t last_it = 0;
         bool any = false;
         for (uint32_t it = 0; tile < num_tiles; ++it, tile += stride) {
@@ -344,6 +357,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                 umma::umma_commit(&S.bar[BAR_L2ALL]);
             }
             if (it > 0) {   // copy the previous tile out while the tensor core and BACK work on
+                resolve_base(tile - stride, (it - 1) & 1u);
                 copy_out((it - 1) & 1u);
                 group_sync(1);
                 if (gtid == 0) mbar_arrive(&S.bar[BAR_STAGEFREE]);
@@ -353,6 +367,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
         }
         if (any) {   // the last tile of this CTA
             if (!umma::mbar_wait(&S.bar[BAR_ACCFREE], last_it & 1u)) S.timeout = 1;
+            resolve_base(tile - stride, last_it & 1u);
             copy_out(last_it & 1u);
         }
     } else {
@@ -415,15 +430,12 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                 S.excl[gtid] = before + incl - v;
             }
             group_sync(2);  // tile-local ranks complete
-            if (gwarp == 0) {
-                // decoupled look-back across tiles.  Only one warp waits here: the others already post-process
-                // their offsets (they need tile_base only for the final copy).
-                const uint64_t excl = lookback_exclusive(scan_state, tile, total);
-                if (lane == 0) {
-                    S.tile_base[parity] = (uint32_t)excl;
-                    S.tile_total[parity] = total;
-                    if (tile == num_tiles - 1) *count_out = (int32_t)(excl + total);
-                }
+            if (gtid == 0) {
+                // publish this tile's count right away; the prefix is resolved later by FRONT, when the copy-out
+                // needs it -- BACK never waits for another CTA
+                S.tile_total[parity] = total;
+                volatile unsigned long long *st = scan_state;
+                st[tile] = (tile == 0 ? kLbInclusive : kLbAggregate) | (unsigned long long)total;
             }
             uint32_t pos = S.excl[row * 2 + half];
 
