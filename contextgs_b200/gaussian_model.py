@@ -271,6 +271,16 @@ class GaussianModel(nn.Module):
                                          _lib.ptr(self.offset_denom), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                    "cgs_training_statis")
 
+    def save_ply(self, path):
+        """scene/gaussian_model.py:578-597 (numpy writer, same 119-column vertex schema)."""
+        from .ply_io import save_ply
+        save_ply(self, path)
+
+    def load_ply_sparse_gaussian(self, path):
+        """scene/gaussian_model.py:599-656."""
+        from .ply_io import load_ply_sparse_gaussian
+        load_ply_sparse_gaussian(self, path)
+
     def conduct_encoding(self, pre_path_name):
         """scene/gaussian_model.py:1005-1300 on the GPU codec (contextgs_b200/codec.py); returns the size summary."""
         from .codec import conduct_encoding
