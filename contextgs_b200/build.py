@@ -41,6 +41,7 @@ SOURCES = {
     "level_divide.cu": ["-fmad=false"],
     "entropy_codec.cu": ["-fmad=false"],
     "loss.cu": [],
+    "anchor_growing.cu": ["-fmad=false"],
 }
 
 

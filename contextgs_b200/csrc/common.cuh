@@ -26,7 +26,7 @@ int check_launch(const char *what);
 enum Stage {
     ST_FILTER = 0, ST_COMPACT, ST_G1_FWD, ST_G1_BWD, ST_PREPROCESS, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT,
     ST_RANGES, ST_RENDER_FWD, ST_RENDER_BWD, ST_PRE_BWD, ST_EB, ST_CTX_LEVEL, ST_CTX_LEVEL_BWD, ST_BITS, ST_ELEMWISE,
-    ST_LEVEL_DIVIDE, ST_CODEC, ST_LOSS, ST_COUNT
+    ST_LEVEL_DIVIDE, ST_CODEC, ST_LOSS, ST_DENSIFY, ST_COUNT
 };
 struct StageScope {
     int stage;

@@ -35,7 +35,7 @@ static const char *const kStageNames[ST_COUNT] = {
     "visible_filter", "compact_indices", "neural_gaussians_fwd", "neural_gaussians_bwd", "preprocess", "depth_sort",
     "scan_emit_pairs", "bin_expand", "pair_sort", "tile_ranges", "render_fwd", "render_bwd", "preprocess_bwd",
     "entropy_bottleneck", "context_level_fwd", "context_level_bwd", "gaussian_bits", "elementwise", "level_divide",
-    "entropy_codec", "l1_ssim_loss"};
+    "entropy_codec", "l1_ssim_loss", "anchor_growing"};
 
 struct StageTimer {
     std::mutex mu;

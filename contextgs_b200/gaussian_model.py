@@ -3,9 +3,9 @@
 MLPs, the three context ("grid") MLPs and the hyper-prior entropy bottleneck, with the same
 attribute names the reference's glue reads (gaussian_renderer/__init__.py:31-142).
 
-Optimizer set-up, densification, ply / checkpoint / bitstream IO are OUT OF SCOPE (SURVEY.md 2.1
-row 2d) and stay with the reference; this class only has to hold `nn.Parameter`s of the same names
-and shapes so that those routines keep working against it.
+The rows of SURVEY.md 8f are mixed in from their own modules: optimiser set-up, anchor growing and pruning
+(densify.py), the bitstream codec (codec.py), point_cloud.ply IO (ply_io.py), densification statistics (below).
+MLP checkpoint files stay torch.save / torch.load of the state dict.
 """
 import math
 
@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .densify import DensifyMixin
 from .encodings import Quantize_anchor
 
 
@@ -94,7 +95,7 @@ def _mlp(i, h, o, act=None):
     return nn.Sequential(*layers)
 
 
-class GaussianModel(nn.Module):
+class GaussianModel(DensifyMixin, nn.Module):
     def __init__(self, feat_dim=50, n_offsets=10, voxel_size=0.001, level_num=3, hyper_divisor=4, target_ratio=0.2,
                  decoded_version=False, device="cuda"):
         super().__init__()

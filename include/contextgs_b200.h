@@ -465,6 +465,27 @@ CGS_API int cgs_training_statis(int N, int K, const uint8_t *anchor_visible, con
                                 int P, float *opacity_accum, float *anchor_demon, float *offset_gradient_accum,
                                 float *offset_denom, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------ anchor growing
+ * One depth of `GaussianModel.anchor_growing` (scene/gaussian_model.py:778-816; called from adjust_anchor :856-863 every
+ * update_interval iterations, train.py:246-247), replacing torch.unique(dim=0), the chunked O(|unique| x N)
+ * occupancy comparison (:790-802) and torch_scatter.scatter_max (:812-816):
+ *   anchor_q[N,3] = get_anchor, offset[N,K,3], scaling = get_scaling (row stride scaling_stride, columns 0..2 used),
+ *   feat[N,feat_dim], hyper[N,hyper_dim], candidate[N*K] uint8 (8-byte aligned): the slots that pass the gradient
+ *   threshold, the offset mask and the random thinning of :766-771 (computed by the caller, torch's own generator);
+ *   cell = round((anchor_q + offset * scaling) / cur_size).int(); the sorted unique cells that no existing anchor's
+ *   cell round(anchor_q / cur_size) occupies become new anchors, in sorted order:
+ *   new_anchor[n_new,3] = cell * cur_size, new_feat / new_hyper = channel-wise maximum over the cell's candidates of
+ *   the SOURCE anchor's rows.  cand_cap >= number of set candidate flags, new_cap >= n_new (<= cand_cap).
+ *   status_dev[5]: [0] n_new, [1] 1 if a cell coordinate left +-2^20, [2] candidates, [3] unique cells,
+ *                  [4] bit 0: n_new > new_cap, bit 1: more candidates than cand_cap (result truncated; an error).
+ * No host synchronisation, no allocation. */
+CGS_API size_t cgs_anchor_growing_workspace_bytes(int n_anchors, int n_offsets, int cand_cap);
+CGS_API int cgs_anchor_growing(const float *anchor_q, const float *offset, const float *scaling, int scaling_stride,
+                               const float *feat, int feat_dim, const float *hyper, int hyper_dim,
+                               const uint8_t *candidate, int n_anchors, int n_offsets, float cur_size, int cand_cap,
+                               float *new_anchor, float *new_feat, float *new_hyper, int new_cap, int32_t *status_dev,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

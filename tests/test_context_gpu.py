@@ -197,6 +197,33 @@ def test_full_size_properties():
     assert float((again - fq).abs().max()) <= 1e-3
 
 
+def test_many_tiles_per_cta_umma_matches_simt(ctx_impl, monkeypatch):
+    """400 k anchors: each persistent CTA of the warp-specialised tcgen05 context kernel loops over many 128-row
+    tiles per level (barrier parities and TMEM hand-over wrap); the fp32-FMA kernel is independent code."""
+    if ctx_impl == "simt":
+        pytest.skip("compares the two implementations once")
+    N = 400_000
+    scene = synthetic.make_scene("bicycle", N, seed=2)
+    pc = er.make_model(scene)
+    model = cuda_model(scene, pc).eval()
+    a, mk = model.get_anchor, model.get_mask_anchor
+    res = {}
+    for impl in ("umma", "simt"):
+        monkeypatch.setenv("CGS_CTX_IMPL", impl)
+        with torch.no_grad():
+            res[impl] = multi_scale_generating(model, a, model._hyper_latent, model._anchor_feat, model._offset,
+                                               model.get_scaling, model.get_mask, mk, predict_bpp=True,
+                                               return_sum_bits=True, return_details=True)
+    (su, du), (ss, ds) = res["umma"], res["simt"]
+    for i in range(6):
+        assert abs(float(su[i]) - float(ss[i])) <= 1e-4 * max(abs(float(ss[i])), 1.0), i
+    for k, q0 in (("feat_q", 1.0), ("scaling_q", 1e-3), ("offsets_q", 0.2)):
+        x, y = du[k], ds[k]
+        mism = float(((x - y).abs() > 1e-3 * q0 + 1e-6 * y.abs()).float().mean())
+        assert mism < 2e-4, (k, mism)
+    assert rel_l2(du["bits"].cpu().numpy(), ds["bits"].cpu().numpy()) < 1e-3
+
+
 def test_sharded_scoring_adds_up_fake_world():
     """anchors sharded by dependency root; each shard runs its three levels without any
     exchange.  One process plays all ranks in turn ("fake world"); the sums must add up to the
