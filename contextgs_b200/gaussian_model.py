@@ -88,6 +88,17 @@ class EntropyBottleneck(nn.Module):
         return out, lik
 
 
+def _compressai_keys(sd):
+    """State-dict keys of CompressAI's EntropyBottleneck -> ours (same shapes): `_matrix3` -> `matrices.3`, ..."""
+    out = {}
+    for k, v in sd.items():
+        for old, new in (("_matrix", "matrices."), ("_bias", "biases."), ("_factor", "factors.")):
+            if k.startswith(old) and k[len(old):].isdigit():
+                k = new + k[len(old):]
+        out[k] = v
+    return out
+
+
 def _mlp(i, h, o, act=None):
     layers = [nn.Linear(i, h), nn.ReLU(True), nn.Linear(h, o)]
     if act is not None:
@@ -292,6 +303,57 @@ class GaussianModel(DensifyMixin, nn.Module):
         from .codec import conduct_decoding
         conduct_decoding(self, pre_path_name)
         return ""
+
+    # ---- checkpoints (scene/gaussian_model.py:221-286 capture / restore, :912-951 MLP checkpoint) ------------------
+    def capture(self):
+        """The same 19-tuple as scene/gaussian_model.py:221-249, so `torch.save((gaussians.capture(), iteration), ...)`
+        (train.py:278) writes the reference's checkpoint layout."""
+        return (self._anchor, self._anchor_feat, self._hyper_latent, self._offset, self._mask, self._scaling, self._rotation,
+                self._opacity, getattr(self, "max_radii2D", None), self.optimizer.state_dict(), self.spatial_lr_scale,
+                self.mlp_opacity.state_dict(), self.mlp_cov.state_dict(), self.mlp_color.state_dict(),
+                self.latent_codec.state_dict(), self.mlp_grid.state_dict(), self.x_bound_min, self.x_bound_max,
+                self.level_scale)
+
+    def restore(self, model_args, training_args):
+        """scene/gaussian_model.py:251-285."""
+        (anchor, feat, hyper, offset, mask, scaling, rotation, opacity, self.max_radii2D, opt_dict, self.spatial_lr_scale,
+         sd_opacity, sd_cov, sd_color, sd_codec, sd_grid, self.x_bound_min, self.x_bound_max, self.level_scale) = model_args
+        dev = self.mlp_opacity[0].weight.device
+        P = lambda t: t if isinstance(t, nn.Parameter) and t.device == dev else nn.Parameter(
+            t.detach().to(dev).float().contiguous(), requires_grad=bool(t.requires_grad))
+        self._anchor, self._anchor_feat, self._hyper_latent, self._offset = P(anchor), P(feat), P(hyper), P(offset)
+        self._mask, self._scaling, self._rotation, self._opacity = P(mask), P(scaling), P(rotation), P(opacity)
+        self.x_bound_min, self.x_bound_max = self.x_bound_min.to(dev), self.x_bound_max.to(dev)
+        self.training_setup(training_args)
+        self.optimizer.load_state_dict(opt_dict)
+        self.mlp_opacity.load_state_dict(sd_opacity)
+        self.mlp_cov.load_state_dict(sd_cov)
+        self.mlp_color.load_state_dict(sd_color)
+        self.latent_codec.load_state_dict(_compressai_keys(sd_codec), strict=False)
+        self.mlp_grid.load_state_dict(sd_grid)
+
+    def save_mlp_checkpoints(self, path):
+        """scene/gaussian_model.py:912-936: same file keys."""
+        import os
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        torch.save({"opacity_mlp": self.mlp_opacity.state_dict(), "cov_mlp": self.mlp_cov.state_dict(),
+                    "color_mlp": self.mlp_color.state_dict(), "latent_codec": self.latent_codec.state_dict(),
+                    "grid_mlp": self.mlp_grid.state_dict(), "bound": [self.x_bound_min, self.x_bound_max],
+                    "level_scale": self.level_scale}, path)
+
+    def load_mlp_checkpoints(self, path):
+        """scene/gaussian_model.py:939-951.  Accepts the reference's files: CompressAI's buffers (`_offset`,
+        `_quantized_cdf`, `_cdf_length`, `target`) are ignored (strict=False there too) and both of CompressAI's
+        parameter namings (`_matrix0` ... of 1.1.x, `matrices.0` ... of >= 1.2) are understood."""
+        dev = self.mlp_opacity[0].weight.device
+        ck = torch.load(path, map_location=dev, weights_only=False)
+        self.mlp_opacity.load_state_dict(ck["opacity_mlp"])
+        self.mlp_cov.load_state_dict(ck["cov_mlp"])
+        self.mlp_color.load_state_dict(ck["color_mlp"])
+        self.latent_codec.load_state_dict(_compressai_keys(ck["latent_codec"]), strict=False)
+        self.mlp_grid.load_state_dict(ck["grid_mlp"])
+        self.x_bound_min, self.x_bound_max = (t.to(dev) for t in ck["bound"])
+        self.level_scale = ck["level_scale"]
 
     def eval(self):
         for m in (self.mlp_opacity, self.mlp_cov, self.mlp_color, self.latent_codec, self.mlp_grid):
