@@ -107,3 +107,21 @@ class GradientBucket:
             if average:
                 self.flat.div_(world)
         return self.flat
+
+
+def adjust_anchor_data_parallel(pc, group=None, **kw):
+    """`adjust_anchor` for data-parallel training: every rank has accumulated `training_statis` over
+    its own cameras, so the four accumulators are SUM all-reduced first; the random thinning of anchor_growing
+    (scene/gaussian_model.py:769) is drawn on rank 0 and broadcast.  All ranks then grow and prune identically
+    (the device path is deterministic: sorted cells, maxima), so parameters and Adam state stay replicated
+    without any further exchange."""
+    import torch.distributed as dist
+    dev = pc._anchor.device
+    n_slots = pc._anchor.shape[0] * pc.n_offsets
+    rand = [torch.rand(n_slots, device=dev) for _ in range(pc.update_depth)]
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for name in ("opacity_accum", "anchor_demon", "offset_gradient_accum", "offset_denom"):
+            dist.all_reduce(getattr(pc, name), op=dist.ReduceOp.SUM, group=group)
+        for r in rand:
+            dist.broadcast(r, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    pc.adjust_anchor(rand=rand, **kw)

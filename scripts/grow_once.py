@@ -20,12 +20,15 @@ K = pc.n_offsets
 cand = (torch.rand(N * K, generator=torch.Generator().manual_seed(1)) < FRAC).cuda()
 
 
-def torch_expression(cur_size):
+def torch_expression(cur_size, true_division=False):
+    """true_division: divide by a device tensor (IEEE division, what torch's CPU kernel and this library do) instead of
+    by a Python scalar (torch's CUDA kernel multiplies by the reciprocal: cells differ at a handful of rounding ties)."""
     with torch.no_grad():
         anchor = pc.get_anchor
         all_xyz = anchor.unsqueeze(1) + pc._offset * pc.get_scaling[:, :3].unsqueeze(1)
-        grid = torch.round(anchor / cur_size).int()
-        sel = torch.round(all_xyz.view(-1, 3)[cand] / cur_size).int()
+        div = torch.full((), cur_size, device="cuda") if true_division else cur_size
+        grid = torch.round(anchor / div).int()
+        sel = torch.round(all_xyz.view(-1, 3)[cand] / div).int()
         uniq, inv = torch.unique(sel, return_inverse=True, dim=0)
         dup = torch.zeros(uniq.shape[0], dtype=torch.bool, device="cuda")
         for i in range(0, grid.shape[0], 4096):
@@ -56,6 +59,8 @@ for cell in (16 * pc.voxel_size, 4 * pc.voxel_size, pc.voxel_size):
     if os.environ.get("GROW_TORCH", "1") == "1" and cell == 16 * pc.voxel_size:
         ms_t, (ta, tf) = timed(lambda: torch_expression(cell), 1)
         entry["torch_expression_ms"] = round(ms_t, 1)
-        entry["identical"] = bool(torch.equal(ta, na) and torch.equal(tf, nf))
+        entry["torch_expression_new_anchors"] = int(ta.shape[0])
+        tb, tg = torch_expression(cell, true_division=True)
+        entry["identical_to_true_division_expression"] = bool(torch.equal(tb, na) and torch.equal(tg, nf))
     res[f"depth_cell_{cell:g}"] = entry
 print(json.dumps(res))

@@ -99,3 +99,41 @@ def test_gloo_world2_bit_sums_and_gradient_bucket():
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def _densify_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from contextgs_b200.distributed import adjust_anchor_data_parallel
+        from tests.helpers import load_npz
+        from tests.test_growing_cpu import model_from_golden, oracle_grow_cells
+        g = load_npz("growing.npz")
+        m = model_from_golden(g, 1, "cpu")
+        GaussianModel.grow_cells = oracle_grow_cells          # host logic only: the device call is the oracle's
+        # each rank saw different cameras: split the fixture's accumulators unevenly between the ranks
+        share = 0.25 if rank == 0 else 0.75
+        for k in ("opacity_accum", "anchor_demon", "offset_gradient_accum", "offset_denom"):
+            setattr(m, k, getattr(m, k) * share)
+        torch.manual_seed(rank)                               # different local generators: the draw must come from rank 0
+        adjust_anchor_data_parallel(m, check_interval=100, success_threshold=0.8, grad_threshold=0.0002, min_opacity=0.005)
+        flat = torch.cat([getattr(m, "_" + k).detach().reshape(-1) for k in ("anchor", "anchor_feat", "scaling", "offset")])
+        sizes = torch.tensor([m._anchor.shape[0], m.offset_denom.shape[0]])
+        gathered = [torch.zeros_like(sizes) for _ in range(world)]
+        dist.all_gather(gathered, sizes)
+        ok = all(torch.equal(gathered[0], t) for t in gathered)
+        if ok:
+            both = [torch.zeros_like(flat) for _ in range(world)]
+            dist.all_gather(both, flat)
+            ok = all(torch.equal(both[0], t) for t in both)
+        ok = ok and m._anchor.shape[0] != g["c1_before_anchor"].shape[0]
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_adjust_anchor_stays_replicated():
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_densify_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)

@@ -50,18 +50,20 @@ def check_against_golden(m, g, case):
     assert m.max_radii2D.shape[0] == m._anchor.shape[0]
 
 
+def oracle_grow_cells(self, candidate_mask, cur_size, n_candidates=None):
+    """Stand-in for GaussianModel.grow_cells (the device call) on CPU-only hosts: the oracle's restatement."""
+    n = lambda t: t.detach().numpy()
+    anchor_q = er.quantize_anchor(self._anchor.detach(), self.x_bound_min, self.x_bound_max)[0]
+    out = gr.grow_cells(n(anchor_q), n(self._offset), n(self.get_scaling), n(self._anchor_feat), n(self._hyper_latent),
+                        candidate_mask.numpy(), cur_size)
+    return tuple(torch.from_numpy(o) for o in out)
+
+
 def test_host_side_of_adjust_anchor_matches_reference_golden(monkeypatch):
     g = load_npz("growing.npz")
     for case in (0, 1):
         m = model_from_golden(g, case, "cpu")
-
-        def grow_cells(self, candidate_mask, cur_size, n_candidates=None):
-            n = lambda t: t.detach().numpy()
-            out = gr.grow_cells(n(er.quantize_anchor(self._anchor.detach(), self.x_bound_min, self.x_bound_max)[0]), n(self._offset), n(self.get_scaling), n(self._anchor_feat),
-                                n(self._hyper_latent), candidate_mask.numpy(), cur_size)
-            return tuple(torch.from_numpy(o) for o in out)
-
-        monkeypatch.setattr(GaussianModel, "grow_cells", grow_cells)
+        monkeypatch.setattr(GaussianModel, "grow_cells", oracle_grow_cells)
         rand = [torch.from_numpy(g[f"c{case}_rand{i}"]) for i in range(int(g[f"c{case}_n_rand"]))]
         m.adjust_anchor(check_interval=100, success_threshold=0.8, grad_threshold=0.0002, min_opacity=0.005, rand=rand)
         check_against_golden(m, g, case)
