@@ -101,6 +101,8 @@ SIGNATURES = {
     "cgs_anchor_growing_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "cgs_anchor_growing": (c_int, [_PTR, _PTR, _PTR, c_int, _PTR, c_int, _PTR, c_int, _PTR, c_int, c_int, ctypes.c_float,
                                    c_int, _PTR, _PTR, _PTR, c_int, _PTR, _PTR, c_size_t, _PTR]),
+    "cgs_knn3_workspace_bytes": (c_size_t, [c_int]),
+    "cgs_knn3_mean_dist2": (c_int, [_PTR, c_int, _PTR, ctypes.c_float, _PTR, _PTR, _PTR, c_size_t, _PTR]),
     "cgs_l1_ssim_forward": (c_int, [_PTR, _PTR, c_int, c_int, _PTR, _PTR, _PTR, _PTR, _PTR]),
     "cgs_l1_ssim_backward": (c_int, [_PTR, _PTR, c_int, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR]),
     "cgs_context_level_backward_packed_floats": (c_int, [c_int]),

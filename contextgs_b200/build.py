@@ -42,6 +42,7 @@ SOURCES = {
     "entropy_codec.cu": ["-fmad=false"],
     "loss.cu": [],
     "anchor_growing.cu": ["-fmad=false"],
+    "knn.cu": ["-fmad=false"],
 }
 
 

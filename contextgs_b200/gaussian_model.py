@@ -304,6 +304,40 @@ class GaussianModel(DensifyMixin, nn.Module):
         conduct_decoding(self, pre_path_name)
         return ""
 
+    # ---- initialisation from an SfM point cloud (scene/gaussian_model.py:377-423) -----------------------------------
+    def voxelize_sample(self, data=None, voxel_size=0.01):
+        """:377-380 (numpy; the shuffle does not change the sorted unique result but keeps the reference's RNG use)."""
+        import numpy as np
+        np.random.shuffle(data)
+        return np.unique(np.round(data / voxel_size), axis=0) * voxel_size
+
+    def create_from_pcd(self, pcd, spatial_lr_scale):
+        """:382-423: anchors = voxelised points; scales from the mean squared distance to the 3 nearest anchors."""
+        import numpy as np
+        from .knn import distCUDA2
+        dev = self.mlp_opacity[0].weight.device
+        self.spatial_lr_scale = spatial_lr_scale
+        points = np.asarray(pcd.points if hasattr(pcd, "points") else pcd)
+        if self.voxel_size <= 0:
+            init_dist = distCUDA2(torch.tensor(points).float().to(dev))
+            self.voxel_size = torch.kthvalue(init_dist, int(init_dist.shape[0] * 0.5))[0].item()
+        points = self.voxelize_sample(points, voxel_size=self.voxel_size)
+        fused = torch.tensor(np.asarray(points)).float().to(dev)
+        n, K = fused.shape[0], self.n_offsets
+        dist2 = torch.clamp_min(distCUDA2(fused), 0.0000001)
+        scales = torch.log(torch.sqrt(dist2))[..., None].repeat(1, 6)
+        rots = torch.zeros((n, 4), device=dev)
+        rots[:, 0] = 1
+        opacities = torch.log(torch.full((n, 1), 0.1, device=dev) / (1 - torch.full((n, 1), 0.1, device=dev)))
+        P = lambda t, g=True: nn.Parameter(t.contiguous().requires_grad_(g))
+        self._anchor, self._offset = P(fused), P(torch.zeros((n, K, 3), device=dev))
+        self._mask = P(torch.ones((n, K, 1), device=dev))
+        self._anchor_feat = P(torch.zeros((n, self.feat_dim), device=dev))
+        self._hyper_latent = P(torch.zeros((n, self.feat_dim // self.hyper_divisor), device=dev))
+        self._scaling, self._rotation, self._opacity = P(scales), P(rots, False), P(opacities, False)
+        self.max_radii2D = torch.zeros((n,), device=dev)
+        self.update_anchor_bound()
+
     # ---- checkpoints (scene/gaussian_model.py:221-286 capture / restore, :912-951 MLP checkpoint) ------------------
     def capture(self):
         """The same 19-tuple as scene/gaussian_model.py:221-249, so `torch.save((gaussians.capture(), iteration), ...)`

@@ -486,6 +486,18 @@ CGS_API int cgs_anchor_growing(const float *anchor_q, const float *offset, const
                                float *new_anchor, float *new_feat, float *new_hyper, int new_cap, int32_t *status_dev,
                                void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------ initial anchor scales (create_from_pcd)
+ * What `simple_knn._C.distCUDA2(points)` returns (third-party, not in the reference tree; call sites
+ * scene/gaussian_model.py:389,407): mean_dist2[i] = mean of the three smallest squared distances from point i to the
+ * OTHER points (FLT_MAX entries when n < 4, as simple-knn).  Exact neighbours through a uniform grid of edge `cell`
+ * anchored at bbox_min_host[3] (host floats; (max - min) / cell must stay below 2^21), shells of cells around each
+ * point, and an all-points scan for isolated points.
+ *   status_dev[2]: [0] points finished by the all-points scan, [1] 1 if there were too many of them
+ *   (> max(4096, n/32)): nothing was written for those, call again with a larger cell. */
+CGS_API size_t cgs_knn3_workspace_bytes(int n);
+CGS_API int cgs_knn3_mean_dist2(const float *points, int n, const float *bbox_min_host, float cell, float *mean_dist2,
+                                int32_t *status_dev, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
