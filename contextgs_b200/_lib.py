@@ -196,3 +196,17 @@ def stage_timing_read():
 def stream_ptr():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def object_cache(obj):
+    """Per-object cache dict for derived tensors (packed weights, ...).  It lives ON the object and dies with it: a
+    module-level dict keyed by id(obj) would hand a later object that reuses the address -- and, through the caching
+    allocator, the same data pointers at the same tensor version -- the previous object's entries."""
+    d = getattr(obj, "_cgs_cache", None)
+    if d is None:
+        d = {}
+        try:
+            object.__setattr__(obj, "_cgs_cache", d)
+        except Exception:
+            pass          # objects without attribute storage simply do not cache
+    return d

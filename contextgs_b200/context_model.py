@@ -16,15 +16,13 @@ from .encodings import get_binary_vxl_size
 
 N_CODED = 86  # 50 feat + 6 scaling + 30 offsets
 
-_grid_pack_cache = {}
-
-
 def pack_grid_weights(pc, level):
     """W1[in][100] | b1[100] | W2[100][176] | b2[176] (k-major) for `pc.get_grid_mlp[level]`."""
     m = pc.get_grid_mlp[level]
     params = (m[0].weight, m[0].bias, m[2].weight, m[2].bias)
     key = tuple((p.data_ptr(), p._version) for p in params)
-    ent = _grid_pack_cache.get((id(pc), level))
+    cache = _lib.object_cache(pc)
+    ent = cache.get(("grid_pack", level))
     if ent is not None and ent[0] == key:
         return ent[1], ent[2]
     with torch.no_grad():
@@ -36,11 +34,8 @@ def pack_grid_weights(pc, level):
         b2[:175] = m[2].bias
         packed = torch.cat([m[0].weight.t().reshape(-1), m[0].bias, W2.reshape(-1), b2]).float().contiguous()
     assert packed.numel() == _lib.lib().cgs_context_level_packed_floats(in_dim)
-    _grid_pack_cache[(id(pc), level)] = (key, packed, in_dim)
+    cache[("grid_pack", level)] = (key, packed, in_dim)
     return packed, in_dim
-
-
-_grid_pack_cache_umma = {}
 
 
 def pack_grid_weights_umma(pc, level):
@@ -50,7 +45,8 @@ def pack_grid_weights_umma(pc, level):
     m = pc.get_grid_mlp[level]
     params = (m[0].weight, m[0].bias, m[2].weight, m[2].bias)
     key = tuple((p.data_ptr(), p._version) for p in params)
-    ent = _grid_pack_cache_umma.get((id(pc), level))
+    cache = _lib.object_cache(pc)
+    ent = cache.get(("grid_pack_umma", level))
     if ent is not None and ent[0] == key:
         return ent[1], ent[2]
     with torch.no_grad():
@@ -64,7 +60,7 @@ def pack_grid_weights_umma(pc, level):
         packed = torch.cat([*umma_b_operand(m[0].weight, 112, k1p), *umma_b_operand(m[2].weight, 176, 104), b1, b2])
         packed = packed.float().contiguous()
     assert packed.numel() == _lib.lib().cgs_context_level_umma_packed_floats(in_dim)
-    _grid_pack_cache_umma[(id(pc), level)] = (key, packed, in_dim)
+    cache[("grid_pack_umma", level)] = (key, packed, in_dim)
     return packed, in_dim
 
 

@@ -9,16 +9,14 @@ from . import _lib
 
 Q_FEAT, Q_SCALING, Q_OFFSETS = 1, 0.001, 0.2  # gaussian_renderer/__init__.py:40-42
 
-_pack_cache = {}
-
-
 def pack_decoder_weights(pc):
     """Packed weight block of the three decoder MLPs (layout: include/contextgs_b200.h), cached per
     parameter version so that inference frames do not repack."""
     mods = (pc.get_opacity_mlp, pc.get_color_mlp, pc.get_cov_mlp)
     params = [p for m in mods for p in (m[0].weight, m[0].bias, m[2].weight, m[2].bias)]
     key = tuple((p.data_ptr(), p._version) for p in params)
-    ent = _pack_cache.get(id(pc))
+    cache = _lib.object_cache(pc)
+    ent = cache.get("decoder_pack")
     if ent is not None and ent[0] == key:
         return ent[1]
     with torch.no_grad():
@@ -38,7 +36,7 @@ def pack_decoder_weights(pc):
             parts += [W2.reshape(-1), b2]
         packed = torch.cat(parts).float().contiguous()
     assert packed.numel() == _lib.lib().cgs_neural_gaussians_packed_floats()
-    _pack_cache[id(pc)] = (key, packed)
+    cache["decoder_pack"] = (key, packed)
     return packed
 
 
@@ -62,9 +60,6 @@ def umma_b_operand(W, n_pad, k_pad):
     return lay(hi), lay(lo)
 
 
-_pack_cache_umma = {}
-
-
 def pack_decoder_weights_umma(pc):
     """Packed block of the tcgen05 G1 kernel (layout: csrc/neural_gaussians_umma.cu `ngu::kOff*`).
     Layer-1 rows: head h (opacity, color, cov) occupies rows 56h .. 56h+49.  Layer-2 rows are placed
@@ -73,7 +68,8 @@ def pack_decoder_weights_umma(pc):
     mods = (pc.get_opacity_mlp, pc.get_color_mlp, pc.get_cov_mlp)
     params = [p for m in mods for p in (m[0].weight, m[0].bias, m[2].weight, m[2].bias)]
     key = tuple((p.data_ptr(), p._version) for p in params)
-    ent = _pack_cache_umma.get(id(pc))
+    cache = _lib.object_cache(pc)
+    ent = cache.get("decoder_pack_umma")
     if ent is not None and ent[0] == key:
         return ent[1]
     with torch.no_grad():
@@ -100,7 +96,7 @@ def pack_decoder_weights_umma(pc):
             biases.append(b2)
         packed = torch.cat(parts + biases).float().contiguous()
     assert packed.numel() == _lib.lib().cgs_neural_gaussians_umma_packed_floats()
-    _pack_cache_umma[id(pc)] = (key, packed)
+    cache["decoder_pack_umma"] = (key, packed)
     return packed
 
 

@@ -43,3 +43,23 @@ def test_missing_library_fails_loudly(monkeypatch):
         assert "no CPU or PyTorch fallback" in str(e)
     else:
         raise AssertionError("expected CgsError")
+
+
+def test_object_cache_lives_on_the_object():
+    """Derived-tensor caches must not outlive their model: a module-level dict keyed by id() handed a NEW model that
+    reused the address (and, via the caching allocator, the data pointers) the previous model's packed weights."""
+    import gc
+    import types
+    from contextgs_b200 import _lib
+    a = types.SimpleNamespace()
+    _lib.object_cache(a)["k"] = 1
+    assert _lib.object_cache(a) == {"k": 1} and a._cgs_cache is _lib.object_cache(a)
+    ident = id(a)
+    del a
+    gc.collect()
+    fresh = [types.SimpleNamespace() for _ in range(64)]         # one of them very likely reuses the address
+    assert all(_lib.object_cache(o) == {} for o in fresh), ident
+    import contextgs_b200.context_model as cm
+    import contextgs_b200.neural_gaussians as ng
+    assert not any(n.endswith("_cache") or n.endswith("_cache_umma") for m in (cm, ng) for n in vars(m)
+                   if isinstance(getattr(m, n), dict))
