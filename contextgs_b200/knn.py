@@ -37,6 +37,8 @@ def distCUDA2(points, cell=None):
         return out
     auto, lo = _grid_cell(pts, n)
     full = float((pts.max(dim=0)[0] - lo).max())
+    if full == 0.0 and n >= 4:          # every point coincides: all neighbour distances are zero
+        return out.zero_()
     h = max(float(cell), full / float(1 << 20) * 1.01) if cell is not None else auto
     lo_host = lo.cpu().float().contiguous()      # host floats: part of the grid definition
     status = torch.empty(2, dtype=torch.int32, device=pts.device)
