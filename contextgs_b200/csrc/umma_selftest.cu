@@ -98,9 +98,100 @@ umma_selftest_kernel(const float *__restrict__ A, const float *__restrict__ W, i
     if (warp == 0) umma::tmem_dealloc(tbase, 512);
 }
 
+// Probe for the weight-gradient GEMMs of the backward kernels: D[M x N] = P^T Q with
+// P[128 rows x M], Q[128 rows x N], i.e. the contraction runs over the tile's ROWS.  Both operands go through
+// shared memory (SS form) in the K-major core-matrix layout with the row index as K: thread `row` writes its own
+// values at ((row / 4) * ld + m) * 4 + row % 4 -- no transposition pass, no MN-major descriptor.  `skew` adds
+// 16-byte units to the leading-dimension byte offset (bank spreading of the 8 row groups).  3xTF32.
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_ss_kernel(const float *__restrict__ P, const float *__restrict__ Q, int M, int N, int skew,
+                        float *__restrict__ D, int32_t *__restrict__ err)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lda = 128 + skew, ldb = N + skew;                  // rows of 16 bytes per K chunk
+    float *a_hi = reinterpret_cast<float *>(smem_raw);
+    float *a_lo = a_hi + (size_t)32 * lda * 4;
+    float *b_hi = a_lo + (size_t)32 * lda * 4;
+    float *b_lo = b_hi + (size_t)32 * ldb * 4;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
+    if (tid == 0) {
+        umma::mbar_init(&s_bar, 1);
+        umma::fence_mbar_init();
+    }
+    const int row = tid;                                          // K index of this thread
+    for (int m = 0; m < 128; ++m) {
+        uint32_t hi = 0, lo = 0;
+        if (m < M) umma::split_tf32(P[(size_t)row * M + m], hi, lo);
+        const int dst = ((row >> 2) * lda + m) * 4 + (row & 3);
+        a_hi[dst] = __uint_as_float(hi);
+        a_lo[dst] = __uint_as_float(lo);
+    }
+    for (int n = 0; n < N; ++n) {
+        uint32_t hi, lo;
+        umma::split_tf32(Q[(size_t)row * N + n], hi, lo);
+        const int dst = ((row >> 2) * ldb + n) * 4 + (row & 3);
+        b_hi[dst] = __uint_as_float(hi);
+        b_lo[dst] = __uint_as_float(lo);
+    }
+    umma::fence_proxy_async_smem();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = s_tmem;
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    if (tid == 0) {
+        const uint32_t idesc = umma::idesc_tf32(128, N);
+        const uint32_t lbo_a = (uint32_t)lda * 16u, lbo_b = (uint32_t)ldb * 16u;
+        for (int s = 0; s < 16; ++s) {                            // K = 128 rows, 8 per instruction
+            const uint64_t ahi = umma::smem_desc_kmajor(umma::smem_u32(a_hi) + (uint32_t)s * 2u * lbo_a, lbo_a, 128u);
+            const uint64_t alo = umma::smem_desc_kmajor(umma::smem_u32(a_lo) + (uint32_t)s * 2u * lbo_a, lbo_a, 128u);
+            const uint64_t bhi = umma::smem_desc_kmajor(umma::smem_u32(b_hi) + (uint32_t)s * 2u * lbo_b, lbo_b, 128u);
+            const uint64_t blo = umma::smem_desc_kmajor(umma::smem_u32(b_lo) + (uint32_t)s * 2u * lbo_b, lbo_b, 128u);
+            umma::mma_tf32_ss(tbase, ahi, blo, idesc, s > 0 ? 1u : 0u);
+            umma::mma_tf32_ss(tbase, alo, bhi, idesc, 1u);
+            umma::mma_tf32_ss(tbase, ahi, bhi, idesc, 1u);
+        }
+        umma::umma_commit(&s_bar);
+    }
+    const bool ok = umma::mbar_wait(&s_bar, 0);
+    umma::fence_after_thread_sync();
+    if (!ok && lane == 0) atomicExch(err, 1);
+    for (int n0 = 0; n0 + 8 <= N; n0 += 8) {                      // lane `tid` of the accumulator = output row m
+        uint32_t v[8];
+        umma::tmem_ld8(lane_base + n0, v);
+        umma::tmem_wait_ld();
+        if (tid < M)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) D[(size_t)tid * N + n0 + j] = __uint_as_float(v[j]);
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tbase, 512);
+}
+
 }  // namespace cgs
 
 using namespace cgs;
+
+extern "C" int cgs_umma_selftest_ss(const float *P, const float *Q, int M, int N, int skew, float *D, int32_t *err,
+                                    void *stream)
+{
+    CGS_CHECK_PTR(P); CGS_CHECK_PTR(Q); CGS_CHECK_PTR(D); CGS_CHECK_PTR(err);
+    if (M < 1 || M > 128 || N < 16 || N > 64 || (N % 16) || skew < 0 || skew > 4) {
+        set_error("%s: need 1 <= M <= 128, 16 <= N <= 64 (N %% 16 == 0), 0 <= skew <= 4", __func__);
+        return -2;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)2 * 32 * (128 + skew) * 16 + (size_t)2 * 32 * (N + skew) * 16;
+    cudaFuncSetAttribute(umma_selftest_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaMemsetAsync(err, 0, sizeof(int32_t), st);
+    StageScope sc(ST_ELEMWISE, st, 1);
+    umma_selftest_ss_kernel<<<1, 128, smem, st>>>(P, Q, M, N, skew, D, err);
+    return check_launch(__func__);
+}
 
 extern "C" int cgs_umma_selftest(const float *A, const float *W, int N, int K, int mode, float *D, int32_t *err,
                                  void *stream)

@@ -85,6 +85,11 @@ CGS_API int cgs_launch_counts(int64_t *launches, int reset);
  * plain TF32 when mode = 0).  *err (device) is set to 1 if the completion barrier timed out. */
 CGS_API int cgs_umma_selftest(const float *A, const float *W, int N, int K, int mode, float *D, int32_t *err,
                               void *stream);
+/* Probe of the SS form (both operands in shared memory) with the ROW index as the contraction: D[M,N] = P^T Q,
+ * P[128,M], Q[128,N], 3xTF32 -- the shape of the backward kernels' weight-gradient GEMMs.
+ * skew: extra 16-byte units in the leading-dimension byte offset.  scripts/umma_ss_probe.py runs it. */
+CGS_API int cgs_umma_selftest_ss(const float *P, const float *Q, int M, int N, int skew, float *D, int32_t *err,
+                                 void *stream);
 
 /* ------------------------------------------------------------------ rasterizer (P1, R0-R7) */
 
