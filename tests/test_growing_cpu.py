@@ -61,7 +61,7 @@ def oracle_grow_cells(self, candidate_mask, cur_size, n_candidates=None):
 
 def test_host_side_of_adjust_anchor_matches_reference_golden(monkeypatch):
     g = load_npz("growing.npz")
-    for case in (0, 1):
+    for case in (0, 1, 2):
         m = model_from_golden(g, case, "cpu")
         monkeypatch.setattr(GaussianModel, "grow_cells", oracle_grow_cells)
         rand = [torch.from_numpy(g[f"c{case}_rand{i}"]) for i in range(int(g[f"c{case}_n_rand"]))]
