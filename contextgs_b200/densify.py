@@ -11,7 +11,6 @@ is ONE library call (csrc/anchor_growing.cu) followed by ONE read of the new-anc
 """
 import math
 
-import numpy as np
 import torch
 import torch.nn as nn
 

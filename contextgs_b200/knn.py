@@ -1,7 +1,6 @@
 """`distCUDA2` of simple_knn (third-party, not in the reference tree; `from simple_knn._C import distCUDA2`,
 scene/gaussian_model.py:22, used at :389 and :407): for every point the mean squared distance to its three nearest
 neighbours.  One library call (csrc/knn.cu: uniform grid + shells, exact neighbours); no CPU path."""
-import math
 
 import torch
 
