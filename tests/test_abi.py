@@ -63,3 +63,22 @@ def test_object_cache_lives_on_the_object():
     import contextgs_b200.neural_gaussians as ng
     assert not any(n.endswith("_cache") or n.endswith("_cache_umma") for m in (cm, ng) for n in vars(m)
                    if isinstance(getattr(m, n), dict))
+
+
+def test_dropin_packages_resolve_the_reference_imports():
+    """gaussian_renderer/__init__.py:20 and scene/gaussian_model.py:22 import these names."""
+    import importlib
+    import sys
+    import contextgs_b200
+    contextgs_b200.install()
+    try:
+        for mod in ("diff_gaussian_rasterization", "simple_knn", "simple_knn._C"):
+            sys.modules.pop(mod, None)
+        r = importlib.import_module("diff_gaussian_rasterization")
+        k = importlib.import_module("simple_knn._C")
+        from contextgs_b200.knn import distCUDA2
+        from contextgs_b200.rasterizer import GaussianRasterizer
+        assert r.GaussianRasterizer is GaussianRasterizer and k.distCUDA2 is distCUDA2
+    finally:
+        for mod in ("diff_gaussian_rasterization", "simple_knn", "simple_knn._C"):
+            sys.modules.pop(mod, None)
