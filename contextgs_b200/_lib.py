@@ -45,6 +45,7 @@ SIGNATURES = {
     "cgs_launch_counts": (c_int, [_PTR, c_int]),
     "cgs_umma_selftest": (c_int, [_PTR, _PTR, c_int, c_int, c_int, _PTR, _PTR, _PTR]),
     "cgs_umma_selftest_ss": (c_int, [_PTR, _PTR, c_int, c_int, c_int, _PTR, _PTR, _PTR]),
+    "cgs_umma_selftest_ss_mn": (c_int, [_PTR, _PTR, c_int, c_int, c_int, _PTR, _PTR, _PTR]),
     "cgs_visible_filter": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR]),
     "cgs_prefilter_workspace_bytes": (c_size_t, [c_int]),
     "cgs_prefilter_anchors": (c_int, [_PTR, c_int, _PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),

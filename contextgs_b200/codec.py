@@ -108,10 +108,22 @@ def _hyper_tables(pc, smin, smax):
     return frequency_tables(lik.t().contiguous() + 1e-12)
 
 
+def _content_key(anchor_q, pc):
+    """Cache key from the CONTENT of the coded anchors and the bounds they are dequantised with: two position-weighted
+    int64 checksums of the 16-bit grid indices + the six bound values, one small read-back.  (Keying on data_ptr /
+    _version of a temporary would let the caching allocator hand the same address to another stream's anchors.)"""
+    q = (anchor_q.to(torch.int64) & 0xffff).reshape(-1)
+    w = torch.arange(1, q.numel() + 1, device=q.device, dtype=torch.int64)
+    sums = torch.stack([q.sum(), (q * (w % 65521 + 1)).sum(), (q * (w % 8191 + 7)).sum()])
+    bounds = torch.cat([pc.x_bound_min.reshape(-1), pc.x_bound_max.reshape(-1)]).float().to(q.device).view(torch.int32)
+    vals = torch.cat([sums, bounds.to(torch.int64)]).tolist()   # exact: integer checksums, bit patterns of the bounds
+    return (tuple(anchor_q.shape),) + tuple(vals)
+
+
 def _plan_for(pc, anchor, key, rank, world):
-    """(full level sizes, plan or shard of it), cached on the model while the coded anchors (`key`) and the level
-    scales are unchanged: the division and especially its dependency-root sharding are index gymnastics with host
-    synchronisations that would otherwise dominate a sharded encode / decode call."""
+    """(full level sizes, plan or shard of it), cached on the model while the coded anchors (`key`: content checksums
+    + bounds, see _content_key) and the level scales are unchanged: the division and especially its dependency-root
+    sharding are index gymnastics with host synchronisations that would otherwise dominate a sharded encode / decode."""
     key = (key, tuple(pc.level_scale), float(pc.voxel_size), rank, world)
     ent = getattr(pc, "_cgs_codec_plan", None)
     if ent is not None and ent[0] == key:
@@ -187,9 +199,7 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1):
     # level division on the DEQUANTISED anchors (what the decoder will see)
     if pc.level_scale is None:
         pc.level_scale = find_divide_scale(pc, anchor, pc.target_ratio, pc.level_num)
-    src = pc._anchor
-    n_levels_full, plan = _plan_for(pc, anchor, ("enc", src.data_ptr(), src._version, tuple(src.shape), pc._mask.data_ptr(), pc._mask._version),
-                                    rank, world)
+    n_levels_full, plan = _plan_for(pc, anchor, _content_key(anchor_q, pc), rank, world)
 
     feat_q, scaling_q, offsets_q = torch.zeros_like(feat), torch.zeros_like(scaling), torch.zeros_like(offsets)
     sums = torch.zeros(16, dtype=torch.float64, device=dev)
@@ -275,7 +285,7 @@ def decode_model(pc, meta, anchor_q, mask_bytes, mask_lens, hyper_bytes, hyper_l
     hyper_q = ((hsym.to(torch.int32) + hmin).float() + median.view(1, -1)).contiguous()
     hyper_ctx = hyper_q * 0 if getattr(pc, "disable_hyper", False) else hyper_q
 
-    sizes, plan = _plan_for(pc, anchor, ("dec", anchor_q.data_ptr(), anchor_q._version, tuple(anchor_q.shape)), rank, world)
+    sizes, plan = _plan_for(pc, anchor, _content_key(anchor_q.to(dev), pc), rank, world)
     if sizes != list(meta["N_levels"]):
         raise _lib.CgsError("decode: the level division of the decoded anchors differs from the encoder's")
     feat_q = torch.zeros((N, 50), dtype=torch.float32, device=dev)
@@ -318,9 +328,13 @@ def conduct_encoding(pc, pre_path_name, chunk_rows=CHUNK_ROWS):
     """scene/gaussian_model.py:1005-1300: writes anchor.npy, masks.b, hyper.b, {feat,scaling,offsets}{level}.b,
     meta.b, mlp.pt under `pre_path_name`; returns the reference's size summary string."""
     os.makedirs(pre_path_name, exist_ok=True)
-    if chunk_rows * max(ATTR_CHUNK_MULT) * 6 * 2 + 16 > 65535 or chunk_rows * TABLE_CHUNK_MULT * 12 * 2 + 16 > 65535:
+    caps = [int(_lib.lib().cgs_codec_gauss_stream_capacity(a, chunk_rows * ATTR_CHUNK_MULT[a])) for a in range(len(ATTRS))]
+    if max(caps) > 65535 or chunk_rows * TABLE_CHUNK_MULT * 12 * 2 + 16 > 65535:
         raise ValueError("chunk_rows too large for the 16-bit chunk lengths of the directory format")
     enc = encode_model(pc, chunk_rows)
+    all_lens = [enc.mask_lens, enc.hyper_lens] + [st.lens for lv in enc.levels for st in lv.streams.values()]
+    if max(int(l.max()) if l.numel() else 0 for l in all_lens) > 65535:
+        raise _lib.CgsError("a chunk is longer than 65535 bytes: it does not fit the 16-bit length of the directory format")
     np.save(os.path.join(pre_path_name, "anchor.npy"), enc.anchor_q.cpu().numpy().view(np.uint16))
     wr = lambda name, t: t.cpu().numpy().tofile(os.path.join(pre_path_name, name))
     wr("masks.b", enc.mask_bytes)
@@ -360,7 +374,21 @@ def conduct_decoding(pc, pre_path_name):
         levels.append(lv)
     out = decode_model(pc, meta, anchor_q, rd("masks.b"), u16(side["mask_lens"]), rd("hyper.b"), u16(side["hyper_lens"]),
                        levels)
-    pc.replace_with_decoded(out["anchor"], out["hyper"], out["feat"], out["offsets"], out["scaling"], out["masks"])
+    if hasattr(pc, "replace_with_decoded"):
+        pc.replace_with_decoded(out["anchor"], out["hyper"], out["feat"], out["offsets"], out["scaling"], out["masks"])
+    else:
+        # bound on the reference's own GaussianModel (INTEGRATION.md hook 4): the parameter replacement of
+        # scene/gaussian_model.py:1503-1533, padded back to the N_full rows the other per-anchor tensors keep
+        P = torch.nn.Parameter
+        n_full, n = int(meta["N_total"]), out["anchor"].shape[0]
+
+        def full(t):
+            buf = torch.zeros((n_full,) + tuple(t.shape[1:]), dtype=torch.float32, device=dev)
+            buf[:n] = t
+            return P(buf)
+        pc._hyper_latent, pc._anchor_feat, pc._offset = full(out["hyper"]), full(out["feat"]), full(out["offsets"])
+        pc.decoded_version = True
+        pc._anchor, pc._scaling, pc._mask = full(out["anchor"]), full(out["scaling"]), full(out["masks"])
     return out
 
 

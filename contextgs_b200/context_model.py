@@ -171,19 +171,40 @@ def build_level_plan(pc, anchor, mask_anchor_bool=None):
     return SimpleNamespace(N=N, levels=levels, inverse=inverse, first=first, level_anchor=level_anchor)
 
 
+def _plan_content_hash(anchor, mask_anchor_bool):
+    """Position-weighted integer checksums of the (quantised) anchor bit patterns and of the anchor mask."""
+    q = anchor.detach().contiguous().view(torch.int32).reshape(-1).to(torch.int64)
+    w = torch.arange(1, q.numel() + 1, device=q.device, dtype=torch.int64)
+    parts = [q.sum(), (q * (w % 65521 + 1)).sum()]
+    if mask_anchor_bool is not None:
+        m = mask_anchor_bool.reshape(-1).to(torch.int64)
+        parts += [m.sum(), (m * (w[:m.numel()] % 8191 + 7)).sum()]
+    return tuple(torch.stack(parts).tolist())
+
+
 def get_level_plan(pc, anchor, mask_anchor_bool):
-    """Plan cache: valid while the anchor positions / offset masks it was derived from are unchanged
-    (position lr is 0 in the reference, arguments/__init__.py:86-87; masks flip rarely)."""
+    """Plan cache.  The plan depends on the quantised anchors (`_anchor`, the bounds, the voxel size) and on which
+    anchors still have a live offset.  Fast path: the source tensors are the SAME objects at the SAME version
+    (evaluation / scoring passes).  Otherwise -- every training iteration, because Adam bumps `_version` of `_anchor`
+    (position lr is 0, arguments/__init__.py:86-87, so the values do not move) and of `_mask` (whose binarised
+    any-offset-alive reduction flips rarely) -- a content checksum of the quantised anchors and of the anchor mask
+    decides (two small reductions and one read-back instead of two voxel sorts and a dozen index kernels)."""
     src_a, src_m = getattr(pc, "_anchor", anchor), getattr(pc, "_mask", None)
-    key = (anchor.shape[0], anchor.data_ptr() if anchor is src_a else None, src_a.data_ptr(), src_a._version,
-           None if src_m is None else (src_m.data_ptr(), src_m._version), mask_anchor_bool is None,
-           tuple(pc.level_scale))
+    fast = (anchor.shape[0], anchor.data_ptr() if anchor is src_a else None, src_a.data_ptr(), src_a._version,
+            None if src_m is None else (src_m.data_ptr(), src_m._version), mask_anchor_bool is None,
+            getattr(pc, "_cgs_bound_version", 0),
+            tuple((t.data_ptr(), t._version) for t in (pc.x_bound_min, pc.x_bound_max)))
+    static = (anchor.shape[0], mask_anchor_bool is None, tuple(pc.level_scale), float(pc.voxel_size))
     ent = getattr(pc, "_cgs_level_plan", None)
-    if ent is not None and ent[0] == key:
+    if ent is not None and ent[0] == fast and ent[2] == static:
         return ent[1]
-    plan = build_level_plan(pc, anchor, mask_anchor_bool)
+    content = _plan_content_hash(anchor, mask_anchor_bool)
+    if ent is not None and ent[2] == static and ent[3] == content:
+        plan = ent[1]
+    else:
+        plan = build_level_plan(pc, anchor, mask_anchor_bool)
     try:
-        pc._cgs_level_plan = (key, plan)
+        pc._cgs_level_plan = (fast, plan, static, content)
     except Exception:
         pass
     return plan

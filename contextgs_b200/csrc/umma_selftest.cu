@@ -172,9 +172,113 @@ umma_selftest_ss_kernel(const float *__restrict__ P, const float *__restrict__ Q
     if (warp == 0) umma::tmem_dealloc(tbase, 512);
 }
 
+
+// Same contraction over the tile's ROWS, but with both operands in the MN-MAJOR no-swizzle layout: a 16-byte unit
+// holds FOUR CONSECUTIVE FEATURES of ONE row, 8 rows x 16 B form a 128-byte core matrix, so thread `row` stores its
+// features as float4 (conflict-free, 4x fewer stores than the K-major form) at [(feature / 4)][row][4].
+// variant 0: SBO = stride between 4-feature groups (rows * 16 B), LBO = stride between 8-row groups (128 B)
+//            (CUTLASS make_umma_desc<Major::MN>, SWIZZLE_NONE);  variant 1: the two offsets swapped.
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_ss_mn_kernel(const float *__restrict__ P, const float *__restrict__ Q, int M, int N, int variant,
+                           float *__restrict__ D, int32_t *__restrict__ err)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *a_hi = reinterpret_cast<float4 *>(smem_raw);          // [32 groups][128 rows]
+    float4 *a_lo = a_hi + 32 * 128;
+    float4 *b_hi = a_lo + 32 * 128;                               // [N / 4 groups][128 rows]
+    float4 *b_lo = b_hi + (N / 4) * 128;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
+    if (tid == 0) {
+        umma::mbar_init(&s_bar, 1);
+        umma::fence_mbar_init();
+    }
+    const int row = tid;
+    for (int g = 0; g < 32; ++g) {
+        float v[4], h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = 4 * g + j;
+            v[j] = m < M ? P[(size_t)row * M + m] : 0.f;
+            uint32_t hi, lo;
+            umma::split_tf32(v[j], hi, lo);
+            h[j] = __uint_as_float(hi);
+            l[j] = __uint_as_float(lo);
+        }
+        a_hi[g * 128 + row] = make_float4(h[0], h[1], h[2], h[3]);
+        a_lo[g * 128 + row] = make_float4(l[0], l[1], l[2], l[3]);
+    }
+    for (int g = 0; g < N / 4; ++g) {
+        float h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t hi, lo;
+            umma::split_tf32(Q[(size_t)row * N + 4 * g + j], hi, lo);
+            h[j] = __uint_as_float(hi);
+            l[j] = __uint_as_float(lo);
+        }
+        b_hi[g * 128 + row] = make_float4(h[0], h[1], h[2], h[3]);
+        b_lo[g * 128 + row] = make_float4(l[0], l[1], l[2], l[3]);
+    }
+    umma::fence_proxy_async_smem();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = s_tmem;
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    if (tid == 0) {
+        const uint32_t idesc = umma::idesc_tf32(128, N) | (1u << 15) | (1u << 16);   // A and B MN-major
+        const uint32_t grp = 128u * 16u, k8 = 128u;
+        const uint32_t lbo = variant == 0 ? k8 : grp, sbo = variant == 0 ? grp : k8;
+        for (int s = 0; s < 16; ++s) {                            // K = 128 rows, 8 per instruction
+            const uint64_t ahi = umma::smem_desc_kmajor(umma::smem_u32(a_hi) + (uint32_t)s * k8, lbo, sbo);
+            const uint64_t alo = umma::smem_desc_kmajor(umma::smem_u32(a_lo) + (uint32_t)s * k8, lbo, sbo);
+            const uint64_t bhi = umma::smem_desc_kmajor(umma::smem_u32(b_hi) + (uint32_t)s * k8, lbo, sbo);
+            const uint64_t blo = umma::smem_desc_kmajor(umma::smem_u32(b_lo) + (uint32_t)s * k8, lbo, sbo);
+            umma::mma_tf32_ss(tbase, ahi, blo, idesc, s > 0 ? 1u : 0u);
+            umma::mma_tf32_ss(tbase, alo, bhi, idesc, 1u);
+            umma::mma_tf32_ss(tbase, ahi, bhi, idesc, 1u);
+        }
+        umma::umma_commit(&s_bar);
+    }
+    const bool ok = umma::mbar_wait(&s_bar, 0);
+    umma::fence_after_thread_sync();
+    if (!ok && lane == 0) atomicExch(err, 1);
+    for (int n0 = 0; n0 + 8 <= N; n0 += 8) {
+        uint32_t v[8];
+        umma::tmem_ld8(lane_base + n0, v);
+        umma::tmem_wait_ld();
+        if (tid < M)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) D[(size_t)tid * N + n0 + j] = __uint_as_float(v[j]);
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tbase, 512);
+}
+
 }  // namespace cgs
 
 using namespace cgs;
+
+extern "C" int cgs_umma_selftest_ss_mn(const float *P, const float *Q, int M, int N, int variant, float *D, int32_t *err,
+                                       void *stream)
+{
+    CGS_CHECK_PTR(P); CGS_CHECK_PTR(Q); CGS_CHECK_PTR(D); CGS_CHECK_PTR(err);
+    if (M < 1 || M > 128 || N < 16 || N > 160 || (N % 16) || variant < 0 || variant > 1) {
+        set_error("%s: need 1 <= M <= 128, 16 <= N <= 160 (N %% 16 == 0), variant 0 / 1", __func__);
+        return -2;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)2 * 32 * 128 * 16 + (size_t)2 * (N / 4) * 128 * 16;
+    cudaFuncSetAttribute(umma_selftest_ss_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaMemsetAsync(err, 0, sizeof(int32_t), st);
+    StageScope sc(ST_ELEMWISE, st, 1);
+    umma_selftest_ss_mn_kernel<<<1, 128, smem, st>>>(P, Q, M, N, variant, D, err);
+    return check_launch(__func__);
+}
 
 extern "C" int cgs_umma_selftest_ss(const float *P, const float *Q, int M, int N, int skew, float *D, int32_t *err,
                                     void *stream)

@@ -107,18 +107,36 @@ def _mlp(i, h, o, act=None):
 
 
 class GaussianModel(DensifyMixin, nn.Module):
-    def __init__(self, feat_dim=50, n_offsets=10, voxel_size=0.001, level_num=3, hyper_divisor=4, target_ratio=0.2,
-                 decoded_version=False, device="cuda"):
+    def __init__(self, feat_dim=50, n_offsets=10, voxel_size=0.001, update_depth=3, update_init_factor=16,
+                 update_hierachy_factor=4, use_feat_bank=False, n_features_per_level=2, resolutions_list=None,
+                 resolutions_list_2D=None, ste_binary=True, ste_multistep=False, add_noise=False, Q=1, use_2D=True,
+                 decoded_version=False, level_num=3, adaptQ_per_channel=False, hyper_divisor=4, target_ratio=0.2,
+                 disable_hyper=False, device="cuda"):
+        """Same positional order and keywords as the reference's constructor (scene/gaussian_model.py:61-83), so the
+        calls at train.py:94-107 / :450, test.py:149 and decompress.py:149 work unchanged; the defaults are the
+        values ContextGS trains with (arguments/__init__.py:50-55,67-68; train.py:595-616), not the reference's
+        signature defaults.  `device` is the one addition (the reference hard-codes .cuda())."""
         super().__init__()
         if (feat_dim, n_offsets, hyper_divisor, level_num) != (50, 10, 4, 3):
             raise NotImplementedError("the CUDA kernels are specialised for the ContextGS defaults "
                                       "feat_dim=50, n_offsets=10, hyper_divisor=4, level_num=3 "
                                       "(arguments/__init__.py:50-52,67-68; train.py:595)")
+        if use_feat_bank or adaptQ_per_channel:
+            raise NotImplementedError("use_feat_bank / adaptQ_per_channel are off in every ContextGS launch script "
+                                      "(scripts/*.py, train_scripts/*.py) and are not part of the hot path")
+        if target_ratio is None:
+            target_ratio = 0.2
         self.feat_dim, self.n_offsets, self.voxel_size = feat_dim, n_offsets, voxel_size
+        # densification constants (instance attributes like the reference; DensifyMixin's class values are the defaults)
+        self.update_depth, self.update_init_factor = int(update_depth), int(update_init_factor)
+        self.update_hierachy_factor, self.use_feat_bank = int(update_hierachy_factor), bool(use_feat_bank)
+        self.n_features_per_level, self.ste_binary, self.ste_multistep = n_features_per_level, ste_binary, ste_multistep
+        self.add_noise, self.Q, self.use_2D = add_noise, Q, use_2D
+        self.resolutions_list, self.resolutions_list_2D = resolutions_list, resolutions_list_2D
         self.level_num, self.hyper_divisor, self.target_ratio = level_num, hyper_divisor, target_ratio
         self.decoded_version = decoded_version
         self.level_scale = None
-        self.disable_hyper = False
+        self.disable_hyper = bool(disable_hyper)
         self.adaptQ_per_channel = False
         self.x_bound_min = torch.zeros(1, 3, device=device)
         self.x_bound_max = torch.ones(1, 3, device=device)
@@ -231,6 +249,7 @@ class GaussianModel(DensifyMixin, nn.Module):
         mx = torch.max(self._anchor, dim=0, keepdim=True)[0].detach()
         self.x_bound_min = torch.where(mn < 0, mn * 1.2, mn * 0.8)
         self.x_bound_max = torch.where(mx > 0, mx * 1.2, mx * 0.8)
+        self._cgs_bound_version = getattr(self, "_cgs_bound_version", 0) + 1   # invalidates the cached level plan
 
     @torch.no_grad()
     def replace_with_decoded(self, anchor, hyper, feat, offsets, scaling, masks):

@@ -90,6 +90,11 @@ CGS_API int cgs_umma_selftest(const float *A, const float *W, int N, int K, int 
  * skew: extra 16-byte units in the leading-dimension byte offset.  scripts/umma_ss_probe.py runs it. */
 CGS_API int cgs_umma_selftest_ss(const float *P, const float *Q, int M, int N, int skew, float *D, int32_t *err,
                                  void *stream);
+/* The same contraction with both operands in the MN-major no-swizzle layout ([feature / 4][row][4 floats]: one
+ * float4 store per four features of a row).  variant 0: SBO = stride between 4-feature groups, LBO = stride
+ * between 8-row groups; variant 1: swapped.  N <= 160. */
+CGS_API int cgs_umma_selftest_ss_mn(const float *P, const float *Q, int M, int N, int variant, float *D, int32_t *err,
+                                    void *stream);
 
 /* ------------------------------------------------------------------ rasterizer (P1, R0-R7) */
 

@@ -264,7 +264,7 @@ def level_plan(N, inverse, first):
 
 def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, binary_grid_masks,
                            mask_anchor_bool=None, training=False, predict_bpp=False, return_sum_bits=False,
-                           return_details=False):
+                           return_details=False, choose_override=None):
     """scene/gaussian_model.py:1541-1707.  `pc` needs: latent_codec, level_scale (or None), target_ratio,
     level_num, voxel_size, x_bound_min/max, mlps['grid'], n_offsets, feat_dim, feat_mean, scaling_mean,
     offset_mean (the three global means the reference takes at :1667-1669).
@@ -316,6 +316,8 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
 
     thresh = 1 if return_sum_bits else 0.15
     choose = torch.rand_like(anchor[:, 0]) <= thresh
+    if choose_override is not None:   # test hook: a caller-chosen subset instead of the random draw (:1658-1659)
+        choose = choose_override.clone()
     if mask_anchor_bool is not None:
         choose = choose & mask_anchor_bool
         rate = mask_anchor_bool.sum() / mask_anchor_bool.numel()
@@ -330,6 +332,7 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
     details = dict(feat_q=feat_q, scaling_q=scaling_q, offsets_q=offsets_q, choose=choose, bit_hyper=bit_hyper,
                    bit_feat=bit_feat, bit_scaling=bit_scaling, bit_offsets=bit_offsets, hyper_q=hyper_q,
                    lik_hyper=lik_hyper, Qf=Qf_all, Qs=Qs_all, Qo=Qo_all, mean_f=mean_f, std_f=std_f,
+                   mean_s=mean_s, std_s=std_s, mean_o=mean_o, std_o=std_o,
                    plan=plan, inverse=inverse, first=first)
     if return_sum_bits:
         bit_anchor = bit_hyper.shape[0] * 3 * 16
