@@ -718,7 +718,7 @@ def parity_block(args, scene, dec, cams_cpu, pc, pc_train, cam_dev, pipe, bg, de
 
 
 def reference_gpu_baseline(args, scene, pc, pc_train, cams_dev, pipe, bg, dev, timed):
-    """Labelled baseline, NOT the product and not `value`: the reference's OWN Python (oracle/_ref/*.pyc, byte-compiled
+    """Labelled baseline, NOT the product and not `value`: the reference's OWN Python (oracle/_ref/*.refbin, byte-compiled
     from /root/reference in the build container; stand-ins for absent third-party modules in oracle/ref_loader.py)
     with its tensors on CUDA -- its real deployment mode (SURVEY.md 8d "reference GPU").
       * entropy path: scene/gaussian_model.py:1541-1707 `multi_scale_generating(predict_bpp=True, return_sum_bits=True)`
@@ -732,7 +732,7 @@ def reference_gpu_baseline(args, scene, pc, pc_train, cams_dev, pipe, bg, dev, t
     The rasterizer has no reference GPU baseline: its source is not in the reference tree."""
     from oracle import ref_loader
     if not ref_loader.available():
-        return {"unavailable": "oracle/_ref/*.pyc not built (python -m oracle.build_ref needs /root/reference)"}
+        return {"unavailable": "oracle/_ref/*.refbin not built (python -m oracle.build_ref needs /root/reference)"}
     from contextgs_b200.neural_gaussians import generate_neural_gaussians
     from contextgs_b200.renderer import prefilter_voxel
     ref = ref_loader.load()

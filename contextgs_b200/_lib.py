@@ -46,6 +46,11 @@ SIGNATURES = {
     "cgs_umma_selftest": (c_int, [_PTR, _PTR, c_int, c_int, c_int, _PTR, _PTR, _PTR]),
     "cgs_umma_selftest_ss": (c_int, [_PTR, _PTR, c_int, c_int, c_int, _PTR, _PTR, _PTR]),
     "cgs_umma_selftest_ss_mn": (c_int, [_PTR, _PTR, c_int, c_int, c_int, _PTR, _PTR, _PTR]),
+    "cgs_neural_gaussians_umma_forward_train": (c_int, [_PTR, _PTR, c_int] + [_PTR] * 19 + [_PTR, c_size_t, _PTR]),
+    "cgs_neural_gaussians_bwd_umma_packed_floats": (c_int, []),
+    "cgs_neural_gaussians_save_floats": (c_int, [c_int]),
+    "cgs_debug_set": (c_int, [c_int, c_int]),
+    "cgs_neural_gaussians_backward_umma": (c_int, [_PTR, _PTR, c_int] + [_PTR] * 27),
     "cgs_visible_filter": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR]),
     "cgs_prefilter_workspace_bytes": (c_size_t, [c_int]),
     "cgs_prefilter_anchors": (c_int, [_PTR, c_int, _PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, c_size_t, _PTR]),
@@ -150,6 +155,25 @@ def lib():
             raise CgsError("libcontextgs_b200.so ABI version mismatch")
         _lib = L
     return _lib
+
+
+_deferred = []   # (int32 device flag, message): error flags of kernels whose result nobody reads back right away
+
+
+def deferred_error_check(flag, message):
+    """Park a device-side error flag; it is inspected at the next natural synchronisation point (`raise_deferred`,
+    called by the forward passes right after their own read-back) instead of forcing one here."""
+    _deferred.append((flag, message))
+    if len(_deferred) > 64:
+        raise_deferred()
+
+
+def raise_deferred():
+    while _deferred:
+        flag, message = _deferred.pop()
+        if int(flag.item()):
+            _deferred.clear()
+            raise CgsError(message)
 
 
 def check(code, what=""):

@@ -36,6 +36,7 @@ SOURCES = {
     "umma_selftest.cu": [],
     "neural_gaussians_umma.cu": ["-fmad=false"],
     "neural_gaussians_bwd.cu": [],
+    "neural_gaussians_bwd_umma.cu": [],
     "context_model_bwd.cu": [],
     "context_model_umma.cu": ["-fmad=false"],
     "level_divide.cu": ["-fmad=false"],

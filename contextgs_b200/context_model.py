@@ -105,16 +105,21 @@ def unique_voxels(points, voxel_size, scale, keep=None):
 
 
 def find_divide_scale(pc, anchor, target_ratio, level_num):
-    """scene/gaussian_model.py:1726-1749."""
-    upper0 = float(((pc.x_bound_max - pc.x_bound_min) / pc.voxel_size).max())
-    cur, lower, scales = anchor, 1.0, []
+    """scene/gaussian_model.py:1726-1749.  The reference bisects with 0-dim float32 TENSORS (scale_upper comes from the
+    bounds, `(scale_upper + scale_lower) / 2` stays a tensor, `.item()` at the end), so the arithmetic of the search is
+    float32: reproduced here with numpy float32 scalars on the host (the scales are saved in checkpoints and define
+    the level division, i.e. the bitstream)."""
+    import numpy as np
+    f32 = np.float32
+    upper0 = f32(float(((pc.x_bound_max - pc.x_bound_min) / pc.voxel_size).max()))
+    cur, lower, scales = anchor, f32(1.0), []
     for _ in range(level_num - 1):
         hi, lo = upper0, lower
         while True:
-            scale = (hi + lo) / 2
-            count, _, first = unique_voxels(cur, pc.voxel_size, scale)
+            scale = f32(f32(hi + lo) / f32(2.0))
+            count, _, first = unique_voxels(cur, pc.voxel_size, float(scale))
             ratio = count / cur.shape[0]
-            if abs(ratio - target_ratio) < 0.01 or abs(hi - lo) < 1:
+            if abs(ratio - target_ratio) < 0.01 or abs(f32(hi - lo)) < 1:
                 break
             if ratio < target_ratio:
                 hi = scale
@@ -122,7 +127,7 @@ def find_divide_scale(pc, anchor, target_ratio, level_num):
                 lo = scale
         # the reference continues with the unique voxel centres; their rows at any coarser scale are
         # what matters for the next search
-        cur = torch.round(cur[first] / pc.voxel_size / scale) * pc.voxel_size * scale
+        cur = torch.round(cur[first] / pc.voxel_size / float(scale)) * pc.voxel_size * float(scale)
         lower = scale
         scales.append(float(scale))
     return scales

@@ -1,0 +1,633 @@
+// Backward of the fused anchor -> neural-Gaussian generation on the tcgen05 tensor cores.
+//
+// Replaces what autograd does for gaussian_renderer/__init__.py:106-145 and the decoder MLPs
+// (scene/gaussian_model.py:153-174), like neural_gaussians_bwd.cu, but with every GEMM on the tensor cores and
+// NOTHING recomputed: the training-mode forward (neural_gaussians_umma.cu, kSave) leaves the hidden activations,
+// their sign bits, the layer-2 pre-activations and the compaction ranks behind (1.3 kB per visible anchor).
+//
+//   kernel 1  neural_gaussians_dgrad_umma_kernel   (data gradients; persistent, 128 anchors per tile, 256 threads,
+//             thread = (row, half) like the forward's BACK group)
+//       E1  gradient of the post-processing per kept (anchor, offset) pair -> dOut[128 x 144] (layer-2 output layout of
+//           the forward: opacity 16 | colour 48 | covariance 80), split hi / lo into TMEM, fp32 copy to HBM for kernel 2;
+//           direct gradients d_offsets, d_mask, partial d_scaling / d_anchor
+//       M1  dH = dOut W2 per head: 3xTF32 tcgen05.mma, A = dOut (TMEM), B = W2^T head (shared memory, K-major)
+//       E2  dPre = dH * (H > 0) (saved sign bits), split, IN PLACE as the next A operand; fp32 copy to HBM
+//       M2  dX = dPre W1 (K = 176, N = 64)
+//       E3  d_feat, d_anchor (view direction / distance), d_scaling
+//   kernel 2  neural_gaussians_wgrad_umma_kernel   (weight gradients; the contraction runs over the ROWS)
+//       dW2_h^T = dOut_h^T H_h and dW1^T = X^T dPre as SS-form tcgen05.mma with both operands in the MN-major
+//       no-swizzle layout ([feature / 4][row][4 floats]: every thread stores float4s, conflict free), 3xTF32,
+//       accumulators resident in TMEM over all slabs of a persistent CTA, one flush (atomicAdd) per CTA.
+//       Bias gradients ride along: a constant-one column in the padding of X (-> db1) and of every head of H (-> db2).
+//
+// TMEM columns of kernel 1 (480 of 512):
+//   [  0,288)  dOut hi [0,144) | lo [144,288)   -> later dPre lo [0,192) and the dX accumulator [192,256)
+//   [288,480)  dH accumulator, head h at 64h (N = 64 per head: 50 units + zero pads) -> overwritten in place by dPre hi
+#include "umma.cuh"
+
+namespace cgs {
+namespace ngbu {
+constexpr int kFeat = 50, kK = 10;
+constexpr int kRows = 128, kThreads = 256;
+constexpr int kOutP = 144, kHidP = 176, kInP = 64;
+constexpr int kHidT = 192;                                  // hidden columns in TMEM: head h at 64h (HBM rows: 56h)
+constexpr int kKo = 16, kKc = 48, kKv = 80;                 // K of the three dH GEMMs (= padded head widths)
+constexpr uint32_t kColAHi = 0, kColALo = 144, kColPLo = 0, kColDX = 192, kColD1 = 288;
+constexpr uint32_t kTmemCols = 512;
+// packed transposed weights (floats): B operands [K/4][64][4], hi then lo
+constexpr int kW2To = (kKo / 4) * 64 * 4, kW2Tc = (kKc / 4) * 64 * 4, kW2Tv = (kKv / 4) * 64 * 4, kW1T = (kHidT / 4) * 64 * 4;
+constexpr int kOffW2ToHi = 0, kOffW2ToLo = kOffW2ToHi + kW2To;
+constexpr int kOffW2TcHi = kOffW2ToLo + kW2To, kOffW2TcLo = kOffW2TcHi + kW2Tc;
+constexpr int kOffW2TvHi = kOffW2TcLo + kW2Tc, kOffW2TvLo = kOffW2TvHi + kW2Tv;
+constexpr int kOffW1THi = kOffW2TvLo + kW2Tv, kOffW1TLo = kOffW1THi + kW1T;
+constexpr int kPacked = kOffW1TLo + kW1T;                  // 43008 floats = 172032 B
+
+struct Smem {
+    float w[kPacked];
+    float part[kRows][10];       // half 0 -> half 1: d_scaling[6] + d_anchor[3] partial sums of the row
+    uint32_t tmem;
+    int timeout;
+    alignas(8) uint64_t bar[2];
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void st_split8(uint32_t tl, uint32_t col_hi, uint32_t col_lo, const float (&v)[8])
+{
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) umma::split_tf32(v[j], hi[j], lo[j]);
+    umma::tmem_st8(tl + col_hi, hi);
+    umma::tmem_st8(tl + col_lo, lo);
+}
+__device__ __forceinline__ void st_split4(uint32_t tl, uint32_t col_hi, uint32_t col_lo, const float (&v)[4])
+{
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) umma::split_tf32(v[j], hi[j], lo[j]);
+    umma::tmem_st4(tl + col_hi, hi);
+    umma::tmem_st4(tl + col_lo, lo);
+}
+}  // namespace ngbu
+
+__global__ void __launch_bounds__(ngbu::kThreads, 1)
+neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int *__restrict__ vis_idx, int Nv,
+                                   const float *__restrict__ anchor, const float *__restrict__ offsets,
+                                   const float *__restrict__ scaling, const float *__restrict__ mask, float cx, float cy,
+                                   float cz, const uint8_t *__restrict__ keep_mask, const float *__restrict__ save_pre2,
+                                   const uint32_t *__restrict__ save_hmask, const uint32_t *__restrict__ save_rowpos,
+                                   const uint32_t *__restrict__ save_tilebase, const float *__restrict__ g_xyz,
+                                   const float *__restrict__ g_color, const float *__restrict__ g_opacity,
+                                   const float *__restrict__ g_scaling, const float *__restrict__ g_rot,
+                                   float *__restrict__ d_anchor, float *__restrict__ d_feat, float *__restrict__ d_offsets,
+                                   float *__restrict__ d_scaling, float *__restrict__ d_mask, float *__restrict__ d_out,
+                                   float *__restrict__ d_pre, int32_t *__restrict__ err)
+{
+    using namespace ngbu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = warp >> 2;
+    const int row = 32 * (warp & 3) + lane;
+    const int num_tiles = (Nv + kRows - 1) / kRows;
+
+    if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
+    if (tid == 0) {
+        umma::mbar_init(&S.bar[0], 1);
+        umma::mbar_init(&S.bar[1], 1);
+        umma::fence_mbar_init();
+        S.timeout = 0;
+    }
+    {
+        const float4 *s4 = reinterpret_cast<const float4 *>(packed_w);
+        float4 *d4 = reinterpret_cast<float4 *>(S.w);
+        for (int i = tid; i < kPacked / 4; i += kThreads) d4[i] = __ldg(s4 + i);
+    }
+    umma::fence_proxy_async_smem();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = S.tmem;
+    const uint32_t tl = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+    const int kbase = 5 * half;
+
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t parity = it & 1u;
+        const int g = tile * kRows + row;
+        const bool valid = g < Nv;
+        const int a = valid ? (vis_idx ? __ldg(vis_idx + g) : g) : -1;
+
+        // ================= E1: gradient of the post-processing =================
+        float dsc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, danc[3] = {0.f, 0.f, 0.f};
+        float dO[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float sc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint32_t keepbits = 0, pos = 0;
+        const float *p2 = save_pre2 + (size_t)(valid ? g : 0) * kOutP;
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) keepbits |= keep_mask[(size_t)g * kK + kbase + j] ? (1u << j) : 0u;
+            pos = __ldg(save_tilebase + tile) + __ldg(save_rowpos + (size_t)g * 2 + half);
+            const float2 *s2 = reinterpret_cast<const float2 *>(scaling + 6 * (size_t)a);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float2 v = __ldg(s2 + i);
+                sc[2 * i] = v.x;
+                sc[2 * i + 1] = v.y;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int k = kbase + j;
+            float dC[4] = {0.f, 0.f, 0.f, 0.f}, dV[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (keepbits & (1u << j)) {
+                const size_t P3 = 3 * (size_t)pos;
+                const size_t ak = (size_t)a * kK + k;
+                const float gx = __ldg(g_xyz + P3), gy = __ldg(g_xyz + P3 + 1), gz = __ldg(g_xyz + P3 + 2);
+                const float o0 = __ldg(offsets + ak * 3), o1 = __ldg(offsets + ak * 3 + 1), o2 = __ldg(offsets + ak * 3 + 2);
+                d_offsets[ak * 3 + 0] = gx * sc[0];
+                d_offsets[ak * 3 + 1] = gy * sc[1];
+                d_offsets[ak * 3 + 2] = gz * sc[2];
+                danc[0] += gx; danc[1] += gy; danc[2] += gz;
+                dsc[0] += gx * o0; dsc[1] += gy * o1; dsc[2] += gz * o2;
+                // opacity = tanh(pre) * mask
+                const float t = tanhf(__ldg(p2 + 8 * half + j));
+                const float go = __ldg(g_opacity + pos);
+                d_mask[ak] = go * t;
+                dO[j] = go * __ldg(mask + ak) * (1.0f - t * t);
+                // colour = sigmoid(pre)
+                const float4 pc = __ldg(reinterpret_cast<const float4 *>(p2 + 16 + 4 * k));
+                const float pcv[3] = {pc.x, pc.y, pc.z};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float s = sigmoidf_(pcv[c]);
+                    dC[c] = __ldg(g_color + P3 + c) * s * (1.0f - s);
+                }
+                // scaling = sc[3:6] * sigmoid(pre[0:3]); rot = normalize(pre[3:7])
+                const float4 pa = __ldg(reinterpret_cast<const float4 *>(p2 + 64 + 8 * k));
+                const float4 pb = __ldg(reinterpret_cast<const float4 *>(p2 + 64 + 8 * k) + 1);
+                const float pv[3] = {pa.x, pa.y, pa.z};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float s = sigmoidf_(pv[c]);
+                    const float gs = __ldg(g_scaling + P3 + c);
+                    dsc[3 + c] += gs * s;
+                    dV[c] = gs * sc[3 + c] * s * (1.0f - s);
+                }
+                const float q0 = pa.w, q1 = pb.x, q2 = pb.y, q3 = pb.z;
+                const float nrm = fmaxf(sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3), 1e-12f);
+                const float4 gr = __ldg(reinterpret_cast<const float4 *>(g_rot) + pos);
+                const float r0 = q0 / nrm, r1 = q1 / nrm, r2 = q2 / nrm, r3 = q3 / nrm;
+                const float dot = r0 * gr.x + r1 * gr.y + r2 * gr.z + r3 * gr.w;
+                dV[3] = (gr.x - r0 * dot) / nrm;
+                dV[4] = (gr.y - r1 * dot) / nrm;
+                dV[5] = (gr.z - r2 * dot) / nrm;
+                dV[6] = (gr.w - r3 * dot) / nrm;
+                ++pos;
+            }
+            st_split4(tl, kColAHi + 16 + 4 * k, kColALo + 16 + 4 * k, dC);
+            st_split8(tl, kColAHi + 64 + 8 * k, kColALo + 64 + 8 * k, dV);
+            if (valid) {
+                float *dst = d_out + (size_t)g * kOutP;
+                *reinterpret_cast<float4 *>(dst + 16 + 4 * k) = make_float4(dC[0], dC[1], dC[2], dC[3]);
+                *reinterpret_cast<float4 *>(dst + 64 + 8 * k) = make_float4(dV[0], dV[1], dV[2], dV[3]);
+                *(reinterpret_cast<float4 *>(dst + 64 + 8 * k) + 1) = make_float4(dV[4], dV[5], dV[6], dV[7]);
+            }
+        }
+        st_split8(tl, kColAHi + 8 * half, kColALo + 8 * half, dO);
+        if (valid) {
+            float *dst = d_out + (size_t)g * kOutP + 8 * half;
+            *reinterpret_cast<float4 *>(dst) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+            *(reinterpret_cast<float4 *>(dst) + 1) = make_float4(dO[4], dO[5], dO[6], dO[7]);
+        }
+        if (half == 1) {   // columns 56..63 of the colour head are padding (10 offsets x 4 = 40 of 48): keep them finite
+            const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            st_split8(tl, kColAHi + 56, kColALo + 56, z8);
+            if (valid) {
+                float *dst = d_out + (size_t)g * kOutP + 56;
+                *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *(reinterpret_cast<float4 *>(dst) + 1) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (half == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) S.part[row][i] = dsc[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) S.part[row][6 + i] = danc[i];
+        }
+        // sign bits of the hidden layer for E2 (in flight while the tensor core works)
+        uint32_t hm[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        if (valid) {
+            const uint2 *m = reinterpret_cast<const uint2 *>(save_hmask + (size_t)g * 6);
+            const uint2 m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2);
+            hm[0] = m0.x; hm[1] = m0.y; hm[2] = m1.x; hm[3] = m1.y; hm[4] = m2.x; hm[5] = m2.y;
+        }
+        umma::tmem_wait_st();
+        umma::fence_before_thread_sync();
+        __syncthreads();
+
+        // ================= M1: dH_h = dOut_h W2_h =================
+        if (tid == 0) {
+            umma::fence_after_thread_sync();
+            umma::gemm_3xtf32(tbase + kColD1 + 0, tbase + kColAHi + 0, tbase + kColALo + 0, S.w + kOffW2ToHi,
+                              S.w + kOffW2ToLo, 64, kKo, true);
+            umma::gemm_3xtf32(tbase + kColD1 + 64, tbase + kColAHi + 16, tbase + kColALo + 16, S.w + kOffW2TcHi,
+                              S.w + kOffW2TcLo, 64, kKc, true);
+            umma::gemm_3xtf32(tbase + kColD1 + 128, tbase + kColAHi + 64, tbase + kColALo + 64, S.w + kOffW2TvHi,
+                              S.w + kOffW2TvLo, 64, kKv, true);
+            umma::umma_commit(&S.bar[0]);
+        }
+        if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
+        umma::fence_after_thread_sync();
+
+        // ================= E2: dPre = dH * (H > 0) =================
+        // TMEM chunk q (8 columns at 64h + 8cc) <-> hidden columns 56h + 8cc .. +7 of the saved layout (cc = 7: padding)
+        {
+#pragma unroll
+            for (int qq = 0; qq < 12; ++qq) {
+                const int q = 12 * half + qq, h = q >> 3, cc = q & 7;
+                const uint32_t tcol = (uint32_t)(64 * h + 8 * cc);
+                float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (cc < 7) {
+                    uint32_t v[8];
+                    umma::tmem_ld8(tl + kColD1 + tcol, v);
+                    umma::tmem_wait_ld8(v);
+                    const int hcol = 56 * h + 8 * cc, hf = hcol >= 88 ? 1 : 0, b = hcol - 88 * hf;
+                    const uint32_t bits = (hm[3 * hf + (b >> 5)] >> (b & 31)) & 0xffu;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = (bits >> j) & 1u ? __uint_as_float(v[j]) : 0.f;
+                    if (valid) {
+                        float *dst = d_pre + (size_t)g * kHidP + hcol;
+                        *reinterpret_cast<float4 *>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+                        *(reinterpret_cast<float4 *>(dst) + 1) = make_float4(f[4], f[5], f[6], f[7]);
+                    }
+                }
+                st_split8(tl, kColD1 + tcol, kColPLo + tcol, f);
+            }
+            if (half == 1 && valid) {   // hidden columns 168..175 of the HBM row are padding
+                float *dst = d_pre + (size_t)g * kHidP + 168;
+                *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *(reinterpret_cast<float4 *>(dst) + 1) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        umma::tmem_wait_st();
+        umma::fence_before_thread_sync();
+        __syncthreads();
+
+        // ================= M2: dX = dPre W1 =================
+        if (tid == 0) {
+            umma::fence_after_thread_sync();
+            umma::gemm_3xtf32(tbase + kColDX, tbase + kColD1, tbase + kColPLo, S.w + kOffW1THi, S.w + kOffW1TLo, kInP,
+                              kHidT, true);
+            umma::umma_commit(&S.bar[1]);
+        }
+        if (!umma::mbar_wait(&S.bar[1], parity)) S.timeout = 1;
+        umma::fence_after_thread_sync();
+
+        // ================= E3: d_feat, d_anchor, d_scaling =================
+        if (half == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[8];
+                umma::tmem_ld8(tl + kColDX + 8 * c, v);
+                umma::tmem_wait_ld8(v);
+                if (valid) {
+                    float2 *df = reinterpret_cast<float2 *>(d_feat + (size_t)a * kFeat + 8 * c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) df[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                }
+            }
+        } else {
+            float x[24];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint32_t v[8];
+                umma::tmem_ld8(tl + kColDX + 32 + 8 * c, v);
+                umma::tmem_wait_ld8(v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[8 * c + j] = __uint_as_float(v[j]);
+            }
+            if (valid) {
+                float2 *df = reinterpret_cast<float2 *>(d_feat + (size_t)a * kFeat + 32);
+#pragma unroll
+                for (int j = 0; j < 9; ++j) df[j] = make_float2(x[2 * j], x[2 * j + 1]);
+                // view = u / |u|, dist = |u|, u = anchor - cam  (gaussian_renderer/__init__.py:106-108)
+                const float ax = __ldg(anchor + 3 * (size_t)a), ay = __ldg(anchor + 3 * (size_t)a + 1),
+                            az = __ldg(anchor + 3 * (size_t)a + 2);
+                const float ux = ax - cx, uy = ay - cy, uz = az - cz;
+                const float d = sqrtf(ux * ux + uy * uy + uz * uz);
+                const float vx = ux / d, vy = uy / d, vz = uz / d;
+                const float gvx = x[18], gvy = x[19], gvz = x[20], gd = x[21];
+                const float dot = vx * gvx + vy * gvy + vz * gvz;
+                d_anchor[3 * (size_t)a + 0] = S.part[row][6] + danc[0] + (gvx - vx * dot) / d + gd * vx;
+                d_anchor[3 * (size_t)a + 1] = S.part[row][7] + danc[1] + (gvy - vy * dot) / d + gd * vy;
+                d_anchor[3 * (size_t)a + 2] = S.part[row][8] + danc[2] + (gvz - vz * dot) / d + gd * vz;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) d_scaling[(size_t)a * 6 + i] = S.part[row][i] + dsc[i];
+            }
+        }
+        umma::fence_before_thread_sync();
+        __syncthreads();   // dX / part consumed: the next tile may overwrite columns [0,288) and S.part
+        umma::fence_after_thread_sync();
+    }
+
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    if (tid == 0 && S.timeout) atomicExch(err, 1);
+    if (warp == 0) umma::tmem_dealloc(tbase, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// kernel 2: weight gradients.  Per slab of kSlab visible rows the CTA stages, split into TF32 hi / lo and in the
+// MN-major layout [group of 4 features][row][4 floats]:
+//     X    14 groups  layer-1 input  [feat 50 | view 3 | dist | 1 | 0]      (the 1 makes row 54 of dW1^T the bias gradient)
+//     dOut 36 groups  (kernel 1)
+//     H    44 groups  (forward), with a 1 in column 56h + 55 of every head (-> db2 in column 55 of dW2_h^T)
+//     dPre 44 groups  (kernel 1)
+// and issues   D_h[out, hid] += dOut_h^T H_h  (M = 128 from group {0, 4, 16} of dOut, N = 64 from group 14h of H)
+//              D_x[in,  hid] += X^T dPre      (M = 128 from group 0 of X,  N = 176).
+// An M = 128 operand that is narrower than 128 features simply runs on into the next array (finite values, their
+// accumulator lanes are never read).  TMEM: D_o | D_c | D_v at columns 0 / 64 / 128, D_x at [192,368).
+namespace ngwu {
+constexpr int kThreads = 256, kSlab = 16;
+constexpr int kGX = 14, kGO = 36, kGH = 44, kGP = 44, kGroups = kGX + kGO + kGH + kGP;   // 138
+constexpr int kOffX = 0, kOffO = kGX, kOffH = kOffO + kGO, kOffP = kOffH + kGH;
+constexpr uint32_t kColDo = 0, kColDc = 64, kColDv = 128, kColDx = 192, kTmemCols = 512;
+// forward-layout weight block of the SIMT kernels (contextgs_b200/neural_gaussians.py pack_decoder_weights): the
+// gradient is returned in this layout
+constexpr int kIn = 54, kLd1 = 152, kLdO = 12, kLdC = 32, kLdV = 72;
+constexpr int kOffW1 = 0, kOffB1 = kOffW1 + kIn * kLd1, kOffW2o = kOffB1 + kLd1, kOffB2o = kOffW2o + 50 * kLdO;
+constexpr int kOffW2c = kOffB2o + kLdO, kOffB2c = kOffW2c + 50 * kLdC, kOffW2v = kOffB2c + kLdC;
+constexpr int kOffB2v = kOffW2v + 50 * kLdV;
+
+struct Buf {
+    float4 hi[kGroups * kSlab];
+    float4 lo[kGroups * kSlab];
+};
+struct Smem {
+    Buf buf[2];
+    uint32_t tmem;
+    int timeout;
+    alignas(8) uint64_t bar[2];
+};
+}  // namespace ngwu
+
+__global__ void __launch_bounds__(ngwu::kThreads, 1)
+neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, const float *__restrict__ anchor,
+                                   const float *__restrict__ feat, float cx, float cy, float cz,
+                                   const float *__restrict__ save_h, const float *__restrict__ d_out,
+                                   const float *__restrict__ d_pre, float *__restrict__ d_w, int32_t *__restrict__ err,
+                                   int desc_variant)
+{
+    using namespace ngwu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int num_slabs = (Nv + kSlab - 1) / kSlab;
+
+    if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
+    if (tid == 0) {
+        umma::mbar_init(&S.bar[0], 1);
+        umma::mbar_init(&S.bar[1], 1);
+        umma::fence_mbar_init();
+        S.timeout = 0;
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = S.tmem;
+
+    const uint32_t idesc64 = umma::idesc_tf32(128, 64) | (1u << 15) | (1u << 16);     // A and B MN-major
+    const uint32_t idesc176 = umma::idesc_tf32(128, 176) | (1u << 15) | (1u << 16);
+    // MN-major no-swizzle: SBO = stride between 4-feature groups, LBO = stride between 8-row groups (variant 0, CUTLASS
+    // make_umma_desc<Major::MN>); variant 1 swaps the two fields (diagnostic switch, cgs_debug_set(0, v))
+    const uint32_t grp = (uint32_t)kSlab * 16u;
+    const uint32_t sbo = desc_variant == 0 ? grp : 128u, lbo = desc_variant == 0 ? 128u : grp;
+
+    uint32_t it = 0;
+    for (int slab = blockIdx.x; slab < num_slabs; slab += gridDim.x, ++it) {
+        const uint32_t b = it & 1u;
+        Buf &B = S.buf[b];
+        // the MMAs that read this buffer two slabs ago must have completed
+        if (it >= 2) {
+            if (!umma::mbar_wait(&S.bar[b], ((it >> 1) - 1) & 1u)) S.timeout = 1;
+            umma::fence_after_thread_sync();
+        }
+        const int row0 = slab * kSlab;
+        for (int i = tid; i < kGroups * kSlab; i += kThreads) {
+            const int r = i & (kSlab - 1), c = i / kSlab;
+            const int g = row0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g < Nv) {
+                if (c >= kOffP) {
+                    v = __ldg(reinterpret_cast<const float4 *>(d_pre + (size_t)g * 176) + (c - kOffP));
+                } else if (c >= kOffH) {
+                    const int gi = c - kOffH;
+                    v = __ldg(reinterpret_cast<const float4 *>(save_h + (size_t)g * 176) + gi);
+                    if (gi == 13 || gi == 27 || gi == 41) v.w = 1.0f;      // column 56h + 55: bias row of head h
+                } else if (c >= kOffO) {
+                    v = __ldg(reinterpret_cast<const float4 *>(d_out + (size_t)g * 144) + (c - kOffO));
+                } else {
+                    const int a = vis_idx ? __ldg(vis_idx + g) : g;
+                    const float *f = feat + (size_t)a * 50;
+                    if (c < 12) {
+                        const float2 p = __ldg(reinterpret_cast<const float2 *>(f + 4 * c));
+                        const float2 q = __ldg(reinterpret_cast<const float2 *>(f + 4 * c) + 1);
+                        v = make_float4(p.x, p.y, q.x, q.y);
+                    } else {
+                        const float ux = __ldg(anchor + 3 * (size_t)a) - cx, uy = __ldg(anchor + 3 * (size_t)a + 1) - cy,
+                                    uz = __ldg(anchor + 3 * (size_t)a + 2) - cz;
+                        const float d = sqrtf(ux * ux + uy * uy + uz * uz);
+                        if (c == 12) {
+                            const float2 p = __ldg(reinterpret_cast<const float2 *>(f + 48));
+                            v = make_float4(p.x, p.y, ux / d, uy / d);
+                        } else {
+                            v = make_float4(uz / d, d, 1.0f, 0.f);
+                        }
+                    }
+                }
+            }
+            uint32_t h[4], l[4];
+            umma::split_tf32(v.x, h[0], l[0]);
+            umma::split_tf32(v.y, h[1], l[1]);
+            umma::split_tf32(v.z, h[2], l[2]);
+            umma::split_tf32(v.w, h[3], l[3]);
+            B.hi[c * kSlab + r] = make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]),
+                                              __uint_as_float(h[3]));
+            B.lo[c * kSlab + r] = make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]),
+                                              __uint_as_float(l[3]));
+        }
+        umma::fence_proxy_async_smem();
+        umma::fence_before_thread_sync();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_thread_sync();
+            const uint32_t hi = umma::smem_u32(B.hi), lo = umma::smem_u32(B.lo);
+            auto desc = [&](uint32_t base, int group, int kstep) {
+                return umma::smem_desc_kmajor(base + (uint32_t)group * grp + (uint32_t)kstep * 128u, lbo, sbo);
+            };
+            const uint32_t acc0 = it > 0 ? 1u : 0u;
+#pragma unroll
+            for (int s = 0; s < kSlab / 8; ++s) {
+                const uint32_t acc = (s > 0) ? 1u : acc0;
+                // three heads of dW2^T
+                const int og[3] = {0, 4, 16};
+                const uint32_t dcol[3] = {kColDo, kColDc, kColDv};
+#pragma unroll
+                for (int h = 0; h < 3; ++h) {
+                    const uint64_t a_hi = desc(hi, kOffO + og[h], s), a_lo = desc(lo, kOffO + og[h], s);
+                    const uint64_t b_hi = desc(hi, kOffH + 14 * h, s), b_lo = desc(lo, kOffH + 14 * h, s);
+                    umma::mma_tf32_ss(tbase + dcol[h], a_hi, b_lo, idesc64, acc);
+                    umma::mma_tf32_ss(tbase + dcol[h], a_lo, b_hi, idesc64, 1u);
+                    umma::mma_tf32_ss(tbase + dcol[h], a_hi, b_hi, idesc64, 1u);
+                }
+                // dW1^T
+                const uint64_t a_hi = desc(hi, kOffX, s), a_lo = desc(lo, kOffX, s);
+                const uint64_t b_hi = desc(hi, kOffP, s), b_lo = desc(lo, kOffP, s);
+                umma::mma_tf32_ss(tbase + kColDx, a_hi, b_lo, idesc176, acc);
+                umma::mma_tf32_ss(tbase + kColDx, a_lo, b_hi, idesc176, 1u);
+                umma::mma_tf32_ss(tbase + kColDx, a_hi, b_hi, idesc176, 1u);
+            }
+            umma::umma_commit(&S.bar[b]);
+        }
+    }
+    // ---- drain: the last commit of each buffer covers every earlier MMA (commits complete in order) ----------------
+    const uint32_t n_it = it;
+    if (n_it >= 1) {
+        const uint32_t last = n_it - 1, bl = last & 1u;
+        if (!umma::mbar_wait(&S.bar[bl], (last >> 1) & 1u)) S.timeout = 1;
+        if (n_it >= 2) {
+            const uint32_t prev = n_it - 2, bp = prev & 1u;
+            if (!umma::mbar_wait(&S.bar[bp], (prev >> 1) & 1u)) S.timeout = 1;
+        }
+    }
+    umma::fence_after_thread_sync();
+
+    // ---- flush: lane = output unit (dW2 heads) / input unit (dW1), column = hidden unit ---------------------------------
+    if (n_it >= 1) {
+        const uint32_t tl = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
+        const int L = 32 * (warp & 3) + lane;     // accumulator lane of this thread
+        const int chalf = warp >> 2;              // warps w and w + 4 share a lane quadrant: split the columns
+        // dW2 heads
+#pragma unroll 1
+        for (int h = 0; h < 3; ++h) {
+            int n = -1, ld = 0, offW = 0, offB = 0;
+            if (h == 0) { if (L < 16 && (L & 7) < 5) n = 5 * (L >> 3) + (L & 7); ld = kLdO; offW = kOffW2o; offB = kOffB2o; }
+            if (h == 1) { if (L < 40 && (L & 3) < 3) n = 3 * (L >> 2) + (L & 3); ld = kLdC; offW = kOffW2c; offB = kOffB2c; }
+            if (h == 2) { if (L < 80 && (L & 7) < 7) n = 7 * (L >> 3) + (L & 7); ld = kLdV; offW = kOffW2v; offB = kOffB2v; }
+            const uint32_t dcol = h == 0 ? kColDo : (h == 1 ? kColDc : kColDv);
+#pragma unroll 1
+            for (int c = chalf; c < 7; c += 2) {
+                uint32_t v[8];
+                umma::tmem_ld8(tl + dcol + 8 * c, v);
+                umma::tmem_wait_ld8(v);
+                if (n >= 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int hh = 8 * c + j;
+                        if (hh < 50) atomicAdd(d_w + offW + hh * ld + n, __uint_as_float(v[j]));
+                        else if (hh == 55) atomicAdd(d_w + offB + n, __uint_as_float(v[j]));
+                    }
+                }
+            }
+        }
+        // dW1 (rows 0..53) and b1 (row 54, the constant-one input)
+#pragma unroll 1
+        for (int c = chalf; c < 22; c += 2) {
+            uint32_t v[8];
+            umma::tmem_ld8(tl + kColDx + 8 * c, v);
+            umma::tmem_wait_ld8(v);
+            if (L <= kIn) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = 8 * c + j, h = col / 56, u = col - 56 * h;
+                    if (h < 3 && u < 50) {
+                        if (L < kIn) atomicAdd(d_w + kOffW1 + L * kLd1 + 50 * h + u, __uint_as_float(v[j]));
+                        else atomicAdd(d_w + kOffB1 + 50 * h + u, __uint_as_float(v[j]));
+                    }
+                }
+            }
+        }
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    if (tid == 0 && S.timeout) atomicExch(err, 1);
+    if (warp == 0) umma::tmem_dealloc(tbase, kTmemCols);
+}
+
+}  // namespace cgs
+
+using namespace cgs;
+
+static int g_wgrad_desc_variant = 0;
+
+/* diagnostic switches: key 0 = descriptor variant of the weight-gradient kernel's MN-major operands (0 / 1) */
+extern "C" int cgs_debug_set(int key, int value)
+{
+    if (key == 0) { g_wgrad_desc_variant = value ? 1 : 0; return 0; }
+    return -1;
+}
+
+extern "C" int cgs_neural_gaussians_bwd_umma_packed_floats(void) { return ngbu::kPacked; }
+
+/* scratch rows of the forward -> backward hand-over, in floats / words per visible anchor */
+extern "C" int cgs_neural_gaussians_save_floats(int what)
+{
+    switch (what) {
+    case 0: return 176;   /* save_h      */
+    case 1: return 6;     /* save_hmask  */
+    case 2: return 144;   /* save_pre2   */
+    case 3: return 2;     /* save_rowpos */
+    case 4: return ngbu::kRows;   /* rows per tile (save_tilebase has one word per tile) */
+    }
+    return -1;
+}
+
+extern "C" int cgs_neural_gaussians_backward_umma(const float *packed_bwd, const int32_t *vis_idx, int Nv,
+                                                  const float *anchor, const float *feat, const float *offsets,
+                                                  const float *scaling, const float *mask, const float *campos_host,
+                                                  const uint8_t *keep_mask, const float *save_h, const uint32_t *save_hmask,
+                                                  const float *save_pre2, const uint32_t *save_rowpos,
+                                                  const uint32_t *save_tilebase, const float *g_xyz, const float *g_color,
+                                                  const float *g_opacity, const float *g_scaling, const float *g_rot,
+                                                  float *d_anchor, float *d_feat, float *d_offsets, float *d_scaling,
+                                                  float *d_mask, float *d_packed_fwd, float *scratch_dout,
+                                                  float *scratch_dpre, int32_t *err, void *stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (Nv <= 0) return 0;
+    CGS_CHECK_PTR(packed_bwd); CGS_CHECK_PTR(anchor); CGS_CHECK_PTR(feat); CGS_CHECK_PTR(offsets); CGS_CHECK_PTR(scaling);
+    CGS_CHECK_PTR(mask); CGS_CHECK_PTR(campos_host); CGS_CHECK_PTR(keep_mask); CGS_CHECK_PTR(save_h);
+    CGS_CHECK_PTR(save_hmask); CGS_CHECK_PTR(save_pre2); CGS_CHECK_PTR(save_rowpos); CGS_CHECK_PTR(save_tilebase);
+    CGS_CHECK_PTR(g_xyz); CGS_CHECK_PTR(g_color); CGS_CHECK_PTR(g_opacity); CGS_CHECK_PTR(g_scaling); CGS_CHECK_PTR(g_rot);
+    CGS_CHECK_PTR(d_anchor); CGS_CHECK_PTR(d_feat); CGS_CHECK_PTR(d_offsets); CGS_CHECK_PTR(d_scaling); CGS_CHECK_PTR(d_mask);
+    CGS_CHECK_PTR(d_packed_fwd); CGS_CHECK_PTR(scratch_dout); CGS_CHECK_PTR(scratch_dpre); CGS_CHECK_PTR(err);
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(neural_gaussians_dgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(ngbu::Smem));
+        cudaFuncSetAttribute(neural_gaussians_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(ngwu::Smem));
+        if (sm_count <= 0) sm_count = kNumSMs;
+    }
+    StageScope sc(ST_G1_BWD, st, 2);
+    {
+        const int tiles = (Nv + ngbu::kRows - 1) / ngbu::kRows;
+        const int grid = tiles < sm_count ? tiles : sm_count;
+        neural_gaussians_dgrad_umma_kernel<<<grid, ngbu::kThreads, sizeof(ngbu::Smem), st>>>(
+            packed_bwd, vis_idx, Nv, anchor, offsets, scaling, mask, campos_host[0], campos_host[1], campos_host[2],
+            keep_mask, save_pre2, save_hmask, save_rowpos, save_tilebase, g_xyz, g_color, g_opacity, g_scaling, g_rot,
+            d_anchor, d_feat, d_offsets, d_scaling, d_mask, scratch_dout, scratch_dpre, err);
+    }
+    {
+        const int slabs = (Nv + ngwu::kSlab - 1) / ngwu::kSlab;
+        const int grid = slabs < sm_count ? slabs : sm_count;
+        neural_gaussians_wgrad_umma_kernel<<<grid, ngwu::kThreads, sizeof(ngwu::Smem), st>>>(
+            vis_idx, Nv, anchor, feat, campos_host[0], campos_host[1], campos_host[2], save_h, scratch_dout, scratch_dpre,
+            d_packed_fwd, err, g_wgrad_desc_variant);
+    }
+    return check_launch(__func__);
+}

@@ -176,20 +176,41 @@ __device__ __forceinline__ float fast_tanh(float x)
     return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
+// What the training-mode forward leaves behind for the tcgen05 backward (neural_gaussians_bwd_umma.cu), per VISIBLE
+// row r (position in the visible list): all NULL in inference.
+struct SaveOut {
+    float *h;             // [Nv][176] hidden activations relu(D1 + b1) in the kernel's column layout (head h at 56h)
+    uint32_t *hmask;      // [Nv][6]   bit (8c + j) of word group `half`: hidden unit 88*half + 8c + j is positive
+    float *pre2;          // [Nv][144] layer-2 pre-activations incl. bias: opacity 16 | colour 48 | covariance 80
+    uint32_t *rowpos;     // [Nv][2]   tile-local rank of the first kept Gaussian of (row, half)
+    uint32_t *tilebase;   // [tiles]   global rank of the tile's first Gaussian
+};
+
 // hidden = relu(D1 + b1) of 8 accumulator columns, split into TF32 hi / lo, written back to TMEM
-__device__ __forceinline__ void relu_split_store(const Smem &S, uint32_t tl, uint32_t col, const uint32_t (&v)[8])
+template <bool kSave>
+__device__ __forceinline__ uint32_t relu_split_store(const Smem &S, uint32_t tl, uint32_t col, const uint32_t (&v)[8],
+                                                     float *save_row)
 {
     uint32_t hi[8], lo[8];
+    float h[8];
+    uint32_t bits = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float h = fmaxf(__uint_as_float(v[j]) + S.w[kOffB1 + col + j], 0.f);
-        umma::split_tf32(h, hi[j], lo[j]);
+        h[j] = fmaxf(__uint_as_float(v[j]) + S.w[kOffB1 + col + j], 0.f);
+        umma::split_tf32(h[j], hi[j], lo[j]);
+        if (kSave) bits |= h[j] > 0.f ? (1u << j) : 0u;
     }
     umma::tmem_st8(tl + kColD1 + col, hi);
     umma::tmem_st8(tl + kColHLo + col, lo);
+    if (kSave && save_row) {
+        reinterpret_cast<float4 *>(save_row + col)[0] = make_float4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<float4 *>(save_row + col)[1] = make_float4(h[4], h[5], h[6], h[7]);
+    }
+    return bits;
 }
 }  // namespace ngu
 
+template <bool kSave>
 __global__ void __launch_bounds__(ngu::kThreads, 1)
 neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__restrict__ vis_idx, int Nv_cap,
                              const int *__restrict__ nv_dev, uint32_t out_cap, const float *__restrict__ anchor, const float *__restrict__ feat,
@@ -198,7 +219,8 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                              float *__restrict__ o_xyz, float *__restrict__ o_color, float *__restrict__ o_opacity,
                              float *__restrict__ o_scaling, float *__restrict__ o_rot,
                              float *__restrict__ o_neural_opacity, uint8_t *__restrict__ o_mask,
-                             unsigned long long *scan_state, uint32_t *ctrl, int32_t *__restrict__ count_out)
+                             unsigned long long *scan_state, uint32_t *ctrl, int32_t *__restrict__ count_out,
+                             ngu::SaveOut save)
 {
     using namespace ngu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -273,6 +295,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                 const uint64_t excl = lookback_walk(scan_state, t, total);
                 if (lane == 0) {
                     S.tile_base[par] = (uint32_t)excl;
+                    if (kSave) save.tilebase[t] = (uint32_t)excl;
                     if (t == num_tiles - 1) *count_out = (int32_t)(excl + total);
                 }
             }
@@ -323,19 +346,26 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
             // software pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
             {
                 const uint32_t col0 = (uint32_t)(88 * half);
+                const int grow = tile * kRows + row;
+                float *save_row = (kSave && grow < Nv) ? save.h + (size_t)grow * kN1 : nullptr;
+                uint32_t hm[3] = {0u, 0u, 0u};
                 uint32_t va[8], vb[8];
                 umma::tmem_ld8(tl + kColD1 + col0, va);
                 umma::tmem_wait_ld8(va);
 #pragma unroll
                 for (int c = 0; c < 10; c += 2) {
                     umma::tmem_ld8(tl + kColD1 + col0 + 8 * (c + 1), vb);
-                    relu_split_store(S, tl, col0 + 8 * c, va);
+                    hm[(8 * c) >> 5] |= relu_split_store<kSave>(S, tl, col0 + 8 * c, va, save_row) << ((8 * c) & 31);
                     umma::tmem_wait_ld8(vb);
                     umma::tmem_ld8(tl + kColD1 + col0 + 8 * (c + 2), va);
-                    relu_split_store(S, tl, col0 + 8 * (c + 1), vb);
+                    hm[(8 * (c + 1)) >> 5] |= relu_split_store<kSave>(S, tl, col0 + 8 * (c + 1), vb, save_row) << ((8 * (c + 1)) & 31);
                     umma::tmem_wait_ld8(va);
                 }
-                relu_split_store(S, tl, col0 + 80, va);
+                hm[2] |= relu_split_store<kSave>(S, tl, col0 + 80, va, save_row) << 16;
+                if (kSave && save_row) {
+                    uint32_t *m = save.hmask + (size_t)grow * 6 + 3 * half;
+                    m[0] = hm[0]; m[1] = hm[1]; m[2] = hm[2];
+                }
             }
             umma::tmem_wait_st();
             umma::fence_before_thread_sync();
@@ -406,6 +436,14 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                         o_mask[gp] = (keepbits >> j) & 1u;
                     }
                 }
+                if (kSave && tile * kRows + row < Nv) {
+                    float p[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) p[j] = j < 5 ? __uint_as_float(v[j]) + S.w[kOffB2o + 8 * half + j] : 0.f;
+                    float4 *dst = reinterpret_cast<float4 *>(save.pre2 + ((size_t)tile * kRows + row) * 144 + 8 * half);
+                    dst[0] = make_float4(p[0], p[1], p[2], p[3]);
+                    dst[1] = make_float4(p[4], p[5], p[6], p[7]);
+                }
             }
             S.cnt[row * 2 + half] = __popc(keepbits);  // order index = row*2 + half
             group_sync(2);
@@ -438,6 +476,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                 st[tile] = (tile == 0 ? kLbInclusive : kLbAggregate) | (unsigned long long)total;
             }
             uint32_t pos = S.excl[row * 2 + half];
+            if (kSave && tile * kRows + row < Nv) save.rowpos[((size_t)tile * kRows + row) * 2 + half] = pos;
 
             // ---- epilogue 2b: post-process the kept offsets into the staging buffers -----------------------
             if (!umma::mbar_wait(&S.bar[BAR_L2ALL], parity)) S.timeout = 1;
@@ -457,6 +496,22 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                     if (j + 1 < 5) {
                         umma::tmem_ld4(tl + kColDc + 4 * (k + 1), vc[b ^ 1]);
                         umma::tmem_ld8(tl + kColDv + 8 * (k + 1), vv[b ^ 1]);
+                    }
+                    if (kSave && tile * kRows + row < Nv) {
+                        float *dst = save.pre2 + ((size_t)tile * kRows + row) * 144;
+                        reinterpret_cast<float4 *>(dst + 16 + 4 * k)[0] =
+                            make_float4(__uint_as_float(vc[b][0]) + S.w[kOffB2c + 4 * k + 0],
+                                        __uint_as_float(vc[b][1]) + S.w[kOffB2c + 4 * k + 1],
+                                        __uint_as_float(vc[b][2]) + S.w[kOffB2c + 4 * k + 2], 0.f);
+                        reinterpret_cast<float4 *>(dst + 64 + 8 * k)[0] =
+                            make_float4(__uint_as_float(vv[b][0]) + S.w[kOffB2v + 8 * k + 0],
+                                        __uint_as_float(vv[b][1]) + S.w[kOffB2v + 8 * k + 1],
+                                        __uint_as_float(vv[b][2]) + S.w[kOffB2v + 8 * k + 2],
+                                        __uint_as_float(vv[b][3]) + S.w[kOffB2v + 8 * k + 3]);
+                        reinterpret_cast<float4 *>(dst + 64 + 8 * k)[1] =
+                            make_float4(__uint_as_float(vv[b][4]) + S.w[kOffB2v + 8 * k + 4],
+                                        __uint_as_float(vv[b][5]) + S.w[kOffB2v + 8 * k + 5],
+                                        __uint_as_float(vv[b][6]) + S.w[kOffB2v + 8 * k + 6], 0.f);
                     }
                     if (keepbits & (1u << j)) {
                         const uint32_t p = pos++;
@@ -528,6 +583,12 @@ extern "C" int cgs_neural_gaussians_umma_forward(const float *packed_weights, co
                                                  stream);
 }
 
+static int launch_g1(const char *func, const float *packed_weights, const int32_t *vis_idx, int Nv, const int32_t *nv_dev,
+                     int64_t out_cap, const float *anchor, const float *feat, const float *offsets, const float *scaling,
+                     const float *mask, const float *campos_host, float *o_xyz, float *o_color, float *o_opacity,
+                     float *o_scaling, float *o_rot, float *o_neural_opacity, uint8_t *o_mask, int32_t *count_dev,
+                     void *workspace, size_t workspace_bytes, void *stream, const ngu::SaveOut &save);
+
 extern "C" int cgs_neural_gaussians_umma_forward_dev(const float *packed_weights, const int32_t *vis_idx, int Nv,
                                                      const int32_t *nv_dev, int64_t out_cap, const float *anchor,
                                                      const float *feat, const float *offsets, const float *scaling,
@@ -535,6 +596,36 @@ extern "C" int cgs_neural_gaussians_umma_forward_dev(const float *packed_weights
                                                      float *o_color, float *o_opacity, float *o_scaling, float *o_rot,
                                                      float *o_neural_opacity, uint8_t *o_mask, int32_t *count_dev,
                                                      void *workspace, size_t workspace_bytes, void *stream)
+{
+    return launch_g1(__func__, packed_weights, vis_idx, Nv, nv_dev, out_cap, anchor, feat, offsets, scaling, mask,
+                     campos_host, o_xyz, o_color, o_opacity, o_scaling, o_rot, o_neural_opacity, o_mask, count_dev, workspace,
+                     workspace_bytes, stream, ngu::SaveOut{nullptr, nullptr, nullptr, nullptr, nullptr});
+}
+
+extern "C" int cgs_neural_gaussians_umma_forward_train(const float *packed_weights, const int32_t *vis_idx, int Nv,
+                                                       const float *anchor, const float *feat, const float *offsets,
+                                                       const float *scaling, const float *mask, const float *campos_host,
+                                                       float *o_xyz, float *o_color, float *o_opacity, float *o_scaling,
+                                                       float *o_rot, float *o_neural_opacity, uint8_t *o_mask,
+                                                       int32_t *count_dev, float *save_h, uint32_t *save_hmask,
+                                                       float *save_pre2, uint32_t *save_rowpos, uint32_t *save_tilebase,
+                                                       void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (Nv > 0) {
+        CGS_CHECK_PTR(o_neural_opacity); CGS_CHECK_PTR(o_mask); CGS_CHECK_PTR(save_h); CGS_CHECK_PTR(save_hmask);
+        CGS_CHECK_PTR(save_pre2); CGS_CHECK_PTR(save_rowpos); CGS_CHECK_PTR(save_tilebase);
+    }
+    return launch_g1(__func__, packed_weights, vis_idx, Nv, nullptr, (int64_t)Nv * ngu::kK, anchor, feat, offsets, scaling,
+                     mask, campos_host, o_xyz, o_color, o_opacity, o_scaling, o_rot, o_neural_opacity, o_mask, count_dev,
+                     workspace, workspace_bytes, stream,
+                     ngu::SaveOut{save_h, save_hmask, save_pre2, save_rowpos, save_tilebase});
+}
+
+static int launch_g1(const char *func, const float *packed_weights, const int32_t *vis_idx, int Nv, const int32_t *nv_dev,
+                     int64_t out_cap, const float *anchor, const float *feat, const float *offsets, const float *scaling,
+                     const float *mask, const float *campos_host, float *o_xyz, float *o_color, float *o_opacity,
+                     float *o_scaling, float *o_rot, float *o_neural_opacity, uint8_t *o_mask, int32_t *count_dev,
+                     void *workspace, size_t workspace_bytes, void *stream, const ngu::SaveOut &save)
 {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CGS_CHECK_PTR(count_dev);
@@ -577,15 +668,23 @@ extern "C" int cgs_neural_gaussians_umma_forward_dev(const float *packed_weights
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(neural_gaussians_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(neural_gaussians_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(ngu::Smem));
+        cudaFuncSetAttribute(neural_gaussians_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(ngu::Smem));
         if (sm_count <= 0) sm_count = kNumSMs;
     }
     const int grid = tiles < sm_count ? tiles : sm_count;
     StageScope sc(ST_G1_FWD, st, 1);
-    neural_gaussians_umma_kernel<<<grid, ngu::kThreads, sizeof(ngu::Smem), st>>>(
-        packed_weights, vis_idx, Nv, nv_dev, (uint32_t)out_cap, anchor, feat, offsets, scaling, mask, campos_host[0],
-        campos_host[1], campos_host[2], o_xyz, o_color, o_opacity, o_scaling, o_rot, o_neural_opacity, o_mask, scan_state,
-        ctrl, count_dev);
-    return check_launch(__func__);
+    if (save.h)
+        neural_gaussians_umma_kernel<true><<<grid, ngu::kThreads, sizeof(ngu::Smem), st>>>(
+            packed_weights, vis_idx, Nv, nv_dev, (uint32_t)out_cap, anchor, feat, offsets, scaling, mask, campos_host[0],
+            campos_host[1], campos_host[2], o_xyz, o_color, o_opacity, o_scaling, o_rot, o_neural_opacity, o_mask,
+            scan_state, ctrl, count_dev, save);
+    else
+        neural_gaussians_umma_kernel<false><<<grid, ngu::kThreads, sizeof(ngu::Smem), st>>>(
+            packed_weights, vis_idx, Nv, nv_dev, (uint32_t)out_cap, anchor, feat, offsets, scaling, mask, campos_host[0],
+            campos_host[1], campos_host[2], o_xyz, o_color, o_opacity, o_scaling, o_rot, o_neural_opacity, o_mask,
+            scan_state, ctrl, count_dev, save);
+    return check_launch(func);
 }

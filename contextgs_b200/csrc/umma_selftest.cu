@@ -267,8 +267,8 @@ extern "C" int cgs_umma_selftest_ss_mn(const float *P, const float *Q, int M, in
                                        void *stream)
 {
     CGS_CHECK_PTR(P); CGS_CHECK_PTR(Q); CGS_CHECK_PTR(D); CGS_CHECK_PTR(err);
-    if (M < 1 || M > 128 || N < 16 || N > 160 || (N % 16) || variant < 0 || variant > 1) {
-        set_error("%s: need 1 <= M <= 128, 16 <= N <= 160 (N %% 16 == 0), variant 0 / 1", __func__);
+    if (M < 1 || M > 128 || N < 16 || N > 48 || (N % 16) || variant < 0 || variant > 1) {
+        set_error("%s: need 1 <= M <= 128, 16 <= N <= 48 (N %% 16 == 0), variant 0 / 1", __func__);
         return -2;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -109,6 +109,51 @@ def g1_impl():
     return v
 
 
+def g1_bwd_impl():
+    """'umma' (tcgen05 data- and weight-gradient kernels fed by what the training-mode forward saves; default with the
+    tcgen05 forward) or 'simt' (fp32 FMA kernel that recomputes the forward; kept for cross-checks)."""
+    import os
+    v = os.environ.get("CGS_G1_BWD_IMPL", "umma" if g1_impl() == "umma" else "simt")
+    if v not in ("umma", "simt"):
+        raise ValueError("CGS_G1_BWD_IMPL must be 'umma' or 'simt'")
+    if v == "umma" and g1_impl() != "umma":
+        raise ValueError("CGS_G1_BWD_IMPL=umma needs the tcgen05 forward (CGS_G1_IMPL=umma): it consumes its saved activations")
+    return v
+
+
+def pack_decoder_weights_bwd_umma(pc):
+    """Transposed B operands of the tcgen05 data-gradient kernel (csrc/neural_gaussians_bwd_umma.cu `ngbu::kOff*`):
+    per head W2^T as [hidden 64][K = padded output layout of the forward], then W1^T as [input 64][K = 192 hidden
+    columns (head h at 64h)], each split into TF32 hi / lo.  Cached per parameter version."""
+    mods = (pc.get_opacity_mlp, pc.get_color_mlp, pc.get_cov_mlp)
+    params = [p for m in mods for p in (m[0].weight, m[2].weight)]
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    cache = _lib.object_cache(pc)
+    ent = cache.get("decoder_pack_bwd_umma")
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    with torch.no_grad():
+        dev = params[0].device
+        K = pc.n_offsets
+        ko = torch.arange(K, device=dev)
+        rows_o = 8 * (ko // 5) + ko % 5
+        rows_c = (4 * ko.view(K, 1) + torch.arange(3, device=dev).view(1, 3)).reshape(-1)
+        rows_v = (8 * ko.view(K, 1) + torch.arange(7, device=dev).view(1, 7)).reshape(-1)
+        parts = []
+        for m, rows, k_pad in zip(mods, (rows_o, rows_c, rows_v), (16, 48, 80)):
+            B = torch.zeros(50, k_pad, device=dev)
+            B[:, rows] = m[2].weight.t()                      # B[j][padded(n)] = W2[n][j]
+            parts += list(umma_b_operand(B, 64, k_pad))
+        B1 = torch.zeros(54, 192, device=dev)
+        for h, m in enumerate(mods):
+            B1[:, 64 * h:64 * h + 50] = m[0].weight.t()       # B[i][64h + u] = W1_h[u][i] (TMEM head stride 64)
+        parts += list(umma_b_operand(B1, 64, 192))
+        packed = torch.cat(parts).float().contiguous()
+    assert packed.numel() == _lib.lib().cgs_neural_gaussians_bwd_umma_packed_floats()
+    cache["decoder_pack_bwd_umma"] = (key, packed)
+    return packed
+
+
 def compact_indices(mask):
     """Order-preserving device-side `nonzero` of a bool/uint8 mask -> (idx[int32, capacity N], count_dev)."""
     L = _lib.lib()
@@ -123,7 +168,7 @@ def compact_indices(mask):
 
 
 def generate_raw(pc, camera_center, anchor, feat, grid_offsets, grid_scaling, binary_grid_masks, vis_idx=None,
-                 n_vis=None, impl=None, nv_dev=None, out_cap=None):
+                 n_vis=None, impl=None, nv_dev=None, out_cap=None, save=False):
     """Launch the fused kernel.  Inputs are the FULL per-anchor arrays plus an optional visible-index
     list; returns capacity-sized outputs and the device-side Gaussian count.
     nv_dev / out_cap (tcgen05 kernel only): the visible-anchor count stays on the device (n_vis is then the
@@ -165,6 +210,25 @@ def generate_raw(pc, camera_center, anchor, feat, grid_offsets, grid_scaling, bi
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     from .rasterizer import _host_floats
     campos = (ctypes.c_float * 3)(*_host_floats(camera_center, 3))
+    if save:
+        # training mode with the tcgen05 backward: the forward leaves its activations behind (1.3 kB / visible anchor)
+        if impl != "umma":
+            raise ValueError("saved activations are produced by the tcgen05 forward only")
+        tiles = (max(Nv, 1) + 127) // 128
+        i32 = torch.int32
+        sv = dict(h=torch.empty((max(Nv, 1), 176), dtype=f32, device=dev), hmask=torch.empty((max(Nv, 1), 6), dtype=i32, device=dev),
+                  pre2=torch.empty((max(Nv, 1), 144), dtype=f32, device=dev),
+                  rowpos=torch.empty((max(Nv, 1), 2), dtype=i32, device=dev), tilebase=torch.empty((tiles,), dtype=i32, device=dev))
+        _lib.check(L.cgs_neural_gaussians_umma_forward_train(
+            _lib.ptr(packed), _lib.ptr(vis_idx), Nv, _lib.ptr(anchor.contiguous()), _lib.ptr(feat.contiguous()),
+            _lib.ptr(grid_offsets.contiguous()), _lib.ptr(grid_scaling.contiguous()), _lib.ptr(binary_grid_masks.contiguous()),
+            campos, _lib.ptr(out["xyz"]), _lib.ptr(out["color"]), _lib.ptr(out["opacity"]), _lib.ptr(out["scaling"]),
+            _lib.ptr(out["rot"]), _lib.ptr(out["neural_opacity"]), _lib.ptr(out["mask"]), _lib.ptr(out["count"]),
+            _lib.ptr(sv["h"]), _lib.ptr(sv["hmask"]), _lib.ptr(sv["pre2"]), _lib.ptr(sv["rowpos"]), _lib.ptr(sv["tilebase"]),
+            _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "cgs_neural_gaussians_umma_forward_train")
+        out["n_vis"] = Nv
+        out["save"] = sv
+        return out
     _lib.check(fn(
         _lib.ptr(packed), _lib.ptr(vis_idx), Nv, _lib.ptr(anchor.contiguous()),
         _lib.ptr(feat.contiguous()), _lib.ptr(grid_offsets.contiguous()), _lib.ptr(grid_scaling.contiguous()),
@@ -229,12 +293,17 @@ class _NeuralGaussians(torch.autograd.Function):
         K = pc.n_offsets
         a, f, o = anchor.detach().contiguous(), feat.detach().contiguous(), offsets.detach().reshape(N, -1).contiguous()
         sc, m = scaling.detach().contiguous(), mask.detach().reshape(N, -1).contiguous()
-        raw = generate_raw(pc, campos, a, f, o, sc, m, vis_idx=vis_idx, n_vis=n_vis)
+        need_grad = any(ctx.needs_input_grad)
+        ctx.bwd_impl = g1_bwd_impl() if need_grad else "simt"
+        raw = generate_raw(pc, campos, a, f, o, sc, m, vis_idx=vis_idx, n_vis=n_vis,
+                           save=(ctx.bwd_impl == "umma" and n_vis > 0))
         P = int(raw["count"].item())  # the reference synchronises here too (boolean indexing, :119,136)
         if P < 0:
             raise _lib.CgsError("cgs_neural_gaussians_umma_forward: a tensor-core completion barrier timed out")
+        _lib.raise_deferred()   # error flags of earlier backward kernels (the read-back above has synchronised)
         ctx.pc, ctx.campos, ctx.n_vis, ctx.P = pc, campos, n_vis, P
         ctx.shapes = (offsets.shape, mask.shape)
+        ctx.saved_act = raw.get("save")
         ctx.save_for_backward(a, f, o, sc, m, vis_idx, raw["mask"])
         nop = raw["neural_opacity"][:n_vis * K]
         keep = raw["mask"][:n_vis * K]
@@ -254,9 +323,25 @@ class _NeuralGaussians(torch.autograd.Function):
             c = lambda g, shape: (torch.zeros(shape, device=dev) if g is None else g.contiguous().float())
             g_xyz, g_color, g_scaling = c(g_xyz, (P, 3)), c(g_color, (P, 3)), c(g_scaling, (P, 3))
             g_opacity, g_rot = c(g_opacity, (P, 1)), c(g_rot, (P, 4))
-            ws = torch.empty((L.cgs_neural_gaussians_backward_workspace_bytes(n_vis),), dtype=torch.uint8, device=dev)
             from .rasterizer import _host_floats
             campos = (ctypes.c_float * 3)(*_host_floats(ctx.campos, 3))
+            sv = ctx.saved_act
+        if P > 0 and n_vis > 0 and sv is not None:
+            # tcgen05 path: data gradients + weight gradients from the saved activations (csrc/neural_gaussians_bwd_umma.cu)
+            d_out = torch.empty((n_vis, 144), dtype=torch.float32, device=dev)
+            d_pre = torch.empty((n_vis, 176), dtype=torch.float32, device=dev)
+            err = torch.zeros(1, dtype=torch.int32, device=dev)
+            _lib.check(L.cgs_neural_gaussians_backward_umma(
+                _lib.ptr(pack_decoder_weights_bwd_umma(pc)), _lib.ptr(vis_idx), n_vis, _lib.ptr(a), _lib.ptr(f), _lib.ptr(o),
+                _lib.ptr(sc), _lib.ptr(m), campos, _lib.ptr(keep), _lib.ptr(sv["h"]), _lib.ptr(sv["hmask"]),
+                _lib.ptr(sv["pre2"]), _lib.ptr(sv["rowpos"]), _lib.ptr(sv["tilebase"]), _lib.ptr(g_xyz), _lib.ptr(g_color),
+                _lib.ptr(g_opacity), _lib.ptr(g_scaling), _lib.ptr(g_rot), _lib.ptr(d_a), _lib.ptr(d_f), _lib.ptr(d_o),
+                _lib.ptr(d_sc), _lib.ptr(d_m), _lib.ptr(d_w), _lib.ptr(d_out), _lib.ptr(d_pre), _lib.ptr(err),
+                _lib.stream_ptr()), "cgs_neural_gaussians_backward_umma")
+            ctx.saved_act = None
+            _lib.deferred_error_check(err, "cgs_neural_gaussians_backward_umma: a tensor-core completion barrier timed out")
+        elif P > 0 and n_vis > 0:
+            ws = torch.empty((L.cgs_neural_gaussians_backward_workspace_bytes(n_vis),), dtype=torch.uint8, device=dev)
             _lib.check(L.cgs_neural_gaussians_backward(
                 _lib.ptr(pack_decoder_weights(pc)), _lib.ptr(pack_decoder_weights_transposed(pc)), _lib.ptr(vis_idx),
                 n_vis, _lib.ptr(a), _lib.ptr(f), _lib.ptr(o), _lib.ptr(sc), _lib.ptr(m), campos, _lib.ptr(keep),

@@ -92,7 +92,7 @@ CGS_API int cgs_umma_selftest_ss(const float *P, const float *Q, int M, int N, i
                                  void *stream);
 /* The same contraction with both operands in the MN-major no-swizzle layout ([feature / 4][row][4 floats]: one
  * float4 store per four features of a row).  variant 0: SBO = stride between 4-feature groups, LBO = stride
- * between 8-row groups; variant 1: swapped.  N <= 160. */
+ * between 8-row groups; variant 1: swapped.  N <= 48. */
 CGS_API int cgs_umma_selftest_ss_mn(const float *P, const float *Q, int M, int N, int variant, float *D, int32_t *err,
                                     void *stream);
 
@@ -209,6 +209,43 @@ CGS_API int cgs_neural_gaussians_umma_forward(const float *packed_weights, const
                                               float *o_rot, float *o_neural_opacity, uint8_t *o_mask,
                                               int32_t *count_dev, void *workspace, size_t workspace_bytes,
                                               void *stream);
+
+/* Training-mode variant of cgs_neural_gaussians_umma_forward: identical outputs, and additionally leaves behind what
+ * the tcgen05 backward consumes, per visible row r: save_h[Nv,176] hidden activations (head h at column 56h),
+ * save_hmask[Nv,6] their sign bits, save_pre2[Nv,144] layer-2 pre-activations (opacity 16 | colour 48 | covariance 80),
+ * save_rowpos[Nv,2] tile-local rank of the first kept Gaussian of (row, half), save_tilebase[ceil(Nv/128)] rank of
+ * each tile's first Gaussian (cgs_neural_gaussians_save_floats(0..4) returns 176, 6, 144, 2, 128). */
+CGS_API int cgs_neural_gaussians_save_floats(int what);
+CGS_API int cgs_neural_gaussians_umma_forward_train(const float *packed_weights, const int32_t *vis_idx, int Nv,
+                                                    const float *anchor, const float *feat, const float *offsets,
+                                                    const float *scaling, const float *mask, const float *campos_host,
+                                                    float *o_xyz, float *o_color, float *o_opacity, float *o_scaling,
+                                                    float *o_rot, float *o_neural_opacity, uint8_t *o_mask,
+                                                    int32_t *count_dev, float *save_h, uint32_t *save_hmask,
+                                                    float *save_pre2, uint32_t *save_rowpos, uint32_t *save_tilebase,
+                                                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward on the tcgen05 tensor cores (csrc/neural_gaussians_bwd_umma.cu), same gradients and conventions as
+ * cgs_neural_gaussians_backward below (reference: autograd through gaussian_renderer/__init__.py:106-145 and
+ * scene/gaussian_model.py:153-174), fed by the activations cgs_neural_gaussians_umma_forward_train saved: a
+ * data-gradient kernel (dOut -> dH -> dX, 3xTF32, TMEM resident) and a weight-gradient kernel (SS-form MMAs with the
+ * row index as the contraction, accumulators resident in TMEM across a persistent CTA).  packed_bwd:
+ * cgs_neural_gaussians_bwd_umma_packed_floats() floats (contextgs_b200/neural_gaussians.py
+ * pack_decoder_weights_bwd_umma).  scratch_dout[Nv,144], scratch_dpre[Nv,176]: hand-over between the two kernels.
+ * *err (device, caller-zeroed) is set to 1 if a tensor-core completion barrier timed out. */
+CGS_API int cgs_neural_gaussians_bwd_umma_packed_floats(void);
+/* Diagnostic switches (tests only).  key 0: descriptor variant (0 / 1) of the weight-gradient kernel's MN-major operands. */
+CGS_API int cgs_debug_set(int key, int value);
+CGS_API int cgs_neural_gaussians_backward_umma(const float *packed_bwd, const int32_t *vis_idx, int Nv,
+                                               const float *anchor, const float *feat, const float *offsets,
+                                               const float *scaling, const float *mask, const float *campos_host,
+                                               const uint8_t *keep_mask, const float *save_h, const uint32_t *save_hmask,
+                                               const float *save_pre2, const uint32_t *save_rowpos,
+                                               const uint32_t *save_tilebase, const float *g_xyz, const float *g_color,
+                                               const float *g_opacity, const float *g_scaling, const float *g_rot,
+                                               float *d_anchor, float *d_feat, float *d_offsets, float *d_scaling,
+                                               float *d_mask, float *d_packed_fwd, float *scratch_dout,
+                                               float *scratch_dpre, int32_t *err, void *stream);
 
 /* Backward of the two entry points above = what autograd does for gaussian_renderer/__init__.py:106-145
  * plus scene/gaussian_model.py:153-174 in the reference (SURVEY 8a row T1 lists the gradients train.py

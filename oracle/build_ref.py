@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE.  Byte-compiles the reference's OWN Python modules of the hot path, from the sources where they
-lie under /root/reference, into oracle/_ref/*.pyc (git-ignored, travels to the GPU box like a built .so).  No reference
+lie under /root/reference, into oracle/_ref/*.refbin (git-ignored, travels to the GPU box like a built .so).  No reference
 source is copied into the repository: only code objects produced by this recipe, and only in this container (the GPU
 box has no /root/reference and uses the prebuilt files).
 
@@ -38,7 +38,7 @@ def build(verbose=False):
     done = []
     for name, rel in MODULES.items():
         src = os.path.join(REF, rel)
-        dst = os.path.join(OUT, name + ".pyc")
+        dst = os.path.join(OUT, name + ".refbin")
         if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
             py_compile.compile(src, cfile=dst, dfile=f"reference:{rel}", doraise=True)
         done.append(dst)

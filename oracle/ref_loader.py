@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE.  Loads the reference's own modules from the code objects oracle/build_ref.py produced
-(oracle/_ref/*.pyc) and wires their third-party imports:
+(oracle/_ref/*.refbin) and wires their third-party imports:
 
   diff_gaussian_rasterization -> contextgs_b200.dropin.diff_gaussian_rasterization   (the thing under test)
   simple_knn._C               -> contextgs_b200.dropin.simple_knn._C
@@ -26,7 +26,7 @@ ORDER = ["utils.general_utils", "utils.graphics_utils", "utils.system_utils", "u
 
 
 def available():
-    return all(os.path.exists(os.path.join(OUT, n + ".pyc")) for n in ORDER)
+    return all(os.path.exists(os.path.join(OUT, n + ".refbin")) for n in ORDER)
 
 
 class EntropyBottleneckTorch(nn.Module):
@@ -101,7 +101,7 @@ def load():
     if _loaded is not None:
         return _loaded
     if not available():
-        raise FileNotFoundError("oracle/_ref/*.pyc missing: run `python -m oracle.build_ref` where /root/reference exists")
+        raise FileNotFoundError("oracle/_ref/*.refbin missing: run `python -m oracle.build_ref` where /root/reference exists")
     _stub("torchac")
     _stub("plyfile", PlyData=object, PlyElement=object)
     _stub("torch_scatter", scatter_max=_not_on_path("torch_scatter.scatter_max"))
@@ -124,7 +124,7 @@ def load():
             m._cgs_ref_pkg = True
     mods = {}
     for name in ORDER:
-        with open(os.path.join(OUT, name + ".pyc"), "rb") as f:
+        with open(os.path.join(OUT, name + ".refbin"), "rb") as f:
             f.read(16)                      # magic, flags, mtime, size (PEP 552 header)
             code = marshal.load(f)
         m = types.ModuleType(name)

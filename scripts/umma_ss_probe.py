@@ -25,7 +25,7 @@ for M, N in ((110, 64), (128, 48), (16, 16), (75, 32)):
         rel = float((D.double() - ref).norm() / ref.norm())
         print(f"M={M} N={N} skew={skew}: timeout={int(err)} rel-L2={rel:.3e}")
 
-for M, N in ((110, 160), (54, 160), (128, 48), (16, 16)):
+for M, N in ((110, 48), (54, 32), (128, 48), (16, 16)):
     for variant in (0, 1):
         g = torch.Generator().manual_seed(M * 100 + N)
         P = torch.randn(128, M, generator=g).cuda()

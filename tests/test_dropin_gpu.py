@@ -3,7 +3,7 @@
 (scene/gaussian_model.py:46-345) run here against `contextgs_b200/dropin/diff_gaussian_rasterization`, and their
 outputs are compared with contextgs_b200.renderer on the same scene, camera and weights.
 
-The reference code comes from oracle/_ref/*.pyc (code objects byte-compiled from /root/reference by
+The reference code comes from oracle/_ref/*.refbin (code objects byte-compiled from /root/reference by
 oracle/build_ref.py in the build container; no reference source is in the repository and /root/reference is not
 read at run time).  Third-party stand-ins are listed in oracle/ref_loader.py."""
 import numpy as np
@@ -18,7 +18,7 @@ from oracle import ref_loader
 from tests.helpers import rel_l2
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not ref_loader.available(), reason="oracle/_ref/*.pyc not built (python -m oracle.build_ref)")]
+              pytest.mark.skipif(not ref_loader.available(), reason="oracle/_ref/*.refbin not built (python -m oracle.build_ref)")]
 
 N, W, H = 50_000, 800, 800     # BASELINE configs[0] size
 
