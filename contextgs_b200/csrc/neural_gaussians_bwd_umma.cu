@@ -15,9 +15,10 @@
 //       M2  dX = dPre W1 (K = 176, N = 64)
 //       E3  d_feat, d_anchor (view direction / distance), d_scaling
 //   kernel 2  neural_gaussians_wgrad_umma_kernel   (weight gradients; the contraction runs over the ROWS)
-//       dW2_h^T = dOut_h^T H_h and dW1^T = X^T dPre as SS-form tcgen05.mma with both operands in the MN-major
-//       no-swizzle layout ([feature / 4][row][4 floats]: every thread stores float4s, conflict free), 3xTF32,
-//       accumulators resident in TMEM over all slabs of a persistent CTA, one flush (atomicAdd) per CTA.
+//       dW2_h^T = dOut_h^T H_h and dW1^T = X^T dPre as SS-form tcgen05.mma with the ROW index playing K: both operands
+//       in the K-major no-swizzle core-matrix layout [row / 4][feature][4 rows] (leading dimension = 1 mod 8 features:
+//       conflict-free scalar stores), 3xTF32, accumulators resident in TMEM over all slabs of a persistent CTA, one
+//       flush (atomicAdd) per CTA.  (The MN-major descriptor form returned zeros in a probe on B200 and is not used.)
 //       Bias gradients ride along: a constant-one column in the padding of X (-> db1) and of every head of H (-> db2).
 //
 // TMEM columns of kernel 1 (480 of 512):
@@ -338,20 +339,21 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// kernel 2: weight gradients.  Per slab of kSlab visible rows the CTA stages, split into TF32 hi / lo and in the
-// MN-major layout [group of 4 features][row][4 floats]:
-//     X    14 groups  layer-1 input  [feat 50 | view 3 | dist | 1 | 0]      (the 1 makes row 54 of dW1^T the bias gradient)
-//     dOut 36 groups  (kernel 1)
-//     H    44 groups  (forward), with a 1 in column 56h + 55 of every head (-> db2 in column 55 of dW2_h^T)
-//     dPre 44 groups  (kernel 1)
-// and issues   D_h[out, hid] += dOut_h^T H_h  (M = 128 from group {0, 4, 16} of dOut, N = 64 from group 14h of H)
-//              D_x[in,  hid] += X^T dPre      (M = 128 from group 0 of X,  N = 176).
-// An M = 128 operand that is narrower than 128 features simply runs on into the next array (finite values, their
+// kernel 2: weight gradients.  Per slab of kSlab visible rows the CTA stages, split into TF32 hi / lo, the features
+//     X    56  layer-1 input  [feat 50 | view 3 | dist | 1 | 0]      (the 1 makes row 54 of dW1^T the bias gradient)
+//     dOut 144 (kernel 1)
+//     H    176 (forward), with a 1 in column 56h + 55 of every head (-> db2 in column 55 of dW2_h^T)
+//     dPre 176 (kernel 1)
+// as ONE K-major operand block [row / 4][feature (kLd = 553)][row % 4] and issues, per 8 rows,
+//     D_h[out, hid] += dOut_h^T H_h  (M = 128 from feature {56, 72, 120}, N = 64 from feature 200 + 56h)
+//     D_x[in,  hid] += X^T dPre      (M = 128 from feature 0,             N = 176 from feature 376).
+// An M = 128 operand that is narrower than 128 features simply runs on into the next features (finite values, their
 // accumulator lanes are never read).  TMEM: D_o | D_c | D_v at columns 0 / 64 / 128, D_x at [192,368).
 namespace ngwu {
 constexpr int kThreads = 256, kSlab = 16;
-constexpr int kGX = 14, kGO = 36, kGH = 44, kGP = 44, kGroups = kGX + kGO + kGH + kGP;   // 138
+constexpr int kGX = 14, kGO = 36, kGH = 44, kGP = 44, kGroups = kGX + kGO + kGH + kGP;   // float4 groups per row: 138
 constexpr int kOffX = 0, kOffO = kGX, kOffH = kOffO + kGO, kOffP = kOffH + kGH;
+constexpr int kLd = 4 * kGroups + 1;      // 553 features per 4-row chunk: = 1 (mod 8) spreads the chunks over the banks
 constexpr uint32_t kColDo = 0, kColDc = 64, kColDv = 128, kColDx = 192, kTmemCols = 512;
 // forward-layout weight block of the SIMT kernels (contextgs_b200/neural_gaussians.py pack_decoder_weights): the
 // gradient is returned in this layout
@@ -361,8 +363,9 @@ constexpr int kOffW2c = kOffB2o + kLdO, kOffB2c = kOffW2c + 50 * kLdC, kOffW2v =
 constexpr int kOffB2v = kOffW2v + 50 * kLdV;
 
 struct Buf {
-    float4 hi[kGroups * kSlab];
-    float4 lo[kGroups * kSlab];
+    float hi[(kSlab / 4) * kLd * 4];     // [row / 4][feature][row % 4]
+    float lo[(kSlab / 4) * kLd * 4];
+    float pad[8];
 };
 struct Smem {
     Buf buf[2];
@@ -397,12 +400,10 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
     umma::fence_after_thread_sync();
     const uint32_t tbase = S.tmem;
 
-    const uint32_t idesc64 = umma::idesc_tf32(128, 64) | (1u << 15) | (1u << 16);     // A and B MN-major
-    const uint32_t idesc176 = umma::idesc_tf32(128, 176) | (1u << 15) | (1u << 16);
-    // MN-major no-swizzle: SBO = stride between 4-feature groups, LBO = stride between 8-row groups (variant 0, CUTLASS
-    // make_umma_desc<Major::MN>); variant 1 swaps the two fields (diagnostic switch, cgs_debug_set(0, v))
-    const uint32_t grp = (uint32_t)kSlab * 16u;
-    const uint32_t sbo = desc_variant == 0 ? grp : 128u, lbo = desc_variant == 0 ? 128u : grp;
+    const uint32_t idesc64 = umma::idesc_tf32(128, 64), idesc176 = umma::idesc_tf32(128, 176);
+    // K-major no-swizzle: LBO = stride between the two 4-row chunks of one K = 8 step, SBO = stride between 8-feature groups
+    const uint32_t lbo = (uint32_t)kLd * 16u, sbo = 128u;
+    (void)desc_variant;
 
     uint32_t it = 0;
     for (int slab = blockIdx.x; slab < num_slabs; slab += gridDim.x, ++it) {
@@ -452,10 +453,17 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
             umma::split_tf32(v.y, h[1], l[1]);
             umma::split_tf32(v.z, h[2], l[2]);
             umma::split_tf32(v.w, h[3], l[3]);
-            B.hi[c * kSlab + r] = make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]),
-                                              __uint_as_float(h[3]));
-            B.lo[c * kSlab + r] = make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]),
-                                              __uint_as_float(l[3]));
+            const int dst = ((r >> 2) * kLd + 4 * c) * 4 + (r & 3);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                B.hi[dst + 4 * j] = __uint_as_float(h[j]);
+                B.lo[dst + 4 * j] = __uint_as_float(l[j]);
+            }
+        }
+        if (tid < (kSlab / 4) * 4) {   // the skew feature (index 552) of every chunk: read by nobody's valid lane, keep it finite
+            const int dst = ((tid >> 2) * kLd + 4 * kGroups) * 4 + (tid & 3);
+            B.hi[dst] = 0.f;
+            B.lo[dst] = 0.f;
         }
         umma::fence_proxy_async_smem();
         umma::fence_before_thread_sync();
@@ -463,8 +471,8 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
         if (tid == 0) {
             umma::fence_after_thread_sync();
             const uint32_t hi = umma::smem_u32(B.hi), lo = umma::smem_u32(B.lo);
-            auto desc = [&](uint32_t base, int group, int kstep) {
-                return umma::smem_desc_kmajor(base + (uint32_t)group * grp + (uint32_t)kstep * 128u, lbo, sbo);
+            auto desc = [&](uint32_t base, int group, int kstep) {   // operand starting at float4 group `group`, rows 8 kstep ..
+                return umma::smem_desc_kmajor(base + (uint32_t)kstep * 2u * lbo + (uint32_t)group * 64u, lbo, sbo);
             };
             const uint32_t acc0 = it > 0 ? 1u : 0u;
 #pragma unroll

@@ -62,3 +62,19 @@ def reference_noise(N, level_sizes, seed=7, K=10):
         levels.append(torch.cat([f, s, o.reshape(n, 3 * K)], dim=1))
     choose = torch.rand(N) <= 0.15
     return dict(eb=eb.reshape(12, N).t().contiguous(), levels=levels, choose=choose)
+
+
+def rel_l2_rows(a, b, row_tol=1e-3):
+    """(fraction of outlier rows, rel-L2 over the other rows).  For gradients that pass through a ReLU: two valid fp32
+    evaluations of the hidden layer (cuBLAS / fp32 FMA vs 3xTF32 tensor cores) can put a pre-activation that is zero to
+    rounding on different sides of the kink, which changes the gradient of THAT anchor row by O(1/sqrt(units)) while
+    every other row agrees to rounding.  Rows are compared one by one; a row is an outlier when its own relative error
+    exceeds `row_tol`."""
+    a = np.asarray(a, np.float64).reshape(a.shape[0], -1)
+    b = np.asarray(b, np.float64).reshape(b.shape[0], -1)
+    num = np.linalg.norm(a - b, axis=1)
+    den = np.linalg.norm(b, axis=1)
+    scale = np.sqrt((den ** 2).mean()) + 1e-30            # rows that are ~0 in both are judged on the global scale
+    bad = num > row_tol * np.maximum(den, 1e-3 * scale)
+    good = ~bad
+    return float(bad.mean()), float(np.linalg.norm((a - b)[good]) / (np.linalg.norm(b[good]) + 1e-30))

@@ -7,7 +7,7 @@ import torch
 from contextgs_b200 import synthetic
 from contextgs_b200.neural_gaussians import compact_indices, generate_neural_gaussians
 from oracle import entropy_ref as er
-from tests.helpers import T, cuda_model, fixture_model, load_npz, rel_l2
+from tests.helpers import T, cuda_model, fixture_model, load_npz, rel_l2, rel_l2_rows
 
 pytestmark = pytest.mark.gpu
 REL_L2 = 1e-4
@@ -180,7 +180,12 @@ def test_backward_umma_matches_simt_many_tiles(g1_impl, monkeypatch):
     names = [n for n in grads["simt"] if n != "P"]
     assert {"_anchor_feat", "_offset", "_scaling", "_mask", "_anchor"} <= set(names)
     errs = {n: rel_l2(grads["umma"][n].cpu().numpy(), grads["simt"][n].cpu().numpy()) for n in names}
-    print("G1 backward umma vs simt rel-L2:", {k: f"{v:.2e}" for k, v in errs.items()})
+    # d feat passes through the ReLU of the hidden layer, which the two backward kernels evaluate differently (saved
+    # from the 3xTF32 forward vs recomputed in fp32 FMA): compare it row by row (see tests/helpers.rel_l2_rows)
+    outliers, errs["_anchor_feat"] = rel_l2_rows(grads["umma"]["_anchor_feat"].cpu().numpy(),
+                                                 grads["simt"]["_anchor_feat"].cpu().numpy())
+    print("G1 backward umma vs simt rel-L2:", {k: f"{v:.2e}" for k, v in errs.items()}, "feat outlier rows", outliers)
+    assert outliers < 1e-3
     bad = {k: v for k, v in errs.items() if not v < (1e-3 if k == "_anchor" else REL_L2)}
     assert not bad, bad
 
