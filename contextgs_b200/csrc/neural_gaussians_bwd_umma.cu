@@ -5,8 +5,10 @@
 // NOTHING recomputed: the training-mode forward (neural_gaussians_umma.cu, kSave) leaves the hidden activations,
 // their sign bits, the layer-2 pre-activations and the compaction ranks behind (1.3 kB per visible anchor).
 //
-//   kernel 1  neural_gaussians_dgrad_umma_kernel   (data gradients; persistent, 128 anchors per tile, 256 threads,
-//             thread = (row, half) like the forward's BACK group)
+//   kernel 1  neural_gaussians_dgrad_umma_kernel   (data gradients; persistent, 128 anchors per tile, 640 threads:
+//             five threads per row, each owning two of the ten offsets; index-type inputs are fetched one tile ahead and
+//             every other load of a tile is issued before the first use -- the first version, 256 threads with loads
+//             inside the per-offset branches, sat on the DRAM latency with 12 % of the issue slots busy)
 //       E1  gradient of the post-processing per kept (anchor, offset) pair -> dOut[128 x 144] (layer-2 output layout of
 //           the forward: opacity 16 | colour 48 | covariance 80), split hi / lo into TMEM, fp32 copy to HBM for kernel 2;
 //           direct gradients d_offsets, d_mask, partial d_scaling / d_anchor
@@ -29,7 +31,7 @@
 namespace cgs {
 namespace ngbu {
 constexpr int kFeat = 50, kK = 10;
-constexpr int kRows = 128, kThreads = 256;
+constexpr int kRows = 128, kThreads = 640;   // five threads per row
 constexpr int kOutP = 144, kHidP = 176, kInP = 64;
 constexpr int kHidT = 192;                                  // hidden columns in TMEM: head h at 64h (HBM rows: 56h)
 constexpr int kKo = 16, kKc = 48, kKv = 80;                 // K of the three dH GEMMs (= padded head widths)
@@ -45,7 +47,7 @@ constexpr int kPacked = kOffW1TLo + kW1T;                  // 43008 floats = 172
 
 struct Smem {
     float w[kPacked];
-    float part[kRows][10];       // half 0 -> half 1: d_scaling[6] + d_anchor[3] partial sums of the row
+    float part[kRows][5][9];     // per (row, fifth): partial sums of d_scaling[6] + d_anchor[3]
     uint32_t tmem;
     int timeout;
     alignas(8) uint64_t bar[2];
@@ -88,7 +90,7 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = warp >> 2;
+    const int fifth = warp >> 2;                       // five threads per row: offsets 2 * fifth, 2 * fifth + 1
     const int row = 32 * (warp & 3) + lane;
     const int num_tiles = (Nv + kRows - 1) / kRows;
 
@@ -110,25 +112,70 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
     umma::fence_after_thread_sync();
     const uint32_t tbase = S.tmem;
     const uint32_t tl = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
-    const int kbase = 5 * half;
+
+    // index-type inputs of a tile (fetched one tile AHEAD: they feed the addresses of everything else)
+    struct Idx {
+        int a;
+        uint32_t keepbits, pos_h0, pos_h1;
+    };
+    auto load_idx = [&](int tile, Idx &ix) {
+        const int g = tile * kRows + row;
+        ix.a = -1; ix.keepbits = 0; ix.pos_h0 = ix.pos_h1 = 0;
+        if (tile >= num_tiles || g >= Nv) return;
+        ix.a = vis_idx ? __ldg(vis_idx + g) : g;
+        const unsigned short *kp = reinterpret_cast<const unsigned short *>(keep_mask + (size_t)g * kK);   // 10 bytes, 2-byte aligned
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const uint32_t v = __ldg(kp + i);
+            ix.keepbits |= ((v & 0xffu) ? 1u : 0u) << (2 * i) | ((v >> 8) ? 1u : 0u) << (2 * i + 1);
+        }
+        const uint2 rp = __ldg(reinterpret_cast<const uint2 *>(save_rowpos) + g);
+        const uint32_t tb = __ldg(save_tilebase + tile);
+        ix.pos_h0 = tb + rp.x;
+        ix.pos_h1 = tb + rp.y;
+    };
+    Idx nxt;
+    load_idx(blockIdx.x, nxt);
 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t parity = it & 1u;
         const int g = tile * kRows + row;
-        const bool valid = g < Nv;
-        const int a = valid ? (vis_idx ? __ldg(vis_idx + g) : g) : -1;
+        const Idx ix = nxt;
+        const bool valid = ix.a >= 0;
+        const int a = valid ? ix.a : 0;
+        load_idx(tile + (int)gridDim.x, nxt);
 
         // ================= E1: gradient of the post-processing =================
-        float dsc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, danc[3] = {0.f, 0.f, 0.f};
-        float dO[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        float sc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        uint32_t keepbits = 0, pos = 0;
+        // all loads of the thread's two offsets are issued before anything is computed (one DRAM round trip per tile)
+        float gxyz[2][3], off[2][3], gop[2], mk[2], po[2], gcol[2][3], gsc[2][3];
+        float4 pc[2], pa[2], pb[2], grot[2];
+        bool kept[2];
         const float *p2 = save_pre2 + (size_t)(valid ? g : 0) * kOutP;
-        if (valid) {
 #pragma unroll
-            for (int j = 0; j < 5; ++j) keepbits |= keep_mask[(size_t)g * kK + kbase + j] ? (1u << j) : 0u;
-            pos = __ldg(save_tilebase + tile) + __ldg(save_rowpos + (size_t)g * 2 + half);
+        for (int j = 0; j < 2; ++j) {
+            const int k = 2 * fifth + j, hk = k >= 5 ? 1 : 0;
+            kept[j] = (ix.keepbits >> k) & 1u;
+            const uint32_t before = __popc(ix.keepbits & ((1u << k) - 1u) & (hk ? 0x3e0u : 0x01fu));
+            const size_t pos = kept[j] ? (size_t)((hk ? ix.pos_h1 : ix.pos_h0) + before) : 0;
+            const size_t ak = (size_t)a * kK + k;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                gxyz[j][c] = __ldg(g_xyz + 3 * pos + c);
+                off[j][c] = __ldg(offsets + 3 * ak + c);
+                gcol[j][c] = __ldg(g_color + 3 * pos + c);
+                gsc[j][c] = __ldg(g_scaling + 3 * pos + c);
+            }
+            gop[j] = __ldg(g_opacity + pos);
+            mk[j] = __ldg(mask + ak);
+            po[j] = __ldg(p2 + 8 * hk + (k - 5 * hk));
+            pc[j] = __ldg(reinterpret_cast<const float4 *>(p2 + 16 + 4 * k));
+            pa[j] = __ldg(reinterpret_cast<const float4 *>(p2 + 64 + 8 * k));
+            pb[j] = __ldg(reinterpret_cast<const float4 *>(p2 + 64 + 8 * k) + 1);
+            grot[j] = __ldg(reinterpret_cast<const float4 *>(g_rot) + pos);
+        }
+        float sc[6];
+        {
             const float2 *s2 = reinterpret_cast<const float2 *>(scaling + 6 * (size_t)a);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -137,92 +184,97 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
                 sc[2 * i + 1] = v.y;
             }
         }
+        // sign bits of the hidden layer for E2
+        uint32_t hm[6];
+        {
+            const uint2 *m = reinterpret_cast<const uint2 *>(save_hmask + (size_t)(valid ? g : 0) * 6);
+            const uint2 m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2);
+            hm[0] = m0.x; hm[1] = m0.y; hm[2] = m1.x; hm[3] = m1.y; hm[4] = m2.x; hm[5] = m2.y;
+        }
+        float dsc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, danc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const int k = kbase + j;
+        for (int j = 0; j < 2; ++j) {
+            const int k = 2 * fifth + j, hk = k >= 5 ? 1 : 0;
+            const size_t ak = (size_t)a * kK + k;
+            float dO = 0.f;
             float dC[4] = {0.f, 0.f, 0.f, 0.f}, dV[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (keepbits & (1u << j)) {
-                const size_t P3 = 3 * (size_t)pos;
-                const size_t ak = (size_t)a * kK + k;
-                const float gx = __ldg(g_xyz + P3), gy = __ldg(g_xyz + P3 + 1), gz = __ldg(g_xyz + P3 + 2);
-                const float o0 = __ldg(offsets + ak * 3), o1 = __ldg(offsets + ak * 3 + 1), o2 = __ldg(offsets + ak * 3 + 2);
-                d_offsets[ak * 3 + 0] = gx * sc[0];
-                d_offsets[ak * 3 + 1] = gy * sc[1];
-                d_offsets[ak * 3 + 2] = gz * sc[2];
-                danc[0] += gx; danc[1] += gy; danc[2] += gz;
-                dsc[0] += gx * o0; dsc[1] += gy * o1; dsc[2] += gz * o2;
+            if (kept[j] && valid) {
+                d_offsets[ak * 3 + 0] = gxyz[j][0] * sc[0];
+                d_offsets[ak * 3 + 1] = gxyz[j][1] * sc[1];
+                d_offsets[ak * 3 + 2] = gxyz[j][2] * sc[2];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    danc[c] += gxyz[j][c];
+                    dsc[c] += gxyz[j][c] * off[j][c];
+                }
                 // opacity = tanh(pre) * mask
-                const float t = tanhf(__ldg(p2 + 8 * half + j));
-                const float go = __ldg(g_opacity + pos);
-                d_mask[ak] = go * t;
-                dO[j] = go * __ldg(mask + ak) * (1.0f - t * t);
+                const float t = tanhf(po[j]);
+                d_mask[ak] = gop[j] * t;
+                dO = gop[j] * mk[j] * (1.0f - t * t);
                 // colour = sigmoid(pre)
-                const float4 pc = __ldg(reinterpret_cast<const float4 *>(p2 + 16 + 4 * k));
-                const float pcv[3] = {pc.x, pc.y, pc.z};
+                const float pcv[3] = {pc[j].x, pc[j].y, pc[j].z};
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float s = sigmoidf_(pcv[c]);
-                    dC[c] = __ldg(g_color + P3 + c) * s * (1.0f - s);
+                    dC[c] = gcol[j][c] * s * (1.0f - s);
                 }
                 // scaling = sc[3:6] * sigmoid(pre[0:3]); rot = normalize(pre[3:7])
-                const float4 pa = __ldg(reinterpret_cast<const float4 *>(p2 + 64 + 8 * k));
-                const float4 pb = __ldg(reinterpret_cast<const float4 *>(p2 + 64 + 8 * k) + 1);
-                const float pv[3] = {pa.x, pa.y, pa.z};
+                const float pv[3] = {pa[j].x, pa[j].y, pa[j].z};
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float s = sigmoidf_(pv[c]);
-                    const float gs = __ldg(g_scaling + P3 + c);
-                    dsc[3 + c] += gs * s;
-                    dV[c] = gs * sc[3 + c] * s * (1.0f - s);
+                    dsc[3 + c] += gsc[j][c] * s;
+                    dV[c] = gsc[j][c] * sc[3 + c] * s * (1.0f - s);
                 }
-                const float q0 = pa.w, q1 = pb.x, q2 = pb.y, q3 = pb.z;
+                const float q0 = pa[j].w, q1 = pb[j].x, q2 = pb[j].y, q3 = pb[j].z;
                 const float nrm = fmaxf(sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3), 1e-12f);
-                const float4 gr = __ldg(reinterpret_cast<const float4 *>(g_rot) + pos);
                 const float r0 = q0 / nrm, r1 = q1 / nrm, r2 = q2 / nrm, r3 = q3 / nrm;
-                const float dot = r0 * gr.x + r1 * gr.y + r2 * gr.z + r3 * gr.w;
-                dV[3] = (gr.x - r0 * dot) / nrm;
-                dV[4] = (gr.y - r1 * dot) / nrm;
-                dV[5] = (gr.z - r2 * dot) / nrm;
-                dV[6] = (gr.w - r3 * dot) / nrm;
-                ++pos;
+                const float dot = r0 * grot[j].x + r1 * grot[j].y + r2 * grot[j].z + r3 * grot[j].w;
+                dV[3] = (grot[j].x - r0 * dot) / nrm;
+                dV[4] = (grot[j].y - r1 * dot) / nrm;
+                dV[5] = (grot[j].z - r2 * dot) / nrm;
+                dV[6] = (grot[j].w - r3 * dot) / nrm;
+            }
+            const uint32_t ocol = (uint32_t)(8 * hk + (k - 5 * hk));
+            {
+                uint32_t hi, lo;
+                umma::split_tf32(dO, hi, lo);
+                umma::tmem_st1(tl + kColAHi + ocol, hi);
+                umma::tmem_st1(tl + kColALo + ocol, lo);
             }
             st_split4(tl, kColAHi + 16 + 4 * k, kColALo + 16 + 4 * k, dC);
             st_split8(tl, kColAHi + 64 + 8 * k, kColALo + 64 + 8 * k, dV);
             if (valid) {
                 float *dst = d_out + (size_t)g * kOutP;
+                dst[ocol] = dO;
                 *reinterpret_cast<float4 *>(dst + 16 + 4 * k) = make_float4(dC[0], dC[1], dC[2], dC[3]);
                 *reinterpret_cast<float4 *>(dst + 64 + 8 * k) = make_float4(dV[0], dV[1], dV[2], dV[3]);
                 *(reinterpret_cast<float4 *>(dst + 64 + 8 * k) + 1) = make_float4(dV[4], dV[5], dV[6], dV[7]);
             }
         }
-        st_split8(tl, kColAHi + 8 * half, kColALo + 8 * half, dO);
-        if (valid) {
-            float *dst = d_out + (size_t)g * kOutP + 8 * half;
-            *reinterpret_cast<float4 *>(dst) = make_float4(dO[0], dO[1], dO[2], dO[3]);
-            *(reinterpret_cast<float4 *>(dst) + 1) = make_float4(dO[4], dO[5], dO[6], dO[7]);
-        }
-        if (half == 1) {   // columns 56..63 of the colour head are padding (10 offsets x 4 = 40 of 48): keep them finite
+        if (fifth == 0) {   // padding columns of the opacity (5..7, 13..15) and colour (56..63) heads: keep them finite (zero)
             const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             st_split8(tl, kColAHi + 56, kColALo + 56, z8);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int i = 5; i < 8; ++i) {
+                    umma::tmem_st1(tl + kColAHi + 8 * c + i, 0u);
+                    umma::tmem_st1(tl + kColALo + 8 * c + i, 0u);
+                }
+            }
             if (valid) {
-                float *dst = d_out + (size_t)g * kOutP + 56;
-                *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-                *(reinterpret_cast<float4 *>(dst) + 1) = make_float4(0.f, 0.f, 0.f, 0.f);
+                float *dst = d_out + (size_t)g * kOutP;
+#pragma unroll
+                for (int i = 5; i < 8; ++i) dst[i] = dst[8 + i] = 0.f;
+                *reinterpret_cast<float4 *>(dst + 56) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4 *>(dst + 60) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        if (half == 0) {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) S.part[row][i] = dsc[i];
+        for (int i = 0; i < 6; ++i) S.part[row][fifth][i] = dsc[i];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) S.part[row][6 + i] = danc[i];
-        }
-        // sign bits of the hidden layer for E2 (in flight while the tensor core works)
-        uint32_t hm[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-        if (valid) {
-            const uint2 *m = reinterpret_cast<const uint2 *>(save_hmask + (size_t)g * 6);
-            const uint2 m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2);
-            hm[0] = m0.x; hm[1] = m0.y; hm[2] = m1.x; hm[3] = m1.y; hm[4] = m2.x; hm[5] = m2.y;
-        }
+        for (int i = 0; i < 3; ++i) S.part[row][fifth][6 + i] = danc[i];
         umma::tmem_wait_st();
         umma::fence_before_thread_sync();
         __syncthreads();
@@ -243,10 +295,11 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
 
         // ================= E2: dPre = dH * (H > 0) =================
         // TMEM chunk q (8 columns at 64h + 8cc) <-> hidden columns 56h + 8cc .. +7 of the saved layout (cc = 7: padding)
-        {
 #pragma unroll
-            for (int qq = 0; qq < 12; ++qq) {
-                const int q = 12 * half + qq, h = q >> 3, cc = q & 7;
+        for (int qq = 0; qq < 5; ++qq) {
+            const int q = fifth + 5 * qq;
+            if (q < 24) {
+                const int h = q >> 3, cc = q & 7;
                 const uint32_t tcol = (uint32_t)(64 * h + 8 * cc);
                 float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (cc < 7) {
@@ -265,11 +318,11 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
                 }
                 st_split8(tl, kColD1 + tcol, kColPLo + tcol, f);
             }
-            if (half == 1 && valid) {   // hidden columns 168..175 of the HBM row are padding
-                float *dst = d_pre + (size_t)g * kHidP + 168;
-                *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-                *(reinterpret_cast<float4 *>(dst) + 1) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        }
+        if (fifth == 4 && valid) {   // hidden columns 168..175 of the HBM row are padding
+            float *dst = d_pre + (size_t)g * kHidP + 168;
+            *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *(reinterpret_cast<float4 *>(dst) + 1) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         umma::tmem_wait_st();
         umma::fence_before_thread_sync();
@@ -286,45 +339,42 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
         umma::fence_after_thread_sync();
 
         // ================= E3: d_feat, d_anchor, d_scaling =================
-        if (half == 0) {
+        // dX chunk c (8 columns): fifth f takes chunk f and, for f < 2, chunk f + 5; chunk 6 = feat 48, 49 | view 3 | dist
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = fifth + 5 * cc;
+            if (c < 7) {
                 uint32_t v[8];
                 umma::tmem_ld8(tl + kColDX + 8 * c, v);
                 umma::tmem_wait_ld8(v);
                 if (valid) {
-                    float2 *df = reinterpret_cast<float2 *>(d_feat + (size_t)a * kFeat + 8 * c);
+                    if (c < 6) {
+                        float2 *df = reinterpret_cast<float2 *>(d_feat + (size_t)ix.a * kFeat + 8 * c);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) df[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                        for (int j = 0; j < 4; ++j) df[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    } else {
+                        float2 *df = reinterpret_cast<float2 *>(d_feat + (size_t)ix.a * kFeat + 48);
+                        df[0] = make_float2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                        // view = u / |u|, dist = |u|, u = anchor - cam  (gaussian_renderer/__init__.py:106-108)
+                        const float ax = __ldg(anchor + 3 * (size_t)ix.a), ay = __ldg(anchor + 3 * (size_t)ix.a + 1),
+                                    az = __ldg(anchor + 3 * (size_t)ix.a + 2);
+                        const float ux = ax - cx, uy = ay - cy, uz = az - cz;
+                        const float d = sqrtf(ux * ux + uy * uy + uz * uz);
+                        const float vx = ux / d, vy = uy / d, vz = uz / d;
+                        const float gvx = __uint_as_float(v[2]), gvy = __uint_as_float(v[3]), gvz = __uint_as_float(v[4]),
+                                    gd = __uint_as_float(v[5]);
+                        const float dot = vx * gvx + vy * gvy + vz * gvz;
+                        float sum[9];
+#pragma unroll
+                        for (int i = 0; i < 9; ++i)
+                            sum[i] = S.part[row][0][i] + S.part[row][1][i] + S.part[row][2][i] + S.part[row][3][i] + S.part[row][4][i];
+                        d_anchor[3 * (size_t)ix.a + 0] = sum[6] + (gvx - vx * dot) / d + gd * vx;
+                        d_anchor[3 * (size_t)ix.a + 1] = sum[7] + (gvy - vy * dot) / d + gd * vy;
+                        d_anchor[3 * (size_t)ix.a + 2] = sum[8] + (gvz - vz * dot) / d + gd * vz;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) d_scaling[(size_t)ix.a * 6 + i] = sum[i];
+                    }
                 }
-            }
-        } else {
-            float x[24];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                uint32_t v[8];
-                umma::tmem_ld8(tl + kColDX + 32 + 8 * c, v);
-                umma::tmem_wait_ld8(v);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[8 * c + j] = __uint_as_float(v[j]);
-            }
-            if (valid) {
-                float2 *df = reinterpret_cast<float2 *>(d_feat + (size_t)a * kFeat + 32);
-#pragma unroll
-                for (int j = 0; j < 9; ++j) df[j] = make_float2(x[2 * j], x[2 * j + 1]);
-                // view = u / |u|, dist = |u|, u = anchor - cam  (gaussian_renderer/__init__.py:106-108)
-                const float ax = __ldg(anchor + 3 * (size_t)a), ay = __ldg(anchor + 3 * (size_t)a + 1),
-                            az = __ldg(anchor + 3 * (size_t)a + 2);
-                const float ux = ax - cx, uy = ay - cy, uz = az - cz;
-                const float d = sqrtf(ux * ux + uy * uy + uz * uz);
-                const float vx = ux / d, vy = uy / d, vz = uz / d;
-                const float gvx = x[18], gvy = x[19], gvz = x[20], gd = x[21];
-                const float dot = vx * gvx + vy * gvy + vz * gvz;
-                d_anchor[3 * (size_t)a + 0] = S.part[row][6] + danc[0] + (gvx - vx * dot) / d + gd * vx;
-                d_anchor[3 * (size_t)a + 1] = S.part[row][7] + danc[1] + (gvy - vy * dot) / d + gd * vy;
-                d_anchor[3 * (size_t)a + 2] = S.part[row][8] + danc[2] + (gvz - vz * dot) / d + gd * vz;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) d_scaling[(size_t)a * 6 + i] = S.part[row][i] + dsc[i];
             }
         }
         umma::fence_before_thread_sync();
@@ -349,12 +399,22 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
 //     D_x[in,  hid] += X^T dPre      (M = 128 from feature 0,             N = 176 from feature 376).
 // An M = 128 operand that is narrower than 128 features simply runs on into the next features (finite values, their
 // accumulator lanes are never read).  TMEM: D_o | D_c | D_v at columns 0 / 64 / 128, D_x at [192,368).
+//
+// Pipeline (the first version loaded through registers and sat on the DRAM latency with 8 % of the issue slots busy):
+//   * the fp32 rows of dOut / H / dPre travel HBM -> shared memory as TMA bulk copies (cp.async.bulk, one per row into
+//     a padded row stride that keeps the later reads conflict free), two slabs ahead, completion on an mbarrier;
+//   * 16 converter warps split the staged rows into TF32 hi / lo and scatter them into the operand block (X, 10 % of the
+//     bytes, is gathered through the visible-anchor list straight from HBM, one slab ahead);
+//   * one extra warp issues the bulk copies and the tcgen05.mma (named barriers: converters only ARRIVE, never wait for it).
 namespace ngwu {
-constexpr int kThreads = 256, kSlab = 16;
+constexpr int kConv = 512, kThreads = kConv + 32, kSlab = 16;
 constexpr int kGX = 14, kGO = 36, kGH = 44, kGP = 44, kGroups = kGX + kGO + kGH + kGP;   // float4 groups per row: 138
 constexpr int kOffX = 0, kOffO = kGX, kOffH = kOffO + kGO, kOffP = kOffH + kGH;
 constexpr int kLd = 4 * kGroups + 1;      // 553 features per 4-row chunk: = 1 (mod 8) spreads the chunks over the banks
 constexpr uint32_t kColDo = 0, kColDc = 64, kColDv = 128, kColDx = 192, kTmemCols = 512;
+// staged raw rows: padded strides (bytes / 4 = 20 mod 32: sixteen rows at the same column hit distinct banks)
+constexpr int kRawO = 148, kRawH = 180, kRawP = 180;             // floats per staged row (144 + 4, 176 + 4)
+constexpr uint32_t kBytesO = 144 * 4, kBytesH = 176 * 4;
 // forward-layout weight block of the SIMT kernels (contextgs_b200/neural_gaussians.py pack_decoder_weights): the
 // gradient is returned in this layout
 constexpr int kIn = 54, kLd1 = 152, kLdO = 12, kLdC = 32, kLdV = 72;
@@ -365,33 +425,56 @@ constexpr int kOffB2v = kOffW2v + 50 * kLdV;
 struct Buf {
     float hi[(kSlab / 4) * kLd * 4];     // [row / 4][feature][row % 4]
     float lo[(kSlab / 4) * kLd * 4];
-    float pad[8];
+};
+struct Raw {
+    float o[kSlab * kRawO];
+    float h[kSlab * kRawH];
+    float p[kSlab * kRawP];
 };
 struct Smem {
     Buf buf[2];
+    Raw raw[2];
     uint32_t tmem;
     int timeout;
-    alignas(8) uint64_t bar[2];
+    alignas(8) uint64_t mma_done[2];   // the MMAs that read buf[b] have completed
+    alignas(8) uint64_t full[2];       // the bulk copies into raw[b] have landed
 };
+
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     umma::smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(umma::smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 }  // namespace ngwu
 
 __global__ void __launch_bounds__(ngwu::kThreads, 1)
 neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, const float *__restrict__ anchor,
                                    const float *__restrict__ feat, float cx, float cy, float cz,
                                    const float *__restrict__ save_h, const float *__restrict__ d_out,
-                                   const float *__restrict__ d_pre, float *__restrict__ d_w, int32_t *__restrict__ err,
-                                   int desc_variant)
+                                   const float *__restrict__ d_pre, float *__restrict__ d_w, int32_t *__restrict__ err)
 {
     using namespace ngwu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int num_slabs = (Nv + kSlab - 1) / kSlab;
+    const int stride = (int)gridDim.x;
+    const bool issuer = tid >= kConv;
 
     if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
     if (tid == 0) {
-        umma::mbar_init(&S.bar[0], 1);
-        umma::mbar_init(&S.bar[1], 1);
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(&S.mma_done[i], 1);
+            umma::mbar_init(&S.full[i], 1);
+        }
         umma::fence_mbar_init();
         S.timeout = 0;
     }
@@ -399,55 +482,90 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
     __syncthreads();
     umma::fence_after_thread_sync();
     const uint32_t tbase = S.tmem;
+    // number of slabs this CTA processes
+    const int n_it = blockIdx.x < num_slabs ? (num_slabs - 1 - (int)blockIdx.x) / stride + 1 : 0;
 
-    const uint32_t idesc64 = umma::idesc_tf32(128, 64), idesc176 = umma::idesc_tf32(128, 176);
-    // K-major no-swizzle: LBO = stride between the two 4-row chunks of one K = 8 step, SBO = stride between 8-feature groups
-    const uint32_t lbo = (uint32_t)kLd * 16u, sbo = 128u;
-    (void)desc_variant;
-
-    uint32_t it = 0;
-    for (int slab = blockIdx.x; slab < num_slabs; slab += gridDim.x, ++it) {
-        const uint32_t b = it & 1u;
-        Buf &B = S.buf[b];
-        // the MMAs that read this buffer two slabs ago must have completed
-        if (it >= 2) {
-            if (!umma::mbar_wait(&S.bar[b], ((it >> 1) - 1) & 1u)) S.timeout = 1;
+    if (issuer) {
+        // =============================== issue warp: TMA bulk copies + tcgen05.mma ===============================
+        const uint32_t idesc64 = umma::idesc_tf32(128, 64), idesc176 = umma::idesc_tf32(128, 176);
+        // K-major no-swizzle: LBO = stride between the two 4-row chunks of one K = 8 step, SBO = stride between 8-feature groups
+        const uint32_t lbo = (uint32_t)kLd * 16u, sbo = 128u;
+        auto stage_rows = [&](int it) {     // bulk copies of slab `it` into raw[it & 1]
+            const int b = it & 1, row0 = ((int)blockIdx.x + it * stride) * kSlab;
+            const int rows = min(kSlab, Nv - row0);
+            if (lane == 0) mbar_expect_tx(&S.full[b], (uint32_t)rows * (kBytesO + 2u * kBytesH));
+            __syncwarp();
+            if (lane < rows) {
+                const size_t g = (size_t)(row0 + lane);
+                bulk_g2s(S.raw[b].o + lane * kRawO, d_out + g * 144, kBytesO, &S.full[b]);
+                bulk_g2s(S.raw[b].h + lane * kRawH, save_h + g * 176, kBytesH, &S.full[b]);
+                bulk_g2s(S.raw[b].p + lane * kRawP, d_pre + g * 176, kBytesH, &S.full[b]);
+            }
+        };
+        if (n_it > 0) stage_rows(0);
+        if (n_it > 1) stage_rows(1);
+        for (int it = 0; it < n_it; ++it) {
+            const uint32_t b = (uint32_t)it & 1u;
+            named_sync(1 + (int)b, kThreads);     // the converters have written buf[b] and are done with raw[b]
             umma::fence_after_thread_sync();
-        }
-        const int row0 = slab * kSlab;
-        for (int i = tid; i < kGroups * kSlab; i += kThreads) {
-            const int r = i & (kSlab - 1), c = i / kSlab;
-            const int g = row0 + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g < Nv) {
-                if (c >= kOffP) {
-                    v = __ldg(reinterpret_cast<const float4 *>(d_pre + (size_t)g * 176) + (c - kOffP));
-                } else if (c >= kOffH) {
-                    const int gi = c - kOffH;
-                    v = __ldg(reinterpret_cast<const float4 *>(save_h + (size_t)g * 176) + gi);
-                    if (gi == 13 || gi == 27 || gi == 41) v.w = 1.0f;      // column 56h + 55: bias row of head h
-                } else if (c >= kOffO) {
-                    v = __ldg(reinterpret_cast<const float4 *>(d_out + (size_t)g * 144) + (c - kOffO));
-                } else {
-                    const int a = vis_idx ? __ldg(vis_idx + g) : g;
-                    const float *f = feat + (size_t)a * 50;
-                    if (c < 12) {
-                        const float2 p = __ldg(reinterpret_cast<const float2 *>(f + 4 * c));
-                        const float2 q = __ldg(reinterpret_cast<const float2 *>(f + 4 * c) + 1);
-                        v = make_float4(p.x, p.y, q.x, q.y);
-                    } else {
-                        const float ux = __ldg(anchor + 3 * (size_t)a) - cx, uy = __ldg(anchor + 3 * (size_t)a + 1) - cy,
-                                    uz = __ldg(anchor + 3 * (size_t)a + 2) - cz;
-                        const float d = sqrtf(ux * ux + uy * uy + uz * uz);
-                        if (c == 12) {
-                            const float2 p = __ldg(reinterpret_cast<const float2 *>(f + 48));
-                            v = make_float4(p.x, p.y, ux / d, uy / d);
-                        } else {
-                            v = make_float4(uz / d, d, 1.0f, 0.f);
-                        }
+            if (lane == 0) {
+                const uint32_t hi = umma::smem_u32(S.buf[b].hi), lo = umma::smem_u32(S.buf[b].lo);
+                auto desc = [&](uint32_t base, int group, int kstep) {   // operand starting at float4 group `group`, rows 8 kstep ..
+                    return umma::smem_desc_kmajor(base + (uint32_t)kstep * 2u * lbo + (uint32_t)group * 64u, lbo, sbo);
+                };
+                const uint32_t acc0 = it > 0 ? 1u : 0u;
+#pragma unroll
+                for (int s = 0; s < kSlab / 8; ++s) {
+                    const uint32_t acc = (s > 0) ? 1u : acc0;
+                    const int og[3] = {0, 4, 16};
+                    const uint32_t dcol[3] = {kColDo, kColDc, kColDv};
+#pragma unroll
+                    for (int h = 0; h < 3; ++h) {
+                        const uint64_t a_hi = desc(hi, kOffO + og[h], s), a_lo = desc(lo, kOffO + og[h], s);
+                        const uint64_t b_hi = desc(hi, kOffH + 14 * h, s), b_lo = desc(lo, kOffH + 14 * h, s);
+                        umma::mma_tf32_ss(tbase + dcol[h], a_hi, b_lo, idesc64, acc);
+                        umma::mma_tf32_ss(tbase + dcol[h], a_lo, b_hi, idesc64, 1u);
+                        umma::mma_tf32_ss(tbase + dcol[h], a_hi, b_hi, idesc64, 1u);
                     }
+                    const uint64_t a_hi = desc(hi, kOffX, s), a_lo = desc(lo, kOffX, s);
+                    const uint64_t b_hi = desc(hi, kOffP, s), b_lo = desc(lo, kOffP, s);
+                    umma::mma_tf32_ss(tbase + kColDx, a_hi, b_lo, idesc176, acc);
+                    umma::mma_tf32_ss(tbase + kColDx, a_lo, b_hi, idesc176, 1u);
+                    umma::mma_tf32_ss(tbase + kColDx, a_hi, b_hi, idesc176, 1u);
+                }
+                umma::umma_commit(&S.mma_done[b]);
+            }
+            __syncwarp();
+            if (it + 2 < n_it) stage_rows(it + 2);    // raw[b] is free again
+        }
+    } else {
+        // =============================== converter warps ===============================================================
+        // X of the first slab travels while the first bulk copies land
+        auto load_x = [&](int it, float4 &v) {
+            v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid >= kGX * kSlab || it >= n_it) return;
+            const int r = tid & (kSlab - 1), c = tid / kSlab;
+            const int g = ((int)blockIdx.x + it * stride) * kSlab + r;
+            if (g >= Nv) return;
+            const int a = vis_idx ? __ldg(vis_idx + g) : g;
+            const float *f = feat + (size_t)a * 50;
+            if (c < 12) {
+                const float2 p = __ldg(reinterpret_cast<const float2 *>(f + 4 * c));
+                const float2 q = __ldg(reinterpret_cast<const float2 *>(f + 4 * c) + 1);
+                v = make_float4(p.x, p.y, q.x, q.y);
+            } else {
+                const float ux = __ldg(anchor + 3 * (size_t)a) - cx, uy = __ldg(anchor + 3 * (size_t)a + 1) - cy,
+                            uz = __ldg(anchor + 3 * (size_t)a + 2) - cz;
+                const float d = sqrtf(ux * ux + uy * uy + uz * uz);
+                if (c == 12) {
+                    const float2 p = __ldg(reinterpret_cast<const float2 *>(f + 48));
+                    v = make_float4(p.x, p.y, ux / d, uy / d);
+                } else {
+                    v = make_float4(uz / d, d, 1.0f, 0.f);
                 }
             }
+        };
+        auto store_item = [&](Buf &B, int r, int c, const float4 &v) {
             uint32_t h[4], l[4];
             umma::split_tf32(v.x, h[0], l[0]);
             umma::split_tf32(v.y, h[1], l[1]);
@@ -459,64 +577,66 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
                 B.hi[dst + 4 * j] = __uint_as_float(h[j]);
                 B.lo[dst + 4 * j] = __uint_as_float(l[j]);
             }
-        }
-        if (tid < (kSlab / 4) * 4) {   // the skew feature (index 552) of every chunk: read by nobody's valid lane, keep it finite
-            const int dst = ((tid >> 2) * kLd + 4 * kGroups) * 4 + (tid & 3);
-            B.hi[dst] = 0.f;
-            B.lo[dst] = 0.f;
-        }
-        umma::fence_proxy_async_smem();
-        umma::fence_before_thread_sync();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_thread_sync();
-            const uint32_t hi = umma::smem_u32(B.hi), lo = umma::smem_u32(B.lo);
-            auto desc = [&](uint32_t base, int group, int kstep) {   // operand starting at float4 group `group`, rows 8 kstep ..
-                return umma::smem_desc_kmajor(base + (uint32_t)kstep * 2u * lbo + (uint32_t)group * 64u, lbo, sbo);
-            };
-            const uint32_t acc0 = it > 0 ? 1u : 0u;
-#pragma unroll
-            for (int s = 0; s < kSlab / 8; ++s) {
-                const uint32_t acc = (s > 0) ? 1u : acc0;
-                // three heads of dW2^T
-                const int og[3] = {0, 4, 16};
-                const uint32_t dcol[3] = {kColDo, kColDc, kColDv};
-#pragma unroll
-                for (int h = 0; h < 3; ++h) {
-                    const uint64_t a_hi = desc(hi, kOffO + og[h], s), a_lo = desc(lo, kOffO + og[h], s);
-                    const uint64_t b_hi = desc(hi, kOffH + 14 * h, s), b_lo = desc(lo, kOffH + 14 * h, s);
-                    umma::mma_tf32_ss(tbase + dcol[h], a_hi, b_lo, idesc64, acc);
-                    umma::mma_tf32_ss(tbase + dcol[h], a_lo, b_hi, idesc64, 1u);
-                    umma::mma_tf32_ss(tbase + dcol[h], a_hi, b_hi, idesc64, 1u);
-                }
-                // dW1^T
-                const uint64_t a_hi = desc(hi, kOffX, s), a_lo = desc(lo, kOffX, s);
-                const uint64_t b_hi = desc(hi, kOffP, s), b_lo = desc(lo, kOffP, s);
-                umma::mma_tf32_ss(tbase + kColDx, a_hi, b_lo, idesc176, acc);
-                umma::mma_tf32_ss(tbase + kColDx, a_lo, b_hi, idesc176, 1u);
-                umma::mma_tf32_ss(tbase + kColDx, a_hi, b_hi, idesc176, 1u);
+        };
+        float4 xv;
+        load_x(0, xv);
+        for (int it = 0; it < n_it; ++it) {
+            const uint32_t b = (uint32_t)it & 1u;
+            Buf &B = S.buf[b];
+            const Raw &R = S.raw[b];
+            const int row0 = ((int)blockIdx.x + it * stride) * kSlab;
+            // the MMAs that read buf[b] two slabs ago must have completed
+            if (it >= 2) {
+                if (!umma::mbar_wait(&S.mma_done[b], (uint32_t)((it >> 1) - 1) & 1u)) S.timeout = 1;
+                umma::fence_after_thread_sync();
             }
-            umma::umma_commit(&S.bar[b]);
+            // X (prefetched one slab ahead), then the next slab's X starts travelling
+            if (tid < kGX * kSlab) store_item(B, tid & (kSlab - 1), tid / kSlab, xv);
+            load_x(it + 1, xv);
+            if (tid < (kSlab / 4) * 4) {   // the skew feature (index 552) of every chunk: keep it finite
+                const int dst = ((tid >> 2) * kLd + 4 * kGroups) * 4 + (tid & 3);
+                B.hi[dst] = 0.f;
+                B.lo[dst] = 0.f;
+            }
+            // the staged rows of dOut / H / dPre
+            if (!umma::mbar_wait(&S.full[b], (uint32_t)(it >> 1) & 1u)) S.timeout = 1;
+            for (int i = tid; i < (kGroups - kGX) * kSlab; i += kConv) {
+                const int r = i & (kSlab - 1), c = kGX + i / kSlab;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + r < Nv) {
+                    if (c >= kOffP) {
+                        v = *reinterpret_cast<const float4 *>(R.p + r * kRawP + 4 * (c - kOffP));
+                    } else if (c >= kOffH) {
+                        const int gi = c - kOffH;
+                        v = *reinterpret_cast<const float4 *>(R.h + r * kRawH + 4 * gi);
+                        if (gi == 13 || gi == 27 || gi == 41) v.w = 1.0f;      // column 56h + 55: bias row of head h
+                    } else {
+                        v = *reinterpret_cast<const float4 *>(R.o + r * kRawO + 4 * (c - kOffO));
+                    }
+                }
+                store_item(B, r, c, v);
+            }
+            umma::fence_proxy_async_smem();
+            umma::fence_before_thread_sync();
+            named_arrive(1 + (int)b, kThreads);
         }
     }
     // ---- drain: the last commit of each buffer covers every earlier MMA (commits complete in order) ----------------
-    const uint32_t n_it = it;
     if (n_it >= 1) {
-        const uint32_t last = n_it - 1, bl = last & 1u;
-        if (!umma::mbar_wait(&S.bar[bl], (last >> 1) & 1u)) S.timeout = 1;
+        const uint32_t last = (uint32_t)n_it - 1, bl = last & 1u;
+        if (!umma::mbar_wait(&S.mma_done[bl], (last >> 1) & 1u)) S.timeout = 1;
         if (n_it >= 2) {
-            const uint32_t prev = n_it - 2, bp = prev & 1u;
-            if (!umma::mbar_wait(&S.bar[bp], (prev >> 1) & 1u)) S.timeout = 1;
+            const uint32_t prev = (uint32_t)n_it - 2, bp = prev & 1u;
+            if (!umma::mbar_wait(&S.mma_done[bp], (prev >> 1) & 1u)) S.timeout = 1;
         }
     }
     umma::fence_after_thread_sync();
 
     // ---- flush: lane = output unit (dW2 heads) / input unit (dW1), column = hidden unit ---------------------------------
-    if (n_it >= 1) {
+    if (n_it >= 1 && !issuer) {
         const uint32_t tl = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
         const int L = 32 * (warp & 3) + lane;     // accumulator lane of this thread
-        const int chalf = warp >> 2;              // warps w and w + 4 share a lane quadrant: split the columns
-        // dW2 heads
+        const int cq = warp >> 2;                 // four warps share a lane quadrant: split the columns
 #pragma unroll 1
         for (int h = 0; h < 3; ++h) {
             int n = -1, ld = 0, offW = 0, offB = 0;
@@ -525,7 +645,7 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
             if (h == 2) { if (L < 80 && (L & 7) < 7) n = 7 * (L >> 3) + (L & 7); ld = kLdV; offW = kOffW2v; offB = kOffB2v; }
             const uint32_t dcol = h == 0 ? kColDo : (h == 1 ? kColDc : kColDv);
 #pragma unroll 1
-            for (int c = chalf; c < 7; c += 2) {
+            for (int c = cq; c < 7; c += 4) {
                 uint32_t v[8];
                 umma::tmem_ld8(tl + dcol + 8 * c, v);
                 umma::tmem_wait_ld8(v);
@@ -541,7 +661,7 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
         }
         // dW1 (rows 0..53) and b1 (row 54, the constant-one input)
 #pragma unroll 1
-        for (int c = chalf; c < 22; c += 2) {
+        for (int c = cq; c < 22; c += 4) {
             uint32_t v[8];
             umma::tmem_ld8(tl + kColDx + 8 * c, v);
             umma::tmem_wait_ld8(v);
@@ -635,7 +755,7 @@ extern "C" int cgs_neural_gaussians_backward_umma(const float *packed_bwd, const
         const int grid = slabs < sm_count ? slabs : sm_count;
         neural_gaussians_wgrad_umma_kernel<<<grid, ngwu::kThreads, sizeof(ngwu::Smem), st>>>(
             vis_idx, Nv, anchor, feat, campos_host[0], campos_host[1], campos_host[2], save_h, scratch_dout, scratch_dpre,
-            d_packed_fwd, err, g_wgrad_desc_variant);
+            d_packed_fwd, err);
     }
     return check_launch(__func__);
 }

@@ -144,6 +144,14 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4])
                  "r"(r[3])
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t r0, uint32_t r1)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
+}
 // wait::ld that names the destination registers of an earlier tcgen05.ld as in/out operands: the compiler cannot
 // move a read of them above the wait (needed when a load is issued ahead of the code that consumes the previous one)
 __device__ __forceinline__ void tmem_wait_ld8(uint32_t (&r)[8])
