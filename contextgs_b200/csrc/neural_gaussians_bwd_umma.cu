@@ -47,7 +47,6 @@ constexpr int kPacked = kOffW1TLo + kW1T;                  // 43008 floats = 172
 
 struct Smem {
     float w[kPacked];
-    float part[kRows][5][9];     // per (row, fifth): partial sums of d_scaling[6] + d_anchor[3]
     uint32_t tmem;
     int timeout;
     alignas(8) uint64_t bar[2];
@@ -73,24 +72,113 @@ __device__ __forceinline__ void st_split4(uint32_t tl, uint32_t col_hi, uint32_t
 }
 }  // namespace ngbu
 
+// kernel 0: gradient of the post-processing, one thread per (visible row, offset) -- plain elementwise work at full
+// occupancy (it used to be the first phase of kernel 1, where 20 warps per SM could not cover the DRAM latency of its
+// gathers).  Writes the layer-2 output gradient dOut[Nv,144] (opacity 16 | colour 48 | covariance 80, padding columns
+// zero), d_offsets, d_mask and accumulates the per-anchor parts of d_scaling / d_anchor (rows zero-filled by the caller).
+__global__ void __launch_bounds__(256)
+neural_gaussians_postproc_backward_kernel(const int *__restrict__ vis_idx, int Nv, const float *__restrict__ offsets,
+                                          const float *__restrict__ scaling, const float *__restrict__ mask,
+                                          const uint8_t *__restrict__ keep_mask, const float *__restrict__ save_pre2,
+                                          const uint32_t *__restrict__ save_rowpos,
+                                          const uint32_t *__restrict__ save_tilebase, const float *__restrict__ g_xyz,
+                                          const float *__restrict__ g_color, const float *__restrict__ g_opacity,
+                                          const float *__restrict__ g_scaling, const float *__restrict__ g_rot,
+                                          float *__restrict__ d_anchor, float *__restrict__ d_offsets,
+                                          float *__restrict__ d_scaling, float *__restrict__ d_mask,
+                                          float *__restrict__ d_out)
+{
+    using namespace ngbu;
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)Nv * 16) return;
+    const int g = (int)(e >> 4), k = (int)(e & 15);          // 16 threads per row: offsets 0..9, 10..15 write the padding
+    float *dst = d_out + (size_t)g * kOutP;
+    if (k >= kK) {
+        // padding columns: opacity 5..7, 13..15 and colour 56..63
+        if (k == 10) { dst[5] = 0.f; dst[6] = 0.f; dst[7] = 0.f; }
+        if (k == 11) { dst[13] = 0.f; dst[14] = 0.f; dst[15] = 0.f; }
+        if (k == 12) *reinterpret_cast<float4 *>(dst + 56) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k == 13) *reinterpret_cast<float4 *>(dst + 60) = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const int hk = k >= 5 ? 1 : 0;
+    const uint32_t ocol = (uint32_t)(8 * hk + (k - 5 * hk));
+    float dO = 0.f;
+    float4 dC = make_float4(0.f, 0.f, 0.f, 0.f), dVa = dC, dVb = dC;
+    if (keep_mask[(size_t)g * kK + k]) {
+        const int a = vis_idx ? __ldg(vis_idx + g) : g;
+        uint32_t before = 0;
+        for (int i = 5 * hk; i < k; ++i) before += keep_mask[(size_t)g * kK + i] ? 1u : 0u;
+        const size_t pos = (size_t)__ldg(save_tilebase + (g >> 7)) + __ldg(save_rowpos + (size_t)g * 2 + hk) + before;
+        const size_t ak = (size_t)a * kK + k;
+        const float *p2 = save_pre2 + (size_t)g * kOutP;
+        const float gx = __ldg(g_xyz + 3 * pos), gy = __ldg(g_xyz + 3 * pos + 1), gz = __ldg(g_xyz + 3 * pos + 2);
+        const float o0 = __ldg(offsets + 3 * ak), o1 = __ldg(offsets + 3 * ak + 1), o2 = __ldg(offsets + 3 * ak + 2);
+        const float gc0 = __ldg(g_color + 3 * pos), gc1 = __ldg(g_color + 3 * pos + 1), gc2 = __ldg(g_color + 3 * pos + 2);
+        const float gs0 = __ldg(g_scaling + 3 * pos), gs1 = __ldg(g_scaling + 3 * pos + 1), gs2 = __ldg(g_scaling + 3 * pos + 2);
+        const float go = __ldg(g_opacity + pos), mk = __ldg(mask + ak), po = __ldg(p2 + ocol);
+        const float4 pc = __ldg(reinterpret_cast<const float4 *>(p2 + 16 + 4 * k));
+        const float4 pa = __ldg(reinterpret_cast<const float4 *>(p2 + 64 + 8 * k));
+        const float4 pb = __ldg(reinterpret_cast<const float4 *>(p2 + 64 + 8 * k) + 1);
+        const float4 gr = __ldg(reinterpret_cast<const float4 *>(g_rot) + pos);
+        float sc[6];
+        {
+            const float2 *s2 = reinterpret_cast<const float2 *>(scaling + 6 * (size_t)a);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float2 v = __ldg(s2 + i);
+                sc[2 * i] = v.x;
+                sc[2 * i + 1] = v.y;
+            }
+        }
+        d_offsets[ak * 3 + 0] = gx * sc[0];
+        d_offsets[ak * 3 + 1] = gy * sc[1];
+        d_offsets[ak * 3 + 2] = gz * sc[2];
+        // opacity = tanh(pre) * mask
+        const float t = tanhf(po);
+        d_mask[ak] = go * t;
+        dO = go * mk * (1.0f - t * t);
+        // colour = sigmoid(pre)
+        const float c0 = sigmoidf_(pc.x), c1 = sigmoidf_(pc.y), c2 = sigmoidf_(pc.z);
+        dC = make_float4(gc0 * c0 * (1.0f - c0), gc1 * c1 * (1.0f - c1), gc2 * c2 * (1.0f - c2), 0.f);
+        // scaling = sc[3:6] * sigmoid(pre[0:3]); rot = normalize(pre[3:7])
+        const float s0 = sigmoidf_(pa.x), s1 = sigmoidf_(pa.y), s2 = sigmoidf_(pa.z);
+        const float q0 = pa.w, q1 = pb.x, q2 = pb.y, q3 = pb.z;
+        const float nrm = fmaxf(sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3), 1e-12f);
+        const float r0 = q0 / nrm, r1 = q1 / nrm, r2 = q2 / nrm, r3 = q3 / nrm;
+        const float dot = r0 * gr.x + r1 * gr.y + r2 * gr.z + r3 * gr.w;
+        dVa = make_float4(gs0 * sc[3] * s0 * (1.0f - s0), gs1 * sc[4] * s1 * (1.0f - s1), gs2 * sc[5] * s2 * (1.0f - s2),
+                          (gr.x - r0 * dot) / nrm);
+        dVb = make_float4((gr.y - r1 * dot) / nrm, (gr.z - r2 * dot) / nrm, (gr.w - r3 * dot) / nrm, 0.f);
+        // per-anchor sums over the offsets (ten threads of one row: distinct addresses across rows, light contention)
+        atomicAdd(d_anchor + 3 * (size_t)a + 0, gx);
+        atomicAdd(d_anchor + 3 * (size_t)a + 1, gy);
+        atomicAdd(d_anchor + 3 * (size_t)a + 2, gz);
+        atomicAdd(d_scaling + 6 * (size_t)a + 0, gx * o0);
+        atomicAdd(d_scaling + 6 * (size_t)a + 1, gy * o1);
+        atomicAdd(d_scaling + 6 * (size_t)a + 2, gz * o2);
+        atomicAdd(d_scaling + 6 * (size_t)a + 3, gs0 * s0);
+        atomicAdd(d_scaling + 6 * (size_t)a + 4, gs1 * s1);
+        atomicAdd(d_scaling + 6 * (size_t)a + 5, gs2 * s2);
+    }
+    dst[ocol] = dO;
+    *reinterpret_cast<float4 *>(dst + 16 + 4 * k) = dC;
+    *reinterpret_cast<float4 *>(dst + 64 + 8 * k) = dVa;
+    *(reinterpret_cast<float4 *>(dst + 64 + 8 * k) + 1) = dVb;
+}
+
 __global__ void __launch_bounds__(ngbu::kThreads, 1)
 neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int *__restrict__ vis_idx, int Nv,
-                                   const float *__restrict__ anchor, const float *__restrict__ offsets,
-                                   const float *__restrict__ scaling, const float *__restrict__ mask, float cx, float cy,
-                                   float cz, const uint8_t *__restrict__ keep_mask, const float *__restrict__ save_pre2,
-                                   const uint32_t *__restrict__ save_hmask, const uint32_t *__restrict__ save_rowpos,
-                                   const uint32_t *__restrict__ save_tilebase, const float *__restrict__ g_xyz,
-                                   const float *__restrict__ g_color, const float *__restrict__ g_opacity,
-                                   const float *__restrict__ g_scaling, const float *__restrict__ g_rot,
-                                   float *__restrict__ d_anchor, float *__restrict__ d_feat, float *__restrict__ d_offsets,
-                                   float *__restrict__ d_scaling, float *__restrict__ d_mask, float *__restrict__ d_out,
-                                   float *__restrict__ d_pre, int32_t *__restrict__ err)
+                                   const float *__restrict__ anchor, float cx, float cy, float cz,
+                                   const uint32_t *__restrict__ save_hmask, const float *__restrict__ d_out,
+                                   float *__restrict__ d_anchor, float *__restrict__ d_feat, float *__restrict__ d_pre,
+                                   int32_t *__restrict__ err)
 {
     using namespace ngbu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int fifth = warp >> 2;                       // five threads per row: offsets 2 * fifth, 2 * fifth + 1
+    const int fifth = warp >> 2;                       // five threads per row
     const int row = 32 * (warp & 3) + lane;
     const int num_tiles = (Nv + kRows - 1) / kRows;
 
@@ -113,168 +201,56 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
     const uint32_t tbase = S.tmem;
     const uint32_t tl = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
 
-    // index-type inputs of a tile (fetched one tile AHEAD: they feed the addresses of everything else)
-    struct Idx {
+    // Everything a tile reads from HBM is fetched one tile AHEAD into registers: this thread's share of the dOut row
+    // (8-column chunks fifth, fifth + 5, ... of 18) and the sign bits of the hidden layer.
+    struct Pre {
+        float4 v[4][2];
+        uint32_t hm[6];
         int a;
-        uint32_t keepbits, pos_h0, pos_h1;
     };
-    auto load_idx = [&](int tile, Idx &ix) {
+    auto prefetch = [&](int tile, Pre &p) {
         const int g = tile * kRows + row;
-        ix.a = -1; ix.keepbits = 0; ix.pos_h0 = ix.pos_h1 = 0;
-        if (tile >= num_tiles || g >= Nv) return;
-        ix.a = vis_idx ? __ldg(vis_idx + g) : g;
-        const unsigned short *kp = reinterpret_cast<const unsigned short *>(keep_mask + (size_t)g * kK);   // 10 bytes, 2-byte aligned
+        p.a = -1;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const uint32_t v = __ldg(kp + i);
-            ix.keepbits |= ((v & 0xffu) ? 1u : 0u) << (2 * i) | ((v >> 8) ? 1u : 0u) << (2 * i + 1);
+        for (int i = 0; i < 6; ++i) p.hm[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p.v[i][0] = p.v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tile >= num_tiles || g >= Nv) return;
+        p.a = vis_idx ? __ldg(vis_idx + g) : g;
+        const float4 *src = reinterpret_cast<const float4 *>(d_out + (size_t)g * kOutP);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = fifth + 5 * i;
+            if (c < 18) {
+                p.v[i][0] = __ldg(src + 2 * c);
+                p.v[i][1] = __ldg(src + 2 * c + 1);
+            }
         }
-        const uint2 rp = __ldg(reinterpret_cast<const uint2 *>(save_rowpos) + g);
-        const uint32_t tb = __ldg(save_tilebase + tile);
-        ix.pos_h0 = tb + rp.x;
-        ix.pos_h1 = tb + rp.y;
+        const uint2 *m = reinterpret_cast<const uint2 *>(save_hmask + (size_t)g * 6);
+        const uint2 m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2);
+        p.hm[0] = m0.x; p.hm[1] = m0.y; p.hm[2] = m1.x; p.hm[3] = m1.y; p.hm[4] = m2.x; p.hm[5] = m2.y;
     };
-    Idx nxt;
-    load_idx(blockIdx.x, nxt);
+    Pre nxt;
+    prefetch(blockIdx.x, nxt);
 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t parity = it & 1u;
         const int g = tile * kRows + row;
-        const Idx ix = nxt;
-        const bool valid = ix.a >= 0;
-        const int a = valid ? ix.a : 0;
-        load_idx(tile + (int)gridDim.x, nxt);
+        const Pre cur = nxt;
+        const bool valid = cur.a >= 0;
+        prefetch(tile + (int)gridDim.x, nxt);
 
-        // ================= E1: gradient of the post-processing =================
-        // all loads of the thread's two offsets are issued before anything is computed (one DRAM round trip per tile)
-        float gxyz[2][3], off[2][3], gop[2], mk[2], po[2], gcol[2][3], gsc[2][3];
-        float4 pc[2], pa[2], pb[2], grot[2];
-        bool kept[2];
-        const float *p2 = save_pre2 + (size_t)(valid ? g : 0) * kOutP;
+        // ================= stage dOut (kernel 0) as the A operand: hi / lo into TMEM =================
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int k = 2 * fifth + j, hk = k >= 5 ? 1 : 0;
-            kept[j] = (ix.keepbits >> k) & 1u;
-            const uint32_t before = __popc(ix.keepbits & ((1u << k) - 1u) & (hk ? 0x3e0u : 0x01fu));
-            const size_t pos = kept[j] ? (size_t)((hk ? ix.pos_h1 : ix.pos_h0) + before) : 0;
-            const size_t ak = (size_t)a * kK + k;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                gxyz[j][c] = __ldg(g_xyz + 3 * pos + c);
-                off[j][c] = __ldg(offsets + 3 * ak + c);
-                gcol[j][c] = __ldg(g_color + 3 * pos + c);
-                gsc[j][c] = __ldg(g_scaling + 3 * pos + c);
-            }
-            gop[j] = __ldg(g_opacity + pos);
-            mk[j] = __ldg(mask + ak);
-            po[j] = __ldg(p2 + 8 * hk + (k - 5 * hk));
-            pc[j] = __ldg(reinterpret_cast<const float4 *>(p2 + 16 + 4 * k));
-            pa[j] = __ldg(reinterpret_cast<const float4 *>(p2 + 64 + 8 * k));
-            pb[j] = __ldg(reinterpret_cast<const float4 *>(p2 + 64 + 8 * k) + 1);
-            grot[j] = __ldg(reinterpret_cast<const float4 *>(g_rot) + pos);
-        }
-        float sc[6];
-        {
-            const float2 *s2 = reinterpret_cast<const float2 *>(scaling + 6 * (size_t)a);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float2 v = __ldg(s2 + i);
-                sc[2 * i] = v.x;
-                sc[2 * i + 1] = v.y;
+        for (int i = 0; i < 4; ++i) {
+            const int c = fifth + 5 * i;
+            if (c < 18) {
+                const float f[8] = {cur.v[i][0].x, cur.v[i][0].y, cur.v[i][0].z, cur.v[i][0].w,
+                                    cur.v[i][1].x, cur.v[i][1].y, cur.v[i][1].z, cur.v[i][1].w};
+                st_split8(tl, kColAHi + 8 * c, kColALo + 8 * c, f);
             }
         }
-        // sign bits of the hidden layer for E2
-        uint32_t hm[6];
-        {
-            const uint2 *m = reinterpret_cast<const uint2 *>(save_hmask + (size_t)(valid ? g : 0) * 6);
-            const uint2 m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2);
-            hm[0] = m0.x; hm[1] = m0.y; hm[2] = m1.x; hm[3] = m1.y; hm[4] = m2.x; hm[5] = m2.y;
-        }
-        float dsc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, danc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int k = 2 * fifth + j, hk = k >= 5 ? 1 : 0;
-            const size_t ak = (size_t)a * kK + k;
-            float dO = 0.f;
-            float dC[4] = {0.f, 0.f, 0.f, 0.f}, dV[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (kept[j] && valid) {
-                d_offsets[ak * 3 + 0] = gxyz[j][0] * sc[0];
-                d_offsets[ak * 3 + 1] = gxyz[j][1] * sc[1];
-                d_offsets[ak * 3 + 2] = gxyz[j][2] * sc[2];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    danc[c] += gxyz[j][c];
-                    dsc[c] += gxyz[j][c] * off[j][c];
-                }
-                // opacity = tanh(pre) * mask
-                const float t = tanhf(po[j]);
-                d_mask[ak] = gop[j] * t;
-                dO = gop[j] * mk[j] * (1.0f - t * t);
-                // colour = sigmoid(pre)
-                const float pcv[3] = {pc[j].x, pc[j].y, pc[j].z};
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float s = sigmoidf_(pcv[c]);
-                    dC[c] = gcol[j][c] * s * (1.0f - s);
-                }
-                // scaling = sc[3:6] * sigmoid(pre[0:3]); rot = normalize(pre[3:7])
-                const float pv[3] = {pa[j].x, pa[j].y, pa[j].z};
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float s = sigmoidf_(pv[c]);
-                    dsc[3 + c] += gsc[j][c] * s;
-                    dV[c] = gsc[j][c] * sc[3 + c] * s * (1.0f - s);
-                }
-                const float q0 = pa[j].w, q1 = pb[j].x, q2 = pb[j].y, q3 = pb[j].z;
-                const float nrm = fmaxf(sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3), 1e-12f);
-                const float r0 = q0 / nrm, r1 = q1 / nrm, r2 = q2 / nrm, r3 = q3 / nrm;
-                const float dot = r0 * grot[j].x + r1 * grot[j].y + r2 * grot[j].z + r3 * grot[j].w;
-                dV[3] = (grot[j].x - r0 * dot) / nrm;
-                dV[4] = (grot[j].y - r1 * dot) / nrm;
-                dV[5] = (grot[j].z - r2 * dot) / nrm;
-                dV[6] = (grot[j].w - r3 * dot) / nrm;
-            }
-            const uint32_t ocol = (uint32_t)(8 * hk + (k - 5 * hk));
-            {
-                uint32_t hi, lo;
-                umma::split_tf32(dO, hi, lo);
-                umma::tmem_st1(tl + kColAHi + ocol, hi);
-                umma::tmem_st1(tl + kColALo + ocol, lo);
-            }
-            st_split4(tl, kColAHi + 16 + 4 * k, kColALo + 16 + 4 * k, dC);
-            st_split8(tl, kColAHi + 64 + 8 * k, kColALo + 64 + 8 * k, dV);
-            if (valid) {
-                float *dst = d_out + (size_t)g * kOutP;
-                dst[ocol] = dO;
-                *reinterpret_cast<float4 *>(dst + 16 + 4 * k) = make_float4(dC[0], dC[1], dC[2], dC[3]);
-                *reinterpret_cast<float4 *>(dst + 64 + 8 * k) = make_float4(dV[0], dV[1], dV[2], dV[3]);
-                *(reinterpret_cast<float4 *>(dst + 64 + 8 * k) + 1) = make_float4(dV[4], dV[5], dV[6], dV[7]);
-            }
-        }
-        if (fifth == 0) {   // padding columns of the opacity (5..7, 13..15) and colour (56..63) heads: keep them finite (zero)
-            const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            st_split8(tl, kColAHi + 56, kColALo + 56, z8);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                for (int i = 5; i < 8; ++i) {
-                    umma::tmem_st1(tl + kColAHi + 8 * c + i, 0u);
-                    umma::tmem_st1(tl + kColALo + 8 * c + i, 0u);
-                }
-            }
-            if (valid) {
-                float *dst = d_out + (size_t)g * kOutP;
-#pragma unroll
-                for (int i = 5; i < 8; ++i) dst[i] = dst[8 + i] = 0.f;
-                *reinterpret_cast<float4 *>(dst + 56) = make_float4(0.f, 0.f, 0.f, 0.f);
-                *reinterpret_cast<float4 *>(dst + 60) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) S.part[row][fifth][i] = dsc[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) S.part[row][fifth][6 + i] = danc[i];
         umma::tmem_wait_st();
         umma::fence_before_thread_sync();
         __syncthreads();
@@ -307,7 +283,10 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
                     umma::tmem_ld8(tl + kColD1 + tcol, v);
                     umma::tmem_wait_ld8(v);
                     const int hcol = 56 * h + 8 * cc, hf = hcol >= 88 ? 1 : 0, b = hcol - 88 * hf;
-                    const uint32_t bits = (hm[3 * hf + (b >> 5)] >> (b & 31)) & 0xffu;
+                    const int wi = 3 * hf + (b >> 5);      // selects instead of a dynamically indexed (local-memory) array
+                    const uint32_t word = wi == 0 ? cur.hm[0] : wi == 1 ? cur.hm[1] : wi == 2 ? cur.hm[2]
+                                        : wi == 3 ? cur.hm[3] : wi == 4 ? cur.hm[4] : cur.hm[5];
+                    const uint32_t bits = (word >> (b & 31)) & 0xffu;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = (bits >> j) & 1u ? __uint_as_float(v[j]) : 0.f;
                     if (valid) {
@@ -349,36 +328,31 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
                 umma::tmem_wait_ld8(v);
                 if (valid) {
                     if (c < 6) {
-                        float2 *df = reinterpret_cast<float2 *>(d_feat + (size_t)ix.a * kFeat + 8 * c);
+                        float2 *df = reinterpret_cast<float2 *>(d_feat + (size_t)cur.a * kFeat + 8 * c);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) df[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
                     } else {
-                        float2 *df = reinterpret_cast<float2 *>(d_feat + (size_t)ix.a * kFeat + 48);
+                        float2 *df = reinterpret_cast<float2 *>(d_feat + (size_t)cur.a * kFeat + 48);
                         df[0] = make_float2(__uint_as_float(v[0]), __uint_as_float(v[1]));
                         // view = u / |u|, dist = |u|, u = anchor - cam  (gaussian_renderer/__init__.py:106-108)
-                        const float ax = __ldg(anchor + 3 * (size_t)ix.a), ay = __ldg(anchor + 3 * (size_t)ix.a + 1),
-                                    az = __ldg(anchor + 3 * (size_t)ix.a + 2);
+                        const float ax = __ldg(anchor + 3 * (size_t)cur.a), ay = __ldg(anchor + 3 * (size_t)cur.a + 1),
+                                    az = __ldg(anchor + 3 * (size_t)cur.a + 2);
                         const float ux = ax - cx, uy = ay - cy, uz = az - cz;
                         const float d = sqrtf(ux * ux + uy * uy + uz * uz);
                         const float vx = ux / d, vy = uy / d, vz = uz / d;
                         const float gvx = __uint_as_float(v[2]), gvy = __uint_as_float(v[3]), gvz = __uint_as_float(v[4]),
                                     gd = __uint_as_float(v[5]);
                         const float dot = vx * gvx + vy * gvy + vz * gvz;
-                        float sum[9];
-#pragma unroll
-                        for (int i = 0; i < 9; ++i)
-                            sum[i] = S.part[row][0][i] + S.part[row][1][i] + S.part[row][2][i] + S.part[row][3][i] + S.part[row][4][i];
-                        d_anchor[3 * (size_t)ix.a + 0] = sum[6] + (gvx - vx * dot) / d + gd * vx;
-                        d_anchor[3 * (size_t)ix.a + 1] = sum[7] + (gvy - vy * dot) / d + gd * vy;
-                        d_anchor[3 * (size_t)ix.a + 2] = sum[8] + (gvz - vz * dot) / d + gd * vz;
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) d_scaling[(size_t)ix.a * 6 + i] = sum[i];
+                        // the per-offset parts were accumulated by kernel 0; this is the only writer of the view path
+                        atomicAdd(d_anchor + 3 * (size_t)cur.a + 0, (gvx - vx * dot) / d + gd * vx);
+                        atomicAdd(d_anchor + 3 * (size_t)cur.a + 1, (gvy - vy * dot) / d + gd * vy);
+                        atomicAdd(d_anchor + 3 * (size_t)cur.a + 2, (gvz - vz * dot) / d + gd * vz);
                     }
                 }
             }
         }
         umma::fence_before_thread_sync();
-        __syncthreads();   // dX / part consumed: the next tile may overwrite columns [0,288) and S.part
+        __syncthreads();   // dX consumed: the next tile may overwrite columns [0,288)
         umma::fence_after_thread_sync();
     }
 
@@ -402,12 +376,13 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
 //
 // Pipeline (the first version loaded through registers and sat on the DRAM latency with 8 % of the issue slots busy):
 //   * the fp32 rows of dOut / H / dPre travel HBM -> shared memory as TMA bulk copies (cp.async.bulk, one per row into
-//     a padded row stride that keeps the later reads conflict free), two slabs ahead, completion on an mbarrier;
+//     a padded row stride that keeps the later reads conflict free), EIGHT 8-row slabs ahead (two 16-row slabs ahead
+//     left the converters waiting for the copies 54 % of the time), completion on one mbarrier per stage;
 //   * 16 converter warps split the staged rows into TF32 hi / lo and scatter them into the operand block (X, 10 % of the
 //     bytes, is gathered through the visible-anchor list straight from HBM, one slab ahead);
 //   * one extra warp issues the bulk copies and the tcgen05.mma (named barriers: converters only ARRIVE, never wait for it).
 namespace ngwu {
-constexpr int kConv = 512, kThreads = kConv + 32, kSlab = 16;
+constexpr int kConv = 512, kThreads = kConv + 32, kSlab = 8, kStages = 8;   // 8 rows = one K step per slab; 8 slabs in flight
 constexpr int kGX = 14, kGO = 36, kGH = 44, kGP = 44, kGroups = kGX + kGO + kGH + kGP;   // float4 groups per row: 138
 constexpr int kOffX = 0, kOffO = kGX, kOffH = kOffO + kGO, kOffP = kOffH + kGH;
 constexpr int kLd = 4 * kGroups + 1;      // 553 features per 4-row chunk: = 1 (mod 8) spreads the chunks over the banks
@@ -433,11 +408,11 @@ struct Raw {
 };
 struct Smem {
     Buf buf[2];
-    Raw raw[2];
+    Raw raw[kStages];
     uint32_t tmem;
     int timeout;
-    alignas(8) uint64_t mma_done[2];   // the MMAs that read buf[b] have completed
-    alignas(8) uint64_t full[2];       // the bulk copies into raw[b] have landed
+    alignas(8) uint64_t mma_done[2];       // the MMAs that read buf[b] have completed
+    alignas(8) uint64_t full[kStages];     // the bulk copies into raw[stage] have landed
 };
 
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
@@ -471,10 +446,8 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
 
     if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            umma::mbar_init(&S.mma_done[i], 1);
-            umma::mbar_init(&S.full[i], 1);
-        }
+        for (int i = 0; i < 2; ++i) umma::mbar_init(&S.mma_done[i], 1);
+        for (int i = 0; i < kStages; ++i) umma::mbar_init(&S.full[i], 1);
         umma::fence_mbar_init();
         S.timeout = 0;
     }
@@ -490,8 +463,8 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
         const uint32_t idesc64 = umma::idesc_tf32(128, 64), idesc176 = umma::idesc_tf32(128, 176);
         // K-major no-swizzle: LBO = stride between the two 4-row chunks of one K = 8 step, SBO = stride between 8-feature groups
         const uint32_t lbo = (uint32_t)kLd * 16u, sbo = 128u;
-        auto stage_rows = [&](int it) {     // bulk copies of slab `it` into raw[it & 1]
-            const int b = it & 1, row0 = ((int)blockIdx.x + it * stride) * kSlab;
+        auto stage_rows = [&](int it) {     // bulk copies of slab `it` into raw[it % kStages]
+            const int b = it % kStages, row0 = ((int)blockIdx.x + it * stride) * kSlab;
             const int rows = min(kSlab, Nv - row0);
             if (lane == 0) mbar_expect_tx(&S.full[b], (uint32_t)rows * (kBytesO + 2u * kBytesH));
             __syncwarp();
@@ -502,8 +475,7 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
                 bulk_g2s(S.raw[b].p + lane * kRawP, d_pre + g * 176, kBytesH, &S.full[b]);
             }
         };
-        if (n_it > 0) stage_rows(0);
-        if (n_it > 1) stage_rows(1);
+        for (int i = 0; i < kStages && i < n_it; ++i) stage_rows(i);
         for (int it = 0; it < n_it; ++it) {
             const uint32_t b = (uint32_t)it & 1u;
             named_sync(1 + (int)b, kThreads);     // the converters have written buf[b] and are done with raw[b]
@@ -536,54 +508,49 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
                 umma::umma_commit(&S.mma_done[b]);
             }
             __syncwarp();
-            if (it + 2 < n_it) stage_rows(it + 2);    // raw[b] is free again
+            if (it + kStages < n_it) stage_rows(it + kStages);    // raw[it % kStages] is free again
         }
     } else {
         // =============================== converter warps ===============================================================
         // X of the first slab travels while the first bulk copies land
-        auto load_x = [&](int it, float4 &v) {
-            v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tid >= kGX * kSlab || it >= n_it) return;
-            const int r = tid & (kSlab - 1), c = tid / kSlab;
+        // Items are float2 (two features of one row): with 8 rows per slab a warp covers 8 rows x 4 feature pairs, and
+        // both the staged-row reads (row stride = 20 banks) and the operand stores (8 c + 4 (r / 4) + r % 4) are conflict free.
+        constexpr int kPairs = 2 * kGroups, kPX = 2 * kGX, kPO = 2 * kOffO, kPH = 2 * kOffH, kPP = 2 * kOffP;
+        auto load_x = [&](int it, float2 &v) {
+            v = make_float2(0.f, 0.f);
+            if (tid >= kPX * kSlab || it >= n_it) return;
+            const int r = tid & (kSlab - 1), c = tid / kSlab;      // c: feature pair 0..27
             const int g = ((int)blockIdx.x + it * stride) * kSlab + r;
             if (g >= Nv) return;
             const int a = vis_idx ? __ldg(vis_idx + g) : g;
-            const float *f = feat + (size_t)a * 50;
-            if (c < 12) {
-                const float2 p = __ldg(reinterpret_cast<const float2 *>(f + 4 * c));
-                const float2 q = __ldg(reinterpret_cast<const float2 *>(f + 4 * c) + 1);
-                v = make_float4(p.x, p.y, q.x, q.y);
+            if (c < 25) {
+                v = __ldg(reinterpret_cast<const float2 *>(feat + (size_t)a * 50) + c);
             } else {
                 const float ux = __ldg(anchor + 3 * (size_t)a) - cx, uy = __ldg(anchor + 3 * (size_t)a + 1) - cy,
                             uz = __ldg(anchor + 3 * (size_t)a + 2) - cz;
                 const float d = sqrtf(ux * ux + uy * uy + uz * uz);
-                if (c == 12) {
-                    const float2 p = __ldg(reinterpret_cast<const float2 *>(f + 48));
-                    v = make_float4(p.x, p.y, ux / d, uy / d);
-                } else {
-                    v = make_float4(uz / d, d, 1.0f, 0.f);
-                }
+                if (c == 25) v = make_float2(ux / d, uy / d);
+                else if (c == 26) v = make_float2(uz / d, d);
+                else v = make_float2(1.0f, 0.f);                   // feature 54 = 1: its row of dW1^T is the bias gradient
             }
         };
-        auto store_item = [&](Buf &B, int r, int c, const float4 &v) {
-            uint32_t h[4], l[4];
+        auto store_item = [&](Buf &B, int r, int c, const float2 &v) {
+            uint32_t h[2], l[2];
             umma::split_tf32(v.x, h[0], l[0]);
             umma::split_tf32(v.y, h[1], l[1]);
-            umma::split_tf32(v.z, h[2], l[2]);
-            umma::split_tf32(v.w, h[3], l[3]);
-            const int dst = ((r >> 2) * kLd + 4 * c) * 4 + (r & 3);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                B.hi[dst + 4 * j] = __uint_as_float(h[j]);
-                B.lo[dst + 4 * j] = __uint_as_float(l[j]);
-            }
+            const int dst = ((r >> 2) * kLd + 2 * c) * 4 + (r & 3);
+            B.hi[dst] = __uint_as_float(h[0]);
+            B.hi[dst + 4] = __uint_as_float(h[1]);
+            B.lo[dst] = __uint_as_float(l[0]);
+            B.lo[dst + 4] = __uint_as_float(l[1]);
         };
-        float4 xv;
+        float2 xv;
         load_x(0, xv);
         for (int it = 0; it < n_it; ++it) {
             const uint32_t b = (uint32_t)it & 1u;
+            const int st = it % kStages;
             Buf &B = S.buf[b];
-            const Raw &R = S.raw[b];
+            const Raw &R = S.raw[st];
             const int row0 = ((int)blockIdx.x + it * stride) * kSlab;
             // the MMAs that read buf[b] two slabs ago must have completed
             if (it >= 2) {
@@ -591,7 +558,7 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
                 umma::fence_after_thread_sync();
             }
             // X (prefetched one slab ahead), then the next slab's X starts travelling
-            if (tid < kGX * kSlab) store_item(B, tid & (kSlab - 1), tid / kSlab, xv);
+            if (tid < kPX * kSlab) store_item(B, tid & (kSlab - 1), tid / kSlab, xv);
             load_x(it + 1, xv);
             if (tid < (kSlab / 4) * 4) {   // the skew feature (index 552) of every chunk: keep it finite
                 const int dst = ((tid >> 2) * kLd + 4 * kGroups) * 4 + (tid & 3);
@@ -599,19 +566,19 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
                 B.lo[dst] = 0.f;
             }
             // the staged rows of dOut / H / dPre
-            if (!umma::mbar_wait(&S.full[b], (uint32_t)(it >> 1) & 1u)) S.timeout = 1;
-            for (int i = tid; i < (kGroups - kGX) * kSlab; i += kConv) {
-                const int r = i & (kSlab - 1), c = kGX + i / kSlab;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!umma::mbar_wait(&S.full[st], (uint32_t)(it / kStages) & 1u)) S.timeout = 1;
+            for (int i = tid; i < (kPairs - kPX) * kSlab; i += kConv) {
+                const int r = i & (kSlab - 1), c = kPX + i / kSlab;
+                float2 v = make_float2(0.f, 0.f);
                 if (row0 + r < Nv) {
-                    if (c >= kOffP) {
-                        v = *reinterpret_cast<const float4 *>(R.p + r * kRawP + 4 * (c - kOffP));
-                    } else if (c >= kOffH) {
-                        const int gi = c - kOffH;
-                        v = *reinterpret_cast<const float4 *>(R.h + r * kRawH + 4 * gi);
-                        if (gi == 13 || gi == 27 || gi == 41) v.w = 1.0f;      // column 56h + 55: bias row of head h
+                    if (c >= kPP) {
+                        v = *reinterpret_cast<const float2 *>(R.p + r * kRawP + 2 * (c - kPP));
+                    } else if (c >= kPH) {
+                        const int pi = c - kPH;
+                        v = *reinterpret_cast<const float2 *>(R.h + r * kRawH + 2 * pi);
+                        if (pi == 27 || pi == 55 || pi == 83) v.y = 1.0f;      // column 56h + 55: bias row of head h
                     } else {
-                        v = *reinterpret_cast<const float4 *>(R.o + r * kRawO + 4 * (c - kOffO));
+                        v = *reinterpret_cast<const float2 *>(R.o + r * kRawO + 2 * (c - kPO));
                     }
                 }
                 store_item(B, r, c, v);
@@ -741,14 +708,19 @@ extern "C" int cgs_neural_gaussians_backward_umma(const float *packed_bwd, const
                              (int)sizeof(ngwu::Smem));
         if (sm_count <= 0) sm_count = kNumSMs;
     }
-    StageScope sc(ST_G1_BWD, st, 2);
+    StageScope sc(ST_G1_BWD, st, 3);
+    {
+        const size_t threads = (size_t)Nv * 16;
+        neural_gaussians_postproc_backward_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+            vis_idx, Nv, offsets, scaling, mask, keep_mask, save_pre2, save_rowpos, save_tilebase, g_xyz, g_color, g_opacity,
+            g_scaling, g_rot, d_anchor, d_offsets, d_scaling, d_mask, scratch_dout);
+    }
     {
         const int tiles = (Nv + ngbu::kRows - 1) / ngbu::kRows;
         const int grid = tiles < sm_count ? tiles : sm_count;
         neural_gaussians_dgrad_umma_kernel<<<grid, ngbu::kThreads, sizeof(ngbu::Smem), st>>>(
-            packed_bwd, vis_idx, Nv, anchor, offsets, scaling, mask, campos_host[0], campos_host[1], campos_host[2],
-            keep_mask, save_pre2, save_hmask, save_rowpos, save_tilebase, g_xyz, g_color, g_opacity, g_scaling, g_rot,
-            d_anchor, d_feat, d_offsets, d_scaling, d_mask, scratch_dout, scratch_dpre, err);
+            packed_bwd, vis_idx, Nv, anchor, campos_host[0], campos_host[1], campos_host[2], save_hmask, scratch_dout,
+            d_anchor, d_feat, scratch_dpre, err);
     }
     {
         const int slabs = (Nv + ngwu::kSlab - 1) / ngwu::kSlab;
