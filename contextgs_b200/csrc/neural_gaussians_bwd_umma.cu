@@ -258,12 +258,12 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
         // ================= M1: dH_h = dOut_h W2_h =================
         if (tid == 0) {
             umma::fence_after_thread_sync();
-            umma::gemm_3xtf32(tbase + kColD1 + 0, tbase + kColAHi + 0, tbase + kColALo + 0, S.w + kOffW2ToHi,
-                              S.w + kOffW2ToLo, 64, kKo, true);
-            umma::gemm_3xtf32(tbase + kColD1 + 64, tbase + kColAHi + 16, tbase + kColALo + 16, S.w + kOffW2TcHi,
-                              S.w + kOffW2TcLo, 64, kKc, true);
-            umma::gemm_3xtf32(tbase + kColD1 + 128, tbase + kColAHi + 64, tbase + kColALo + 64, S.w + kOffW2TvHi,
-                              S.w + kOffW2TvLo, 64, kKv, true);
+            // the three heads accumulate into different columns: issued round-robin so that their dependency chains overlap
+            const umma::Gemm3x heads[3] = {
+                {tbase + kColD1 + 0, tbase + kColAHi + 0, tbase + kColALo + 0, S.w + kOffW2ToHi, S.w + kOffW2ToLo, 64, kKo},
+                {tbase + kColD1 + 64, tbase + kColAHi + 16, tbase + kColALo + 16, S.w + kOffW2TcHi, S.w + kOffW2TcLo, 64, kKc},
+                {tbase + kColD1 + 128, tbase + kColAHi + 64, tbase + kColALo + 64, S.w + kOffW2TvHi, S.w + kOffW2TvLo, 64, kKv}};
+            umma::gemm_3xtf32_interleaved<3>(heads);
             umma::umma_commit(&S.bar[0]);
         }
         if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
@@ -491,19 +491,17 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
                     const uint32_t acc = (s > 0) ? 1u : acc0;
                     const int og[3] = {0, 4, 16};
                     const uint32_t dcol[3] = {kColDo, kColDc, kColDv};
+                    // one TF32 product of each of the four accumulators in turn (independent dependency chains overlap)
 #pragma unroll
-                    for (int h = 0; h < 3; ++h) {
-                        const uint64_t a_hi = desc(hi, kOffO + og[h], s), a_lo = desc(lo, kOffO + og[h], s);
-                        const uint64_t b_hi = desc(hi, kOffH + 14 * h, s), b_lo = desc(lo, kOffH + 14 * h, s);
-                        umma::mma_tf32_ss(tbase + dcol[h], a_hi, b_lo, idesc64, acc);
-                        umma::mma_tf32_ss(tbase + dcol[h], a_lo, b_hi, idesc64, 1u);
-                        umma::mma_tf32_ss(tbase + dcol[h], a_hi, b_hi, idesc64, 1u);
+                    for (int p = 0; p < 3; ++p) {
+                        const uint32_t abase = p == 1 ? lo : hi, bbase = p == 0 ? lo : hi;
+#pragma unroll
+                        for (int h = 0; h < 3; ++h)
+                            umma::mma_tf32_ss(tbase + dcol[h], desc(abase, kOffO + og[h], s), desc(bbase, kOffH + 14 * h, s),
+                                              idesc64, p == 0 ? acc : 1u);
+                        umma::mma_tf32_ss(tbase + kColDx, desc(abase, kOffX, s), desc(bbase, kOffP, s), idesc176,
+                                          p == 0 ? acc : 1u);
                     }
-                    const uint64_t a_hi = desc(hi, kOffX, s), a_lo = desc(lo, kOffX, s);
-                    const uint64_t b_hi = desc(hi, kOffP, s), b_lo = desc(lo, kOffP, s);
-                    umma::mma_tf32_ss(tbase + kColDx, a_hi, b_lo, idesc176, acc);
-                    umma::mma_tf32_ss(tbase + kColDx, a_lo, b_hi, idesc176, 1u);
-                    umma::mma_tf32_ss(tbase + kColDx, a_hi, b_hi, idesc176, 1u);
                 }
                 umma::umma_commit(&S.mma_done[b]);
             }

@@ -380,10 +380,13 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                 umma::gemm_3xtf32(tbase + kColDo, tbase + kColD1 + 0 * kHeadStride, tbase + kColHLo + 0 * kHeadStride,
                                   S.w + kOffW2oHi, S.w + kOffW2oLo, kNo, kK1, true);
                 umma::umma_commit(&S.bar[BAR_L2O]);
-                umma::gemm_3xtf32(tbase + kColDc, tbase + kColD1 + 1 * kHeadStride, tbase + kColHLo + 1 * kHeadStride,
-                                  S.w + kOffW2cHi, S.w + kOffW2cLo, kNc, kK1, true);
-                umma::gemm_3xtf32(tbase + kColDv, tbase + kColD1 + 2 * kHeadStride, tbase + kColHLo + 2 * kHeadStride,
-                                  S.w + kOffW2vHi, S.w + kOffW2vLo, kNv, kK1, true);
+                // colour and covariance accumulate into different columns: issued round-robin (their dependency chains overlap)
+                const umma::Gemm3x cv[2] = {
+                    {tbase + kColDc, tbase + kColD1 + 1 * kHeadStride, tbase + kColHLo + 1 * kHeadStride, S.w + kOffW2cHi,
+                     S.w + kOffW2cLo, kNc, kK1},
+                    {tbase + kColDv, tbase + kColD1 + 2 * kHeadStride, tbase + kColHLo + 2 * kHeadStride, S.w + kOffW2vHi,
+                     S.w + kOffW2vLo, kNv, kK1}};
+                umma::gemm_3xtf32_interleaved<2>(cv);
                 umma::umma_commit(&S.bar[BAR_L2ALL]);
             }
             if (it > 0) {   // copy the previous tile out while the tensor core and BACK work on

@@ -196,5 +196,37 @@ __device__ __forceinline__ void gemm_3xtf32(uint32_t d_tmem, uint32_t a_hi_tmem,
     }
 }
 
+// Several INDEPENDENT 3xTF32 GEMMs (different accumulators) issued round-robin, one TF32 product of each in turn.
+// A tcgen05.mma that accumulates into the columns the previous one wrote has to wait for it; with K = 8 per
+// instruction and narrow N the instructions are far shorter than that dependency latency, so back-to-back MMAs of ONE
+// chain run at the latency, not at the throughput, of the tensor pipe.  Interleaving independent chains hides it.
+struct Gemm3x {
+    uint32_t d_tmem, a_hi_tmem, a_lo_tmem;
+    const float *w_hi, *w_lo;
+    int N, K;
+};
+template <int kCount>
+__device__ __forceinline__ void gemm_3xtf32_interleaved(const Gemm3x (&g)[kCount])
+{
+    int max_steps = 0;
+#pragma unroll
+    for (int i = 0; i < kCount; ++i) max_steps = g[i].K / 8 > max_steps ? g[i].K / 8 : max_steps;
+    for (int s = 0; s < max_steps; ++s) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int i = 0; i < kCount; ++i) {
+                if (s < g[i].K / 8) {
+                    const uint32_t lbo = (uint32_t)g[i].N * 16u;
+                    const uint32_t w = smem_u32(p == 0 ? g[i].w_lo : g[i].w_hi) + (uint32_t)s * 2u * lbo;
+                    const uint32_t a = (p == 1 ? g[i].a_lo_tmem : g[i].a_hi_tmem) + 8 * s;
+                    mma_tf32_ts(g[i].d_tmem, a, smem_desc_kmajor(w, lbo, 128u), idesc_tf32(128, g[i].N),
+                                (s == 0 && p == 0) ? 0u : 1u);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace umma
 }  // namespace cgs
