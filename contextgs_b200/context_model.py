@@ -64,6 +64,41 @@ def pack_grid_weights_umma(pc, level):
     return packed, in_dim
 
 
+def pack_grid_weights_bwd_umma(pc, level):
+    """Transposed B operands of the tcgen05 data-gradient kernel (csrc/context_model_bwd_umma.cu `cbu::DLayout`):
+    W2^T as [hidden 112][K = 176 outputs], W1^T as [input 80 | 16][K = 104 hidden], each split into TF32 hi / lo.
+    Cached per parameter version."""
+    from .neural_gaussians import umma_b_operand
+    m = pc.get_grid_mlp[level]
+    params = (m[0].weight, m[2].weight)
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    cache = _lib.object_cache(pc)
+    ent = cache.get(("grid_pack_bwd_umma", level))
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    with torch.no_grad():
+        in_dim = m[0].weight.shape[1]
+        n1 = 80 if in_dim == 71 else 16
+        packed = torch.cat([*umma_b_operand(m[2].weight.t().contiguous(), 112, 176),      # B[j][n] = W2[n][j]
+                            *umma_b_operand(m[0].weight.t().contiguous(), n1, 104)])      # B[i][h] = W1[h][i]
+        packed = packed.float().contiguous()
+    assert packed.numel() == _lib.lib().cgs_context_level_bwd_umma_packed_floats(in_dim)
+    cache[("grid_pack_bwd_umma", level)] = (key, packed)
+    return packed
+
+
+def ctx_bwd_impl():
+    """'umma' (tcgen05 kernels fed by what the training-mode forward saves; default with the tcgen05 forward) or 'simt'
+    (fp32 FMA kernel that recomputes the forward; kept for cross-checks)."""
+    import os
+    v = os.environ.get("CGS_CTX_BWD_IMPL", "umma" if ctx_impl() == "umma" else "simt")
+    if v not in ("umma", "simt"):
+        raise ValueError("CGS_CTX_BWD_IMPL must be 'umma' or 'simt'")
+    if v == "umma" and ctx_impl() != "umma":
+        raise ValueError("CGS_CTX_BWD_IMPL=umma needs the tcgen05 forward (CGS_CTX_IMPL=umma)")
+    return v
+
+
 def ctx_impl():
     """'umma' (tcgen05 tensor cores, default) or 'simt' (fp32 FMA tiles; kept for cross-checks)."""
     import os
@@ -235,7 +270,8 @@ def global_means(pc):
 
 # ----------------------------------------------------------------------------- forward core + training autograd
 
-def _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choose_u8, noise, training, return_details):
+def _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choose_u8, noise, training, return_details,
+                    save=False):
     """EntropyBottleneck kernel + one fused kernel per level (coarse -> fine).  All inputs are detached,
     contiguous [N, .] tensors.  Returns a dict with the quantised attributes, the fp64 bit sums
     ([4i..4i+3] level i: feat, scaling, offsets, chosen rows; [12] hyper) and what the backward needs."""
@@ -251,6 +287,7 @@ def _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choo
     means = global_means(pc)
     stream = _lib.stream_ptr()
     level_noise = []
+    saved = [None] * len(plan.levels)
     umma = ctx_impl() == "umma"
     err = torch.zeros(1, dtype=torch.int32, device=dev) if umma else None
     for li, lv in enumerate(plan.levels):
@@ -265,7 +302,17 @@ def _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choo
                 _lib.ptr(hyper_q), _lib.ptr(feat), _lib.ptr(scaling), _lib.ptr(offsets), _lib.ptr(masks),
                 _lib.ptr(choose_u8), _lib.ptr(nz), means[0], means[1], means[2], _lib.ptr(feat_q), _lib.ptr(scaling_q),
                 _lib.ptr(offsets_q), _lib.ptr(bits_out), _lib.ptr(sums[4 * li:4 * li + 4]))
-        if umma:
+        if umma and save:
+            # training with the tcgen05 backward: the forward leaves (mean, scale, Q), the hidden layer and its signs behind
+            packed, in_dim = pack_grid_weights_umma(pc, lv.level)
+            sv = dict(params=torch.empty((lv.n, 176), dtype=torch.float32, device=dev),
+                      h=torch.empty((lv.n, 112), dtype=torch.float32, device=dev),
+                      hmask=torch.empty((lv.n, 4), dtype=torch.int32, device=dev))
+            saved[li] = sv
+            _lib.check(L.cgs_context_level_umma_forward_train(in_dim, _lib.ptr(packed), *args, _lib.ptr(err), _lib.ptr(sv["params"]),
+                                                              _lib.ptr(sv["h"]), _lib.ptr(sv["hmask"]), stream),
+                       "cgs_context_level_umma_forward_train")
+        elif umma:
             packed, in_dim = pack_grid_weights_umma(pc, lv.level)
             _lib.check(L.cgs_context_level_umma_forward(in_dim, _lib.ptr(packed), *args, _lib.ptr(err), stream),
                        "cgs_context_level_umma_forward")
@@ -273,7 +320,7 @@ def _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choo
             packed, in_dim = pack_grid_weights(pc, lv.level)
             _lib.check(L.cgs_context_level_forward(in_dim, _lib.ptr(packed), *args, stream), "cgs_context_level_forward")
     return dict(feat_q=feat_q, scaling_q=scaling_q, offsets_q=offsets_q, hyper_q=hyper_q, lik=lik, sums=sums,
-                bits_out=bits_out, level_noise=level_noise, means=means, err=err)
+                bits_out=bits_out, level_noise=level_noise, means=means, err=err, saved=saved)
 
 
 def pack_grid_weights_bwd(m):
@@ -296,8 +343,9 @@ class _ContextModelTrain(torch.autograd.Function):
                 masks, eb_packed, *w_bwd):
         d = lambda t: t.detach().contiguous()
         anchor, hyper, feat, offsets, scaling, masks = (d(t) for t in (anchor, hyper, feat, offsets, scaling, masks))
+        bwd_impl = ctx_bwd_impl()
         out = _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choose_u8, noise, True,
-                              return_details)
+                              return_details, save=(bwd_impl == "umma"))
         s = out["sums"].tolist()  # the one host read-back of the forward
         out["sums_host"] = s
         info.update(out)
@@ -310,7 +358,11 @@ class _ContextModelTrain(torch.autograd.Function):
         # Row lists of the backward, without a host synchronisation: a stable sort moves the rows chosen for the
         # bit-rate term to the front (their count per level came back with the bit sums above).
         ctx.row_lists = []
+        ctx.bwd_impl, ctx.saved_act = bwd_impl, out["saved"]
         for li, lv in enumerate(plan.levels):
+            if bwd_impl == "umma":      # every row of a level takes the same path: no row lists
+                ctx.row_lists.append(None)
+                continue
             if lv.n == 0:
                 ctx.row_lists.append(None)
                 continue
@@ -334,11 +386,28 @@ class _ContextModelTrain(torch.autograd.Function):
         ticket = torch.zeros(4, dtype=torch.int32, device=dev)
         g_ptr = None if g_bpp is None else _lib.ptr(g_bpp.contiguous().float())
         stream = _lib.stream_ptr()
+        err_flag = None
         for li in reversed(range(len(plan.levels))):       # fine -> coarse
             lv = plan.levels[li]
             if lv.n == 0:
                 continue
             in_dim = 15 if lv.ctx_src is None else 71
+            if ctx.bwd_impl == "umma":
+                sv = ctx.saved_act[li]
+                d_out = torch.empty((lv.n, 176), dtype=torch.float32, device=dev)
+                d_pre = torch.empty((lv.n, 112), dtype=torch.float32, device=dev)
+                if err_flag is None:
+                    err_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                _lib.check(L.cgs_context_level_backward_umma(
+                    in_dim, _lib.ptr(pack_grid_weights_bwd_umma(ctx.pc, lv.level)), _lib.ptr(lv.orig), _lib.ptr(lv.ctx_src),
+                    _lib.ptr(lv.level_anchor), lv.n, _lib.ptr(anchor), _lib.ptr(hyper_q), _lib.ptr(feat_q),
+                    _lib.ptr(scaling_q), _lib.ptr(offsets_q), _lib.ptr(masks), _lib.ptr(choose_u8),
+                    _lib.ptr(ctx.level_noise[li]), ctx.means[0], ctx.means[1], ctx.means[2], g_ptr, ctx.factor,
+                    _lib.ptr(sv["params"]), _lib.ptr(sv["h"]), _lib.ptr(sv["hmask"]), _lib.ptr(G_f), _lib.ptr(G_s),
+                    _lib.ptr(G_o), _lib.ptr(d_mask), _lib.ptr(d_hyper), _lib.ptr(d_anchor), _lib.ptr(d_w[li]),
+                    _lib.ptr(d_out), _lib.ptr(d_pre), _lib.ptr(err_flag), stream), "cgs_context_level_backward_umma")
+                ctx.saved_act[li] = None
+                continue
             # rows chosen for the bit-rate term take the full kernel, the other ~85 % the 3-output one
             perm, n_full = ctx.row_lists[li]
             row_lists = ((perm[:n_full], 0), (perm[n_full:], 1))
@@ -356,6 +425,8 @@ class _ContextModelTrain(torch.autograd.Function):
             _lib.check(L.cgs_eb_backward(_lib.ptr(eb_packed), eb_packed.shape[0], _lib.ptr(hyper_q), N,
                                          _lib.ptr(choose_u8), g_ptr, ctx.factor, _lib.ptr(d_hyper), _lib.ptr(d_eb),
                                          stream), "cgs_eb_backward")
+        if err_flag is not None:
+            _lib.deferred_error_check(err_flag, "cgs_context_level_backward_umma: a tensor-core completion barrier timed out")
         return (None,) * 7 + (d_anchor, d_hyper, G_f, G_o, G_s, d_mask, d_eb, *d_w)
 
 

@@ -63,8 +63,10 @@ struct Args {
     float *feat_q, *scaling_q, *offsets_q, *bits_out;
     double *bit_sums;
     int32_t *err_flag;
-    float *params_out;   // [n_rows][176]: mean[86] | scale[86] | Q_feat Q_scaling Q_offsets | 0 (codec; optional)
+    float *params_out;   // [n_rows][176]: mean[86] | scale[86] | Q_feat Q_scaling Q_offsets | 0 (codec / backward; optional)
     int predict_only;    // 1: only params_out is produced (decoder: the attributes are not known yet)
+    float *save_h;       // [n_rows][112] hidden activations relu(D1 + b1) (training: consumed by the tcgen05 backward; optional)
+    uint32_t *save_hmask;   // [n_rows][4] their sign bits: bit (8c + j) of word pair `half` <-> hidden unit 56 half + 8c + j
 };
 
 template <int K1>
@@ -230,19 +232,35 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
             umma::fence_after_thread_sync();
             // ---- epilogue 1: hidden = relu(D1 + b1) -> hi in place, lo to region 0 (cols 56*half .. +56) ----
+            const int grow_f = tile * kRows + row;
+            float *save_row = (A.save_h && grow_f < A.n_rows) ? A.save_h + (size_t)grow_f * kN1 : nullptr;
+            uint32_t hm0 = 0u, hm1 = 0u;
 #pragma unroll 1
             for (int c = 0; c < 7; ++c) {
                 const uint32_t col = (uint32_t)(56 * half + 8 * c);
                 uint32_t v[8], hi[8], lo[8];
+                float h[8];
+                uint32_t bits = 0u;
                 umma::tmem_ld8(tl + kColD1 + col, v);
                 umma::tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float h = fmaxf(__uint_as_float(v[j]) + S.w[LY::kOffB1 + col + j], 0.f);
-                    umma::split_tf32(h, hi[j], lo[j]);
+                    h[j] = fmaxf(__uint_as_float(v[j]) + S.w[LY::kOffB1 + col + j], 0.f);
+                    umma::split_tf32(h[j], hi[j], lo[j]);
+                    bits |= h[j] > 0.f ? (1u << j) : 0u;
                 }
                 umma::tmem_st8(tl + kColD1 + col, hi);
                 umma::tmem_st8(tl + kColHLo + col, lo);
+                if (save_row) {
+                    reinterpret_cast<float4 *>(save_row + col)[0] = make_float4(h[0], h[1], h[2], h[3]);
+                    reinterpret_cast<float4 *>(save_row + col)[1] = make_float4(h[4], h[5], h[6], h[7]);
+                    if (c < 4) hm0 |= bits << (8 * c);
+                    else hm1 |= bits << (8 * (c - 4));
+                }
+            }
+            if (save_row) {
+                A.save_hmask[(size_t)grow_f * 4 + 2 * half] = hm0;
+                A.save_hmask[(size_t)grow_f * 4 + 2 * half + 1] = hm1;
             }
             umma::tmem_wait_st();
             umma::fence_before_thread_sync();
@@ -427,6 +445,40 @@ extern "C" int cgs_context_level_umma_forward(int in_dim, const float *packed_w,
                                              feat_q, scaling_q, offsets_q, bits_out, bit_sums, err_flag, nullptr, 0, stream);
 }
 
+extern "C" int cgs_context_level_umma_forward_train(int in_dim, const float *packed_w, const int32_t *orig_idx,
+                                                    const int32_t *ctx_src, const float *level_anchor, int n_rows,
+                                                    const float *anchor, const float *hyper_q, const float *feat,
+                                                    const float *scaling, const float *offsets, const float *mask,
+                                                    const uint8_t *choose, const float *noise, float feat_mean,
+                                                    float scaling_mean, float offset_mean, float *feat_q, float *scaling_q,
+                                                    float *offsets_q, float *bits_out, double *bit_sums, int32_t *err_flag,
+                                                    float *params_out, float *save_h, uint32_t *save_hmask, void *stream)
+{
+    if (n_rows <= 0) return 0;
+    CGS_CHECK_PTR(packed_w); CGS_CHECK_PTR(orig_idx); CGS_CHECK_PTR(anchor); CGS_CHECK_PTR(hyper_q);
+    CGS_CHECK_PTR(feat_q); CGS_CHECK_PTR(scaling_q); CGS_CHECK_PTR(bit_sums); CGS_CHECK_PTR(err_flag);
+    CGS_CHECK_PTR(feat); CGS_CHECK_PTR(scaling); CGS_CHECK_PTR(offsets); CGS_CHECK_PTR(mask); CGS_CHECK_PTR(offsets_q);
+    CGS_CHECK_PTR(params_out); CGS_CHECK_PTR(save_h); CGS_CHECK_PTR(save_hmask);
+    cmu::Args a;
+    a.params_out = params_out; a.predict_only = 0; a.save_h = save_h; a.save_hmask = save_hmask;
+    a.packed_w = packed_w; a.orig_idx = orig_idx; a.ctx_src = ctx_src; a.level_anchor = level_anchor; a.n_rows = n_rows;
+    a.anchor = anchor; a.hyper_q = hyper_q; a.feat = feat; a.scaling = scaling; a.offsets = offsets; a.mask = mask;
+    a.choose = choose; a.noise = noise; a.feat_mean = feat_mean; a.scaling_mean = scaling_mean;
+    a.offset_mean = offset_mean; a.feat_q = feat_q; a.scaling_q = scaling_q; a.offsets_q = offsets_q;
+    a.bits_out = bits_out; a.bit_sums = bit_sums; a.err_flag = err_flag;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (in_dim == 71) {
+        CGS_CHECK_PTR(ctx_src);
+        return cmu::launch<71>(a, st);
+    }
+    if (in_dim == 15) {
+        CGS_CHECK_PTR(level_anchor);
+        return cmu::launch<15>(a, st);
+    }
+    set_error("%s: unsupported context-MLP input width %d", __func__, in_dim);
+    return -2;
+}
+
 extern "C" int cgs_context_level_umma_forward_ex(int in_dim, const float *packed_w, const int32_t *orig_idx,
                                                  const int32_t *ctx_src, const float *level_anchor, int n_rows,
                                                  const float *anchor, const float *hyper_q, const float *feat,
@@ -445,7 +497,7 @@ extern "C" int cgs_context_level_umma_forward_ex(int in_dim, const float *packed
         CGS_CHECK_PTR(feat); CGS_CHECK_PTR(scaling); CGS_CHECK_PTR(offsets); CGS_CHECK_PTR(mask); CGS_CHECK_PTR(offsets_q);
     }
     cmu::Args a;
-    a.params_out = params_out; a.predict_only = predict_only;
+    a.params_out = params_out; a.predict_only = predict_only; a.save_h = nullptr; a.save_hmask = nullptr;
     a.packed_w = packed_w; a.orig_idx = orig_idx; a.ctx_src = ctx_src; a.level_anchor = level_anchor; a.n_rows = n_rows;
     a.anchor = anchor; a.hyper_q = hyper_q; a.feat = feat; a.scaling = scaling; a.offsets = offsets; a.mask = mask;
     a.choose = choose; a.noise = noise; a.feat_mean = feat_mean; a.scaling_mean = scaling_mean;

@@ -370,6 +370,37 @@ CGS_API int cgs_context_level_umma_forward_ex(int in_dim, const float *packed_w,
                                               float *offsets_q, float *bits_out, double *bit_sums, int32_t *err_flag,
                                               float *params_out, int predict_only, void *stream);
 
+/* Training-mode variant of cgs_context_level_umma_forward (scene/gaussian_model.py:1596-1652 with training=True): same
+ * outputs, and additionally params_out[n_rows,176] (mean[86] | scale[86] | Q_feat Q_scaling Q_offsets | 0, biases applied),
+ * save_h[n_rows,112] (hidden activations) and save_hmask[n_rows,4] (their sign bits) for the tcgen05 backward. */
+CGS_API int cgs_context_level_umma_forward_train(int in_dim, const float *packed_w, const int32_t *orig_idx,
+                                                 const int32_t *ctx_src, const float *level_anchor, int n_rows,
+                                                 const float *anchor, const float *hyper_q, const float *feat,
+                                                 const float *scaling, const float *offsets, const float *mask,
+                                                 const uint8_t *choose, const float *noise, float feat_mean,
+                                                 float scaling_mean, float offset_mean, float *feat_q, float *scaling_q,
+                                                 float *offsets_q, float *bits_out, double *bit_sums, int32_t *err_flag,
+                                                 float *params_out, float *save_h, uint32_t *save_hmask, void *stream);
+
+/* Backward of one level on the tcgen05 tensor cores (csrc/context_model_bwd_umma.cu): same gradients and in / out
+ * conventions as cgs_context_level_backward below (reference: autograd through scene/gaussian_model.py:1596-1652,
+ * 1666-1670 and utils/entropy_models.py:30-50,141-156), over ALL rows of the level, fed by what
+ * cgs_context_level_umma_forward_train saved.  packed_bwd: cgs_context_level_bwd_umma_packed_floats(in_dim) floats
+ * (contextgs_b200/context_model.py pack_grid_weights_bwd_umma: W2^T and W1^T as K-major B operands, TF32 hi / lo);
+ * d_packed_w: the gradient in the layout of cgs_context_level_backward (accumulated).  scratch_dout[n_rows,176],
+ * scratch_dpre[n_rows,112]: hand-over between the three kernels.  *err (device, caller-zeroed): completion time-out. */
+CGS_API int cgs_context_level_bwd_umma_packed_floats(int in_dim);
+CGS_API int cgs_context_level_backward_umma(int in_dim, const float *packed_bwd, const int32_t *orig_idx,
+                                            const int32_t *ctx_src, const float *level_anchor, int n_rows,
+                                            const float *anchor, const float *hyper_q, const float *feat_q,
+                                            const float *scaling_q, const float *offsets_q, const float *mask,
+                                            const uint8_t *choose, const float *noise, float feat_mean,
+                                            float scaling_mean, float offset_mean, const float *g_bits_dev,
+                                            float bits_factor, const float *params, const float *save_h,
+                                            const uint32_t *save_hmask, float *G_feat, float *G_scaling, float *G_offsets,
+                                            float *d_mask, float *d_hyper_q, float *d_anchor, float *d_packed_w,
+                                            float *scratch_dout, float *scratch_dpre, int32_t *err, void *stream);
+
 /* Backward of one level in TRAINING mode (noise != NULL in the forward): what autograd does in the
  * reference for the loop body scene/gaussian_model.py:1562-1652 plus the Entropy_gaussian terms of
  * bit_per_param (:1666-1693).  Launch fine -> coarse.  G_feat/G_scaling/G_offsets [N,*] hold the gradient

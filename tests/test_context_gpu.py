@@ -9,7 +9,7 @@ from contextgs_b200.context_model import build_level_plan, multi_scale_generatin
 from contextgs_b200.encodings import Quantize_anchor, STE_multistep
 from contextgs_b200.entropy_models import Entropy_gaussian
 from oracle import entropy_ref as er
-from tests.helpers import T, cuda_model, fixture_model, load_npz, reference_noise, rel_l2
+from tests.helpers import T, cuda_model, fixture_model, load_npz, reference_noise, rel_l2, rel_l2_rows
 
 pytestmark = pytest.mark.gpu
 REL_L2 = 1e-4
@@ -382,6 +382,49 @@ def test_training_backward_matches_autograd_of_the_oracle(LAM, TOL, BODY):
         for ours, theirs in zip(list(model.latent_codec.matrices) + list(model.latent_codec.biases) +
                                 list(model.latent_codec.factors), eb.matrices + eb.biases + eb.factors):
             assert rel_l2(ours.grad.cpu().numpy(), theirs.grad.numpy()) < TOL, "entropy bottleneck"
+
+
+def test_backward_umma_matches_simt_many_tiles(ctx_impl, monkeypatch):
+    """300 k anchors: every persistent CTA of the tcgen05 backward kernels runs many tiles / slabs per level (mbarrier
+    parities, TMEM regions, TMA stages and operand buffers wrap many times).  The fp32-FMA backward (which recomputes the
+    forward) is independent code; both run behind the same tcgen05 forward, with the same noise."""
+    if ctx_impl == "simt":
+        pytest.skip("compares the two backward implementations once")
+    from contextgs_b200 import _lib
+    N = 300_000
+    scene = synthetic.make_scene("bicycle", N, seed=3)
+    pc = er.make_model(scene)
+    grads = {}
+    g = torch.Generator().manual_seed(5)
+    wf, ws, wo = torch.randn(N, 50, generator=g).cuda(), torch.randn(N, 6, generator=g).cuda(), \
+        torch.randn(N, 10, 3, generator=g).cuda()
+    noise = None
+    for impl in ("umma", "simt"):
+        monkeypatch.setenv("CGS_CTX_BWD_IMPL", impl)
+        model = cuda_model(scene, pc).train()
+        if noise is None:
+            plan = build_level_plan(model, model.get_anchor.detach(), model.get_mask_anchor)
+            noise = reference_noise(N, [lv.n for lv in plan.levels], seed=11)
+        res = multi_scale_generating(model, model.get_anchor.detach(), model._hyper_latent, model._anchor_feat, model._offset,
+                                     model.get_scaling, model.get_mask, model.get_mask_anchor, predict_bpp=True,
+                                     training=True, noise=noise)
+        ((res[0] * wf).sum() + (res[1] * ws).sum() + (res[2] * wo).sum() + 50.0 * res[3]).backward()
+        torch.cuda.synchronize()
+        _lib.raise_deferred()
+        grads[impl] = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    names = sorted(grads["simt"])
+    assert {"_anchor_feat", "_offset", "_scaling", "_mask", "_hyper_latent"} <= set(names)
+    errs, outl = {}, {}
+    for n in names:
+        a, b = grads["umma"][n].cpu().numpy(), grads["simt"][n].cpu().numpy()
+        if n.startswith("_") and a.ndim >= 2 and a.shape[0] == N:
+            outl[n], errs[n] = rel_l2_rows(a, b)        # per-anchor gradients pass through the hidden layer's ReLU kink
+        else:
+            errs[n] = rel_l2(a, b)
+    print("context backward umma vs simt rel-L2:", {k: f"{v:.2e}" for k, v in errs.items()}, "outlier rows", outl)
+    assert all(v < 2e-3 for v in outl.values()), outl
+    bad = {k: v for k, v in errs.items() if not v < (1e-4 if k.startswith("_") else 3e-3)}
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("n,scale", [(1, 2.0), (7, 1.5), (2048, 3.0), (2049, 1.0), (300_001, 7.3)])
