@@ -325,9 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             }
             if (half == 0 && chosen) n_chosen += 1.f;
             float *prow = (A.params_out && o >= 0) ? A.params_out + (size_t)grow * kLdG2 : nullptr;
-            if (prow && half == 0) {
-                prow[172] = Qf; prow[173] = Qs; prow[174] = Qo; prow[175] = 0.f;
-            }
+            if (prow && half == 0) *reinterpret_cast<float4 *>(prow + 172) = make_float4(Qf, Qs, Qo, 0.f);
             const float *nz = A.noise ? A.noise + (size_t)grow * kCE : nullptr;
 #pragma unroll 1
             for (int c = 0; c < 3; ++c) {
@@ -345,15 +343,27 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                 const float x_mean = cd.grp == 0 ? A.feat_mean : (cd.grp == 1 ? A.scaling_mean : A.offset_mean);
                 float *dst = (cd.grp == 0 ? A.feat_q : (cd.grp == 1 ? A.scaling_q : A.offsets_q)) + o * cd.dim + cd.k0;
                 float acc = 0.f;
+                if (prow) {
+                    // (mean, scale) of the group as 8-byte stores (every group starts on an even index and holds an even
+                    // number of values; scalar stores cost one 32-byte sector transaction per value and doubled the
+                    // kernel's time when the training path started to save them)
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        if (j < cd.cnt) {
+                            *reinterpret_cast<float2 *>(prow + cd.j0 + j) =
+                                make_float2(__uint_as_float(vm[j]) + S.w[LY::kOffB2 + cd.mu_col + j],
+                                            __uint_as_float(vm[j + 1]) + S.w[LY::kOffB2 + cd.mu_col + j + 1]);
+                            *reinterpret_cast<float2 *>(prow + kCE + cd.j0 + j) =
+                                make_float2(__uint_as_float(vs[j]) + S.w[LY::kOffB2 + cd.sg_col + j],
+                                            __uint_as_float(vs[j + 1]) + S.w[LY::kOffB2 + cd.sg_col + j + 1]);
+                        }
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (j < cd.cnt) {
                         const float mean = __uint_as_float(vm[j]) + S.w[LY::kOffB2 + cd.mu_col + j];
                         const float scale = __uint_as_float(vs[j]) + S.w[LY::kOffB2 + cd.sg_col + j];
-                        if (prow) {
-                            prow[cd.j0 + j] = mean;
-                            prow[kCE + cd.j0 + j] = scale;
-                        }
                         if (pred) continue;
                         const float x = xc[j];
                         const float xq = nz ? x + nz[cd.j0 + j] * Q : ste_round(x, Q);

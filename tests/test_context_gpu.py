@@ -403,7 +403,11 @@ def test_backward_umma_matches_simt_many_tiles(ctx_impl, monkeypatch):
         monkeypatch.setenv("CGS_CTX_BWD_IMPL", impl)
         model = cuda_model(scene, pc).train()
         if noise is None:
-            plan = build_level_plan(model, model.get_anchor.detach(), model.get_mask_anchor)
+            from contextgs_b200.context_model import find_divide_scale
+            a0 = model.get_anchor.detach()
+            pc.level_scale = find_divide_scale(model, a0[model.get_mask_anchor], model.target_ratio, model.level_num)
+            model.level_scale = list(pc.level_scale)
+            plan = build_level_plan(model, a0, model.get_mask_anchor)
             noise = reference_noise(N, [lv.n for lv in plan.levels], seed=11)
         res = multi_scale_generating(model, model.get_anchor.detach(), model._hyper_latent, model._anchor_feat, model._offset,
                                      model.get_scaling, model.get_mask, model.get_mask_anchor, predict_bpp=True,
