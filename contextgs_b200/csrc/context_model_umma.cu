@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                 const float x_mean = cd.grp == 0 ? A.feat_mean : (cd.grp == 1 ? A.scaling_mean : A.offset_mean);
                 float *dst = (cd.grp == 0 ? A.feat_q : (cd.grp == 1 ? A.scaling_q : A.offsets_q)) + o * cd.dim + cd.k0;
                 float acc = 0.f;
-                if (prow) {
+                if (prow && (chosen || !A.save_h)) {   // training: the backward reads (mean, scale) of the chosen rows only
                     // (mean, scale) of the group as 8-byte stores (every group starts on an even index and holds an even
                     // number of values; scalar stores cost one 32-byte sector transaction per value and doubled the
                     // kernel's time when the training path started to save them)
