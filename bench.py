@@ -425,9 +425,31 @@ def main():
             traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo, "ms_per_launch": top_ms,
-                "note": "render_fwd/bwd are FP32/SFU-issue bound per (pixel, instance), not HBM bound (SURVEY 8a R6); "
-                        "HBM fraction reported as the contract requires"}
+                "algorithmic_bytes_per_launch": algo, "ms_per_launch": top_ms}
+    # Instruction-issue roofline of the same kernel: the blend loop is bound by FP32 / SFU instruction issue per
+    # (pixel, instance), not by HBM.  Executed warp instructions come from the tracked ncu capture, scaled
+    # by the instance count; peak = SMs x 4 schedulers x the SM clock sampled during the timed region.
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            t = json.load(f).get(top) or {}
+        if t.get("inst_executed") and counts.get("R"):
+            sm_hz = 1e6 * float(clocks.get("sm_mhz") or 1965.0)
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            inst = t["inst_executed"] * counts["R"] / float(t["inst_at_R"])
+            a_issue, p_issue = inst / (top_ms * 1e-3) / 1e9, n_sm * 4 * sm_hz / 1e9
+            roofline["issue"] = {"achieved": a_issue, "peak": p_issue, "unit": "G warp-instructions/s",
+                                 "frac": a_issue / p_issue, "warp_instructions_per_launch": inst,
+                                 "source": t.get("inst_source")}
+            roofline["true_limiter"] = "issue" if a_issue / p_issue > achieved / peak else "hbm"
+    roofline["note"] = ("`bound`/`frac` are the HBM roofline the contract asks for; render_fwd / render_bwd are limited by "
+                        "instruction issue (see `issue`), every other frame stage by HBM or latency (see roofline_stages)")
+    # per-stage table: algorithmic bytes of SURVEY.md 8d / DESIGN.md section 4 over the stage's measured time
+    stage_table = {}
+    for k, v in per_frame.items():
+        if k in ALGO_BYTES and v > 0:
+            ab = ALGO_BYTES[k](counts)
+            stage_table[k] = {"ms": round(v, 4), "algorithmic_mb": round(ab / 1e6, 2), "gb_per_s": round(ab / (v * 1e-3) / 1e9, 1),
+                              "frac_of_hbm_peak": round(ab / (v * 1e-3) / 1e9 / peak, 4)}
 
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -437,7 +459,7 @@ def main():
                 "d2h_bytes_per_step": 3 * H * W * 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches_total), "clocks": clocks, "roofline": roofline,
         "stage_ms_per_frame": {k: round(v, 4) for k, v in sorted(per_frame.items(), key=lambda kv: -kv[1])},
-        "counts": counts,
+        "roofline_stages": stage_table, "counts": counts,
     }
 
     # ---- extras: training-side rasterizer fwd+bwd and the entropy scoring pass -----------------
@@ -463,6 +485,12 @@ def main():
     elif "cpu_baseline" not in line:
         line["cpu_baseline"] = None
 
+    # the data-parallel training figures go LAST in the line (a tail of the output keeps them)
+    if world > 1 and "extras" in line:
+        line["dp_training"] = {k: line["extras"][k] for k in list(line["extras"]) if "dp_allreduce" in k or k == "grad_bucket_mb"}
+        line["dp_training"]["note"] = ("iterations/s summed over the ranks: forward + backward of one camera per rank + ONE NCCL "
+                                       "all-reduce of the flat fp32 gradient bucket per step (BASELINE configs[4] shape of work "
+                                       "at the bench's 1.5 M anchors)")
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -503,6 +531,27 @@ def extras(args, pc, pc_train, cams_dev, my_cam, pipe, bg, timed, world, dev):
     ex["train_iter_per_s_render_only"] = world * k / (ms * 1e-3)
     ms = timed(lambda i: train_step(i, 20000), k, 3)
     ex["train_iter_per_s_with_context_model"] = world * k / (ms * 1e-3)
+    # stage-timed pass of the full training iteration (library-side CUDA events around every stage) with the HBM
+    # roofline of the two tcgen05 backward stages: algorithmic bytes per SURVEY.md 8d (backward = 2 x forward)
+    from contextgs_b200 import _lib as _L
+    _L.stage_timing(True)
+    for i in range(3):
+        train_step(i, 20000)
+    torch.cuda.synchronize()
+    st_ms, st_n = _L.stage_timing_read()
+    _L.stage_timing(False)
+    ex["train_stage_ms_per_iter"] = {kk: round(v / 3, 4) for kk, v in sorted(st_ms.items(), key=lambda kv: -kv[1]) if st_n[kk] > 0}
+    with torch.no_grad():
+        vis0 = prefilter_voxel(cams_dev[my_cam(0)], pc_train, pipe, bg)
+    nv, n_all = int(vis0.sum()), int(pc_train._anchor.shape[0])
+    hbm_peak = peaks()[0]
+    bwd_roof = {}
+    for key, bytes_ in (("neural_gaussians_bwd", 2.0 * (446.0 * nv + 56.0 * 4.7 * nv)), ("context_level_bwd", 2.0 * 1024.0 * n_all)):
+        ms_k = ex["train_stage_ms_per_iter"].get(key)
+        if ms_k:
+            bwd_roof[key] = {"ms": ms_k, "algorithmic_mb": round(bytes_ / 1e6, 1), "gb_per_s": round(bytes_ / (ms_k * 1e-3) / 1e9, 1),
+                             "frac_of_hbm_peak": round(bytes_ / (ms_k * 1e-3) / 1e9 / hbm_peak, 4)}
+    ex["train_backward_roofline"] = bwd_roof
     if world > 1:
         # data-parallel training step (BASELINE configs[4]): every rank renders its own camera, the
         # gradients of all parameters land in ONE flat fp32 bucket that is all-reduced (NCCL, sum / world) per step

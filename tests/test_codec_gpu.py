@@ -100,6 +100,63 @@ def test_table_streams_are_byte_identical_to_the_cpu_range_coder():
     assert codec_ref.encode(syms, lambda i: i % 12, tabs) == enc.hyper_bytes.cpu().numpy().tobytes()[:n0]
 
 
+def test_gaussian_streams_decode_with_an_independent_table_decoder():
+    """Independent check of the Gaussian-CDF streams (the counterpart of utils/encodings.py:119-144, where the reference
+    materialises a dense [symbols, alphabet] CDF tensor per chunk and hands it to torchac): the bytes the GPU coder wrote are
+    decoded by the plain-Python range decoder of oracle/codec_ref.py from DENSE per-symbol cumulative-frequency tables
+    built with torch ops (C(i) = min(rn(Phi(((smin + i) - 1/2) Q) (65536 - L)), 65536 - L) + i, the formula of
+    DESIGN.md section 4) -- neither the closed-form evaluation nor the search of the GPU decoder is involved.  The encoder
+    side is checked too: re-encoding the decoded symbols on the CPU reproduces the GPU's bytes."""
+    pc = _model(700)
+    enc = codec.encode_model(pc, chunk_rows=4)
+    q = enc.quantised
+    dev = q["feat"].device
+    means = codec.global_means(pc)
+    sums = torch.zeros(16, dtype=torch.float64, device=dev)
+    terr = torch.zeros(1, dtype=torch.int32, device=dev)
+    checked = 0
+    for li, (lv, coded) in enumerate(zip(enc.plan.levels, enc.levels)):
+        if lv.n == 0:
+            continue
+        fq, sq, oq = q["feat"].clone(), q["scaling"].clone(), q["offsets"].clone()
+        params = codec._level_params(pc, lv, q["anchor"], q["hyper"] * (0 if pc.disable_hyper else 1), None, None, None, None,
+                                     fq, sq, oq, sums[4 * li:4 * li + 4], terr, means, True)
+        for attr, (name, dim) in enumerate(codec.ATTRS):
+            st = coded.streams[name]
+            smin, smax = (int(v) for v in st.minmax.tolist())
+            L = smax - smin + 1
+            col0 = (0, 50, 56)[attr]
+            rows = 4 * codec.ATTR_CHUNK_MULT[attr]
+            values = (q["feat"], q["scaling"], q["offsets"])[attr]
+            data = st.bytes.cpu().numpy().tobytes()
+            off = 0
+            for c, nbytes in enumerate(st.lens.tolist()[:3]):          # the first chunks of every stream
+                r0, r1 = c * rows, min((c + 1) * rows, lv.n)
+                o = lv.orig[r0:r1].long()
+                pr = params[r0:r1]
+                Q = pr[:, 172 + attr:173 + attr]
+                mean, scale = pr[:, col0:col0 + dim], pr[:, 86 + col0:86 + col0 + dim]
+                inv = torch.reciprocal(torch.clamp(scale, min=1e-9))
+                x = values[o]
+                keep = torch.ones_like(x, dtype=torch.bool) if attr != 2 else \
+                    (q["masks"][o].repeat_interleave(3, dim=1) != 0)
+                sym = torch.round(x / Q).to(torch.int64) - smin
+                # dense tables: boundary i of every symbol position, i = 0 .. L
+                i = torch.arange(L + 1, device=dev, dtype=torch.float32).view(1, 1, -1)
+                z = ((smin + i) - 0.5) * Q.unsqueeze(-1)
+                phi = 0.5 * (1.0 + torch.erf((z - mean.unsqueeze(-1)) * inv.unsqueeze(-1) * 0.70710678118654752))
+                M = float(65536 - L)
+                tab = (torch.clamp(torch.round(phi * M), max=M) + i).to(torch.int64)
+                tabs = tab[keep].cpu().tolist()
+                syms = sym[keep].cpu().tolist()
+                chunk = data[off:off + nbytes]
+                off += nbytes
+                assert codec_ref.decode(chunk, len(syms), lambda k: k, tabs) == syms, (li, name, c)
+                assert codec_ref.encode(syms, lambda k: k, tabs) == chunk, (li, name, c)
+                checked += len(syms)
+    assert checked > 2000 and int(terr.item()) == 0
+
+
 def test_directory_round_trip_and_render(tmp_path):
     pc = _model(5000, kind="chair")
     summary = pc.conduct_encoding(str(tmp_path))
