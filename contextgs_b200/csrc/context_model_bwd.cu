@@ -417,7 +417,10 @@ __device__ __forceinline__ float eb_logits_backward(const float *__restrict__ p,
 }
 
 // d hyper[e] (+)= w * d(-log2 lik)/d hyper_q for chosen anchors; d_params[C,59] += ...
-__global__ void __launch_bounds__(256)
+// Every thread stays on ONE channel (the grid stride is a multiple of C), so the 58 parameter gradients of the channel
+// accumulate in REGISTERS over all the elements the thread visits and reach shared memory once per thread (the first
+// version did 58 shared-memory atomics per element: 0.87 ms for 1.5 M anchors, most of it serialised atomics).
+__global__ void __launch_bounds__(192)
 eb_backward_kernel(const float *__restrict__ params, int C, const float *__restrict__ hyper_q, int N,
                    const uint8_t *__restrict__ choose, const float *__restrict__ g_bits_dev, float bits_factor,
                    float *__restrict__ d_hyper, float *__restrict__ d_params)
@@ -431,19 +434,19 @@ eb_backward_kernel(const float *__restrict__ params, int C, const float *__restr
     __syncthreads();
     const float w = __ldg(g_bits_dev) * bits_factor;
     const size_t total = (size_t)N * C;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;       // a multiple of C (host): e % C is constant per thread
+    const size_t e0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (int)(e0 % C);
+    const float *p = sp + c * kEbParams;
+    float dp[kEbParams];
+#pragma unroll
+    for (int i = 0; i < kEbParams; ++i) dp[i] = 0.f;
+    bool any = false;
+    for (size_t e = e0; e < total; e += stride) {
         if (w == 0.f || (choose && !choose[e / C])) continue;
-        const int c = (int)(e % C);
-        const float *p = sp + c * kEbParams;
         const float out = hyper_q[e];
-        float dummy[kEbParams];
-        // forward quantities
         float lower, upper;
         {
-            // logits without gradient bookkeeping (g = 0 keeps dp untouched up to +0)
-#pragma unroll
-            for (int i = 0; i < kEbParams; ++i) dummy[i] = 0.f;
-            // reuse the backward routine's forward part through a cheap re-evaluation
             float l[3], m[3];
             for (int side = 0; side < 2; ++side) {
                 const float v = out + (side ? 0.5f : -0.5f);
@@ -481,16 +484,15 @@ eb_backward_kernel(const float *__restrict__ params, int C, const float *__restr
         const float sd = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
         const float g_upper = g_lik * sd * a * (1.0f - a) * sign;
         const float g_lower = -g_lik * sd * b * (1.0f - b) * sign;
-        float dp[kEbParams];
-#pragma unroll
-        for (int i = 0; i < kEbParams; ++i) dp[i] = 0.f;
         float gv = eb_logits_backward(p, out + 0.5f, g_upper, dp);
         gv += eb_logits_backward(p, out - 0.5f, g_lower, dp);
         d_hyper[e] += gv;
+        any = true;
+    }
+    if (any) {
 #pragma unroll
         for (int i = 0; i < kEbParams - 1; ++i)
             if (dp[i] != 0.f) atomicAdd(&sg[c * kEbParams + i], dp[i]);
-        (void)dummy;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < C * kEbParams; i += blockDim.x)
@@ -598,9 +600,11 @@ extern "C" int cgs_eb_backward(const float *packed_params, int C, const float *h
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t total = (size_t)N * C;
-    const int grid = (int)min((size_t)kNumSMs * 8, (total + 255) / 256);
+    // block size = a multiple of C, so that the grid stride keeps every thread on one channel
+    const int block = C <= 192 ? (192 / C) * C : C;
+    const int grid = (int)min((size_t)kNumSMs * 8, (total + block - 1) / block);
     StageScope sc(ST_EB, st, 1);
-    cmb::eb_backward_kernel<<<grid, 256, 2 * C * cmb::kEbParams * sizeof(float), st>>>(
+    cmb::eb_backward_kernel<<<grid, block, 2 * C * cmb::kEbParams * sizeof(float), st>>>(
         packed_params, C, hyper_q, N, choose, g_bits_dev, bits_factor, d_hyper, d_packed_params);
     return check_launch(__func__);
 }
