@@ -344,6 +344,25 @@ class _ContextModelTrain(torch.autograd.Function):
         d = lambda t: t.detach().contiguous()
         anchor, hyper, feat, offsets, scaling, masks = (d(t) for t in (anchor, hyper, feat, offsets, scaling, masks))
         bwd_impl = ctx_bwd_impl()
+        if bwd_impl == "umma":
+            # The rows of a level are independent, so the training pass is free to order them: rows chosen for the bit-rate
+            # term first.  Everything the forward saves is then in that order and the backward treats the two CONTIGUOUS
+            # ranges differently (the ~85 % not chosen have an output gradient with three non-zero columns).
+            levels, lv_noise = [], []
+            for li, lv in enumerate(plan.levels):
+                if lv.n == 0:
+                    levels.append(lv)
+                    lv_noise.append(None)
+                    continue
+                perm = torch.argsort(choose_u8[lv.orig.long()] == 0, stable=True)
+                levels.append(SimpleNamespace(
+                    level=lv.level, n=lv.n, orig=lv.orig[perm].contiguous(),
+                    ctx_src=None if lv.ctx_src is None else lv.ctx_src[perm].contiguous(),
+                    level_anchor=None if lv.level_anchor is None else lv.level_anchor[perm].contiguous()))
+                lv_noise.append(None if noise is None else noise["levels"][li].to(anchor.device)[perm].contiguous())
+            plan = SimpleNamespace(N=plan.N, levels=levels)
+            if noise is not None:
+                noise = dict(noise, levels=lv_noise)
         out = _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choose_u8, noise, True,
                               return_details, save=(bwd_impl == "umma"))
         s = out["sums"].tolist()  # the one host read-back of the forward
@@ -360,8 +379,8 @@ class _ContextModelTrain(torch.autograd.Function):
         ctx.row_lists = []
         ctx.bwd_impl, ctx.saved_act = bwd_impl, out["saved"]
         for li, lv in enumerate(plan.levels):
-            if bwd_impl == "umma":      # every row of a level takes the same path: no row lists
-                ctx.row_lists.append(None)
+            if bwd_impl == "umma":      # rows [0, n_full) are the chosen ones (ordered above): no row lists
+                ctx.row_lists.append((None, int(round(s[4 * li + 3]))))
                 continue
             if lv.n == 0:
                 ctx.row_lists.append(None)
@@ -405,7 +424,8 @@ class _ContextModelTrain(torch.autograd.Function):
                     _lib.ptr(ctx.level_noise[li]), ctx.means[0], ctx.means[1], ctx.means[2], g_ptr, ctx.factor,
                     _lib.ptr(sv["params"]), _lib.ptr(sv["h"]), _lib.ptr(sv["hmask"]), _lib.ptr(G_f), _lib.ptr(G_s),
                     _lib.ptr(G_o), _lib.ptr(d_mask), _lib.ptr(d_hyper), _lib.ptr(d_anchor), _lib.ptr(d_w[li]),
-                    _lib.ptr(d_out), _lib.ptr(d_pre), _lib.ptr(err_flag), stream), "cgs_context_level_backward_umma")
+                    _lib.ptr(d_out), _lib.ptr(d_pre), _lib.ptr(err_flag), 0 if g_ptr is None else ctx.row_lists[li][1], stream),
+                    "cgs_context_level_backward_umma")
                 ctx.saved_act[li] = None
                 continue
             # rows chosen for the bit-rate term take the full kernel, the other ~85 % the 3-output one

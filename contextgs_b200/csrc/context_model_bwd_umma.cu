@@ -52,7 +52,7 @@ __device__ __forceinline__ void bits_grad(float x0, float mu, float s0, float q,
 
 struct ElemArgs {
     const int *orig_idx;
-    int n_rows;
+    int row0, n_rows;                              // level rows [row0, row0 + n_rows)
     const float *params;                           // [n_rows,176] forward: mean[86] | scale[86] | Q[3] | 0
     const float *feat_q, *scaling_q, *offsets_q;   // forward outputs [N,*]
     const float *mask;                             // [N,10]
@@ -66,14 +66,17 @@ struct ElemArgs {
     float *d_out;                                  // [n_rows,176] gradient of the context MLP's output
 };
 
+// LITE: rows that are NOT chosen for the bit-rate term (the training forward orders every level so that the chosen rows come
+// first): only the three step columns of dOut are non-zero, so the 8-column chunk [168,176) is all that is written.
+template <bool LITE>
 __global__ void __launch_bounds__(256) context_level_bwd_elem_kernel(ElemArgs A)
 {
     const int lane = threadIdx.x & 31;
-    const int row = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (row >= A.n_rows) return;
+    const int row = A.row0 + (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (row >= A.row0 + A.n_rows) return;
     const int o = __ldg(A.orig_idx + row);
-    const float wbits = A.g_bits_dev ? __ldg(A.g_bits_dev) * A.bits_factor : 0.f;
-    const bool chosen = wbits != 0.f && (A.choose ? A.choose[o] != 0 : true);
+    const float wbits = (!LITE && A.g_bits_dev) ? __ldg(A.g_bits_dev) * A.bits_factor : 0.f;
+    const bool chosen = !LITE && wbits != 0.f && (A.choose ? A.choose[o] != 0 : true);
     const float *prow = A.params + (size_t)row * kOut;
     float *drow = A.d_out + (size_t)row * kOut;
     const float Qg[3] = {__ldg(prow + 172), __ldg(prow + 173), __ldg(prow + 174)};
@@ -114,8 +117,10 @@ __global__ void __launch_bounds__(256) context_level_bwd_elem_kernel(ElemArgs A)
         }
         dqj += __ldg(A.noise + (size_t)row * kCE + j) * gx_total;
         dq[grp] += dqj;
-        drow[mcol] = d_mean;
-        drow[scol] = d_scale;
+        if (!LITE) {
+            drow[mcol] = d_mean;
+            drow[scol] = d_scale;
+        }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -130,6 +135,8 @@ __global__ void __launch_bounds__(256) context_level_bwd_elem_kernel(ElemArgs A)
         drow[2 * kCE + lane] = q > 1e-9f ? d * q0 * u * (2.0f - u) : 0.f;
     } else if (lane == 3) {
         drow[175] = 0.f;
+    } else if (LITE && lane < 8) {
+        drow[164 + lane] = 0.f;      // columns 168..171 of the chunk the LITE data-gradient kernel stages
     }
 }
 
@@ -156,7 +163,7 @@ struct DSmem {
 struct DArgs {
     const float *packed_w;
     const int *orig_idx, *ctx_src;
-    int n_rows;
+    int row0, n_rows;                // level rows [row0, row0 + n_rows)
     const uint32_t *save_hmask;      // [n_rows,4]
     const float *d_out;              // [n_rows,176] (kernel 0)
     float *d_pre;                    // [n_rows,112] -> kernel 2
@@ -174,7 +181,9 @@ __device__ __forceinline__ void st_split8(uint32_t tl, uint32_t col_hi, uint32_t
     umma::tmem_st8(tl + col_lo, lo);
 }
 
-template <int K1>
+// LITE (rows not chosen for the bit-rate term): dOut is zero outside the chunk [168,176), so one chunk is staged and the
+// first GEMM shrinks from K = 176 (66 tcgen05.mma) to K = 8 (3).
+template <int K1, bool LITE>
 __global__ void __launch_bounds__(kDThreads, 1) context_level_dgrad_umma_kernel(DArgs A)
 {
     using LY = DLayout<K1>;
@@ -217,22 +226,29 @@ __global__ void __launch_bounds__(kDThreads, 1) context_level_dgrad_umma_kernel(
         int o, s;
     };
     auto prefetch = [&](int tile, Pre &p) {
-        const int g = tile * kRows + row;
+        const int g = A.row0 + tile * kRows + row;
         p.o = -1; p.s = -1;
 #pragma unroll
         for (int i = 0; i < 4; ++i) p.hm[i] = 0u;
 #pragma unroll
         for (int i = 0; i < 5; ++i) p.v[i][0] = p.v[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tile >= num_tiles || g >= A.n_rows) return;
+        if (tile >= num_tiles || g >= A.row0 + A.n_rows) return;
         p.o = __ldg(A.orig_idx + g);
         p.s = K1 == 71 ? __ldg(A.ctx_src + g) : p.o;
         const float4 *src = reinterpret_cast<const float4 *>(A.d_out + (size_t)g * kOut);
+        if (LITE) {
+            if (fifth == 0) {
+                p.v[0][0] = __ldg(src + 42);
+                p.v[0][1] = __ldg(src + 43);
+            }
+        } else {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const int c = fifth + 5 * i;
-            if (c < 22) {
-                p.v[i][0] = __ldg(src + 2 * c);
-                p.v[i][1] = __ldg(src + 2 * c + 1);
+            for (int i = 0; i < 5; ++i) {
+                const int c = fifth + 5 * i;
+                if (c < 22) {
+                    p.v[i][0] = __ldg(src + 2 * c);
+                    p.v[i][1] = __ldg(src + 2 * c + 1);
+                }
             }
         }
         const uint4 m = __ldg(reinterpret_cast<const uint4 *>(A.save_hmask) + g);
@@ -244,7 +260,7 @@ __global__ void __launch_bounds__(kDThreads, 1) context_level_dgrad_umma_kernel(
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t parity = it & 1u;
-        const int g = tile * kRows + row;
+        const int g = A.row0 + tile * kRows + row;
         Cur cur;
 #pragma unroll
         for (int i = 0; i < 4; ++i) cur.hm[i] = nxt.hm[i];
@@ -252,13 +268,21 @@ __global__ void __launch_bounds__(kDThreads, 1) context_level_dgrad_umma_kernel(
         const bool valid = cur.o >= 0;
 
         // ---- stage dOut as the A operand: hi / lo into TMEM; then the next tile's row starts travelling -----------------
+        if (LITE) {
+            if (fifth == 0) {
+                const float f[8] = {nxt.v[0][0].x, nxt.v[0][0].y, nxt.v[0][0].z, nxt.v[0][0].w,
+                                    nxt.v[0][1].x, nxt.v[0][1].y, nxt.v[0][1].z, nxt.v[0][1].w};
+                st_split8(tl, kColAHi + 168, kColALo + 168, f);
+            }
+        } else {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const int c = fifth + 5 * i;
-            if (c < 22) {
-                const float f[8] = {nxt.v[i][0].x, nxt.v[i][0].y, nxt.v[i][0].z, nxt.v[i][0].w,
-                                    nxt.v[i][1].x, nxt.v[i][1].y, nxt.v[i][1].z, nxt.v[i][1].w};
-                st_split8(tl, kColAHi + 8 * c, kColALo + 8 * c, f);
+            for (int i = 0; i < 5; ++i) {
+                const int c = fifth + 5 * i;
+                if (c < 22) {
+                    const float f[8] = {nxt.v[i][0].x, nxt.v[i][0].y, nxt.v[i][0].z, nxt.v[i][0].w,
+                                        nxt.v[i][1].x, nxt.v[i][1].y, nxt.v[i][1].z, nxt.v[i][1].w};
+                    st_split8(tl, kColAHi + 8 * c, kColALo + 8 * c, f);
+                }
             }
         }
         prefetch(tile + (int)gridDim.x, nxt);
@@ -268,8 +292,12 @@ __global__ void __launch_bounds__(kDThreads, 1) context_level_dgrad_umma_kernel(
         // ---- M1: dH = dOut W2 ------------------------------------------------------------------------------------------
         if (tid == 0) {
             umma::fence_after_thread_sync();
-            umma::gemm_3xtf32(tbase + kColD1, tbase + kColAHi, tbase + kColALo, S.w + LY::kOffW2THi, S.w + LY::kOffW2TLo, kHid,
-                              kOut, true);
+            if (LITE)   // K chunk [168,176): B chunks 42, 43 of W2^T
+                umma::gemm_3xtf32(tbase + kColD1, tbase + kColAHi + 168, tbase + kColALo + 168, S.w + LY::kOffW2THi + 42 * kHid * 4,
+                                  S.w + LY::kOffW2TLo + 42 * kHid * 4, kHid, 8, true);
+            else
+                umma::gemm_3xtf32(tbase + kColD1, tbase + kColAHi, tbase + kColALo, S.w + LY::kOffW2THi, S.w + LY::kOffW2TLo,
+                                  kHid, kOut, true);
             umma::umma_commit(&S.bar[0]);
         }
         if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
@@ -383,7 +411,7 @@ struct WSmem {
 struct WArgs {
     const int *orig_idx, *ctx_src;
     const float *level_anchor;
-    int n_rows;
+    int row0, n_rows;                // level rows [row0, row0 + n_rows)
     const float *anchor, *hyper_q, *feat_q, *scaling_q;
     const float *save_h, *d_out, *d_pre;
     float *d_w;                      // packed layout of pack_grid_weights_bwd: W1[in][101] | b1[100] | W2[100][177] | b2[176]
@@ -404,7 +432,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-template <int K1>
+// LITE (rows not chosen for the bit-rate term): only the columns [168,176) of dOut are non-zero -- 64 bytes of the row
+// are staged (columns 160..175), 16 features converted and the dW2 product runs with N = 16 into columns [160,176).
+template <int K1, bool LITE>
 __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(WArgs A)
 {
     using LY = WLayout<K1>;
@@ -439,12 +469,14 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
         auto stage_rows = [&](int it) {
             const int st = it % kStages, row0 = ((int)blockIdx.x + it * stride) * kSlab;
             const int rows = min(kSlab, A.n_rows - row0);
-            if (lane == 0) mbar_expect_tx(&S.full[st], (uint32_t)rows * (uint32_t)((2 * kHid + kOut) * 4));
+            constexpr uint32_t kOBytes = LITE ? 64u : (uint32_t)(kOut * 4);
+            if (lane == 0) mbar_expect_tx(&S.full[st], (uint32_t)rows * ((uint32_t)(2 * kHid * 4) + kOBytes));
             __syncwarp();
             if (lane < rows) {
-                const size_t g = (size_t)(row0 + lane);
+                const size_t g = (size_t)(A.row0 + row0 + lane);
                 bulk_g2s(&S.raw_h[st][lane * kRawH], A.save_h + g * kHid, kHid * 4, &S.full[st]);
-                bulk_g2s(&S.raw_o[st][lane * kRawO], A.d_out + g * kOut, kOut * 4, &S.full[st]);
+                if (LITE) bulk_g2s(&S.raw_o[st][lane * kRawO + 160], A.d_out + g * kOut + 160, 64, &S.full[st]);
+                else bulk_g2s(&S.raw_o[st][lane * kRawO], A.d_out + g * kOut, kOut * 4, &S.full[st]);
                 bulk_g2s(&S.raw_p[st][lane * kRawP], A.d_pre + g * kHid, kHid * 4, &S.full[st]);
             }
         };
@@ -456,7 +488,8 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
         }
     } else if (warp == kConv / 32) {
         // =============================== MMA warp ==========================================================================
-        const uint32_t idescW2 = umma::idesc_tf32(128, kOut), idescW1 = umma::idesc_tf32(128, kHid);
+        const uint32_t idescW2 = umma::idesc_tf32(128, LITE ? 16 : kOut), idescW1 = umma::idesc_tf32(128, kHid);
+        constexpr int kOFeat = LITE ? 160 : 0;      // first dOut feature of the dW2 product (and its accumulator column)
         const uint32_t lbo = (uint32_t)LY::kLd * 16u, sbo = 128u;
         for (int it = 0; it < n_it; ++it) {
             const uint32_t b = (uint32_t)it & 1u;
@@ -471,7 +504,8 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
 #pragma unroll
                 for (int p = 0; p < 3; ++p) {
                     const uint32_t ab = p == 1 ? lo : hi, bb = p == 0 ? lo : hi;
-                    umma::mma_tf32_ss(tbase + kColW2, desc(ab, LY::kFH), desc(bb, LY::kFO), idescW2, p == 0 ? acc : 1u);
+                    umma::mma_tf32_ss(tbase + kColW2 + kOFeat, desc(ab, LY::kFH), desc(bb, LY::kFO + kOFeat), idescW2,
+                                      p == 0 ? acc : 1u);
                     umma::mma_tf32_ss(tbase + kColW1, desc(ab, 0), desc(bb, LY::kFP), idescW1, p == 0 ? acc : 1u);
                 }
                 umma::umma_commit(&S.mma_done[b]);
@@ -485,8 +519,9 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
             v = make_float2(0.f, 0.f);
             if (tid >= (LY::kXF / 2) * kSlab || it >= n_it) return;
             const int r = tid & (kSlab - 1), c = tid / kSlab;
-            const int g = ((int)blockIdx.x + it * stride) * kSlab + r;
-            if (g >= A.n_rows) return;
+            const int gl = ((int)blockIdx.x + it * stride) * kSlab + r;
+            if (gl >= A.n_rows) return;
+            const int g = A.row0 + gl;
             const int o = __ldg(A.orig_idx + g);
             const int s = K1 == 71 ? __ldg(A.ctx_src + g) : o;
             float e[2];
@@ -548,11 +583,20 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
                 }
                 store_item(r, LY::kFH + 2 * c, v);
             }
-            for (int i = tid; i < (kOut / 2) * kSlab; i += kConv) {
-                const int r = i & (kSlab - 1), c = i / kSlab;
-                float2 v = make_float2(0.f, 0.f);
-                if (row0 + r < A.n_rows) v = *reinterpret_cast<const float2 *>(&S.raw_o[st][r * kRawO + 2 * c]);
-                store_item(r, LY::kFO + 2 * c, v);
+            if (LITE) {
+                for (int i = tid; i < 8 * kSlab; i += kConv) {          // features 160..175: zeros | the step chunk
+                    const int r = i & (kSlab - 1), c = 80 + i / kSlab;
+                    float2 v = make_float2(0.f, 0.f);
+                    if (row0 + r < A.n_rows && c >= 84) v = *reinterpret_cast<const float2 *>(&S.raw_o[st][r * kRawO + 2 * c]);
+                    store_item(r, LY::kFO + 2 * c, v);
+                }
+            } else {
+                for (int i = tid; i < (kOut / 2) * kSlab; i += kConv) {
+                    const int r = i & (kSlab - 1), c = i / kSlab;
+                    float2 v = make_float2(0.f, 0.f);
+                    if (row0 + r < A.n_rows) v = *reinterpret_cast<const float2 *>(&S.raw_o[st][r * kRawO + 2 * c]);
+                    store_item(r, LY::kFO + 2 * c, v);
+                }
             }
             for (int i = tid; i < (kHid / 2) * kSlab; i += kConv) {
                 const int r = i & (kSlab - 1), c = i / kSlab;
@@ -585,7 +629,7 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
         const int L = 32 * (warp & 3) + lane;     // accumulator lane: hidden unit (D_w2) / input unit (D_w1)
         const int cq = warp >> 2;                 // four warps share a lane quadrant: split the columns
 #pragma unroll 1
-        for (int c = cq; c < kOut / 8; c += 4) {
+        for (int c = (LITE ? 20 : 0) + cq; c < kOut / 8; c += 4) {
             uint32_t v[8];
             umma::tmem_ld8(tl + kColW2 + 8 * c, v);
             umma::tmem_wait_ld8(v);
@@ -620,26 +664,44 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
 }
 
 template <int K1>
-static int launch_all(const ElemArgs &e, const DArgs &d, const WArgs &w, cudaStream_t st)
+static int launch_all(ElemArgs e, DArgs d, WArgs w, int n_full, cudaStream_t st)
 {
     static int sm_count = 0;
     if (sm_count == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(context_level_dgrad_umma_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(context_level_dgrad_umma_kernel<K1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(DSmem<K1>));
-        cudaFuncSetAttribute(context_level_wgrad_umma_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(context_level_dgrad_umma_kernel<K1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(DSmem<K1>));
+        cudaFuncSetAttribute(context_level_wgrad_umma_kernel<K1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(WSmem<K1>));
+        cudaFuncSetAttribute(context_level_wgrad_umma_kernel<K1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(WSmem<K1>));
         if (sm_count <= 0) sm_count = kNumSMs;
     }
-    StageScope sc(ST_CTX_LEVEL_BWD, st, 3);
-    const int n = e.n_rows;
-    context_level_bwd_elem_kernel<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, st>>>(e);
-    const int tiles = (n + kRows - 1) / kRows;
-    context_level_dgrad_umma_kernel<K1><<<tiles < sm_count ? tiles : sm_count, kDThreads, sizeof(DSmem<K1>), st>>>(d);
-    const int slabs = (n + kSlab - 1) / kSlab;
-    context_level_wgrad_umma_kernel<K1><<<slabs < sm_count ? slabs : sm_count, kWThreads, sizeof(WSmem<K1>), st>>>(w);
+    const int n_all = e.n_rows;
+    // rows [0, n_full): chosen for the bit-rate term (full output gradient); rows [n_full, n): step columns only
+    for (int part = 0; part < 2; ++part) {
+        const int row0 = part == 0 ? 0 : n_full, n = part == 0 ? n_full : n_all - n_full;
+        if (n <= 0) continue;
+        e.row0 = d.row0 = w.row0 = row0;
+        e.n_rows = d.n_rows = w.n_rows = n;
+        StageScope sc(ST_CTX_LEVEL_BWD, st, 3);
+        const unsigned eb = (unsigned)(((size_t)n * 32 + 255) / 256);
+        const int tiles = (n + kRows - 1) / kRows, slabs = (n + kSlab - 1) / kSlab;
+        const int gd = tiles < sm_count ? tiles : sm_count, gw = slabs < sm_count ? slabs : sm_count;
+        if (part == 0) {
+            context_level_bwd_elem_kernel<false><<<eb, 256, 0, st>>>(e);
+            context_level_dgrad_umma_kernel<K1, false><<<gd, kDThreads, sizeof(DSmem<K1>), st>>>(d);
+            context_level_wgrad_umma_kernel<K1, false><<<gw, kWThreads, sizeof(WSmem<K1>), st>>>(w);
+        } else {
+            context_level_bwd_elem_kernel<true><<<eb, 256, 0, st>>>(e);
+            context_level_dgrad_umma_kernel<K1, true><<<gd, kDThreads, sizeof(DSmem<K1>), st>>>(d);
+            context_level_wgrad_umma_kernel<K1, true><<<gw, kWThreads, sizeof(WSmem<K1>), st>>>(w);
+        }
+    }
     return check_launch("cgs_context_level_backward_umma");
 }
 }  // namespace cbu
@@ -663,35 +725,40 @@ extern "C" int cgs_context_level_backward_umma(int in_dim, const float *packed_b
                                                float bits_factor, const float *params, const float *save_h,
                                                const uint32_t *save_hmask, float *G_feat, float *G_scaling, float *G_offsets,
                                                float *d_mask, float *d_hyper_q, float *d_anchor, float *d_packed_w,
-                                               float *scratch_dout, float *scratch_dpre, int32_t *err, void *stream)
+                                               float *scratch_dout, float *scratch_dpre, int32_t *err, int n_full,
+                                               void *stream)
 {
     if (n_rows <= 0) return 0;
+    if (n_full < 0 || n_full > n_rows) {
+        set_error("%s: n_full out of range", __func__);
+        return -2;
+    }
     CGS_CHECK_PTR(packed_bwd); CGS_CHECK_PTR(orig_idx); CGS_CHECK_PTR(anchor); CGS_CHECK_PTR(hyper_q); CGS_CHECK_PTR(feat_q);
     CGS_CHECK_PTR(scaling_q); CGS_CHECK_PTR(offsets_q); CGS_CHECK_PTR(mask); CGS_CHECK_PTR(noise); CGS_CHECK_PTR(params);
     CGS_CHECK_PTR(save_h); CGS_CHECK_PTR(save_hmask); CGS_CHECK_PTR(G_feat); CGS_CHECK_PTR(G_scaling); CGS_CHECK_PTR(G_offsets);
     CGS_CHECK_PTR(d_mask); CGS_CHECK_PTR(d_hyper_q); CGS_CHECK_PTR(d_anchor); CGS_CHECK_PTR(d_packed_w);
     CGS_CHECK_PTR(scratch_dout); CGS_CHECK_PTR(scratch_dpre); CGS_CHECK_PTR(err);
     cbu::ElemArgs e;
-    e.orig_idx = orig_idx; e.n_rows = n_rows; e.params = params; e.feat_q = feat_q; e.scaling_q = scaling_q;
+    e.orig_idx = orig_idx; e.row0 = 0; e.n_rows = n_rows; e.params = params; e.feat_q = feat_q; e.scaling_q = scaling_q;
     e.offsets_q = offsets_q; e.mask = mask; e.choose = choose; e.noise = noise; e.feat_mean = feat_mean;
     e.scaling_mean = scaling_mean; e.offset_mean = offset_mean; e.g_bits_dev = g_bits_dev; e.bits_factor = bits_factor;
     e.G_feat = G_feat; e.G_scaling = G_scaling; e.G_offsets = G_offsets; e.d_mask = d_mask; e.d_out = scratch_dout;
     cbu::DArgs d;
-    d.packed_w = packed_bwd; d.orig_idx = orig_idx; d.ctx_src = ctx_src; d.n_rows = n_rows; d.save_hmask = save_hmask;
+    d.packed_w = packed_bwd; d.orig_idx = orig_idx; d.ctx_src = ctx_src; d.row0 = 0; d.n_rows = n_rows; d.save_hmask = save_hmask;
     d.d_out = scratch_dout; d.d_pre = scratch_dpre; d.G_feat = G_feat; d.G_scaling = G_scaling; d.d_hyper_q = d_hyper_q;
     d.d_anchor = d_anchor; d.err = err;
     cbu::WArgs w;
-    w.orig_idx = orig_idx; w.ctx_src = ctx_src; w.level_anchor = level_anchor; w.n_rows = n_rows; w.anchor = anchor;
+    w.orig_idx = orig_idx; w.ctx_src = ctx_src; w.level_anchor = level_anchor; w.row0 = 0; w.n_rows = n_rows; w.anchor = anchor;
     w.hyper_q = hyper_q; w.feat_q = feat_q; w.scaling_q = scaling_q; w.save_h = save_h; w.d_out = scratch_dout;
     w.d_pre = scratch_dpre; w.d_w = d_packed_w; w.err = err;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (in_dim == 71) {
         CGS_CHECK_PTR(ctx_src);
-        return cbu::launch_all<71>(e, d, w, st);
+        return cbu::launch_all<71>(e, d, w, n_full, st);
     }
     if (in_dim == 15) {
         CGS_CHECK_PTR(level_anchor);
-        return cbu::launch_all<15>(e, d, w, st);
+        return cbu::launch_all<15>(e, d, w, n_full, st);
     }
     set_error("%s: unsupported context-MLP input width %d", __func__, in_dim);
     return -2;

@@ -388,7 +388,9 @@ CGS_API int cgs_context_level_umma_forward_train(int in_dim, const float *packed
  * cgs_context_level_umma_forward_train saved.  packed_bwd: cgs_context_level_bwd_umma_packed_floats(in_dim) floats
  * (contextgs_b200/context_model.py pack_grid_weights_bwd_umma: W2^T and W1^T as K-major B operands, TF32 hi / lo);
  * d_packed_w: the gradient in the layout of cgs_context_level_backward (accumulated).  scratch_dout[n_rows,176],
- * scratch_dpre[n_rows,112]: hand-over between the three kernels.  *err (device, caller-zeroed): completion time-out. */
+ * scratch_dpre[n_rows,112]: hand-over between the three kernels.  *err (device, caller-zeroed): completion time-out.
+ * n_full: the level rows [0, n_full) are the ones chosen for the bit-rate term (the training forward orders them first);
+ * rows [n_full, n_rows) take the reduced path (output gradient = the three step columns).  n_full = n_rows is always valid. */
 CGS_API int cgs_context_level_bwd_umma_packed_floats(int in_dim);
 CGS_API int cgs_context_level_backward_umma(int in_dim, const float *packed_bwd, const int32_t *orig_idx,
                                             const int32_t *ctx_src, const float *level_anchor, int n_rows,
@@ -399,7 +401,8 @@ CGS_API int cgs_context_level_backward_umma(int in_dim, const float *packed_bwd,
                                             float bits_factor, const float *params, const float *save_h,
                                             const uint32_t *save_hmask, float *G_feat, float *G_scaling, float *G_offsets,
                                             float *d_mask, float *d_hyper_q, float *d_anchor, float *d_packed_w,
-                                            float *scratch_dout, float *scratch_dpre, int32_t *err, void *stream);
+                                            float *scratch_dout, float *scratch_dpre, int32_t *err, int n_full,
+                                            void *stream);
 
 /* Backward of one level in TRAINING mode (noise != NULL in the forward): what autograd does in the
  * reference for the loop body scene/gaussian_model.py:1562-1652 plus the Entropy_gaussian terms of
