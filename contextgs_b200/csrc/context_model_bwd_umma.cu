@@ -514,25 +514,31 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
         }
     } else {
         // =============================== converter warps ===================================================================
-        // layer-1 input of a row, feature f (as the forward stages it), fetched one slab ahead
-        auto load_x = [&](int it, float2 &v) {
-            v = make_float2(0.f, 0.f);
-            if (tid >= (LY::kXF / 2) * kSlab || it >= n_it) return;
-            const int r = tid & (kSlab - 1), c = tid / kSlab;
-            const int gl = ((int)blockIdx.x + it * stride) * kSlab + r;
+        // layer-1 input of a row, feature pair c (as the forward stages it): the row's indices (orig, ctx_src) are fetched
+        // TWO slabs ahead and the values ONE slab ahead, so neither of the two dependent loads is waited for
+        const bool xthread = tid < (LY::kXF / 2) * kSlab;
+        const int xr = tid & (kSlab - 1), xc = tid / kSlab;
+        auto load_idx = [&](int it, int &o, int &s2) {
+            o = -1; s2 = -1;
+            if (!xthread || it >= n_it) return;
+            const int gl = ((int)blockIdx.x + it * stride) * kSlab + xr;
             if (gl >= A.n_rows) return;
-            const int g = A.row0 + gl;
-            const int o = __ldg(A.orig_idx + g);
-            const int s = K1 == 71 ? __ldg(A.ctx_src + g) : o;
+            o = __ldg(A.orig_idx + A.row0 + gl);
+            s2 = K1 == 71 ? __ldg(A.ctx_src + A.row0 + gl) : o;
+        };
+        auto load_x = [&](int it, int o, int s2, float2 &v) {
+            v = make_float2(0.f, 0.f);
+            if (o < 0) return;
+            const int g = A.row0 + ((int)blockIdx.x + it * stride) * kSlab + xr;
             float e[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                const int f = 2 * c + i;
+                const int f = 2 * xc + i;
                 float x = 0.f;
                 if (K1 == 71) {
-                    if (f < 3) x = __ldg(A.anchor + 3 * (size_t)s + f);
-                    else if (f < 3 + kCF) x = A.feat_q[(size_t)s * kCF + (f - 3)];
-                    else if (f < 3 + kCF + kCS) x = A.scaling_q[(size_t)s * kCS + (f - 3 - kCF)];
+                    if (f < 3) x = __ldg(A.anchor + 3 * (size_t)s2 + f);
+                    else if (f < 3 + kCF) x = A.feat_q[(size_t)s2 * kCF + (f - 3)];
+                    else if (f < 3 + kCF + kCS) x = A.scaling_q[(size_t)s2 * kCS + (f - 3 - kCF)];
                     else if (f < K1) x = __ldg(A.hyper_q + (size_t)o * kHyper + (f - 3 - kCF - kCS));
                     else if (f == K1) x = 1.0f;
                 } else {
@@ -545,7 +551,11 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
             v = make_float2(e[0], e[1]);
         };
         float2 xv;
-        load_x(0, xv);
+        int o1, s1, o2, s2;
+        load_idx(0, o1, s1);
+        load_x(0, o1, s1, xv);
+        load_idx(1, o1, s1);
+        load_idx(2, o2, s2);
         for (int it = 0; it < n_it; ++it) {
             const uint32_t b = (uint32_t)it & 1u;
             const int st = it % kStages;
@@ -565,8 +575,10 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
                 if (!umma::mbar_wait(&S.mma_done[b], (uint32_t)((it >> 1) - 1) & 1u)) S.timeout = 1;
                 umma::fence_after_thread_sync();
             }
-            if (tid < (LY::kXF / 2) * kSlab) store_item(tid & (kSlab - 1), 2 * (tid / kSlab), xv);
-            load_x(it + 1, xv);
+            if (xthread) store_item(xr, 2 * xc, xv);
+            load_x(it + 1, o1, s1, xv);
+            o1 = o2; s1 = s2;
+            load_idx(it + 3, o2, s2);
             if (tid < kSlab) {   // the skew feature of every chunk: keep it finite
                 const int dst = ((tid >> 2) * LY::kLd + LY::kFeat) * 4 + (tid & 3);
                 Bhi[dst] = 0.f;

@@ -514,21 +514,27 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
         // Items are float2 (two features of one row): with 8 rows per slab a warp covers 8 rows x 4 feature pairs, and
         // both the staged-row reads (row stride = 20 banks) and the operand stores (8 c + 4 (r / 4) + r % 4) are conflict free.
         constexpr int kPairs = 2 * kGroups, kPX = 2 * kGX, kPO = 2 * kOffO, kPH = 2 * kOffH, kPP = 2 * kOffP;
-        auto load_x = [&](int it, float2 &v) {
-            v = make_float2(0.f, 0.f);
-            if (tid >= kPX * kSlab || it >= n_it) return;
-            const int r = tid & (kSlab - 1), c = tid / kSlab;      // c: feature pair 0..27
-            const int g = ((int)blockIdx.x + it * stride) * kSlab + r;
+        // the visible-anchor index is fetched TWO slabs ahead and the values ONE slab ahead: neither dependent load is waited for
+        const bool xthread = tid < kPX * kSlab;
+        const int xr = tid & (kSlab - 1), xc = tid / kSlab;      // xc: feature pair 0..27
+        auto load_idx = [&](int it, int &a) {
+            a = -1;
+            if (!xthread || it >= n_it) return;
+            const int g = ((int)blockIdx.x + it * stride) * kSlab + xr;
             if (g >= Nv) return;
-            const int a = vis_idx ? __ldg(vis_idx + g) : g;
-            if (c < 25) {
-                v = __ldg(reinterpret_cast<const float2 *>(feat + (size_t)a * 50) + c);
+            a = vis_idx ? __ldg(vis_idx + g) : g;
+        };
+        auto load_x = [&](int a, float2 &v) {
+            v = make_float2(0.f, 0.f);
+            if (a < 0) return;
+            if (xc < 25) {
+                v = __ldg(reinterpret_cast<const float2 *>(feat + (size_t)a * 50) + xc);
             } else {
                 const float ux = __ldg(anchor + 3 * (size_t)a) - cx, uy = __ldg(anchor + 3 * (size_t)a + 1) - cy,
                             uz = __ldg(anchor + 3 * (size_t)a + 2) - cz;
                 const float d = sqrtf(ux * ux + uy * uy + uz * uz);
-                if (c == 25) v = make_float2(ux / d, uy / d);
-                else if (c == 26) v = make_float2(uz / d, d);
+                if (xc == 25) v = make_float2(ux / d, uy / d);
+                else if (xc == 26) v = make_float2(uz / d, d);
                 else v = make_float2(1.0f, 0.f);                   // feature 54 = 1: its row of dW1^T is the bias gradient
             }
         };
@@ -543,7 +549,11 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
             B.lo[dst + 4] = __uint_as_float(l[1]);
         };
         float2 xv;
-        load_x(0, xv);
+        int a1, a2;
+        load_idx(0, a1);
+        load_x(a1, xv);
+        load_idx(1, a1);
+        load_idx(2, a2);
         for (int it = 0; it < n_it; ++it) {
             const uint32_t b = (uint32_t)it & 1u;
             const int st = it % kStages;
@@ -556,8 +566,10 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
                 umma::fence_after_thread_sync();
             }
             // X (prefetched one slab ahead), then the next slab's X starts travelling
-            if (tid < kPX * kSlab) store_item(B, tid & (kSlab - 1), tid / kSlab, xv);
-            load_x(it + 1, xv);
+            if (xthread) store_item(B, xr, xc, xv);
+            load_x(a1, xv);
+            a1 = a2;
+            load_idx(it + 3, a2);
             if (tid < (kSlab / 4) * 4) {   // the skew feature (index 552) of every chunk: keep it finite
                 const int dst = ((tid >> 2) * kLd + 4 * kGroups) * 4 + (tid & 3);
                 B.hi[dst] = 0.f;
