@@ -50,6 +50,7 @@ SIGNATURES = {
     "cgs_neural_gaussians_bwd_umma_packed_floats": (c_int, []),
     "cgs_neural_gaussians_save_floats": (c_int, [c_int]),
     "cgs_debug_set": (c_int, [c_int, c_int]),
+    "cgs_umma_mma_rate": (c_int, [c_int, c_int, c_int, c_int, _PTR, _PTR]),
     "cgs_neural_gaussians_backward_umma": (c_int, [_PTR, _PTR, c_int] + [_PTR] * 27),
     "cgs_visible_filter": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR]),
     "cgs_prefilter_workspace_bytes": (c_size_t, [c_int]),

@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(kDThreads, 1) context_level_dgrad_umma_kernel(
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fifth = warp >> 2;                       // five threads per row
     const int row = 32 * (warp & 3) + lane;
+    const int uwarp = umma::uniform_warp();
     const int num_tiles = (A.n_rows + kRows - 1) / kRows;
 
     if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(kDThreads, 1) context_level_dgrad_umma_kernel(
         umma::fence_before_thread_sync();
         __syncthreads();
         // ---- M1: dH = dOut W2 ------------------------------------------------------------------------------------------
-        if (tid == 0) {
+        if (uwarp == 0 && umma::elect_one_sync()) {     // warp-uniform branch + elect: back-to-back tcgen05.mma (umma.cuh)
             umma::fence_after_thread_sync();
             if (LITE)   // K chunk [168,176): B chunks 42, 43 of W2^T
                 umma::gemm_3xtf32(tbase + kColD1, tbase + kColAHi + 168, tbase + kColALo + 168, S.w + LY::kOffW2THi + 42 * kHid * 4,
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(kDThreads, 1) context_level_dgrad_umma_kernel(
         umma::fence_before_thread_sync();
         __syncthreads();
         // ---- M2: dX = dPre W1 --------------------------------------------------------------------------------------------
-        if (tid == 0) {
+        if (uwarp == 0 && umma::elect_one_sync()) {
             umma::fence_after_thread_sync();
             umma::gemm_3xtf32(tbase + kColDX, tbase + kColD1, tbase + kColPLo, S.w + LY::kOffW1THi, S.w + LY::kOffW1TLo,
                               LY::kN1, kHidK, true);
@@ -464,21 +465,26 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
     const uint32_t tbase = S.tmem;
     constexpr int kSyncCount = kConv + 32;     // converters arrive, the MMA warp waits
 
-    if (warp == kConv / 32 + 1) {
+    const int role_warp = umma::uniform_warp();                  // warp-uniform roles
+    if (role_warp == kConv / 32 + 1) {
         // =============================== TMA warp: bulk copies of the staged rows, kStages slabs ahead ===================
         auto stage_rows = [&](int it) {
             const int st = it % kStages, row0 = ((int)blockIdx.x + it * stride) * kSlab;
             const int rows = min(kSlab, A.n_rows - row0);
             constexpr uint32_t kOBytes = LITE ? 64u : (uint32_t)(kOut * 4);
-            if (lane == 0) mbar_expect_tx(&S.full[st], (uint32_t)rows * ((uint32_t)(2 * kHid * 4) + kOBytes));
-            __syncwarp();
-            if (lane < rows) {
-                const size_t g = (size_t)(A.row0 + row0 + lane);
-                bulk_g2s(&S.raw_h[st][lane * kRawH], A.save_h + g * kHid, kHid * 4, &S.full[st]);
-                if (LITE) bulk_g2s(&S.raw_o[st][lane * kRawO + 160], A.d_out + g * kOut + 160, 64, &S.full[st]);
-                else bulk_g2s(&S.raw_o[st][lane * kRawO], A.d_out + g * kOut, kOut * 4, &S.full[st]);
-                bulk_g2s(&S.raw_p[st][lane * kRawP], A.d_pre + g * kHid, kHid * 4, &S.full[st]);
+            // ONE elected lane issues every copy of the slab with warp-uniform operands (per-lane copies make the compiler
+            // serialise the lanes through a vote / BRA.U.ANY loop around each UBLKCP)
+            if (umma::elect_one_sync()) {
+                mbar_expect_tx(&S.full[st], (uint32_t)rows * ((uint32_t)(2 * kHid * 4) + kOBytes));
+                for (int r = 0; r < rows; ++r) {
+                    const size_t g = (size_t)(A.row0 + row0 + r);
+                    bulk_g2s(&S.raw_h[st][r * kRawH], A.save_h + g * kHid, kHid * 4, &S.full[st]);
+                    if (LITE) bulk_g2s(&S.raw_o[st][r * kRawO + 160], A.d_out + g * kOut + 160, 64, &S.full[st]);
+                    else bulk_g2s(&S.raw_o[st][r * kRawO], A.d_out + g * kOut, kOut * 4, &S.full[st]);
+                    bulk_g2s(&S.raw_p[st][r * kRawP], A.d_pre + g * kHid, kHid * 4, &S.full[st]);
+                }
             }
+            __syncwarp();
         };
         for (int i = 0; i < kStages && i < n_it; ++i) stage_rows(i);
         for (int it = 0; it + kStages < n_it; ++it) {
@@ -486,7 +492,7 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
             if (!umma::mbar_wait(&S.empty[it % kStages], (uint32_t)(it / kStages) & 1u)) S.timeout = 1;
             stage_rows(it + kStages);
         }
-    } else if (warp == kConv / 32) {
+    } else if (role_warp == kConv / 32) {
         // =============================== MMA warp ==========================================================================
         const uint32_t idescW2 = umma::idesc_tf32(128, LITE ? 16 : kOut), idescW1 = umma::idesc_tf32(128, kHid);
         constexpr int kOFeat = LITE ? 160 : 0;      // first dOut feature of the dW2 product (and its accumulator column)
@@ -495,7 +501,7 @@ __global__ void __launch_bounds__(kWThreads, 1) context_level_wgrad_umma_kernel(
             const uint32_t b = (uint32_t)it & 1u;
             named_sync(1 + (int)b, kSyncCount);     // the converters have written buffer b
             umma::fence_after_thread_sync();
-            if (lane == 0) {
+            if (umma::elect_one_sync()) {
                 const uint32_t hi = umma::smem_u32(S.hi[b]), lo = umma::smem_u32(S.lo[b]);
                 auto desc = [&](uint32_t base, int feature) {
                     return umma::smem_desc_kmajor(base + (uint32_t)feature * 16u, lbo, sbo);

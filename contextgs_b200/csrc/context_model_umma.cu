@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
     // epilogue is the long pole) quantises and scores tile t.  TMEM columns [0,256) belong to FRONT (free once the
     // layer-2 MMAs have read the hidden activations), [256,432) change hands through an mbarrier.
     const bool front = tid < kFront;
+    const int uwarp = umma::uniform_warp();                   // warp index the compiler knows to be warp-uniform
     const int gtid = front ? tid : tid - kFront, gwarp = gtid >> 5;
     const int half = gwarp >> 2;      // FRONT: half of the row's inputs / hidden units; BACK: quarter of its coded values
     const int row = 32 * (warp & 3) + lane;
@@ -223,11 +224,14 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             umma::tmem_wait_st();
             umma::fence_before_thread_sync();
             group_sync<kFront>(1);
-            if (gtid == 0) {
-                umma::fence_after_thread_sync();
-                umma::gemm_3xtf32(tbase + kColD1, tbase + kColXHi, tbase + kColXLo, S.w + LY::kOffW1Hi, S.w + LY::kOffW1Lo,
-                                  kN1, LY::kK1p, true);
-                umma::umma_commit(&S.bar[0]);
+            if (uwarp == 0) {      // warp-uniform branch + elect: back-to-back tcgen05.mma (see umma.cuh)
+                if (umma::elect_one_sync()) {
+                    umma::fence_after_thread_sync();
+                    umma::gemm_3xtf32(tbase + kColD1, tbase + kColXHi, tbase + kColXLo, S.w + LY::kOffW1Hi, S.w + LY::kOffW1Lo,
+                                      kN1, LY::kK1p, true);
+                    umma::umma_commit(&S.bar[0]);
+                }
+                __syncwarp();
             }
             if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;
             umma::fence_after_thread_sync();
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             umma::tmem_wait_st();
             umma::fence_before_thread_sync();
             group_sync<kFront>(1);
-            if (gtid == 0) {
+            if (uwarp == 0 && umma::elect_one_sync()) {
                 umma::fence_after_thread_sync();
                 if (it > 0) {   // BACK has finished reading the layer-2 accumulator of the previous tile
                     if (!umma::mbar_wait(&S.bar[2], parity ^ 1u)) S.timeout = 1;

@@ -180,6 +180,7 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fifth = warp >> 2;                       // five threads per row
     const int row = 32 * (warp & 3) + lane;
+    const int uwarp = umma::uniform_warp();
     const int num_tiles = (Nv + kRows - 1) / kRows;
 
     if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
@@ -256,7 +257,7 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
         __syncthreads();
 
         // ================= M1: dH_h = dOut_h W2_h =================
-        if (tid == 0) {
+        if (uwarp == 0 && umma::elect_one_sync()) {     // warp-uniform branch + elect: back-to-back tcgen05.mma (umma.cuh)
             umma::fence_after_thread_sync();
             // the three heads accumulate into different columns: issued round-robin so that their dependency chains overlap
             const umma::Gemm3x heads[3] = {
@@ -308,7 +309,7 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
         __syncthreads();
 
         // ================= M2: dX = dPre W1 =================
-        if (tid == 0) {
+        if (uwarp == 0 && umma::elect_one_sync()) {
             umma::fence_after_thread_sync();
             umma::gemm_3xtf32(tbase + kColDX, tbase + kColD1, tbase + kColPLo, S.w + kOffW1THi, S.w + kOffW1TLo, kInP,
                               kHidT, true);
@@ -442,7 +443,7 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int num_slabs = (Nv + kSlab - 1) / kSlab;
     const int stride = (int)gridDim.x;
-    const bool issuer = tid >= kConv;
+    const bool issuer = umma::uniform_warp() >= kConv / 32;     // warp-uniform role
 
     if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
     if (tid == 0) {
@@ -466,21 +467,25 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
         auto stage_rows = [&](int it) {     // bulk copies of slab `it` into raw[it % kStages]
             const int b = it % kStages, row0 = ((int)blockIdx.x + it * stride) * kSlab;
             const int rows = min(kSlab, Nv - row0);
-            if (lane == 0) mbar_expect_tx(&S.full[b], (uint32_t)rows * (kBytesO + 2u * kBytesH));
-            __syncwarp();
-            if (lane < rows) {
-                const size_t g = (size_t)(row0 + lane);
-                bulk_g2s(S.raw[b].o + lane * kRawO, d_out + g * 144, kBytesO, &S.full[b]);
-                bulk_g2s(S.raw[b].h + lane * kRawH, save_h + g * 176, kBytesH, &S.full[b]);
-                bulk_g2s(S.raw[b].p + lane * kRawP, d_pre + g * 176, kBytesH, &S.full[b]);
+            // ONE elected lane issues every copy of the slab with warp-uniform operands (per-lane copies make the compiler
+            // serialise the lanes through a vote / BRA.U.ANY loop around each UBLKCP)
+            if (umma::elect_one_sync()) {
+                mbar_expect_tx(&S.full[b], (uint32_t)rows * (kBytesO + 2u * kBytesH));
+                for (int r = 0; r < rows; ++r) {
+                    const size_t g = (size_t)(row0 + r);
+                    bulk_g2s(S.raw[b].o + r * kRawO, d_out + g * 144, kBytesO, &S.full[b]);
+                    bulk_g2s(S.raw[b].h + r * kRawH, save_h + g * 176, kBytesH, &S.full[b]);
+                    bulk_g2s(S.raw[b].p + r * kRawP, d_pre + g * 176, kBytesH, &S.full[b]);
+                }
             }
+            __syncwarp();
         };
         for (int i = 0; i < kStages && i < n_it; ++i) stage_rows(i);
         for (int it = 0; it < n_it; ++it) {
             const uint32_t b = (uint32_t)it & 1u;
             named_sync(1 + (int)b, kThreads);     // the converters have written buf[b] and are done with raw[b]
             umma::fence_after_thread_sync();
-            if (lane == 0) {
+            if (umma::elect_one_sync()) {
                 const uint32_t hi = umma::smem_u32(S.buf[b].hi), lo = umma::smem_u32(S.buf[b].lo);
                 auto desc = [&](uint32_t base, int group, int kstep) {   // operand starting at float4 group `group`, rows 8 kstep ..
                     return umma::smem_desc_kmajor(base + (uint32_t)kstep * 2u * lbo + (uint32_t)group * 64u, lbo, sbo);

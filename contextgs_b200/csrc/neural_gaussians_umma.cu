@@ -227,6 +227,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool front = tid < kGroup;
+    const int uwarp = umma::uniform_warp();                   // warp index the compiler knows to be warp-uniform
     const int gtid = tid & (kGroup - 1), gwarp = gtid >> 5;   // inside the group
     const int half = gwarp >> 2;
     const int row = 32 * (warp & 3) + lane;                   // warp % 4 == gwarp % 4: the lane quadrant this warp may touch
@@ -330,11 +331,14 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
             umma::fence_before_thread_sync();
             group_sync(1);
             // ---- layer 1: D1[128 x 176] = x[128 x 56] * W1^T ----------------------------------------
-            if (gtid == 0) {
-                umma::fence_after_thread_sync();
-                umma::gemm_3xtf32(tbase + kColD1, tbase + kColXHi, tbase + kColXLo, S.w + kOffW1Hi, S.w + kOffW1Lo, kN1,
-                                  kK1, true);
-                umma::umma_commit(&S.bar[BAR_L1]);
+            if (uwarp == 0) {      // warp-uniform branch + elect: back-to-back tcgen05.mma (see umma.cuh)
+                if (umma::elect_one_sync()) {
+                    umma::fence_after_thread_sync();
+                    umma::gemm_3xtf32(tbase + kColD1, tbase + kColXHi, tbase + kColXLo, S.w + kOffW1Hi, S.w + kOffW1Lo, kN1,
+                                      kK1, true);
+                    umma::umma_commit(&S.bar[BAR_L1]);
+                }
+                __syncwarp();
             }
             // while the tensor core works: the next tile's input rows start travelling (index fetched a tile earlier)
             FrontInputs nxt;
@@ -375,7 +379,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                 if (!umma::mbar_wait(&S.bar[BAR_ACCFREE], parity ^ 1u)) S.timeout = 1;
                 umma::fence_after_thread_sync();
             }
-            if (gtid == 0) {
+            if (uwarp == 0 && umma::elect_one_sync()) {
                 umma::fence_after_thread_sync();
                 umma::gemm_3xtf32(tbase + kColDo, tbase + kColD1 + 0 * kHeadStride, tbase + kColHLo + 0 * kHeadStride,
                                   S.w + kOffW2oHi, S.w + kOffW2oLo, kNo, kK1, true);

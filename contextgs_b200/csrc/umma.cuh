@@ -19,6 +19,20 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- single-thread issue from a warp-uniform context ------------------------------------------------------
+// tcgen05.mma / tcgen05.commit / bulk copies are issued by ONE thread.  Guarding them with `threadIdx.x == 0` makes the
+// compiler wrap EVERY such instruction in a vote / ELECT / BRA.U.ANY loop (it cannot prove that one lane is active and that
+// the uniform-register operands are warp-uniform): measured 199 cycles per tcgen05.mma regardless of its shape
+// (scripts/umma_rate_probe.py).  The canonical form -- a warp-uniform branch on `uniform_warp()` followed by
+// `if (elect_one_sync())` -- compiles to back-to-back UTCHMMA.
+__device__ __forceinline__ int uniform_warp() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMEM allocation: one full warp calls these (.sync.aligned) ---------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols)
 {

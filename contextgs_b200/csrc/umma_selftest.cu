@@ -259,6 +259,52 @@ umma_selftest_ss_mn_kernel(const float *__restrict__ P, const float *__restrict_
     if (warp == 0) umma::tmem_dealloc(tbase, 512);
 }
 
+
+// Micro-benchmark: cycles per tcgen05.mma.kind::tf32 (M = 128, K = 8) for a chain of `iters` instructions issued by one
+// thread.  form 0: A in TMEM (TS), 1: A in shared memory (SS).  n_acc independent accumulators are used round-robin
+// (n_acc = 1: every MMA accumulates into the columns the previous one wrote).  Operand contents are irrelevant (zeros).
+__global__ void __launch_bounds__(128, 1)
+umma_mma_rate_kernel(int form, int N, int n_acc, int iters, long long *__restrict__ out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *sm = reinterpret_cast<float *>(smem_raw);
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
+    if (tid == 0) {
+        umma::mbar_init(&s_bar, 1);
+        umma::fence_mbar_init();
+    }
+    for (int i = tid; i < 2 * (128 + 256) * 8; i += blockDim.x) sm[i] = 0.f;     // A [2][128][4] + B [2][256][4]
+    umma::fence_proxy_async_smem();
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    umma::fence_after_thread_sync();
+    const uint32_t tbase = s_tmem;
+    const bool one = form >= 2 ? (umma::uniform_warp() == 0 && umma::elect_one_sync()) : tid == 0;   // forms 2, 3: canonical issue
+    form &= 1;
+    if (one) {
+        const uint32_t idesc = umma::idesc_tf32(128, N);
+        const uint32_t a_s = umma::smem_u32(sm), b_s = a_s + 2 * 128 * 16;
+        const uint64_t adesc = umma::smem_desc_kmajor(a_s, 128 * 16, 128), bdesc = umma::smem_desc_kmajor(b_s, 256 * 16, 128);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint32_t d = tbase + 256 + (uint32_t)(i % n_acc) * (uint32_t)N;     // accumulators in columns [256,512)
+            if (form == 0) umma::mma_tf32_ts(d, tbase, bdesc, idesc, 1u);
+            else umma::mma_tf32_ss(d, adesc, bdesc, idesc, 1u);
+        }
+        umma::umma_commit(&s_bar);
+        const long long t1 = clock64();
+        umma::mbar_wait(&s_bar, 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0;      // issue time
+        out[1] = t2 - t0;      // issue + completion
+    }
+    umma::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tbase, 512);
+}
 }  // namespace cgs
 
 using namespace cgs;
@@ -314,5 +360,20 @@ extern "C" int cgs_umma_selftest(const float *A, const float *W, int N, int K, i
     cudaMemsetAsync(err, 0, sizeof(int32_t), st);
     StageScope sc(ST_ELEMWISE, st, 1);
     umma_selftest_kernel<<<1, 128, smem, st>>>(A, W, N, K, mode, D, err);
+    return check_launch(__func__);
+}
+
+extern "C" int cgs_umma_mma_rate(int form, int N, int n_acc, int iters, long long *out_cycles, void *stream)
+{
+    CGS_CHECK_PTR(out_cycles);
+    if (form < 0 || form > 3 || N < 16 || N > 256 || (N % 16) || n_acc < 1 || n_acc * N > 256 || iters < 1) {
+        set_error("%s: invalid arguments", __func__);
+        return -2;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)2 * (128 + 256) * 8 * sizeof(float);
+    cudaFuncSetAttribute(umma_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    StageScope sc(ST_ELEMWISE, st, 1);
+    umma_mma_rate_kernel<<<1, 128, smem, st>>>(form, N, n_acc, iters, out_cycles);
     return check_launch(__func__);
 }

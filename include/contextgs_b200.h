@@ -93,6 +93,10 @@ CGS_API int cgs_umma_selftest_ss(const float *P, const float *Q, int M, int N, i
 /* The same contraction with both operands in the MN-major no-swizzle layout ([feature / 4][row][4 floats]: one
  * float4 store per four features of a row).  variant 0: SBO = stride between 4-feature groups, LBO = stride
  * between 8-row groups; variant 1: swapped.  N <= 48. */
+/* Micro-benchmark (diagnostic): cycles for a chain of `iters` tcgen05.mma.kind::tf32 (M = 128, K = 8, given N) issued by
+ * one thread; form 0 = A in TMEM, 1 = A in shared memory; n_acc independent accumulators round-robin.
+ * out_cycles[0] = issue time, [1] = issue + completion (SM clock cycles).  scripts/umma_rate_probe.py. */
+CGS_API int cgs_umma_mma_rate(int form, int N, int n_acc, int iters, long long *out_cycles, void *stream);
 CGS_API int cgs_umma_selftest_ss_mn(const float *P, const float *Q, int M, int N, int variant, float *D, int32_t *err,
                                     void *stream);
 
