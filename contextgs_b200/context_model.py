@@ -282,14 +282,19 @@ def _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choo
                                    choose=choose_u8, bit_sum=sums[12:13])
     if getattr(pc, "disable_hyper", False):
         hyper_q = hyper_q * 0
-    feat_q, scaling_q, offsets_q = torch.zeros_like(feat), torch.zeros_like(scaling), torch.zeros_like(offsets)
+    # every anchor is coded by exactly one level, so a full plan overwrites every row: no 516 MB zero-fill per pass
+    # (a shard of the plan leaves the other ranks' rows at zero: the assembled result is a sum)
+    full_plan = sum(lv.n for lv in plan.levels) == N
+    alloc = torch.empty_like if full_plan else torch.zeros_like
+    feat_q, scaling_q, offsets_q = alloc(feat), alloc(scaling), alloc(offsets)
     bits_out = torch.zeros((N, N_CODED), dtype=torch.float32, device=dev) if return_details else None
     means = global_means(pc)
     stream = _lib.stream_ptr()
     level_noise = []
     saved = [None] * len(plan.levels)
     umma = ctx_impl() == "umma"
-    err = torch.zeros(1, dtype=torch.int32, device=dev) if umma else None
+    # the tensor-core time-out flag lives in the last slot of the bit sums (as an int32 view): ONE read-back serves both
+    err = sums[15:16].view(torch.int32)[:1] if umma else None
     for li, lv in enumerate(plan.levels):
         nz = None
         if training and lv.n:
@@ -520,7 +525,7 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
         from .distributed import all_reduce_sums
         all_reduce_sums(sums, group)
     s = info["sums_host"] if "sums_host" in info else sums.tolist()  # one host read-back (the reference: several .item())
-    if info.get("err") is not None and int(info["err"].item()):
+    if info.get("err") is not None and s[15] != 0.0:   # the int32 flag aliases the low word of slot 15
         raise _lib.CgsError("cgs_context_level_umma_forward: a tensor-core completion barrier timed out")
     bit_feat, bit_scaling, bit_offsets = (sum(s[4 * i + c] for i in range(3)) for c in range(3))
     n_chosen = sum(s[4 * i + 3] for i in range(3))

@@ -273,7 +273,7 @@ umma_mma_rate_kernel(int form, int N, int n_acc, int iters, long long *__restric
     const int tid = threadIdx.x, warp = tid >> 5;
     if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
     if (tid == 0) {
-        umma::mbar_init(&s_bar, 1);
+        umma::mbar_init(&s_bar, form >= 6 ? 4 : (form >= 4 ? 2 : 1));
         umma::fence_mbar_init();
     }
     for (int i = tid; i < 2 * (128 + 256) * 8; i += blockDim.x) sm[i] = 0.f;     // A [2][128][4] + B [2][256][4]
@@ -282,15 +282,22 @@ umma_mma_rate_kernel(int form, int N, int n_acc, int iters, long long *__restric
     __syncthreads();
     umma::fence_after_thread_sync();
     const uint32_t tbase = s_tmem;
-    const bool one = form >= 2 ? (umma::uniform_warp() == 0 && umma::elect_one_sync()) : tid == 0;   // forms 2, 3: canonical issue
+    uint32_t tbase_off = 0;
+    // forms 2, 3: canonical issue (warp-uniform branch + elect); forms 4..7: the same from TWO / FOUR warps at once (4, 5: two
+    // issuing warps TS / SS; 6, 7: four), each with its own accumulator -- does the ~200-cycle cost per instruction overlap?
+    const int n_issuers = form >= 6 ? 4 : (form >= 4 ? 2 : 1);
+    const int uw = umma::uniform_warp();
+    const bool one = form >= 2 ? (uw < n_issuers && umma::elect_one_sync()) : tid == 0;
     form &= 1;
     if (one) {
+        n_acc = 1;
+        tbase_off = (uint32_t)uw * 64u;
         const uint32_t idesc = umma::idesc_tf32(128, N);
         const uint32_t a_s = umma::smem_u32(sm), b_s = a_s + 2 * 128 * 16;
         const uint64_t adesc = umma::smem_desc_kmajor(a_s, 128 * 16, 128), bdesc = umma::smem_desc_kmajor(b_s, 256 * 16, 128);
         const long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
-            const uint32_t d = tbase + 256 + (uint32_t)(i % n_acc) * (uint32_t)N;     // accumulators in columns [256,512)
+            const uint32_t d = tbase + 256 + tbase_off + (uint32_t)(i % n_acc) * (uint32_t)N;     // accumulators in columns [256,512)
             if (form == 0) umma::mma_tf32_ts(d, tbase, bdesc, idesc, 1u);
             else umma::mma_tf32_ss(d, adesc, bdesc, idesc, 1u);
         }
@@ -298,8 +305,10 @@ umma_mma_rate_kernel(int form, int N, int n_acc, int iters, long long *__restric
         const long long t1 = clock64();
         umma::mbar_wait(&s_bar, 0);
         const long long t2 = clock64();
-        out[0] = t1 - t0;      // issue time
-        out[1] = t2 - t0;      // issue + completion
+        if (uw == 0) {
+            out[0] = t1 - t0;      // issue time
+            out[1] = t2 - t0;      // issue + completion
+        }
     }
     umma::fence_before_thread_sync();
     __syncthreads();
@@ -366,7 +375,7 @@ extern "C" int cgs_umma_selftest(const float *A, const float *W, int N, int K, i
 extern "C" int cgs_umma_mma_rate(int form, int N, int n_acc, int iters, long long *out_cycles, void *stream)
 {
     CGS_CHECK_PTR(out_cycles);
-    if (form < 0 || form > 3 || N < 16 || N > 256 || (N % 16) || n_acc < 1 || n_acc * N > 256 || iters < 1) {
+    if (form < 0 || form > 7 || (form >= 4 && N > 64) || N < 16 || N > 256 || (N % 16) || n_acc < 1 || n_acc * N > 256 || iters < 1) {
         set_error("%s: invalid arguments", __func__);
         return -2;
     }
