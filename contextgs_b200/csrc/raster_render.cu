@@ -137,9 +137,14 @@ render_forward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__res
                       const float *__restrict__ geom, int W, int H, float bg0, float bg1, float bg2,
                       float *__restrict__ out_color, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib)
 {
-    __shared__ __align__(16) float4 s_a[2][kBatch];
-    __shared__ __align__(16) float4 s_b[2][kBatch];
-    __shared__ __align__(8) float2 s_c[2][kBatch];
+    // one 48-byte record per staged Gaussian {a, b, c, pad}: the blend loop forms ONE address per record and reads the three
+    // parts at immediate offsets (three separate arrays cost an address computation each)
+    struct __align__(16) Rec {
+        float4 a, b;
+        float2 c;
+        float2 pad;
+    };
+    __shared__ Rec s_rec[2][kBatch];
     __shared__ uint8_t s_mask[2][kBatch];
     __shared__ uint8_t s_list[kWarps][kBatch];
 
@@ -149,7 +154,11 @@ render_forward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__res
     const int px = tx0 + (warp & 1) * kBlockW + (lane & (kBlockW - 1));
     const int py = ty0 + (warp >> 1) * kBlockH + (lane >> 3);
     const bool inside = px < W && py < H;
-    const float fx = (float)px, fy = (float)py;
+    // A pixel that has saturated (or lies outside the image) is moved infinitely far away: every later record then fails
+    // the `p2 >= thr` test on its own (p2 = -inf for any ellipse), so the loop carries no `done` flag.
+    constexpr float kFar = -3.0e38f;
+    float fx = inside ? (float)px : kFar;
+    const float fy = (float)py;
 
     const uint32_t rb = ranges[2 * tile], re = ranges[2 * tile + 1];
     const int todo = (int)(re - rb);
@@ -157,7 +166,6 @@ render_forward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__res
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t last_contributor = 0;
-    bool done = !inside;
 
     // software pipeline: the record of batch r+1 and the id of batch r+2 are in flight while batch r blends
     float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
@@ -174,9 +182,9 @@ render_forward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__res
         const int buf = r & 1;
         {
             const StagedRecord s = stage_record(g0, g1, g2, gv, tx0, ty0, W, H);
-            s_a[buf][threadIdx.x] = s.a;
-            s_b[buf][threadIdx.x] = s.b;
-            s_c[buf][threadIdx.x] = s.c;
+            s_rec[buf][threadIdx.x].a = s.a;
+            s_rec[buf][threadIdx.x].b = s.b;
+            s_rec[buf][threadIdx.x].c = s.c;
             s_mask[buf][threadIdx.x] = (uint8_t)s.mask;
             const int i1 = (r + 1) * kBatch + threadIdx.x;
             gv = i1 < todo;
@@ -189,29 +197,29 @@ render_forward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__res
         }
         // one barrier per batch: publishes buffer `buf`; buffer buf^1 (batch r-1) is free again
         // because every thread finished blending it before arriving here
+        const bool done = fx == kFar;     // saturated / outside pixels carry their state in fx
         if (__syncthreads_count(done) == kTilePixels) break;
         if (__all_sync(0xffffffffu, done)) continue;
 
         const int n = build_warp_list(s_mask[buf], s_list[warp], warp, lane);
-        const float4 *ra = s_a[buf];
-        const float4 *rbv = s_b[buf];
-        const float2 *rc = s_c[buf];
+        const Rec *recs = s_rec[buf];
         const uint8_t *list = s_list[warp];
         const uint32_t pos_base = (uint32_t)(r * kBatch + 1);
         for (int j = 0; j < n; ++j) {
             const int idx = list[j];
-            const float4 a = ra[idx];   // x y A2 B2
-            const float4 b = rbv[idx];  // C2 thr2 op r
+            const Rec *rec = recs + idx;
+            const float4 a = rec->a;   // x y A2 B2
+            const float4 b = rec->b;   // C2 thr2 op r
             const float dx = a.x - fx, dy = a.y - fy;
             const float p2 = dx * (a.z * dx + a.w * dy) + b.x * (dy * dy);
-            // skip: alpha < 1/255, the reference's `power > 0` guard, or a pixel that has saturated
-            if (!(p2 >= b.y) || p2 > 0.0f || done) continue;
+            // skip: alpha < 1/255 or the reference's `power > 0` guard (a saturated pixel sits at -3e38: p2 = -inf)
+            if (!(p2 >= b.y) || p2 > 0.0f) continue;
             const float alpha = fminf(kAlphaMax, b.z * fast_exp2(p2));
             const float test_T = T * (1.0f - alpha);
             if (test_T < kTEps) {
-                done = true;
+                fx = kFar;
             } else {
-                const float2 c = rc[idx];
+                const float2 c = rec->c;
                 const float w = alpha * T;
                 C0 += b.w * w;
                 C1 += c.x * w;
@@ -282,10 +290,12 @@ render_backward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__re
                        const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
                        const float *__restrict__ dL_dpix, float *__restrict__ acc)
 {
-    __shared__ __align__(16) float4 s_a[2][kBatch];
-    __shared__ __align__(16) float4 s_b[2][kBatch];
-    __shared__ __align__(8) float2 s_c[2][kBatch];
-    __shared__ uint32_t s_id[2][kBatch];
+    struct __align__(16) Rec {      // one 48-byte staged record: one address per record in the loop below
+        float4 a, b;
+        float2 c;
+        uint32_t id, pad;
+    };
+    __shared__ Rec s_rec[2][kBatch];
     __shared__ uint8_t s_mask[2][kBatch];
     __shared__ uint8_t s_list[kWarps][kBatch];
     __shared__ int s_max_contrib;
@@ -342,10 +352,10 @@ render_backward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__re
         const int hi = max_contrib - r * kBatch;
         {
             const StagedRecord s = stage_record(g0, g1, g2, gv, tx0, ty0, W, H);
-            s_a[buf][threadIdx.x] = s.a;
-            s_b[buf][threadIdx.x] = s.b;
-            s_c[buf][threadIdx.x] = s.c;
-            s_id[buf][threadIdx.x] = gid;
+            s_rec[buf][threadIdx.x].a = s.a;
+            s_rec[buf][threadIdx.x].b = s.b;
+            s_rec[buf][threadIdx.x].c = s.c;
+            s_rec[buf][threadIdx.x].id = gid;
             s_mask[buf][threadIdx.x] = (uint8_t)s.mask;
             const int p1 = hi - kBatch - 1 - (int)threadIdx.x;
             gv = p1 >= 0;
@@ -361,25 +371,23 @@ render_backward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__re
         if (hi - kBatch >= warp_max) continue;  // the whole batch lies behind this warp's deepest contributor
 
         const int n = build_warp_list(s_mask[buf], s_list[warp], warp, lane);
-        const float4 *ra = s_a[buf];
-        const float4 *rbv = s_b[buf];
-        const float2 *rc = s_c[buf];
-        const uint32_t *rid = s_id[buf];
+        const Rec *recs = s_rec[buf];
         const uint8_t *list = s_list[warp];
         for (int j = 0; j < n; ++j) {
             const int idx = list[j];
+            const Rec *rec = recs + idx;
             const int pos = hi - 1 - idx;  // 0-based position in the tile's list
             float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             float g_bl = 0.f;
             bool active = false;
             if (pos < last_contributor) {
-                const float4 a = ra[idx];   // x y A2 B2
-                const float4 b = rbv[idx];  // C2 thr2 op r
+                const float4 a = rec->a;   // x y A2 B2
+                const float4 b = rec->b;   // C2 thr2 op r
                 const float dx = a.x - fx, dy = a.y - fy;
                 const float p2 = dx * (a.z * dx + a.w * dy) + b.x * (dy * dy);
                 if (p2 >= b.y && !(p2 > 0.0f)) {
                     active = true;
-                    const float2 c = rc[idx];
+                    const float2 c = rec->c;
                     const float G = fast_exp2(p2);
                     const float alpha = fminf(kAlphaMax, b.z * G);
                     const float ca = a.z * (-2.0f * kLn2), cb = a.w * (-kLn2), cc = b.x * (-2.0f * kLn2);
@@ -407,7 +415,7 @@ render_backward_kernel(const uint32_t *__restrict__ ranges, const uint32_t *__re
             if (__ballot_sync(0xffffffffu, active) == 0u) continue;
             const float s8 = warp_transpose_reduce8(g, lane);
             g_bl = warp_sum(g_bl);
-            float *dst = acc + (size_t)rid[idx] * 9;
+            float *dst = acc + (size_t)rec->id * 9;
             if ((lane & 3) == 0) {
                 const int id = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
                 atomicAdd(dst + id, s8);
