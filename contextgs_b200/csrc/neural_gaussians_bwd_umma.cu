@@ -185,7 +185,7 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
 
     if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
     if (tid == 0) {
-        umma::mbar_init(&S.bar[0], 1);
+        umma::mbar_init(&S.bar[0], 3);      // three issuing threads commit the head GEMMs
         umma::mbar_init(&S.bar[1], 1);
         umma::fence_mbar_init();
         S.timeout = 0;
@@ -257,14 +257,19 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
         __syncthreads();
 
         // ================= M1: dH_h = dOut_h W2_h =================
-        if (uwarp == 0 && umma::elect_one_sync()) {     // warp-uniform branch + elect: back-to-back tcgen05.mma (umma.cuh)
+        // three independent heads, one issuing warp each (MMAs of different warps overlap; one thread issues one every ~95
+        // cycles): each issuing thread commits its own MMAs, bar[0] counts three arrivals
+        if (uwarp < 3 && umma::elect_one_sync()) {
             umma::fence_after_thread_sync();
-            // the three heads accumulate into different columns: issued round-robin so that their dependency chains overlap
-            const umma::Gemm3x heads[3] = {
-                {tbase + kColD1 + 0, tbase + kColAHi + 0, tbase + kColALo + 0, S.w + kOffW2ToHi, S.w + kOffW2ToLo, 64, kKo},
-                {tbase + kColD1 + 64, tbase + kColAHi + 16, tbase + kColALo + 16, S.w + kOffW2TcHi, S.w + kOffW2TcLo, 64, kKc},
-                {tbase + kColD1 + 128, tbase + kColAHi + 64, tbase + kColALo + 64, S.w + kOffW2TvHi, S.w + kOffW2TvLo, 64, kKv}};
-            umma::gemm_3xtf32_interleaved<3>(heads);
+            if (uwarp == 0)
+                umma::gemm_3xtf32(tbase + kColD1 + 0, tbase + kColAHi + 0, tbase + kColALo + 0, S.w + kOffW2ToHi,
+                                  S.w + kOffW2ToLo, 64, kKo, true);
+            else if (uwarp == 1)
+                umma::gemm_3xtf32(tbase + kColD1 + 64, tbase + kColAHi + 16, tbase + kColALo + 16, S.w + kOffW2TcHi,
+                                  S.w + kOffW2TcLo, 64, kKc, true);
+            else
+                umma::gemm_3xtf32(tbase + kColD1 + 128, tbase + kColAHi + 64, tbase + kColALo + 64, S.w + kOffW2TvHi,
+                                  S.w + kOffW2TvLo, 64, kKv, true);
             umma::umma_commit(&S.bar[0]);
         }
         if (!umma::mbar_wait(&S.bar[0], parity)) S.timeout = 1;

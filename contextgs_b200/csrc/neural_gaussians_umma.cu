@@ -241,7 +241,7 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
 
     if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
     if (tid == 0) {
-        for (int i = 0; i < BAR_COUNT; ++i) umma::mbar_init(&S.bar[i], 1);
+        for (int i = 0; i < BAR_COUNT; ++i) umma::mbar_init(&S.bar[i], i == BAR_L2ALL ? 3 : 1);   // three issuing threads commit layer 2
         umma::fence_mbar_init();
         S.timeout = 0;
     }
@@ -379,18 +379,22 @@ neural_gaussians_umma_kernel(const float *__restrict__ packed_w, const int *__re
                 if (!umma::mbar_wait(&S.bar[BAR_ACCFREE], parity ^ 1u)) S.timeout = 1;
                 umma::fence_after_thread_sync();
             }
-            if (uwarp == 0 && umma::elect_one_sync()) {
+            // The three heads are independent GEMMs.  One thread issues a tcgen05.mma every ~95 cycles whatever its shape, and
+            // MMAs issued by different warps overlap (scripts/umma_rate_probe.py): three warps issue one head each, 21 MMAs
+            // per warp instead of 63 from one thread.  Every issuing thread commits its own MMAs (BAR_L2ALL counts three).
+            if (uwarp < 3 && umma::elect_one_sync()) {
                 umma::fence_after_thread_sync();
-                umma::gemm_3xtf32(tbase + kColDo, tbase + kColD1 + 0 * kHeadStride, tbase + kColHLo + 0 * kHeadStride,
-                                  S.w + kOffW2oHi, S.w + kOffW2oLo, kNo, kK1, true);
-                umma::umma_commit(&S.bar[BAR_L2O]);
-                // colour and covariance accumulate into different columns: issued round-robin (their dependency chains overlap)
-                const umma::Gemm3x cv[2] = {
-                    {tbase + kColDc, tbase + kColD1 + 1 * kHeadStride, tbase + kColHLo + 1 * kHeadStride, S.w + kOffW2cHi,
-                     S.w + kOffW2cLo, kNc, kK1},
-                    {tbase + kColDv, tbase + kColD1 + 2 * kHeadStride, tbase + kColHLo + 2 * kHeadStride, S.w + kOffW2vHi,
-                     S.w + kOffW2vLo, kNv, kK1}};
-                umma::gemm_3xtf32_interleaved<2>(cv);
+                if (uwarp == 0) {
+                    umma::gemm_3xtf32(tbase + kColDo, tbase + kColD1 + 0 * kHeadStride, tbase + kColHLo + 0 * kHeadStride,
+                                      S.w + kOffW2oHi, S.w + kOffW2oLo, kNo, kK1, true);
+                    umma::umma_commit(&S.bar[BAR_L2O]);
+                } else if (uwarp == 1) {
+                    umma::gemm_3xtf32(tbase + kColDc, tbase + kColD1 + 1 * kHeadStride, tbase + kColHLo + 1 * kHeadStride,
+                                      S.w + kOffW2cHi, S.w + kOffW2cLo, kNc, kK1, true);
+                } else {
+                    umma::gemm_3xtf32(tbase + kColDv, tbase + kColD1 + 2 * kHeadStride, tbase + kColHLo + 2 * kHeadStride,
+                                      S.w + kOffW2vHi, S.w + kOffW2vLo, kNv, kK1, true);
+                }
                 umma::umma_commit(&S.bar[BAR_L2ALL]);
             }
             if (it > 0) {   // copy the previous tile out while the tensor core and BACK work on
