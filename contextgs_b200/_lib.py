@@ -103,9 +103,13 @@ SIGNATURES = {
     "cgs_context_level_backward_umma": (c_int, [c_int, _PTR, _PTR, _PTR, _PTR, c_int] + [_PTR] * 8 + [ctypes.c_float] * 3 +
                                         [_PTR, ctypes.c_float] + [_PTR] * 13 + [c_int, _PTR]),
     "cgs_codec_gauss_stream_capacity": (c_int64, [c_int, c_int]),
-    "cgs_codec_gauss_minmax": (c_int, [c_int, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR]),
-    "cgs_codec_gauss_encode": (c_int, [c_int, _PTR, c_int, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, c_int64, _PTR, _PTR, _PTR]),
-    "cgs_codec_gauss_decode": (c_int, [c_int, _PTR, c_int, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR]),
+    "cgs_codec_gauss_level_chunks": (c_int64, [c_int, _PTR, _PTR]),
+    "cgs_codec_gauss_level_minmax": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR]),
+    "cgs_codec_gauss_level_encode": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
+                                             _PTR]),
+    "cgs_codec_gauss_level_pack": (c_int, [c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR]),
+    "cgs_codec_gauss_level_decode": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
+                                             _PTR, _PTR]),
     "cgs_codec_table_encode": (c_int, [_PTR, c_int, c_int, c_int, _PTR, c_int, c_int, _PTR, c_int64, _PTR, _PTR, _PTR]),
     "cgs_codec_table_decode": (c_int, [_PTR, _PTR, _PTR, c_int, c_int, c_int, _PTR, _PTR, c_int, c_int, _PTR, _PTR]),
     "cgs_codec_pack_streams": (c_int, [_PTR, c_int64, _PTR, _PTR, c_int, _PTR, _PTR]),

@@ -13,6 +13,7 @@ Everything heavy runs on the GPU: one level kernel (cgs_context_level_umma_forwa
 (mean, scale, Q) of every coded value, one thread per ~1600-symbol chunk range-codes it in closed form.
 The host only builds two tiny frequency tables and concatenates streams.
 """
+import ctypes
 import os
 from types import SimpleNamespace
 
@@ -42,33 +43,39 @@ def dequantize_anchor(q, x_bound_min, x_bound_max):
 
 
 def frequency_tables(pmf):
-    """pmf [T, L] (any positive weights) -> uint32 [T, L + 1] cumulative 16-bit frequencies with every symbol
-    codable: C(i) = floor(cum_i / cum_L * (65536 - L)) + i, C(0) = 0, C(L) = 65536."""
-    pmf = pmf.detach().to("cpu", torch.float64).clamp_min(0)
+    """pmf [T, L] (any positive weights) -> int32 [T, L + 1] cumulative 16-bit frequencies with every symbol
+    codable: C(i) = floor(cum_i / cum_L * (65536 - L)) + i, C(0) = 0, C(L) = 65536.  Computed in float64 on the
+    device of `pmf` (no host round trip when the weights are already on the GPU)."""
+    pmf = pmf.detach().to(torch.float64).clamp_min(0)
     T, L = pmf.shape
     if L >= 32768:
         raise ValueError("alphabet too large for 16-bit frequencies")
+    dev = pmf.device
     cum = torch.cumsum(pmf, dim=1)
     total = cum[:, -1:].clamp_min(1e-300)
-    body = torch.floor(cum / total * (65536 - L)).to(torch.int64) + torch.arange(1, L + 1).view(1, L)
+    body = torch.floor(cum / total * (65536 - L)).to(torch.int64) + torch.arange(1, L + 1, device=dev).view(1, L)
     body[:, -1] = 65536
-    return torch.cat([torch.zeros(T, 1, dtype=torch.int64), body], dim=1).to(torch.int32)
+    return torch.cat([torch.zeros(T, 1, dtype=torch.int64, device=dev), body], dim=1).to(torch.int32)
 
 
-def _pack(scratch, cap, lens, dev):
-    """fixed-stride chunks -> (packed uint8 tensor, offsets int64)"""
-    L = _lib.lib()
-    n = lens.numel()
-    off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(lens.to(torch.int64), 0, out=off[1:])
-    total = int(off[-1].item())
-    packed = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
-    _lib.check(L.cgs_codec_pack_streams(_lib.ptr(scratch), cap, _lib.ptr(lens), _lib.ptr(off), n, _lib.ptr(packed),
-                                        _lib.stream_ptr()), "cgs_codec_pack_streams")
-    return packed[:total], off[:-1].contiguous()
+def mask_table(p1):
+    """The Bernoulli table of the offset-mask stream from P(mask = 1) (utils/encodings.py:147-165).  `p1` is a python
+    float (decoder: from the metadata) or a 0-dim tensor (encoder: stays on the device); both go through the same
+    float64 arithmetic, so the two sides build identical tables."""
+    p = p1.detach().to(torch.float64).reshape(()) if torch.is_tensor(p1) else torch.tensor(float(p1), dtype=torch.float64)
+    return frequency_tables(torch.stack([(1.0 - p).clamp_min(1e-9), p.clamp_min(1e-9)]).view(1, 2))
+
+
+def _offsets(lens):
+    """exclusive prefix sum of the chunk lengths, with the total appended: int64 [n + 1]"""
+    off = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=lens.device)
+    torch.cumsum(lens, 0, dtype=torch.int64, out=off[1:])
+    return off
 
 
 def _table_encode(symbols, tables, chunk_rows, err):
+    """Codes a static-table stream into fixed-stride scratch slots.  Returns (scratch, cap, lens, off): packing into one
+    byte string needs the total on the host and is deferred to _table_pack so that an encode has ONE read-back."""
     L = _lib.lib()
     dev = symbols.device
     n, C = symbols.shape
@@ -80,19 +87,27 @@ def _table_encode(symbols, tables, chunk_rows, err):
     _lib.check(L.cgs_codec_table_encode(_lib.ptr(symbols), n, C, chunk_rows, _lib.ptr(tb), tb.shape[0], tb.shape[1],
                                         _lib.ptr(scratch), cap, _lib.ptr(lens), _lib.ptr(err), _lib.stream_ptr()),
                "cgs_codec_table_encode")
-    packed, _ = _pack(scratch, cap, lens[:n_chunks], dev)
-    return packed, lens[:n_chunks]
+    lens = lens[:n_chunks]
+    return scratch, cap, lens, _offsets(lens)
+
+
+def _table_pack(pending, total):
+    scratch, cap, lens, off = pending
+    packed = torch.empty(max(total, 1), dtype=torch.uint8, device=lens.device)
+    _lib.check(_lib.lib().cgs_codec_pack_streams(_lib.ptr(scratch), cap, _lib.ptr(lens), _lib.ptr(off), lens.numel(),
+                                                 _lib.ptr(packed), _lib.stream_ptr()), "cgs_codec_pack_streams")
+    return packed[:total]
 
 
 def _table_decode(packed, lens, n, C, tables, chunk_rows):
     L = _lib.lib()
     dev = packed.device
-    off = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(lens.to(torch.int64), 0, out=off[1:])
+    lens = lens.to(torch.int32).contiguous()
+    off = _offsets(lens)
     tb = tables.to(dev).contiguous()
     tlen = torch.full((tb.shape[0],), tb.shape[1] - 1, dtype=torch.int32, device=dev)
     sym = torch.empty((n, C), dtype=torch.int16, device=dev)
-    _lib.check(L.cgs_codec_table_decode(_lib.ptr(packed), _lib.ptr(off), _lib.ptr(lens.contiguous()), n, C, chunk_rows,
+    _lib.check(L.cgs_codec_table_decode(_lib.ptr(packed), _lib.ptr(off), _lib.ptr(lens), n, C, chunk_rows,
                                         _lib.ptr(tb), _lib.ptr(tlen), tb.shape[0], tb.shape[1], _lib.ptr(sym),
                                         _lib.stream_ptr()), "cgs_codec_table_decode")
     return sym
@@ -108,16 +123,20 @@ def _hyper_tables(pc, smin, smax):
     return frequency_tables(lik.t().contiguous() + 1e-12)
 
 
-def _content_key(anchor_q, pc):
+def _content_key(anchor_q, pc, extra=None):
     """Cache key from the CONTENT of the coded anchors and the bounds they are dequantised with: two position-weighted
     int64 checksums of the 16-bit grid indices + the six bound values, one small read-back.  (Keying on data_ptr /
-    _version of a temporary would let the caching allocator hand the same address to another stream's anchors.)"""
+    _version of a temporary would let the caching allocator hand the same address to another stream's anchors.)
+    `extra`: int64 device scalars the caller needs on the host as well; they ride on the same read-back and are
+    returned as a list after the key."""
     q = (anchor_q.to(torch.int64) & 0xffff).reshape(-1)
     w = torch.arange(1, q.numel() + 1, device=q.device, dtype=torch.int64)
     sums = torch.stack([q.sum(), (q * (w % 65521 + 1)).sum(), (q * (w % 8191 + 7)).sum()])
     bounds = torch.cat([pc.x_bound_min.reshape(-1), pc.x_bound_max.reshape(-1)]).float().to(q.device).view(torch.int32)
-    vals = torch.cat([sums, bounds.to(torch.int64)]).tolist()   # exact: integer checksums, bit patterns of the bounds
-    return (tuple(anchor_q.shape),) + tuple(vals)
+    parts = [sums, bounds.to(torch.int64)] + ([] if extra is None else [torch.stack(list(extra)).to(torch.int64)])
+    vals = torch.cat(parts).tolist()   # exact: integer checksums, bit patterns of the bounds
+    key = (tuple(anchor_q.shape),) + tuple(vals[:9])
+    return key if extra is None else (key, vals[9:])
 
 
 def _plan_for(pc, anchor, key, rank, world):
@@ -180,32 +199,33 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1):
     anchor_q = qv.to(torch.int32)
     anchor = dequantize_anchor(anchor_q, pc.x_bound_min, pc.x_bound_max).contiguous()
 
-    # offset masks: one Bernoulli table
-    p1 = float(masks.mean())
-    mask_tables = frequency_tables(torch.tensor([[max(1.0 - p1, 1e-9), max(p1, 1e-9)]]))
-    mask_bytes, mask_lens = _table_encode(masks.to(torch.int16).contiguous(), mask_tables, chunk_rows * TABLE_CHUNK_MULT, err)
+    # offset masks: one Bernoulli table (built on the device; P(1) reaches the host with the final read-back)
+    p1_dev = masks.mean()
+    mask_pending = _table_encode(masks.to(torch.int16).contiguous(), mask_table(p1_dev), chunk_rows * TABLE_CHUNK_MULT, err)
 
-    # hyper latents under the factorised prior
+    # hyper latents under the factorised prior.  The symbol range sizes the table, so it is needed on the host: it shares
+    # the read-back of the level-plan cache key
     hyper_q, _ = pc.latent_codec(hyper, training=False)
     median = pc.latent_codec.quantiles[:, 0, 1].detach()
     hsym = torch.round(hyper_q - median.view(1, -1)).to(torch.int32)
-    hmin, hmax = int(hsym.min()), int(hsym.max())
-    hyper_tables = _hyper_tables(pc, hmin, hmax)
-    hyper_bytes, hyper_lens = _table_encode((hsym - hmin).to(torch.int16).contiguous(), hyper_tables,
-                                            chunk_rows * TABLE_CHUNK_MULT, err)
+    hlo, hhi = torch.aminmax(hsym)
+    content_key, (hmin, hmax) = _content_key(anchor_q, pc, extra=(hlo, hhi))
+    hyper_pending = _table_encode((hsym - hmin).to(torch.int16).contiguous(), _hyper_tables(pc, hmin, hmax),
+                                  chunk_rows * TABLE_CHUNK_MULT, err)
     if getattr(pc, "disable_hyper", False):
         hyper_q = hyper_q * 0
 
     # level division on the DEQUANTISED anchors (what the decoder will see)
     if pc.level_scale is None:
         pc.level_scale = find_divide_scale(pc, anchor, pc.target_ratio, pc.level_num)
-    n_levels_full, plan = _plan_for(pc, anchor, _content_key(anchor_q, pc), rank, world)
+    n_levels_full, plan = _plan_for(pc, anchor, content_key, rank, world)
 
     feat_q, scaling_q, offsets_q = torch.zeros_like(feat), torch.zeros_like(scaling), torch.zeros_like(offsets)
     sums = torch.zeros(16, dtype=torch.float64, device=dev)
     terr = torch.zeros(1, dtype=torch.int32, device=dev)
     means = global_means(pc)
-    levels = []
+    rows3 = (ctypes.c_int * 3)(*[chunk_rows * m for m in ATTR_CHUNK_MULT])
+    levels, pending = [], []
     for li, lv in enumerate(plan.levels):
         entry = SimpleNamespace(level=lv.level, n=lv.n, streams={})
         levels.append(entry)
@@ -213,36 +233,55 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1):
             continue
         params = _level_params(pc, lv, anchor, hyper_q, feat, scaling, offsets, masks, feat_q, scaling_q, offsets_q,
                                sums[4 * li:4 * li + 4], terr, means, False)
-        for attr, (name, dim) in enumerate(ATTRS):
-            rows = chunk_rows * ATTR_CHUNK_MULT[attr]
-            n_chunks = (lv.n + rows - 1) // rows
-            cap = int(L.cgs_codec_gauss_stream_capacity(attr, rows))
-            scratch = torch.empty(n_chunks * cap // 4, dtype=torch.int32, device=dev)
-            lens = torch.zeros(n_chunks, dtype=torch.int32, device=dev)
-            minmax = torch.empty(2, dtype=torch.int32, device=dev)
-            values = (feat_q, scaling_q, offsets_q)[attr]
-            _lib.check(L.cgs_codec_gauss_minmax(attr, _lib.ptr(lv.orig), lv.n, _lib.ptr(params), _lib.ptr(masks),
-                                                _lib.ptr(values), _lib.ptr(minmax), _lib.stream_ptr()), "cgs_codec_gauss_minmax")
-            _lib.check(L.cgs_codec_gauss_encode(attr, _lib.ptr(lv.orig), lv.n, rows, _lib.ptr(params), _lib.ptr(masks),
-                                                _lib.ptr(values), _lib.ptr(minmax), _lib.ptr(scratch), cap, _lib.ptr(lens),
-                                                _lib.ptr(err), _lib.stream_ptr()), "cgs_codec_gauss_encode")
-            packed, _ = _pack(scratch, cap, lens, dev)
-            entry.streams[name] = SimpleNamespace(bytes=packed, lens=lens, minmax=minmax)
-    e, te = int(err.item()), int(terr.item())
+        counts = (ctypes.c_int32 * 3)()
+        words = int(L.cgs_codec_gauss_level_chunks(lv.n, rows3, counts))
+        counts = list(counts)
+        minmax = torch.empty(6, dtype=torch.int32, device=dev)
+        intervals = torch.empty(lv.n * 86, dtype=torch.int32, device=dev)
+        scratch = torch.empty(words, dtype=torch.int32, device=dev)
+        lens = torch.zeros(sum(counts), dtype=torch.int32, device=dev)
+        p = _lib.ptr
+        _lib.check(L.cgs_codec_gauss_level_minmax(p(lv.orig), lv.n, p(params), p(masks), p(feat_q), p(scaling_q), p(offsets_q),
+                                                  p(minmax), _lib.stream_ptr()), "cgs_codec_gauss_level_minmax")
+        _lib.check(L.cgs_codec_gauss_level_encode(p(lv.orig), lv.n, rows3, p(params), p(masks), p(feat_q), p(scaling_q),
+                                                  p(offsets_q), p(minmax), p(intervals), p(scratch), p(lens), p(err),
+                                                  _lib.stream_ptr()), "cgs_codec_gauss_level_encode")
+        off = _offsets(lens)
+        bounds = [counts[0], counts[0] + counts[1], counts[0] + counts[1] + counts[2]]
+        pending.append((entry, lv.n, scratch, lens, off, counts, minmax, off[bounds]))
+
+    # ONE read-back for everything the host needs: error flags, stream sizes (to allocate the packed byte strings),
+    # P(mask), the estimated bits
+    i64 = lambda t: t.reshape(-1).to(torch.int64)
+    parts = [i64(err), i64(terr), mask_pending[3][-1:], hyper_pending[3][-1:], p1_dev.double().reshape(1).view(torch.int64),
+             sums.view(torch.int64)] + [pd[7] for pd in pending]
+    host = torch.cat(parts).cpu()
+    e, te, mask_total, hyper_total = (int(v) for v in host[:4])
     if te:
         raise _lib.CgsError("cgs_context_level_umma_forward_ex: a tensor-core completion barrier timed out")
     if e:
         raise _lib.CgsError({1: "a symbol has an empty coding interval", 2: "a chunk's alphabet exceeds 32768 symbols",
                              3: "a stream outgrew its capacity"}.get(e, f"codec error {e}"))
+    p1 = float(host[4:5].view(torch.float64)[0])
+    s = host[5:21].view(torch.float64).tolist()
+    mask_bytes, hyper_bytes = _table_pack(mask_pending, mask_total), _table_pack(hyper_pending, hyper_total)
+    for (entry, n, scratch, lens, off, counts, minmax, _), ends in zip(pending, host[21:].reshape(len(pending), 3).tolist()):
+        packed = torch.empty(max(ends[2], 1), dtype=torch.uint8, device=dev)
+        _lib.check(L.cgs_codec_gauss_level_pack(n, rows3, _lib.ptr(scratch), _lib.ptr(lens), _lib.ptr(off), _lib.ptr(packed),
+                                                _lib.stream_ptr()), "cgs_codec_gauss_level_pack")
+        b0 = c0 = 0
+        for attr, (name, dim) in enumerate(ATTRS):
+            entry.streams[name] = SimpleNamespace(bytes=packed[b0:ends[attr]], lens=lens[c0:c0 + counts[attr]],
+                                                  minmax=minmax[2 * attr:2 * attr + 2])
+            b0, c0 = ends[attr], c0 + counts[attr]
     meta = dict(version=1, N_total=int(pc._anchor.shape[0]), N=N, chunk_rows=chunk_rows, voxel_size=float(pc.voxel_size),
-                level_scale=[float(s) for s in pc.level_scale], x_bound_min=pc.x_bound_min.detach().cpu(),
+                level_scale=[float(s_) for s_ in pc.level_scale], x_bound_min=pc.x_bound_min.detach().cpu(),
                 x_bound_max=pc.x_bound_max.detach().cpu(), prob_masks=p1, hyper_min=hmin, hyper_max=hmax,
                 means=means, N_levels=n_levels_full, world=world)
-    s = sums.tolist()
     est = dict(hyper=None, feat=sum(s[4 * i] for i in range(3)), scaling=sum(s[4 * i + 1] for i in range(3)),
                offsets=sum(s[4 * i + 2] for i in range(3)))
-    return SimpleNamespace(meta=meta, anchor_q=anchor_q.to(torch.int16), mask_bytes=mask_bytes, mask_lens=mask_lens,
-                           hyper_bytes=hyper_bytes, hyper_lens=hyper_lens, levels=levels, valid=sel,
+    return SimpleNamespace(meta=meta, anchor_q=anchor_q.to(torch.int16), mask_bytes=mask_bytes, mask_lens=mask_pending[2],
+                           hyper_bytes=hyper_bytes, hyper_lens=hyper_pending[2], levels=levels, valid=sel,
                            quantised=dict(anchor=anchor, hyper=hyper_q, feat=feat_q, scaling=scaling_q, offsets=offsets_q,
                                           masks=masks), estimated_bits=est, plan=plan)
 
@@ -273,9 +312,7 @@ def decode_model(pc, meta, anchor_q, mask_bytes, mask_lens, hyper_bytes, hyper_l
     pc.voxel_size = meta["voxel_size"]
     anchor = dequantize_anchor(anchor_q.to(dev).to(torch.int32) & 0xffff, pc.x_bound_min, pc.x_bound_max).contiguous()
 
-    p1 = meta["prob_masks"]
-    mask_tables = frequency_tables(torch.tensor([[max(1.0 - p1, 1e-9), max(p1, 1e-9)]]))
-    masks = _table_decode(mask_bytes.to(dev), mask_lens.to(dev), N, K, mask_tables,
+    masks = _table_decode(mask_bytes.to(dev), mask_lens.to(dev), N, K, mask_table(meta["prob_masks"]),
                           chunk_rows * TABLE_CHUNK_MULT).float().contiguous()
 
     hmin, hmax = meta["hyper_min"], meta["hyper_max"]
@@ -294,22 +331,21 @@ def decode_model(pc, meta, anchor_q, mask_bytes, mask_lens, hyper_bytes, hyper_l
     sums = torch.zeros(16, dtype=torch.float64, device=dev)
     terr = torch.zeros(1, dtype=torch.int32, device=dev)
     means = tuple(meta["means"])
+    rows3 = (ctypes.c_int * 3)(*[chunk_rows * m for m in ATTR_CHUNK_MULT])
     for li, (lv, coded) in enumerate(zip(plan.levels, levels)):
         if lv.n == 0:
             continue
         params = _level_params(pc, lv, anchor, hyper_ctx, None, None, None, None, feat_q, scaling_q, offsets_q,
                                sums[4 * li:4 * li + 4], terr, means, True)
-        for attr, (name, dim) in enumerate(ATTRS):
-            st = coded.streams[name]
-            lens = st.lens.to(dev).contiguous()
-            off = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=dev)
-            torch.cumsum(lens.to(torch.int64), 0, out=off[1:])
-            values = (feat_q, scaling_q, offsets_q)[attr]
-            _lib.check(L.cgs_codec_gauss_decode(attr, _lib.ptr(lv.orig), lv.n, chunk_rows * ATTR_CHUNK_MULT[attr],
-                                                _lib.ptr(params), _lib.ptr(masks),
-                                                _lib.ptr(st.bytes.to(dev)), _lib.ptr(off), _lib.ptr(lens),
-                                                _lib.ptr(st.minmax.to(dev).to(torch.int32).contiguous()), _lib.ptr(values),
-                                                _lib.stream_ptr()), "cgs_codec_gauss_decode")
+        st = [coded.streams[name] for name, _ in ATTRS]
+        lens = torch.cat([t.lens.to(dev).to(torch.int32) for t in st])
+        minmax = torch.cat([t.minmax.to(dev).to(torch.int32) for t in st])
+        data = [t.bytes.to(dev).contiguous() for t in st]   # named: the pointers must outlive the launch
+        off = _offsets(lens)
+        p = _lib.ptr
+        _lib.check(L.cgs_codec_gauss_level_decode(p(lv.orig), lv.n, rows3, p(params), p(masks), p(data[0]), p(data[1]),
+                                                  p(data[2]), p(off), p(lens), p(minmax), p(feat_q), p(scaling_q),
+                                                  p(offsets_q), _lib.stream_ptr()), "cgs_codec_gauss_level_decode")
     if int(terr.item()):
         raise _lib.CgsError("cgs_context_level_umma_forward_ex: a tensor-core completion barrier timed out")
     return dict(anchor=anchor, hyper=hyper_q, feat=feat_q, offsets=offsets_q.view(N, K, 3), scaling=scaling_q,

@@ -7,8 +7,10 @@
 // a sequential C++ arithmetic coder per 1000-anchor chunk.  Here every chunk of every stream is coded by
 // its own GPU thread with a byte-wise 32-bit range coder (carry propagation through a cached byte, 16-bit
 // cumulative frequencies); the discretised-Gaussian CDF of a symbol is evaluated IN CLOSED FORM from
-// (mean, scale, Q) -- two erf per encoded symbol, a binary search of ~log2(alphabet) evaluations per decoded
-// symbol -- so no table ever exists.  The container is this library's own (torchac is not in the reference
+// (mean, scale, Q), so no table ever exists.  Encoding is two passes per level: a fully parallel pass writes the
+// coding interval of every value (two erf each, coalesced), then one thread per chunk runs only the carried
+// (low, range) state over its intervals.  Decoding inverts the Gaussian CDF at the coder's target to land on the
+// symbol directly and confirms it with ~2 CDF evaluations (bisection only in the tails).  The container is this library's own (torchac is not in the reference
 // tree, its stream format cannot be pinned): parity = encode -> decode returns the quantised tensors bit
 // for bit, and the stream length matches the estimated bits.
 //
@@ -119,128 +121,257 @@ __device__ __forceinline__ uint32_t gauss_cum(int s, int smin, int L, float Q, f
     return c + (uint32_t)(s - smin);
 }
 
-struct GaussStream {
+// All three Gaussian streams (feat / scaling / offsets) of ONE level; attr 0 / 1 / 2, dim 50 / 6 / 30, first params
+// column 0 / 50 / 56.  Chunk ids run over the three streams back to back: [0, n_chunks[0]) feat, then scaling, then offsets.
+struct LevelStreams {
     const int32_t *orig_idx;   // [n_rows] level row -> original anchor
     const float *params;       // [n_rows][176]
     const float *mask;         // [N][10] (offsets stream only)
-    int n_rows, chunk_rows, attr, dim, col0;   // attr 0 feat / 1 scaling / 2 offsets; dim 50 / 6 / 30; col0 0 / 50 / 56
+    float *values[3];          // [N][dim] quantised values (read by the encoder, written by the decoder)
+    int n_rows;
+    int rows[3];               // level rows per chunk
+    int n_chunks[3];
+    uint32_t cap[3];           // bytes reserved per chunk in the encoder's scratch
+    int64_t region[3];         // first scratch WORD of each stream
 };
 
-__device__ __forceinline__ bool coded(const GaussStream &g, int o, int k)
+constexpr uint32_t kSkip = 0xffffffffu;   // interval slot of a value that is not coded (lo 65535 + width 65536 cannot occur)
+
+__device__ __forceinline__ int attr_of_col(int col) { return col < kCF ? 0 : col < kCF + kCS ? 1 : 2; }
+__device__ __forceinline__ int attr_dim(int a) { return a == 0 ? kCF : a == 1 ? kCS : kCO; }
+__device__ __forceinline__ int attr_col0(int a) { return a == 0 ? 0 : a == 1 ? kCF : kCF + kCS; }
+template <typename T> __device__ __forceinline__ T pick3(const T (&v)[3], int a) { return a == 0 ? v[0] : a == 1 ? v[1] : v[2]; }
+
+// chunk id over the three streams -> (attr, chunk of that stream)
+__device__ __forceinline__ bool locate_chunk(const LevelStreams &g, int c, int &attr, int &cl)
 {
-    return g.attr != 2 || g.mask[(size_t)o * 10 + k / 3] != 0.0f;
+    if (c < g.n_chunks[0]) { attr = 0; cl = c; return true; }
+    c -= g.n_chunks[0];
+    if (c < g.n_chunks[1]) { attr = 1; cl = c; return true; }
+    c -= g.n_chunks[1];
+    attr = 2; cl = c;
+    return c < g.n_chunks[2];
 }
 
-// Alphabet of one (level, attribute) stream: min / max of rint(value / Q) over all its coded values.
-// One thread per level row, warp-reduced, two atomics per warp.
-__global__ void __launch_bounds__(256)
-gauss_minmax_kernel(GaussStream g, const float *__restrict__ values, int32_t *__restrict__ minmax)
+__global__ void minmax_init_kernel(int32_t *minmax)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    int smin = 0x7fffffff, smax = -0x7fffffff;
-    if (r < g.n_rows) {
-        const int o = g.orig_idx[r];
-        const float Q = g.params[(size_t)r * kLdG2 + 172 + g.attr];
-        const float *x = values + (size_t)o * g.dim;
-        for (int k = 0; k < g.dim; ++k) {
-            if (!coded(g, o, k)) continue;
-            const int s = (int)rintf(__fdiv_rn(x[k], Q));
-            smin = min(smin, s);
-            smax = max(smax, s);
+    if (threadIdx.x < 6) minmax[threadIdx.x] = (threadIdx.x & 1) ? -2139062144 : 2139062143;   // empty stream: max < min
+}
+
+// Alphabets of the three streams of a level: min / max of rint(value / Q) over the coded values.  One warp per level
+// row (lane -> columns lane, lane + 32, lane + 64 of the 86 coded values: the row's loads are coalesced and its anchor
+// index / Q are fetched once), redux per warp, shared atomics per block, six global atomics per block.
+constexpr int kRowsPerWarp = 4;
+
+__global__ void __launch_bounds__(256)
+gauss_level_minmax_kernel(LevelStreams g, int32_t *__restrict__ minmax)
+{
+    __shared__ int32_t sm[6];
+    if (threadIdx.x < 6) sm[threadIdx.x] = (threadIdx.x & 1) ? -0x7fffffff : 0x7fffffff;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int row0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kRowsPerWarp;
+    int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-0x7fffffff, -0x7fffffff, -0x7fffffff};
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int row = row0 + rr;
+        if (row >= g.n_rows) break;
+        const int o = g.orig_idx[row];
+        const float *pr = g.params + (size_t)row * kLdG2;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {   // j is also the stream of most of these columns; the exact one is attr
+            const int col = lane + 32 * j;
+            if (col >= kCE) continue;
+            const int attr = attr_of_col(col), k = col - attr_col0(attr);
+            if (attr == 2 && g.mask[(size_t)o * 10 + k / 3] == 0.0f) continue;
+            const int s = (int)rintf(__fdiv_rn(pick3(g.values, attr)[(size_t)o * attr_dim(attr) + k], pr[172 + attr]));
+            if (attr == 0) { lo[0] = min(lo[0], s); hi[0] = max(hi[0], s); }
+            else if (attr == 1) { lo[1] = min(lo[1], s); hi[1] = max(hi[1], s); }
+            else { lo[2] = min(lo[2], s); hi[2] = max(hi[2], s); }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, o));
-        smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    for (int a = 0; a < 3; ++a) {
+        const int l = __reduce_min_sync(0xffffffffu, lo[a]), h = __reduce_max_sync(0xffffffffu, hi[a]);
+        if (lane == 0 && l <= h) {
+            atomicMin(&sm[2 * a], l);
+            atomicMax(&sm[2 * a + 1], h);
+        }
     }
-    if ((threadIdx.x & 31) == 0 && smin <= smax) {
-        atomicMin(&minmax[0], smin);
-        atomicMax(&minmax[1], smax);
+    __syncthreads();
+    if (threadIdx.x < 6 && sm[threadIdx.x & ~1] <= sm[threadIdx.x | 1]) {
+        if (threadIdx.x & 1) atomicMax(&minmax[threadIdx.x], sm[threadIdx.x]);
+        else atomicMin(&minmax[threadIdx.x], sm[threadIdx.x]);
     }
 }
 
-// One thread per chunk.  The next symbol's value / mean / scale are fetched before the current symbol is coded:
-// the coder's carried state (low, range) is the only true dependency between symbols.
-__global__ void __launch_bounds__(64)
-gauss_encode_kernel(GaussStream g, const float *__restrict__ values /* [N][dim], quantised */,
-                    const int32_t *__restrict__ minmax, uint32_t *__restrict__ out, uint32_t cap_bytes,
-                    int32_t *__restrict__ stream_len, int32_t *__restrict__ err)
+// Encoder pass 1, one warp per level row (columns as above): the coding interval [C(s), C(s + 1)) of every coded value,
+// packed as lo | (hi - lo - 1) << 16 into iv[n_rows * col0 + row * dim + k] (kSkip for values that are not coded), so the
+// two erf and the division are out of the sequential coder and all loads are coalesced.
+__global__ void __launch_bounds__(256)
+gauss_level_intervals_kernel(LevelStreams g, const int32_t *__restrict__ minmax, uint32_t *__restrict__ iv,
+                             int32_t *__restrict__ err)
 {
-    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_chunks = (g.n_rows + g.chunk_rows - 1) / g.chunk_rows;
-    if (chunk >= n_chunks) return;
-    const int r0 = chunk * g.chunk_rows, r1 = min(r0 + g.chunk_rows, g.n_rows);
-    const int smin = minmax[0], smax = minmax[1];
-    const int L = smax - smin + 1;
-    if (smax < smin || L > 32768) {   // empty stream / cannot happen after the +-15000-step clamp of STE_multistep
-        if (smax >= smin) atomicExch(err, 2);
-        stream_len[chunk] = 0;
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= g.n_rows) return;
+    const int o = g.orig_idx[row];
+    const float *pr = g.params + (size_t)row * kLdG2;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int col = lane + 32 * j;
+        if (col >= kCE) continue;
+        const int attr = attr_of_col(col), col0 = attr_col0(attr), dim = attr_dim(attr), k = col - col0;
+        const int smin = minmax[2 * attr], smax = minmax[2 * attr + 1];
+        const int L = smax - smin + 1;
+        uint32_t packed = kSkip;
+        if (smax >= smin && L > 32768) {   // cannot happen after the +-15000-step clamp of STE_multistep
+            atomicExch(err, 2);
+        } else if (smax >= smin && (attr != 2 || g.mask[(size_t)o * 10 + k / 3] != 0.0f)) {
+            const float Q = pr[172 + attr];
+            const float x = pick3(g.values, attr)[(size_t)o * dim + k];
+            const float mean = pr[col], inv = __frcp_rn(fmaxf(pr[kCE + col], 1e-9f));
+            const int s = (int)rintf(__fdiv_rn(x, Q));
+            const uint32_t lo = gauss_cum(s, smin, L, Q, mean, inv), hi = gauss_cum(s + 1, smin, L, Q, mean, inv);
+            if (hi <= lo || s < smin || s > smax) atomicExch(err, 1);   // erf not monotone at rounding level: undecodable
+            else packed = lo | ((hi - lo - 1u) << 16);
+        }
+        iv[(size_t)g.n_rows * col0 + (size_t)row * dim + k] = packed;
+    }
+}
+
+// Encoder pass 2, one thread per chunk of any of the three streams: only the range coder's carried state is sequential.
+// Intervals are read two at a time (every stream has an even number of values per row) one pair ahead of their use.
+__global__ void __launch_bounds__(64)
+gauss_level_encode_kernel(LevelStreams g, const int32_t *__restrict__ minmax, const uint32_t *__restrict__ iv,
+                          uint32_t *__restrict__ out, int32_t *__restrict__ stream_len, int32_t *__restrict__ err)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int attr, cl;
+    if (!locate_chunk(g, c, attr, cl)) return;
+    if (minmax[2 * attr + 1] < minmax[2 * attr] || minmax[2 * attr + 1] - minmax[2 * attr] + 1 > 32768) {
+        stream_len[c] = 0;   // empty stream / alphabet error (reported by pass 1)
         return;
     }
+    const int dim = attr_dim(attr), rows = pick3(g.rows, attr);
+    const int r0 = cl * rows, r1 = min(r0 + rows, g.n_rows);
+    const uint32_t cap = pick3(g.cap, attr);
     Encoder enc;
-    enc.init(out + (size_t)chunk * (cap_bytes / 4), cap_bytes);
-    for (int r = r0; r < r1; ++r) {
-        const int o = g.orig_idx[r];
-        const float *pr = g.params + (size_t)r * kLdG2;
-        const float Q = pr[172 + g.attr];
-        const float *x = values + (size_t)o * g.dim;
-        float xv = x[0], mv = pr[g.col0], sv = pr[kCE + g.col0];
-        for (int k = 0; k < g.dim; ++k) {
-            const float xc = xv, mean = mv, sc = sv;
-            if (k + 1 < g.dim) {
-                xv = x[k + 1]; mv = pr[g.col0 + k + 1]; sv = pr[kCE + g.col0 + k + 1];
-            }
-            if (!coded(g, o, k)) continue;
-            const int s = (int)rintf(__fdiv_rn(xc, Q));
-            const float inv = __frcp_rn(fmaxf(sc, 1e-9f));
-            const uint32_t lo = gauss_cum(s, smin, L, Q, mean, inv), hi = gauss_cum(s + 1, smin, L, Q, mean, inv);
-            if (hi <= lo || s < smin || s > smax) {   // erf not monotone at rounding level: the symbol would be undecodable
-                atomicExch(err, 1);
-                continue;
-            }
-            enc.encode(lo, hi);
-        }
+    enc.init(out + pick3(g.region, attr) + (size_t)cl * (cap / 4), cap);
+    const uint2 *src = reinterpret_cast<const uint2 *>(iv + (size_t)g.n_rows * attr_col0(attr) + (size_t)r0 * dim);
+    const int pairs = (r1 - r0) * dim / 2;
+    uint2 nxt = pairs ? src[0] : make_uint2(kSkip, kSkip);
+    for (int i = 0; i < pairs; ++i) {
+        const uint2 cur = nxt;
+        if (i + 1 < pairs) nxt = src[i + 1];
+        if (cur.x != kSkip) enc.encode(cur.x & 0xffffu, (cur.x & 0xffffu) + (cur.x >> 16) + 1u);
+        if (cur.y != kSkip) enc.encode(cur.y & 0xffffu, (cur.y & 0xffffu) + (cur.y >> 16) + 1u);
     }
-    stream_len[chunk] = (int32_t)enc.finish();
+    stream_len[c] = (int32_t)enc.finish();
     if (enc.overflow) atomicExch(err, 3);
 }
 
-__global__ void __launch_bounds__(64)
-gauss_decode_kernel(GaussStream g, const uint8_t *__restrict__ bytes, const int64_t *__restrict__ stream_off,
-                    const int32_t *__restrict__ stream_len, const int32_t *__restrict__ minmax,
-                    float *__restrict__ values /* [N][dim] out */)
+// One warp per chunk: scratch slot -> its place in the level's packed byte string.
+__global__ void __launch_bounds__(256)
+gauss_level_pack_kernel(LevelStreams g, const uint32_t *__restrict__ scratch, const int32_t *__restrict__ stream_len,
+                        const int64_t *__restrict__ stream_off, uint8_t *__restrict__ packed)
 {
-    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_chunks = (g.n_rows + g.chunk_rows - 1) / g.chunk_rows;
-    if (chunk >= n_chunks) return;
-    const int r0 = chunk * g.chunk_rows, r1 = min(r0 + g.chunk_rows, g.n_rows);
-    const int smin = minmax[0], smax = minmax[1];
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int attr, cl;
+    if (!locate_chunk(g, c, attr, cl)) return;
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(scratch + pick3(g.region, attr)) + (size_t)cl * pick3(g.cap, attr);
+    uint8_t *dst = packed + stream_off[c];
+    const int n = stream_len[c];
+    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+// One thread per chunk of any of the three streams.  Symbol search: the inverse Gaussian CDF of the coder's target gives
+// the symbol to within a step; it is confirmed / corrected by evaluating C next to it -- normally two evaluations --
+// galloping further and bisecting only where the estimate is off (far tails, where C is flat).
+__global__ void __launch_bounds__(64)
+gauss_level_decode_kernel(LevelStreams g, const uint8_t *__restrict__ b0, const uint8_t *__restrict__ b1,
+                          const uint8_t *__restrict__ b2, const int64_t *__restrict__ stream_off,
+                          const int32_t *__restrict__ stream_len, const int32_t *__restrict__ minmax)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int attr, cl;
+    if (!locate_chunk(g, c, attr, cl)) return;
+    const int dim = attr_dim(attr), col0 = attr_col0(attr), rows = pick3(g.rows, attr);
+    const int r0 = cl * rows, r1 = min(r0 + rows, g.n_rows);
+    const int smin = minmax[2 * attr], smax = minmax[2 * attr + 1];
     const int L = smax - smin + 1;
+    const uint32_t M = 65536u - (uint32_t)L;
+    const float inv_M = 1.0f / (float)M;
+    // byte offsets are cumulative over the whole level; each stream's bytes start at its first chunk's offset
+    const uint8_t *bytes = attr == 0 ? b0 : attr == 1 ? b1 : b2;
+    const int64_t first = stream_off[c - cl];
     Decoder dec;
-    dec.init(bytes + stream_off[chunk], (uint32_t)stream_len[chunk]);
+    dec.init(bytes + (stream_off[c] - first), (uint32_t)stream_len[c]);
+    float *values = pick3(g.values, attr);
     for (int r = r0; r < r1; ++r) {
         const int o = g.orig_idx[r];
         const float *pr = g.params + (size_t)r * kLdG2;
-        const float Q = pr[172 + g.attr];
-        float *x = values + (size_t)o * g.dim;
-        for (int k = 0; k < g.dim; ++k) {
-            if (!coded(g, o, k)) {
+        const float Q = pr[172 + attr];
+        const float inv_Q = __frcp_rn(Q);
+        float *x = values + (size_t)o * dim;
+        for (int k = 0; k < dim; ++k) {
+            if (attr == 2 && g.mask[(size_t)o * 10 + k / 3] == 0.0f) {
                 x[k] = 0.0f;
                 continue;
             }
-            const float mean = pr[g.col0 + k];
-            const float inv = __frcp_rn(fmaxf(pr[kCE + g.col0 + k], 1e-9f));
+            const float mean = pr[col0 + k];
+            const float sc = fmaxf(pr[kCE + col0 + k], 1e-9f);
+            const float inv = __frcp_rn(sc);
             const uint32_t v = dec.target();
-            // largest s in [smin, smax] with C(s) <= v; the search starts around the predicted mean
-            int lo_s = smin, hi_s = smax;
-            const int guess = min(max((int)rintf(__fdiv_rn(mean, Q)), smin), smax);
-            if (gauss_cum(guess, smin, L, Q, mean, inv) <= v) lo_s = guess; else hi_s = guess - 1;
-            while (lo_s < hi_s) {
-                const int mid = lo_s + (hi_s - lo_s + 1) / 2;
-                if (gauss_cum(mid, smin, L, Q, mean, inv) <= v) lo_s = mid; else hi_s = mid - 1;
+            // z-score of the lower boundary of symbol s
+            auto zscore = [&](int s) { return (((float)s - 0.5f) * Q - mean) * inv; };
+            int lo_s, hi_s;
+            uint32_t clo = 0, chi = 0;
+            bool have_lo = false, have_hi = false;  // clo == C(lo_s) / chi == C(hi_s + 1) already evaluated
+            // Flat tails first.  Below z = -kFlat the rounded Gaussian term of C is exactly 0 (Phi(-4.7) M < 0.15) and above
+            // +kFlat it is exactly M, so C(s) = s - smin resp. M + s - smin there and the symbol follows from v alone.  A
+            // badly predicted value (most of an untrained model's) costs ~16 bits but no search at all.
+            constexpr float kFlat = 4.7f;
+            const int s_a = smin + (int)v, s_b = s_a - (int)M;
+            const float z_a = zscore(s_a);
+            if (s_a <= smax && z_a < -kFlat) {
+                lo_s = hi_s = s_a; clo = v; have_lo = true;
+                if (z_a + Q * inv < -kFlat) { chi = v + 1u; have_hi = true; }
+            } else if (s_b >= smin && s_b <= smax && zscore(s_b) > kFlat) {
+                lo_s = hi_s = s_b; clo = v; chi = v + 1u; have_lo = have_hi = true;
+            } else {
+                // The symbol lies within (or one step outside) mean +- kFlat sigma: were it deeper in a tail, one of the
+                // two cases above would have recognised it.
+                // invariant: C(lo_s) <= v (or lo_s == smin), C(hi_s + 1) > v (or hi_s == smax)
+                lo_s = (int)fminf(fmaxf(floorf((mean - kFlat * sc) * inv_Q) - 1.0f, (float)smin), (float)smax);
+                hi_s = (int)fminf(fmaxf(ceilf((mean + kFlat * sc) * inv_Q) + 2.0f, (float)lo_s), (float)smax);
+                // C(s) = rn(Phi_s M) + (s - smin) <= v: invert Phi with the ramp term taken at the current estimate of s
+                // (first the mean's symbol), twice -- the ramp moves by 1 / M per symbol, so the second pass is on target
+                int m = min(max(__float2int_rn(mean * inv_Q), lo_s), hi_s);
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    float u = ((float)v - (float)(m - smin) + 0.5f) * inv_M;
+                    u = fminf(fmaxf(u, 1e-7f), 1.0f - 1e-7f);
+                    const float xs = fmaf(normcdfinvf(u), sc, mean);
+                    m = (int)fminf(fmaxf(floorf(fmaf(xs, inv_Q, 0.5f)), (float)lo_s), (float)hi_s);
+                }
+                // confirm: probe the estimate, then gallop away from it until the symbol is bracketed, then bisect
+                bool up = true, bracketed = false;
+                for (int step = 0; lo_s < hi_s && !bracketed; step = 2 * step + 1) {
+                    if (step) m = up ? min(lo_s + step, hi_s) : max(hi_s - step + 1, lo_s + 1);
+                    const uint32_t cw = gauss_cum(m, smin, L, Q, mean, inv);
+                    const bool le = cw <= v;
+                    if (le) { lo_s = m; clo = cw; have_lo = true; } else { hi_s = m - 1; chi = cw; have_hi = true; }
+                    if (step) bracketed = le != up; else up = le;
+                }
+                while (lo_s < hi_s) {
+                    const int mid = lo_s + (hi_s - lo_s + 1) / 2;
+                    const uint32_t cw = gauss_cum(mid, smin, L, Q, mean, inv);
+                    if (cw <= v) { lo_s = mid; clo = cw; have_lo = true; } else { hi_s = mid - 1; chi = cw; have_hi = true; }
+                }
             }
-            const uint32_t clo = gauss_cum(lo_s, smin, L, Q, mean, inv), chi = gauss_cum(lo_s + 1, smin, L, Q, mean, inv);
+            if (!have_lo) clo = gauss_cum(lo_s, smin, L, Q, mean, inv);
+            if (!have_hi || hi_s < lo_s) chi = gauss_cum(lo_s + 1, smin, L, Q, mean, inv);
             dec.consume(clo, chi > clo ? chi : clo + 1);
             x[k] = (float)lo_s * Q;
         }
@@ -335,65 +466,116 @@ extern "C" int64_t cgs_codec_gauss_stream_capacity(int attr, int chunk_rows)
     return ((int64_t)2 * dim * chunk_rows + 16 + 3) / 4 * 4;   // <= 16 bits per symbol + flush
 }
 
-extern "C" int cgs_codec_gauss_minmax(int attr, const int32_t *orig_idx, int n_rows, const float *params,
-                                      const float *mask, const float *values, int32_t *minmax, void *stream)
+// fills the launch descriptor shared by the level-wide entry points; returns 0 or an error code
+static int level_streams(codec::LevelStreams *g, const char *fn, const int32_t *orig_idx, int n_rows, const int *chunk_rows,
+                         const float *params, const float *mask, float *feat_q, float *scaling_q, float *offsets_q)
 {
-    codec::GaussStream g;
-    if (int e = attr_layout(attr, &g.dim, &g.col0)) return e;
+    if (!orig_idx || !params || !mask || !feat_q || !scaling_q || !offsets_q || !chunk_rows) {
+        set_error("%s: null pointer argument", fn);
+        return -2;
+    }
+    g->orig_idx = orig_idx; g->params = params; g->mask = mask; g->n_rows = n_rows;
+    g->values[0] = feat_q; g->values[1] = scaling_q; g->values[2] = offsets_q;
+    int64_t word = 0;
+    for (int a = 0; a < 3; ++a) {
+        if (chunk_rows[a] <= 0) {
+            set_error("%s: invalid chunk size", fn);
+            return -2;
+        }
+        g->rows[a] = chunk_rows[a];
+        g->n_chunks[a] = (n_rows + chunk_rows[a] - 1) / chunk_rows[a];
+        g->cap[a] = (uint32_t)cgs_codec_gauss_stream_capacity(a, chunk_rows[a]);
+        g->region[a] = word;
+        word += (int64_t)g->n_chunks[a] * (g->cap[a] / 4);
+    }
+    return 0;
+}
+
+extern "C" int64_t cgs_codec_gauss_level_chunks(int n_rows, const int *chunk_rows, int32_t *n_chunks)
+{
+    if (!chunk_rows || n_rows < 0) return -1;
+    int64_t words = 0;
+    for (int a = 0; a < 3; ++a) {
+        if (chunk_rows[a] <= 0) return -1;
+        const int n = (n_rows + chunk_rows[a] - 1) / chunk_rows[a];
+        if (n_chunks) n_chunks[a] = n;
+        words += (int64_t)n * (cgs_codec_gauss_stream_capacity(a, chunk_rows[a]) / 4);
+    }
+    return words;
+}
+
+extern "C" int cgs_codec_gauss_level_minmax(const int32_t *orig_idx, int n_rows, const float *params, const float *mask,
+                                            const float *feat_q, const float *scaling_q, const float *offsets_q,
+                                            int32_t *minmax, void *stream)
+{
     CGS_CHECK_PTR(minmax);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaMemsetAsync(minmax, 0x7f, sizeof(int32_t), st);        // +2139062143
-    cudaMemsetAsync(minmax + 1, 0x80, sizeof(int32_t), st);    // -2139062144: an empty stream keeps max < min
+    StageScope sc(ST_CODEC, st, n_rows > 0 ? 2 : 1);
+    codec::minmax_init_kernel<<<1, 32, 0, st>>>(minmax);
     if (n_rows <= 0) return check_launch(__func__);
-    CGS_CHECK_PTR(orig_idx); CGS_CHECK_PTR(params); CGS_CHECK_PTR(values);
-    if (attr == 2) CGS_CHECK_PTR(mask);
-    g.orig_idx = orig_idx; g.params = params; g.mask = mask; g.n_rows = n_rows; g.chunk_rows = 1; g.attr = attr;
+    codec::LevelStreams g;
+    const int one[3] = {1, 1, 1};
+    if (int e = level_streams(&g, __func__, orig_idx, n_rows, one, params, mask, const_cast<float *>(feat_q),
+                              const_cast<float *>(scaling_q), const_cast<float *>(offsets_q)))
+        return e;
+    const int rows_per_block = 8 * codec::kRowsPerWarp;
+    codec::gauss_level_minmax_kernel<<<(n_rows + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(g, minmax);
+    return check_launch(__func__);
+}
+
+extern "C" int cgs_codec_gauss_level_encode(const int32_t *orig_idx, int n_rows, const int *chunk_rows, const float *params,
+                                            const float *mask, const float *feat_q, const float *scaling_q,
+                                            const float *offsets_q, const int32_t *minmax, uint32_t *intervals,
+                                            uint32_t *scratch, int32_t *stream_len, int32_t *err, void *stream)
+{
+    if (n_rows <= 0) return 0;
+    CGS_CHECK_PTR(minmax); CGS_CHECK_PTR(intervals); CGS_CHECK_PTR(scratch); CGS_CHECK_PTR(stream_len); CGS_CHECK_PTR(err);
+    codec::LevelStreams g;
+    if (int e = level_streams(&g, __func__, orig_idx, n_rows, chunk_rows, params, mask, const_cast<float *>(feat_q),
+                              const_cast<float *>(scaling_q), const_cast<float *>(offsets_q)))
+        return e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StageScope sc(ST_CODEC, st, 2);
+    codec::gauss_level_intervals_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(g, minmax, intervals, err);
+    const int chunks = g.n_chunks[0] + g.n_chunks[1] + g.n_chunks[2];
+    codec::gauss_level_encode_kernel<<<(chunks + 63) / 64, 64, 0, st>>>(g, minmax, intervals, scratch, stream_len, err);
+    return check_launch(__func__);
+}
+
+extern "C" int cgs_codec_gauss_level_pack(int n_rows, const int *chunk_rows, const uint32_t *scratch,
+                                          const int32_t *stream_len, const int64_t *stream_off, uint8_t *packed, void *stream)
+{
+    if (n_rows <= 0) return 0;
+    CGS_CHECK_PTR(scratch); CGS_CHECK_PTR(stream_len); CGS_CHECK_PTR(stream_off); CGS_CHECK_PTR(packed);
+    codec::LevelStreams g;
+    float dummy;   // the descriptor's tensor pointers are not used by the pack kernel
+    if (int e = level_streams(&g, __func__, reinterpret_cast<const int32_t *>(&dummy), n_rows, chunk_rows, &dummy, &dummy,
+                              &dummy, &dummy, &dummy))
+        return e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     StageScope sc(ST_CODEC, st, 1);
-    codec::gauss_minmax_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(g, values, minmax);
+    const int64_t chunks = (int64_t)g.n_chunks[0] + g.n_chunks[1] + g.n_chunks[2];
+    codec::gauss_level_pack_kernel<<<(unsigned)((chunks * 32 + 255) / 256), 256, 0, st>>>(g, scratch, stream_len, stream_off,
+                                                                                         packed);
     return check_launch(__func__);
 }
 
-extern "C" int cgs_codec_gauss_encode(int attr, const int32_t *orig_idx, int n_rows, int chunk_rows, const float *params,
-                                      const float *mask, const float *values, const int32_t *minmax, uint32_t *scratch,
-                                      int64_t cap_bytes, int32_t *stream_len, int32_t *err, void *stream)
+extern "C" int cgs_codec_gauss_level_decode(const int32_t *orig_idx, int n_rows, const int *chunk_rows, const float *params,
+                                            const float *mask, const uint8_t *feat_bytes, const uint8_t *scaling_bytes,
+                                            const uint8_t *offsets_bytes, const int64_t *stream_off,
+                                            const int32_t *stream_len, const int32_t *minmax, float *feat_q,
+                                            float *scaling_q, float *offsets_q, void *stream)
 {
     if (n_rows <= 0) return 0;
-    codec::GaussStream g;
-    if (int e = attr_layout(attr, &g.dim, &g.col0)) return e;
-    CGS_CHECK_PTR(orig_idx); CGS_CHECK_PTR(params); CGS_CHECK_PTR(values); CGS_CHECK_PTR(scratch);
-    CGS_CHECK_PTR(stream_len); CGS_CHECK_PTR(minmax); CGS_CHECK_PTR(err);
-    if (attr == 2) CGS_CHECK_PTR(mask);
-    if (chunk_rows <= 0 || cap_bytes < cgs_codec_gauss_stream_capacity(attr, chunk_rows) || (cap_bytes & 3)) {
-        set_error("%s: invalid chunk size / stream capacity", __func__);
-        return -2;
-    }
-    g.orig_idx = orig_idx; g.params = params; g.mask = mask; g.n_rows = n_rows; g.chunk_rows = chunk_rows; g.attr = attr;
-    const int n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
-    StageScope sc(ST_CODEC, static_cast<cudaStream_t>(stream), 1);
-    codec::gauss_encode_kernel<<<(n_chunks + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-        g, values, minmax, scratch, (uint32_t)cap_bytes, stream_len, err);
-    return check_launch(__func__);
-}
-
-extern "C" int cgs_codec_gauss_decode(int attr, const int32_t *orig_idx, int n_rows, int chunk_rows, const float *params,
-                                      const float *mask, const uint8_t *bytes, const int64_t *stream_off,
-                                      const int32_t *stream_len, const int32_t *minmax, float *values, void *stream)
-{
-    if (n_rows <= 0) return 0;
-    codec::GaussStream g;
-    if (int e = attr_layout(attr, &g.dim, &g.col0)) return e;
-    CGS_CHECK_PTR(orig_idx); CGS_CHECK_PTR(params); CGS_CHECK_PTR(bytes); CGS_CHECK_PTR(stream_off);
-    CGS_CHECK_PTR(stream_len); CGS_CHECK_PTR(minmax); CGS_CHECK_PTR(values);
-    if (attr == 2) CGS_CHECK_PTR(mask);
-    if (chunk_rows <= 0) {
-        set_error("%s: invalid chunk size", __func__);
-        return -2;
-    }
-    g.orig_idx = orig_idx; g.params = params; g.mask = mask; g.n_rows = n_rows; g.chunk_rows = chunk_rows; g.attr = attr;
-    const int n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
-    StageScope sc(ST_CODEC, static_cast<cudaStream_t>(stream), 1);
-    codec::gauss_decode_kernel<<<(n_chunks + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-        g, bytes, stream_off, stream_len, minmax, values);
+    CGS_CHECK_PTR(feat_bytes); CGS_CHECK_PTR(scaling_bytes); CGS_CHECK_PTR(offsets_bytes); CGS_CHECK_PTR(stream_off);
+    CGS_CHECK_PTR(stream_len); CGS_CHECK_PTR(minmax);
+    codec::LevelStreams g;
+    if (int e = level_streams(&g, __func__, orig_idx, n_rows, chunk_rows, params, mask, feat_q, scaling_q, offsets_q)) return e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StageScope sc(ST_CODEC, st, 1);
+    const int chunks = g.n_chunks[0] + g.n_chunks[1] + g.n_chunks[2];
+    codec::gauss_level_decode_kernel<<<(chunks + 63) / 64, 64, 0, st>>>(g, feat_bytes, scaling_bytes, offsets_bytes, stream_off,
+                                                                       stream_len, minmax);
     return check_launch(__func__);
 }
 

@@ -489,29 +489,43 @@ CGS_API int cgs_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in,
 /* ------------------------------------------------------------------ bitstream codec
  * GPU replacement of `encoder_gaussian` / `decoder_gaussian` + torchac (utils/encodings.py:83-144; chunk loops
  * scene/gaussian_model.py:1192-1232,1422-1477), of `latent_codec.compress/decompress` (:1088,1331) and of the
- * binary-mask `encoder` / `decoder` (utils/encodings.py:147-183).  One GPU thread codes one chunk of one
- * stream with a byte-wise 32-bit range coder; Gaussian CDFs are evaluated in closed form from params
+ * binary-mask `encoder` / `decoder` (utils/encodings.py:147-183).  One GPU thread carries the (low, range) state of
+ * one chunk of one stream through a byte-wise 32-bit range coder; Gaussian CDFs are evaluated in closed form from params
  * (cgs_context_level_umma_forward_ex), never tabulated.  Container format: this library's own
  * (csrc/entropy_codec.cu), torchac's is not pinnable.
  *
- * Gaussian streams, per level and attribute (attr 0 feat[.,50] / 1 scaling[.,6] / 2 offsets[.,30]; offsets whose
- * mask[anchor][k/3] is 0 are not coded and decode to 0):
- *   symbol = rint(value / Q); alphabet = minmax[0..1] (device int32 x2) = min / max symbol of the whole stream,
- *   computed by cgs_codec_gauss_minmax (parallel pre-pass) and stored with the stream;
- *   chunk c = level rows [c*chunk_rows, (c+1)*chunk_rows) is coded by ONE thread: encode writes it at
- *   scratch + c*cap_bytes (cap_bytes >= cgs_codec_gauss_stream_capacity) and its byte count to stream_len[c];
- *   *err != 0 reports an uncodable symbol (1), an alphabet over 32768 (2) or a capacity overflow (3).
- *   decode reads chunk c at bytes + stream_off[c] and writes value = symbol * Q at values[orig_idx[row]][k] --
+ * Gaussian streams, per level: attr 0 feat[.,50] / 1 scaling[.,6] / 2 offsets[.,30]; offsets whose mask[anchor][k/3]
+ * is 0 are not coded and decode to 0.  The three streams of a level are coded by the same launches; chunk ids run over
+ * them back to back (n_chunks[a] = ceil(n_rows / chunk_rows[a]) chunks of stream a; chunk c of stream a = level rows
+ * [c*chunk_rows[a], (c+1)*chunk_rows[a])).  chunk_rows and n_chunks are HOST arrays of three ints.
+ *   symbol = rint(value / Q); alphabet of stream a = minmax[2a], minmax[2a+1] (device int32 x6) = min / max symbol of the
+ *   whole stream, computed by cgs_codec_gauss_level_minmax (parallel pre-pass) and stored with the stream;
+ *   cgs_codec_gauss_level_chunks: chunk counts of the three streams; returns the 32-bit words of `scratch` an encode
+ *   needs (chunk c of stream a sits at a fixed stride of cgs_codec_gauss_stream_capacity(a, chunk_rows[a]) bytes);
+ *   cgs_codec_gauss_level_encode: pass 1 writes the 16-bit coding interval of each of the n_rows*86 values to `intervals`
+ *   (uint32 each), pass 2 codes every chunk with ONE thread into its scratch slot and writes its byte count to
+ *   stream_len[chunk id]; *err != 0 reports an uncodable symbol (1), an alphabet over 32768 (2), a capacity overflow (3);
+ *   cgs_codec_gauss_level_pack: scratch slots -> packed + stream_off[chunk id] (stream_off = exclusive prefix sum of
+ *   stream_len over the level, so the three streams are three consecutive slices of `packed`);
+ *   cgs_codec_gauss_level_decode: reads chunk c of stream a at {feat,scaling,offsets}_bytes + stream_off[c] -
+ *   stream_off[first chunk of a] and writes value = symbol * Q at {feat,scaling,offsets}_q[orig_idx[row]][k] --
  *   bit-identical to the encoder's input. */
 CGS_API int64_t cgs_codec_gauss_stream_capacity(int attr, int chunk_rows);
-CGS_API int cgs_codec_gauss_minmax(int attr, const int32_t *orig_idx, int n_rows, const float *params, const float *mask,
-                                   const float *values, int32_t *minmax, void *stream);
-CGS_API int cgs_codec_gauss_encode(int attr, const int32_t *orig_idx, int n_rows, int chunk_rows, const float *params,
-                                   const float *mask, const float *values, const int32_t *minmax, uint32_t *scratch,
-                                   int64_t cap_bytes, int32_t *stream_len, int32_t *err, void *stream);
-CGS_API int cgs_codec_gauss_decode(int attr, const int32_t *orig_idx, int n_rows, int chunk_rows, const float *params,
-                                   const float *mask, const uint8_t *bytes, const int64_t *stream_off,
-                                   const int32_t *stream_len, const int32_t *minmax, float *values, void *stream);
+CGS_API int64_t cgs_codec_gauss_level_chunks(int n_rows, const int *chunk_rows, int32_t *n_chunks);
+CGS_API int cgs_codec_gauss_level_minmax(const int32_t *orig_idx, int n_rows, const float *params, const float *mask,
+                                         const float *feat_q, const float *scaling_q, const float *offsets_q,
+                                         int32_t *minmax, void *stream);
+CGS_API int cgs_codec_gauss_level_encode(const int32_t *orig_idx, int n_rows, const int *chunk_rows, const float *params,
+                                         const float *mask, const float *feat_q, const float *scaling_q,
+                                         const float *offsets_q, const int32_t *minmax, uint32_t *intervals,
+                                         uint32_t *scratch, int32_t *stream_len, int32_t *err, void *stream);
+CGS_API int cgs_codec_gauss_level_pack(int n_rows, const int *chunk_rows, const uint32_t *scratch, const int32_t *stream_len,
+                                       const int64_t *stream_off, uint8_t *packed, void *stream);
+CGS_API int cgs_codec_gauss_level_decode(const int32_t *orig_idx, int n_rows, const int *chunk_rows, const float *params,
+                                         const float *mask, const uint8_t *feat_bytes, const uint8_t *scaling_bytes,
+                                         const uint8_t *offsets_bytes, const int64_t *stream_off, const int32_t *stream_len,
+                                         const int32_t *minmax, float *feat_q, float *scaling_q, float *offsets_q,
+                                         void *stream);
 /* Static-table streams: symbols[n_rows][C] int16 (index into the table of channel c, tables[c % T][0..table_ld),
  * cumulative 16-bit frequencies, tables[.][len] = 65536); chunking and outputs as above. */
 CGS_API int cgs_codec_table_encode(const int16_t *symbols, int n_rows, int C, int chunk_rows, const uint32_t *tables,

@@ -24,6 +24,9 @@ def summarize(prof, title):
     print(title, "span us", t1 - t0, "busy us", sum(v[0] for v in agg.values()))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]:
         print(f"   {v[0]:10.1f} us  x{v[1]:4d}  {k}")
+    for e in sorted(evs, key=lambda e: e.time_range.start):
+        if "cgs::" in e.name:
+            print(f"      {e.time_range.start - t0:9.1f} +{e.time_range.end - e.time_range.start:8.1f}  {e.name[:60]}")
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     enc = codec.encode_model(pc)
     torch.cuda.synchronize()
@@ -35,3 +38,5 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     codec.decode_model(d, enc.meta, enc.anchor_q, enc.mask_bytes, enc.mask_lens, enc.hyper_bytes, enc.hyper_lens, enc.levels)
     torch.cuda.synchronize()
 summarize(prof, "decode")
+for lv in enc.levels:
+    print("level", lv.level, "rows", lv.n, {k: (st.minmax.tolist(), st.bytes.numel()) for k, st in lv.streams.items()})

@@ -77,8 +77,7 @@ def test_table_streams_are_byte_identical_to_the_cpu_range_coder():
     pc = _model(700)
     enc = codec.encode_model(pc, chunk_rows=32)
     q = enc.quantised
-    p1 = enc.meta["prob_masks"]
-    tb = codec.frequency_tables(torch.tensor([[max(1.0 - p1, 1e-9), max(p1, 1e-9)]]))[0].tolist()
+    tb = codec.mask_table(enc.meta["prob_masks"])[0].tolist()
     rows = 32 * codec.TABLE_CHUNK_MULT
     data = enc.mask_bytes.cpu().numpy().tobytes()
     lens = enc.mask_lens.tolist()
