@@ -95,7 +95,7 @@ SIGNATURES = {
                                                _PTR, _PTR, _PTR, _PTR, _PTR]),
     "cgs_context_level_umma_forward_ex": (c_int, [c_int, _PTR, _PTR, _PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
                                                   _PTR, _PTR, ctypes.c_float, ctypes.c_float, ctypes.c_float, _PTR, _PTR,
-                                                  _PTR, _PTR, _PTR, _PTR, _PTR, c_int, _PTR]),
+                                                  _PTR, _PTR, _PTR, _PTR, _PTR, c_int, _PTR, _PTR]),
     "cgs_context_level_umma_forward_train": (c_int, [c_int, _PTR, _PTR, _PTR, _PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,
                                                      _PTR, _PTR, ctypes.c_float, ctypes.c_float, ctypes.c_float, _PTR, _PTR,
                                                      _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR]),
@@ -103,6 +103,7 @@ SIGNATURES = {
     "cgs_context_level_backward_umma": (c_int, [c_int, _PTR, _PTR, _PTR, _PTR, c_int] + [_PTR] * 8 + [ctypes.c_float] * 3 +
                                         [_PTR, ctypes.c_float] + [_PTR] * 13 + [c_int, _PTR]),
     "cgs_codec_gauss_stream_capacity": (c_int64, [c_int, c_int]),
+    "cgs_codec_phi_table": (c_int, [_PTR, c_int, _PTR, _PTR]),
     "cgs_codec_gauss_level_chunks": (c_int64, [c_int, _PTR, _PTR]),
     "cgs_codec_gauss_level_minmax": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR]),
     "cgs_codec_gauss_level_encode": (c_int, [_PTR, c_int, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR,

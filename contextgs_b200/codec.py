@@ -66,6 +66,15 @@ def mask_table(p1):
     return frequency_tables(torch.stack([(1.0 - p).clamp_min(1e-9), p.clamp_min(1e-9)]).view(1, 2))
 
 
+def phi_table():
+    """(T float32 [4097], z0, inv_h): the tabulated normal CDF of the Gaussian streams (include/contextgs_b200.h)."""
+    T = np.empty(4097, dtype=np.float32)
+    z0, inv_h = ctypes.c_float(), ctypes.c_float()
+    _lib.check(_lib.lib().cgs_codec_phi_table(T.ctypes.data_as(ctypes.c_void_p), T.size, ctypes.byref(z0), ctypes.byref(inv_h)),
+               "cgs_codec_phi_table")
+    return T, float(z0.value), float(inv_h.value)
+
+
 def _offsets(lens):
     """exclusive prefix sum of the chunk lengths, with the total appended: int64 [n + 1]"""
     off = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=lens.device)
@@ -160,24 +169,28 @@ def _plan_for(pc, anchor, key, rank, world):
 
 
 def _level_params(pc, lv, anchor, hyper_q, feat, scaling, offsets, masks, feat_q, scaling_q, offsets_q, sums, err, means,
-                  predict_only):
-    """(mean, scale, Q) of every coded value of one level (and, when encoding, the level's quantised values)."""
+                  predict_only, minmax=None, choose=None):
+    """(mean, scale, Q) of every coded value of one level (and, when encoding, the level's quantised values and, in
+    `minmax`, the alphabets of its three streams).  `choose` (uint8 per anchor): rows whose bits are estimated (None: all)."""
     L = _lib.lib()
     packed, in_dim = pack_grid_weights_umma(pc, lv.level)
     params = torch.empty((lv.n, PARAM_LD), dtype=torch.float32, device=anchor.device)
     p = _lib.ptr
     _lib.check(L.cgs_context_level_umma_forward_ex(
         in_dim, p(packed), p(lv.orig), p(lv.ctx_src), p(lv.level_anchor), lv.n, p(anchor), p(hyper_q), p(feat), p(scaling),
-        p(offsets), p(masks), None, None, means[0], means[1], means[2], p(feat_q), p(scaling_q), p(offsets_q), None,
-        p(sums), p(err), p(params), int(predict_only), _lib.stream_ptr()), "cgs_context_level_umma_forward_ex")
+        p(offsets), p(masks), p(choose), None, means[0], means[1], means[2], p(feat_q), p(scaling_q), p(offsets_q), None,
+        p(sums), p(err), p(params), int(predict_only), p(minmax), _lib.stream_ptr()), "cgs_context_level_umma_forward_ex")
     return params
 
 
 @torch.no_grad()
-def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1):
+def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1, estimate_bits=True):
     """Encode every valid anchor of `pc`.  Returns a SimpleNamespace with the byte streams (CUDA uint8 tensors),
     the metadata the decoder needs, the quantised tensors that were coded (for parity checks) and the
     estimated bits of the same pass.
+    estimate_bits=False skips the entropy estimate (`estimated_bits` is then None): the reference's conduct_encoding only
+    reports the sizes of the streams it wrote, and the estimate (two erf and a log per value) costs about as much as
+    predicting the level.
     world > 1 (BASELINE configs[3]: anchors sharded over the GPUs): the level plan is split by
     dependency root (distributed.shard_level_plan), so rank `rank` predicts and codes only its own rows of every
     level, with no exchange; the small anchor / mask / hyper streams are produced identically on every rank (they
@@ -225,24 +238,23 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1):
     terr = torch.zeros(1, dtype=torch.int32, device=dev)
     means = global_means(pc)
     rows3 = (ctypes.c_int * 3)(*[chunk_rows * m for m in ATTR_CHUNK_MULT])
+    no_rows = None if estimate_bits else torch.zeros(N, dtype=torch.uint8, device=dev)
     levels, pending = [], []
     for li, lv in enumerate(plan.levels):
         entry = SimpleNamespace(level=lv.level, n=lv.n, streams={})
         levels.append(entry)
         if lv.n == 0:
             continue
+        minmax = torch.empty(6, dtype=torch.int32, device=dev)
         params = _level_params(pc, lv, anchor, hyper_q, feat, scaling, offsets, masks, feat_q, scaling_q, offsets_q,
-                               sums[4 * li:4 * li + 4], terr, means, False)
+                               sums[4 * li:4 * li + 4], terr, means, False, minmax, no_rows)
         counts = (ctypes.c_int32 * 3)()
         words = int(L.cgs_codec_gauss_level_chunks(lv.n, rows3, counts))
         counts = list(counts)
-        minmax = torch.empty(6, dtype=torch.int32, device=dev)
         intervals = torch.empty(lv.n * 86, dtype=torch.int32, device=dev)
         scratch = torch.empty(words, dtype=torch.int32, device=dev)
         lens = torch.zeros(sum(counts), dtype=torch.int32, device=dev)
         p = _lib.ptr
-        _lib.check(L.cgs_codec_gauss_level_minmax(p(lv.orig), lv.n, p(params), p(masks), p(feat_q), p(scaling_q), p(offsets_q),
-                                                  p(minmax), _lib.stream_ptr()), "cgs_codec_gauss_level_minmax")
         _lib.check(L.cgs_codec_gauss_level_encode(p(lv.orig), lv.n, rows3, p(params), p(masks), p(feat_q), p(scaling_q),
                                                   p(offsets_q), p(minmax), p(intervals), p(scratch), p(lens), p(err),
                                                   _lib.stream_ptr()), "cgs_codec_gauss_level_encode")
@@ -279,7 +291,7 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1):
                 x_bound_max=pc.x_bound_max.detach().cpu(), prob_masks=p1, hyper_min=hmin, hyper_max=hmax,
                 means=means, N_levels=n_levels_full, world=world)
     est = dict(hyper=None, feat=sum(s[4 * i] for i in range(3)), scaling=sum(s[4 * i + 1] for i in range(3)),
-               offsets=sum(s[4 * i + 2] for i in range(3)))
+               offsets=sum(s[4 * i + 2] for i in range(3))) if estimate_bits else None
     return SimpleNamespace(meta=meta, anchor_q=anchor_q.to(torch.int16), mask_bytes=mask_bytes, mask_lens=mask_pending[2],
                            hyper_bytes=hyper_bytes, hyper_lens=hyper_pending[2], levels=levels, valid=sel,
                            quantised=dict(anchor=anchor, hyper=hyper_q, feat=feat_q, scaling=scaling_q, offsets=offsets_q,

@@ -41,6 +41,7 @@ struct Smem {
     float w[Layout<K1>::kPacked];
     uint32_t tmem;
     int timeout;
+    int sym_minmax[6];            // min / max coded symbol of the feat, scaling, offsets streams seen by this CTA
     alignas(8) uint64_t bar[3];   // layer-1 done | layer-2 done | layer-2 accumulator released by BACK
 };
 
@@ -64,6 +65,7 @@ struct Args {
     double *bit_sums;
     int32_t *err_flag;
     float *params_out;   // [n_rows][176]: mean[86] | scale[86] | Q_feat Q_scaling Q_offsets | 0 (codec / backward; optional)
+    int32_t *symbol_minmax;   // optional [6]: min / max coded symbol of the feat, scaling, offsets streams of this level
     int predict_only;    // 1: only params_out is produced (decoder: the attributes are not known yet)
     float *save_h;       // [n_rows][112] hidden activations relu(D1 + b1) (training: consumed by the tcgen05 backward; optional)
     uint32_t *save_hmask;   // [n_rows][4] their sign bits: bit (8c + j) of word pair `half` <-> hidden unit 56 half + 8c + j
@@ -148,7 +150,7 @@ __device__ __forceinline__ ChunkDesc chunk_desc_q(int c, int q)
     return d;
 }
 
-template <int K1>
+template <int K1, bool kSym>   // kSym: also reduce the min / max coded symbol of each stream (bitstream encoder)
 __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
 {
     using LY = Layout<K1>;
@@ -176,6 +178,8 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
         umma::mbar_init(&S.bar[2], 1);
         umma::fence_mbar_init();
         S.timeout = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) S.sym_minmax[i] = (i & 1) ? -0x7fffffff : 0x7fffffff;
     }
     {
         const float4 *s4 = reinterpret_cast<const float4 *>(A.packed_w);
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             const bool chosen = !pred && o >= 0 && (A.choose ? A.choose[o] != 0 : true);
             // offset masks of the row as bits (values are exactly 0 / 1: utils/entropy_models / gaussian_model.py:1670)
             uint32_t mkbits = 0x3ffu;
-            if (o >= 0 && half >= 2 && chosen) {
+            if (o >= 0 && half >= 2 && (chosen || (kSym && !pred))) {   // kSym: the alphabets only cover coded offsets
                 mkbits = 0;
 #pragma unroll
                 for (int k = 0; k < 10; ++k) mkbits |= __ldg(A.mask + o * 10 + k) != 0.f ? (1u << k) : 0u;
@@ -309,8 +313,13 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             auto fetch_x = [&](int c, float (&x8)[8]) {
                 const ChunkDesc cd = chunk_desc_q(c, half);
                 const float *src = (cd.grp == 0 ? A.feat : (cd.grp == 1 ? A.scaling : A.offsets)) + (size_t)(o < 0 ? 0 : o) * cd.dim + cd.k0;
+                // every group starts on an even index of an 8-byte aligned row and holds an even number of values
 #pragma unroll
-                for (int j = 0; j < 8; ++j) x8[j] = (!pred && o >= 0 && j < cd.cnt) ? __ldg(src + j) : 0.f;
+                for (int j = 0; j < 8; j += 2) {
+                    const float2 v = (!pred && o >= 0 && j < cd.cnt) ? __ldg(reinterpret_cast<const float2 *>(src + j))
+                                                                     : make_float2(0.f, 0.f);
+                    x8[j] = v.x; x8[j + 1] = v.y;
+                }
             };
             float xn[8];
             fetch_x(0, xn);
@@ -342,11 +351,13 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                 umma::tmem_ld8(tl + kColD2 + cd.sg_col, vs);
                 if (c + 1 < 3) fetch_x(c + 1, xn);
                 umma::tmem_wait_ld();
-                if (o < 0) continue;
+                // alphabet bounds of the level's three streams (bitstream codec): the symbols exist here anyway
+                float sym_lo = 3.0e38f, sym_hi = -3.0e38f;
+                if (o >= 0) {
                 const float Q = cd.grp == 0 ? Qf : (cd.grp == 1 ? Qs : Qo);
                 const float x_mean = cd.grp == 0 ? A.feat_mean : (cd.grp == 1 ? A.scaling_mean : A.offset_mean);
                 float *dst = (cd.grp == 0 ? A.feat_q : (cd.grp == 1 ? A.scaling_q : A.offsets_q)) + o * cd.dim + cd.k0;
-                float acc = 0.f;
+                float acc = 0.f, xq_even = 0.f;
                 if (prow && (chosen || !A.save_h)) {   // training: the backward reads (mean, scale) of the chosen rows only
                     // (mean, scale) of the group as 8-byte stores (every group starts on an even index and holds an even
                     // number of values; scalar stores cost one 32-byte sector transaction per value and doubled the
@@ -370,8 +381,14 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                         const float scale = __uint_as_float(vs[j]) + S.w[LY::kOffB2 + cd.sg_col + j];
                         if (pred) continue;
                         const float x = xc[j];
-                        const float xq = nz ? x + nz[cd.j0 + j] * Q : ste_round(x, Q);
-                        dst[j] = xq;
+                        float sym;
+                        const float xq = nz ? x + nz[cd.j0 + j] * Q : ste_round_sym(x, Q, sym);
+                        if (j & 1) *reinterpret_cast<float2 *>(dst + j - 1) = make_float2(xq_even, xq);   // 8-byte stores
+                        else xq_even = xq;
+                        if (kSym && !nz && (cd.grp != 2 || ((mkbits >> ((cd.k0 + j) / 3)) & 1u))) {
+                            sym_lo = fminf(sym_lo, sym);
+                            sym_hi = fmaxf(sym_hi, sym);
+                        }
                         float bits = 0.f;
                         if (chosen) {
                             bits = gaussian_bits_one(xq, mean, scale, Q, x_mean);
@@ -384,6 +401,15 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                 if (cd.grp == 0) sum_f += acc;
                 else if (cd.grp == 1) sum_s += acc;
                 else sum_o += acc;
+                }
+                if (kSym) {   // whole warp, same group: one shared atomic pair per warp and chunk
+                    const int lo = __reduce_min_sync(0xffffffffu, (int)fminf(sym_lo, 2.0e9f));
+                    const int hi = __reduce_max_sync(0xffffffffu, (int)fmaxf(sym_hi, -2.0e9f));
+                    if (lane == 0 && lo <= hi) {
+                        atomicMin(&S.sym_minmax[2 * cd.grp], lo);
+                        atomicMax(&S.sym_minmax[2 * cd.grp + 1], hi);
+                    }
+                }
             }
             tot_f += (double)sum_f; tot_s += (double)sum_s; tot_o += (double)sum_o;
             // all TMEM reads of this tile are complete: FRONT may issue the next tile's layer-2 MMAs
@@ -412,8 +438,17 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
         for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
         if (v != 0.0) atomicAdd(A.bit_sums + tid, v);
     }
+    if (kSym && tid < 6 && S.sym_minmax[tid & ~1] <= S.sym_minmax[tid | 1]) {   // published by the barrier above
+        if (tid & 1) atomicMax(A.symbol_minmax + tid, S.sym_minmax[tid]);
+        else atomicMin(A.symbol_minmax + tid, S.sym_minmax[tid]);
+    }
     if (tid == 0 && S.timeout) atomicExch(A.err_flag, 1);
     if (warp == 0) umma::tmem_dealloc(tbase, kTmemCols);
+}
+
+__global__ void symbol_minmax_init_kernel(int32_t *minmax)
+{
+    if (threadIdx.x < 6) minmax[threadIdx.x] = (threadIdx.x & 1) ? -2139062144 : 2139062143;   // empty stream: max < min
 }
 
 template <int K1>
@@ -425,12 +460,23 @@ static int launch(const Args &a, cudaStream_t st)
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(context_level_umma_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
+        cudaFuncSetAttribute(context_level_umma_kernel<K1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
+        cudaFuncSetAttribute(context_level_umma_kernel<K1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
         if (sm_count <= 0) sm_count = kNumSMs;
     }
+    // the per-anchor attributes are read and written two floats at a time
+    for (const void *q : {(const void *)a.feat, (const void *)a.scaling, (const void *)a.offsets, (const void *)a.feat_q,
+                          (const void *)a.scaling_q, (const void *)a.offsets_q}) {
+        if (reinterpret_cast<uintptr_t>(q) & 7u) {
+            set_error("cgs_context_level_umma_forward: the attribute arrays must be 8-byte aligned");
+            return -2;
+        }
+    }
     const int tiles = (a.n_rows + kRows - 1) / kRows;
+    const int grid = tiles < sm_count ? tiles : sm_count;
     StageScope sc(ST_CTX_LEVEL, st, 1);
-    context_level_umma_kernel<K1><<<tiles < sm_count ? tiles : sm_count, kThreads, sizeof(SM), st>>>(a);
+    if (a.symbol_minmax) context_level_umma_kernel<K1, true><<<grid, kThreads, sizeof(SM), st>>>(a);
+    else context_level_umma_kernel<K1, false><<<grid, kThreads, sizeof(SM), st>>>(a);
     return check_launch("cgs_context_level_umma_forward");
 }
 }  // namespace cmu
@@ -456,7 +502,7 @@ extern "C" int cgs_context_level_umma_forward(int in_dim, const float *packed_w,
 {
     return cgs_context_level_umma_forward_ex(in_dim, packed_w, orig_idx, ctx_src, level_anchor, n_rows, anchor, hyper_q, feat,
                                              scaling, offsets, mask, choose, noise, feat_mean, scaling_mean, offset_mean,
-                                             feat_q, scaling_q, offsets_q, bits_out, bit_sums, err_flag, nullptr, 0, stream);
+                                             feat_q, scaling_q, offsets_q, bits_out, bit_sums, err_flag, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int cgs_context_level_umma_forward_train(int in_dim, const float *packed_w, const int32_t *orig_idx,
@@ -474,7 +520,7 @@ extern "C" int cgs_context_level_umma_forward_train(int in_dim, const float *pac
     CGS_CHECK_PTR(feat); CGS_CHECK_PTR(scaling); CGS_CHECK_PTR(offsets); CGS_CHECK_PTR(mask); CGS_CHECK_PTR(offsets_q);
     CGS_CHECK_PTR(params_out); CGS_CHECK_PTR(save_h); CGS_CHECK_PTR(save_hmask);
     cmu::Args a;
-    a.params_out = params_out; a.predict_only = 0; a.save_h = save_h; a.save_hmask = save_hmask;
+    a.params_out = params_out; a.predict_only = 0; a.save_h = save_h; a.save_hmask = save_hmask; a.symbol_minmax = nullptr;
     a.packed_w = packed_w; a.orig_idx = orig_idx; a.ctx_src = ctx_src; a.level_anchor = level_anchor; a.n_rows = n_rows;
     a.anchor = anchor; a.hyper_q = hyper_q; a.feat = feat; a.scaling = scaling; a.offsets = offsets; a.mask = mask;
     a.choose = choose; a.noise = noise; a.feat_mean = feat_mean; a.scaling_mean = scaling_mean;
@@ -500,9 +546,10 @@ extern "C" int cgs_context_level_umma_forward_ex(int in_dim, const float *packed
                                                  const uint8_t *choose, const float *noise, float feat_mean,
                                                  float scaling_mean, float offset_mean, float *feat_q, float *scaling_q,
                                                  float *offsets_q, float *bits_out, double *bit_sums, int32_t *err_flag,
-                                                 float *params_out, int predict_only, void *stream)
+                                                 float *params_out, int predict_only, int32_t *symbol_minmax, void *stream)
 {
-    if (n_rows <= 0) return 0;
+    if (symbol_minmax) cmu::symbol_minmax_init_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(symbol_minmax);
+    if (n_rows <= 0) return symbol_minmax ? check_launch(__func__) : 0;
     CGS_CHECK_PTR(packed_w); CGS_CHECK_PTR(orig_idx); CGS_CHECK_PTR(anchor); CGS_CHECK_PTR(hyper_q);
     CGS_CHECK_PTR(feat_q); CGS_CHECK_PTR(scaling_q); CGS_CHECK_PTR(bit_sums); CGS_CHECK_PTR(err_flag);
     if (predict_only) {
@@ -512,6 +559,7 @@ extern "C" int cgs_context_level_umma_forward_ex(int in_dim, const float *packed
     }
     cmu::Args a;
     a.params_out = params_out; a.predict_only = predict_only; a.save_h = nullptr; a.save_hmask = nullptr;
+    a.symbol_minmax = predict_only ? nullptr : symbol_minmax;
     a.packed_w = packed_w; a.orig_idx = orig_idx; a.ctx_src = ctx_src; a.level_anchor = level_anchor; a.n_rows = n_rows;
     a.anchor = anchor; a.hyper_q = hyper_q; a.feat = feat; a.scaling = scaling; a.offsets = offsets; a.mask = mask;
     a.choose = choose; a.noise = noise; a.feat_mean = feat_mean; a.scaling_mean = scaling_mean;

@@ -15,9 +15,12 @@
 // for bit, and the stream length matches the estimated bits.
 //
 // Cumulative frequency of symbol index i in [0, L] (alphabet = [smin, smax] of the whole (level, attribute)
-// stream, found by a parallel pre-pass; L = smax - smin + 1):
-//   C(i) = min(rn(Phi(((smin + i) - 0.5) * Q; mean, scale) * (65536 - L)), 65536 - L) + i
-// (the "+ i" keeps every symbol codable, as torchac's _convert_to_int_and_normalize does).
+// stream, found while the level is quantised; L = smax - smin + 1):
+//   C(i) = min(rn(Phi((((smin + i) - 0.5) * Q - mean) / scale) * (65536 - L)), 65536 - L) + i
+// (the "+ i" keeps every symbol codable, as torchac's _convert_to_int_and_normalize does).  Phi is the coder's own
+// tabulated normal CDF (phi_interp below, |error| < 2e-7).
+#include <algorithm>
+
 #include "entropy_math.cuh"
 
 namespace cgs {
@@ -26,59 +29,68 @@ namespace codec {
 constexpr uint32_t kTopValue = 1u << 24;
 constexpr int kTotalBits = 16;
 
+// Encoder.  The byte string is the classic carry-propagating range coder's (one leading zero byte, then the digits of
+// the final code value, then the four bytes of `low`): the same bytes oracle/codec_ref.py produces with the cached-byte
+// formulation.  Here the 0 / 1 / 2 bytes a symbol shifts out of `low` are appended to a 64-bit register of pending bytes
+// without a loop, and stored 32 bits at a time; a carry out of `low` is an increment of that register and only ripples into
+// memory when every pending byte is 0xff.
 struct Encoder {
-    uint64_t low;
-    uint32_t range;
-    uint32_t cache_size;
-    uint8_t cache;
-    uint32_t *out;      // 4-byte aligned
-    uint32_t pos, cap;  // bytes written / capacity
-    uint32_t word;
+    uint32_t low, range;
+    uint32_t *out;             // 4-byte aligned
+    uint32_t pos, stored, cap; // bytes emitted / of those, stored to memory (multiple of 4) / capacity (multiple of 4)
+    uint64_t acc;              // the pos - stored (<= 3 between symbols) pending bytes, first emitted most significant
     bool overflow;
 
     __device__ void init(uint32_t *o, uint32_t capacity)
     {
-        low = 0; range = 0xffffffffu; cache_size = 1; cache = 0; out = o; pos = 0; cap = capacity; word = 0; overflow = false;
+        low = 0; range = 0xffffffffu; out = o; pos = 1; stored = 0; cap = capacity; acc = 0; overflow = false;   // pos 1: the leading zero
     }
-    __device__ __forceinline__ void put(uint8_t b)
+    __device__ __forceinline__ void append(uint32_t bytes, uint32_t nb)   // nb <= 2
     {
-        word |= (uint32_t)b << (8 * (pos & 3));
-        if ((pos & 3) == 3) {
-            if (pos < cap) out[pos >> 2] = word;
+        acc = (acc << (8 * nb)) | bytes;
+        pos += nb;
+        const uint32_t cnt = pos - stored;
+        if (cnt >= 4u) {
+            const uint32_t w = (uint32_t)(acc >> (8 * (cnt - 4u)));
+            if (stored + 4u <= cap) out[stored >> 2] = __byte_perm(w, 0, 0x0123);   // memory order = emission order
             else overflow = true;
-            word = 0;
+            stored += 4u;
         }
-        ++pos;
     }
-    __device__ __forceinline__ void shift_low()
+    __device__ __forceinline__ void carry()
     {
-        if ((uint32_t)low < 0xff000000u || (low >> 32) != 0) {
-            const uint8_t carry = (uint8_t)(low >> 32);
-            uint8_t temp = cache;
-            do {
-                put((uint8_t)(temp + carry));
-                temp = 0xff;
-            } while (--cache_size);
-            cache = (uint8_t)((low >> 24) & 0xff);
+        const uint32_t cnt = pos - stored;
+        const uint64_t mask = (1ull << (8 * cnt)) - 1ull;
+        if ((acc & mask) != mask) { acc += 1ull; return; }
+        acc &= ~mask;
+        for (int i = (int)(stored >> 2) - 1; i >= 0; --i) {
+            if ((uint32_t)i >= cap / 4) continue;
+            const uint32_t w = __byte_perm(out[i], 0, 0x0123) + 1u;
+            out[i] = __byte_perm(w, 0, 0x0123);
+            if (w != 0u) break;
         }
-        ++cache_size;
-        low = (low & 0x00ffffffull) << 8;
     }
     __device__ __forceinline__ void encode(uint32_t lo, uint32_t hi)   // cumulative frequencies out of 2^16
     {
         const uint32_t r = range >> kTotalBits;
-        low += (uint64_t)r * lo;
-        range = r * (hi - lo);
-        while (range < kTopValue) {
-            range <<= 8;
-            shift_low();
-        }
+        const uint32_t t = low + r * lo;
+        if (t < low) carry();
+        low = t;
+        range = r * (hi - lo);                                             // >= 2^8: at most two bytes leave
+        const uint32_t nb = range < kTopValue ? (range < (1u << 16) ? 2u : 1u) : 0u;
+        append(__funnelshift_l(low, 0u, 8 * nb), nb);                      // the top nb bytes of low (0 for nb = 0)
+        low <<= 8 * nb;
+        range <<= 8 * nb;
     }
     __device__ uint32_t finish()
     {
-        for (int i = 0; i < 5; ++i) shift_low();
-        const uint32_t n = pos;
-        while (pos & 3) put(0);   // flush the partial word (padding is not counted)
+        append(low >> 16, 2);
+        append(low & 0xffffu, 2);
+        const uint32_t n = pos, cnt = pos - stored;
+        if (cnt) {   // flush the partial word (padding is not counted)
+            if (stored + 4u <= cap) out[stored >> 2] = __byte_perm((uint32_t)(acc << (8 * (4u - cnt))), 0, 0x0123);
+            else overflow = true;
+        }
         return n;
     }
 };
@@ -110,13 +122,39 @@ struct Decoder {
     }
 };
 
-// cumulative frequency of the boundary below symbol s (see the header); L = alphabet size
-__device__ __forceinline__ uint32_t gauss_cum(int s, int smin, int L, float Q, float mean, float inv_scale)
+// Phi of the coder: the standard normal CDF tabulated at kPhiN + 1 points of [kPhiZ0, -kPhiZ0] (host, fp64 erfc, rounded to
+// fp32; T[0] = 0, T[kPhiN] = 1) and interpolated linearly: |error| < 2e-7, far below the 2^-16 resolution of the coder,
+// monotone, and an order of magnitude cheaper than erff inside the sequential decoder.  Every operation is a single
+// correctly rounded fp32 operation in a fixed order (no contraction), so the function is reproducible outside this file
+// (tests/test_codec_gpu.py rebuilds the dense CDF tables with torch ops from cgs_codec_phi_table).
+constexpr int kPhiN = 4096;
+constexpr float kPhiZ0 = -4.75f;
+constexpr float kPhiInvH = (float)kPhiN / 9.5f;
+__device__ float g_phi_table[kPhiN + 1];
+
+__device__ __forceinline__ void load_phi_table(float *__restrict__ T)
 {
-    const float z = ((float)s - 0.5f) * Q;
-    const float phi = 0.5f * (1.0f + erff((z - mean) * inv_scale * 0.70710678118654752f));
-    const uint32_t M = 65536u - (uint32_t)L;
-    uint32_t c = __float2uint_rn(phi * (float)M);
+    for (int i = threadIdx.x; i <= kPhiN; i += blockDim.x) T[i] = g_phi_table[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ float phi_interp(const float *__restrict__ T, float z)
+{
+    float t = __fmul_rn(__fsub_rn(z, kPhiZ0), kPhiInvH);
+    t = fminf(fmaxf(t, 0.0f), (float)kPhiN);   // NaN -> 0
+    const int j = min((int)t, kPhiN - 1);
+    const float f = __fsub_rn(t, (float)j);
+    const float t0 = T[j];
+    return __fadd_rn(t0, __fmul_rn(f, __fsub_rn(T[j + 1], t0)));
+}
+
+// cumulative frequency of the boundary below symbol s (see the header); M = 65536 - alphabet size
+__device__ __forceinline__ uint32_t gauss_cum(const float *__restrict__ T, int s, int smin, uint32_t M, float Q, float mean,
+                                              float inv_scale)
+{
+    const float z = __fmul_rn((float)s - 0.5f, Q);
+    const float phi = phi_interp(T, __fmul_rn(__fsub_rn(z, mean), inv_scale));
+    uint32_t c = __float2uint_rn(__fmul_rn(phi, (float)M));
     c = c > M ? M : c;
     return c + (uint32_t)(s - smin);
 }
@@ -205,38 +243,83 @@ gauss_level_minmax_kernel(LevelStreams g, int32_t *__restrict__ minmax)
     }
 }
 
-// Encoder pass 1, one warp per level row (columns as above): the coding interval [C(s), C(s + 1)) of every coded value,
-// packed as lo | (hi - lo - 1) << 16 into iv[n_rows * col0 + row * dim + k] (kSkip for values that are not coded), so the
-// two erf and the division are out of the sequential coder and all loads are coalesced.
+// Encoder pass 1: the coding interval [C(s), C(s + 1)) of every coded value, packed as lo | (hi - lo - 1) << 16 into
+// iv[n_rows * col0 + row * dim + k] (kSkip for values that are not coded), so the CDF evaluations and the division are out
+// of the sequential coder and all loads are coalesced.  One warp per level row, in four passes with compile-time stream
+// (feat 0..31, feat 32..49, scaling, offsets): no per-value stream selection, the row's anchor index / steps loaded once.
+struct CodedValue {
+    float x, mean, scale;
+    bool coded;
+};
+
+template <int ATTR>
+__device__ __forceinline__ CodedValue load_value(const LevelStreams &g, const float *__restrict__ pr, int o, int k, bool active)
+{
+    constexpr int dim = ATTR == 0 ? kCF : ATTR == 1 ? kCS : kCO;
+    constexpr int col0 = ATTR == 0 ? 0 : ATTR == 1 ? kCF : kCF + kCS;
+    CodedValue v;
+    v.coded = active && (ATTR != 2 || g.mask[(size_t)o * 10 + k / 3] != 0.0f);
+    v.x = active ? g.values[ATTR][(size_t)o * dim + k] : 0.0f;
+    v.mean = active ? pr[col0 + k] : 0.0f;
+    v.scale = active ? pr[kCE + col0 + k] : 1.0f;
+    return v;
+}
+
+template <int ATTR>
+__device__ __forceinline__ void interval_of_value(const LevelStreams &g, const float *__restrict__ T, const CodedValue &v, float Q,
+                                                  int row, int k, bool active, int smin, int smax, uint32_t *__restrict__ iv,
+                                                  int32_t *__restrict__ err)
+{
+    constexpr int dim = ATTR == 0 ? kCF : ATTR == 1 ? kCS : kCO;
+    constexpr int col0 = ATTR == 0 ? 0 : ATTR == 1 ? kCF : kCF + kCS;
+    if (!active) return;
+    uint32_t packed = kSkip;
+    if (smax >= smin && v.coded) {
+        const float inv = __frcp_rn(fmaxf(v.scale, 1e-9f));
+        // x is an integer multiple of Q (|multiple| <= 15000): the approximate quotient rounds to the same integer
+        const int s = __float2int_rn(__fdividef(v.x, Q));
+        const uint32_t M = 65536u - (uint32_t)(smax - smin + 1);
+        const uint32_t lo = gauss_cum(T, s, smin, M, Q, v.mean, inv), hi = gauss_cum(T, s + 1, smin, M, Q, v.mean, inv);
+        if (hi <= lo || s < smin || s > smax) atomicExch(err, 1);   // CDF not monotone at rounding level: undecodable
+        else packed = lo | ((hi - lo - 1u) << 16);
+    }
+    iv[(size_t)g.n_rows * col0 + (size_t)row * dim + k] = packed;
+}
+
 __global__ void __launch_bounds__(256)
 gauss_level_intervals_kernel(LevelStreams g, const int32_t *__restrict__ minmax, uint32_t *__restrict__ iv,
                              int32_t *__restrict__ err)
 {
+    __shared__ float T[kPhiN + 1];
+    load_phi_table(T);
     const int lane = threadIdx.x & 31;
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= g.n_rows) return;
-    const int o = g.orig_idx[row];
-    const float *pr = g.params + (size_t)row * kLdG2;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const int col = lane + 32 * j;
-        if (col >= kCE) continue;
-        const int attr = attr_of_col(col), col0 = attr_col0(attr), dim = attr_dim(attr), k = col - col0;
-        const int smin = minmax[2 * attr], smax = minmax[2 * attr + 1];
-        const int L = smax - smin + 1;
-        uint32_t packed = kSkip;
-        if (smax >= smin && L > 32768) {   // cannot happen after the +-15000-step clamp of STE_multistep
-            atomicExch(err, 2);
-        } else if (smax >= smin && (attr != 2 || g.mask[(size_t)o * 10 + k / 3] != 0.0f)) {
-            const float Q = pr[172 + attr];
-            const float x = pick3(g.values, attr)[(size_t)o * dim + k];
-            const float mean = pr[col], inv = __frcp_rn(fmaxf(pr[kCE + col], 1e-9f));
-            const int s = (int)rintf(__fdiv_rn(x, Q));
-            const uint32_t lo = gauss_cum(s, smin, L, Q, mean, inv), hi = gauss_cum(s + 1, smin, L, Q, mean, inv);
-            if (hi <= lo || s < smin || s > smax) atomicExch(err, 1);   // erf not monotone at rounding level: undecodable
-            else packed = lo | ((hi - lo - 1u) << 16);
-        }
-        iv[(size_t)g.n_rows * col0 + (size_t)row * dim + k] = packed;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    int lo0 = minmax[0], hi0 = minmax[1], lo1 = minmax[2], hi1 = minmax[3], lo2 = minmax[4], hi2 = minmax[5];
+    if (hi0 - lo0 + 1 > 32768 || hi1 - lo1 + 1 > 32768 || hi2 - lo2 + 1 > 32768) {
+        // cannot happen after the +-15000-step clamp of STE_multistep; such a stream is skipped entirely
+        if (threadIdx.x == 0) atomicExch(err, 2);
+        if (hi0 - lo0 + 1 > 32768) hi0 = lo0 - 1;
+        if (hi1 - lo1 + 1 > 32768) hi1 = lo1 - 1;
+        if (hi2 - lo2 + 1 > 32768) hi2 = lo2 - 1;
+    }
+    // persistent blocks (the table is staged once per block), rows dealt to the warps round-robin; every load of a row is
+    // issued before the first value is evaluated, the next row's anchor index one row ahead
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int o_next = row < g.n_rows ? g.orig_idx[row] : 0;
+    for (; row < g.n_rows; row += warps) {
+        const int o = o_next;
+        if (row + warps < g.n_rows) o_next = g.orig_idx[row + warps];
+        const float *pr = g.params + (size_t)row * kLdG2;
+        const bool a1 = lane < kCF - 32, a2 = lane < kCS, a3 = lane < kCO;
+        const CodedValue v0 = load_value<0>(g, pr, o, lane, true);
+        const CodedValue v1 = load_value<0>(g, pr, o, 32 + lane, a1);
+        const CodedValue v2 = load_value<1>(g, pr, o, lane, a2);
+        const CodedValue v3 = load_value<2>(g, pr, o, lane, a3);
+        const float Qf = pr[172], Qs = pr[173], Qo = pr[174];
+        interval_of_value<0>(g, T, v0, Qf, row, lane, true, lo0, hi0, iv, err);
+        interval_of_value<0>(g, T, v1, Qf, row, 32 + lane, a1, lo0, hi0, iv, err);
+        interval_of_value<1>(g, T, v2, Qs, row, lane, a2, lo1, hi1, iv, err);
+        interval_of_value<2>(g, T, v3, Qo, row, lane, a3, lo2, hi2, iv, err);
     }
 }
 
@@ -260,10 +343,12 @@ gauss_level_encode_kernel(LevelStreams g, const int32_t *__restrict__ minmax, co
     enc.init(out + pick3(g.region, attr) + (size_t)cl * (cap / 4), cap);
     const uint2 *src = reinterpret_cast<const uint2 *>(iv + (size_t)g.n_rows * attr_col0(attr) + (size_t)r0 * dim);
     const int pairs = (r1 - r0) * dim / 2;
-    uint2 nxt = pairs ? src[0] : make_uint2(kSkip, kSkip);
-    for (int i = 0; i < pairs; ++i) {
-        const uint2 cur = nxt;
-        if (i + 1 < pairs) nxt = src[i + 1];
+    const uint2 none = make_uint2(kSkip, kSkip);
+    uint2 n1 = pairs > 0 ? src[0] : none, n2 = pairs > 1 ? src[1] : none, n3 = pairs > 2 ? src[2] : none;
+    for (int i = 0; i < pairs; ++i) {   // three pairs in flight
+        const uint2 cur = n1;
+        n1 = n2; n2 = n3;
+        if (i + 3 < pairs) n3 = src[i + 3];
         if (cur.x != kSkip) enc.encode(cur.x & 0xffffu, (cur.x & 0xffffu) + (cur.x >> 16) + 1u);
         if (cur.y != kSkip) enc.encode(cur.y & 0xffffu, (cur.y & 0xffffu) + (cur.y >> 16) + 1u);
     }
@@ -288,11 +373,13 @@ gauss_level_pack_kernel(LevelStreams g, const uint32_t *__restrict__ scratch, co
 // One thread per chunk of any of the three streams.  Symbol search: the inverse Gaussian CDF of the coder's target gives
 // the symbol to within a step; it is confirmed / corrected by evaluating C next to it -- normally two evaluations --
 // galloping further and bisecting only where the estimate is off (far tails, where C is flat).
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 gauss_level_decode_kernel(LevelStreams g, const uint8_t *__restrict__ b0, const uint8_t *__restrict__ b1,
                           const uint8_t *__restrict__ b2, const int64_t *__restrict__ stream_off,
                           const int32_t *__restrict__ stream_len, const int32_t *__restrict__ minmax)
 {
+    __shared__ float T[kPhiN + 1];
+    load_phi_table(T);
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     int attr, cl;
     if (!locate_chunk(g, c, attr, cl)) return;
@@ -328,7 +415,7 @@ gauss_level_decode_kernel(LevelStreams g, const uint8_t *__restrict__ b0, const 
             int lo_s, hi_s;
             uint32_t clo = 0, chi = 0;
             bool have_lo = false, have_hi = false;  // clo == C(lo_s) / chi == C(hi_s + 1) already evaluated
-            // Flat tails first.  Below z = -kFlat the rounded Gaussian term of C is exactly 0 (Phi(-4.7) M < 0.15) and above
+            // Flat tails first.  Below z = -kFlat the rounded Gaussian term of C is exactly 0 (Phi(-4.7) M < 0.09) and above
             // +kFlat it is exactly M, so C(s) = s - smin resp. M + s - smin there and the symbol follows from v alone.  A
             // badly predicted value (most of an untrained model's) costs ~16 bits but no search at all.
             constexpr float kFlat = 4.7f;
@@ -346,10 +433,10 @@ gauss_level_decode_kernel(LevelStreams g, const uint8_t *__restrict__ b0, const 
                 lo_s = (int)fminf(fmaxf(floorf((mean - kFlat * sc) * inv_Q) - 1.0f, (float)smin), (float)smax);
                 hi_s = (int)fminf(fmaxf(ceilf((mean + kFlat * sc) * inv_Q) + 2.0f, (float)lo_s), (float)smax);
                 // C(s) = rn(Phi_s M) + (s - smin) <= v: invert Phi with the ramp term taken at the current estimate of s
-                // (first the mean's symbol), twice -- the ramp moves by 1 / M per symbol, so the second pass is on target
+                // (first the mean's symbol)
                 int m = min(max(__float2int_rn(mean * inv_Q), lo_s), hi_s);
-#pragma unroll
-                for (int it = 0; it < 2; ++it) {
+                const int iters = L > 2048 ? 2 : 1;   // the second pass only pays where the ramp is a large part of C
+                for (int it = 0; it < iters; ++it) {
                     float u = ((float)v - (float)(m - smin) + 0.5f) * inv_M;
                     u = fminf(fmaxf(u, 1e-7f), 1.0f - 1e-7f);
                     const float xs = fmaf(normcdfinvf(u), sc, mean);
@@ -359,19 +446,19 @@ gauss_level_decode_kernel(LevelStreams g, const uint8_t *__restrict__ b0, const 
                 bool up = true, bracketed = false;
                 for (int step = 0; lo_s < hi_s && !bracketed; step = 2 * step + 1) {
                     if (step) m = up ? min(lo_s + step, hi_s) : max(hi_s - step + 1, lo_s + 1);
-                    const uint32_t cw = gauss_cum(m, smin, L, Q, mean, inv);
+                    const uint32_t cw = gauss_cum(T, m, smin, M, Q, mean, inv);
                     const bool le = cw <= v;
                     if (le) { lo_s = m; clo = cw; have_lo = true; } else { hi_s = m - 1; chi = cw; have_hi = true; }
                     if (step) bracketed = le != up; else up = le;
                 }
                 while (lo_s < hi_s) {
                     const int mid = lo_s + (hi_s - lo_s + 1) / 2;
-                    const uint32_t cw = gauss_cum(mid, smin, L, Q, mean, inv);
+                    const uint32_t cw = gauss_cum(T, mid, smin, M, Q, mean, inv);
                     if (cw <= v) { lo_s = mid; clo = cw; have_lo = true; } else { hi_s = mid - 1; chi = cw; have_hi = true; }
                 }
             }
-            if (!have_lo) clo = gauss_cum(lo_s, smin, L, Q, mean, inv);
-            if (!have_hi || hi_s < lo_s) chi = gauss_cum(lo_s + 1, smin, L, Q, mean, inv);
+            if (!have_lo) clo = gauss_cum(T, lo_s, smin, M, Q, mean, inv);
+            if (!have_hi || hi_s < lo_s) chi = gauss_cum(T, lo_s + 1, smin, M, Q, mean, inv);
             dec.consume(clo, chi > clo ? chi : clo + 1);
             x[k] = (float)lo_s * Q;
         }
@@ -449,6 +536,52 @@ pack_streams_kernel(const uint32_t *__restrict__ scratch, uint32_t cap_bytes, co
 }  // namespace cgs
 
 using namespace cgs;
+
+// host copy of the Phi table; uploaded to each device on first use
+static const float *phi_table_host()
+{
+    static float table[codec::kPhiN + 1];
+    static bool ready = false;
+    if (!ready) {
+        for (int j = 0; j <= codec::kPhiN; ++j) {
+            const double z = -4.75 + 9.5 * (double)j / (double)codec::kPhiN;   // exact: 9.5 / 4096 is a binary fraction
+            table[j] = (float)(0.5 * erfc(-z * 0.70710678118654752440));
+        }
+        table[0] = 0.0f;
+        table[codec::kPhiN] = 1.0f;
+        ready = true;
+    }
+    return table;
+}
+
+static int ensure_phi_table()
+{
+    static bool uploaded[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!uploaded[dev]) {
+        if (cudaMemcpyToSymbol(codec::g_phi_table, phi_table_host(), sizeof(float) * (codec::kPhiN + 1)) != cudaSuccess) {
+            set_error("entropy codec: uploading the Phi table failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return -101;
+        }
+        uploaded[dev] = true;
+    }
+    return 0;
+}
+
+extern "C" int cgs_codec_phi_table(float *table, int n, float *z0, float *inv_h)
+{
+    if (!table || n != codec::kPhiN + 1) {
+        set_error("%s: the table has %d entries", __func__, codec::kPhiN + 1);
+        return -2;
+    }
+    const float *t = phi_table_host();
+    for (int j = 0; j < n; ++j) table[j] = t[j];
+    if (z0) *z0 = codec::kPhiZ0;
+    if (inv_h) *inv_h = codec::kPhiInvH;
+    return 0;
+}
 
 static int attr_layout(int attr, int *dim, int *col0)
 {
@@ -534,9 +667,10 @@ extern "C" int cgs_codec_gauss_level_encode(const int32_t *orig_idx, int n_rows,
     if (int e = level_streams(&g, __func__, orig_idx, n_rows, chunk_rows, params, mask, const_cast<float *>(feat_q),
                               const_cast<float *>(scaling_q), const_cast<float *>(offsets_q)))
         return e;
+    if (int e = ensure_phi_table()) return e;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     StageScope sc(ST_CODEC, st, 2);
-    codec::gauss_level_intervals_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(g, minmax, intervals, err);
+    codec::gauss_level_intervals_kernel<<<std::min((n_rows + 7) / 8, 148 * 8), 256, 0, st>>>(g, minmax, intervals, err);
     const int chunks = g.n_chunks[0] + g.n_chunks[1] + g.n_chunks[2];
     codec::gauss_level_encode_kernel<<<(chunks + 63) / 64, 64, 0, st>>>(g, minmax, intervals, scratch, stream_len, err);
     return check_launch(__func__);
@@ -571,10 +705,11 @@ extern "C" int cgs_codec_gauss_level_decode(const int32_t *orig_idx, int n_rows,
     CGS_CHECK_PTR(stream_len); CGS_CHECK_PTR(minmax);
     codec::LevelStreams g;
     if (int e = level_streams(&g, __func__, orig_idx, n_rows, chunk_rows, params, mask, feat_q, scaling_q, offsets_q)) return e;
+    if (int e = ensure_phi_table()) return e;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     StageScope sc(ST_CODEC, st, 1);
     const int chunks = g.n_chunks[0] + g.n_chunks[1] + g.n_chunks[2];
-    codec::gauss_level_decode_kernel<<<(chunks + 63) / 64, 64, 0, st>>>(g, feat_bytes, scaling_bytes, offsets_bytes, stream_off,
+    codec::gauss_level_decode_kernel<<<(chunks + 127) / 128, 128, 0, st>>>(g, feat_bytes, scaling_bytes, offsets_bytes, stream_off,
                                                                        stream_len, minmax);
     return check_launch(__func__);
 }

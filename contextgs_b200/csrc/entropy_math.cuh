@@ -38,4 +38,12 @@ __device__ __forceinline__ float ste_round(float x, float Q)
     return rintf(__fdiv_rn(x, Q)) * Q;
 }
 
+// same value; `sym` receives the integer step count (the symbol the bitstream codec codes: rint(value / Q))
+__device__ __forceinline__ float ste_round_sym(float x, float Q, float &sym)
+{
+    x = fminf(fmaxf(x, -kClampSteps * Q), kClampSteps * Q);
+    sym = rintf(__fdiv_rn(x, Q));
+    return sym * Q;
+}
+
 }  // namespace cgs

@@ -364,7 +364,10 @@ CGS_API int cgs_context_level_umma_forward(int in_dim, const float *packed_w, co
  *   params_out[n_rows][176] (optional) receives what the entropy coder needs for every level row:
  *     mean[86] | scale[86] (raw MLP outputs, feat 50 | scaling 6 | offsets 30) | Q_feat Q_scaling Q_offsets | 0;
  *   predict_only != 0 : ONLY params_out is produced -- the decoder calls this before the level's attributes exist
- *     (feat / scaling / offsets / mask / offsets_q may be NULL; feat_q / scaling_q are read as context only). */
+ *     (feat / scaling / offsets / mask / offsets_q may be NULL; feat_q / scaling_q are read as context only);
+ *   symbol_minmax (optional, device int32[6], ignored when predict_only): min / max of the coded symbols rint(value / Q) of
+ *     the level's feat, scaling and (unmasked) offsets streams = the alphabets the bitstream codec needs (the same values
+ *     cgs_codec_gauss_level_minmax computes in a separate pass); max < min marks an empty stream. */
 CGS_API int cgs_context_level_umma_forward_ex(int in_dim, const float *packed_w, const int32_t *orig_idx,
                                               const int32_t *ctx_src, const float *level_anchor, int n_rows,
                                               const float *anchor, const float *hyper_q, const float *feat,
@@ -372,7 +375,8 @@ CGS_API int cgs_context_level_umma_forward_ex(int in_dim, const float *packed_w,
                                               const uint8_t *choose, const float *noise, float feat_mean,
                                               float scaling_mean, float offset_mean, float *feat_q, float *scaling_q,
                                               float *offsets_q, float *bits_out, double *bit_sums, int32_t *err_flag,
-                                              float *params_out, int predict_only, void *stream);
+                                              float *params_out, int predict_only, int32_t *symbol_minmax,
+                                              void *stream);
 
 /* Training-mode variant of cgs_context_level_umma_forward (scene/gaussian_model.py:1596-1652 with training=True): same
  * outputs, and additionally params_out[n_rows,176] (mean[86] | scale[86] | Q_feat Q_scaling Q_offsets | 0, biases applied),
@@ -499,7 +503,8 @@ CGS_API int cgs_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in,
  * them back to back (n_chunks[a] = ceil(n_rows / chunk_rows[a]) chunks of stream a; chunk c of stream a = level rows
  * [c*chunk_rows[a], (c+1)*chunk_rows[a])).  chunk_rows and n_chunks are HOST arrays of three ints.
  *   symbol = rint(value / Q); alphabet of stream a = minmax[2a], minmax[2a+1] (device int32 x6) = min / max symbol of the
- *   whole stream, computed by cgs_codec_gauss_level_minmax (parallel pre-pass) and stored with the stream;
+ *   whole stream, computed by cgs_codec_gauss_level_minmax (parallel pass; cgs_context_level_umma_forward_ex returns the
+ *   same bounds for free when it quantises the level) and stored with the stream;
  *   cgs_codec_gauss_level_chunks: chunk counts of the three streams; returns the 32-bit words of `scratch` an encode
  *   needs (chunk c of stream a sits at a fixed stride of cgs_codec_gauss_stream_capacity(a, chunk_rows[a]) bytes);
  *   cgs_codec_gauss_level_encode: pass 1 writes the 16-bit coding interval of each of the n_rows*86 values to `intervals`
@@ -511,6 +516,12 @@ CGS_API int cgs_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in,
  *   stream_off[first chunk of a] and writes value = symbol * Q at {feat,scaling,offsets}_q[orig_idx[row]][k] --
  *   bit-identical to the encoder's input. */
 CGS_API int64_t cgs_codec_gauss_stream_capacity(int attr, int chunk_rows);
+/* The coder's normal CDF: Phi(z) = T[j] + f * (T[j+1] - T[j]) with t = clamp((z - z0) * inv_h, 0, n - 1), j = min((int)t,
+ * n - 2), f = t - j, every operation one correctly rounded fp32 operation in this order; T = fp32(0.5 erfc(-z_j / sqrt 2))
+ * at z_j = z0 + j / inv_h, T[0] = 0, T[n-1] = 1.  Copies T (n = 4097 entries) to HOST memory, and z0 / inv_h if not NULL.
+ * Cumulative frequency of symbol boundary s: min(rn(Phi((((s - 0.5) * Q) - mean) * (1 / max(scale, 1e-9))) * M), M)
+ * + (s - smin), M = 65536 - (smax - smin + 1). */
+CGS_API int cgs_codec_phi_table(float *table, int n, float *z0, float *inv_h);
 CGS_API int64_t cgs_codec_gauss_level_chunks(int n_rows, const int *chunk_rows, int32_t *n_chunks);
 CGS_API int cgs_codec_gauss_level_minmax(const int32_t *orig_idx, int n_rows, const float *params, const float *mask,
                                          const float *feat_q, const float *scaling_q, const float *offsets_q,

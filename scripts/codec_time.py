@@ -30,6 +30,13 @@ def enc():
     box["e"] = codec.encode_model(pc)
 ms_e = timed(enc)
 e = box["e"]
+def enc_plain():
+    box["p"] = codec.encode_model(pc, estimate_bits=False)
+ms_p = timed(enc_plain)
+for lv, lp in zip(e.levels, box["p"].levels):
+    for k in lv.streams:
+        assert torch.equal(lv.streams[k].bytes, lp.streams[k].bytes) and torch.equal(lv.streams[k].lens, lp.streams[k].lens), k
+print(f"encode without the entropy estimate {ms_p:.2f} ms (same bytes)")
 def decf():
     box["o"] = codec.decode_model(d, e.meta, e.anchor_q, e.mask_bytes, e.mask_lens, e.hyper_bytes, e.hyper_lens, e.levels)
 ms_d = timed(decf)

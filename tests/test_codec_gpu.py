@@ -73,6 +73,42 @@ def test_quantised_values_equal_the_scoring_pass_and_sizes_match_estimates():
     assert bits["anchor"] == 48 * a.shape[0]
 
 
+def test_alphabets_from_the_level_kernel_equal_the_stand_alone_pass():
+    """The encoder takes each stream's (min, max) symbol from the level kernel's epilogue (`symbol_minmax` of
+    cgs_context_level_umma_forward_ex); cgs_codec_gauss_level_minmax recomputes them from the quantised tensors, and torch
+    once more from the definition rint(value / Q) over the coded values."""
+    from contextgs_b200 import _lib
+    pc = _model(3000)
+    enc = codec.encode_model(pc)
+    q = enc.quantised
+    dev = q["feat"].device
+    means = codec.global_means(pc)
+    sums = torch.zeros(16, dtype=torch.float64, device=dev)
+    terr = torch.zeros(1, dtype=torch.int32, device=dev)
+    seen = 0
+    for li, (lv, coded) in enumerate(zip(enc.plan.levels, enc.levels)):
+        if lv.n == 0:
+            continue
+        fq, sq, oq = q["feat"].clone(), q["scaling"].clone(), q["offsets"].clone()
+        params = codec._level_params(pc, lv, q["anchor"], q["hyper"] * (0 if pc.disable_hyper else 1), None, None, None, None,
+                                     fq, sq, oq, sums[4 * li:4 * li + 4], terr, means, True)
+        mm = torch.empty(6, dtype=torch.int32, device=dev)
+        p = _lib.ptr
+        _lib.check(_lib.lib().cgs_codec_gauss_level_minmax(p(lv.orig), lv.n, p(params), p(q["masks"]), p(q["feat"]),
+                                                           p(q["scaling"]), p(q["offsets"]), p(mm), _lib.stream_ptr()),
+                   "cgs_codec_gauss_level_minmax")
+        fused = torch.cat([coded.streams[name].minmax for name, _ in codec.ATTRS])
+        assert torch.equal(mm, fused), (li, mm.tolist(), fused.tolist())
+        o = lv.orig.long()
+        for attr, (name, dim) in enumerate(codec.ATTRS):
+            sym = torch.round((q["feat"], q["scaling"], q["offsets"])[attr][o] / params[:, 172 + attr:173 + attr])
+            if attr == 2:
+                sym = sym[q["masks"][o].repeat_interleave(3, dim=1) != 0]
+            assert [int(sym.min()), int(sym.max())] == mm[2 * attr:2 * attr + 2].tolist(), (li, name)
+            seen += 1
+    assert seen >= 6
+
+
 def test_table_streams_are_byte_identical_to_the_cpu_range_coder():
     pc = _model(700)
     enc = codec.encode_model(pc, chunk_rows=32)
@@ -104,8 +140,14 @@ def test_gaussian_streams_decode_with_an_independent_table_decoder():
     materialises a dense [symbols, alphabet] CDF tensor per chunk and hands it to torchac): the bytes the GPU coder wrote are
     decoded by the plain-Python range decoder of oracle/codec_ref.py from DENSE per-symbol cumulative-frequency tables
     built with torch ops (C(i) = min(rn(Phi(((smin + i) - 1/2) Q) (65536 - L)), 65536 - L) + i, the formula of
-    DESIGN.md section 4) -- neither the closed-form evaluation nor the search of the GPU decoder is involved.  The encoder
-    side is checked too: re-encoding the decoded symbols on the CPU reproduces the GPU's bytes."""
+    DESIGN.md section 4, Phi = the coder's tabulated normal CDF, itself checked against math.erfc here) -- neither the
+    GPU's evaluation of C nor the search of the GPU decoder is involved.  The encoder side is checked too: re-encoding the
+    decoded symbols on the CPU reproduces the GPU's bytes."""
+    import math
+    T_np, z0, inv_h = codec.phi_table()
+    want = np.array([0.5 * math.erfc(-(-4.75 + 9.5 * j / 4096) / math.sqrt(2.0)) for j in range(4097)]).astype(np.float32)
+    want[0], want[-1] = 0.0, 1.0
+    assert np.array_equal(T_np, want) and z0 == -4.75 and inv_h == float(np.float32(4096 / 9.5))
     pc = _model(700)
     enc = codec.encode_model(pc, chunk_rows=4)
     q = enc.quantised
@@ -143,7 +185,10 @@ def test_gaussian_streams_decode_with_an_independent_table_decoder():
                 # dense tables: boundary i of every symbol position, i = 0 .. L
                 i = torch.arange(L + 1, device=dev, dtype=torch.float32).view(1, 1, -1)
                 z = ((smin + i) - 0.5) * Q.unsqueeze(-1)
-                phi = 0.5 * (1.0 + torch.erf((z - mean.unsqueeze(-1)) * inv.unsqueeze(-1) * 0.70710678118654752))
+                t = torch.clamp((((z - mean.unsqueeze(-1)) * inv.unsqueeze(-1)) - z0) * inv_h, 0.0, 4096.0)
+                j = torch.clamp(t.to(torch.int64), max=4095)
+                T = torch.from_numpy(T_np).to(dev)
+                phi = T[j] + (t - j.to(torch.float32)) * (T[j + 1] - T[j])
                 M = float(65536 - L)
                 tab = (torch.clamp(torch.round(phi * M), max=M) + i).to(torch.int64)
                 tabs = tab[keep].cpu().tolist()
