@@ -218,9 +218,11 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1, estimate_bits=True)
 
     # hyper latents under the factorised prior.  The symbol range sizes the table, so it is needed on the host: it shares
     # the read-back of the level-plan cache key
-    hyper_q, _ = pc.latent_codec(hyper, training=False)
-    median = pc.latent_codec.quantiles[:, 0, 1].detach()
-    hsym = torch.round(hyper_q - median.view(1, -1)).to(torch.int32)
+    # eval-mode quantisation of the EntropyBottleneck (round about the per-channel median) without its likelihoods
+    median = pc.latent_codec.quantiles[:, 0, 1].detach().float()
+    hsteps = torch.round(hyper - median.view(1, -1))
+    hyper_q = hsteps + median.view(1, -1)
+    hsym = hsteps.to(torch.int32)
     hlo, hhi = torch.aminmax(hsym)
     content_key, (hmin, hmax) = _content_key(anchor_q, pc, extra=(hlo, hhi))
     hyper_pending = _table_encode((hsym - hmin).to(torch.int16).contiguous(), _hyper_tables(pc, hmin, hmax),
@@ -379,7 +381,7 @@ def conduct_encoding(pc, pre_path_name, chunk_rows=CHUNK_ROWS):
     caps = [int(_lib.lib().cgs_codec_gauss_stream_capacity(a, chunk_rows * ATTR_CHUNK_MULT[a])) for a in range(len(ATTRS))]
     if max(caps) > 65535 or chunk_rows * TABLE_CHUNK_MULT * 12 * 2 + 16 > 65535:
         raise ValueError("chunk_rows too large for the 16-bit chunk lengths of the directory format")
-    enc = encode_model(pc, chunk_rows)
+    enc = encode_model(pc, chunk_rows, estimate_bits=False)
     all_lens = [enc.mask_lens, enc.hyper_lens] + [st.lens for lv in enc.levels for st in lv.streams.values()]
     if max(int(l.max()) if l.numel() else 0 for l in all_lens) > 65535:
         raise _lib.CgsError("a chunk is longer than 65535 bytes: it does not fit the 16-bit length of the directory format")

@@ -63,6 +63,8 @@ def test_quantised_values_equal_the_scoring_pass_and_sizes_match_estimates():
                                         binary_grid_masks=t(pc.get_mask), predict_bpp=True, return_sum_bits=True,
                                         return_details=True)
     assert torch.equal(det["feat_q"], enc.quantised["feat"]) and torch.equal(det["scaling_q"], enc.quantised["scaling"])
+    # the encoder quantises the hyper latents inline; the EntropyBottleneck kernel must agree bit for bit
+    assert torch.equal(pc.latent_codec(t(pc._hyper_latent).contiguous(), training=False)[0], enc.quantised["hyper"])
     assert torch.allclose(a, t(pc.get_anchor), atol=0, rtol=0)
     bits = codec.encoded_bits(enc)
     est = dict(hyper=res[1], feat=res[2], scaling=res[3], offsets=res[4], masks=res[5])
