@@ -95,14 +95,34 @@ struct Encoder {
     }
 };
 
+// Decoder.  The chunk's bytes are read through 32-bit words (the aligned word holding the current byte and the next one,
+// fetched a word ahead of its use): one global load per four bytes, off the coder's critical path.  Only words that hold
+// at least one byte of the chunk are touched; bytes past the chunk read as zero.
 struct Decoder {
-    const uint8_t *in;
-    uint32_t pos, len;
+    const uint32_t *words;   // aligned word that holds byte 0 of the chunk
+    uint32_t bpos, end;      // byte position / end of the chunk, both counted from words[0]
+    uint32_t cur, nxt;       // words[bpos / 4] and words[bpos / 4 + 1]
     uint32_t code, range;
-    __device__ __forceinline__ uint8_t next() { return pos < len ? in[pos++] : (uint8_t)0; }
+    __device__ __forceinline__ uint32_t fetch(uint32_t w) const { return 4u * w < end ? __ldg(words + w) : 0u; }
+    __device__ __forceinline__ uint32_t next()
+    {
+        const uint32_t b = bpos < end ? (cur >> (8u * (bpos & 3u))) & 0xffu : 0u;
+        ++bpos;
+        if ((bpos & 3u) == 0u) {
+            cur = nxt;
+            nxt = fetch((bpos >> 2) + 1u);
+        }
+        return b;
+    }
     __device__ void init(const uint8_t *p, uint32_t n)
     {
-        in = p; pos = 0; len = n; code = 0; range = 0xffffffffu;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        words = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        bpos = (uint32_t)(a & 3u);
+        end = bpos + n;
+        cur = fetch(0);
+        nxt = fetch(1);
+        code = 0; range = 0xffffffffu;
         for (int i = 0; i < 5; ++i) code = (code << 8) | next();
     }
     __device__ __forceinline__ uint32_t target()
@@ -395,19 +415,40 @@ gauss_level_decode_kernel(LevelStreams g, const uint8_t *__restrict__ b0, const 
     Decoder dec;
     dec.init(bytes + (stream_off[c] - first), (uint32_t)stream_len[c]);
     float *values = pick3(g.values, attr);
+    // Values are decoded two at a time (every stream has an even number per row): their (mean, scale) arrive as 8-byte
+    // loads issued one pair ahead, the row's offset masks as one bit field, the decoded pair leaves as one 8-byte store.
+    int o_next = g.orig_idx[r0];
     for (int r = r0; r < r1; ++r) {
-        const int o = g.orig_idx[r];
+        const int o = o_next;
+        if (r + 1 < r1) o_next = g.orig_idx[r + 1];
         const float *pr = g.params + (size_t)r * kLdG2;
         const float Q = pr[172 + attr];
         const float inv_Q = __frcp_rn(Q);
         float *x = values + (size_t)o * dim;
-        for (int k = 0; k < dim; ++k) {
-            if (attr == 2 && g.mask[(size_t)o * 10 + k / 3] == 0.0f) {
-                x[k] = 0.0f;
-                continue;
+        uint32_t mkbits = 0xffffffffu;   // bit (k / 3): value k is coded (feat / scaling: always)
+        if (attr == 2) {
+            mkbits = 0;
+            const float2 *mk = reinterpret_cast<const float2 *>(g.mask + (size_t)o * 10);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const float2 m2 = __ldg(mk + i);
+                mkbits |= (m2.x != 0.0f ? 1u : 0u) << (2 * i) | (m2.y != 0.0f ? 2u : 0u) << (2 * i);
             }
-            const float mean = pr[col0 + k];
-            const float sc = fmaxf(pr[kCE + col0 + k], 1e-9f);
+        }
+        const float2 *pm = reinterpret_cast<const float2 *>(pr + col0), *ps = reinterpret_cast<const float2 *>(pr + kCE + col0);
+        float2 m_next = __ldg(pm), s_next = __ldg(ps);
+        for (int k = 0; k < dim; k += 2) {
+            const float2 m2 = m_next, s2 = s_next;
+            if (k + 2 < dim) {
+                m_next = __ldg(pm + (k >> 1) + 1);
+                s_next = __ldg(ps + (k >> 1) + 1);
+            }
+            float out0 = 0.0f, out1 = 0.0f;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+            if (!((mkbits >> ((k + h) / 3)) & 1u)) continue;   // not coded: decodes to 0
+            const float mean = h ? m2.y : m2.x;
+            const float sc = fmaxf(h ? s2.y : s2.x, 1e-9f);
             const float inv = __frcp_rn(sc);
             const uint32_t v = dec.target();
             // z-score of the lower boundary of symbol s
@@ -460,44 +501,66 @@ gauss_level_decode_kernel(LevelStreams g, const uint8_t *__restrict__ b0, const 
             if (!have_lo) clo = gauss_cum(T, lo_s, smin, M, Q, mean, inv);
             if (!have_hi || hi_s < lo_s) chi = gauss_cum(T, lo_s + 1, smin, M, Q, mean, inv);
             dec.consume(clo, chi > clo ? chi : clo + 1);
-            x[k] = (float)lo_s * Q;
+            if (h) out1 = (float)lo_s * Q; else out0 = (float)lo_s * Q;
+            }
+            *reinterpret_cast<float2 *>(x + k) = make_float2(out0, out1);
         }
     }
 }
 
 // ---- static-table streams (hyper latents: one table per channel; offset masks: one table) ------------
 // symbols[n][C] int16 (already relative to the table's first symbol); table of channel c = tables[(c % T)][.]
+// kSmem: the tables (T * table_ld words) are staged in shared memory -- the coder's table look-ups (encode: two per
+// symbol, decode: a binary search per symbol) are then off the global-memory latency path.
+template <bool kSmem>
+__device__ __forceinline__ const uint32_t *stage_tables(const uint32_t *__restrict__ tables, int words)
+{
+    extern __shared__ uint32_t s_tables[];
+    if (!kSmem) return tables;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) s_tables[i] = tables[i];
+    __syncthreads();
+    return s_tables;
+}
+
+template <bool kSmem>
 __global__ void __launch_bounds__(64)
 table_encode_kernel(const int16_t *__restrict__ symbols, int n_rows, int C, int chunk_rows, const uint32_t *__restrict__ tables,
                     int T, int table_ld, uint32_t *__restrict__ out, uint32_t cap_bytes, int32_t *__restrict__ stream_len,
                     int32_t *__restrict__ err)
 {
+    const uint32_t *tabs = stage_tables<kSmem>(tables, T * table_ld);
     const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
     if (chunk >= n_chunks) return;
     const int r0 = chunk * chunk_rows, r1 = min(r0 + chunk_rows, n_rows);
     Encoder enc;
     enc.init(out + (size_t)chunk * (cap_bytes / 4), cap_bytes);
-    for (int r = r0; r < r1; ++r)
-        for (int c = 0; c < C; ++c) {
-            const int s = symbols[(size_t)r * C + c];
-            const uint32_t *tb = tables + (size_t)(c % T) * table_ld;
-            if (s < 0 || s + 1 >= table_ld || tb[s + 1] <= tb[s]) {
-                atomicExch(err, 1);
-                continue;
-            }
-            enc.encode(tb[s], tb[s + 1]);
+    const int16_t *sym = symbols + (size_t)r0 * C;
+    const int total = (r1 - r0) * C;
+    int s_next = total > 0 ? sym[0] : 0;
+    for (int i = 0, c = 0; i < total; ++i) {
+        const int s = s_next;
+        if (i + 1 < total) s_next = sym[i + 1];
+        const uint32_t *tb = tabs + (size_t)(c % T) * table_ld;
+        c = c + 1 == C ? 0 : c + 1;
+        if (s < 0 || s + 1 >= table_ld || tb[s + 1] <= tb[s]) {
+            atomicExch(err, 1);
+            continue;
         }
+        enc.encode(tb[s], tb[s + 1]);
+    }
     stream_len[chunk] = (int32_t)enc.finish();
     if (enc.overflow) atomicExch(err, 3);
 }
 
+template <bool kSmem>
 __global__ void __launch_bounds__(64)
 table_decode_kernel(const uint8_t *__restrict__ bytes, const int64_t *__restrict__ stream_off,
                     const int32_t *__restrict__ stream_len, int n_rows, int C, int chunk_rows,
                     const uint32_t *__restrict__ tables, const int32_t *__restrict__ table_len, int T, int table_ld,
                     int16_t *__restrict__ symbols)
 {
+    const uint32_t *tabs = stage_tables<kSmem>(tables, T * table_ld);
     const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
     if (chunk >= n_chunks) return;
@@ -506,7 +569,7 @@ table_decode_kernel(const uint8_t *__restrict__ bytes, const int64_t *__restrict
     dec.init(bytes + stream_off[chunk], (uint32_t)stream_len[chunk]);
     for (int r = r0; r < r1; ++r)
         for (int c = 0; c < C; ++c) {
-            const uint32_t *tb = tables + (size_t)(c % T) * table_ld;
+            const uint32_t *tb = tabs + (size_t)(c % T) * table_ld;
             const int Lsym = table_len[c % T];   // symbols in this table: boundaries tb[0..Lsym]
             const uint32_t v = dec.target();
             int lo = 0, hi = Lsym - 1;
@@ -727,8 +790,13 @@ extern "C" int cgs_codec_table_encode(const int16_t *symbols, int n_rows, int C,
     }
     const int n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
     StageScope sc(ST_CODEC, static_cast<cudaStream_t>(stream), 1);
-    codec::table_encode_kernel<<<(n_chunks + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-        symbols, n_rows, C, chunk_rows, tables, T, table_ld, scratch, (uint32_t)cap_bytes, stream_len, err);
+    const size_t table_bytes = (size_t)T * table_ld * sizeof(uint32_t);
+    if (table_bytes <= 40 * 1024)
+        codec::table_encode_kernel<true><<<(n_chunks + 63) / 64, 64, table_bytes, static_cast<cudaStream_t>(stream)>>>(
+            symbols, n_rows, C, chunk_rows, tables, T, table_ld, scratch, (uint32_t)cap_bytes, stream_len, err);
+    else
+        codec::table_encode_kernel<false><<<(n_chunks + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+            symbols, n_rows, C, chunk_rows, tables, T, table_ld, scratch, (uint32_t)cap_bytes, stream_len, err);
     return check_launch(__func__);
 }
 
@@ -745,8 +813,13 @@ extern "C" int cgs_codec_table_decode(const uint8_t *bytes, const int64_t *strea
     }
     const int n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
     StageScope sc(ST_CODEC, static_cast<cudaStream_t>(stream), 1);
-    codec::table_decode_kernel<<<(n_chunks + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-        bytes, stream_off, stream_len, n_rows, C, chunk_rows, tables, table_len, T, table_ld, symbols);
+    const size_t table_bytes = (size_t)T * table_ld * sizeof(uint32_t);
+    if (table_bytes <= 40 * 1024)
+        codec::table_decode_kernel<true><<<(n_chunks + 63) / 64, 64, table_bytes, static_cast<cudaStream_t>(stream)>>>(
+            bytes, stream_off, stream_len, n_rows, C, chunk_rows, tables, table_len, T, table_ld, symbols);
+    else
+        codec::table_decode_kernel<false><<<(n_chunks + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+            bytes, stream_off, stream_len, n_rows, C, chunk_rows, tables, table_len, T, table_ld, symbols);
     return check_launch(__func__);
 }
 
