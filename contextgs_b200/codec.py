@@ -199,7 +199,7 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1, estimate_bits=True)
     sel = pc.get_mask_anchor
     dev = sel.device
     tensors = (pc._anchor, pc._hyper_latent, pc._anchor_feat, pc._offset, pc.get_scaling, pc.get_mask)
-    if not bool(sel.all()):
+    if not (pc.all_anchors_valid() if hasattr(pc, "all_anchors_valid") else bool(sel.all())):
         idx = torch.nonzero(sel)[:, 0]
         tensors = tuple(t.index_select(0, idx) for t in tensors)
     a_raw, hyper, feat, offsets, scaling, masks = (t.detach().contiguous().float() for t in tensors)
@@ -214,7 +214,9 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1, estimate_bits=True)
 
     # offset masks: one Bernoulli table (built on the device; P(1) reaches the host with the final read-back)
     p1_dev = masks.mean()
-    mask_pending = _table_encode(masks.to(torch.int16).contiguous(), mask_table(p1_dev), chunk_rows * TABLE_CHUNK_MULT, err)
+    # (symbols by comparison: the straight-through value of a kept offset is (1 - s) + s, not exactly 1 for every s)
+    mask_pending = _table_encode((masks != 0).to(torch.int16).contiguous(), mask_table(p1_dev), chunk_rows * TABLE_CHUNK_MULT,
+                                 err)
 
     # hyper latents under the factorised prior.  The symbol range sizes the table, so it is needed on the host: it shares
     # the read-back of the level-plan cache key

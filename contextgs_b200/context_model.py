@@ -9,6 +9,7 @@ arrays (`LevelPlan`) and cached while anchors and masks are unchanged.
 """
 from types import SimpleNamespace
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -524,7 +525,15 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
     if sharded:
         from .distributed import all_reduce_sums
         all_reduce_sums(sums, group)
-    s = info["sums_host"] if "sums_host" in info else sums.tolist()  # one host read-back (the reference: several .item())
+    # one host read-back (the reference: several .item()); the mask count of the size report rides on it
+    pos_num = None
+    if "sums_host" in info:
+        s = info["sums_host"]
+    elif return_sum_bits:
+        vals = torch.cat([sums, binary_grid_masks.sum(dtype=torch.float64).view(1)]).tolist()
+        s, pos_num = vals[:-1], vals[-1]
+    else:
+        s = sums.tolist()
     if info.get("err") is not None and s[15] != 0.0:   # the int32 flag aliases the low word of slot 15
         raise _lib.CgsError("cgs_context_level_umma_forward: a tensor-core completion barrier timed out")
     bit_feat, bit_scaling, bit_offsets = (sum(s[4 * i + c] for i in range(3)) for c in range(3))
@@ -534,7 +543,15 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
                    lik_hyper=lik, choose=choose, sums=s, plan=plan)
     if return_sum_bits:
         bit_anchor = int(n_chosen) * 3 * 16
-        bit_masks = get_binary_vxl_size(binary_grid_masks)[1].item()
+        if pos_num is None:
+            bit_masks = get_binary_vxl_size(binary_grid_masks)[1].item()
+        else:   # utils/encodings.py:15-32 on the host, in the fp32 arithmetic of the reference's tensors (the clamp bound
+            # 1 - 1e-6 is not representable: its fp32 value decides the result when every offset is kept)
+            f32 = np.float32
+            ttl = binary_grid_masks.numel()
+            pos, neg = f32(pos_num), f32(ttl) - f32(pos_num)
+            pg = np.clip(pos / f32(ttl), f32(1e-6), f32(1 - 1e-6))
+            bit_masks = float(pos * -np.log2(pg) + neg * -np.log2(f32(1) - pg) + f32(32))
         res = (bit_anchor, bit_hyper, bit_feat, bit_scaling, bit_offsets, bit_masks)
         return (res, details) if return_details else res
     nc = max(n_chosen, 1e-30)

@@ -203,17 +203,42 @@ class GaussianModel(DensifyMixin, nn.Module):
     def get_mask(self):
         if self.decoded_version:
             return self._mask
-        mask_sig = torch.sigmoid(self._mask)
-        return ((mask_sig > 0.01).float() - mask_sig).detach() + mask_sig
+        if torch.is_grad_enabled() and self._mask.requires_grad:   # training: autograd needs the expression (STE)
+            mask_sig = torch.sigmoid(self._mask)
+            return ((mask_sig > 0.01).float() - mask_sig).detach() + mask_sig
+        return self._binary_mask_state()[2]
+
+    def _binary_mask_state(self):
+        """(parameter, version, mask [N,K,1], anchor-valid bool [N], [all valid: bool or None]) of the no-grad evaluation
+        of scene/gaussian_model.py:295-310, shared by `get_mask`, `get_mask_anchor` and the callers that need to know whether
+        every anchor is valid (scoring pass, encoder).  The reference re-evaluates the expression on every access (SURVEY.md
+        G2); here it is evaluated once per version of `_mask`.  The entry holds the parameter object itself, so "same
+        object, same version" cannot be confused by a new tensor that reuses the address."""
+        ent = self.__dict__.get("_cgs_mask_state")
+        if ent is None or ent[0] is not self._mask or ent[1] != self._mask._version:
+            with torch.no_grad():
+                mask_sig = torch.sigmoid(self._mask)
+                mask = ((mask_sig > 0.01).float() - mask_sig) + mask_sig
+                valid = torch.sum(mask, dim=1)[:, 0] > 0
+            ent = [self._mask, self._mask._version, mask, valid, None]
+            self.__dict__["_cgs_mask_state"] = ent
+        return ent
+
+    def all_anchors_valid(self):
+        """bool(get_mask_anchor.all()) with the host read-back done once per version of `_mask`."""
+        if self.decoded_version:
+            return bool(self.get_mask_anchor.all())
+        ent = self._binary_mask_state()
+        if ent[4] is None:
+            ent[4] = bool(ent[3].all())
+        return ent[4]
 
     @property
     def get_mask_anchor(self):
         with torch.no_grad():
             if self.decoded_version:
                 return (torch.sum(self._mask, dim=1)[:, 0]) > 0
-            mask_sig = torch.sigmoid(self._mask)
-            mask = ((mask_sig > 0.01).float() - mask_sig).detach() + mask_sig
-            return (torch.sum(mask, dim=1)[:, 0]) > 0
+            return self._binary_mask_state()[3]
 
     @property
     def get_opacity_mlp(self):
@@ -424,7 +449,7 @@ class GaussianModel(DensifyMixin, nn.Module):
         from .context_model import multi_scale_generating
         sel = self.get_mask_anchor
         tensors = (self.get_anchor, self._hyper_latent, self._anchor_feat, self._offset, self.get_scaling, self.get_mask)
-        if not bool(sel.all()):  # one index list for the six gathers (the reference runs six boolean-mask selects)
+        if not self.all_anchors_valid():  # one index list for the six gathers (the reference runs six boolean-mask selects)
             idx = torch.nonzero(sel)[:, 0]
             tensors = tuple(t.index_select(0, idx) for t in tensors)
         a, h, f, o, s, m = tensors
