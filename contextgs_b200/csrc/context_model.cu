@@ -10,6 +10,8 @@
 //    leave shared memory.
 //  * gaussian_bits_{forward,backward}, ste_multistep, quantize_anchor : stand-alone elementwise
 //    kernels behind the drop-in utils.entropy_models / utils.encodings surface.
+#include <algorithm>
+
 #include "entropy_math.cuh"
 #include "mlp_tile.cuh"
 
@@ -22,7 +24,7 @@ __device__ __forceinline__ float eb_logits(const float *__restrict__ p, float v)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         l[j] = p[j] * v + p[3 + j];
-        l[j] += p[6 + j] * tanhf(l[j]);
+        l[j] += p[6 + j] * eb_tanh(l[j]);
     }
     const float *q = p + 9;
 #pragma unroll
@@ -30,7 +32,7 @@ __device__ __forceinline__ float eb_logits(const float *__restrict__ p, float v)
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             float s = q[3 * i] * l[0] + q[3 * i + 1] * l[1] + q[3 * i + 2] * l[2] + q[9 + i];
-            m[i] = s + q[12 + i] * tanhf(s);
+            m[i] = s + q[12 + i] * eb_tanh(s);
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) l[i] = m[i];
@@ -40,20 +42,25 @@ __device__ __forceinline__ float eb_logits(const float *__restrict__ p, float v)
 }
 
 // hyper [N,C] -> hyper_q [N,C], likelihood [N,C].  noise (training) is [N,C] or null (eval: round
-// about the per-channel median).
+// about the per-channel median).  The block size is a multiple of C and the grid stride a multiple of the block, so a
+// thread stays on ONE channel: its 59 parameters live in registers (from shared memory they cost 116 LDS per latent and
+// bound the kernel) and consecutive threads still touch consecutive addresses.
 __global__ void __launch_bounds__(256)
 eb_forward_kernel(const float *__restrict__ params, int C, const float *__restrict__ hyper,
                   const float *__restrict__ noise, int N, float *__restrict__ hyper_q, float *__restrict__ lik,
                   const uint8_t *__restrict__ choose, double *bit_sum)
 {
-    extern __shared__ float sp[];
     float local_bits = 0.f;
-    for (int i = threadIdx.x; i < C * kEbParams; i += blockDim.x) sp[i] = params[i];
-    __syncthreads();
+    const int c = threadIdx.x % C;
+    float p[kEbParams];
+#pragma unroll
+    for (int i = 0; i < kEbParams; ++i) p[i] = params[c * kEbParams + i];
     const size_t total = (size_t)N * C;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(e % C);
-        const float *p = sp + c * kEbParams;
+    const uint32_t used = blockDim.x / C * C;                // threads of the block that work (the rest only join the reduction)
+    uint32_t row = (blockIdx.x * used + threadIdx.x) / C;   // used % C == 0: the row advances uniformly
+    const uint32_t row_step = gridDim.x * used / C;
+    for (size_t e = threadIdx.x < used ? (size_t)blockIdx.x * used + threadIdx.x : total; e < total;
+         e += (size_t)gridDim.x * used, row += row_step) {
         const float x = hyper[e];
         float out;
         if (noise) {
@@ -71,7 +78,7 @@ eb_forward_kernel(const float *__restrict__ params, int C, const float *__restri
         hyper_q[e] = out;
         const float lk = fmaxf(fabsf(a - b), 1e-9f);
         lik[e] = lk;
-        if (bit_sum && (!choose || choose[e / C])) local_bits += -log2f(lk);
+        if (bit_sum && (!choose || choose[row])) local_bits += -log2f(lk);
     }
     if (bit_sum) {
 #pragma unroll
@@ -373,7 +380,9 @@ extern "C" int cgs_eb_forward(const float *packed_params, int C, const float *hy
         return -2;
     }
     StageScope sc(ST_EB, static_cast<cudaStream_t>(stream), 1);
-    eb_forward_kernel<<<ew_grid((size_t)N * C), 256, C * kEbParams * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+    const int used = 256 / C * C;   // working threads per block, a multiple of C: every thread keeps one channel
+    const size_t want = ((size_t)N * C + used - 1) / used;
+    eb_forward_kernel<<<(unsigned)std::min<size_t>(want, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         packed_params, C, hyper, noise, N, hyper_q, likelihood, choose, bit_sum);
     return check_launch(__func__);
 }

@@ -15,6 +15,7 @@
 //
 // Forward activations are recomputed per tile; weight gradients live in registers across the tiles of
 // a persistent CTA.  One copy of each weight matrix (odd leading dimension) serves W and W^T.
+#include "entropy_math.cuh"
 #include "mlp_tile.cuh"
 
 namespace cgs {
@@ -363,7 +364,7 @@ __device__ __forceinline__ float eb_logits_backward(const float *__restrict__ p,
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         l0[j] = p[j] * v + p[3 + j];
-        t0[j] = tanhf(l0[j]);
+        t0[j] = eb_tanh(l0[j]);
         a[0][j] = l0[j] + p[6 + j] * t0[j];
     }
     const float *q = p + 9;
@@ -372,7 +373,7 @@ __device__ __forceinline__ float eb_logits_backward(const float *__restrict__ p,
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             s[layer][i] = q[3 * i] * a[layer][0] + q[3 * i + 1] * a[layer][1] + q[3 * i + 2] * a[layer][2] + q[9 + i];
-            t[layer][i] = tanhf(s[layer][i]);
+            t[layer][i] = eb_tanh(s[layer][i]);
             a[layer + 1][i] = s[layer][i] + q[12 + i] * t[layer][i];
         }
         q += 15;
@@ -453,7 +454,7 @@ eb_backward_kernel(const float *__restrict__ params, int C, const float *__restr
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     l[j] = p[j] * v + p[3 + j];
-                    l[j] += p[6 + j] * tanhf(l[j]);
+                    l[j] += p[6 + j] * eb_tanh(l[j]);
                 }
                 const float *q = p + 9;
 #pragma unroll
@@ -461,7 +462,7 @@ eb_backward_kernel(const float *__restrict__ params, int C, const float *__restr
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         const float s = q[3 * i] * l[0] + q[3 * i + 1] * l[1] + q[3 * i + 2] * l[2] + q[9 + i];
-                        m[i] = s + q[12 + i] * tanhf(s);
+                        m[i] = s + q[12 + i] * eb_tanh(s);
                     }
 #pragma unroll
                     for (int i = 0; i < 3; ++i) l[i] = m[i];
