@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                 const float x_mean = cd.grp == 0 ? A.feat_mean : (cd.grp == 1 ? A.scaling_mean : A.offset_mean);
                 float *dst = (cd.grp == 0 ? A.feat_q : (cd.grp == 1 ? A.scaling_q : A.offsets_q)) + o * cd.dim + cd.k0;
                 float acc = 0.f, xq_even = 0.f;
+                float2 nz2 = make_float2(0.f, 0.f);
                 if (prow && (chosen || !A.save_h)) {   // training: the backward reads (mean, scale) of the chosen rows only
                     // (mean, scale) of the group as 8-byte stores (every group starts on an even index and holds an even
                     // number of values; scalar stores cost one 32-byte sector transaction per value and doubled the
@@ -382,7 +383,8 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                         if (pred) continue;
                         const float x = xc[j];
                         float sym;
-                        const float xq = nz ? x + nz[cd.j0 + j] * Q : ste_round_sym(x, Q, sym);
+                        if (nz && !(j & 1)) nz2 = __ldg(reinterpret_cast<const float2 *>(nz + cd.j0 + j));   // 8-byte loads
+                        const float xq = nz ? x + ((j & 1) ? nz2.y : nz2.x) * Q : ste_round_sym(x, Q, sym);
                         if (j & 1) *reinterpret_cast<float2 *>(dst + j - 1) = make_float2(xq_even, xq);   // 8-byte stores
                         else xq_even = xq;
                         if (kSym && !nz && (cd.grp != 2 || ((mkbits >> ((cd.k0 + j) / 3)) & 1u))) {
