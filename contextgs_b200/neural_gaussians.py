@@ -60,13 +60,27 @@ def umma_b_operand(W, n_pad, k_pad):
     return lay(hi), lay(lo)
 
 
+def _mlp_params(mods):
+    """(weight, bias) of layers 0 and 2 of each `nn.Sequential(Linear, ReLU, Linear[, act])`, read from the module
+    dictionaries: this runs once per frame as a cache key, and `m[0].weight` costs a Sequential.__getitem__ plus a
+    Module.__getattr__ per access (~30 us per frame for the twelve tensors)."""
+    out = []
+    for m in mods:
+        sub = m._modules
+        for name in ("0", "2"):
+            prm = sub[name]._parameters
+            out.append(prm["weight"])
+            out.append(prm["bias"])
+    return out
+
+
 def pack_decoder_weights_umma(pc):
     """Packed block of the tcgen05 G1 kernel (layout: csrc/neural_gaussians_umma.cu `ngu::kOff*`).
     Layer-1 rows: head h (opacity, color, cov) occupies rows 56h .. 56h+49.  Layer-2 rows are placed
     where the epilogue reads them: opacity of offset k at row 8(k/5)+k%5, colour (k, c) at 4k+c,
     covariance (k, i) at 8k+i."""
     mods = (pc.get_opacity_mlp, pc.get_color_mlp, pc.get_cov_mlp)
-    params = [p for m in mods for p in (m[0].weight, m[0].bias, m[2].weight, m[2].bias)]
+    params = _mlp_params(mods)
     key = tuple((p.data_ptr(), p._version) for p in params)
     cache = _lib.object_cache(pc)
     ent = cache.get("decoder_pack_umma")

@@ -21,6 +21,26 @@ def _settings(viewpoint_camera, pipe, bg_color, scaling_modifier):
         prefiltered=False, debug=bool(getattr(pipe, "debug", False)))
 
 
+def _c_settings(viewpoint_camera, pipe, bg_color, scaling_modifier):
+    """`to_c_settings(_settings(...))`, remembered on the camera object while every input is the same object at the same
+    version (two calls per frame -- prefilter_voxel and render -- rebuild the same 51 numbers otherwise)."""
+    wvt, prj, cc = viewpoint_camera.world_view_transform, viewpoint_camera.full_proj_transform, viewpoint_camera.camera_center
+    dbg = bool(getattr(pipe, "debug", False))
+    ver = lambda t: t._version if torch.is_tensor(t) else None
+    sig = (int(viewpoint_camera.image_height), int(viewpoint_camera.image_width), float(viewpoint_camera.FoVx),
+           float(viewpoint_camera.FoVy), float(scaling_modifier), dbg, ver(wvt), ver(prj), ver(cc), ver(bg_color))
+    ent = getattr(viewpoint_camera, "_cgs_c_settings", None)
+    if (ent is not None and ent[0] == sig and ent[1] is wvt and ent[2] is prj and ent[3] is cc and ent[4] is bg_color
+            and torch.is_tensor(bg_color)):
+        return ent[5]
+    cs = to_c_settings(_settings(viewpoint_camera, pipe, bg_color, scaling_modifier))
+    try:
+        viewpoint_camera._cgs_c_settings = (sig, wvt, prj, cc, bg_color, cs)
+    except Exception:   # cameras that do not take attributes
+        pass
+    return cs
+
+
 class _FrameScratch:
     """Per-device buffers of the inference frame that never leave this module (Gaussian attributes, packed
     records, binning lists, sort workspace): allocated once, grown on demand and reused frame after frame
@@ -71,7 +91,7 @@ def _render_inference(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, vi
     L = _lib.lib()
     anchor, feat, offsets, scaling, masks, _ = select_attributes(pc, False, 0)
     N, K, dev = anchor.shape[0], pc.n_offsets, anchor.device
-    cs = to_c_settings(_settings(viewpoint_camera, pipe, bg_color, scaling_modifier))
+    cs = _c_settings(viewpoint_camera, pipe, bg_color, scaling_modifier)
     H, W = cs.image_height, cs.image_width
     if visible_mask is None:
         vis_idx, nv_dev = None, None
@@ -107,9 +127,6 @@ def _render_inference(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, vi
             sc.g1_ws.numel(), sc.r_cap, _lib.ptr(color), _lib.ptr(radii), _lib.ptr(sc.geom), _lib.ptr(sc.point_list),
             _lib.ptr(sc.ranges), _lib.ptr(sc.final_T), _lib.ptr(sc.n_contrib), _lib.ptr(status), _lib.ptr(sc.ws),
             sc.ws.numel(), stream), "cgs_render_anchors_forward")
-        # everything the caller gets is enqueued BEFORE the read-back, so no kernel follows the synchronisation
-        vis_filter = radii > 0
-        screenspace = torch.zeros((sc.p_cap, 3), dtype=torch.float32, device=dev)
         st = status.tolist()  # the frame's only synchronisation
         P, R = st[_lib.STATUS_NUM_GAUSSIANS], st[_lib.STATUS_NUM_RENDERED]
         if P < 0:
@@ -130,8 +147,10 @@ def _render_inference(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, vi
     radii = radii[:P]
     if P == 0:
         color.zero_()   # upstream returns an all-zero image (not the background) when there is nothing to draw
-    return {"render": color, "viewspace_points": screenspace[:P], "visibility_filter": vis_filter[:P], "radii": radii,
-            "time_sub": 0}
+    # by-products of the reference's return value, sized by the now known P: enqueued after the read-back, they run while
+    # the host prepares the next call instead of delaying this frame's completion
+    return {"render": color, "viewspace_points": torch.zeros((P, 3), dtype=torch.float32, device=dev),
+            "visibility_filter": radii > 0, "radii": radii, "time_sub": 0}
 
 
 def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, visible_mask=None, retain_grad=False, step=0):
@@ -172,7 +191,7 @@ def prefilter_voxel(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, 
     `render` picks up instead of compacting the mask again."""
     with torch.no_grad():
         L = _lib.lib()
-        cs = to_c_settings(_settings(viewpoint_camera, pipe, bg_color, scaling_modifier))
+        cs = _c_settings(viewpoint_camera, pipe, bg_color, scaling_modifier)
         means3D = pc.get_anchor.detach()
         scales = pc.get_scaling.detach()
         rot_row = pc._rotation.detach()[0]

@@ -51,3 +51,13 @@ for st in (100, 20000):
     print("  span us", round(t1 - t0), "busy us", round(sum(v[0] for v in agg.values())), "kernels", len(evs))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:22]:
         print(f"   {v[0]:10.1f} us  x{v[1]:4d}  {k}")
+    ks = sorted(evs, key=lambda e: e.time_range.start)
+    gaps = []
+    for a, b in zip(ks, ks[1:]):
+        g = b.time_range.start - a.time_range.end
+        if g > 25:
+            gaps.append((g, a.time_range.end - t0, a.name[:50], b.name[:50]))
+    print("  largest gaps (us, at, after kernel, before kernel); total of gaps > 25 us:", round(sum(g[0] for g in gaps)))
+    for g in sorted(gaps, reverse=True)[:18]:
+        print(f"   {g[0]:8.1f} at {g[1]:9.1f}  {g[2]}  ->  {g[3]}")
+
