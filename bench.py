@@ -284,6 +284,7 @@ def main():
                          "the CPU oracle arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
@@ -456,7 +457,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": cam_bytes,
-                "d2h_bytes_per_step": 3 * H * W * 4, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": 3 * H * W * 4, "ms_per_step": ms_e2e / args.steps,
+                "host_numa_node_rank0": numa_node},
         "gpu_launches": int(launches_total), "clocks": clocks, "roofline": roofline,
         "stage_ms_per_frame": {k: round(v, 4) for k, v in sorted(per_frame.items(), key=lambda kv: -kv[1])},
         "roofline_stages": stage_table, "counts": counts,
@@ -697,6 +699,31 @@ def extras(args, pc, pc_train, cams_dev, my_cam, pipe, bg, timed, world, dev):
                           "what estimate_final_bits sums, gaussian_model.py:1685) / wall time of the full 3-level "
                           "scoring pass; first figure rebuilds the level division every call like the reference")
     return ex
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run this process (and, by first touch, place its pinned host buffers) on the NUMA node the GPU
+    hangs off -- the end-to-end pass moves 25 MB per frame per rank to host memory, and a buffer on the other socket costs
+    inter-socket bandwidth that eight ranks share.  Returns the node, or None when the topology cannot be read."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
 
 
 def parity_block(args, scene, dec, cams_cpu, pc, pc_train, cam_dev, pipe, bg, dev):

@@ -27,13 +27,20 @@ from .encodings import Q_anchor, Quantize_anchor
 # Level rows per independently coded chunk of a feat stream (the reference: 1000 anchors, coded one after the
 # other on the host).  One GPU thread codes one chunk and the kernel time is the serial latency of one coder, so
 # the chunk size sets the speed: 8 rows = 400 feat symbols give ~190 k concurrent coders per million anchors.
-# Side information per chunk: a 16-bit length (+ the coder's 5 flush bytes), ~1 % of a 700-byte chunk; the
-# alphabet bounds are per (level, attribute) stream.  Streams with fewer values per row use more rows per chunk.
+# Side information per chunk: a 16-bit length (+ the coder's single termination byte); the alphabet bounds are per
+# (level, attribute) stream.  Streams with fewer values per row use more rows per chunk.
 CHUNK_ROWS = 8
 ATTRS = (("feat", 50), ("scaling", 6), ("offsets", 30))
-ATTR_CHUNK_MULT = (1, 8, 2)     # rows per chunk = CHUNK_ROWS * mult: ~1600 / 1536 / 1920 symbols per chunk
+ATTR_CHUNK_MULT = (1, 8, 2)     # rows per chunk = CHUNK_ROWS * mult: 400 / 384 / 480 symbols per chunk
 TABLE_CHUNK_MULT = 4            # hyper (12 per row) and mask (10 per row) streams: 32 rows per chunk
 PARAM_LD = 176
+# A level with few rows has few chunks, i.e. few coder threads, and then the SERIAL length of a chunk is the whole kernel
+# time (decode of the 60 k-row coarsest level of a 1.5 M-anchor model: 12 k threads walking 400 symbols each took as long
+# as the 1.2 M-row level).  Levels therefore halve their chunk rows until they have MIN_FEAT_CHUNKS feat chunks (or reach
+# MIN_CHUNK_ROWS); the rows actually used travel with the level (`chunk_rows` of its entry, `meta.b`).  A chunk costs 3
+# bytes of side information (16-bit length + the coder's single termination byte).
+MIN_FEAT_CHUNKS = 100_000
+MIN_CHUNK_ROWS = 2
 
 
 def dequantize_anchor(q, x_bound_min, x_bound_max):
@@ -73,6 +80,14 @@ def phi_table():
     _lib.check(_lib.lib().cgs_codec_phi_table(T.ctypes.data_as(ctypes.c_void_p), T.size, ctypes.byref(z0), ctypes.byref(inv_h)),
                "cgs_codec_phi_table")
     return T, float(z0.value), float(inv_h.value)
+
+
+def level_chunk_rows(n_rows, chunk_rows, adaptive=True):
+    """Rows per chunk of the (feat, scaling, offsets) streams of a level with `n_rows` rows."""
+    rows = int(chunk_rows)
+    while adaptive and rows > MIN_CHUNK_ROWS and rows % 2 == 0 and n_rows // rows < MIN_FEAT_CHUNKS:
+        rows //= 2
+    return [rows * m for m in ATTR_CHUNK_MULT]
 
 
 def _offsets(lens):
@@ -184,10 +199,12 @@ def _level_params(pc, lv, anchor, hyper_q, feat, scaling, offsets, masks, feat_q
 
 
 @torch.no_grad()
-def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1, estimate_bits=True):
+def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1, estimate_bits=True, adaptive_chunks=True):
     """Encode every valid anchor of `pc`.  Returns a SimpleNamespace with the byte streams (CUDA uint8 tensors),
     the metadata the decoder needs, the quantised tensors that were coded (for parity checks) and the
     estimated bits of the same pass.
+    chunk_rows: level rows per feat chunk (scaling / offsets: ATTR_CHUNK_MULT times as many); with adaptive_chunks small
+    levels use fewer (level_chunk_rows).
     estimate_bits=False skips the entropy estimate (`estimated_bits` is then None): the reference's conduct_encoding only
     reports the sizes of the streams it wrote, and the estimate (two erf and a log per value) costs about as much as
     predicting the level.
@@ -241,14 +258,14 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1, estimate_bits=True)
     sums = torch.zeros(16, dtype=torch.float64, device=dev)
     terr = torch.zeros(1, dtype=torch.int32, device=dev)
     means = global_means(pc)
-    rows3 = (ctypes.c_int * 3)(*[chunk_rows * m for m in ATTR_CHUNK_MULT])
     no_rows = None if estimate_bits else torch.zeros(N, dtype=torch.uint8, device=dev)
     levels, pending = [], []
     for li, lv in enumerate(plan.levels):
-        entry = SimpleNamespace(level=lv.level, n=lv.n, streams={})
+        entry = SimpleNamespace(level=lv.level, n=lv.n, streams={}, chunk_rows=level_chunk_rows(lv.n, chunk_rows, adaptive_chunks))
         levels.append(entry)
         if lv.n == 0:
             continue
+        rows3 = (ctypes.c_int * 3)(*entry.chunk_rows)
         minmax = torch.empty(6, dtype=torch.int32, device=dev)
         params = _level_params(pc, lv, anchor, hyper_q, feat, scaling, offsets, masks, feat_q, scaling_q, offsets_q,
                                sums[4 * li:4 * li + 4], terr, means, False, minmax, no_rows)
@@ -264,7 +281,7 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1, estimate_bits=True)
                                                   _lib.stream_ptr()), "cgs_codec_gauss_level_encode")
         off = _offsets(lens)
         bounds = [counts[0], counts[0] + counts[1], counts[0] + counts[1] + counts[2]]
-        pending.append((entry, lv.n, scratch, lens, off, counts, minmax, off[bounds]))
+        pending.append((entry, lv.n, scratch, lens, off, counts, minmax, off[bounds], rows3))
 
     # ONE read-back for everything the host needs: error flags, stream sizes (to allocate the packed byte strings),
     # P(mask), the estimated bits
@@ -281,7 +298,8 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1, estimate_bits=True)
     p1 = float(host[4:5].view(torch.float64)[0])
     s = host[5:21].view(torch.float64).tolist()
     mask_bytes, hyper_bytes = _table_pack(mask_pending, mask_total), _table_pack(hyper_pending, hyper_total)
-    for (entry, n, scratch, lens, off, counts, minmax, _), ends in zip(pending, host[21:].reshape(len(pending), 3).tolist()):
+    for (entry, n, scratch, lens, off, counts, minmax, _, rows3), ends in zip(pending,
+                                                                              host[21:].reshape(len(pending), 3).tolist()):
         packed = torch.empty(max(ends[2], 1), dtype=torch.uint8, device=dev)
         _lib.check(L.cgs_codec_gauss_level_pack(n, rows3, _lib.ptr(scratch), _lib.ptr(lens), _lib.ptr(off), _lib.ptr(packed),
                                                 _lib.stream_ptr()), "cgs_codec_gauss_level_pack")
@@ -347,10 +365,10 @@ def decode_model(pc, meta, anchor_q, mask_bytes, mask_lens, hyper_bytes, hyper_l
     sums = torch.zeros(16, dtype=torch.float64, device=dev)
     terr = torch.zeros(1, dtype=torch.int32, device=dev)
     means = tuple(meta["means"])
-    rows3 = (ctypes.c_int * 3)(*[chunk_rows * m for m in ATTR_CHUNK_MULT])
     for li, (lv, coded) in enumerate(zip(plan.levels, levels)):
         if lv.n == 0:
             continue
+        rows3 = (ctypes.c_int * 3)(*(getattr(coded, "chunk_rows", None) or level_chunk_rows(lv.n, chunk_rows, False)))
         params = _level_params(pc, lv, anchor, hyper_ctx, None, None, None, None, feat_q, scaling_q, offsets_q,
                                sums[4 * li:4 * li + 4], terr, means, True)
         st = [coded.streams[name] for name, _ in ATTRS]
@@ -393,7 +411,7 @@ def conduct_encoding(pc, pre_path_name, chunk_rows=CHUNK_ROWS):
     wr("hyper.b", enc.hyper_bytes)
     side = dict(mask_lens=enc.mask_lens.cpu().to(torch.int16), hyper_lens=enc.hyper_lens.cpu().to(torch.int16), levels=[])
     for lv in enc.levels:
-        ent = dict(level=lv.level, n=lv.n, streams={})
+        ent = dict(level=lv.level, n=lv.n, streams={}, chunk_rows=list(lv.chunk_rows))
         for name, st in lv.streams.items():
             wr(f"{name}{lv.level}.b", st.bytes)
             ent["streams"][name] = dict(lens=st.lens.cpu().to(torch.int16), minmax=st.minmax.cpu())
@@ -420,7 +438,7 @@ def conduct_decoding(pc, pre_path_name):
     anchor_q = torch.from_numpy(np.load(os.path.join(pre_path_name, "anchor.npy")).astype(np.int32)).to(dev)
     levels = []
     for ent in side["levels"]:
-        lv = SimpleNamespace(level=ent["level"], n=ent["n"], streams={})
+        lv = SimpleNamespace(level=ent["level"], n=ent["n"], streams={}, chunk_rows=ent.get("chunk_rows"))
         for name, st in ent["streams"].items():
             lv.streams[name] = SimpleNamespace(bytes=rd(f"{name}{ent['level']}.b"), lens=u16(st["lens"]), minmax=st["minmax"])
         levels.append(lv)

@@ -29,9 +29,10 @@ namespace codec {
 constexpr uint32_t kTopValue = 1u << 24;
 constexpr int kTotalBits = 16;
 
-// Encoder.  The byte string is the classic carry-propagating range coder's (one leading zero byte, then the digits of
-// the final code value, then the four bytes of `low`): the same bytes oracle/codec_ref.py produces with the cached-byte
-// formulation.  Here the 0 / 1 / 2 bytes a symbol shifts out of `low` are appended to a 64-bit register of pending bytes
+// Encoder.  The byte string is the classic carry-propagating range coder's digits of the final code value -- without the
+// always-zero leading byte, and terminated by ONE byte: the coder ends on V = low rounded up to a multiple of 2^24 (inside
+// [low, low + range) because range >= 2^24) and V's three low bytes are zeros the decoder supplies itself.  The same bytes
+// come out of oracle/codec_ref.py's cached-byte formulation.  Here the 0 / 1 / 2 bytes a symbol shifts out of `low` are appended to a 64-bit register of pending bytes
 // without a loop, and stored 32 bits at a time; a carry out of `low` is an increment of that register and only ripples into
 // memory when every pending byte is 0xff.
 struct Encoder {
@@ -43,7 +44,7 @@ struct Encoder {
 
     __device__ void init(uint32_t *o, uint32_t capacity)
     {
-        low = 0; range = 0xffffffffu; out = o; pos = 1; stored = 0; cap = capacity; acc = 0; overflow = false;   // pos 1: the leading zero
+        low = 0; range = 0xffffffffu; out = o; pos = 0; stored = 0; cap = capacity; acc = 0; overflow = false;
     }
     __device__ __forceinline__ void append(uint32_t bytes, uint32_t nb)   // nb <= 2
     {
@@ -84,8 +85,9 @@ struct Encoder {
     }
     __device__ uint32_t finish()
     {
-        append(low >> 16, 2);
-        append(low & 0xffffu, 2);
+        const uint32_t t = low + 0x00ffffffu;   // round up to a multiple of 2^24
+        if (t < low) carry();
+        append(t >> 24, 1);
         const uint32_t n = pos, cnt = pos - stored;
         if (cnt) {   // flush the partial word (padding is not counted)
             if (stored + 4u <= cap) out[stored >> 2] = __byte_perm((uint32_t)(acc << (8 * (4u - cnt))), 0, 0x0123);
@@ -123,7 +125,7 @@ struct Decoder {
         cur = fetch(0);
         nxt = fetch(1);
         code = 0; range = 0xffffffffu;
-        for (int i = 0; i < 5; ++i) code = (code << 8) | next();
+        for (int i = 0; i < 4; ++i) code = (code << 8) | next();
     }
     __device__ __forceinline__ uint32_t target()
     {

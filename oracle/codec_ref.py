@@ -13,14 +13,18 @@ MASK32 = 0xFFFFFFFF
 def encode(symbols, table_of, tables):
     """symbols: ints; table_of(i) -> table index of the i-th symbol; tables[t]: cumulative 16-bit frequencies."""
     low, rng, cache, cache_size, out = 0, MASK32, 0, 1, bytearray()
+    first = True   # the byte cached at the start is always zero (the code value is < 1) and is not transmitted
 
     def shift_low():
-        nonlocal low, cache, cache_size
+        nonlocal low, cache, cache_size, first
         if (low & MASK32) < 0xFF000000 or (low >> 32) != 0:
             carry = (low >> 32) & 0xFF
             temp = cache
             while True:
-                out.append((temp + carry) & 0xFF)
+                if first:
+                    first = False
+                else:
+                    out.append((temp + carry) & 0xFF)
                 temp = 0xFF
                 cache_size -= 1
                 if cache_size == 0:
@@ -38,8 +42,11 @@ def encode(symbols, table_of, tables):
         while rng < TOP:
             rng = (rng << 8) & MASK32
             shift_low()
-    for _ in range(5):
-        shift_low()
+    # termination: the smallest multiple of 2^24 that is >= low lies inside [low, low + range) (range >= 2^24); only its top
+    # byte is written, the decoder reads zeros past the end of the stream
+    low = (low + 0x00FFFFFF) & ~0x00FFFFFF
+    shift_low()
+    shift_low()
     return bytes(out)
 
 
@@ -52,7 +59,7 @@ def decode(data, n, table_of, tables):
         pos += 1
         return b
 
-    for _ in range(5):
+    for _ in range(4):
         code = ((code << 8) | nxt()) & MASK32
     out = []
     for i in range(n):

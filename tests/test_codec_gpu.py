@@ -28,10 +28,12 @@ def _model(N=6000, seed=11, kind="chair"):
     return pc
 
 
-@pytest.mark.parametrize("N,chunk", [(6000, 32), (1500, 64), (300, 1000)])
-def test_encode_decode_round_trip_is_bit_exact(N, chunk):
+@pytest.mark.parametrize("N,chunk,adaptive", [(6000, 32, False), (1500, 64, False), (300, 1000, False), (6000, 8, True)])
+def test_encode_decode_round_trip_is_bit_exact(N, chunk, adaptive):
     pc = _model(N)
-    enc = codec.encode_model(pc, chunk_rows=chunk)
+    enc = codec.encode_model(pc, chunk_rows=chunk, adaptive_chunks=adaptive)
+    rows = [lv.chunk_rows[0] for lv in enc.levels]
+    assert rows == ([codec.MIN_CHUNK_ROWS] * 3 if adaptive else [chunk] * 3)   # small levels: short chunks
     q = enc.quantised
     # the coded values are what the scoring pass quantises (same kernels): feat_q etc. of multi_scale_generating
     sel = pc.get_mask_anchor
@@ -68,10 +70,13 @@ def test_quantised_values_equal_the_scoring_pass_and_sizes_match_estimates():
     assert torch.allclose(a, t(pc.get_anchor), atol=0, rtol=0)
     bits = codec.encoded_bits(enc)
     est = dict(hyper=res[1], feat=res[2], scaling=res[3], offsets=res[4], masks=res[5])
+    chunks = dict(hyper=enc.hyper_lens.numel(), masks=enc.mask_lens.numel(),
+                  **{k: sum(lv.streams[k].lens.numel() for lv in enc.levels if lv.streams) for k in ("feat", "scaling", "offsets")})
     for k in ("feat", "scaling", "offsets", "hyper", "masks"):
         # 16-bit frequencies floor every probability at 2^-16 (the estimate floors at 1e-6 ~ 2^-20), so the real
-        # stream may be SHORTER than the estimate where the model is badly wrong; it must never be much longer
-        assert bits[k] < 1.03 * est[k] + 104 * (sum(lv.n for lv in enc.levels) // codec.CHUNK_ROWS + 8), (k, bits[k], est[k])
+        # stream may be SHORTER than the estimate where the model is badly wrong; it must never be much longer: per chunk a
+        # 16-bit length, the coder's termination byte and the rounding up to whole bytes, per stream its 64 bits of bounds
+        assert bits[k] < 1.03 * est[k] + 32 * chunks[k] + 256, (k, bits[k], est[k], chunks[k])
     assert bits["anchor"] == 48 * a.shape[0]
 
 
@@ -113,7 +118,7 @@ def test_alphabets_from_the_level_kernel_equal_the_stand_alone_pass():
 
 def test_table_streams_are_byte_identical_to_the_cpu_range_coder():
     pc = _model(700)
-    enc = codec.encode_model(pc, chunk_rows=32)
+    enc = codec.encode_model(pc, chunk_rows=32, adaptive_chunks=False)
     q = enc.quantised
     tb = codec.mask_table(enc.meta["prob_masks"])[0].tolist()
     rows = 32 * codec.TABLE_CHUNK_MULT
@@ -151,7 +156,7 @@ def test_gaussian_streams_decode_with_an_independent_table_decoder():
     want[0], want[-1] = 0.0, 1.0
     assert np.array_equal(T_np, want) and z0 == -4.75 and inv_h == float(np.float32(4096 / 9.5))
     pc = _model(700)
-    enc = codec.encode_model(pc, chunk_rows=4)
+    enc = codec.encode_model(pc, chunk_rows=4, adaptive_chunks=False)
     q = enc.quantised
     dev = q["feat"].device
     means = codec.global_means(pc)
