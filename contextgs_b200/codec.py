@@ -9,9 +9,12 @@ offsets{L}.b, meta.b, mlp.pt).  The byte format of the .b streams is this librar
 (torchac is not part of the reference tree and cannot be pinned): what is guaranteed and tested is that
 decoding returns the encoder's quantised tensors bit for bit.
 
-Everything heavy runs on the GPU: one level kernel (cgs_context_level_umma_forward_ex) produces the
-(mean, scale, Q) of every coded value, one thread per ~1600-symbol chunk range-codes it in closed form.
-The host only builds two tiny frequency tables and concatenates streams.
+Everything heavy runs on the GPU: per level one kernel (cgs_context_level_umma_forward_ex) produces the
+(mean, scale, Q) of every coded value and the alphabets of the level's three streams, a parallel pass turns every
+value into its 16-bit coding interval and one thread per <= 480-symbol chunk carries the range coder's state over
+them (cgs_codec_gauss_level_encode); decoding inverts the tabulated normal CDF per symbol
+(cgs_codec_gauss_level_decode).  The host reads back ONE block of scalars per encode (stream sizes, error flags) and
+slices the packed byte strings.
 """
 import ctypes
 import os
