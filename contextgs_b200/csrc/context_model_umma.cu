@@ -150,7 +150,8 @@ __device__ __forceinline__ ChunkDesc chunk_desc_q(int c, int q)
     return d;
 }
 
-template <int K1, bool kSym>   // kSym: also reduce the min / max coded symbol of each stream (bitstream encoder)
+// kSym: also reduce the min / max coded symbol of each stream (bitstream encoder); kNoise: training (A.noise is given)
+template <int K1, bool kSym, bool kNoise>
 __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
 {
     using LY = Layout<K1>;
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
             if (half == 0 && chosen) n_chosen += 1.f;
             float *prow = (A.params_out && o >= 0) ? A.params_out + (size_t)grow * kLdG2 : nullptr;
             if (prow && half == 0) *reinterpret_cast<float4 *>(prow + 172) = make_float4(Qf, Qs, Qo, 0.f);
-            const float *nz = A.noise ? A.noise + (size_t)grow * kCE : nullptr;
+            const float *nz = kNoise ? A.noise + (size_t)grow * kCE : nullptr;
 #pragma unroll 1
             for (int c = 0; c < 3; ++c) {
                 const ChunkDesc cd = chunk_desc_q(c, half);
@@ -349,6 +350,15 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                 for (int j = 0; j < 8; ++j) xc[j] = xn[j];
                 umma::tmem_ld8(tl + kColD2 + cd.mu_col, vm);
                 umma::tmem_ld8(tl + kColD2 + cd.sg_col, vs);
+                float nzv[kNoise ? 8 : 1];   // training noise of the chunk: in flight while the TMEM loads and the stores complete
+                if (kNoise) {
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const float2 v = (o >= 0 && j < cd.cnt) ? __ldg(reinterpret_cast<const float2 *>(nz + cd.j0 + j))
+                                                                : make_float2(0.f, 0.f);   // (rows past the level have no noise)
+                        nzv[kNoise ? j : 0] = v.x; nzv[kNoise ? j + 1 : 0] = v.y;
+                    }
+                }
                 if (c + 1 < 3) fetch_x(c + 1, xn);
                 umma::tmem_wait_ld();
                 // alphabet bounds of the level's three streams (bitstream codec): the symbols exist here anyway
@@ -358,7 +368,6 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                 const float x_mean = cd.grp == 0 ? A.feat_mean : (cd.grp == 1 ? A.scaling_mean : A.offset_mean);
                 float *dst = (cd.grp == 0 ? A.feat_q : (cd.grp == 1 ? A.scaling_q : A.offsets_q)) + o * cd.dim + cd.k0;
                 float acc = 0.f, xq_even = 0.f;
-                float2 nz2 = make_float2(0.f, 0.f);
                 if (prow && (chosen || !A.save_h)) {   // training: the backward reads (mean, scale) of the chosen rows only
                     // (mean, scale) of the group as 8-byte stores (every group starts on an even index and holds an even
                     // number of values; scalar stores cost one 32-byte sector transaction per value and doubled the
@@ -383,11 +392,10 @@ __global__ void __launch_bounds__(kThreads, 1) context_level_umma_kernel(Args A)
                         if (pred) continue;
                         const float x = xc[j];
                         float sym;
-                        if (nz && !(j & 1)) nz2 = __ldg(reinterpret_cast<const float2 *>(nz + cd.j0 + j));   // 8-byte loads
-                        const float xq = nz ? x + ((j & 1) ? nz2.y : nz2.x) * Q : ste_round_sym(x, Q, sym);
+                        const float xq = kNoise ? x + nzv[kNoise ? j : 0] * Q : ste_round_sym(x, Q, sym);
                         if (j & 1) *reinterpret_cast<float2 *>(dst + j - 1) = make_float2(xq_even, xq);   // 8-byte stores
                         else xq_even = xq;
-                        if (kSym && !nz && (cd.grp != 2 || ((mkbits >> ((cd.k0 + j) / 3)) & 1u))) {
+                        if (kSym && !kNoise && (cd.grp != 2 || ((mkbits >> ((cd.k0 + j) / 3)) & 1u))) {
                             sym_lo = fminf(sym_lo, sym);
                             sym_hi = fmaxf(sym_hi, sym);
                         }
@@ -462,8 +470,9 @@ static int launch(const Args &a, cudaStream_t st)
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(context_level_umma_kernel<K1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
-        cudaFuncSetAttribute(context_level_umma_kernel<K1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
+        cudaFuncSetAttribute(context_level_umma_kernel<K1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
+        cudaFuncSetAttribute(context_level_umma_kernel<K1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
+        cudaFuncSetAttribute(context_level_umma_kernel<K1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM));
         if (sm_count <= 0) sm_count = kNumSMs;
     }
     // the per-anchor attributes are read and written two floats at a time
@@ -477,8 +486,9 @@ static int launch(const Args &a, cudaStream_t st)
     const int tiles = (a.n_rows + kRows - 1) / kRows;
     const int grid = tiles < sm_count ? tiles : sm_count;
     StageScope sc(ST_CTX_LEVEL, st, 1);
-    if (a.symbol_minmax) context_level_umma_kernel<K1, true><<<grid, kThreads, sizeof(SM), st>>>(a);
-    else context_level_umma_kernel<K1, false><<<grid, kThreads, sizeof(SM), st>>>(a);
+    if (a.noise) context_level_umma_kernel<K1, false, true><<<grid, kThreads, sizeof(SM), st>>>(a);   // (training has no alphabets)
+    else if (a.symbol_minmax) context_level_umma_kernel<K1, true, false><<<grid, kThreads, sizeof(SM), st>>>(a);
+    else context_level_umma_kernel<K1, false, false><<<grid, kThreads, sizeof(SM), st>>>(a);
     return check_launch("cgs_context_level_umma_forward");
 }
 }  // namespace cmu
