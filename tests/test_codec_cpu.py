@@ -29,3 +29,27 @@ def test_range_coder_restatement_round_trips():
         assert codec_ref.decode(data, n, lambda i: i % 2, tables) == syms
         if n == 5000:   # close to the entropy of the source (0.47 + 1.58 bits per pair)
             assert len(data) * 8 < 1.05 * n / 2 * (0.469 + 1.58) + 64
+
+
+def test_phi_table_is_the_documented_function():
+    """Host-only entry point: the coder's tabulated normal CDF is fp32(0.5 erfc(-z / sqrt 2)) on 4097 points of
+    [-4.75, 4.75] with exact end points, as include/contextgs_b200.h documents (no GPU involved)."""
+    import math
+    import numpy as np
+    from contextgs_b200 import codec
+    T, z0, inv_h = codec.phi_table()
+    want = np.array([0.5 * math.erfc(-(-4.75 + 9.5 * j / 4096) / math.sqrt(2.0)) for j in range(4097)]).astype(np.float32)
+    want[0], want[-1] = 0.0, 1.0
+    assert np.array_equal(T, want)
+    assert z0 == -4.75 and inv_h == float(np.float32(4096 / 9.5))
+    assert np.all(np.diff(T) >= 0) and abs(float(T[2048]) - 0.5) < 1e-7
+
+
+def test_small_levels_get_short_chunks():
+    from contextgs_b200 import codec
+    mult = list(codec.ATTR_CHUNK_MULT)
+    assert codec.level_chunk_rows(1_212_902, 8) == [8 * m for m in mult]          # enough chunks already
+    assert codec.level_chunk_rows(227_251, 8) == [2 * m for m in mult]            # halved until 100 k feat chunks
+    assert codec.level_chunk_rows(59_847, 8) == [codec.MIN_CHUNK_ROWS * m for m in mult]
+    assert codec.level_chunk_rows(59_847, 8, adaptive=False) == [8 * m for m in mult]
+    assert codec.level_chunk_rows(10, 1000) == [125 * m for m in mult]            # stops when the row count turns odd
