@@ -215,12 +215,13 @@ class GaussianModel(DensifyMixin, nn.Module):
         G2); here it is evaluated once per version of `_mask`.  The entry holds the parameter object itself, so "same
         object, same version" cannot be confused by a new tensor that reuses the address."""
         ent = self.__dict__.get("_cgs_mask_state")
-        if ent is None or ent[0] is not self._mask or ent[1] != self._mask._version:
+        if (ent is None or ent[0] is not self._mask or ent[1] != self._mask._version
+                or ent[5] != self._mask.data_ptr()):   # (`p.data = t` swaps the storage without a version bump)
             with torch.no_grad():
                 mask_sig = torch.sigmoid(self._mask)
                 mask = ((mask_sig > 0.01).float() - mask_sig) + mask_sig
                 valid = torch.sum(mask, dim=1)[:, 0] > 0
-            ent = [self._mask, self._mask._version, mask, valid, None]
+            ent = [self._mask, self._mask._version, mask, valid, None, self._mask.data_ptr()]
             self.__dict__["_cgs_mask_state"] = ent
         return ent
 
