@@ -436,11 +436,13 @@ __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 }  // namespace ngwu
 
+static int g_wgrad_dbg = 0;
+
 __global__ void __launch_bounds__(ngwu::kThreads, 1)
 neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, const float *__restrict__ anchor,
                                    const float *__restrict__ feat, float cx, float cy, float cz,
                                    const float *__restrict__ save_h, const float *__restrict__ d_out,
-                                   const float *__restrict__ d_pre, float *__restrict__ d_w, int32_t *__restrict__ err)
+                                   const float *__restrict__ d_pre, float *__restrict__ d_w, int32_t *__restrict__ err, int dbg)
 {
     using namespace ngwu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -475,8 +477,8 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
             // ONE elected lane issues every copy of the slab with warp-uniform operands (per-lane copies make the compiler
             // serialise the lanes through a vote / BRA.U.ANY loop around each UBLKCP)
             if (umma::elect_one_sync()) {
-                mbar_expect_tx(&S.full[b], (uint32_t)rows * (kBytesO + 2u * kBytesH));
-                for (int r = 0; r < rows; ++r) {
+                mbar_expect_tx(&S.full[b], (dbg & 4) ? 0u : (uint32_t)rows * (kBytesO + 2u * kBytesH));
+                for (int r = 0; r < rows && !(dbg & 4); ++r) {
                     const size_t g = (size_t)(row0 + r);
                     bulk_g2s(S.raw[b].o + r * kRawO, d_out + g * 144, kBytesO, &S.full[b]);
                     bulk_g2s(S.raw[b].h + r * kRawH, save_h + g * 176, kBytesH, &S.full[b]);
@@ -497,7 +499,7 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
                 };
                 const uint32_t acc0 = it > 0 ? 1u : 0u;
 #pragma unroll
-                for (int s = 0; s < kSlab / 8; ++s) {
+                for (int s = 0; s < kSlab / 8 && !(dbg & 1); ++s) {
                     const uint32_t acc = (s > 0) ? 1u : acc0;
                     const int og[3] = {0, 4, 16};
                     const uint32_t dcol[3] = {kColDo, kColDc, kColDv};
@@ -576,7 +578,7 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
                 umma::fence_after_thread_sync();
             }
             // X (prefetched one slab ahead), then the next slab's X starts travelling
-            if (xthread) store_item(B, xr, xc, xv);
+            if (xthread && !(dbg & 2)) store_item(B, xr, xc, xv);
             load_x(a1, xv);
             a1 = a2;
             load_idx(it + 3, a2);
@@ -601,7 +603,7 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
                         v = *reinterpret_cast<const float2 *>(R.o + r * kRawO + 2 * (c - kPO));
                     }
                 }
-                store_item(B, r, c, v);
+                if (!(dbg & 2)) store_item(B, r, c, v);
             }
             umma::fence_proxy_async_smem();
             umma::fence_before_thread_sync();
@@ -674,12 +676,13 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
 
 using namespace cgs;
 
-static int g_wgrad_desc_variant = 0;
-
-/* diagnostic switches: key 0 = descriptor variant of the weight-gradient kernel's MN-major operands (0 / 1) */
+/* diagnostic switches (timing experiments only: results are wrong when set): key 1 = weight-gradient kernel of G1,
+ * bit 0 skips the tcgen05.mma instructions, bit 1 the converters' hi / lo stores, bit 2 the bulk copies
+ * (scripts/wgrad_probe.py: with all three skipped the kernel still takes 0.66 of its 0.95 ms -- it is bound by the
+ * converters' instruction stream, index arithmetic + LDS + split, not by MMA issue, TMA issue or operand buffers) */
 extern "C" int cgs_debug_set(int key, int value)
 {
-    if (key == 0) { g_wgrad_desc_variant = value ? 1 : 0; return 0; }
+    if (key == 1) { g_wgrad_dbg = value; return 0; }
     return -1;
 }
 
@@ -747,7 +750,7 @@ extern "C" int cgs_neural_gaussians_backward_umma(const float *packed_bwd, const
         const int grid = slabs < sm_count ? slabs : sm_count;
         neural_gaussians_wgrad_umma_kernel<<<grid, ngwu::kThreads, sizeof(ngwu::Smem), st>>>(
             vis_idx, Nv, anchor, feat, campos_host[0], campos_host[1], campos_host[2], save_h, scratch_dout, scratch_dpre,
-            d_packed_fwd, err);
+            d_packed_fwd, err, g_wgrad_dbg);
     }
     return check_launch(__func__);
 }

@@ -238,7 +238,9 @@ CGS_API int cgs_neural_gaussians_umma_forward_train(const float *packed_weights,
  * pack_decoder_weights_bwd_umma).  scratch_dout[Nv,144], scratch_dpre[Nv,176]: hand-over between the two kernels.
  * *err (device, caller-zeroed) is set to 1 if a tensor-core completion barrier timed out. */
 CGS_API int cgs_neural_gaussians_bwd_umma_packed_floats(void);
-/* Diagnostic switches (tests only).  key 0: descriptor variant (0 / 1) of the weight-gradient kernel's MN-major operands. */
+/* Diagnostic switches for timing experiments (results are WRONG while one is set; scripts/wgrad_probe.py).  key 1: the G1
+ * weight-gradient kernel skips its tcgen05.mma instructions (bit 0), the converters' operand stores (bit 1), the bulk
+ * copies (bit 2).  Returns -1 for an unknown key. */
 CGS_API int cgs_debug_set(int key, int value);
 CGS_API int cgs_neural_gaussians_backward_umma(const float *packed_bwd, const int32_t *vis_idx, int Nv,
                                                const float *anchor, const float *feat, const float *offsets,
