@@ -388,7 +388,9 @@ neural_gaussians_dgrad_umma_kernel(const float *__restrict__ packed_w, const int
 //     bytes, is gathered through the visible-anchor list straight from HBM, one slab ahead);
 //   * one extra warp issues the bulk copies and the tcgen05.mma (named barriers: converters only ARRIVE, never wait for it).
 namespace ngwu {
-constexpr int kConv = 512, kThreads = kConv + 32, kSlab = 8, kStages = 8;   // 8 rows = one K step per slab; 8 slabs in flight
+// 8 rows = one K step per slab; 8 slabs of raw rows in flight; 2 operand buffers (a third one, a second MMA-issuing warp and
+// bulk copies issued from two warps were each measured at +-0.5 %: scripts/wgrad_probe.py)
+constexpr int kConv = 512, kThreads = kConv + 32, kSlab = 8, kStages = 8, kBufs = 2;
 constexpr int kGX = 14, kGO = 36, kGH = 44, kGP = 44, kGroups = kGX + kGO + kGH + kGP;   // float4 groups per row: 138
 constexpr int kOffX = 0, kOffO = kGX, kOffH = kOffO + kGO, kOffP = kOffH + kGH;
 constexpr int kLd = 4 * kGroups + 1;      // 553 features per 4-row chunk: = 1 (mod 8) spreads the chunks over the banks
@@ -413,11 +415,11 @@ struct Raw {
     float p[kSlab * kRawP];
 };
 struct Smem {
-    Buf buf[2];
+    Buf buf[kBufs];
     Raw raw[kStages];
     uint32_t tmem;
     int timeout;
-    alignas(8) uint64_t mma_done[2];       // the MMAs that read buf[b] have completed
+    alignas(8) uint64_t mma_done[kBufs];   // the MMAs that read buf[b] have completed
     alignas(8) uint64_t full[kStages];     // the bulk copies into raw[stage] have landed
 };
 
@@ -454,7 +456,7 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
 
     if (warp == 0) umma::tmem_alloc(&S.tmem, kTmemCols);
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) umma::mbar_init(&S.mma_done[i], 1);
+        for (int i = 0; i < kBufs; ++i) umma::mbar_init(&S.mma_done[i], 1);
         for (int i = 0; i < kStages; ++i) umma::mbar_init(&S.full[i], 1);
         umma::fence_mbar_init();
         S.timeout = 0;
@@ -489,7 +491,7 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
         };
         for (int i = 0; i < kStages && i < n_it; ++i) stage_rows(i);
         for (int it = 0; it < n_it; ++it) {
-            const uint32_t b = (uint32_t)it & 1u;
+            const uint32_t b = (uint32_t)it % kBufs;
             named_sync(1 + (int)b, kThreads);     // the converters have written buf[b] and are done with raw[b]
             umma::fence_after_thread_sync();
             if (umma::elect_one_sync()) {
@@ -567,14 +569,14 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
         load_idx(1, a1);
         load_idx(2, a2);
         for (int it = 0; it < n_it; ++it) {
-            const uint32_t b = (uint32_t)it & 1u;
+            const uint32_t b = (uint32_t)it % kBufs;
             const int st = it % kStages;
             Buf &B = S.buf[b];
             const Raw &R = S.raw[st];
             const int row0 = ((int)blockIdx.x + it * stride) * kSlab;
-            // the MMAs that read buf[b] two slabs ago must have completed
-            if (it >= 2) {
-                if (!umma::mbar_wait(&S.mma_done[b], (uint32_t)((it >> 1) - 1) & 1u)) S.timeout = 1;
+            // the MMAs that read buf[b] kBufs slabs ago must have completed
+            if (it >= kBufs) {
+                if (!umma::mbar_wait(&S.mma_done[b], (uint32_t)(it / kBufs - 1) & 1u)) S.timeout = 1;
                 umma::fence_after_thread_sync();
             }
             // X (prefetched one slab ahead), then the next slab's X starts travelling
@@ -589,21 +591,40 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
             }
             // the staged rows of dOut / H / dPre
             if (!umma::mbar_wait(&S.full[st], (uint32_t)(it / kStages) & 1u)) S.timeout = 1;
-            for (int i = tid; i < (kPairs - kPX) * kSlab; i += kConv) {
-                const int r = i & (kSlab - 1), c = kPX + i / kSlab;
-                float2 v = make_float2(0.f, 0.f);
-                if (row0 + r < Nv) {
-                    if (c >= kPP) {
-                        v = *reinterpret_cast<const float2 *>(R.p + r * kRawP + 2 * (c - kPP));
-                    } else if (c >= kPH) {
-                        const int pi = c - kPH;
-                        v = *reinterpret_cast<const float2 *>(R.h + r * kRawH + 2 * pi);
-                        if (pi == 27 || pi == 55 || pi == 83) v.y = 1.0f;      // column 56h + 55: bias row of head h
-                    } else {
-                        v = *reinterpret_cast<const float2 *>(R.o + r * kRawO + 2 * (c - kPO));
-                    }
+            // One item = one feature of FOUR consecutive rows: four scalar reads of the staged rows (row stride = 20 banks,
+            // consecutive lanes on consecutive features: conflict free) and ONE 16-byte store each for the hi and the lo
+            // operand -- the four rows of a feature are adjacent in the K-major layout.  (A flat (row, feature-pair) item
+            // needed four scalar stores and twice the index arithmetic per value; the converters' instruction stream is
+            // what bounds this kernel, scripts/wgrad_probe.py.)
+            constexpr int kFeat = 4 * (kGroups - kGX);     // 496 staged features: dOut 144 | H 176 | dPre 176
+#pragma unroll
+            for (int k = 0; k < (kFeat * (kSlab / 4) + kConv - 1) / kConv; ++k) {
+                const int i = tid + k * kConv;
+                if (i >= kFeat * (kSlab / 4)) break;
+                const int q = i >= kFeat ? 1 : 0, f = i - q * kFeat;     // (kSlab / 4 == 2 row quads)
+                const float *src;
+                int ldr;
+                float one = 0.f;                                          // columns 56h + 55 of H: bias rows of the heads
+                if (f < 4 * kGO) { src = R.o + f; ldr = kRawO; }
+                else if (f < 4 * (kGO + kGH)) {
+                    const int fh = f - 4 * kGO;
+                    src = R.h + fh; ldr = kRawH;
+                    one = (fh == 55 || fh == 111 || fh == 167) ? 1.0f : 0.f;
+                } else { src = R.p + (f - 4 * (kGO + kGH)); ldr = kRawP; }
+                float v[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int row = 4 * q + r;
+                    v[r] = row0 + row < Nv ? (one != 0.f ? 1.0f : src[row * ldr]) : 0.f;
                 }
-                if (!(dbg & 2)) store_item(B, r, c, v);
+                if (!(dbg & 2)) {
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) umma::split_tf32(v[r], h[r], l[r]);
+                    const int dst = (q * kLd + 4 * kGX + f) * 4;
+                    *reinterpret_cast<uint4 *>(B.hi + dst) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4 *>(B.lo + dst) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
             }
             umma::fence_proxy_async_smem();
             umma::fence_before_thread_sync();
@@ -611,13 +632,9 @@ neural_gaussians_wgrad_umma_kernel(const int *__restrict__ vis_idx, int Nv, cons
         }
     }
     // ---- drain: the last commit of each buffer covers every earlier MMA (commits complete in order) ----------------
-    if (n_it >= 1) {
-        const uint32_t last = (uint32_t)n_it - 1, bl = last & 1u;
-        if (!umma::mbar_wait(&S.mma_done[bl], (last >> 1) & 1u)) S.timeout = 1;
-        if (n_it >= 2) {
-            const uint32_t prev = (uint32_t)n_it - 2, bp = prev & 1u;
-            if (!umma::mbar_wait(&S.mma_done[bp], (prev >> 1) & 1u)) S.timeout = 1;
-        }
+    for (int k = 0; k < kBufs && k < n_it; ++k) {
+        const uint32_t idx = (uint32_t)(n_it - 1 - k);
+        if (!umma::mbar_wait(&S.mma_done[idx % kBufs], (idx / kBufs) & 1u)) S.timeout = 1;
     }
     umma::fence_after_thread_sync();
 
