@@ -50,12 +50,18 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--anchors", type=int, default=N_ANCHORS)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4],
+                    help="BASELINE.json configs index: 2 = the headline workload (1.5 M anchors), 4 = the data-parallel "
+                         "training shape (2 M anchors, one camera per rank); sets --anchors unless given explicitly")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the full-size GPU-vs-oracle comparison")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-Python-on-CUDA baseline extras")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="time budget of the reference arm")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.config == 4 and args.anchors == N_ANCHORS:
+        args.anchors = 2_000_000
+    return args
 
 
 # ------------------------------------------------------------------------------------ helpers
@@ -260,7 +266,7 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args):
-    return {"workload": f"BASELINE configs[2]: mipnerf360/bicycle-shaped synthetic scene, {args.anchors} anchors x 10 "
+    return {"workload": f"BASELINE configs[{args.config}]: mipnerf360/bicycle-shaped synthetic scene, {args.anchors} anchors x 10 "
                         "offsets, 1920x1080, decoded model, per frame prefilter_voxel + generate_neural_gaussians + "
                         "rasterize forward; camera batch sharded over ranks",
             "anchors": args.anchors, "image": [1920, 1080], "cameras": N_CAMERAS, "gaussian_scale": GAUSSIAN_SCALE,
