@@ -371,8 +371,9 @@ class _ContextModelTrain(torch.autograd.Function):
                 noise = dict(noise, levels=lv_noise)
         out = _forward_levels(pc, plan, anchor, hyper, feat, scaling, offsets, masks, choose_u8, noise, True,
                               return_details, save=(bwd_impl == "umma"))
-        s = out["sums"].tolist()  # the one host read-back of the forward
-        out["sums_host"] = s
+        s = (out["sums"] if rate is None else torch.cat([out["sums"], rate])).tolist()  # the one host read-back of the forward
+        rate = 1.0 if rate is None else s.pop() / info["rate_den"]
+        out["sums_host"], out["rate"] = s, rate
         info.update(out)
         n_chosen = sum(s[4 * i + 3] for i in range(3))
         total_bits = sum(s[4 * i + c] for i in range(3) for c in range(3)) + s[12]
@@ -503,11 +504,14 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
         choose = choose & owned
     choose_u8 = choose.contiguous().view(torch.uint8)
 
-    rate = float(mask_anchor_bool.sum()) / mask_anchor_bool.numel() if mask_anchor_bool is not None else 1.0
+    # mask_anchor_rate of the reference (scene/gaussian_model.py:1660): the count stays on the device and reaches the host with
+    # the bit sums (one read-back instead of two)
+    rate = mask_anchor_bool.sum(dtype=torch.float64).view(1) if mask_anchor_bool is not None else None
+    rate_den = mask_anchor_bool.numel() if mask_anchor_bool is not None else 1
     differentiable = (training and predict_bpp and not return_sum_bits and not sharded and torch.is_grad_enabled()
                       and any(t.requires_grad for t in (hyper, feat, grid_offsets, grid_scaling, binary_grid_masks,
                                                         *pc.get_grid_mlp.parameters())))
-    info = {}
+    info = {"rate_den": rate_den}
     if differentiable:
         wb = [pack_grid_weights_bwd(pc.get_grid_mlp[lv.level]) for lv in plan.levels]
         feat_q, scaling_q, offsets_q, per_param_t = _ContextModelTrain.apply(
@@ -528,12 +532,15 @@ def multi_scale_generating(pc, anchor, hyper, feat, grid_offsets, grid_scaling, 
     # one host read-back (the reference: several .item()); the mask count of the size report rides on it
     pos_num = None
     if "sums_host" in info:
-        s = info["sums_host"]
-    elif return_sum_bits:
-        vals = torch.cat([sums, binary_grid_masks.sum(dtype=torch.float64).view(1)]).tolist()
-        s, pos_num = vals[:-1], vals[-1]
+        s, rate = info["sums_host"], info["rate"]
     else:
-        s = sums.tolist()
+        extra = ([] if rate is None else [rate]) + ([binary_grid_masks.sum(dtype=torch.float64).view(1)] if return_sum_bits else [])
+        vals = torch.cat([sums] + extra).tolist() if extra else sums.tolist()
+        s = vals[:sums.numel()]
+        tail = vals[sums.numel():]
+        rate = 1.0 if rate is None else tail.pop(0) / rate_den
+        if return_sum_bits:
+            pos_num = tail.pop(0)
     if info.get("err") is not None and s[15] != 0.0:   # the int32 flag aliases the low word of slot 15
         raise _lib.CgsError("cgs_context_level_umma_forward: a tensor-core completion barrier timed out")
     bit_feat, bit_scaling, bit_offsets = (sum(s[4 * i + c] for i in range(3)) for c in range(3))
