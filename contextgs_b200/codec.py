@@ -42,6 +42,7 @@ PARAM_LD = 176
 # as the 1.2 M-row level).  Levels therefore halve their chunk rows until they have MIN_FEAT_CHUNKS feat chunks (or reach
 # MIN_CHUNK_ROWS); the rows actually used travel with the level (`chunk_rows` of its entry, `meta.b`).  A chunk costs 3
 # bytes of side information (16-bit length + the coder's single termination byte).
+STREAM_VERSION = 2              # 2: one termination byte per chunk, no leading zero, per-level chunk rows, tabulated normal CDF
 MIN_FEAT_CHUNKS = 100_000
 MIN_CHUNK_ROWS = 2
 
@@ -311,7 +312,7 @@ def encode_model(pc, chunk_rows=CHUNK_ROWS, rank=0, world=1, estimate_bits=True,
             entry.streams[name] = SimpleNamespace(bytes=packed[b0:ends[attr]], lens=lens[c0:c0 + counts[attr]],
                                                   minmax=minmax[2 * attr:2 * attr + 2])
             b0, c0 = ends[attr], c0 + counts[attr]
-    meta = dict(version=1, N_total=int(pc._anchor.shape[0]), N=N, chunk_rows=chunk_rows, voxel_size=float(pc.voxel_size),
+    meta = dict(version=STREAM_VERSION, N_total=int(pc._anchor.shape[0]), N=N, chunk_rows=chunk_rows, voxel_size=float(pc.voxel_size),
                 level_scale=[float(s_) for s_ in pc.level_scale], x_bound_min=pc.x_bound_min.detach().cpu(),
                 x_bound_max=pc.x_bound_max.detach().cpu(), prob_masks=p1, hyper_min=hmin, hyper_max=hmax,
                 means=means, N_levels=n_levels_full, world=world)
@@ -342,6 +343,9 @@ def decode_model(pc, meta, anchor_q, mask_bytes, mask_lens, hyper_bytes, hyper_l
     world > 1: `levels` are the streams rank `rank` encoded; only that shard's rows of feat / scaling / offsets are
     filled (the rest stays zero), so the SUM over the ranks (one all-reduce) is the decoded model."""
     L = _lib.lib()
+    if meta.get("version") != STREAM_VERSION:
+        raise _lib.CgsError(f"bitstream version {meta.get('version')} cannot be decoded by this library (expects "
+                            f"{STREAM_VERSION}): the coder's termination, chunking and CDF changed between versions")
     dev = pc.latent_codec.quantiles.device
     N, K, chunk_rows = meta["N"], pc.n_offsets, meta["chunk_rows"]
     pc.x_bound_min, pc.x_bound_max = meta["x_bound_min"].to(dev), meta["x_bound_max"].to(dev)
