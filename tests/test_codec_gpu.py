@@ -54,6 +54,18 @@ def test_encode_decode_round_trip_is_bit_exact(N, chunk, adaptive):
     assert float(out["feat"].abs().max()) > 0 and float(out["offsets"].abs().max()) > 0
 
 
+def test_decoder_rejects_streams_of_another_format_version():
+    from contextgs_b200 import _lib
+    pc = _model(300)
+    enc = codec.encode_model(pc, estimate_bits=False)
+    assert enc.meta["version"] == codec.STREAM_VERSION and enc.estimated_bits is None
+    fresh = GaussianModel(device="cuda")
+    fresh.load_state_dict({k: v for k, v in pc.state_dict().items() if not k.startswith("_")}, strict=False)
+    with pytest.raises(_lib.CgsError, match="bitstream version"):
+        codec.decode_model(fresh, dict(enc.meta, version=1), enc.anchor_q, enc.mask_bytes, enc.mask_lens, enc.hyper_bytes,
+                           enc.hyper_lens, enc.levels)
+
+
 def test_quantised_values_equal_the_scoring_pass_and_sizes_match_estimates():
     pc = _model(6000)
     enc = codec.encode_model(pc)
