@@ -505,7 +505,7 @@ def main():
         line["dp_training"] = {k: line["extras"][k] for k in list(line["extras"]) if "dp_allreduce" in k or k == "grad_bucket_mb"}
         line["dp_training"]["note"] = ("iterations/s summed over the ranks: forward + backward of one camera per rank + ONE NCCL "
                                        "all-reduce of the flat fp32 gradient bucket per step (BASELINE configs[4] shape of work "
-                                       "at the bench's 1.5 M anchors)")
+                                       f"at {args.anchors} anchors; `--config 4` selects that config's 2 M)")
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
