@@ -98,14 +98,24 @@ struct Encoder {
 };
 
 // Decoder.  The chunk's bytes are read through 32-bit words (the aligned word holding the current byte and the next one,
-// fetched a word ahead of its use): one global load per four bytes, off the coder's critical path.  Only words that hold
-// at least one byte of the chunk are touched; bytes past the chunk read as zero.
+// fetched a word ahead of its use): one global load per four bytes, off the coder's critical path.  No byte past the end
+// of the chunk is touched (the word holding its last bytes is assembled from them); bytes past the chunk read as zero.
 struct Decoder {
     const uint32_t *words;   // aligned word that holds byte 0 of the chunk
     uint32_t bpos, end;      // byte position / end of the chunk, both counted from words[0]
     uint32_t cur, nxt;       // words[bpos / 4] and words[bpos / 4 + 1]
     uint32_t code, range;
-    __device__ __forceinline__ uint32_t fetch(uint32_t w) const { return 4u * w < end ? __ldg(words + w) : 0u; }
+    __device__ __forceinline__ uint32_t fetch(uint32_t w) const
+    {
+        const uint32_t lo = 4u * w;
+        if (lo + 4u <= end) return __ldg(words + w);
+        if (lo >= end) return 0u;
+        // the word that holds the chunk's last bytes: the byte string may END inside it, so only its own bytes are read
+        const uint8_t *p = reinterpret_cast<const uint8_t *>(words + w);
+        uint32_t v = 0;
+        for (uint32_t i = 0; lo + i < end; ++i) v |= (uint32_t)p[i] << (8u * i);
+        return v;
+    }
     __device__ __forceinline__ uint32_t next()
     {
         const uint32_t b = bpos < end ? (cur >> (8u * (bpos & 3u))) & 0xffu : 0u;
