@@ -410,7 +410,8 @@ class _ContextModelTrain(torch.autograd.Function):
         d_w = [torch.zeros_like(w) for w in w_bwd]
         d_eb = torch.zeros_like(eb_packed)
         ticket = torch.zeros(4, dtype=torch.int32, device=dev)
-        g_ptr = None if g_bpp is None else _lib.ptr(g_bpp.contiguous().float())
+        g_bpp_c = None if g_bpp is None else g_bpp.contiguous().float()   # named: must outlive the launches below
+        g_ptr = _lib.ptr(g_bpp_c)
         stream = _lib.stream_ptr()
         err_flag = None
         for li in reversed(range(len(plan.levels))):       # fine -> coarse

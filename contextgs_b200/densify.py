@@ -158,9 +158,11 @@ class DensifyMixin:
         new_hyper = torch.empty((M, H), device=dev)
         status = torch.empty(5, dtype=torch.int32, device=dev)
         ws = torch.empty((L.cgs_anchor_growing_workspace_bytes(N, K, M),), dtype=torch.uint8, device=dev)
+        offset, feat = self._offset.detach().contiguous(), self._anchor_feat.detach().contiguous()   # named: outlive the launch
+        hyper = self._hyper_latent.detach().contiguous()
         _lib.check(L.cgs_anchor_growing(
-            _lib.ptr(anchor_q), _lib.ptr(self._offset.detach().contiguous()), _lib.ptr(scaling), scaling.shape[1],
-            _lib.ptr(self._anchor_feat.detach().contiguous()), self.feat_dim, _lib.ptr(self._hyper_latent.detach().contiguous()),
+            _lib.ptr(anchor_q), _lib.ptr(offset), _lib.ptr(scaling), scaling.shape[1],
+            _lib.ptr(feat), self.feat_dim, _lib.ptr(hyper),
             H, _lib.ptr(cand), N, K, float(cur_size), M, _lib.ptr(new_anchor), _lib.ptr(new_feat), _lib.ptr(new_hyper), M,
             _lib.ptr(status), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "cgs_anchor_growing")
         n_new, bad_range, _, _, overflow = status.tolist()

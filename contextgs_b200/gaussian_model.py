@@ -82,8 +82,9 @@ class EntropyBottleneck(nn.Module):
         if training and noise is None:
             noise = torch.empty_like(x).uniform_(-0.5, 0.5)
         out, lik = torch.empty_like(x), torch.empty_like(x)
+        noise = noise.contiguous() if training else None   # named: a copy made here must outlive the launch
         _lib.check(_lib.lib().cgs_eb_forward(
-            _lib.ptr(self.packed()), C, _lib.ptr(x), _lib.ptr(noise.contiguous()) if training else None, N,
+            _lib.ptr(self.packed()), C, _lib.ptr(x), _lib.ptr(noise), N,
             _lib.ptr(out), _lib.ptr(lik), _lib.ptr(choose), _lib.ptr(bit_sum), _lib.stream_ptr()), "cgs_eb_forward")
         return out, lik
 

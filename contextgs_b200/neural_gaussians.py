@@ -200,10 +200,13 @@ def generate_raw(pc, camera_center, anchor, feat, grid_offsets, grid_scaling, bi
         ws = torch.empty((L.cgs_neural_gaussians_umma_workspace_bytes(Nv),), dtype=torch.uint8, device=dev)
         from .rasterizer import _host_floats
         campos = (ctypes.c_float * 3)(*_host_floats(camera_center, 3))
+        # named, so that a copy made by .contiguous() outlives the launch (a pointer taken from a temporary dangles)
+        anchor, feat, grid_offsets = anchor.contiguous(), feat.contiguous(), grid_offsets.contiguous()
+        grid_scaling, binary_grid_masks = grid_scaling.contiguous(), binary_grid_masks.contiguous()
         _lib.check(L.cgs_neural_gaussians_umma_forward_dev(
             _lib.ptr(pack_decoder_weights_umma(pc)), _lib.ptr(vis_idx), Nv, _lib.ptr(nv_dev), cap,
-            _lib.ptr(anchor.contiguous()), _lib.ptr(feat.contiguous()), _lib.ptr(grid_offsets.contiguous()),
-            _lib.ptr(grid_scaling.contiguous()), _lib.ptr(binary_grid_masks.contiguous()), campos, _lib.ptr(out["xyz"]),
+            _lib.ptr(anchor), _lib.ptr(feat), _lib.ptr(grid_offsets),
+            _lib.ptr(grid_scaling), _lib.ptr(binary_grid_masks), campos, _lib.ptr(out["xyz"]),
             _lib.ptr(out["color"]), _lib.ptr(out["opacity"]), _lib.ptr(out["scaling"]), _lib.ptr(out["rot"]), None, None,
             _lib.ptr(out["count"]), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "cgs_neural_gaussians_umma_forward_dev")
         out["n_vis"] = Nv
@@ -224,6 +227,8 @@ def generate_raw(pc, camera_center, anchor, feat, grid_offsets, grid_scaling, bi
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     from .rasterizer import _host_floats
     campos = (ctypes.c_float * 3)(*_host_floats(camera_center, 3))
+    anchor, feat, grid_offsets = anchor.contiguous(), feat.contiguous(), grid_offsets.contiguous()   # (named: see above)
+    grid_scaling, binary_grid_masks = grid_scaling.contiguous(), binary_grid_masks.contiguous()
     if save:
         # training mode with the tcgen05 backward: the forward leaves its activations behind (1.3 kB / visible anchor)
         if impl != "umma":
@@ -234,8 +239,8 @@ def generate_raw(pc, camera_center, anchor, feat, grid_offsets, grid_scaling, bi
                   pre2=torch.empty((max(Nv, 1), 144), dtype=f32, device=dev),
                   rowpos=torch.empty((max(Nv, 1), 2), dtype=i32, device=dev), tilebase=torch.empty((tiles,), dtype=i32, device=dev))
         _lib.check(L.cgs_neural_gaussians_umma_forward_train(
-            _lib.ptr(packed), _lib.ptr(vis_idx), Nv, _lib.ptr(anchor.contiguous()), _lib.ptr(feat.contiguous()),
-            _lib.ptr(grid_offsets.contiguous()), _lib.ptr(grid_scaling.contiguous()), _lib.ptr(binary_grid_masks.contiguous()),
+            _lib.ptr(packed), _lib.ptr(vis_idx), Nv, _lib.ptr(anchor), _lib.ptr(feat),
+            _lib.ptr(grid_offsets), _lib.ptr(grid_scaling), _lib.ptr(binary_grid_masks),
             campos, _lib.ptr(out["xyz"]), _lib.ptr(out["color"]), _lib.ptr(out["opacity"]), _lib.ptr(out["scaling"]),
             _lib.ptr(out["rot"]), _lib.ptr(out["neural_opacity"]), _lib.ptr(out["mask"]), _lib.ptr(out["count"]),
             _lib.ptr(sv["h"]), _lib.ptr(sv["hmask"]), _lib.ptr(sv["pre2"]), _lib.ptr(sv["rowpos"]), _lib.ptr(sv["tilebase"]),
@@ -244,9 +249,9 @@ def generate_raw(pc, camera_center, anchor, feat, grid_offsets, grid_scaling, bi
         out["save"] = sv
         return out
     _lib.check(fn(
-        _lib.ptr(packed), _lib.ptr(vis_idx), Nv, _lib.ptr(anchor.contiguous()),
-        _lib.ptr(feat.contiguous()), _lib.ptr(grid_offsets.contiguous()), _lib.ptr(grid_scaling.contiguous()),
-        _lib.ptr(binary_grid_masks.contiguous()), campos, _lib.ptr(out["xyz"]), _lib.ptr(out["color"]),
+        _lib.ptr(packed), _lib.ptr(vis_idx), Nv, _lib.ptr(anchor),
+        _lib.ptr(feat), _lib.ptr(grid_offsets), _lib.ptr(grid_scaling),
+        _lib.ptr(binary_grid_masks), campos, _lib.ptr(out["xyz"]), _lib.ptr(out["color"]),
         _lib.ptr(out["opacity"]), _lib.ptr(out["scaling"]), _lib.ptr(out["rot"]), _lib.ptr(out["neural_opacity"]),
         _lib.ptr(out["mask"]), _lib.ptr(out["count"]), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
         "cgs_neural_gaussians_forward")
@@ -356,8 +361,9 @@ class _NeuralGaussians(torch.autograd.Function):
             _lib.deferred_error_check(err, "cgs_neural_gaussians_backward_umma: a tensor-core completion barrier timed out")
         elif P > 0 and n_vis > 0:
             ws = torch.empty((L.cgs_neural_gaussians_backward_workspace_bytes(n_vis),), dtype=torch.uint8, device=dev)
+            w_t = pack_decoder_weights_transposed(pc)   # named: not cached, must outlive the launch
             _lib.check(L.cgs_neural_gaussians_backward(
-                _lib.ptr(pack_decoder_weights(pc)), _lib.ptr(pack_decoder_weights_transposed(pc)), _lib.ptr(vis_idx),
+                _lib.ptr(pack_decoder_weights(pc)), _lib.ptr(w_t), _lib.ptr(vis_idx),
                 n_vis, _lib.ptr(a), _lib.ptr(f), _lib.ptr(o), _lib.ptr(sc), _lib.ptr(m), campos, _lib.ptr(keep),
                 _lib.ptr(g_xyz), _lib.ptr(g_color), _lib.ptr(g_opacity), _lib.ptr(g_scaling), _lib.ptr(g_rot),
                 _lib.ptr(d_a), _lib.ptr(d_f), _lib.ptr(d_o), _lib.ptr(d_sc), _lib.ptr(d_m), _lib.ptr(d_w), _lib.ptr(ws),
