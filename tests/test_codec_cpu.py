@@ -53,3 +53,15 @@ def test_small_levels_get_short_chunks():
     assert codec.level_chunk_rows(59_847, 8) == [codec.MIN_CHUNK_ROWS * m for m in mult]
     assert codec.level_chunk_rows(59_847, 8, adaptive=False) == [8 * m for m in mult]
     assert codec.level_chunk_rows(10, 1000) == [125 * m for m in mult]            # stops when the row count turns odd
+
+
+def test_mask_table_is_the_same_from_a_tensor_and_from_the_stored_float():
+    """The encoder builds the Bernoulli table from the fp32 device scalar, the decoder from the python float stored in the
+    metadata: the two routes must give identical 16-bit frequencies for every probability."""
+    from contextgs_b200 import codec
+    g = torch.Generator().manual_seed(3)
+    for p in torch.rand(200, generator=g).tolist() + [0.0, 1.0, 1e-12, 1 - 1e-7]:
+        t = torch.tensor(p, dtype=torch.float32)
+        a, b = codec.mask_table(t), codec.mask_table(float(t))
+        assert torch.equal(a, b), p
+        assert a[0, 0] == 0 and a[0, 2] == 65536 and 0 < a[0, 1] < 65536
